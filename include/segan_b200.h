@@ -1,0 +1,243 @@
+/*
+ * segan_b200.h -- C ABI of libsegan_b200.so: the B200 (sm_100a) kernels underneath the
+ * santi-pdp/segan_pytorch Python API (Generator / Discriminator / SEGAN train step).
+ *
+ * The reference has no FFI of its own (it is pure Python over torch ops): every
+ * entry point below names the reference call site (file:line under /root/reference) whose
+ * library dispatch it replaces.  Conventions:
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless noted
+ *   - the caller owns all memory (outputs and workspaces included); nothing is retained
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden syncs
+ *   - return 0 on success, <0 on error; sg_last_error() gives the thread-local message
+ *   - no C++ exceptions cross the boundary
+ *
+ * HBM layout ("NLC rows"): an activation of a layer with C channels and L positions is stored
+ * time-major, channels innermost: [B][H + R + H][Cr] 16-bit, where a "row" groups `g`
+ * consecutive positions (g = 4 for the input of a stride-4 conv, else 1), R = L / g rows,
+ * Cr = g*C, and H explicit halo rows on each side (H = 4 rows = 16 positions for reflect-padded
+ * conv inputs, 0 otherwise).  [B][L][C] and [B][L/4][4C] are the same bytes, which is what turns
+ * the K=31 / stride-4 (transposed) convolutions into stride-1, 9-tap "tap-GEMMs" (DESIGN.md).
+ * Waveform ends (C = 1) are fp32 [B][L], identical to the reference's NCL tensors.
+ */
+#ifndef SEGAN_B200_H
+#define SEGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 1
+
+/* status codes */
+#define SG_OK 0
+#define SG_ERR_INVALID -1
+#define SG_ERR_LAUNCH -2
+#define SG_ERR_UNSUPPORTED -3
+
+/* element types */
+#define SG_F32 0
+#define SG_F16 1
+#define SG_BF16 2
+
+/* activation kinds */
+#define SG_ACT_NONE 0
+#define SG_ACT_PRELU 1
+#define SG_ACT_TANH 2
+
+/* tap-GEMM back ends */
+#define SG_BACKEND_FFMA 0    /* CUDA-core fp32 reference implementation (validation / fallback) */
+#define SG_BACKEND_TCGEN05 1 /* TMA + tcgen05.mma + TMEM (the product path) */
+
+int sg_abi_version(void);
+const char* sg_last_error(void);
+/* 1 if the loaded device is sm_100 class and the tcgen05 kernels can run */
+int sg_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-GEMM, forward form ("F"):
+ *     out[b, m, n] = bias[n % bias_mod] + sum_{d = d_lo..d_hi} sum_{kc valid for d}
+ *                        A[b, m + d, kc] * Wp[d + 4][n][kc]          m in [m_lo, m_hi), n in [n_lo, n_hi)
+ * A is the channel-concatenation of up to two NLC-row tensors (a0 | a1); rows outside
+ * [-a_halo, a_rows + a_halo) read as zero.  Wp is the packed weight [9][nc][kc].
+ * Replaces: nn.Conv1d on a reflect-padded input (segan/models/modules.py:92-99), its data
+ * gradient, nn.ConvTranspose1d (modules.py:136) and its data gradient, torch.cat of the skip
+ * connection (segan/models/generator.py:76,205), and nn.Linear fc.0 (discriminator.py:112).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sg_tapgemm_f {
+  const void* a0;     /* [B][a_halo + a_rows + a_halo][a0_c] */
+  const void* a1;     /* same geometry, a1_c channels, or NULL */
+  int32_t a0_c, a1_c; /* kc = a0_c + a1_c */
+  int32_t a_rows, a_halo;
+  int32_t a_dtype;    /* SG_F16 | SG_BF16 */
+  const void* w;      /* packed [9][nc][kc], w_dtype */
+  int32_t w_dtype;
+  int32_t kc, nc;
+  int32_t d_lo, d_hi; /* inclusive, within [-4, 4] */
+  /* per tap (index d+4): valid K range [k_lo, k_hi) and valid N range [n_lo, n_hi) in channels
+     (multiples of 64); blocks outside are structurally zero in Wp and are skipped */
+  int32_t tap_k_lo[9], tap_k_hi[9], tap_n_lo[9], tap_n_hi[9];
+  void* out;          /* [B][out_halo + out_rows + out_halo][nc] */
+  int32_t out_dtype;  /* SG_F16 | SG_BF16 | SG_F32 (F32: atomically accumulated, pre-zeroed by caller) */
+  int32_t out_rows, out_halo;
+  int32_t m_lo, m_hi; /* rows computed per batch element (may reach into the out halo) */
+  int32_t n_lo, n_hi; /* channels computed */
+  const float* bias;  /* or NULL */
+  int32_t bias_mod;   /* bias index = n % bias_mod */
+  int32_t batch;
+  int32_t ksplit;     /* >1 only with out_dtype == SG_F32 */
+  int32_t backend;    /* SG_BACKEND_* */
+} sg_tapgemm_f;
+
+int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-GEMM, weight-gradient form ("W"):
+ *     dWp[d + 4][n][kc] += sum_{b, m in [0, g_rows)} G[b, m, n] * A[b, m + d, kc]
+ * G: [B][g_rows][nc] (exact, no halo); A as above.  dWp fp32 packed [9][nc][kc], accumulated
+ * atomically (caller zeroes it).  Replaces the weight gradient of nn.Conv1d / nn.ConvTranspose1d /
+ * nn.Linear computed by autograd for model.py:299,306,320.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sg_tapgemm_w {
+  const void* g;
+  int32_t g_rows, g_dtype;
+  const void* a0;
+  const void* a1;
+  int32_t a0_c, a1_c;
+  int32_t a_rows, a_halo, a_dtype;
+  int32_t kc, nc;
+  int32_t d_lo, d_hi;
+  int32_t tap_k_lo[9], tap_k_hi[9], tap_n_lo[9], tap_n_hi[9];
+  float* dw; /* [9][nc][kc] fp32 */
+  int32_t batch;
+  int32_t ksplit; /* number of position-range splits (>=1) */
+  int32_t backend;
+} sg_tapgemm_w;
+
+int sg_tapgemm_w_run(const sg_tapgemm_w* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight packing (fp32 master [reference layout] -> 16-bit tap-GEMM operands) and gradient
+ * unpacking (fp32 packed dWp -> fp32 reference layout).  kind:
+ *   0 = Conv1d  W[cout][cin][31]      (modules.py:79)   -> Wf [9][cout][4cin]  and Wdg [9][4cin][cout]
+ *   1 = ConvTranspose1d W[cin][cout][31] (modules.py:116) -> Wt [9][4cout][cin] and Wtd [9][cin][4cout]
+ *       alpha (or NULL): per-input-channel scale for channels >= alpha_from (GSkip, generator.py:68-69)
+ *   2 = Linear W[nout][c*T + t] (discriminator.py:112) -> W1p [nout][t*C + c] and W1dg [t*C + c][nout]
+ * ------------------------------------------------------------------------------------------ */
+int sg_pack_weights(int kind, const float* w, int c_out, int c_in, int t_len,
+                    const float* alpha, int alpha_from,
+                    void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad, void* stream);
+/* dw (reference layout) = unpack(dwp); for kind 1 with alpha: dw[ci>=alpha_from] = alpha*dWeff and
+ * dalpha[c] = sum_{co,k} dWeff[ci,co,k] * w[ci,co,k].  accumulate: 0 = overwrite, 1 = add */
+int sg_unpack_wgrad(int kind, const float* dwp, int c_out, int c_in, int t_len,
+                    const float* w, const float* alpha, int alpha_from,
+                    float* dw, float* dalpha, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Waveform-end layers (Cin or Cout in {1,2}: HBM-bound, CUDA cores).
+ * ------------------------------------------------------------------------------------------ */
+/* First encoder layer (G: 1 ch, D: 2 ch = candidate | reference; model.py:173-175 cat is never
+ * materialised).  x0/x1: fp32 [B][L]; roll: signed circular shift applied before the reflect
+ * pad (discriminator.py:160-172; 0 for G).  a_out: [B][L/4][cout] fp16 raw pre-activation
+ * (+bias).  If h_out != NULL also writes PReLU(a) into the padded consumer-ready buffer
+ * [B][4 + L/16 + 4][4*cout] with the reflect halo (G path, modules.py:98-101). */
+int sg_wave_conv_fwd(const float* x0, const float* x1, int cin, int batch, int L, int roll,
+                     const float* w, const float* bias, int cout,
+                     void* a_out, const float* prelu, void* h_out, void* stream);
+/* dW[cout][cin][31], dbias[cout] (or NULL) += over batch; g_a: [B][L/4][cout] bf16 */
+int sg_wave_conv_wgrad(const float* x0, const float* x1, int cin, int batch, int L, int roll,
+                       const void* g_a, int cout, float* dw, float* dbias, void* stream);
+/* data gradient w.r.t. channel 0 of the (rolled, padded) input, un-rolled and halo-folded:
+ * gx0[b][l] (=|+=) sum ...   Used in the G step (model.py:315-320). */
+int sg_wave_conv_dgrad(const void* g_a, int batch, int L, int roll, const float* w, int cin,
+                       int cout, float* gx0, int accumulate, void* stream);
+/* Last decoder layer: ConvTranspose1d(cin -> 1) + bias + tanh (modules.py:135-141 with
+ * act='Tanh').  x0|x1: [B][Lin][c0|c1] fp16 (decoder act | skip pre-activation, alpha folded
+ * into w_eff by the caller: w_eff[ci][31]).  y: fp32 [B][4*Lin]. */
+int sg_wave_deconv_fwd(const void* x0, int c0, const void* x1, int c1, int batch, int Lin,
+                       const float* w_eff, const float* bias, float* y, void* stream);
+/* backward of the above given gy [B][4Lin] fp32 and y: gpre = gy*(1-y^2);
+ * gx: [B][Lin][c0+c1] bf16 (w.r.t. cat(x0,x1) i.e. already alpha-scaled for the skip half),
+ * dw_eff[ci][31], dbias[1] accumulated.  gpre_ws: fp32 workspace [B][4*Lin]. */
+int sg_wave_deconv_bwd(const void* x0, int c0, const void* x1, int c1, int batch, int Lin,
+                       const float* w_eff, const float* gy, const float* y, float* gpre_ws,
+                       void* gx, float* dw_eff, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise / reduction glue (HBM-bound).
+ * ------------------------------------------------------------------------------------------ */
+/* per-channel sum / sum of squares of a [rows_total][C] 16-bit tensor into double stats[2][C]
+ * (accumulated; caller zeroes).  BatchNorm1d batch statistics, modules.py:11,100. */
+int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream);
+/* stats -> scale/shift (fp32 [2][C]: scale = gamma*invstd, shift = beta - mean*scale), saved
+ * mean/invstd (fp32 [2][C]) and running-stat update (momentum 0.1, unbiased var, eps 1e-5). */
+int sg_bn_finalize(const double* stats, int64_t count, int C, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var,
+                   float* scale_shift, float* mean_invstd, void* stream);
+/* h = act(a*scale + shift) written to [B][oh + Lout_rows + oh][g*C] with circular roll and
+ * reflect halo (the consumer's view).  scale_shift may be NULL.  a: [B][L][C] exact.
+ * out_halo_pos = halo in positions (0 or 16).  act: SG_ACT_NONE|SG_ACT_PRELU. */
+int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
+               const float* slope, int act, int roll, int out_halo_pos, void* h, void* stream);
+/* backward of sg_act_fwd (+ optional BatchNorm backward).  g_h: gradient w.r.t. the consumer
+ * view (bf16, same geometry as h incl. halo & roll) ; g_add: optional extra gradient w.r.t. the
+ * activation output in exact geometry (skip connection), may be NULL.
+ * pass 1 (sg_act_bwd_reduce): red[0][C] = sum g_y*[y<0]*y (d slope), red[1][C] = sum g_pre (d beta),
+ *   red[2][C] = sum g_pre * ahat (d gamma), where y = a*scale+shift, g_pre = g_y*act'(y).
+ *   Without BatchNorm g_a = g_pre is final and pass 1 writes it when g_a_out_or_null != NULL.
+ * pass 2 (sg_act_bwd_apply): g_a (bf16 exact) = no BN: g_pre ;
+ *   BN: scale * (g_pre - red1/N - ahat*red2/N). */
+int sg_act_bwd_reduce(const void* g_h, int in_halo_pos, int roll, const void* g_add,
+                      const void* a, int dtype, int batch, int L, int C,
+                      const float* scale_shift, const float* mean_invstd, const float* slope,
+                      int act, double* red, void* g_a_out_or_null, void* stream);
+int sg_act_bwd_apply(const void* g_h, int in_halo_pos, int roll, const void* g_add,
+                     const void* a, int dtype, int batch, int L, int C,
+                     const float* scale_shift, const float* mean_invstd, const float* slope,
+                     int act, const double* red, int use_bn, void* g_a, void* stream);
+/* fp32 NCL [B][C][L] <-> 16-bit NLC [B][L][C] (z input, generator.py:195-205; ret_hid outputs) */
+int sg_ncl_to_nlc(const float* src, int batch, int C, int L, void* dst, int dtype, void* stream);
+int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L, float* dst, void* stream);
+/* per-channel column sums of a 16-bit [rows][C] tensor into fp32 out[C % mod] (bias gradients) */
+int sg_colsum(const void* a, int dtype, int64_t rows, int C, int mod, float* out, int accumulate,
+              double* tmp /* [C] workspace */, void* stream);
+
+/* D head after fc.0 (discriminator.py:111-117): z1 = fc0_acc + b0 ; h1 = PReLU(z1) ; z2 = W2 h1 + b2 ;
+ * h2 = PReLU(z2) ; logit = W4 h2 + b4.  Saves z1,z2 (fp32) for backward. */
+int sg_fc_tail_fwd(const float* fc0_acc, const float* b0, const float* s1, const float* w2,
+                   const float* b2, const float* s3, const float* w4, const float* b4, int batch,
+                   float* z1, float* z2, float* logit, void* stream);
+/* loss = mean((logit-target)^2)*weight ; g_logit = 2(logit-target)/B*weight ; backward through the
+ * head: g_z1 (bf16 [B][256] for the fc.0 tap-GEMMs) and (if grads != NULL) parameter gradients
+ * accumulated into: g_b0[256], g_s1[256], g_w2[128*256], g_b2[128], g_s3[128], g_w4[128], g_b4[1]. */
+int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit, float target, float weight,
+                   const float* s1, const float* w2, const float* s3, const float* w4, int batch,
+                   float* loss_out, void* g_z1_bf16, float* ws /* fp32 [B*(1+128+256)] */,
+                   float* g_b0, float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4,
+                   float* g_b4, void* stream);
+/* G regression loss (model.py:318): loss = w * mean|y - clean| ; gy (+)= w*sign(y-clean)/(B*L) */
+int sg_l1_loss_bwd(const float* y, const float* clean, int64_t n, float weight, float* loss_out,
+                   float* gy, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimisers on flat fp32 buffers (torch.optim.RMSprop / Adam as used at model.py:221-225).
+ * grad_scale multiplies the gradient first (1/world_size after an all-reduce SUM).
+ * ------------------------------------------------------------------------------------------ */
+int sg_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr,
+                    float alpha, float eps, float grad_scale, void* stream);
+int sg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Inference tail (clean.py:72 -> model.py:156 -> se_dataset.py:119-126): de-emphasis
+ * x[n] = coef*x[n-1] + y[n] per utterance as a parallel scan; and the inverse used on input.
+ * ------------------------------------------------------------------------------------------ */
+int sg_deemphasis(const float* y, int64_t n, float coef, float* x, void* stream);
+int sg_preemphasis(const float* x, int64_t n, float coef, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGAN_B200_H */

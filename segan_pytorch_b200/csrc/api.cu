@@ -1,0 +1,78 @@
+// C-ABI plumbing: error slot, device probe, tap-GEMM argument validation + back-end dispatch.
+#include "common.cuh"
+#include <string.h>
+
+namespace sg {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int tapgemm_f_ffma_launch(const sg_tapgemm_f* q, cudaStream_t st);
+int tapgemm_w_ffma_launch(const sg_tapgemm_w* q, cudaStream_t st);
+int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st);
+int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st);
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" int sg_abi_version(void) { return SG_ABI_VERSION; }
+extern "C" const char* sg_last_error(void) { return g_err; }
+
+extern "C" int sg_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+static int check_taps(const int32_t* k_lo, const int32_t* k_hi, const int32_t* n_lo, const int32_t* n_hi, int d_lo,
+                      int d_hi, int kc, int nc) {
+  for (int d = d_lo; d <= d_hi; ++d) {
+    const int i = d + 4;
+    if (k_lo[i] < 0 || k_hi[i] > kc || k_lo[i] % 64 || k_hi[i] % 64 || k_lo[i] >= k_hi[i]) return 0;
+    if (n_lo[i] < 0 || n_hi[i] > nc || n_lo[i] % 64 || n_hi[i] % 64 || n_lo[i] >= n_hi[i]) return 0;
+  }
+  return 1;
+}
+
+extern "C" int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream) {
+  SG_CHECK_ARG(p != nullptr);
+  SG_CHECK_ARG(p->a0 && p->w && p->out);
+  SG_CHECK_ARG(p->a0_c > 0 && p->a0_c % 64 == 0 && p->a1_c % 64 == 0 && p->kc == p->a0_c + p->a1_c);
+  SG_CHECK_ARG((p->a1 != nullptr) == (p->a1_c > 0));
+  SG_CHECK_ARG(p->nc % 64 == 0 && p->n_lo % 64 == 0 && p->n_hi % 64 == 0 && p->n_lo >= 0 && p->n_hi <= p->nc &&
+               p->n_lo < p->n_hi);
+  SG_CHECK_ARG(p->d_lo >= -4 && p->d_hi <= 4 && p->d_lo <= p->d_hi);
+  SG_CHECK_ARG(check_taps(p->tap_k_lo, p->tap_k_hi, p->tap_n_lo, p->tap_n_hi, p->d_lo, p->d_hi, p->kc, p->nc));
+  SG_CHECK_ARG(p->a_dtype == SG_F16 || p->a_dtype == SG_BF16);
+  SG_CHECK_ARG(p->w_dtype == SG_F16 || p->w_dtype == SG_BF16);
+  SG_CHECK_ARG(p->out_dtype == SG_F16 || p->out_dtype == SG_BF16 || p->out_dtype == SG_F32);
+  SG_CHECK_ARG(p->ksplit <= 1 || p->out_dtype == SG_F32);
+  SG_CHECK_ARG(p->m_lo >= -p->out_halo && p->m_hi <= p->out_rows + p->out_halo && p->m_lo < p->m_hi);
+  SG_CHECK_ARG(p->batch > 0 && p->a_rows > 0 && p->a_halo >= 0);
+  if (p->backend == SG_BACKEND_TCGEN05) return tapgemm_f_tc_launch(p, (cudaStream_t)stream);
+  if (p->backend == SG_BACKEND_FFMA) return tapgemm_f_ffma_launch(p, (cudaStream_t)stream);
+  set_error("unknown backend %d", p->backend);
+  return SG_ERR_UNSUPPORTED;
+}
+
+extern "C" int sg_tapgemm_w_run(const sg_tapgemm_w* p, void* stream) {
+  SG_CHECK_ARG(p != nullptr);
+  SG_CHECK_ARG(p->g && p->a0 && p->dw);
+  SG_CHECK_ARG(p->a0_c > 0 && p->a0_c % 64 == 0 && p->a1_c % 64 == 0 && p->kc == p->a0_c + p->a1_c);
+  SG_CHECK_ARG((p->a1 != nullptr) == (p->a1_c > 0));
+  SG_CHECK_ARG(p->nc % 128 == 0);
+  SG_CHECK_ARG(p->d_lo >= -4 && p->d_hi <= 4 && p->d_lo <= p->d_hi);
+  SG_CHECK_ARG(check_taps(p->tap_k_lo, p->tap_k_hi, p->tap_n_lo, p->tap_n_hi, p->d_lo, p->d_hi, p->kc, p->nc));
+  SG_CHECK_ARG(p->g_dtype == SG_F16 || p->g_dtype == SG_BF16);
+  SG_CHECK_ARG(p->a_dtype == SG_F16 || p->a_dtype == SG_BF16);
+  SG_CHECK_ARG(p->batch > 0 && p->g_rows > 0 && (p->g_rows >= 64 ? p->g_rows % 64 == 0 : 64 % p->g_rows == 0));
+  if (p->backend == SG_BACKEND_TCGEN05) return tapgemm_w_tc_launch(p, (cudaStream_t)stream);
+  if (p->backend == SG_BACKEND_FFMA) return tapgemm_w_ffma_launch(p, (cudaStream_t)stream);
+  set_error("unknown backend %d", p->backend);
+  return SG_ERR_UNSUPPORTED;
+}

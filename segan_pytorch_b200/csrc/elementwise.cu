@@ -1,0 +1,559 @@
+// HBM-bound glue between the tap-GEMMs: BatchNorm statistics / finalize, the fused
+// "BN-apply + PReLU + circular phase shift + reflect halo" producer of conv inputs and its
+// backward, layout converters, the discriminator FC tail, and the loss tails.
+// All 16-bit tensors are NLC ([positions][C], C innermost); threads own 8 consecutive channels
+// (one 16-byte vector) so every access is a coalesced 128-bit transaction.
+#include "common.cuh"
+
+namespace sg {
+
+__device__ __forceinline__ V8 ldv8(const void* p, int64_t elem_off) {
+  return *reinterpret_cast<const V8*>(reinterpret_cast<const uint16_t*>(p) + elem_off);
+}
+__device__ __forceinline__ void stv8(void* p, int64_t elem_off, const V8& v) {
+  *reinterpret_cast<V8*>(reinterpret_cast<uint16_t*>(p) + elem_off) = v;
+}
+
+// block-level reduction of per-thread 8-channel partials: threads with the same channel group
+// (tid % cgs) are summed, then one double atomic per channel.
+template <int NS>
+__device__ __forceinline__ void block_reduce_channels(float (&part)[NS][8], int cgs, int C, double* out,
+                                                      float* smem /* [256][8] */) {
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  for (int s = 0; s < NS; ++s) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) smem[tid * 8 + j] = part[s][j];
+    __syncthreads();
+    if (tid < cgs) {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int t = tid; t < blockDim.x; t += cgs)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += (double)smem[t * 8 + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(out + (int64_t)s * C + cg * 8 + j, acc[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const void* __restrict__ a, int dtype, int64_t rows, int C, double* __restrict__ stats) {
+  __shared__ float red[256 * 8];
+  const int cgs = C / 8;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int rpb = 256 / cgs;             // rows per block iteration
+  float part[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { part[0][j] = 0.f; part[1][j] = 0.f; }
+  for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
+    const V8 v = ldv8(a, r * C + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = up16(v.v[j], dtype);
+      part[0][j] += x;
+      part[1][j] = fmaf(x, x, part[1][j]);
+    }
+  }
+  block_reduce_channels<2>(part, cgs, C, stats, red);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = stats[c] / count;
+  double var = stats[C + c] / count - mean * mean;
+  if (var < 0) var = 0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = beta[c] - (float)mean * sc;
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = invstd;
+  if (rmean) {
+    const double unbiased = count > 1 ? var * count / (count - 1.0) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// h[b][q + H][c] = act(a[b][src(q)][c] * scale + shift),  q in [-H, L + H),
+// src(q) = unroll(reflect(q))
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
+               const float* __restrict__ scale_shift, const float* __restrict__ slope, int act, int roll, int H,
+               void* __restrict__ h) {
+  const int cgs = C / 8;
+  const int Lh = L + 2 * H;
+  const int64_t total = (int64_t)batch * Lh * cgs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    const int64_t pr = i / cgs;
+    const int qh = (int)(pr % Lh);
+    const int b = (int)(pr / Lh);
+    const int src = unroll_idx(reflect_idx(qh - H, L), roll, L);
+    const V8 v = ldv8(a, ((int64_t)b * L + src) * C + cg * 8);
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      float y = up16(v.v[j], dtype);
+      if (scale_shift) y = fmaf(y, scale_shift[c], scale_shift[C + c]);
+      if (act == SG_ACT_PRELU) y = y > 0.f ? y : slope[c] * y;
+      o.v[j] = cvt16(y, dtype);
+    }
+    stv8(h, ((int64_t)b * Lh + qh) * C + cg * 8, o);
+  }
+}
+
+// gradient w.r.t. the activation output at exact position l: gathers the consumer-view
+// gradient (rolled position + its reflect-halo mirrors) and the optional skip gradient
+__device__ __forceinline__ void gather_gy(const void* g_h, int H, int roll, const void* g_add, int b, int l, int L,
+                                          int C, int cg, float (&gy)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gy[j] = 0.f;
+  if (g_h) {
+    const int Lh = L + 2 * H;
+    int q0 = l + roll;
+    if (q0 >= L) q0 -= L;
+    if (q0 < 0) q0 += L;
+    const int64_t base = (int64_t)b * Lh + H;
+    V8 v = ldv8(g_h, (base + q0) * C + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+    if (H > 0) {
+      if (q0 >= 1 && q0 <= 14) {
+        v = ldv8(g_h, (base - q0) * C + cg * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+      }
+      if (q0 >= L - 16 && q0 <= L - 2) {
+        v = ldv8(g_h, (base + 2 * (L - 1) - q0) * C + cg * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+      }
+    }
+  }
+  if (g_add) {
+    const V8 v = ldv8(g_add, ((int64_t)b * L + l) * C + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+  }
+}
+
+// MODE 0: reductions only (and, when g_a_out != null and no BN, the final g_a in the same pass)
+// MODE 1: apply (BN backward) using the reductions
+template <int MODE>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const void* __restrict__ g_h, int H, int roll, const void* __restrict__ g_add,
+               const void* __restrict__ a, int dtype, int batch, int L, int C,
+               const float* __restrict__ scale_shift, const float* __restrict__ mean_invstd,
+               const float* __restrict__ slope, int act, double* __restrict__ red, int use_bn,
+               void* __restrict__ g_a_out) {
+  __shared__ float sred[256 * 8];
+  const int cgs = C / 8;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int rpb = 256 / cgs;
+  const int64_t rows = (int64_t)batch * L;
+  float sc[8], sh[8], mu[8], is[8], sl[8], r1[8], r2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = scale_shift ? scale_shift[c] : 1.f;
+    sh[j] = scale_shift ? scale_shift[C + c] : 0.f;
+    mu[j] = mean_invstd ? mean_invstd[c] : 0.f;
+    is[j] = mean_invstd ? mean_invstd[C + c] : 1.f;
+    sl[j] = (act == SG_ACT_PRELU) ? slope[c] : 1.f;
+    if (MODE == 1) {
+      r1[j] = (float)(red[C + c] / (double)rows);
+      r2[j] = (float)(red[2 * C + c] / (double)rows);
+    }
+  }
+  float part[3][8];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[s][j] = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
+    const int b = (int)(r / L), l = (int)(r % L);
+    float gy[8];
+    gather_gy(g_h, H, roll, g_add, b, l, L, C, cg, gy);
+    const V8 av = ldv8(a, r * C + cg * 8);
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = up16(av.v[j], dtype);
+      const float y = fmaf(x, sc[j], sh[j]);
+      const float ahat = (x - mu[j]) * is[j];
+      float gpre = gy[j];
+      if (act == SG_ACT_PRELU) {
+        if (y <= 0.f) {
+          if (MODE == 0) part[0][j] = fmaf(gy[j], y, part[0][j]);
+          gpre = gy[j] * sl[j];
+        }
+      }
+      if (MODE == 0) {
+        part[1][j] += gpre;
+        part[2][j] = fmaf(gpre, ahat, part[2][j]);
+        o.v[j] = cvt16(gpre, SG_BF16);
+      } else {
+        const float ga = use_bn ? sc[j] * (gpre - r1[j] - ahat * r2[j]) : gpre;
+        o.v[j] = cvt16(ga, SG_BF16);
+      }
+    }
+    if (g_a_out) stv8(g_a_out, r * C + cg * 8, o);
+  }
+  if (MODE == 0) block_reduce_channels<3>(part, cgs, C, red, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout converters (32 x 32 smem transpose tiles)
+// ------------------------------------------------------------------------------------------
+__global__ void ncl_to_nlc_kernel(const float* __restrict__ src, int C, int L, void* __restrict__ dst, int dtype) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    tile[i][tx] = (c < C && l < L) ? src[((int64_t)b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    if (c < C && l < L) st16(dst, ((int64_t)b * L + l) * C + c, tile[tx][i], dtype);
+  }
+}
+__global__ void nlc_to_ncl_kernel(const void* __restrict__ src, int dtype, int C, int L, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    tile[i][tx] = (c < C && l < L) ? ld16(src, ((int64_t)b * L + l) * C + c, dtype) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    if (c < C && l < L) dst[((int64_t)b * C + c) * L + l] = tile[tx][i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ a, int dtype, int64_t rows, int C, double* __restrict__ tmp) {
+  __shared__ float red[256 * 8];
+  const int cgs = C / 8;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int rpb = 256 / cgs;
+  float part[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[0][j] = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
+    const V8 v = ldv8(a, r * C + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[0][j] += up16(v.v[j], dtype);
+  }
+  block_reduce_channels<1>(part, cgs, C, tmp, red);
+}
+__global__ void colsum_fold_kernel(const double* __restrict__ tmp, int C, int mod, float* __restrict__ out,
+                                   int accumulate) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= mod) return;
+  double s = 0;
+  for (int c = m; c < C; c += mod) s += tmp[c];
+  out[m] = (accumulate ? out[m] : 0.f) + (float)s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Discriminator head after fc.0 (discriminator.py:111-117)
+// ------------------------------------------------------------------------------------------
+constexpr int FC1 = 256, FC2 = 128;
+
+__global__ void __launch_bounds__(256)
+fc_tail_fwd_kernel(const float* __restrict__ fc0_acc, const float* __restrict__ b0, const float* __restrict__ s1,
+                   const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ s3,
+                   const float* __restrict__ w4, const float* __restrict__ b4, float* __restrict__ z1,
+                   float* __restrict__ z2, float* __restrict__ logit) {
+  __shared__ float h1[FC1];
+  __shared__ float h2[FC2];
+  __shared__ float wred[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  {
+    const float z = fc0_acc[(int64_t)b * FC1 + tid] + b0[tid];
+    z1[(int64_t)b * FC1 + tid] = z;
+    h1[tid] = z > 0.f ? z : s1[tid] * z;
+  }
+  __syncthreads();
+  // z2[j] = b2[j] + sum_i w2[j][i] h1[i] : one warp per 16 outputs, lanes stride the 256 inputs
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int j = warp * 16; j < warp * 16 + 16; ++j) {
+    float s = 0.f;
+    for (int i = lane; i < FC1; i += 32) s = fmaf(w2[j * FC1 + i], h1[i], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float z = s + b2[j];
+      z2[(int64_t)b * FC2 + j] = z;
+      h2[j] = z > 0.f ? z : s3[j] * z;
+    }
+  }
+  __syncthreads();
+  float s = tid < FC2 ? w4[tid] * h2[tid] : 0.f;
+  s = warp_sum(s);
+  if (lane == 0) wred[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float t = b4[0];
+    for (int i = 0; i < 8; ++i) t += wred[i];
+    logit[b] = t;
+  }
+}
+
+// per-row backward: g_z2 [B][128] and g_z1 [B][256] (fp32 workspaces) + bf16 copy of g_z1
+__global__ void __launch_bounds__(256)
+fc_tail_bwd_rows_kernel(const float* __restrict__ z1, const float* __restrict__ z2, const float* __restrict__ logit,
+                        float target, float weight, const float* __restrict__ s1, const float* __restrict__ w2,
+                        const float* __restrict__ s3, const float* __restrict__ w4, int batch,
+                        float* __restrict__ loss_out, float* __restrict__ g_logit_ws, float* __restrict__ g_z2_ws,
+                        float* __restrict__ g_z1_ws, void* __restrict__ g_z1_bf16) {
+  __shared__ float gz2[FC2];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float diff = logit[b] - target;
+  const float gl = 2.f * diff / (float)batch * weight;
+  if (tid == 0) {
+    g_logit_ws[b] = gl;
+    if (loss_out) atomicAdd(loss_out, diff * diff / (float)batch * weight);
+  }
+  if (tid < FC2) {
+    const float z = z2[(int64_t)b * FC2 + tid];
+    const float gh2 = gl * w4[tid];
+    const float g = z > 0.f ? gh2 : gh2 * s3[tid];
+    gz2[tid] = g;
+    g_z2_ws[(int64_t)b * FC2 + tid] = g;
+  }
+  __syncthreads();
+  float gh1 = 0.f;
+  for (int j = 0; j < FC2; ++j) gh1 = fmaf(gz2[j], w2[j * FC1 + tid], gh1);
+  const float z = z1[(int64_t)b * FC1 + tid];
+  const float g = z > 0.f ? gh1 : gh1 * s1[tid];
+  g_z1_ws[(int64_t)b * FC1 + tid] = g;
+  st16(g_z1_bf16, (int64_t)b * FC1 + tid, g, SG_BF16);
+}
+
+// parameter gradients of the head: one thread per output element, serial over the batch
+__global__ void fc_tail_bwd_params_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                          const float* __restrict__ g_logit, const float* __restrict__ g_z2,
+                                          const float* __restrict__ g_z1, const float* __restrict__ s1,
+                                          const float* __restrict__ s3, const float* __restrict__ w2,
+                                          const float* __restrict__ w4, int batch, float* __restrict__ g_b0,
+                                          float* __restrict__ g_s1, float* __restrict__ g_w2, float* __restrict__ g_b2,
+                                          float* __restrict__ g_s3, float* __restrict__ g_w4, float* __restrict__ g_b4) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < FC2 * FC1) {                 // g_w2[j][i] = sum_b g_z2[b][j] * h1[b][i]
+    const int j = idx / FC1, i = idx % FC1;
+    const float sl = s1[i];
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) {
+      const float z = z1[(int64_t)b * FC1 + i];
+      const float h = z > 0.f ? z : sl * z;
+      s = fmaf(g_z2[(int64_t)b * FC2 + j], h, s);
+    }
+    g_w2[idx] += s;
+    return;
+  }
+  int r = idx - FC2 * FC1;
+  if (r < FC1) {                         // g_b0, g_s1
+    float sb = 0.f, ss = 0.f;
+    const float sl = s1[r];
+    for (int b = 0; b < batch; ++b) {
+      const float g = g_z1[(int64_t)b * FC1 + r];
+      const float z = z1[(int64_t)b * FC1 + r];
+      sb += g;
+      // g_z1 = g_h1 * (z>0 ? 1 : s1)  =>  d s1 = sum g_h1 * z [z<=0]; recover g_h1 only where needed
+      if (z <= 0.f) {
+        // g_h1 = sum_j g_z2[b][j] * w2[j][r]
+        float gh = 0.f;
+        for (int j = 0; j < FC2; ++j) gh = fmaf(g_z2[(int64_t)b * FC2 + j], w2[j * FC1 + r], gh);
+        ss = fmaf(gh, z, ss);
+      }
+    }
+    (void)sl;
+    g_b0[r] += sb;
+    g_s1[r] += ss;
+    return;
+  }
+  r -= FC1;
+  if (r < FC2) {                         // g_b2, g_s3, g_w4
+    float sb = 0.f, ss = 0.f, sw = 0.f;
+    const float sl = s3[r];
+    const float w = w4[r];
+    for (int b = 0; b < batch; ++b) {
+      const float z = z2[(int64_t)b * FC2 + r];
+      const float gl = g_logit[b];
+      sb += g_z2[(int64_t)b * FC2 + r];
+      const float h = z > 0.f ? z : sl * z;
+      sw = fmaf(gl, h, sw);
+      if (z <= 0.f) ss = fmaf(gl * w, z, ss);
+    }
+    g_b2[r] += sb;
+    g_s3[r] += ss;
+    g_w4[r] += sw;
+    return;
+  }
+  r -= FC2;
+  if (r == 0) {
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) s += g_logit[b];
+    g_b4[0] += s;
+  }
+}
+
+__global__ void l1_loss_bwd_kernel(const float* __restrict__ y, const float* __restrict__ clean, int64_t n,
+                                   float weight, float* __restrict__ loss_out, float* __restrict__ gy,
+                                   int accumulate) {
+  float s = 0.f;
+  const float gscale = weight / (float)n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = y[i] - clean[i];
+    s += fabsf(d);
+    const float g = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f);
+    if (gy) gy[i] = accumulate ? gy[i] + g : g;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0 && loss_out) atomicAdd(loss_out, s * gscale);
+}
+
+static inline int ew_grid(int64_t work_items, int per_block) {
+  int64_t g = cdiv(work_items, per_block);
+  const int64_t cap = 8 * NUM_SMS;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream) {
+  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && a && stats);
+  const int rpb = 256 / (C / 8);
+  bn_stats_kernel<<<ew_grid(rows_total, rpb * 8), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_bn_finalize(const double* stats, int64_t count, int C, const float* gamma, const float* beta,
+                              float eps, float momentum, float* running_mean, float* running_var,
+                              float* scale_shift, float* mean_invstd, void* stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(stats, (double)count, C, gamma, beta, eps, momentum,
+                                                      running_mean, running_var, scale_shift, mean_invstd);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
+                          const float* slope, int act, int roll, int out_halo_pos, void* h, void* stream) {
+  SG_CHECK_ARG(C % 8 == 0 && (out_halo_pos == 0 || L >= 32));
+  SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
+  const int64_t total = (int64_t)batch * (L + 2 * out_halo_pos) * (C / 8);
+  act_fwd_kernel<<<ew_grid(total, 256 * 4), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
+                                                          out_halo_pos, h);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_act_bwd_reduce(const void* g_h, int in_halo_pos, int roll, const void* g_add, const void* a,
+                                 int dtype, int batch, int L, int C, const float* scale_shift,
+                                 const float* mean_invstd, const float* slope, int act, double* red,
+                                 void* g_a_out, void* stream) {
+  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red);
+  const int rpb = 256 / (C / 8);
+  act_bwd_kernel<0><<<ew_grid((int64_t)batch * L, rpb * 8), 256, 0, ST>>>(
+      g_h, in_halo_pos, roll, g_add, a, dtype, batch, L, C, scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_act_bwd_apply(const void* g_h, int in_halo_pos, int roll, const void* g_add, const void* a,
+                                int dtype, int batch, int L, int C, const float* scale_shift,
+                                const float* mean_invstd, const float* slope, int act, const double* red,
+                                int use_bn, void* g_a, void* stream) {
+  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red && g_a);
+  const int rpb = 256 / (C / 8);
+  act_bwd_kernel<1><<<ew_grid((int64_t)batch * L, rpb * 8), 256, 0, ST>>>(
+      g_h, in_halo_pos, roll, g_add, a, dtype, batch, L, C, scale_shift, mean_invstd, slope, act,
+      const_cast<double*>(red), use_bn, g_a);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_ncl_to_nlc(const float* src, int batch, int C, int L, void* dst, int dtype, void* stream) {
+  dim3 grid((L + 31) / 32, (C + 31) / 32, batch), block(32, 8);
+  ncl_to_nlc_kernel<<<grid, block, 0, ST>>>(src, C, L, dst, dtype);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+extern "C" int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L, float* dst, void* stream) {
+  dim3 grid((L + 31) / 32, (C + 31) / 32, batch), block(32, 8);
+  nlc_to_ncl_kernel<<<grid, block, 0, ST>>>(src, dtype, C, L, dst);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_colsum(const void* a, int dtype, int64_t rows, int C, int mod, float* out, int accumulate,
+                         double* tmp, void* stream) {
+  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && tmp && C % mod == 0);
+  SG_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * C, ST));
+  const int rpb = 256 / (C / 8);
+  colsum_kernel<<<ew_grid(rows, rpb * 8), 256, 0, ST>>>(a, dtype, rows, C, tmp);
+  SG_CHECK_LAUNCH();
+  colsum_fold_kernel<<<(mod + 127) / 128, 128, 0, ST>>>(tmp, C, mod, out, accumulate);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_fc_tail_fwd(const float* fc0_acc, const float* b0, const float* s1, const float* w2,
+                              const float* b2, const float* s3, const float* w4, const float* b4, int batch,
+                              float* z1, float* z2, float* logit, void* stream) {
+  fc_tail_fwd_kernel<<<batch, 256, 0, ST>>>(fc0_acc, b0, s1, w2, b2, s3, w4, b4, z1, z2, logit);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit, float target, float weight,
+                              const float* s1, const float* w2, const float* s3, const float* w4, int batch,
+                              float* loss_out, void* g_z1_bf16, float* ws /* [B*(1+128+256)] */, float* g_b0,
+                              float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4, float* g_b4,
+                              void* stream) {
+  SG_CHECK_ARG(ws && g_z1_bf16);
+  float* g_logit = ws;
+  float* g_z2 = ws + batch;
+  float* g_z1 = g_z2 + (int64_t)batch * FC2;
+  fc_tail_bwd_rows_kernel<<<batch, 256, 0, ST>>>(z1, z2, logit, target, weight, s1, w2, s3, w4, batch, loss_out,
+                                                 g_logit, g_z2, g_z1, g_z1_bf16);
+  SG_CHECK_LAUNCH();
+  if (g_w2) {
+    const int n = FC2 * FC1 + FC1 + FC2 + 1;
+    fc_tail_bwd_params_kernel<<<(n + 127) / 128, 128, 0, ST>>>(z1, z2, g_logit, g_z2, g_z1, s1, s3, w2, w4, batch,
+                                                               g_b0, g_s1, g_w2, g_b2, g_s3, g_w4, g_b4);
+    SG_CHECK_LAUNCH();
+  }
+  return SG_OK;
+}
+
+extern "C" int sg_l1_loss_bwd(const float* y, const float* clean, int64_t n, float weight, float* loss_out,
+                              float* gy, int accumulate, void* stream) {
+  l1_loss_bwd_kernel<<<2 * NUM_SMS, 256, 0, ST>>>(y, clean, n, weight, loss_out, gy, accumulate);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}

@@ -1,0 +1,314 @@
+// Optimisers on flat fp32 parameter buffers, weight packing into the 16-bit tap-GEMM operand
+// layouts, gradient unpacking, and the inference-side emphasis filters.
+#include "common.cuh"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------
+// torch.optim.RMSprop (centered=False, momentum=0, weight_decay=0):
+//   sq = alpha*sq + (1-alpha)*g*g ; p -= lr * g / (sqrt(sq) + eps)
+// ------------------------------------------------------------------------------------------
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
+                               int64_t n, float lr, float alpha, float eps, float gscale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float s = alpha * sq[i] + (1.f - alpha) * gi * gi;
+    sq[i] = s;
+    p[i] = p[i] - lr * (gi / (sqrtf(s) + eps));
+  }
+}
+// torch.optim.Adam (amsgrad=False, weight_decay=0)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float gscale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// packing.  One block handles a 16 x 16 (outer x inner channel) tile of the fp32 master and all
+// 31 taps: coalesced 496-float reads, 32-byte segment writes into both packed layouts.
+//
+// kind 0 (Conv1d W[co][ci][k]):
+//   Wf [d+4][co][p*Cin + ci] = W[co][ci][ 4d + p + 14]        (fwd:   K = (p,ci), N = co)
+//   Wdg[d+4][p*Cin + ci][co] = W[co][ci][-4d + p + 14]        (dgrad: K = co, N = (p,ci))
+// kind 1 (ConvTranspose1d W[ci][co][k], alpha folded for ci >= alpha_from):
+//   Wt [d+4][r*Cout + co][ci] = a(ci) W[ci][co][-4d + r + 13] (fwd:   K = ci, N = (r,co))
+//   Wtd[d+4][ci][r*Cout + co] = a(ci) W[ci][co][ 4d + r + 13] (dgrad: K = (r,co), N = ci)
+// entries whose tap index falls outside [0, 30] are zero.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner, const float* __restrict__ alpha,
+                 int alpha_from, void* __restrict__ w_fwd, void* __restrict__ w_dg, int dt_fwd, int dt_dg) {
+  // master layout is [outer][inner][31]; kind 0: outer = co, inner = ci ; kind 1: outer = ci, inner = co
+  __shared__ float tile[16][16][KW + 1];
+  const int o0 = blockIdx.y * 16, i0 = blockIdx.x * 16;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < 16 * 16 * KW; idx += 256) {
+    const int oo = idx / (16 * KW), rem = idx % (16 * KW);
+    const int ii = rem / KW, k = rem % KW;
+    float v = w[((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k];
+    if (kind == 1 && alpha && (o0 + oo) >= alpha_from) v *= alpha[o0 + oo - alpha_from];
+    tile[oo][ii][k] = v;
+  }
+  __syncthreads();
+  // 9 taps x 4 phases x 16 x 16 outputs per packed layout
+  for (int idx = tid; idx < NTAP * 4 * 256; idx += 256) {
+    const int lo = idx % 16;            // fastest index -> contiguous channel in the destination
+    const int hi = (idx / 16) % 16;
+    const int ph = (idx / 256) % 4;
+    const int ti = idx / 1024;          // d + 4
+    const int d = ti - 4;
+    if (kind == 0) {
+      const int Cout = c_outer, Cin = c_inner;
+      {  // Wf[ti][co = hi][ph*Cin + ci = lo]
+        const int k = 4 * d + ph + 14;
+        const float v = (k >= 0 && k < KW) ? tile[hi][lo][k] : 0.f;
+        st16(w_fwd, ((int64_t)ti * Cout + (o0 + hi)) * (4 * Cin) + ph * Cin + (i0 + lo), v, dt_fwd);
+      }
+      {  // Wdg[ti][ph*Cin + ci = hi][co = lo]
+        const int k = -4 * d + ph + 14;
+        const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
+        st16(w_dg, ((int64_t)ti * (4 * Cin) + ph * Cin + (i0 + hi)) * Cout + (o0 + lo), v, dt_dg);
+      }
+    } else {
+      const int Cin = c_outer, Cout = c_inner;
+      {  // Wt[ti][ph*Cout + co = hi][ci = lo]
+        const int k = -4 * d + ph + 13;
+        const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
+        st16(w_fwd, ((int64_t)ti * (4 * Cout) + ph * Cout + (i0 + hi)) * Cin + (o0 + lo), v, dt_fwd);
+      }
+      {  // Wtd[ti][ci = hi][ph*Cout + co = lo]
+        const int k = 4 * d + ph + 13;
+        const float v = (k >= 0 && k < KW) ? tile[hi][lo][k] : 0.f;
+        st16(w_dg, ((int64_t)ti * Cin + (o0 + hi)) * (4 * Cout) + ph * Cout + (i0 + lo), v, dt_dg);
+      }
+    }
+  }
+}
+
+// kind 2 (Linear W[n][c*T + t]) -> W1p[n][t*C + c] ; W1dg[t*C + c][n]
+__global__ void pack_fc_kernel(const float* __restrict__ w, int nout, int C, int T, void* __restrict__ w_fwd,
+                               void* __restrict__ w_dg, int dt_fwd, int dt_dg) {
+  const int64_t total = (int64_t)nout * C * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes the destination W1p (coalesced writes)
+    const int n = (int)(i / ((int64_t)C * T));
+    const int kk = (int)(i % ((int64_t)C * T));
+    const int t = kk / C, c = kk % C;
+    const float v = w[(int64_t)n * C * T + (int64_t)c * T + t];
+    st16(w_fwd, i, v, dt_fwd);
+    st16(w_dg, (int64_t)kk * nout + n, v, dt_dg);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// unpack: packed fp32 dWp -> reference layout
+// kind 0: dW[co][ci][k] = dWf[d+4][co][p*Cin+ci],  k = 4d + p + 14
+// kind 1: dWe[ci][co][k] = dWt[d+4][r*Cout+co][ci], k = -4d + r + 13 ; dW = a(ci) dWe ;
+//         dalpha[ci-alpha_from] = sum_{co,k} dWe * W
+// kind 2: dW[n][c*T+t] = dW1p[n][t*C+c]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_inner, const float* __restrict__ w,
+                   const float* __restrict__ alpha, int alpha_from, float* __restrict__ dw,
+                   float* __restrict__ dalpha, int accumulate) {
+  __shared__ float tile[16][16][KW + 1];
+  __shared__ float ared[16];
+  const int o0 = blockIdx.y * 16, i0 = blockIdx.x * 16;
+  const int tid = threadIdx.x;
+  if (tid < 16) ared[tid] = 0.f;
+  for (int idx = tid; idx < NTAP * 4 * 256; idx += 256) {
+    const int lo = idx % 16, hi = (idx / 16) % 16, ph = (idx / 256) % 4, ti = idx / 1024;
+    const int d = ti - 4;
+    if (kind == 0) {
+      const int Cout = c_outer, Cin = c_inner;
+      const int k = 4 * d + ph + 14;
+      if (k >= 0 && k < KW)
+        tile[hi][lo][k] = dwp[((int64_t)ti * Cout + (o0 + hi)) * (4 * Cin) + ph * Cin + (i0 + lo)];
+    } else {
+      const int Cin = c_outer, Cout = c_inner;
+      const int k = -4 * d + ph + 13;
+      if (k >= 0 && k < KW)
+        tile[lo][hi][k] = dwp[((int64_t)ti * (4 * Cout) + ph * Cout + (i0 + hi)) * Cin + (o0 + lo)];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 16 * 16 * KW; idx += 256) {
+    const int oo = idx / (16 * KW), rem = idx % (16 * KW);
+    const int ii = rem / KW, k = rem % KW;
+    const int64_t gi = ((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k;
+    float v = tile[oo][ii][k];
+    if (kind == 1 && alpha && (o0 + oo) >= alpha_from) {
+      if (dalpha) atomicAdd(&ared[oo], v * w[gi]);
+      v *= alpha[o0 + oo - alpha_from];
+    }
+    dw[gi] = accumulate ? dw[gi] + v : v;
+  }
+  __syncthreads();
+  if (kind == 1 && alpha && dalpha && tid < 16 && (o0 + tid) >= alpha_from)
+    atomicAdd(dalpha + (o0 + tid - alpha_from), ared[tid]);
+}
+
+__global__ void unpack_fc_kernel(const float* __restrict__ dwp, int nout, int C, int T, float* __restrict__ dw,
+                                 int accumulate) {
+  const int64_t total = (int64_t)nout * C * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / ((int64_t)C * T));
+    const int kk = (int)(i % ((int64_t)C * T));
+    const int t = kk / C, c = kk % C;
+    const int64_t o = (int64_t)n * C * T + (int64_t)c * T + t;
+    dw[o] = accumulate ? dw[o] + dwp[i] : dwp[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// emphasis filters (se_dataset.py:111-126).  De-emphasis x[n] = c x[n-1] + y[n] is a linear
+// recurrence: single block, chunked scan over (a, b) pairs with the carry kept in a register.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) deemph_kernel(const float* __restrict__ y, int64_t n, float c,
+                                                      float* __restrict__ x) {
+  constexpr int PER = 4;
+  __shared__ float sa[32], sb[32];
+  __shared__ float carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0.f;
+  __syncthreads();
+  const float c2 = c * c, c4 = c2 * c2;
+  for (int64_t base = 0; base < n; base += 1024 * PER) {
+    const int64_t i0 = base + (int64_t)tid * PER;
+    float v[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) v[j] = (i0 + j < n) ? y[i0 + j] : 0.f;
+    // local serial part: x_j = c x_{j-1} + v_j with x_{-1} = 0 ; thread transform is (A = c^4, B = local[3])
+    float loc[PER];
+    loc[0] = v[0];
+#pragma unroll
+    for (int j = 1; j < PER; ++j) loc[j] = fmaf(c, loc[j - 1], v[j]);
+    float A = c4, Bv = loc[PER - 1];
+    // inclusive scan of affine maps within the warp: (A2,B2) o (A1,B1) = (A1*A2, A2*B1 + B2)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float Ap = __shfl_up_sync(0xffffffffu, A, o);
+      const float Bp = __shfl_up_sync(0xffffffffu, Bv, o);
+      if (lane >= o) { Bv = fmaf(A, Bp, Bv); A = A * Ap; }
+    }
+    if (lane == 31) { sa[warp] = A; sb[warp] = Bv; }
+    __syncthreads();
+    if (warp == 0) {
+      float wa = sa[lane], wb = sb[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float Ap = __shfl_up_sync(0xffffffffu, wa, o);
+        const float Bp = __shfl_up_sync(0xffffffffu, wb, o);
+        if (lane >= o) { wb = fmaf(wa, Bp, wb); wa = wa * Ap; }
+      }
+      sa[lane] = wa; sb[lane] = wb;
+    }
+    __syncthreads();
+    const float carry = carry_s;
+    // exclusive prefix for this thread: state before its first element
+    float Aw = 1.f, Bw = 0.f;             // warps before
+    if (warp > 0) { Aw = sa[warp - 1]; Bw = sb[warp - 1]; }
+    float Al = __shfl_up_sync(0xffffffffu, A, 1), Bl = __shfl_up_sync(0xffffffffu, Bv, 1);
+    if (lane == 0) { Al = 1.f; Bl = 0.f; }
+    // state_in = Al*(Aw*carry + Bw) + Bl
+    const float sin_ = fmaf(Al, fmaf(Aw, carry, Bw), Bl);
+    float cp = c, xv = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      xv = fmaf(cp, sin_, loc[j]);
+      if (i0 + j < n) x[i0 + j] = xv;
+      cp *= c;
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = xv;      // filter state after this chunk
+    __syncthreads();
+  }
+}
+
+__global__ void preemph_kernel(const float* __restrict__ x, int64_t n, float c, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = i == 0 ? x[0] : x[i] - c * x[i - 1];
+}
+
+}  // namespace sg
+
+using namespace sg;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int sg_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr, float alpha,
+                               float eps, float grad_scale, void* stream) {
+  rmsprop_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(param, grad, square_avg, n, lr, alpha, eps, grad_scale);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                            float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1,
+                                           sqrtf(bc2), grad_scale);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_pack_weights(int kind, const float* w, int c_out, int c_in, int t_len, const float* alpha,
+                               int alpha_from, void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad,
+                               void* stream) {
+  SG_CHECK_ARG(w && w_fwd && w_dgrad);
+  if (kind == 0) {
+    SG_CHECK_ARG(c_out % 16 == 0 && c_in % 16 == 0);
+    dim3 grid(c_in / 16, c_out / 16);
+    pack_conv_kernel<<<grid, 256, 0, ST>>>(0, w, c_out, c_in, nullptr, 0, w_fwd, w_dgrad, dtype_fwd, dtype_dgrad);
+  } else if (kind == 1) {
+    SG_CHECK_ARG(c_out % 16 == 0 && c_in % 16 == 0);
+    dim3 grid(c_out / 16, c_in / 16);
+    pack_conv_kernel<<<grid, 256, 0, ST>>>(1, w, c_in, c_out, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
+                                           dtype_dgrad);
+  } else if (kind == 2) {
+    pack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(w, c_out, c_in, t_len, w_fwd, w_dgrad, dtype_fwd, dtype_dgrad);
+  } else {
+    SG_CHECK_ARG(false);
+  }
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_unpack_wgrad(int kind, const float* dwp, int c_out, int c_in, int t_len, const float* w,
+                               const float* alpha, int alpha_from, float* dw, float* dalpha, int accumulate,
+                               void* stream) {
+  SG_CHECK_ARG(dwp && dw);
+  if (kind == 0) {
+    dim3 grid(c_in / 16, c_out / 16);
+    unpack_conv_kernel<<<grid, 256, 0, ST>>>(0, dwp, c_out, c_in, nullptr, nullptr, 0, dw, nullptr, accumulate);
+  } else if (kind == 1) {
+    dim3 grid(c_out / 16, c_in / 16);
+    unpack_conv_kernel<<<grid, 256, 0, ST>>>(1, dwp, c_in, c_out, w, alpha, alpha_from, dw, dalpha, accumulate);
+  } else if (kind == 2) {
+    unpack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(dwp, c_out, c_in, t_len, dw, accumulate);
+  } else {
+    SG_CHECK_ARG(false);
+  }
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_deemphasis(const float* y, int64_t n, float coef, float* x, void* stream) {
+  deemph_kernel<<<1, 1024, 0, ST>>>(y, n, coef, x);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+extern "C" int sg_preemphasis(const float* x, int64_t n, float coef, float* y, void* stream) {
+  preemph_kernel<<<2 * NUM_SMS, 256, 0, ST>>>(x, n, coef, y);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}

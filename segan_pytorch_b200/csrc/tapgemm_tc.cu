@@ -1,0 +1,661 @@
+// tcgen05 / TMA / TMEM implementation of the two tap-GEMM forms (SG_BACKEND_TCGEN05), sm_100a.
+//
+// Both kernels are persistent (one CTA per SM, static round-robin tile schedule), warp
+// specialised -- warp 0: TMA producer, warp 1: TMEM allocator + single-thread tcgen05.mma
+// issuer, warps 2..5: epilogue (TMEM -> registers -> HBM) -- with a 4-stage smem ring
+// (full/empty mbarriers) and a double-buffered 128 x 256 fp32 accumulator in TMEM
+// (tmem_full/tmem_empty mbarriers) so that the epilogue of tile i overlaps the main loop of
+// tile i+1.
+//
+// Every operand tile is a TMA box of 64 channels (128 B) x rows, 128B-swizzled, so the same
+// smem bytes serve as
+//   * a K-major  UMMA operand (rows = M/N, 64 channels = K)   -> form F (fwd / dgrad)
+//   * an MN-major UMMA operand (64 channels = M/N, rows = K)  -> form W (wgrad)
+// i.e. no im2col, no transposed copies in HBM: the 9 row-taps are just 9 different TMA
+// coordinates into the same NLC-row tensor.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done) {
+      // watchdog: a pipeline bug must surface as a launch error, never as a hung GPU
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (count 1) on `bar` once all previously issued tcgen05.mma of this thread retire
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, 128B swizzle, version 1 (Blackwell).
+//   K-major : rows of 128 B (64 x 16-bit along K); 8-row groups SBO bytes apart; LBO unused.
+//   MN-major: 128 B lines hold 64 MN-elements for one K index; 8 K-lines form a 1024 B group,
+//             groups SBO bytes apart; 64-element MN blocks LBO bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+  d |= (uint64_t)((saddr >> 7) & 0x7) << 49;        // base offset (0 for 1024 B aligned tiles)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor for kind::f16, fp32 accumulate
+__host__ __device__ inline uint32_t make_idesc(int a_bf16, int b_bf16, int a_mn_major, int b_mn_major, int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // C format: F32
+  d |= (uint32_t)(a_bf16 ? 1 : 0) << 7;  // A format
+  d |= (uint32_t)(b_bf16 ? 1 : 0) << 10; // B format
+  d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = 128 * 128;   // 128 rows x 128 B
+constexpr int B_STAGE_BYTES = 256 * 128;   // up to 256 rows x 128 B
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+
+struct TapRangesTC {
+  int k_lo[NTAP], k_hi[NTAP], n_lo[NTAP], n_hi[NTAP];
+};
+
+struct FTcParams {
+  int a0_c, kc, nc, a_halo;
+  int d_lo, d_hi;
+  TapRangesTC tr;
+  void* out; int out_dtype, out_rows, out_halo;
+  int m_lo, m_hi, n_lo;
+  const float* bias; int bias_mod;
+  int batch, ksplit;
+  int TR, TB, TN;            // M tile = TB batches x TR rows (<= 128), N tile
+  int m_tiles_per_b, b_tiles, n_tiles;
+  uint32_t idesc;
+};
+
+struct SharedCtl {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------
+// form F:  out[b,m,n] = bias + sum_d sum_kc A[b,m+d,kc] * Wp[d+4][n][kc]
+//   UMMA: M = 128 (rows: TB batches x TR rows), N = TN output channels, K = 64-channel blocks.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+             const __grid_constant__ CUtensorMap tmW, const FTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  const int m_tiles = p.m_tiles_per_b * p.b_tiles;
+  const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
+  const uint32_t a_bytes = (uint32_t)p.TR * p.TB * 128u;
+  const uint32_t b_bytes = (uint32_t)p.TN * 128u;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles;
+        const int rest = tile / m_tiles;
+        const int ks = rest % p.ksplit;
+        const int nt = rest / p.ksplit;
+        const int b0 = (mt / p.m_tiles_per_b) * p.TB;
+        const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * p.TR;
+        const int n0 = p.n_lo + nt * p.TN;
+        int step = 0;
+        for (int d = p.d_lo; d <= p.d_hi; ++d) {
+          const int ti = d + 4;
+          if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
+          for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
+            if (step % p.ksplit != ks) continue;
+            mbar_wait(&ctl->empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
+            if (k0 < p.a0_c) tma_load_3d(sa, &tmA0, &ctl->full[stage], k0, m0 + d + p.a_halo, b0);
+            else tma_load_3d(sa, &tmA1, &ctl->full[stage], k0 - p.a0_c, m0 + d + p.a_halo, b0);
+            tma_load_2d(sb, &tmW, &ctl->full[stage], k0, ti * p.nc + n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int rest = tile / m_tiles;
+        const int ks = rest % p.ksplit;
+        const int nt = rest / p.ksplit;
+        const int n0 = p.n_lo + nt * p.TN;
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        uint32_t accum = 0;
+        int step = 0;
+        for (int d = p.d_lo; d <= p.d_hi; ++d) {
+          const int ti = d + 4;
+          if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
+          for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
+            if (step % p.ksplit != ks) continue;
+            mbar_wait(&ctl->full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sb = sa + A_STAGE_BYTES;
+            const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // advance 16 elements (32 B) along K inside the 128 B swizzled row
+              umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, accum);
+              accum = 1;
+            }
+            umma_commit(&ctl->empty[stage]);   // frees the smem slot when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&ctl->tmem_full[acc]);     // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;           // accumulator row = tile row
+    int acc = 0; uint32_t acc_phase = 0;
+    const int out_buf_rows = p.out_rows + 2 * p.out_halo;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % m_tiles;
+      const int rest = tile / m_tiles;
+      const int ks = rest % p.ksplit;
+      const int nt = rest / p.ksplit;
+      const int b0 = (mt / p.m_tiles_per_b) * p.TB;
+      const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * p.TR;
+      const int n0 = p.n_lo + nt * p.TN;
+      const int tb = row / p.TR, tr = row % p.TR;
+      const int b = b0 + tb, m = m0 + tr;
+      const bool valid = (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.nc + n0;
+      for (int c0 = 0; c0 < p.TN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr && ks == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ((n0 + c0 + j) % p.bias_mod));
+          }
+          if (p.out_dtype == SG_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + obase + c0;
+            if (p.ksplit == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+            }
+          } else {
+            uint32_t pk[16];
+            if (p.out_dtype == SG_F16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&ctl->tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// form W:  dWp[d+4][n][kc] += sum_{b,m} G[b,m,n] * A[b,m+d,kc]
+//   UMMA: M = 128 channels n (MN-major from G), N = TK channels kc (MN-major from A),
+//   K = 64 positions per stage (PB batches x PR rows).
+// ------------------------------------------------------------------------------------------
+struct WTcParams {
+  int a0_c, kc, nc, a_halo;
+  int d_lo, d_hi;
+  TapRangesTC tr;
+  float* dw;
+  int g_rows, batch, ksplit;
+  int PR, PB;                // K block = PB batches x PR rows = 64 positions
+  int TK;                    // N tile (kc), <= 256
+  int n_tiles, k_tiles;      // nc/128, kc/TK
+  int row_chunks, b_chunks;  // ceil(g_rows/PR), ceil(batch/PB)
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA0,
+             const __grid_constant__ CUtensorMap tmA1, const WTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmG); prefetch_tmap(&tmA0); prefetch_tmap(&tmA1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  const int ntaps = p.d_hi - p.d_lo + 1;
+  const int total_tiles = ntaps * p.n_tiles * p.k_tiles * p.ksplit;
+  const int pos_steps = p.row_chunks * p.b_chunks;
+  const int steps_per_split = (pos_steps + p.ksplit - 1) / p.ksplit;
+  const int kboxes = p.TK / 64;
+  const uint32_t stage_tx = (uint32_t)(2 + kboxes) * 64u * 128u;
+
+  // tile -> (d, n0, kc0, split); returns false when the (tap, n, kc) block is structurally zero
+  auto decode = [&](int tile, int& d, int& n0, int& kc0, int& sp) -> bool {
+    sp = tile % p.ksplit; tile /= p.ksplit;
+    const int kt = tile % p.k_tiles; tile /= p.k_tiles;
+    const int nt = tile % p.n_tiles; tile /= p.n_tiles;
+    d = p.d_lo + tile;
+    n0 = nt * 128; kc0 = kt * p.TK;
+    const int ti = d + 4;
+    if (n0 + 128 <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) return false;
+    if (kc0 + p.TK <= p.tr.k_lo[ti] || kc0 >= p.tr.k_hi[ti]) return false;
+    return true;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int d, n0, kc0, sp;
+        if (!decode(tile, d, n0, kc0, sp)) continue;
+        const int s_lo = sp * steps_per_split;
+        const int s_hi = min(pos_steps, s_lo + steps_per_split);
+        for (int s = s_lo; s < s_hi; ++s) {
+          const int r0 = (s % p.row_chunks) * p.PR;
+          const int b0 = (s / p.row_chunks) * p.PB;
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;      // G boxes (2 x 8 KB)
+          uint8_t* sb = sa + A_STAGE_BYTES;              // A boxes (kboxes x 8 KB)
+          mbar_expect_tx(&ctl->full[stage], stage_tx);
+          tma_load_3d(sa, &tmG, &ctl->full[stage], n0, r0, b0);
+          tma_load_3d(sa + 8192, &tmG, &ctl->full[stage], n0 + 64, r0, b0);
+          for (int j = 0; j < kboxes; ++j) {
+            const int kk = kc0 + 64 * j;
+            if (kk < p.a0_c) tma_load_3d(sb + 8192 * j, &tmA0, &ctl->full[stage], kk, r0 + d + p.a_halo, b0);
+            else tma_load_3d(sb + 8192 * j, &tmA1, &ctl->full[stage], kk - p.a0_c, r0 + d + p.a_halo, b0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int d, n0, kc0, sp;
+        if (!decode(tile, d, n0, kc0, sp)) continue;
+        const int s_lo = sp * steps_per_split;
+        const int s_hi = min(pos_steps, s_lo + steps_per_split);
+        if (s_lo >= s_hi) continue;
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        uint32_t accum = 0;
+        for (int s = s_lo; s < s_hi; ++s) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // 16 positions = 16 lines of 128 B = 2048 B along K
+            const uint64_t adesc = make_smem_desc(sa + k * 2048, 8192, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
+            umma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
+            accum = 1;
+          }
+          umma_commit(&ctl->empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&ctl->tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int d, n0, kc0, sp;
+      if (!decode(tile, d, n0, kc0, sp)) continue;
+      const int s_lo = sp * steps_per_split;
+      const int s_hi = min(pos_steps, s_lo + steps_per_split);
+      if (s_lo >= s_hi) continue;
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      float* o = p.dw + ((int64_t)(d + 4) * p.nc + n0 + row) * p.kc + kc0;
+      const int ti = d + 4;
+      for (int c0 = 0; c0 < p.TK; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        // skip column blocks that are structurally zero for this tap
+        if (kc0 + c0 + 32 <= p.tr.k_lo[ti] || kc0 + c0 >= p.tr.k_hi[ti]) continue;
+        if (n0 + row < p.tr.n_lo[ti] || n0 + row >= p.tr.n_hi[ti]) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(o + c0 + j, __uint_as_float(r[j]));
+      }
+      tc_fence_before();
+      mbar_arrive(&ctl->tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// 3-D map over [B][rows][C] 16-bit, box (64, box_rows, box_b), 128B swizzle, OOB -> 0
+static int make_map3(CUtensorMap* m, const void* base, int dtype, int C, int rows, int B, int box_rows, int box_b) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SG_ERR_LAUNCH; }
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_b};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, dtype == SG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d C=%d rows=%d B=%d box=%d,%d) failed: %d", C, rows, B, box_rows, box_b, (int)r);
+    return SG_ERR_LAUNCH;
+  }
+  return SG_OK;
+}
+static int make_map2(CUtensorMap* m, const void* base, int dtype, int C, int64_t rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return SG_ERR_LAUNCH; }
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, dtype == SG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d C=%d rows=%lld box=%d) failed: %d", C, (long long)rows, box_rows, (int)r);
+    return SG_ERR_LAUNCH;
+  }
+  return SG_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = NUM_SMS;
+  }
+  return n;
+}
+
+int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_f_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  FTcParams p;
+  p.a0_c = q->a0_c; p.kc = q->kc; p.nc = q->nc; p.a_halo = q->a_halo;
+  p.d_lo = q->d_lo; p.d_hi = q->d_hi;
+  for (int i = 0; i < NTAP; ++i) {
+    p.tr.k_lo[i] = q->tap_k_lo[i]; p.tr.k_hi[i] = q->tap_k_hi[i];
+    p.tr.n_lo[i] = q->tap_n_lo[i]; p.tr.n_hi[i] = q->tap_n_hi[i];
+  }
+  p.out = q->out; p.out_dtype = q->out_dtype; p.out_rows = q->out_rows; p.out_halo = q->out_halo;
+  p.m_lo = q->m_lo; p.m_hi = q->m_hi; p.n_lo = q->n_lo;
+  p.bias = q->bias; p.bias_mod = q->bias_mod > 0 ? q->bias_mod : q->nc;
+  p.batch = q->batch; p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
+  const int rows_m = q->m_hi - q->m_lo;
+  const int ncols = q->n_hi - q->n_lo;
+  p.TN = (ncols % 256 == 0) ? 256 : (ncols % 128 == 0 ? 128 : 64);
+  if (rows_m >= 128) { p.TR = 128; p.TB = 1; }
+  else { p.TR = rows_m; p.TB = 128 / rows_m; if (p.TB > q->batch) p.TB = q->batch; if (p.TB > 256) p.TB = 256; }
+  p.m_tiles_per_b = (rows_m + p.TR - 1) / p.TR;
+  p.b_tiles = (q->batch + p.TB - 1) / p.TB;
+  p.n_tiles = ncols / p.TN;
+  p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 128, p.TN);
+  CUtensorMap tmA0, tmA1, tmW;
+  const int a_buf_rows = q->a_rows + 2 * q->a_halo;
+  int rc = make_map3(&tmA0, q->a0, q->a_dtype, q->a0_c, a_buf_rows, q->batch, p.TR, p.TB);
+  if (rc) return rc;
+  if (q->a1) rc = make_map3(&tmA1, q->a1, q->a_dtype, q->a1_c, a_buf_rows, q->batch, p.TR, p.TB);
+  else tmA1 = tmA0;
+  if (rc) return rc;
+  rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)NTAP * q->nc, p.TN);
+  if (rc) return rc;
+  const int total = p.m_tiles_per_b * p.b_tiles * p.n_tiles * p.ksplit;
+  const int grid = total < num_sms() ? total : num_sms();
+  tapgemm_f_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA0, tmA1, tmW, p);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_w_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  WTcParams p;
+  p.a0_c = q->a0_c; p.kc = q->kc; p.nc = q->nc; p.a_halo = q->a_halo;
+  p.d_lo = q->d_lo; p.d_hi = q->d_hi;
+  for (int i = 0; i < NTAP; ++i) {
+    p.tr.k_lo[i] = q->tap_k_lo[i]; p.tr.k_hi[i] = q->tap_k_hi[i];
+    p.tr.n_lo[i] = q->tap_n_lo[i]; p.tr.n_hi[i] = q->tap_n_hi[i];
+  }
+  p.dw = q->dw; p.g_rows = q->g_rows; p.batch = q->batch;
+  p.PR = q->g_rows >= 64 ? 64 : q->g_rows;
+  p.PB = 64 / p.PR;
+  p.TK = q->kc >= 256 ? 256 : q->kc;
+  if (q->a1 && q->a0_c < 256 && p.TK > q->a0_c) p.TK = q->a0_c;   // a kc tile never straddles the two sources unevenly
+  p.n_tiles = q->nc / 128;
+  p.k_tiles = q->kc / p.TK;
+  p.row_chunks = (q->g_rows + p.PR - 1) / p.PR;
+  p.b_chunks = (q->batch + p.PB - 1) / p.PB;
+  const int pos_steps = p.row_chunks * p.b_chunks;
+  p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
+  if (p.ksplit > pos_steps) p.ksplit = pos_steps;
+  p.idesc = make_idesc(q->g_dtype == SG_BF16, q->a_dtype == SG_BF16, 1, 1, 128, p.TK);
+  CUtensorMap tmG, tmA0, tmA1;
+  int rc = make_map3(&tmG, q->g, q->g_dtype, q->nc, q->g_rows, q->batch, p.PR, p.PB);
+  if (rc) return rc;
+  const int a_buf_rows = q->a_rows + 2 * q->a_halo;
+  rc = make_map3(&tmA0, q->a0, q->a_dtype, q->a0_c, a_buf_rows, q->batch, p.PR, p.PB);
+  if (rc) return rc;
+  if (q->a1) rc = make_map3(&tmA1, q->a1, q->a_dtype, q->a1_c, a_buf_rows, q->batch, p.PR, p.PB);
+  else tmA1 = tmA0;
+  if (rc) return rc;
+  const int total = (q->d_hi - q->d_lo + 1) * p.n_tiles * p.k_tiles * p.ksplit;
+  const int grid = total < num_sms() ? total : num_sms();
+  tapgemm_w_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmG, tmA0, tmA1, p);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+}  // namespace sg
