@@ -71,14 +71,16 @@ typedef struct sg_tapgemm_f {
   int32_t a0_c, a1_c; /* kc = a0_c + a1_c */
   int32_t a_rows, a_halo;
   int32_t a_dtype;    /* SG_F16 | SG_BF16 */
-  const void* w;      /* packed [9][nc][kc], w_dtype */
+  const void* w;      /* packed [slots][nc][kc], w_dtype; slot = (d + 4) - w_tap0 */
   int32_t w_dtype;
+  int32_t w_tap0;     /* tap index stored in slot 0 (0 for the 9-slot conv packs, 4 for a Linear) */
   int32_t kc, nc;
   int32_t d_lo, d_hi; /* inclusive, within [-4, 4] */
   /* per tap (index d+4): valid K range [k_lo, k_hi) and valid N range [n_lo, n_hi) in channels
      (multiples of 64); blocks outside are structurally zero in Wp and are skipped */
   int32_t tap_k_lo[9], tap_k_hi[9], tap_n_lo[9], tap_n_hi[9];
-  void* out;          /* [B][out_halo + out_rows + out_halo][nc] */
+  void* out;          /* [B][out_halo + out_rows + out_halo][out_ld]; column of channel n = n - n_lo + out_col0 */
+  int32_t out_ld, out_col0;
   int32_t out_dtype;  /* SG_F16 | SG_BF16 | SG_F32 (F32: atomically accumulated, pre-zeroed by caller) */
   int32_t out_rows, out_halo;
   int32_t m_lo, m_hi; /* rows computed per batch element (may reach into the out halo) */
@@ -109,7 +111,8 @@ typedef struct sg_tapgemm_w {
   int32_t kc, nc;
   int32_t d_lo, d_hi;
   int32_t tap_k_lo[9], tap_k_hi[9], tap_n_lo[9], tap_n_hi[9];
-  float* dw; /* [9][nc][kc] fp32 */
+  float* dw; /* [slots][nc][kc] fp32; slot = (d + 4) - dw_tap0 */
+  int32_t dw_tap0;
   int32_t batch;
   int32_t ksplit; /* number of position-range splits (>=1) */
   int32_t backend;
@@ -188,11 +191,13 @@ int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* s
  *   Without BatchNorm g_a = g_pre is final and pass 1 writes it when g_a_out_or_null != NULL.
  * pass 2 (sg_act_bwd_apply): g_a (bf16 exact) = no BN: g_pre ;
  *   BN: scale * (g_pre - red1/N - ahat*red2/N). */
-int sg_act_bwd_reduce(const void* g_h, int in_halo_pos, int roll, const void* g_add,
+/* g_h_ld / g_add_ld: row pitch in elements of g_h / g_add (>= C; lets a consumer read one half of
+ * a channel-concatenated gradient in place; the pointers are pre-offset by the caller) */
+int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add, int g_add_ld,
                       const void* a, int dtype, int batch, int L, int C,
                       const float* scale_shift, const float* mean_invstd, const float* slope,
                       int act, double* red, void* g_a_out_or_null, void* stream);
-int sg_act_bwd_apply(const void* g_h, int in_halo_pos, int roll, const void* g_add,
+int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add, int g_add_ld,
                      const void* a, int dtype, int batch, int L, int C,
                      const float* scale_shift, const float* mean_invstd, const float* slope,
                      int act, const double* red, int use_bn, void* g_a, void* stream);
@@ -211,7 +216,8 @@ int sg_fc_tail_fwd(const float* fc0_acc, const float* b0, const float* s1, const
 /* loss = mean((logit-target)^2)*weight ; g_logit = 2(logit-target)/B*weight ; backward through the
  * head: g_z1 (bf16 [B][256] for the fc.0 tap-GEMMs) and (if grads != NULL) parameter gradients
  * accumulated into: g_b0[256], g_s1[256], g_w2[128*256], g_b2[128], g_s3[128], g_w4[128], g_b4[1]. */
-int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit, float target, float weight,
+int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit,
+                   const float* g_logit_in /* or NULL: use the fused MSE gradient below */, float target, float weight,
                    const float* s1, const float* w2, const float* s3, const float* w4, int batch,
                    float* loss_out, void* g_z1_bf16, float* ws /* fp32 [B*(1+128+256)] */,
                    float* g_b0, float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4,

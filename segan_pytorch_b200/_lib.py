@@ -1,0 +1,114 @@
+"""ctypes binding of libsegan_b200.so (the C ABI declared in include/segan_b200.h).
+
+The library is the product: if it is missing, not loadable, or the device is not sm_100 class,
+every compute entry point raises -- there is no CPU / ATen fallback behind this module.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegan_b200.so")
+
+SG_F32, SG_F16, SG_BF16 = 0, 1, 2
+ACT_NONE, ACT_PRELU, ACT_TANH = 0, 1, 2
+BACKEND_FFMA, BACKEND_TCGEN05 = 0, 1
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+I9 = C.c_int32 * 9
+
+
+class TapGemmF(C.Structure):
+    _fields_ = [
+        ("a0", _vp), ("a1", _vp), ("a0_c", C.c_int32), ("a1_c", C.c_int32),
+        ("a_rows", C.c_int32), ("a_halo", C.c_int32), ("a_dtype", C.c_int32),
+        ("w", _vp), ("w_dtype", C.c_int32), ("w_tap0", C.c_int32),
+        ("kc", C.c_int32), ("nc", C.c_int32), ("d_lo", C.c_int32), ("d_hi", C.c_int32),
+        ("tap_k_lo", I9), ("tap_k_hi", I9), ("tap_n_lo", I9), ("tap_n_hi", I9),
+        ("out", _vp), ("out_ld", C.c_int32), ("out_col0", C.c_int32),
+        ("out_dtype", C.c_int32), ("out_rows", C.c_int32), ("out_halo", C.c_int32),
+        ("m_lo", C.c_int32), ("m_hi", C.c_int32), ("n_lo", C.c_int32), ("n_hi", C.c_int32),
+        ("bias", _vp), ("bias_mod", C.c_int32), ("batch", C.c_int32), ("ksplit", C.c_int32),
+        ("backend", C.c_int32),
+    ]
+
+
+class TapGemmW(C.Structure):
+    _fields_ = [
+        ("g", _vp), ("g_rows", C.c_int32), ("g_dtype", C.c_int32),
+        ("a0", _vp), ("a1", _vp), ("a0_c", C.c_int32), ("a1_c", C.c_int32),
+        ("a_rows", C.c_int32), ("a_halo", C.c_int32), ("a_dtype", C.c_int32),
+        ("kc", C.c_int32), ("nc", C.c_int32), ("d_lo", C.c_int32), ("d_hi", C.c_int32),
+        ("tap_k_lo", I9), ("tap_k_hi", I9), ("tap_n_lo", I9), ("tap_n_hi", I9),
+        ("dw", _vp), ("dw_tap0", C.c_int32),
+        ("batch", C.c_int32), ("ksplit", C.c_int32), ("backend", C.c_int32),
+    ]
+
+
+# name -> argtypes (all return int status)
+_SIGS = {
+    "sg_tapgemm_f_run": [C.POINTER(TapGemmF), _vp],
+    "sg_tapgemm_w_run": [C.POINTER(TapGemmW), _vp],
+    "sg_pack_weights": [_i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp],
+    "sg_unpack_wgrad": [_i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp],
+    "sg_wave_conv_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
+    "sg_wave_conv_wgrad": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
+    "sg_wave_conv_dgrad": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp],
+    "sg_wave_deconv_fwd": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "sg_wave_deconv_bwd": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sg_bn_stats": [_vp, _i, _i64, _i, _vp, _vp],
+    "sg_bn_finalize": [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
+    "sg_act_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "sg_act_bwd_reduce": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "sg_act_bwd_apply": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
+    "sg_ncl_to_nlc": [_vp, _i, _i, _i, _vp, _i, _vp],
+    "sg_nlc_to_ncl": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "sg_colsum": [_vp, _i, _i64, _i, _i, _vp, _i, _vp, _vp],
+    "sg_fc_tail_fwd": [_vp] * 8 + [_i, _vp, _vp, _vp, _vp],
+    "sg_fc_tail_bwd": [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp] + [_vp] * 7 + [_vp],
+    "sg_l1_loss_bwd": [_vp, _vp, _i64, _f, _vp, _vp, _i, _vp],
+    "sg_rmsprop_step": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
+    "sg_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp],
+    "sg_deemphasis": [_vp, _i64, _f, _vp, _vp],
+    "sg_preemphasis": [_vp, _i64, _f, _vp, _vp],
+}
+EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok"] + list(_SIGS)
+
+_lib = None
+
+
+class SeganB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (building nothing: see segan_pytorch_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SeganB200Error(
+            "libsegan_b200.so not found at %s -- build it with `python -m segan_pytorch_b200.build` "
+            "(there is no fallback path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.sg_abi_version.restype = C.c_int
+    lib.sg_last_error.restype = C.c_char_p
+    lib.sg_device_ok.restype = C.c_int
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    if lib.sg_abi_version() != 1:
+        raise SeganB200Error("ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise SeganB200Error("%s failed (%d): %s" % (name, rc, lib.sg_last_error().decode(errors="replace")))
+
+
+def device_ok():
+    return bool(load().sg_device_ok())

@@ -115,8 +115,8 @@ act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
 
 // gradient w.r.t. the activation output at exact position l: gathers the consumer-view
 // gradient (rolled position + its reflect-halo mirrors) and the optional skip gradient
-__device__ __forceinline__ void gather_gy(const void* g_h, int H, int roll, const void* g_add, int b, int l, int L,
-                                          int C, int cg, float (&gy)[8]) {
+__device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int roll, const void* g_add, int lda, int b,
+                                          int l, int L, int cg, float (&gy)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) gy[j] = 0.f;
   if (g_h) {
@@ -125,24 +125,24 @@ __device__ __forceinline__ void gather_gy(const void* g_h, int H, int roll, cons
     if (q0 >= L) q0 -= L;
     if (q0 < 0) q0 += L;
     const int64_t base = (int64_t)b * Lh + H;
-    V8 v = ldv8(g_h, (base + q0) * C + cg * 8);
+    V8 v = ldv8(g_h, (base + q0) * ldh + cg * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
     if (H > 0) {
       if (q0 >= 1 && q0 <= 14) {
-        v = ldv8(g_h, (base - q0) * C + cg * 8);
+        v = ldv8(g_h, (base - q0) * ldh + cg * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
       }
       if (q0 >= L - 16 && q0 <= L - 2) {
-        v = ldv8(g_h, (base + 2 * (L - 1) - q0) * C + cg * 8);
+        v = ldv8(g_h, (base + 2 * (L - 1) - q0) * ldh + cg * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
       }
     }
   }
   if (g_add) {
-    const V8 v = ldv8(g_add, ((int64_t)b * L + l) * C + cg * 8);
+    const V8 v = ldv8(g_add, ((int64_t)b * L + l) * lda + cg * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
   }
@@ -152,7 +152,7 @@ __device__ __forceinline__ void gather_gy(const void* g_h, int H, int roll, cons
 // MODE 1: apply (BN backward) using the reductions
 template <int MODE>
 __global__ void __launch_bounds__(256)
-act_bwd_kernel(const void* __restrict__ g_h, int H, int roll, const void* __restrict__ g_add,
+act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const void* __restrict__ g_add, int lda,
                const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ mean_invstd,
                const float* __restrict__ slope, int act, double* __restrict__ red, int use_bn,
@@ -185,7 +185,7 @@ act_bwd_kernel(const void* __restrict__ g_h, int H, int roll, const void* __rest
   for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
     const int b = (int)(r / L), l = (int)(r % L);
     float gy[8];
-    gather_gy(g_h, H, roll, g_add, b, l, L, C, cg, gy);
+    gather_gy(g_h, ldh, H, roll, g_add, lda, b, l, L, cg, gy);
     const V8 av = ldv8(a, r * C + cg * 8);
     V8 o;
 #pragma unroll
@@ -321,14 +321,14 @@ fc_tail_fwd_kernel(const float* __restrict__ fc0_acc, const float* __restrict__ 
 // per-row backward: g_z2 [B][128] and g_z1 [B][256] (fp32 workspaces) + bf16 copy of g_z1
 __global__ void __launch_bounds__(256)
 fc_tail_bwd_rows_kernel(const float* __restrict__ z1, const float* __restrict__ z2, const float* __restrict__ logit,
-                        float target, float weight, const float* __restrict__ s1, const float* __restrict__ w2,
+                        const float* __restrict__ g_logit_in, float target, float weight, const float* __restrict__ s1, const float* __restrict__ w2,
                         const float* __restrict__ s3, const float* __restrict__ w4, int batch,
                         float* __restrict__ loss_out, float* __restrict__ g_logit_ws, float* __restrict__ g_z2_ws,
                         float* __restrict__ g_z1_ws, void* __restrict__ g_z1_bf16) {
   __shared__ float gz2[FC2];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float diff = logit[b] - target;
-  const float gl = 2.f * diff / (float)batch * weight;
+  const float gl = g_logit_in ? g_logit_in[b] : 2.f * diff / (float)batch * weight;
   if (tid == 0) {
     g_logit_ws[b] = gl;
     if (loss_out) atomicAdd(loss_out, diff * diff / (float)batch * weight);
@@ -472,27 +472,30 @@ extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, con
   return SG_OK;
 }
 
-extern "C" int sg_act_bwd_reduce(const void* g_h, int in_halo_pos, int roll, const void* g_add, const void* a,
+extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add,
+                                 int g_add_ld, const void* a,
                                  int dtype, int batch, int L, int C, const float* scale_shift,
                                  const float* mean_invstd, const float* slope, int act, double* red,
                                  void* g_a_out, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red);
   const int rpb = 256 / (C / 8);
   act_bwd_kernel<0><<<ew_grid((int64_t)batch * L, rpb * 8), 256, 0, ST>>>(
-      g_h, in_halo_pos, roll, g_add, a, dtype, batch, L, C, scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
+      g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
+      scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
 
-extern "C" int sg_act_bwd_apply(const void* g_h, int in_halo_pos, int roll, const void* g_add, const void* a,
+extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add,
+                                int g_add_ld, const void* a,
                                 int dtype, int batch, int L, int C, const float* scale_shift,
                                 const float* mean_invstd, const float* slope, int act, const double* red,
                                 int use_bn, void* g_a, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red && g_a);
   const int rpb = 256 / (C / 8);
   act_bwd_kernel<1><<<ew_grid((int64_t)batch * L, rpb * 8), 256, 0, ST>>>(
-      g_h, in_halo_pos, roll, g_add, a, dtype, batch, L, C, scale_shift, mean_invstd, slope, act,
-      const_cast<double*>(red), use_bn, g_a);
+      g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
+      scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -530,7 +533,8 @@ extern "C" int sg_fc_tail_fwd(const float* fc0_acc, const float* b0, const float
   return SG_OK;
 }
 
-extern "C" int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit, float target, float weight,
+extern "C" int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit, const float* g_logit_in,
+                              float target, float weight,
                               const float* s1, const float* w2, const float* s3, const float* w4, int batch,
                               float* loss_out, void* g_z1_bf16, float* ws /* [B*(1+128+256)] */, float* g_b0,
                               float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4, float* g_b4,
@@ -539,7 +543,7 @@ extern "C" int sg_fc_tail_bwd(const float* z1, const float* z2, const float* log
   float* g_logit = ws;
   float* g_z2 = ws + batch;
   float* g_z1 = g_z2 + (int64_t)batch * FC2;
-  fc_tail_bwd_rows_kernel<<<batch, 256, 0, ST>>>(z1, z2, logit, target, weight, s1, w2, s3, w4, batch, loss_out,
+  fc_tail_bwd_rows_kernel<<<batch, 256, 0, ST>>>(z1, z2, logit, g_logit_in, target, weight, s1, w2, s3, w4, batch, loss_out,
                                                  g_logit, g_z2, g_z1, g_z1_bf16);
   SG_CHECK_LAUNCH();
   if (g_w2) {

@@ -13,10 +13,10 @@ struct TapRanges {
 struct FParams {
   const void* a0; const void* a1;
   int a0_c, a1_c, a_rows, a_halo, a_dtype;
-  const void* w; int w_dtype;
+  const void* w; int w_dtype, w_tap0;
   int kc, nc, d_lo, d_hi;
   TapRanges tr;
-  void* out; int out_dtype, out_rows, out_halo;
+  void* out; int out_dtype, out_rows, out_halo, out_ld, out_col0;
   int m_lo, m_hi, n_lo, n_hi;
   const float* bias; int bias_mod;
   int batch, ksplit;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) tapgemm_f_ffma(FParams p) {
       }
       {
         const int n = n0 + lrow;
-        const int64_t base = ((int64_t)ti * p.nc + n) * p.kc + k0 + lk;
+        const int64_t base = ((int64_t)(ti - p.w_tap0) * p.nc + n) * p.kc + k0 + lk;
 #pragma unroll
         for (int j = 0; j < 4; ++j) Ws[lk + j][lrow] = ld16(p.w, base + j, p.w_dtype);
       }
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) tapgemm_f_ffma(FParams p) {
       const int n = n0 + tx * 4 + j;
       float v = acc[i][j];
       if (p.bias && ks == 0) v += p.bias[n % p.bias_mod];
-      const int64_t o = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.nc + n;
+      const int64_t o = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n - p.n_lo + p.out_col0);
       if (p.out_dtype == SG_F32) atomicAdd(reinterpret_cast<float*>(p.out) + o, v);
       else st16(p.out, o, v, p.out_dtype);
     }
@@ -105,7 +105,7 @@ struct WParams {
   int a0_c, a1_c, a_rows, a_halo, a_dtype;
   int kc, nc, d_lo, d_hi;
   TapRanges tr;
-  float* dw;
+  float* dw; int dw_tap0;
   int batch, ksplit;
 };
 
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) tapgemm_w_ffma(WParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + ty * 4 + i, kc = kc0 + tx * 4 + j;
-      atomicAdd(p.dw + ((int64_t)ti * p.nc + n) * p.kc + kc, acc[i][j]);
+      atomicAdd(p.dw + ((int64_t)(ti - p.dw_tap0) * p.nc + n) * p.kc + kc, acc[i][j]);
     }
 }
 
@@ -180,13 +180,15 @@ int tapgemm_f_ffma_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   FParams p;
   p.a0 = q->a0; p.a1 = q->a1; p.a0_c = q->a0_c; p.a1_c = q->a1_c;
   p.a_rows = q->a_rows; p.a_halo = q->a_halo; p.a_dtype = q->a_dtype;
-  p.w = q->w; p.w_dtype = q->w_dtype; p.kc = q->kc; p.nc = q->nc;
+  p.w = q->w; p.w_dtype = q->w_dtype; p.w_tap0 = q->w_tap0; p.kc = q->kc; p.nc = q->nc;
   p.d_lo = q->d_lo; p.d_hi = q->d_hi;
   for (int i = 0; i < NTAP; ++i) {
     p.tr.k_lo[i] = q->tap_k_lo[i]; p.tr.k_hi[i] = q->tap_k_hi[i];
     p.tr.n_lo[i] = q->tap_n_lo[i]; p.tr.n_hi[i] = q->tap_n_hi[i];
   }
   p.out = q->out; p.out_dtype = q->out_dtype; p.out_rows = q->out_rows; p.out_halo = q->out_halo;
+  p.out_ld = q->out_ld > 0 ? q->out_ld : q->nc;
+  p.out_col0 = q->out_ld > 0 ? q->out_col0 : q->n_lo;
   p.m_lo = q->m_lo; p.m_hi = q->m_hi; p.n_lo = q->n_lo; p.n_hi = q->n_hi;
   p.bias = q->bias; p.bias_mod = q->bias_mod > 0 ? q->bias_mod : q->nc;
   p.batch = q->batch; p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
@@ -207,7 +209,7 @@ int tapgemm_w_ffma_launch(const sg_tapgemm_w* q, cudaStream_t st) {
     p.tr.k_lo[i] = q->tap_k_lo[i]; p.tr.k_hi[i] = q->tap_k_hi[i];
     p.tr.n_lo[i] = q->tap_n_lo[i]; p.tr.n_hi[i] = q->tap_n_hi[i];
   }
-  p.dw = q->dw; p.batch = q->batch; p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
+  p.dw = q->dw; p.dw_tap0 = q->dw_tap0; p.batch = q->batch; p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
   dim3 grid(q->kc / TM, (q->nc / TNn) * (q->d_hi - q->d_lo + 1), p.ksplit);
   tapgemm_w_ffma<<<grid, 256, 0, st>>>(p);
   SG_CHECK_LAUNCH();

@@ -159,7 +159,8 @@ struct FTcParams {
   int a0_c, kc, nc, a_halo;
   int d_lo, d_hi;
   TapRangesTC tr;
-  void* out; int out_dtype, out_rows, out_halo;
+  void* out; int out_dtype, out_rows, out_halo, out_ld, out_col0;
+  int w_tap0;
   int m_lo, m_hi, n_lo;
   const float* bias; int bias_mod;
   int batch, ksplit;
@@ -229,7 +230,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
             if (k0 < p.a0_c) tma_load_3d(sa, &tmA0, &ctl->full[stage], k0, m0 + d + p.a_halo, b0);
             else tma_load_3d(sa, &tmA1, &ctl->full[stage], k0 - p.a0_c, m0 + d + p.a_halo, b0);
-            tma_load_2d(sb, &tmW, &ctl->full[stage], k0, ti * p.nc + n0);
+            tma_load_2d(sb, &tmW, &ctl->full[stage], k0, (ti - p.w_tap0) * p.nc + n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -295,7 +296,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
-      const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.nc + n0;
+      const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
       for (int c0 = 0; c0 < p.TN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
@@ -361,7 +362,7 @@ struct WTcParams {
   int a0_c, kc, nc, a_halo;
   int d_lo, d_hi;
   TapRangesTC tr;
-  float* dw;
+  float* dw; int dw_tap0;
   int g_rows, batch, ksplit;
   int PR, PB;                // K block = PB batches x PR rows = 64 positions
   int TK;                    // N tile (kc), <= 256
@@ -483,7 +484,7 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
-      float* o = p.dw + ((int64_t)(d + 4) * p.nc + n0 + row) * p.kc + kc0;
+      float* o = p.dw + ((int64_t)(d + 4 - p.dw_tap0) * p.nc + n0 + row) * p.kc + kc0;
       const int ti = d + 4;
       for (int c0 = 0; c0 < p.TK; c0 += 32) {
         uint32_t r[32];
@@ -588,6 +589,9 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     p.tr.n_lo[i] = q->tap_n_lo[i]; p.tr.n_hi[i] = q->tap_n_hi[i];
   }
   p.out = q->out; p.out_dtype = q->out_dtype; p.out_rows = q->out_rows; p.out_halo = q->out_halo;
+  p.out_ld = q->out_ld > 0 ? q->out_ld : q->nc;
+  p.out_col0 = q->out_ld > 0 ? q->out_col0 : q->n_lo;
+  p.w_tap0 = q->w_tap0;
   p.m_lo = q->m_lo; p.m_hi = q->m_hi; p.n_lo = q->n_lo;
   p.bias = q->bias; p.bias_mod = q->bias_mod > 0 ? q->bias_mod : q->nc;
   p.batch = q->batch; p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
@@ -607,7 +611,7 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   if (q->a1) rc = make_map3(&tmA1, q->a1, q->a_dtype, q->a1_c, a_buf_rows, q->batch, p.TR, p.TB);
   else tmA1 = tmA0;
   if (rc) return rc;
-  rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)NTAP * q->nc, p.TN);
+  rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)(q->d_hi + 4 - q->w_tap0 + 1) * q->nc, p.TN);
   if (rc) return rc;
   const int total = p.m_tiles_per_b * p.b_tiles * p.n_tiles * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
@@ -629,7 +633,7 @@ int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st) {
     p.tr.k_lo[i] = q->tap_k_lo[i]; p.tr.k_hi[i] = q->tap_k_hi[i];
     p.tr.n_lo[i] = q->tap_n_lo[i]; p.tr.n_hi[i] = q->tap_n_hi[i];
   }
-  p.dw = q->dw; p.g_rows = q->g_rows; p.batch = q->batch;
+  p.dw = q->dw; p.dw_tap0 = q->dw_tap0; p.g_rows = q->g_rows; p.batch = q->batch;
   p.PR = q->g_rows >= 64 ? 64 : q->g_rows;
   p.PB = 64 / p.PR;
   p.TK = q->kc >= 256 ? 256 : q->kc;

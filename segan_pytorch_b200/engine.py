@@ -1,0 +1,639 @@
+"""Host-side orchestration of the B200 kernels for the SEGAN+ Generator and Discriminator.
+
+PyTorch is used for device memory (caching allocator), streams and parameter storage only; every
+FLOP of the hot path runs in libsegan_b200.so through the C ABI (segan_pytorch_b200._lib).
+
+Layer geometry follows the reference (file:line into /root/reference):
+  encoder block  = reflect-pad(14,15) -> Conv1d(k31,s4) -> [BatchNorm1d] -> PReLU   segan/models/modules.py:91-105
+  decoder block  = ConvTranspose1d(k31,s4,p13)[:-1] -> PReLU | Tanh                 segan/models/modules.py:135-141
+  G wiring       = 5 enc -> cat(z, h) -> 5 x (cat(h, alpha*skip), dec)              segan/models/generator.py:180-230
+  D wiring       = 5 x (phase shift, enc with BN) -> FC 16384-256-128-1             segan/models/discriminator.py:150-194
+
+HBM layouts are described in include/segan_b200.h and DESIGN.md.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_PRELU, BACKEND_FFMA, BACKEND_TCGEN05, SG_BF16, SG_F16, SG_F32,
+                   TapGemmF, TapGemmW)
+
+KW = 31
+
+
+def default_backend():
+    v = os.environ.get("SEGAN_B200_BACKEND", "tcgen05").lower()
+    return BACKEND_FFMA if v in ("ffma", "ref", "0") else BACKEND_TCGEN05
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SeganB200Error(
+                "segan_pytorch_b200 runs on B200 GPUs only: got a CPU tensor (there is no CPU path; "
+                "the CPU restatement under oracle/ is test infrastructure)")
+
+
+# --------------------------------------------------------------------------------------------
+# structural-zero tap ranges of the four packed weight layouts
+# --------------------------------------------------------------------------------------------
+def tap_ranges(kind, c, kc, nc):
+    """kind: conv_fwd | conv_dgrad | deconv_fwd | deconv_dgrad | full ; c = the channel count whose
+    four stride phases are interleaved (Cin for conv, Cout for deconv)."""
+    k_lo, k_hi, n_lo, n_hi = [0] * 9, [kc] * 9, [0] * 9, [nc] * 9
+    if kind == "conv_fwd":        # K = (p, ci): d=-4 -> p in {2,3}; d=+4 -> p = 0
+        k_lo[0], k_hi[0] = 2 * c, 4 * c
+        k_lo[8], k_hi[8] = 0, c
+    elif kind == "conv_dgrad":    # N = (p, ci): d=-4 -> p = 0; d=+4 -> p in {2,3}
+        n_lo[0], n_hi[0] = 0, c
+        n_lo[8], n_hi[8] = 2 * c, 4 * c
+    elif kind == "deconv_fwd":    # N = (r, co): d=-4 -> r in {0,1}; d=+4 -> r = 3
+        n_lo[0], n_hi[0] = 0, 2 * c
+        n_lo[8], n_hi[8] = 3 * c, 4 * c
+    elif kind == "deconv_dgrad":  # K = (r, co): d=-4 -> r = 3; d=+4 -> r in {0,1}
+        k_lo[0], k_hi[0] = 3 * c, 4 * c
+        k_lo[8], k_hi[8] = 0, 2 * c
+    elif kind != "full":
+        raise ValueError(kind)
+    return k_lo, k_hi, n_lo, n_hi
+
+
+def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dtype, out_rows, out_halo,
+          m_lo, m_hi, batch, bias=None, bias_mod=0, n_lo=0, n_hi=None, d_lo=-4, d_hi=4, w_tap0=0,
+          out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0):
+    q = TapGemmF()
+    q.a0, q.a1 = _p(a0), _p(a1)
+    q.a0_c = kc if a0_c is None else a0_c
+    q.a1_c = a1_c
+    q.a_rows, q.a_halo, q.a_dtype = a_rows, a_halo, a_dtype
+    q.w, q.w_dtype, q.w_tap0 = _p(w), w_dtype, w_tap0
+    q.kc, q.nc, q.d_lo, q.d_hi = kc, nc, d_lo, d_hi
+    for i in range(9):
+        q.tap_k_lo[i], q.tap_k_hi[i], q.tap_n_lo[i], q.tap_n_hi[i] = taps[0][i], taps[1][i], taps[2][i], taps[3][i]
+    q.out, q.out_ld, q.out_col0 = _p(out), out_ld, out_col0
+    q.out_dtype, q.out_rows, q.out_halo = out_dtype, out_rows, out_halo
+    q.m_lo, q.m_hi, q.n_lo, q.n_hi = m_lo, m_hi, n_lo, (nc if n_hi is None else n_hi)
+    q.bias, q.bias_mod = _p(bias), bias_mod
+    q.batch, q.ksplit = batch, ksplit
+    q.backend = default_backend() if backend is None else backend
+    _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
+
+
+def run_w(g, g_rows, g_dtype, a0, a1, a_rows, a_halo, a_dtype, kc, nc, taps, dw, batch, d_lo=-4, d_hi=4,
+          dw_tap0=0, ksplit=1, backend=None, a0_c=None, a1_c=0):
+    q = TapGemmW()
+    q.g, q.g_rows, q.g_dtype = _p(g), g_rows, g_dtype
+    q.a0, q.a1 = _p(a0), _p(a1)
+    q.a0_c = kc if a0_c is None else a0_c
+    q.a1_c = a1_c
+    q.a_rows, q.a_halo, q.a_dtype = a_rows, a_halo, a_dtype
+    q.kc, q.nc, q.d_lo, q.d_hi = kc, nc, d_lo, d_hi
+    for i in range(9):
+        q.tap_k_lo[i], q.tap_k_hi[i], q.tap_n_lo[i], q.tap_n_hi[i] = taps[0][i], taps[1][i], taps[2][i], taps[3][i]
+    q.dw, q.dw_tap0 = _p(dw), dw_tap0
+    q.batch, q.ksplit = batch, ksplit
+    q.backend = default_backend() if backend is None else backend
+    _lib.call("sg_tapgemm_w_run", C.byref(q), _stream())
+
+
+def wgrad_ksplit(total_positions, n_tiles):
+    """Position-range splits so that a weight-gradient tap-GEMM fills ~2 waves of 148 SMs."""
+    steps = max(1, total_positions // 64)
+    want = max(1, (2 * 148 + n_tiles - 1) // max(1, n_tiles))
+    return int(max(1, min(want, steps)))
+
+
+class _Buffers:
+    """Named device buffers, reused across steps (keyed by name; re-allocated on shape change)."""
+
+    def __init__(self):
+        self.t = {}
+
+    def get(self, name, shape, dtype, device, zero=False):
+        cur = self.t.get(name)
+        shape = tuple(int(s) for s in shape)
+        if cur is None or tuple(cur.shape) != shape or cur.dtype != dtype or cur.device != device:
+            cur = torch.empty(shape, dtype=dtype, device=device)
+            self.t[name] = cur
+            if not zero:
+                cur.zero_()       # never expose uninitialised halos
+        if zero:
+            cur.zero_()
+        return cur
+
+
+F16, BF16, F32, F64 = torch.float16, torch.bfloat16, torch.float32, torch.float64
+
+
+def flatten_params(module):
+    """Re-points every parameter of `module` at a slice of one flat fp32 buffer (and the same for
+    gradients) so that the optimiser, the NCCL all-reduce and the weight-gradient kernels see one
+    contiguous bucket.  Safe to call again after .to(device)."""
+    params = [p for p in module.parameters(recurse=True)]
+    if not params:
+        return None, None, {}
+    dev = params[0].device
+    total = sum(p.numel() for p in params)
+    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    grad = torch.zeros(total, dtype=torch.float32, device=dev)
+    off = 0
+    index = {}
+    for name, p in module.named_parameters():
+        n = p.numel()
+        flat[off:off + n].copy_(p.data.reshape(-1))
+        p.data = flat[off:off + n].view(p.shape)
+        p.grad = None
+        index[name] = (off, n, tuple(p.shape))
+        off += n
+    return flat, grad, index
+
+
+class _NetEngine:
+    """Shared machinery: flat parameter / gradient buckets and lazily re-packed 16-bit weights."""
+
+    def __init__(self, module):
+        self.module = module
+        self.flat = None
+        self.grad = None
+        self.index = {}
+        self.buf = _Buffers()
+        self._packed_version = None
+        self.backend = None
+
+    # -- parameters -------------------------------------------------------------------------
+    def bind(self):
+        ps = list(self.module.named_parameters())
+        dev = ps[0][1].device
+        ok = self.flat is not None and self.flat.device == dev
+        if ok:
+            for name, p in ps:
+                off, n, _ = self.index[name]
+                if p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                    ok = False
+                    break
+        if not ok:
+            self.flat, self.grad, self.index = flatten_params(self.module)
+            self._packed_version = None
+        return self
+
+    def pview(self, name):
+        off, n, shape = self.index[name]
+        return self.flat[off:off + n].view(shape)
+
+    def gview(self, name):
+        off, n, shape = self.index[name]
+        return self.grad[off:off + n].view(shape)
+
+    def _version(self):
+        return tuple(p._version for p in self.module.parameters()) + (self.flat.data_ptr(),)
+
+    def mark_dirty(self):
+        self._packed_version = None
+
+    def ensure_packed(self):
+        self.bind()
+        v = self._version()
+        if v != self._packed_version:
+            self.pack()
+            self._packed_version = self._version()
+
+    def export_grads(self):
+        """Copies the flat gradient bucket into per-parameter .grad tensors (API compatibility)."""
+        for name, p in self.module.named_parameters():
+            if p.requires_grad:
+                g = self.gview(name)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+
+
+# ============================================================================================
+# Generator
+# ============================================================================================
+class GeneratorEngine(_NetEngine):
+    def __init__(self, module):
+        super().__init__(module)
+        m = module
+        self.fmaps = list(m.enc_fmaps)
+        self.nl = len(self.fmaps)
+        self.enc_bias = m.bias
+        self.packed = {}
+
+    # -- weights ----------------------------------------------------------------------------
+    def pack(self):
+        dev = self.flat.device
+        fm = self.fmaps
+        st = _stream()
+        for l in range(1, self.nl):
+            cin, cout = fm[l - 1], fm[l]
+            wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
+            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), BF16, dev)
+            _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
+                      None, 0, _p(wf), _p(wd), SG_F16, SG_BF16, st)
+            self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
+        for l in range(self.nl - 1):
+            cin = self.dec_cin(l)
+            cout = self.dec_cout(l)
+            w = self.pview("dec_blocks.%d.deconv.weight" % l)
+            alpha = self.alpha_for_dec(l)
+            wt = self.buf.get("Wt%d" % l, (9, 4 * cout, cin), F16, dev)
+            wtd = self.buf.get("Wtd%d" % l, (9, cin, 4 * cout), BF16, dev)
+            _lib.call("sg_pack_weights", 1, _p(w), cout, cin, 0, _p(alpha), cin // 2,
+                      _p(wt), _p(wtd), SG_F16, SG_BF16, st)
+            self.packed["Wt%d" % l], self.packed["Wtd%d" % l] = wt, wtd
+        # last decoder layer (Cout = 1): fp32 [cin][31] with alpha folded (tiny: torch ops)
+        l = self.nl - 1
+        w = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
+        alpha = self.alpha_for_dec(l)
+        half = w.shape[0] // 2
+        weff = w.clone()
+        weff[half:] = weff[half:] * alpha.view(-1, 1)
+        self.packed["w_last_eff"] = weff.contiguous()
+
+    def dwp_elems(self):
+        fm, nl = self.fmaps, self.nl
+        sizes = [9 * 4 * self.dec_cout(l) * self.dec_cin(l) for l in range(nl - 1)]
+        sizes += [9 * fm[l] * 4 * fm[l - 1] for l in range(1, nl)]
+        return max(sizes)
+
+    def dec_cin(self, l):
+        return 2 * self.fmaps[-1] if l == 0 else 2 * self.fmaps[self.nl - 1 - l]
+
+    def dec_cout(self, l):
+        return self.fmaps[self.nl - 2 - l] if l < self.nl - 1 else 1
+
+    def alpha_for_dec(self, l):
+        """alpha of the skip merged before decoder block l (None for block 0: cat(z, h))."""
+        if l == 0:
+            return None
+        return self.pview("alpha_%d.skip_k" % (self.nl - 1 - l)).reshape(-1)
+
+    # -- forward ----------------------------------------------------------------------------
+    def forward(self, x, z, want_ctx=True, fresh=False):
+        """x: (B,1,L) fp32 cuda, z: (B, C4, L/1024) fp32 cuda.  Returns y (B,1,L) fp32.
+        fresh=True gives the saved activations their own storage (generic autograd use, where several
+        forwards may precede a backward); the fused train step reuses one persistent workspace."""
+        _require_cuda(x, z)
+        self.ensure_packed()
+        B, _, L = x.shape
+        fm, nl, dev, st = self.fmaps, self.nl, x.device, _stream()
+        buf = _Buffers() if fresh else self.buf
+        assert L % (4 ** nl) == 0 and L // (4 ** nl) >= 1 and L >= 4096, "window length must be a multiple of 1024, >= 4096"
+        x = x.contiguous().float()
+        Lq = [L // 4 ** (l + 1) for l in range(nl)]
+        a, hp = [None] * nl, [None] * nl
+        # ---- encoder
+        a[0] = buf.get("g.a0", (B, Lq[0], fm[0]), F16, dev)
+        hp[0] = buf.get("g.hp0", (B, Lq[0] + 32, fm[0]), F16, dev)
+        bias0 = self.pview("enc_blocks.0.conv.bias") if self.enc_bias else None
+        _lib.call("sg_wave_conv_fwd", _p(x), None, 1, B, L, 0, _p(self.pview("enc_blocks.0.conv.weight")),
+                  _p(bias0), fm[0], _p(a[0]), _p(self.pview("enc_blocks.0.act.weight")), _p(hp[0]), st)
+        for l in range(1, nl):
+            cin, cout = fm[l - 1], fm[l]
+            a[l] = buf.get("g.a%d" % l, (B, Lq[l], cout), F16, dev)
+            bias = self.pview("enc_blocks.%d.conv.bias" % l) if self.enc_bias else None
+            run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
+                  tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
+                  bias=bias, bias_mod=cout, backend=self.backend)
+            halo = 16 if l < nl - 1 else 0
+            hp[l] = buf.get("g.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
+            _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, None,
+                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, 0, halo, _p(hp[l]), st)
+        # ---- z
+        zc = z.shape[1]
+        z16 = buf.get("g.z16", (B, Lq[-1], zc), F16, dev)
+        _lib.call("sg_ncl_to_nlc", _p(z.contiguous().float()), B, zc, Lq[-1], _p(z16), SG_F16, st)
+        # ---- decoder
+        ad, dd = [None] * nl, [None] * nl
+        src0, src1 = z16, hp[nl - 1]
+        lin = Lq[-1]
+        for l in range(nl - 1):
+            cin, cout = self.dec_cin(l), self.dec_cout(l)
+            assert src0.shape[-1] + src1.shape[-1] == cin
+            ad[l] = buf.get("g.ad%d" % l, (B, lin, 4 * cout), F16, dev)
+            run_f(src0, src1, lin, 0, SG_F16, self.packed["Wt%d" % l], SG_F16, cin, 4 * cout,
+                  tap_ranges("deconv_fwd", cout, cin, 4 * cout), ad[l], SG_F16, lin, 0, 0, lin, B,
+                  bias=self.pview("dec_blocks.%d.deconv.bias" % l), bias_mod=cout,
+                  a0_c=src0.shape[-1], a1_c=src1.shape[-1], backend=self.backend)
+            dd[l] = buf.get("g.dd%d" % l, (B, 4 * lin, cout), F16, dev)
+            _lib.call("sg_act_fwd", _p(ad[l]), SG_F16, B, 4 * lin, cout, None,
+                      _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, 0, _p(dd[l]), st)
+            lin *= 4
+            src0, src1 = dd[l], a[nl - 2 - l]
+        y = torch.empty(B, 1, L, dtype=F32, device=dev)
+        _lib.call("sg_wave_deconv_fwd", _p(src0), src0.shape[-1], _p(src1), src1.shape[-1], B, lin,
+                  _p(self.packed["w_last_eff"]), _p(self.pview("dec_blocks.%d.deconv.bias" % (nl - 1))),
+                  _p(y), st)
+        ctx = dict(x=x, B=B, L=L, Lq=Lq, a=a, hp=hp, z16=z16, ad=ad, dd=dd, y=y) if want_ctx else None
+        return y, ctx
+
+    def hidden_ncl(self, ctx):
+        """`hall` of generator.py:186-227 as fp32 NCL tensors (inspection path)."""
+        nl, st = self.nl, _stream()
+        B, Lq = ctx["B"], ctx["Lq"]
+        hall = {}
+
+        def to_ncl(t16, C_, L_):
+            out = torch.empty(B, C_, L_, dtype=F32, device=t16.device)
+            _lib.call("sg_nlc_to_ncl", _p(t16), SG_F16, B, C_, L_, _p(out), st)
+            return out
+        for l in range(nl):
+            a = to_ncl(ctx["a"][l], self.fmaps[l], Lq[l])
+            hall["enc_%d" % l] = torch.nn.functional.prelu(a, self.pview("enc_blocks.%d.act.weight" % l))
+        zc = ctx["z16"].shape[-1]
+        hall["enc_zc"] = torch.cat((to_ncl(ctx["z16"], zc, Lq[-1]), hall["enc_%d" % (nl - 1)]), 1)
+        lin = Lq[-1]
+        for l in range(nl - 1):
+            hall["dec_%d" % l] = to_ncl(ctx["dd"][l], self.dec_cout(l), 4 * lin)
+            lin *= 4
+        hall["dec_%d" % (nl - 1)] = ctx["y"]
+        return hall
+
+    # -- backward ---------------------------------------------------------------------------
+    def backward(self, ctx, gy, accumulate=False):
+        """gy: (B,1,L) fp32 gradient w.r.t. the output.  Fills self.grad (flat, reference layout)."""
+        fm, nl, st, buf = self.fmaps, self.nl, _stream(), self.buf
+        B, L, Lq = ctx["B"], ctx["L"], ctx["Lq"]
+        a, hp, ad, dd = ctx["a"], ctx["hp"], ctx["ad"], ctx["dd"]
+        dev = gy.device
+        gy = gy.contiguous().float()
+        if not accumulate:
+            self.grad.zero_()
+        dwp_all = buf.get("g.dwp", (self.dwp_elems(),), F32, dev)
+        # ---- last decoder block (tanh, Cout = 1)
+        l = nl - 1
+        lin = Lq[0]
+        cin = self.dec_cin(l)
+        half = cin // 2
+        g_in = buf.get("g.gin%d" % l, (B, lin, cin), BF16, dev)
+        gpre = buf.get("g.gpre", (B, L), F32, dev)
+        dweff = buf.get("g.dweff", (cin, KW), F32, dev, zero=True)
+        gb = self.gview("dec_blocks.%d.deconv.bias" % l)
+        src0 = dd[l - 1]
+        src1 = a[0]
+        _lib.call("sg_wave_deconv_bwd", _p(src0), half, _p(src1), half, B, lin, _p(self.packed["w_last_eff"]),
+                  _p(gy), _p(ctx["y"]), _p(gpre), _p(g_in), _p(dweff), _p(gb), st)
+        w_last = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
+        alpha = self.alpha_for_dec(l)
+        gw = self.gview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
+        gw[:half] += dweff[:half]
+        gw[half:] += dweff[half:] * alpha.view(-1, 1)
+        self.gview("alpha_0.skip_k").view(-1).add_((dweff[half:] * w_last[half:]).sum(1))
+        # ---- decoder blocks nl-2 .. 0
+        g_next = g_in            # gradient w.r.t. cat(dd[l-1], alpha*a_skip) of block l
+        for l in range(nl - 2, -1, -1):
+            cin, cout = self.dec_cin(l), self.dec_cout(l)
+            lin = Lq[nl - 1 - l]
+            cnext = g_next.shape[-1]
+            # PReLU backward on [B, 4*lin, cout]
+            g_ad = buf.get("g.gad%d" % l, (B, lin, 4 * cout), BF16, dev)
+            red = buf.get("g.redd%d" % l, (3, cout), F64, dev, zero=True)
+            _lib.call("sg_act_bwd_reduce", _p(g_next), cnext, 0, 0, None, 0, _p(ad[l]), SG_F16, B, 4 * lin, cout,
+                      None, None, _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, _p(red), _p(g_ad), st)
+            self.gview("dec_blocks.%d.act.weight" % l).add_(red[0].float())
+            self.gview("dec_blocks.%d.deconv.bias" % l).add_(red[1].float())
+            if l == 0:
+                s0, s1 = ctx["z16"], hp[nl - 1]
+            else:
+                s0, s1 = dd[l - 1], a[nl - 1 - l]
+            c0, c1 = s0.shape[-1], s1.shape[-1]
+            taps = tap_ranges("deconv_fwd", cout, cin, 4 * cout)
+            dwp = dwp_all[:9 * 4 * cout * cin]
+            dwp.zero_()
+            n_tiles = 9 * (4 * cout // 128) * max(1, cin // 256)
+            run_w(g_ad, lin, SG_BF16, s0, s1, lin, 0, SG_F16, cin, 4 * cout, taps, dwp, B,
+                  ksplit=wgrad_ksplit(B * lin, n_tiles), a0_c=c0, a1_c=c1, backend=self.backend)
+            alpha = self.alpha_for_dec(l)
+            galpha = self.gview("alpha_%d.skip_k" % (nl - 1 - l)).view(-1) if l > 0 else None
+            _lib.call("sg_unpack_wgrad", 1, _p(dwp), cout, cin, 0, _p(self.pview("dec_blocks.%d.deconv.weight" % l)),
+                      _p(alpha), cin // 2, _p(self.gview("dec_blocks.%d.deconv.weight" % l)), _p(galpha), 1, st)
+            # data gradient w.r.t. cat(s0, s1); block 0 only needs the encoder half (z gets no gradient)
+            g_in = buf.get("g.gin%d" % l, (B, lin, cin), BF16, dev)
+            run_f(g_ad, None, lin, 0, SG_BF16, self.packed["Wtd%d" % l], SG_BF16, 4 * cout, cin,
+                  tap_ranges("deconv_dgrad", cout, 4 * cout, cin), g_in, SG_BF16, lin, 0, 0, lin, B,
+                  n_lo=(cin // 2 if l == 0 else 0), n_hi=cin, backend=self.backend)
+            g_next = g_in
+        # ---- encoder blocks nl-1 .. 0
+        g_hp = None
+        for l in range(nl - 1, -1, -1):
+            cout = fm[l]
+            g_a = buf.get("g.ga%d" % l, (B, Lq[l], cout), BF16, dev)
+            red = buf.get("g.rede%d" % l, (3, cout), F64, dev, zero=True)
+            slope = self.pview("enc_blocks.%d.act.weight" % l)
+            if l == nl - 1:
+                gin0 = buf.t["g.gin0"]
+                gh_ptr = C.c_void_p(gin0.data_ptr() + 2 * (gin0.shape[-1] // 2))
+                _lib.call("sg_act_bwd_reduce", gh_ptr, gin0.shape[-1], 0, 0, None, 0, _p(a[l]), SG_F16, B, Lq[l],
+                          cout, None, None, _p(slope), ACT_PRELU, _p(red), _p(g_a), st)
+            else:
+                gsk = buf.t["g.gin%d" % (nl - 1 - l)]
+                gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * (gsk.shape[-1] // 2))
+                _lib.call("sg_act_bwd_reduce", _p(g_hp), cout, 16, 0, gadd_ptr, gsk.shape[-1], _p(a[l]), SG_F16,
+                          B, Lq[l], cout, None, None, _p(slope), ACT_PRELU, _p(red), _p(g_a), st)
+            self.gview("enc_blocks.%d.act.weight" % l).add_(red[0].float())
+            if self.enc_bias:
+                self.gview("enc_blocks.%d.conv.bias" % l).add_(red[1].float())
+            if l == 0:
+                _lib.call("sg_wave_conv_wgrad", _p(ctx["x"]), None, 1, B, L, 0, _p(g_a), cout,
+                          _p(self.gview("enc_blocks.0.conv.weight")), None, st)
+                break
+            cin = fm[l - 1]
+            taps = tap_ranges("conv_fwd", cin, 4 * cin, cout)
+            dwp_l = dwp_all[:9 * cout * 4 * cin]
+            dwp_l.zero_()
+            n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
+            run_w(g_a, Lq[l], SG_BF16, hp[l - 1], None, Lq[l], 4, SG_F16, 4 * cin, cout, taps, dwp_l, B,
+                  ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
+            _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
+                      _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, st)
+            g_hp = buf.get("g.ghp%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
+            run_f(g_a, None, Lq[l], 0, SG_BF16, self.packed["Wdg%d" % l], SG_BF16, cout, 4 * cin,
+                  tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_hp, SG_BF16, Lq[l], 4, -4, Lq[l] + 4, B,
+                  backend=self.backend)
+        return self.grad
+
+
+# ============================================================================================
+# Discriminator
+# ============================================================================================
+class DiscriminatorEngine(_NetEngine):
+    def __init__(self, module):
+        super().__init__(module)
+        self.fmaps = list(module.fmaps)
+        self.nl = len(self.fmaps)
+        self.packed = {}
+        self.eps = 1e-5
+        self.momentum = 0.1
+
+    def pack(self):
+        dev, fm, st = self.flat.device, self.fmaps, _stream()
+        for l in range(1, self.nl):
+            cin, cout = fm[l - 1], fm[l]
+            wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
+            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), BF16, dev)
+            _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
+                      None, 0, _p(wf), _p(wd), SG_F16, SG_BF16, st)
+            self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
+        w1 = self.pview("fc.0.weight")
+        nout, kin = w1.shape
+        C_ = fm[-1]
+        T = kin // C_
+        w1p = self.buf.get("W1p", (nout, kin), F16, dev)
+        w1d = self.buf.get("W1dg", (kin, nout), BF16, dev)
+        _lib.call("sg_pack_weights", 2, _p(w1), nout, C_, T, None, 0, _p(w1p), _p(w1d), SG_F16, SG_BF16, st)
+        self.packed["W1p"], self.packed["W1dg"] = w1p, w1d
+
+    def forward(self, x0, x1, shifts, training=True, fresh=False):
+        """x0: candidate (B,1,L), x1: reference/noisy (B,1,L) -- the reference's cat((x_, ref), 1)
+        (model.py:173-175) is never materialised.  shifts: nl signed phase shifts."""
+        _require_cuda(x0, x1)
+        self.ensure_packed()
+        m = self.module
+        B, _, L = x0.shape
+        fm, nl, dev, st = self.fmaps, self.nl, x0.device, _stream()
+        buf = _Buffers() if fresh else self.buf
+        x0 = x0.contiguous().float()
+        x1 = x1.contiguous().float()
+        Lq = [L // 4 ** (l + 1) for l in range(nl)]
+        assert Lq[-1] * fm[-1] == self.pview("fc.0.weight").shape[1], "D expects L = 16384"
+        a, hp, ss, mi = [None] * nl, [None] * nl, [None] * nl, [None] * nl
+        for l in range(nl):
+            cout = fm[l]
+            a[l] = buf.get("d.a%d" % l, (B, Lq[l], cout), F16, dev)
+            bias = self.pview("enc_blocks.%d.conv.bias" % l) if m.bias else None
+            if l == 0:
+                _lib.call("sg_wave_conv_fwd", _p(x0), _p(x1), 2, B, L, int(shifts[0]),
+                          _p(self.pview("enc_blocks.0.conv.weight")), _p(bias), cout, _p(a[0]), None, None, st)
+            else:
+                cin = fm[l - 1]
+                run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
+                      tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
+                      bias=bias, bias_mod=cout, backend=self.backend)
+            bn = m.enc_blocks[l].norm
+            ss[l] = buf.get("d.ss%d" % l, (2, cout), F32, dev)
+            mi[l] = buf.get("d.mi%d" % l, (2, cout), F32, dev)
+            if training:
+                st2 = buf.get("d.stats%d" % l, (2, cout), F64, dev, zero=True)
+                _lib.call("sg_bn_stats", _p(a[l]), SG_F16, B * Lq[l], cout, _p(st2), st)
+                _lib.call("sg_bn_finalize", _p(st2), B * Lq[l], cout,
+                          _p(self.pview("enc_blocks.%d.norm.weight" % l)),
+                          _p(self.pview("enc_blocks.%d.norm.bias" % l)), self.eps, self.momentum,
+                          _p(bn.running_mean), _p(bn.running_var), _p(ss[l]), _p(mi[l]), st)
+                bn.num_batches_tracked += 1
+            else:
+                invstd = torch.rsqrt(bn.running_var + self.eps)
+                sc = self.pview("enc_blocks.%d.norm.weight" % l) * invstd
+                ss[l][0].copy_(sc)
+                ss[l][1].copy_(self.pview("enc_blocks.%d.norm.bias" % l) - bn.running_mean * sc)
+                mi[l][0].copy_(bn.running_mean)
+                mi[l][1].copy_(invstd)
+            halo = 16 if l < nl - 1 else 0
+            roll = int(shifts[l + 1]) if l < nl - 1 else 0
+            hp[l] = buf.get("d.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
+            _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, _p(ss[l]),
+                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, roll, halo, _p(hp[l]), st)
+        # ---- FC head
+        kin = Lq[-1] * fm[-1]
+        acc = buf.get("d.fc0", (B, 256), F32, dev, zero=True)
+        run_f(hp[-1], None, 1, 0, SG_F16, self.packed["W1p"], SG_F16, kin, 256,
+              tap_ranges("full", 0, kin, 256), acc, SG_F32, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4,
+              ksplit=16, backend=self.backend)
+        z1 = buf.get("d.z1", (B, 256), F32, dev)
+        z2 = buf.get("d.z2", (B, 128), F32, dev)
+        logit = torch.empty(B, 1, dtype=F32, device=dev)
+        _lib.call("sg_fc_tail_fwd", _p(acc), _p(self.pview("fc.0.bias")), _p(self.pview("fc.1.weight")),
+                  _p(self.pview("fc.2.weight")), _p(self.pview("fc.2.bias")), _p(self.pview("fc.3.weight")),
+                  _p(self.pview("fc.4.weight")), _p(self.pview("fc.4.bias")), B, _p(z1), _p(z2), _p(logit), st)
+        ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, ss=ss, mi=mi, z1=z1, z2=z2, logit=logit,
+                   shifts=[int(s) for s in shifts])
+        return logit, ctx
+
+    def backward(self, ctx, target, weight=1.0, param_grads=True, input_grad=None, loss_out=None, g_logit=None,
+                 input_grad1=None):
+        """Backward of  weight * mean((logit - target)^2)  (nn.MSELoss, model.py:298,305,316).
+        param_grads: accumulate parameter gradients into self.grad (D steps) or skip them (G step).
+        input_grad: optional fp32 (B,1,L) buffer that receives (+=) the gradient w.r.t. x0."""
+        m = self.module
+        fm, nl, st, buf = self.fmaps, self.nl, _stream(), self.buf
+        B, L, Lq = ctx["B"], ctx["L"], ctx["Lq"]
+        a, hp, ss, mi, shifts = ctx["a"], ctx["hp"], ctx["ss"], ctx["mi"], ctx["shifts"]
+        dev = ctx["x0"].device
+        kin = Lq[-1] * fm[-1]
+        g_z1 = buf.get("d.gz1", (B, 256), BF16, dev)
+        ws = buf.get("d.fcws", (B * (1 + 128 + 256),), F32, dev)
+        gv = (lambda n: _p(self.gview(n))) if param_grads else (lambda n: None)
+        _lib.call("sg_fc_tail_bwd", _p(ctx["z1"]), _p(ctx["z2"]), _p(ctx["logit"]), _p(g_logit), float(target),
+                  float(weight),
+                  _p(self.pview("fc.1.weight")), _p(self.pview("fc.2.weight")), _p(self.pview("fc.3.weight")),
+                  _p(self.pview("fc.4.weight")), B, _p(loss_out), _p(g_z1), _p(ws),
+                  gv("fc.0.bias"), gv("fc.1.weight"), gv("fc.2.weight"), gv("fc.2.bias"), gv("fc.3.weight"),
+                  gv("fc.4.weight"), gv("fc.4.bias"), st)
+        if param_grads:
+            dwp = buf.get("d.dwp", (9 * 4 * fm[-2] * fm[-1],), F32, dev)
+            dw1 = dwp[:256 * kin]
+            dw1.zero_()
+            run_w(g_z1, 1, SG_BF16, hp[-1], None, 1, 0, SG_F16, kin, 256, tap_ranges("full", 0, kin, 256), dw1, B,
+                  d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
+            _lib.call("sg_unpack_wgrad", 2, _p(dw1), 256, fm[-1], Lq[-1], None, None, 0,
+                      _p(self.gview("fc.0.weight")), None, 1, st)
+        g_h = buf.get("d.gh%d" % (nl - 1), (B, Lq[-1], fm[-1]), BF16, dev)
+        run_f(g_z1, None, 1, 0, SG_BF16, self.packed["W1dg"], SG_BF16, 256, kin, tap_ranges("full", 0, 256, kin),
+              g_h, SG_BF16, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+        red = buf.get("d.red", (3, 2048), F64, dev)
+        tmp = buf.get("d.cstmp", (2048,), F64, dev)
+        for l in range(nl - 1, -1, -1):
+            cout = fm[l]
+            halo = 16 if l < nl - 1 else 0
+            roll = shifts[l + 1] if l < nl - 1 else 0
+            g_a = buf.get("d.ga%d" % l, (B, Lq[l], cout), BF16, dev)
+            redl = buf.get("d.red%d" % l, (3, cout), F64, dev, zero=True)
+            slope = self.pview("enc_blocks.%d.act.weight" % l)
+            _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
+                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
+            _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
+                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
+            if param_grads:
+                self.gview("enc_blocks.%d.act.weight" % l).add_(redl[0].float())
+                self.gview("enc_blocks.%d.norm.bias" % l).add_(redl[1].float())
+                self.gview("enc_blocks.%d.norm.weight" % l).add_(redl[2].float())
+                if m.bias:
+                    _lib.call("sg_colsum", _p(g_a), SG_BF16, B * Lq[l], cout, cout,
+                              _p(self.gview("enc_blocks.%d.conv.bias" % l)), 1, _p(tmp), st)
+            if l == 0:
+                if param_grads:
+                    _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a), cout,
+                              _p(self.gview("enc_blocks.0.conv.weight")), None, st)
+                w0 = self.pview("enc_blocks.0.conv.weight")
+                if input_grad is not None:
+                    _lib.call("sg_wave_conv_dgrad", _p(g_a), B, L, shifts[0], _p(w0), 2, cout, _p(input_grad), 1, st)
+                if input_grad1 is not None:     # gradient w.r.t. the second input channel
+                    w1 = C.c_void_p(w0.data_ptr() + 4 * KW)
+                    _lib.call("sg_wave_conv_dgrad", _p(g_a), B, L, shifts[0], w1, 2, cout, _p(input_grad1), 1, st)
+                break
+            cin = fm[l - 1]
+            if param_grads:
+                dwp = buf.get("d.dwp", (9 * 4 * fm[-2] * fm[-1],), F32, dev)
+                dwp_l = dwp[:9 * cout * 4 * cin]
+                dwp_l.zero_()
+                n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
+                run_w(g_a, Lq[l], SG_BF16, hp[l - 1], None, Lq[l], 4, SG_F16, 4 * cin, cout,
+                      tap_ranges("conv_fwd", cin, 4 * cin, cout), dwp_l, B,
+                      ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
+                _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
+                          _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, st)
+            g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
+            run_f(g_a, None, Lq[l], 0, SG_BF16, self.packed["Wdg%d" % l], SG_BF16, cout, 4 * cin,
+                  tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_h, SG_BF16, Lq[l], 4, -4, Lq[l] + 4, B,
+                  backend=self.backend)
+        return self.grad

@@ -1,0 +1,4 @@
+from .se_dataset import (collate_fn, normalize_wave_minmax, pre_emphasize, de_emphasize,
+                         SyntheticSEDataset)
+
+__all__ = ["collate_fn", "normalize_wave_minmax", "pre_emphasize", "de_emphasize", "SyntheticSEDataset"]

@@ -1,0 +1,57 @@
+"""Input contract of the hot path (reference: segan/datasets/se_dataset.py:21-29,108-126,355-368):
+int16 PCM -> normalize_wave_minmax -> pre_emphasize(0.95) -> 16384-sample (clean, noisy) windows,
+collated as [names, clean(B,16384), noisy(B,16384), slice_idx(B)].
+
+The wav-directory dataset itself (pickle cache + per-sample WAV reads) is a SURVEY.md 8(f)-N3
+"next" row; BASELINE.json's configs use synthetic pairs, provided here by SyntheticSEDataset."""
+import numpy as np
+import torch
+from torch.utils.data.dataset import Dataset
+from torch.utils.data.dataloader import default_collate
+
+
+def collate_fn(batch):
+    data_batch = []
+    uttname_batch = []
+    for sample in batch:
+        uttname_batch.append(sample[0])
+        data_batch.append(sample[1:])
+    data_batch = default_collate(data_batch)
+    return [uttname_batch] + data_batch
+
+
+def normalize_wave_minmax(x):
+    return (2. / 65535.) * (x - 32767.) + 1.
+
+
+def pre_emphasize(x, coef=0.95):
+    if coef <= 0:
+        return x
+    x0 = np.reshape(x[0], (1,))
+    diff = x[1:] - coef * x[:-1]
+    return np.concatenate((x0, diff), axis=0)
+
+
+def de_emphasize(y, coef=0.95):
+    """Host version (the GPU scan `sg_deemphasis` is what SEGAN.generate uses).  Same recurrence as
+    se_dataset.py:119-126, evaluated with scipy's direct-form IIR instead of a Python loop."""
+    if coef <= 0:
+        return y
+    from scipy.signal import lfilter
+    return lfilter([1.0], [1.0, -coef], np.asarray(y, dtype=np.float64)).astype(np.float32)
+
+
+class SyntheticSEDataset(Dataset):
+    """Synthetic (clean, noisy) 16384-sample pairs of SURVEY.md 8(d): clean = 0.3*randn,
+    noisy = clean + 0.1*randn, clamped to [-1, 1]; items shaped like SEDataset.__getitem__."""
+
+    def __init__(self, n_items, slice_size=16384, seed=111):
+        g = torch.Generator().manual_seed(seed)
+        self.clean = (0.3 * torch.randn(n_items, slice_size, generator=g)).clamp_(-1, 1)
+        self.noisy = (self.clean + 0.1 * torch.randn(n_items, slice_size, generator=g)).clamp_(-1, 1)
+
+    def __len__(self):
+        return self.clean.shape[0]
+
+    def __getitem__(self, i):
+        return ['synthetic_%d' % i, self.clean[i], self.noisy[i], 0]

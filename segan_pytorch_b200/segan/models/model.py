@@ -1,0 +1,399 @@
+"""Drop-in `SEGAN` / `WSEGAN` (reference: segan/models/model.py:28-766).
+
+Constructor, `generate`, `discriminate`, `infer_G`, `infer_D`, `build_optimizers` and `train` keep
+the reference's signatures and step order (model.py:283-321); the step itself is the fused kernel
+pipeline of segan_pytorch_b200.engine plus one gradient all-reduce per optimiser step when
+torch.distributed is initialised (one process per GPU)."""
+import ctypes as C
+import os
+import random
+import timeit
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .core import Model, Saver
+from .discriminator import Discriminator, draw_phase_shifts
+from .generator import Generator
+from ... import _lib
+from ... import engine as _engine
+from ...engine import _p, _stream
+
+try:  # optional, absent in this image
+    from tensorboardX import SummaryWriter
+except Exception:  # pragma: no cover
+    class SummaryWriter(object):
+        def __init__(self, *a, **k):
+            pass
+
+        def add_scalar(self, *a, **k):
+            pass
+
+        def add_histogram(self, *a, **k):
+            pass
+
+
+def weights_init(m):
+    """model.py:28-43 -- matches class names containing 'Conv1d' / 'Linear' only
+    (nn.ConvTranspose1d keeps torch's default init)."""
+    classname = m.__class__.__name__
+    if classname.find('Conv1DResBlock') != -1:
+        for k, p in m.named_parameters():
+            if 'weight' in k and 'conv' in k:
+                p.data.normal_(0.0, 0.02)
+    elif classname.find('Conv1d') != -1:
+        m.weight.data.normal_(0.0, 0.02)
+        if hasattr(m, 'bias') and m.bias is not None:
+            m.bias.data.fill_(0)
+    elif classname.find('Linear') != -1:
+        nn.init.xavier_uniform_(m.weight.data)
+
+
+def wsegan_weights_init(m):
+    """model.py:45-60 -- xavier on Conv1d, ConvTranspose1d and Linear."""
+    classname = m.__class__.__name__
+    if classname.find('Conv1DResBlock') != -1:
+        for k, p in m.named_parameters():
+            if 'weight' in k and 'conv' in k:
+                nn.init.xavier_uniform_(p.data)
+    elif classname.find('Conv1d') != -1:
+        nn.init.xavier_uniform_(m.weight.data)
+    elif classname.find('ConvTranspose1d') != -1:
+        nn.init.xavier_uniform_(m.weight.data)
+    elif classname.find('Linear') != -1:
+        nn.init.xavier_uniform_(m.weight.data)
+
+
+class FusedOptimizer(object):
+    """torch.optim.RMSprop / Adam semantics (model.py:221-225) as ONE kernel over the flat fp32
+    parameter bucket of a network.  state_dict() is torch-compatible (per-parameter tensors)."""
+
+    def __init__(self, eng, kind, lr, betas=(0.0, 0.9), alpha=0.99, eps=1e-8):
+        self.eng, self.kind, self.lr, self.betas, self.alpha, self.eps = eng, kind, lr, betas, alpha, eps
+        self.t = 0
+        self.s1 = None
+        self.s2 = None
+        self.param_groups = [dict(lr=lr)]
+
+    def _state(self):
+        flat = self.eng.bind().flat
+        if self.s1 is None or self.s1.shape != flat.shape or self.s1.device != flat.device:
+            self.s1 = torch.zeros_like(flat)
+            self.s2 = torch.zeros_like(flat) if self.kind == 'adam' else None
+        return flat
+
+    def zero_grad(self):
+        self.eng.bind()
+        self.eng.grad.zero_()
+
+    def step(self, grad_scale=1.0):
+        flat = self._state()
+        lr = self.param_groups[0]['lr']
+        self.t += 1
+        n = flat.numel()
+        if self.kind == 'rmsprop':
+            _lib.call("sg_rmsprop_step", _p(flat), _p(self.eng.grad), _p(self.s1), n, lr, self.alpha, self.eps,
+                      float(grad_scale), _stream())
+        else:
+            _lib.call("sg_adam_step", _p(flat), _p(self.eng.grad), _p(self.s1), _p(self.s2), n, lr, self.betas[0],
+                      self.betas[1], self.eps, self.t, float(grad_scale), _stream())
+        self.eng.mark_dirty()
+
+    def state_dict(self):
+        self._state()
+        state = {}
+        for i, (name, p) in enumerate(self.eng.module.named_parameters()):
+            off, n, shape = self.eng.index[name]
+            if self.kind == 'rmsprop':
+                state[i] = {'step': self.t, 'square_avg': self.s1[off:off + n].view(shape).detach().cpu().clone()}
+            else:
+                state[i] = {'step': self.t, 'exp_avg': self.s1[off:off + n].view(shape).detach().cpu().clone(),
+                            'exp_avg_sq': self.s2[off:off + n].view(shape).detach().cpu().clone()}
+        return {'state': state if self.t > 0 else {},
+                'param_groups': [dict(lr=self.param_groups[0]['lr'], kind=self.kind,
+                                      params=list(range(len(self.eng.index))))]}
+
+    def load_state_dict(self, sd):
+        self._state()
+        for i, (name, p) in enumerate(self.eng.module.named_parameters()):
+            st = sd.get('state', {}).get(i)
+            if st is None:
+                continue
+            off, n, shape = self.eng.index[name]
+            self.t = int(st.get('step', self.t))
+            if 'square_avg' in st:
+                self.s1[off:off + n].copy_(st['square_avg'].reshape(-1))
+            if 'exp_avg' in st:
+                self.s1[off:off + n].copy_(st['exp_avg'].reshape(-1))
+                self.s2[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def allreduce_grads(eng):
+    """The single gradient collective of an optimiser step: one all-reduce (SUM) over the flat
+    bucket the weight-gradient kernels wrote into (no pack pass).  Returns the grad scale."""
+    dist = _dist()
+    if dist is None:
+        return 1.0
+    dist.all_reduce(eng.grad, op=dist.ReduceOp.SUM)
+    return 1.0 / dist.get_world_size()
+
+
+class SEGAN(Model):
+
+    def __init__(self, opts, name='SEGAN', generator=None, discriminator=None):
+        super(SEGAN, self).__init__(name)
+        self.save_path = opts.save_path
+        self.preemph = opts.preemph
+        # the shipped ckpt_segan+/train.opts has no reg_loss key
+        self.reg_loss_name = getattr(opts, 'reg_loss', 'l1_loss')
+        self.reg_loss = getattr(F, self.reg_loss_name)
+        if generator is None:
+            self.G = Generator(1, opts.genc_fmaps, opts.gkwidth, opts.genc_poolings, opts.gdec_fmaps,
+                               opts.gdec_kwidth, opts.gdec_poolings, z_dim=opts.z_dim, no_z=opts.no_z,
+                               skip=(not opts.no_skip), bias=opts.bias, skip_init=opts.skip_init,
+                               skip_type=opts.skip_type, skip_merge=opts.skip_merge,
+                               skip_kwidth=opts.skip_kwidth)
+        else:
+            self.G = generator
+        self.G.apply(weights_init)
+        if discriminator is None:
+            dkwidth = opts.gkwidth if opts.dkwidth is None else opts.dkwidth
+            self.D = Discriminator(2, opts.denc_fmaps, dkwidth, poolings=opts.denc_poolings,
+                                   pool_type=opts.dpool_type, pool_slen=opts.dpool_slen,
+                                   norm_type=opts.dnorm_type, phase_shift=opts.phase_shift,
+                                   sinc_conv=opts.sinc_conv)
+        else:
+            self.D = discriminator
+        self.D.apply(weights_init)
+        self.z_device = getattr(opts, 'z_device', 'cpu')
+
+    # ------------------------------------------------------------------------------------------
+    # inference (model.py:116-175)
+    # ------------------------------------------------------------------------------------------
+    def generate(self, inwav, z=None, device=None):
+        """Chunked enhancement of one utterance (1,1,T).  All 16384-sample windows are run as ONE
+        batch (they are independent), with the reference's z semantics: the given z (or the z drawn
+        for the first window) for window 0 and `G.z` -- the first z G ever saw -- afterwards
+        (model.py:144-146).  De-emphasis runs on the GPU as a scan (se_dataset.py:119-126)."""
+        self.G.eval()
+        N = 16384
+        dev = next(super(Model, self.G).parameters()).device
+        inwav = torch.as_tensor(inwav).float()
+        T = inwav.shape[2]
+        nchunks = (T + N - 1) // N
+        x = torch.zeros(nchunks, 1, N, dtype=torch.float32, device=dev)
+        flat = inwav[0, 0].to(dev)
+        x.view(-1)[:T].copy_(flat)
+        code_len = N // (4 ** len(self.G.enc_blocks))
+        if z is None:
+            z0 = torch.randn(1, self.G.z_dim, code_len).to(dev)
+            if not hasattr(self.G, 'z'):
+                self.G.z = z0
+            zrest = self.G.z
+        else:
+            z0 = z.to(dev)
+            if not hasattr(self.G, 'z'):
+                self.G.z = z0
+            zrest = z0
+        zb = torch.cat([z0[:1]] + [zrest[:1]] * (nchunks - 1), 0) if nchunks > 1 else z0[:1]
+        with torch.no_grad():
+            y, hall = self.G(x, z=zb, ret_hid=True)
+        g_c = hall['enc_{}'.format(len(self.G.enc_blocks) - 1)][-1:]
+        c = y.reshape(-1)[:T].contiguous()
+        out = torch.empty_like(c)
+        if self.preemph > 0:
+            _lib.call("sg_deemphasis", _p(c), T, float(self.preemph), _p(out), _stream())
+        else:
+            out = c
+        return out.cpu().numpy(), g_c
+
+    def generate_batch(self, windows, z=None):
+        """Streaming inference (BASELINE config 5): (N,1,16384) pre-emphasised windows -> enhanced
+        windows, no de-emphasis (windows of different utterances)."""
+        self.G.eval()
+        with torch.no_grad():
+            return self.G(windows, z=z)
+
+    def discriminate(self, cwav, nwav):
+        self.D.eval()
+        d_in = torch.cat((cwav, nwav), dim=1)
+        d_veredict, _ = self.D(d_in)
+        return d_veredict
+
+    def infer_G(self, nwav, cwav=None, z=None, ret_hid=False):
+        if ret_hid:
+            Genh, hall = self.G(nwav, z=z, ret_hid=ret_hid)
+            return Genh, hall
+        return self.G(nwav, z=z, ret_hid=ret_hid)
+
+    def infer_D(self, x_, ref):
+        D_in = torch.cat((x_, ref), dim=1)
+        return self.D(D_in)
+
+    def build_optimizers(self, opts):
+        ge, de = self.G.engine.bind(), self.D.engine.bind()
+        if opts.opt == 'rmsprop':
+            Gopt = FusedOptimizer(ge, 'rmsprop', opts.g_lr)
+            Dopt = FusedOptimizer(de, 'rmsprop', opts.d_lr)
+        elif opts.opt == 'adam':
+            Gopt = FusedOptimizer(ge, 'adam', opts.g_lr, betas=(0, 0.9))
+            Dopt = FusedOptimizer(de, 'adam', opts.d_lr, betas=(0, 0.9))
+        else:
+            raise ValueError('Unrecognized optimizer {}'.format(opts.opt))
+        return Gopt, Dopt
+
+    # ------------------------------------------------------------------------------------------
+    # one LSGAN + L1 step (model.py:283-321) on device-resident (B,1,L) tensors
+    # ------------------------------------------------------------------------------------------
+    def _sample_z(self, B, code_len, dev):
+        if self.z_device == 'cpu':
+            z = torch.randn(B, self.G.z_dim, code_len).to(dev)        # generator.py:197-199
+        else:
+            z = torch.randn(B, self.G.z_dim, code_len, device=dev)
+        if not hasattr(self.G, 'z'):
+            self.G.z = z
+        return z
+
+    def train_step(self, clean, noisy, Gopt, Dopt, l1_weight, z=None, shifts3=None, losses=None):
+        """clean / noisy: (B,1,L) fp32 cuda.  Returns the device tensor of the four losses
+        [d_real, d_fake, g_adv, g_l1] (no host sync)."""
+        ge, de = self.G.engine, self.D.engine
+        B, _, L = clean.shape
+        dev = clean.device
+        st = _stream()
+        nl = len(self.D.enc_blocks)
+        if losses is None:
+            losses = torch.zeros(4, dtype=torch.float32, device=dev)
+        else:
+            losses.zero_()
+        if z is None:
+            z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+        lptr = lambda i: C.c_void_p(losses.data_ptr() + 4 * i)
+        # G forward (model.py:295)
+        Genh, gctx = ge.forward(noisy, z)
+        # (1) D real (model.py:297-299) and (2) D fake (model.py:303-306)
+        Dopt.zero_grad()
+        sh = shifts3[0] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
+        _, c = de.forward(clean, noisy, sh, training=True)
+        de.backward(c, 1.0, 1.0, param_grads=True, loss_out=lptr(0))
+        sh = shifts3[1] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
+        _, c = de.forward(Genh, noisy, sh, training=True)
+        de.backward(c, 0.0, 1.0, param_grads=True, loss_out=lptr(1))
+        Dopt.step(allreduce_grads(de))                                   # model.py:308
+        # (3) G update against the UPDATED D (model.py:313-321)
+        Gopt.zero_grad()
+        sh = shifts3[2] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
+        _, c = de.forward(Genh, noisy, sh, training=True)
+        gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
+        de.backward(c, 1.0, 1.0, param_grads=False, input_grad=gy, loss_out=lptr(2))
+        if self.reg_loss_name != 'l1_loss':
+            raise NotImplementedError("reg_loss %r: only 'l1_loss' (train.py:179 default) is built" % self.reg_loss_name)
+        _lib.call("sg_l1_loss_bwd", _p(Genh), _p(clean.contiguous()), B * L, float(l1_weight), lptr(3), _p(gy), 1, st)
+        ge.backward(gctx, gy)
+        Gopt.step(allreduce_grads(ge))                                   # model.py:321
+        return losses
+
+    def train(self, opts, dloader, criterion, l1_init, l1_dec_step, l1_dec_epoch, log_freq, va_dloader=None,
+              device='cuda'):
+        """Train the SEGAN (model.py:230-437): same loop structure, logging line and checkpoint
+        cadence.  `criterion` must be nn.MSELoss (LSGAN); it is fused into the D head backward."""
+        if not isinstance(criterion, nn.MSELoss):
+            raise NotImplementedError("SEGAN.train is built for the LSGAN criterion nn.MSELoss (train.py:94)")
+        rank0 = _dist() is None or _dist().get_rank() == 0
+        self.writer = SummaryWriter(os.path.join(self.save_path, 'train')) if rank0 else SummaryWriter()
+        self.z_device = getattr(opts, 'z_device', self.z_device)
+        Gopt, Dopt = self.build_optimizers(opts)
+        self.G.optim = Gopt
+        self.D.optim = Dopt
+        eoe_g_saver = Saver(self.G, opts.save_path, max_ckpts=3, optimizer=self.G.optim, prefix='EOE_G-')
+        eoe_d_saver = Saver(self.D, opts.save_path, max_ckpts=3, optimizer=self.D.optim, prefix='EOE_D-')
+        l1_weight = l1_init
+        iteration = 1
+        timings = []
+        losses = None
+        for epoch in range(1, opts.epoch + 1):
+            beg_t = timeit.default_timer()
+            self.G.train()
+            self.D.train()
+            for bidx, batch in enumerate(dloader, start=1):
+                if epoch >= l1_dec_epoch:
+                    if l1_weight > 0:
+                        l1_weight -= l1_dec_step
+                        l1_weight = max(0, l1_weight)
+                if len(batch) != 4:
+                    raise ValueError('Returned {} elements per sample?'.format(len(batch)))
+                uttname, clean, noisy, slice_idx = batch
+                clean = clean.unsqueeze(1).to(device, non_blocking=True).float()
+                noisy = noisy.unsqueeze(1).to(device, non_blocking=True).float()
+                losses = self.train_step(clean, noisy, Gopt, Dopt, l1_weight, losses=losses)
+                end_t = timeit.default_timer()
+                timings.append(end_t - beg_t)
+                beg_t = timeit.default_timer()
+                if bidx % log_freq == 0 or bidx >= len(dloader):
+                    lv = losses.tolist()                                   # the only host sync
+                    if rank0:
+                        print('(Iter {}) Batch {}/{} (Epoch {}) d_real:{:.4f}, d_fake:{:.4f}, g_adv:{:.4f}, '
+                              'g_l1:{:.4f} l1_w: {:.2f}, btime: {:.4f} s, mbtime: {:.4f} s'
+                              ''.format(iteration, bidx, len(dloader), epoch, lv[0], lv[1], lv[2], lv[3],
+                                        l1_weight, timings[-1], np.mean(timings)))
+                        self.writer.add_scalar('D_real', lv[0], iteration)
+                        self.writer.add_scalar('D_fake', lv[1], iteration)
+                        self.writer.add_scalar('G_adv', lv[2], iteration)
+                        self.writer.add_scalar('G_l1', lv[3], iteration)
+                iteration += 1
+            if va_dloader is not None:
+                raise NotImplementedError("validation with composite objective metrics (model.py:394-433) is "
+                                          "out of the hot-path scope (SURVEY.md 2.1)")
+            if rank0:
+                self.G.save(self.save_path, iteration, saver=eoe_g_saver)
+                self.D.save(self.save_path, iteration, saver=eoe_d_saver)
+        self.last_losses = losses
+        return timings
+
+
+class WSEGAN(SEGAN):
+    """Whisper-SEGAN (model.py:509-766).  Constructor / init parity is built; the fused WSEGAN step
+    (extra misaligned-pair D pass + STFT log-power L1) is the next row."""
+
+    def __init__(self, opts, name='WSEGAN', generator=None, discriminator=None):
+        self.lbd = 1
+        self.critic_iters = 1
+        self.misalign_pair = opts.misalign_pair
+        self.interf_pair = opts.interf_pair
+        self.pow_weight = opts.pow_weight
+        self.vanilla_gan = opts.vanilla_gan
+        self.n_fft = opts.n_fft
+        super(WSEGAN, self).__init__(opts, name, None, None)
+        self.G.apply(wsegan_weights_init)
+        self.D.apply(wsegan_weights_init)
+
+    def infer_G(self, nwav, cwav=None, z=None, ret_hid=False):
+        return self.G(nwav, z=z, ret_hid=ret_hid)
+
+    def generate(self, inwav, z=None):
+        """model.py:755-766: un-chunked inference on the utterance zero-padded to a multiple of 1024
+        (make_divN pads a full extra block when already divisible, utils.py:26-38)."""
+        self.G.eval()
+        dev = next(super(Model, self.G).parameters()).device
+        inwav = torch.as_tensor(inwav).float()
+        ori_len = inwav.size(2)
+        pad_num = (ori_len + 1024) - (ori_len % 1024) - ori_len
+        p_wav = torch.cat((inwav, torch.zeros(inwav.size(0), inwav.size(1), pad_num)), dim=2).to(dev)
+        with torch.no_grad():
+            c_res, hall = self.infer_G(p_wav, z=z, ret_hid=True)
+        c = c_res[0, 0, :ori_len].contiguous()
+        out = torch.empty_like(c)
+        if self.preemph > 0:
+            _lib.call("sg_deemphasis", _p(c), ori_len, float(self.preemph), _p(out), _stream())
+        else:
+            out = c
+        return out.cpu().numpy(), hall
