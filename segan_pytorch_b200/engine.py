@@ -139,7 +139,7 @@ def flatten_params(module):
     """Re-points every parameter of `module` at a slice of one flat fp32 buffer (and the same for
     gradients) so that the optimiser, the NCCL all-reduce and the weight-gradient kernels see one
     contiguous bucket.  Safe to call again after .to(device)."""
-    params = [p for p in module.parameters(recurse=True)]
+    params = [p for _, p in module.named_parameters()]
     if not params:
         return None, None, {}
     dev = params[0].device
@@ -195,7 +195,7 @@ class _NetEngine:
         return self.grad[off:off + n].view(shape)
 
     def _version(self):
-        return tuple(p._version for p in self.module.parameters()) + (self.flat.data_ptr(),)
+        return tuple(p._version for _, p in self.module.named_parameters()) + (self.flat.data_ptr(),)
 
     def mark_dirty(self):
         self._packed_version = None

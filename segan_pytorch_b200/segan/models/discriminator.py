@@ -34,7 +34,6 @@ class _DiscriminatorFn(torch.autograd.Function):
         x1 = x[:, 1:2, :].contiguous()
         logit, ectx = eng.forward(x0, x1, shifts, training=training, fresh=True)
         ctx.eng, ctx.ectx = eng, ectx
-        ctx.need_x = x.requires_grad
         eng._last_ctx = ectx
         return logit
 
@@ -43,6 +42,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         eng, ectx = ctx.eng, ctx.ectx
         gx = None
         g0 = g1 = None
+        ctx.need_x = ctx.needs_input_grad[1]
         if ctx.need_x:
             B, L = ectx["B"], ectx["L"]
             g0 = torch.zeros(B, 1, L, dtype=torch.float32, device=g_logit.device)

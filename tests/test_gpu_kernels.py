@@ -1,0 +1,425 @@
+"""Kernel-level GPU tests: every C-ABI kernel against a plain fp32 torch evaluation of the same
+formula on the same (16-bit-rounded) operands, and the tcgen05 tap-GEMMs against the FFMA ones.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from segan_pytorch_b200 import _lib, engine as E          # noqa: E402
+from segan_pytorch_b200._lib import SG_BF16, SG_F16, SG_F32, BACKEND_FFMA, BACKEND_TCGEN05  # noqa: E402
+from oracle import segan_oracle as O                       # noqa: E402
+from tests.util import max_abs, rel_err                    # noqa: E402
+
+DEV = "cuda"
+_p, _stream = E._p, E._stream
+
+
+def _gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def _packed_random(kind, c, kc, nc, g, dtype, scale=0.05):
+    taps = E.tap_ranges(kind, c, kc, nc)
+    w = torch.randn(9, nc, kc, generator=g) * scale
+    for i in range(9):
+        mask = torch.zeros(nc, kc)
+        mask[taps[2][i]:taps[3][i], taps[0][i]:taps[1][i]] = 1
+        w[i] *= mask
+    return w.to(dtype).to(DEV), taps
+
+
+def _ref_f(a_pad, halo, w, m_lo, m_hi, d_lo=-4, d_hi=4, w_tap0=0):
+    """a_pad: (B, R+2H, Kc) float32 with zero rows already in place; returns (B, m_hi-m_lo, Nc)."""
+    B, RH, Kc = a_pad.shape
+    R = RH - 2 * halo
+    ext = 16
+    ap = F.pad(a_pad, (0, 0, ext, ext))
+    out = 0
+    for d in range(d_lo, d_hi + 1):
+        rows = ap[:, ext + halo + m_lo + d: ext + halo + m_hi + d, :]
+        out = out + rows @ w[d + 4 - w_tap0].float().t()
+    return out
+
+
+@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
+@pytest.mark.parametrize("case", ["conv_fwd", "conv_dgrad", "deconv_fwd_cat", "deconv_dgrad", "small_rows", "fc"])
+def test_tapgemm_f(backend, case):
+    g = _gen(1)
+    B = 3
+    bias = None
+    a1 = None
+    a1_c = 0
+    n_lo, n_hi = 0, None
+    d_lo, d_hi, w_tap0, ksplit = -4, 4, 0, 1
+    out_dtype, tdt = SG_F16, torch.float16
+    if case == "conv_fwd":
+        cin, cout, R, halo = 64, 128, 160, 4
+        kc, nc = 4 * cin, cout
+        w, taps = _packed_random("conv_fwd", cin, kc, nc, g, torch.float16)
+        a0 = (torch.randn(B, R + 2 * halo, kc, generator=g)).to(torch.float16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        bias = torch.randn(nc, generator=g).to(DEV)
+        adt, wdt = SG_F16, SG_F16
+    elif case == "conv_dgrad":
+        cin, cout, R, halo = 64, 128, 96, 0
+        kc, nc = cout, 4 * cin
+        w, taps = _packed_random("conv_dgrad", cin, kc, nc, g, torch.bfloat16)
+        a0 = torch.randn(B, R, kc, generator=g).to(torch.bfloat16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = -4, R + 4, R, 4
+        adt, wdt, out_dtype, tdt = SG_BF16, SG_BF16, SG_BF16, torch.bfloat16
+    elif case == "deconv_fwd_cat":
+        cin, cout, R, halo = 256, 64, 64, 0
+        kc, nc = cin, 4 * cout
+        w, taps = _packed_random("deconv_fwd", cout, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1_c = 128
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        bias = torch.randn(cout, generator=g).to(DEV)
+        adt, wdt = SG_F16, SG_F16
+    elif case == "deconv_dgrad":
+        cin, cout, R, halo = 256, 64, 64, 0
+        kc, nc = 4 * cout, cin
+        w, taps = _packed_random("deconv_dgrad", cout, kc, nc, g, torch.bfloat16)
+        a0 = torch.randn(B, R, kc, generator=g).to(torch.bfloat16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        n_lo, n_hi = 128, 256
+        adt, wdt, out_dtype, tdt = SG_BF16, SG_BF16, SG_BF16, torch.bfloat16
+    elif case == "small_rows":
+        B = 11
+        cin, cout, R, halo = 128, 256, 16, 4
+        kc, nc = 4 * cin, cout
+        w, taps = _packed_random("conv_fwd", cin, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        adt, wdt = SG_F16, SG_F16
+    else:  # fc: one tap, rows = 1, split-K into fp32
+        B = 70
+        kc, nc, R, halo = 2048, 256, 1, 0
+        taps = E.tap_ranges("full", 0, kc, nc)
+        w = (torch.randn(1, nc, kc, generator=g) * 0.05).to(torch.float16).to(DEV)
+        a0 = torch.randn(B, 1, kc, generator=g).to(torch.float16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = 0, 1, 1, 0
+        d_lo = d_hi = 0
+        w_tap0, ksplit = 4, 4
+        adt, wdt, out_dtype, tdt = SG_F16, SG_F16, SG_F32, torch.float32
+    nhi = nc if n_hi is None else n_hi
+    out = torch.zeros(B, out_rows + 2 * out_halo, nc, dtype=tdt, device=DEV)
+    E.run_f(a0, a1, R, halo, adt, w, wdt, kc, nc, taps, out, out_dtype, out_rows, out_halo, m_lo, m_hi, B,
+            bias=bias, bias_mod=(bias.numel() if bias is not None else 0), n_lo=n_lo, n_hi=n_hi,
+            d_lo=d_lo, d_hi=d_hi, w_tap0=w_tap0, ksplit=ksplit, backend=backend,
+            a0_c=a0.shape[-1], a1_c=a1_c)
+    torch.cuda.synchronize()
+    a_full = a0.float() if a1 is None else torch.cat((a0.float(), a1.float()), -1)
+    ref = _ref_f(a_full, halo, w, m_lo, m_hi, d_lo, d_hi, w_tap0)
+    if bias is not None:
+        ref = ref + bias.repeat(nc // bias.numel())
+    got = out[:, out_halo + m_lo: out_halo + m_hi, n_lo:nhi].float()
+    ref = ref[:, :, n_lo:nhi]
+    err = max_abs(got, ref)
+    tol = 3e-2 if tdt != torch.float32 else 2e-3
+    assert err <= tol * max(1.0, float(ref.abs().max())), (case, backend, err, float(ref.abs().max()))
+    if n_lo > 0:   # untouched columns stay zero
+        assert float(out[:, :, :n_lo].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
+@pytest.mark.parametrize("case", ["conv", "deconv_cat", "small_rows", "fc"])
+def test_tapgemm_w(backend, case):
+    g = _gen(2)
+    a1, a1_c = None, 0
+    d_lo, d_hi, tap0, ksplit = -4, 4, 0, 3
+    if case == "conv":
+        B, cin, cout, R, halo = 3, 64, 128, 128, 4
+        kc, nc = 4 * cin, cout
+        taps = E.tap_ranges("conv_fwd", cin, kc, nc)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+    elif case == "deconv_cat":
+        B, cin, cout, R, halo = 2, 256, 64, 64, 0
+        kc, nc = cin, 4 * cout
+        taps = E.tap_ranges("deconv_fwd", cout, kc, nc)
+        a0 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1_c = 128
+    elif case == "small_rows":
+        B, cin, cout, R, halo = 9, 128, 128, 16, 4
+        kc, nc = 4 * cin, cout
+        taps = E.tap_ranges("conv_fwd", cin, kc, nc)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+    else:
+        B, kc, nc, R, halo = 70, 1024, 256, 1, 0
+        taps = E.tap_ranges("full", 0, kc, nc)
+        a0 = torch.randn(B, 1, kc, generator=g).to(torch.float16).to(DEV)
+        d_lo = d_hi = 0
+        tap0, ksplit = 4, 1
+    gg = (torch.randn(B, R, nc, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+    slots = d_hi + 4 - tap0 + 1
+    dw = torch.zeros(slots, nc, kc, dtype=torch.float32, device=DEV)
+    E.run_w(gg, R, SG_BF16, a0, a1, R, halo, SG_F16, kc, nc, taps, dw, B, d_lo=d_lo, d_hi=d_hi, dw_tap0=tap0,
+            ksplit=ksplit, backend=backend, a0_c=a0.shape[-1], a1_c=a1_c)
+    torch.cuda.synchronize()
+    a_full = a0.float() if a1 is None else torch.cat((a0.float(), a1.float()), -1)
+    ap = F.pad(a_full, (0, 0, 16, 16))
+    for d in range(d_lo, d_hi + 1):
+        rows = ap[:, 16 + halo + d: 16 + halo + d + R, :]
+        ref = torch.einsum("bmn,bmk->nk", gg.float(), rows)
+        mask = torch.zeros(nc, kc, device=DEV)
+        mask[taps[2][d + 4]:taps[3][d + 4], taps[0][d + 4]:taps[1][d + 4]] = 1
+        got = dw[d + 4 - tap0]
+        err = max_abs(got * mask, ref * mask)
+        assert err <= 2e-3 * max(1.0, float(ref.abs().max())), (case, backend, d, err)
+        assert float((got * (1 - mask)).abs().max()) == 0.0, (case, d, "structural zeros written")
+
+
+def test_pack_and_unpack_roundtrip():
+    g = _gen(3)
+    for kind, (co, ci) in ((0, (128, 64)), (1, (64, 256))):
+        shape = (co, ci, 31) if kind == 0 else (ci, co, 31)
+        w = (torch.randn(*shape, generator=g) * 0.1).to(DEV)
+        alpha = (torch.rand(ci // 2, generator=g) + 0.5).to(DEV) if kind == 1 else None
+        if kind == 0:
+            wf = torch.zeros(9, co, 4 * ci, dtype=torch.float16, device=DEV)
+            wd = torch.zeros(9, 4 * ci, co, dtype=torch.bfloat16, device=DEV)
+        else:
+            wf = torch.zeros(9, 4 * co, ci, dtype=torch.float16, device=DEV)
+            wd = torch.zeros(9, ci, 4 * co, dtype=torch.bfloat16, device=DEV)
+        _lib.call("sg_pack_weights", kind, _p(w), co, ci, 0, _p(alpha), ci // 2, _p(wf), _p(wd), SG_F16, SG_BF16,
+                  _stream())
+        # semantic check: tap-GEMM on the packed weights == the reference op on the fp32 weights
+        B, R = 2, 32
+        if kind == 0:
+            x = torch.randn(B, ci, 4 * R, generator=g).to(DEV)                # NCL input, L = 4R
+            ref = O.gconv_linear(x.cpu(), w.cpu().half().float(), None)       # (B, co, R)
+            xp = F.pad(x, (16, 16), mode="reflect")                          # 16-position halo
+            a = xp.permute(0, 2, 1).contiguous().view(B, R + 8, 4 * ci).half()
+            out = torch.zeros(B, R, co, dtype=torch.float16, device=DEV)
+            E.run_f(a, None, R, 4, SG_F16, wf, SG_F16, 4 * ci, co, E.tap_ranges("conv_fwd", ci, 4 * ci, co), out,
+                    SG_F16, R, 0, 0, R, B, backend=BACKEND_FFMA)
+            got = out.float().permute(0, 2, 1).cpu()
+            ref = O.gconv_linear(x.half().float().cpu(), w.cpu().half().float(), None)
+        else:
+            x = torch.randn(B, ci, R, generator=g).to(DEV)
+            weff = w.clone()
+            weff[ci // 2:] *= alpha.view(-1, 1, 1)
+            ref = O.gdeconv_linear(x.half().float().cpu(), weff.cpu().half().float(), torch.zeros(co))
+            a = x.permute(0, 2, 1).contiguous().half()
+            out = torch.zeros(B, R, 4 * co, dtype=torch.float16, device=DEV)
+            E.run_f(a, None, R, 0, SG_F16, wf, SG_F16, ci, 4 * co, E.tap_ranges("deconv_fwd", co, ci, 4 * co), out,
+                    SG_F16, R, 0, 0, R, B, backend=BACKEND_FFMA)
+            got = out.float().view(B, 4 * R, co).permute(0, 2, 1).cpu()
+        torch.cuda.synchronize()
+        assert max_abs(got, ref) <= 2e-2 * max(1.0, float(ref.abs().max())), kind
+        # unpack(pack-layout gradient) restores the reference layout
+        dwp = wf.float().contiguous()
+        dw = torch.zeros_like(w)
+        dalpha = torch.zeros(ci // 2, device=DEV) if kind == 1 else None
+        _lib.call("sg_unpack_wgrad", kind, _p(dwp), co, ci, 0, _p(w), _p(alpha), ci // 2, _p(dw), _p(dalpha), 0,
+                  _stream())
+        torch.cuda.synchronize()
+        if kind == 0:
+            assert max_abs(dw, w.half().float()) == 0.0
+        else:
+            weff16 = (weff.half().float())
+            exp = weff16.clone()
+            exp[ci // 2:] *= alpha.view(-1, 1, 1)
+            assert max_abs(dw, exp) <= 1e-6
+            assert max_abs(dalpha, (weff16[ci // 2:] * w[ci // 2:]).sum((1, 2))) <= 1e-3
+
+
+def test_wave_conv_fwd_and_grads():
+    g = _gen(4)
+    B, L, roll = 3, 4096, -3
+    x0 = (0.3 * torch.randn(B, L, generator=g)).to(DEV)
+    x1 = (0.3 * torch.randn(B, L, generator=g)).to(DEV)
+    w = (0.05 * torch.randn(64, 2, 31, generator=g)).to(DEV)
+    bias = (0.1 * torch.randn(64, generator=g)).to(DEV)
+    a = torch.zeros(B, L // 4, 64, dtype=torch.float16, device=DEV)
+    _lib.call("sg_wave_conv_fwd", _p(x0), _p(x1), 2, B, L, roll, _p(w), _p(bias), 64, _p(a), None, None, _stream())
+    xin = torch.stack((x0, x1), 1).cpu()
+    ref = O.gconv_linear(O.phase_roll(xin, roll), w.cpu(), bias.cpu())
+    torch.cuda.synchronize()
+    assert max_abs(a.float().permute(0, 2, 1).cpu(), ref) <= 2e-3 * float(ref.abs().max())
+    # G variant: 1 channel, PReLU + reflect halo
+    slope = (0.2 * torch.rand(64, generator=g)).to(DEV)
+    hp = torch.zeros(B, L // 4 + 32, 64, dtype=torch.float16, device=DEV)
+    w1 = w[:, :1].contiguous()
+    _lib.call("sg_wave_conv_fwd", _p(x0), None, 1, B, L, 0, _p(w1), None, 64, _p(a), _p(slope), _p(hp), _stream())
+    ref1 = O.gconv_linear(x0.cpu().unsqueeze(1), w1.cpu(), None)
+    h_ref = F.pad(F.prelu(ref1, slope.cpu()), (16, 16), mode="reflect")
+    torch.cuda.synchronize()
+    assert max_abs(hp.float().permute(0, 2, 1).cpu(), h_ref) <= 2e-3 * float(h_ref.abs().max())
+    # gradients of the 2-channel rolled conv
+    ga = (0.1 * torch.randn(B, L // 4, 64, generator=g)).to(torch.bfloat16).to(DEV)
+    dw = torch.zeros_like(w)
+    db = torch.zeros(64, device=DEV)
+    _lib.call("sg_wave_conv_wgrad", _p(x0), _p(x1), 2, B, L, roll, _p(ga), 64, _p(dw), _p(db), _stream())
+    gx0 = torch.zeros(B, L, device=DEV)
+    _lib.call("sg_wave_conv_dgrad", _p(ga), B, L, roll, _p(w), 2, 64, _p(gx0), 0, _stream())
+    xin_r = xin.clone().requires_grad_(True)
+    wr = w.cpu().clone().requires_grad_(True)
+    out = O.gconv_linear(O.phase_roll(xin_r, roll), wr, bias.cpu())
+    out.backward(ga.float().permute(0, 2, 1).cpu())
+    torch.cuda.synchronize()
+    assert rel_err(dw.cpu(), wr.grad) <= 1e-4
+    assert rel_err(db.cpu(), ga.float().sum((0, 1)).cpu()) <= 1e-4
+    assert rel_err(gx0.cpu(), xin_r.grad[:, 0]) <= 1e-4
+
+
+def test_wave_deconv_fwd_and_bwd():
+    g = _gen(5)
+    B, Lin = 2, 1024
+    x0 = (torch.randn(B, Lin, 64, generator=g)).to(torch.float16).to(DEV)
+    x1 = (torch.randn(B, Lin, 64, generator=g)).to(torch.float16).to(DEV)
+    w = (0.05 * torch.randn(128, 31, generator=g)).to(DEV)
+    bias = torch.tensor([0.05], device=DEV)
+    y = torch.zeros(B, 4 * Lin, device=DEV)
+    _lib.call("sg_wave_deconv_fwd", _p(x0), 64, _p(x1), 64, B, Lin, _p(w), _p(bias), _p(y), _stream())
+    xin = torch.cat((x0, x1), -1).float().permute(0, 2, 1).cpu().requires_grad_(True)
+    wr = w.cpu().view(128, 1, 31).clone().requires_grad_(True)
+    br = bias.cpu().clone().requires_grad_(True)
+    ref = torch.tanh(O.gdeconv_linear(xin, wr, br))
+    torch.cuda.synchronize()
+    assert max_abs(y.cpu(), ref[:, 0].detach()) <= 1e-4
+    gy = (torch.randn(B, 4 * Lin, generator=g)).to(DEV)
+    gpre = torch.zeros_like(gy)
+    gx = torch.zeros(B, Lin, 128, dtype=torch.bfloat16, device=DEV)
+    dw = torch.zeros_like(w)
+    db = torch.zeros(1, device=DEV)
+    _lib.call("sg_wave_deconv_bwd", _p(x0), 64, _p(x1), 64, B, Lin, _p(w), _p(gy), _p(y), _p(gpre), _p(gx),
+              _p(dw), _p(db), _stream())
+    ref.backward(gy.cpu().unsqueeze(1))
+    torch.cuda.synchronize()
+    assert rel_err(dw.cpu(), wr.grad[:, 0]) <= 1e-3
+    assert rel_err(db.cpu(), br.grad) <= 1e-3
+    assert rel_err(gx.float().permute(0, 2, 1).cpu(), xin.grad) <= 1e-2      # bf16 output
+
+
+@pytest.mark.parametrize("C_,L,roll,halo", [(64, 256, 2, 16), (256, 64, -5, 16), (1024, 16, 0, 0)])
+def test_bn_act_fwd_bwd(C_, L, roll, halo):
+    g = _gen(6)
+    B = 4
+    a = torch.randn(B, L, C_, generator=g).to(torch.float16).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(C_, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(C_, generator=g)).to(DEV)
+    slope = (0.2 * torch.rand(C_, generator=g)).to(DEV)
+    rm, rv = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
+    stats = torch.zeros(2, C_, dtype=torch.float64, device=DEV)
+    ss = torch.zeros(2, C_, device=DEV)
+    mi = torch.zeros(2, C_, device=DEV)
+    _lib.call("sg_bn_stats", _p(a), SG_F16, B * L, C_, _p(stats), _stream())
+    _lib.call("sg_bn_finalize", _p(stats), B * L, C_, _p(gamma), _p(beta), 1e-5, 0.1, _p(rm), _p(rv), _p(ss),
+              _p(mi), _stream())
+    h = torch.zeros(B, L + 2 * halo, C_, dtype=torch.float16, device=DEV)
+    _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, roll, halo, _p(h), _stream())
+    # reference: NCL fp32
+    an = a.float().permute(0, 2, 1).cpu().requires_grad_(True)
+    gm, bt, sl = (t.cpu().clone().requires_grad_(True) for t in (gamma, beta, slope))
+    rm_r, rv_r = torch.zeros(C_), torch.ones(C_)
+    y = F.prelu(O.batchnorm_train(an, gm, bt, rm_r, rv_r), sl)
+    yr = O.phase_roll(y, roll)
+    if halo:
+        yr = F.pad(yr, (halo, halo), mode="reflect")
+    torch.cuda.synchronize()
+    assert max_abs(h.float().permute(0, 2, 1).cpu(), yr.detach()) <= 1e-2
+    assert max_abs(rm.cpu(), rm_r) <= 1e-5 and max_abs(rv.cpu(), rv_r) <= 1e-4
+    # backward: gradient arrives in the consumer view (incl. halo)
+    gh = (torch.randn(B, L + 2 * halo, C_, generator=g)).to(torch.bfloat16).to(DEV)
+    yr.backward(gh.float().permute(0, 2, 1).cpu())
+    red = torch.zeros(3, C_, dtype=torch.float64, device=DEV)
+    ga = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
+    _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+              _p(slope), 1, _p(red), None, _stream())
+    _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+              _p(slope), 1, _p(red), 1, _p(ga), _stream())
+    torch.cuda.synchronize()
+    assert rel_err(red[0].float().cpu(), sl.grad) <= 2e-3
+    assert rel_err(red[1].float().cpu(), bt.grad) <= 2e-3
+    assert rel_err(red[2].float().cpu(), gm.grad) <= 2e-3
+    assert rel_err(ga.float().permute(0, 2, 1).cpu(), an.grad) <= 1e-2
+
+
+def test_fc_tail_and_losses():
+    g = _gen(7)
+    B = 6
+    acc = torch.randn(B, 256, generator=g).to(DEV)
+    b0, s1 = (0.1 * torch.randn(256, generator=g)).to(DEV), (0.25 * torch.ones(256)).to(DEV)
+    w2, b2 = (0.1 * torch.randn(128, 256, generator=g)).to(DEV), (0.1 * torch.randn(128, generator=g)).to(DEV)
+    s3 = (0.25 * torch.ones(128)).to(DEV)
+    w4, b4 = (0.1 * torch.randn(1, 128, generator=g)).to(DEV), torch.tensor([0.02], device=DEV)
+    z1, z2 = torch.zeros(B, 256, device=DEV), torch.zeros(B, 128, device=DEV)
+    logit = torch.zeros(B, 1, device=DEV)
+    _lib.call("sg_fc_tail_fwd", _p(acc), _p(b0), _p(s1), _p(w2), _p(b2), _p(s3), _p(w4), _p(b4), B, _p(z1), _p(z2),
+              _p(logit), _stream())
+    ps = [t.cpu().clone().requires_grad_(True) for t in (acc, b0, s1, w2, b2, s3, w4, b4)]
+    h = F.prelu(ps[0] + ps[1], ps[2])
+    h = F.prelu(F.linear(h, ps[3], ps[4]), ps[5])
+    ref = F.linear(h, ps[6], ps[7])
+    torch.cuda.synchronize()
+    assert max_abs(logit.cpu(), ref.detach()) <= 1e-5
+    loss = 0.5 * F.mse_loss(ref.view(-1), torch.ones(B))
+    loss.backward()
+    gz1 = torch.zeros(B, 256, dtype=torch.bfloat16, device=DEV)
+    ws = torch.zeros(B * 385, device=DEV)
+    gs = [torch.zeros_like(t) for t in (b0, s1, w2, b2, s3, w4, b4)]
+    lo = torch.zeros(1, device=DEV)
+    _lib.call("sg_fc_tail_bwd", _p(z1), _p(z2), _p(logit), None, 1.0, 0.5, _p(s1), _p(w2), _p(s3), _p(w4), B, _p(lo),
+              _p(gz1), _p(ws), *[_p(t) for t in gs], _stream())
+    torch.cuda.synchronize()
+    assert abs(float(lo) - float(loss)) <= 1e-5
+    assert rel_err(gz1.float().cpu(), ps[0].grad) <= 1e-2
+    for got, p in zip(gs, ps[1:]):
+        assert rel_err(got.cpu().reshape(-1), p.grad.reshape(-1)) <= 1e-4
+    # L1
+    y, c = torch.randn(B, 64, generator=g).to(DEV), torch.randn(B, 64, generator=g).to(DEV)
+    gy = torch.zeros_like(y)
+    lo.zero_()
+    _lib.call("sg_l1_loss_bwd", _p(y), _p(c), y.numel(), 100.0, _p(lo), _p(gy), 0, _stream())
+    yr = y.cpu().requires_grad_(True)
+    l = 100.0 * F.l1_loss(yr, c.cpu())
+    l.backward()
+    torch.cuda.synchronize()
+    assert abs(float(lo) - float(l)) <= 1e-3 and max_abs(gy.cpu(), yr.grad) <= 1e-7
+
+
+def test_optimizers_and_emphasis():
+    g = _gen(8)
+    n = 10007
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) for _ in range(3)]
+    for kind in ("rmsprop", "adam"):
+        pr = p0.clone().requires_grad_(True)
+        opt = torch.optim.RMSprop([pr], lr=5e-5) if kind == "rmsprop" else torch.optim.Adam([pr], lr=5e-5, betas=(0, 0.9))
+        p = p0.clone().to(DEV)
+        s1, s2 = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        for t, gr in enumerate(grads, 1):
+            pr.grad = gr.clone()
+            opt.step()
+            gd = gr.to(DEV)
+            if kind == "rmsprop":
+                _lib.call("sg_rmsprop_step", _p(p), _p(gd), _p(s1), n, 5e-5, 0.99, 1e-8, 1.0, _stream())
+            else:
+                _lib.call("sg_adam_step", _p(p), _p(gd), _p(s1), _p(s2), n, 5e-5, 0.0, 0.9, 1e-8, t, 1.0, _stream())
+        torch.cuda.synchronize()
+        assert max_abs(p.cpu(), pr.detach()) <= 2e-7, kind
+    y = (0.1 * torch.randn(50001, generator=g))
+    x = torch.zeros_like(y).to(DEV)
+    _lib.call("sg_deemphasis", _p(y.to(DEV)), y.numel(), 0.95, _p(x), _stream())
+    torch.cuda.synchronize()
+    ref = O.de_emphasize(y.numpy(), 0.95)
+    assert max_abs(x.cpu(), torch.from_numpy(ref)) <= 2e-5
+    back = torch.zeros_like(x)
+    _lib.call("sg_preemphasis", _p(x), y.numel(), 0.95, _p(back), _stream())
+    torch.cuda.synchronize()
+    assert max_abs(back.cpu(), y) <= 1e-5
+
+
+def test_cpu_tensor_rejected_loudly():
+    from tests.util import build_segan
+    s = build_segan()
+    with pytest.raises(RuntimeError):
+        s.G(torch.zeros(1, 1, 16384))

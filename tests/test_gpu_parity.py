@@ -1,0 +1,186 @@
+"""Parity of the CUDA path with the reference, through the drop-in API:
+  * against the golden vectors produced by the unmodified reference (tests/golden/*.npz)
+  * against the oracle on the same seeded inputs
+north_star tolerance: 1e-3 max-abs on fp32 waveforms (written below as WAVE_TOL).
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import segan_oracle as O                                         # noqa: E402
+from segan_pytorch_b200._lib import BACKEND_FFMA, BACKEND_TCGEN05           # noqa: E402
+from tests.util import build_segan, cpu_state, golden, max_abs, rel_err, sd_sha  # noqa: E402
+
+WAVE_TOL = 1e-3
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def segan():
+    s = build_segan()
+    assert sd_sha(s.G.state_dict()) == str(golden("g_forward_cfg1.npz")["sha_G"])
+    return s.to(DEV)
+
+
+@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
+def test_generator_forward_cfg1(segan, backend):
+    """BASELINE config 1: G forward on 1x16384, eval, vs the reference's CPU output."""
+    g = golden("g_forward_cfg1.npz")
+    segan.G.eval()
+    segan.G.engine.backend = backend
+    with torch.no_grad():
+        y, hall = segan.G(torch.from_numpy(g["x"]).to(DEV), z=torch.from_numpy(g["z"]).to(DEV), ret_hid=True)
+    torch.cuda.synchronize()
+    for k in hall:
+        idx = torch.from_numpy(g["hall_idx." + k]).to(DEV)
+        got = hall[k].reshape(-1)[idx].cpu()
+        ref = torch.from_numpy(g["hall_val." + k])
+        assert max_abs(got, ref) <= 4e-3 * max(1.0, float(ref.abs().max())), (k, backend)
+    err = max_abs(y.cpu(), g["y"])
+    print("G fwd cfg1 backend %d max-abs %.3e" % (backend, err))
+    assert err <= WAVE_TOL
+
+
+@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
+def test_generator_forward_batched(segan, backend):
+    g = golden("g_forward_b3.npz")
+    segan.G.eval()
+    segan.G.engine.backend = backend
+    with torch.no_grad():
+        y = segan.G(torch.from_numpy(g["x"]).to(DEV), z=torch.from_numpy(g["z"]).to(DEV))
+    assert max_abs(y.cpu(), g["y"]) <= WAVE_TOL
+
+
+@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
+def test_discriminator_forward(backend):
+    d = golden("d_forward.npz")
+    s = build_segan().to(DEV)
+    s.D.engine.backend = backend
+    x = torch.from_numpy(d["x"]).to(DEV)
+    s.D.train()
+    random.seed(int(d["py_random_seed"]))
+    with torch.no_grad():
+        y, acts = s.D(x)
+    assert max_abs(y.cpu(), d["y_train"]) <= 2e-2
+    for l in range(5):
+        bn = s.D.enc_blocks[l].norm
+        assert max_abs(bn.running_mean.cpu(), d["running_mean.%d" % l]) <= 1e-4
+        assert max_abs(bn.running_var.cpu(), d["running_var.%d" % l]) <= 1e-3
+        idx = torch.from_numpy(d["act_idx.%d" % l]).to(DEV)
+        assert max_abs(acts["h_%d" % l].reshape(-1)[idx].cpu(), d["act_val.%d" % l]) <= 3e-2, l
+    s.D.eval()
+    random.seed(8)
+    with torch.no_grad():
+        ye, _ = s.D(x)
+    assert max_abs(ye.cpu(), d["y_eval"]) <= 2e-2
+
+
+def _check_sampled(t, tag, name, got, tol_rel):
+    idx = torch.from_numpy(t["idx." + tag + name])
+    ref = torch.from_numpy(t["val." + tag + name])
+    g = got.detach().float().cpu().reshape(-1)[idx]
+    norm = float(t["norm." + tag + name])
+    rms = norm / max(1.0, got.numel()) ** 0.5
+    return float((g - ref).abs().max()), rms
+
+
+@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
+def test_train_step_vs_reference(backend):
+    """One SEGAN+ G+D step (model.py:283-321) from the reference's seed state: losses, sampled
+    gradients (norm-relative), BN running stats and the post-step parameter deltas."""
+    t = golden("train_step_b4.npz")
+    B = t["clean"].shape[0]
+    s = build_segan(batch_size=B)
+    assert sd_sha(s.G.state_dict()) == str(t["sha_G"]) and sd_sha(s.D.state_dict()) == str(t["sha_D"])
+    s = s.to(DEV)
+    s.G.engine.backend = backend
+    s.D.engine.backend = backend
+    s.G.train()
+    s.D.train()
+    opts = __import__("tests.util", fromlist=["load_opts"]).load_opts(batch_size=B)
+    Gopt, Dopt = s.build_optimizers(opts)
+    random.seed(int(t["py_random_seed"]))
+    torch.manual_seed(int(t["torch_seed_z"]))
+    clean = torch.from_numpy(t["clean"]).unsqueeze(1).to(DEV)
+    noisy = torch.from_numpy(t["noisy"]).unsqueeze(1).to(DEV)
+    pre = {("G." + k): v.detach().clone() for k, v in s.G.state_dict().items()}
+    pre.update({("D." + k): v.detach().clone() for k, v in s.D.state_dict().items()})
+    # capture the D-step gradients before the G step overwrites nothing (G step skips D wgrad)
+    losses = s.train_step(clean, noisy, Gopt, Dopt, 100.0)
+    torch.cuda.synchronize()
+    lv = losses.tolist()
+    print("losses", lv, [float(t[k]) for k in ("d_real_loss", "d_fake_loss", "g_adv_loss", "g_l1_loss")])
+    assert max_abs(s.G.z.cpu(), t["z"]) == 0.0          # same z as the reference drew
+    for got, k in zip(lv, ("d_real_loss", "d_fake_loss", "g_adv_loss", "g_l1_loss")):
+        ref = float(t[k])
+        assert abs(got - ref) <= 2e-2 * max(1.0, abs(ref)), (k, got, ref)
+    ge, de = s.G.engine, s.D.engine
+    worst = {}
+    for tag, eng in (("gD.", de), ("gG.", ge)):
+        for name, p in eng.module.named_parameters():
+            if tag == "gD." and name.startswith("enc_blocks") and name.endswith("conv.bias"):
+                continue       # gradient is zero in exact arithmetic (bias feeds BatchNorm)
+            err, rms = _check_sampled(t, tag, name, eng.gview(name), 0)
+            worst[tag + name] = err / (rms + 1e-12)
+    bad = {k: v for k, v in worst.items() if v > 0.25}
+    print("worst sampled grad err / rms:", sorted(worst.items(), key=lambda kv: -kv[1])[:8])
+    assert not bad, bad
+    for name, sd in (("G.", s.G.state_dict()), ("D.", s.D.state_dict())):
+        for k, v in sd.items():
+            if "running_" in k:
+                assert max_abs(v.cpu(), t["post_full." + name + k]) <= 2e-3, k
+            elif v.dtype.is_floating_point:
+                delta = (v - pre[name + k]).detach().cpu().reshape(-1)
+                idx = torch.from_numpy(t["post_idx." + name + k])
+                ref = torch.from_numpy(t["post_delta." + name + k])
+                # RMSprop's first step is +-lr*g/(0.1|g|+eps): sign-like, so compare loosely by count
+                if "conv.bias" in k and name == "D.":
+                    continue
+                mism = float(((delta[idx] - ref).abs() > 2.5e-4).float().mean())
+                assert mism <= 0.05, (name + k, mism)
+
+
+def test_generate_chunked_vs_reference(segan):
+    g = golden("generate_40000.npz")
+    if hasattr(segan.G, "z"):
+        del segan.G.z
+    out, g_c = segan.generate(torch.from_numpy(g["wav"]), z=torch.from_numpy(g["z"]))
+    assert out.shape == g["out"].shape
+    # de-emphasis integrates the waveform error (gain 1/(1-0.95) = 20)
+    assert max_abs(out, g["out"]) <= 20 * WAVE_TOL
+    assert tuple(g_c.shape) == (1, 1024, 16)
+
+
+def test_autograd_path_matches_fused_step(segan):
+    """Generator / Discriminator used as ordinary autograd modules give the same gradients as the
+    fused step's engines (API compatibility path)."""
+    gen = torch.Generator().manual_seed(9)
+    B = 2
+    clean = (0.3 * torch.randn(B, 1, 16384, generator=gen)).to(DEV)
+    noisy = (clean.cpu() + 0.1 * torch.randn(B, 1, 16384, generator=gen)).to(DEV)
+    z = torch.randn(B, 1024, 16, generator=gen).to(DEV)
+    s = build_segan().to(DEV)
+    s.G.train()
+    s.D.train()
+    y = s.G(noisy, z=z)
+    shifts = [1, -2, 3, -4, 5]
+    logit, _ = s.D(torch.cat((y, noisy), 1), shifts=shifts)
+    loss = torch.nn.functional.mse_loss(logit.view(-1), torch.ones(B, device=DEV)) + \
+        100 * torch.nn.functional.l1_loss(y, clean)
+    loss.backward()
+    gG = {n: p.grad.detach().clone() for n, p in s.G.named_parameters()}
+    # oracle gradients on CPU
+    sdG, sdD = cpu_state(s.G), cpu_state(s.D)
+    pG = {k: sdG[k].clone().requires_grad_(True) for k in O._trainable(sdG)}
+    with O.oracle_mode():
+        yo = O.generator_forward({**sdG, **pG}, noisy.cpu(), z.cpu())
+        lo = O.discriminator_forward(dict(sdD), torch.cat((yo, noisy.cpu()), 1), shifts, training=True)
+        losso = torch.nn.functional.mse_loss(lo.view(-1), torch.ones(B)) + 100 * torch.nn.functional.l1_loss(yo, clean.cpu())
+        go = dict(zip(pG.keys(), torch.autograd.grad(losso, list(pG.values()))))
+    assert abs(float(loss) - float(losso)) <= 2e-2 * max(1.0, abs(float(losso)))
+    for k, ref in go.items():
+        assert rel_err(gG[k].cpu(), ref) <= 6e-2, (k, rel_err(gG[k].cpu(), ref))
