@@ -180,9 +180,13 @@ int sg_bn_finalize(const double* stats, int64_t count, int C, const float* gamma
                    float* scale_shift, float* mean_invstd, void* stream);
 /* h = act(a*scale + shift) written to [B][oh + Lout_rows + oh][g*C] with circular roll and
  * reflect halo (the consumer's view).  scale_shift may be NULL.  a: [B][L][C] exact.
- * out_halo_pos = halo in positions (0 or 16).  act: SG_ACT_NONE|SG_ACT_PRELU. */
+ * out_halo_pos = halo in positions (0 or 16).  act: SG_ACT_NONE|SG_ACT_PRELU.
+ * The bf16 twins feed the weight-gradient tap-GEMM, whose two operands must share one 16-bit
+ * format (tcgen05 kind::f16 rejects f16 x bf16; gradients are bf16 for range). */
 int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
-               const float* slope, int act, int roll, int out_halo_pos, void* h, void* stream);
+               const float* slope, int act, int roll, int out_halo_pos, void* h,
+               void* h_bf16 /* optional bf16 twin of h (same geometry) */,
+               void* a_bf16 /* optional bf16 copy of a (exact geometry) */, void* stream);
 /* backward of sg_act_fwd (+ optional BatchNorm backward).  g_h: gradient w.r.t. the consumer
  * view (bf16, same geometry as h incl. halo & roll) ; g_add: optional extra gradient w.r.t. the
  * activation output in exact geometry (skip connection), may be NULL.

@@ -57,7 +57,7 @@ _SIGS = {
     "sg_wave_deconv_bwd": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "sg_bn_stats": [_vp, _i, _i64, _i, _vp, _vp],
     "sg_bn_finalize": [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
-    "sg_act_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "sg_act_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "sg_act_bwd_reduce": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "sg_act_bwd_apply": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "sg_ncl_to_nlc": [_vp, _i, _i, _i, _vp, _i, _vp],

@@ -54,7 +54,10 @@ extern "C" int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream) {
   SG_CHECK_ARG(p->ksplit <= 1 || p->out_dtype == SG_F32);
   SG_CHECK_ARG(p->m_lo >= -p->out_halo && p->m_hi <= p->out_rows + p->out_halo && p->m_lo < p->m_hi);
   SG_CHECK_ARG(p->batch > 0 && p->a_rows > 0 && p->a_halo >= 0);
-  if (p->backend == SG_BACKEND_TCGEN05) return tapgemm_f_tc_launch(p, (cudaStream_t)stream);
+  if (p->backend == SG_BACKEND_TCGEN05) {
+    SG_CHECK_ARG(p->a_dtype == p->w_dtype);
+    return tapgemm_f_tc_launch(p, (cudaStream_t)stream);
+  }
   if (p->backend == SG_BACKEND_FFMA) return tapgemm_f_ffma_launch(p, (cudaStream_t)stream);
   set_error("unknown backend %d", p->backend);
   return SG_ERR_UNSUPPORTED;
@@ -71,7 +74,11 @@ extern "C" int sg_tapgemm_w_run(const sg_tapgemm_w* p, void* stream) {
   SG_CHECK_ARG(p->g_dtype == SG_F16 || p->g_dtype == SG_BF16);
   SG_CHECK_ARG(p->a_dtype == SG_F16 || p->a_dtype == SG_BF16);
   SG_CHECK_ARG(p->batch > 0 && p->g_rows > 0 && (p->g_rows >= 64 ? p->g_rows % 64 == 0 : 64 % p->g_rows == 0));
-  if (p->backend == SG_BACKEND_TCGEN05) return tapgemm_w_tc_launch(p, (cudaStream_t)stream);
+  if (p->backend == SG_BACKEND_TCGEN05) {
+    // tcgen05.mma kind::f16 raises an illegal-instruction fault for f16 x bf16 (measured on B200)
+    SG_CHECK_ARG(p->g_dtype == p->a_dtype);
+    return tapgemm_w_tc_launch(p, (cudaStream_t)stream);
+  }
   if (p->backend == SG_BACKEND_FFMA) return tapgemm_w_ffma_launch(p, (cudaStream_t)stream);
   set_error("unknown backend %d", p->backend);
   return SG_ERR_UNSUPPORTED;

@@ -89,7 +89,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 __global__ void __launch_bounds__(256)
 act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ slope, int act, int roll, int H,
-               void* __restrict__ h) {
+               void* __restrict__ h, void* __restrict__ h_bf16, void* __restrict__ a_bf16) {
   const int cgs = C / 8;
   const int Lh = L + 2 * H;
   const int64_t total = (int64_t)batch * Lh * cgs;
@@ -100,16 +100,21 @@ act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
     const int b = (int)(pr / Lh);
     const int src = unroll_idx(reflect_idx(qh - H, L), roll, L);
     const V8 v = ldv8(a, ((int64_t)b * L + src) * C + cg * 8);
-    V8 o;
+    V8 o, ob, ab;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = cg * 8 + j;
       float y = up16(v.v[j], dtype);
+      ab.v[j] = cvt16(y, SG_BF16);
       if (scale_shift) y = fmaf(y, scale_shift[c], scale_shift[C + c]);
       if (act == SG_ACT_PRELU) y = y > 0.f ? y : slope[c] * y;
       o.v[j] = cvt16(y, dtype);
+      ob.v[j] = cvt16(y, SG_BF16);
     }
     stv8(h, ((int64_t)b * Lh + qh) * C + cg * 8, o);
+    // bf16 twins: operands of the weight-gradient tap-GEMM (tcgen05 kind::f16 cannot mix f16 x bf16)
+    if (h_bf16) stv8(h_bf16, ((int64_t)b * Lh + qh) * C + cg * 8, ob);
+    if (a_bf16 && qh >= H && qh < H + L) stv8(a_bf16, ((int64_t)b * L + src) * C + cg * 8, ab);
   }
 }
 
@@ -129,12 +134,12 @@ __device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int r
 #pragma unroll
     for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
     if (H > 0) {
-      if (q0 >= 1 && q0 <= 14) {
+      if (q0 >= 1 && q0 <= H) {
         v = ldv8(g_h, (base - q0) * ldh + cg * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
       }
-      if (q0 >= L - 16 && q0 <= L - 2) {
+      if (q0 >= L - 1 - H && q0 <= L - 2) {
         v = ldv8(g_h, (base + 2 * (L - 1) - q0) * ldh + cg * 8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
@@ -462,12 +467,13 @@ extern "C" int sg_bn_finalize(const double* stats, int64_t count, int C, const f
 }
 
 extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
-                          const float* slope, int act, int roll, int out_halo_pos, void* h, void* stream) {
+                          const float* slope, int act, int roll, int out_halo_pos, void* h, void* h_bf16,
+                          void* a_bf16, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && (out_halo_pos == 0 || L >= 32));
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
   const int64_t total = (int64_t)batch * (L + 2 * out_halo_pos) * (C / 8);
   act_fwd_kernel<<<ew_grid(total, 256 * 4), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
-                                                          out_halo_pos, h);
+                                                          out_halo_pos, h, h_bf16, a_bf16);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

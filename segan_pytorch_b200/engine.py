@@ -293,27 +293,38 @@ class GeneratorEngine(_NetEngine):
         x = x.contiguous().float()
         Lq = [L // 4 ** (l + 1) for l in range(nl)]
         a, hp = [None] * nl, [None] * nl
+        # bf16 twins (only when a backward will follow): operands of the weight-gradient tap-GEMMs
+        hpb, ab, ddb, z16b = [None] * nl, [None] * nl, [None] * nl, None
         # ---- encoder
-        a[0] = buf.get("g.a0", (B, Lq[0], fm[0]), F16, dev)
-        hp[0] = buf.get("g.hp0", (B, Lq[0] + 32, fm[0]), F16, dev)
-        bias0 = self.pview("enc_blocks.0.conv.bias") if self.enc_bias else None
-        _lib.call("sg_wave_conv_fwd", _p(x), None, 1, B, L, 0, _p(self.pview("enc_blocks.0.conv.weight")),
-                  _p(bias0), fm[0], _p(a[0]), _p(self.pview("enc_blocks.0.act.weight")), _p(hp[0]), st)
-        for l in range(1, nl):
-            cin, cout = fm[l - 1], fm[l]
+        for l in range(nl):
+            cout = fm[l]
             a[l] = buf.get("g.a%d" % l, (B, Lq[l], cout), F16, dev)
             bias = self.pview("enc_blocks.%d.conv.bias" % l) if self.enc_bias else None
-            run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
-                  tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
-                  bias=bias, bias_mod=cout, backend=self.backend)
+            if l == 0:
+                _lib.call("sg_wave_conv_fwd", _p(x), None, 1, B, L, 0, _p(self.pview("enc_blocks.0.conv.weight")),
+                          _p(bias), cout, _p(a[0]), None, None, st)
+            else:
+                cin = fm[l - 1]
+                run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
+                      tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
+                      bias=bias, bias_mod=cout, backend=self.backend)
             halo = 16 if l < nl - 1 else 0
             hp[l] = buf.get("g.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
+            if want_ctx:
+                hpb[l] = buf.get("g.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), BF16, dev)
+                if l < nl - 1:
+                    ab[l] = buf.get("g.ab%d" % l, (B, Lq[l], cout), BF16, dev)
             _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, None,
-                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, 0, halo, _p(hp[l]), st)
+                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, 0, halo, _p(hp[l]), _p(hpb[l]),
+                      _p(ab[l]), st)
         # ---- z
         zc = z.shape[1]
         z16 = buf.get("g.z16", (B, Lq[-1], zc), F16, dev)
-        _lib.call("sg_ncl_to_nlc", _p(z.contiguous().float()), B, zc, Lq[-1], _p(z16), SG_F16, st)
+        zf = z.contiguous().float()
+        _lib.call("sg_ncl_to_nlc", _p(zf), B, zc, Lq[-1], _p(z16), SG_F16, st)
+        if want_ctx:
+            z16b = buf.get("g.z16b", (B, Lq[-1], zc), BF16, dev)
+            _lib.call("sg_ncl_to_nlc", _p(zf), B, zc, Lq[-1], _p(z16b), SG_BF16, st)
         # ---- decoder
         ad, dd = [None] * nl, [None] * nl
         src0, src1 = z16, hp[nl - 1]
@@ -327,15 +338,18 @@ class GeneratorEngine(_NetEngine):
                   bias=self.pview("dec_blocks.%d.deconv.bias" % l), bias_mod=cout,
                   a0_c=src0.shape[-1], a1_c=src1.shape[-1], backend=self.backend)
             dd[l] = buf.get("g.dd%d" % l, (B, 4 * lin, cout), F16, dev)
+            if want_ctx:
+                ddb[l] = buf.get("g.ddb%d" % l, (B, 4 * lin, cout), BF16, dev)
             _lib.call("sg_act_fwd", _p(ad[l]), SG_F16, B, 4 * lin, cout, None,
-                      _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, 0, _p(dd[l]), st)
+                      _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, 0, _p(dd[l]), _p(ddb[l]), None, st)
             lin *= 4
             src0, src1 = dd[l], a[nl - 2 - l]
         y = torch.empty(B, 1, L, dtype=F32, device=dev)
         _lib.call("sg_wave_deconv_fwd", _p(src0), src0.shape[-1], _p(src1), src1.shape[-1], B, lin,
                   _p(self.packed["w_last_eff"]), _p(self.pview("dec_blocks.%d.deconv.bias" % (nl - 1))),
                   _p(y), st)
-        ctx = dict(x=x, B=B, L=L, Lq=Lq, a=a, hp=hp, z16=z16, ad=ad, dd=dd, y=y) if want_ctx else None
+        ctx = dict(x=x, B=B, L=L, Lq=Lq, a=a, hp=hp, z16=z16, ad=ad, dd=dd, y=y, hpb=hpb, ab=ab, ddb=ddb,
+                   z16b=z16b) if want_ctx else None
         return y, ctx
 
     def hidden_ncl(self, ctx):
@@ -404,15 +418,15 @@ class GeneratorEngine(_NetEngine):
             self.gview("dec_blocks.%d.act.weight" % l).add_(red[0].float())
             self.gview("dec_blocks.%d.deconv.bias" % l).add_(red[1].float())
             if l == 0:
-                s0, s1 = ctx["z16"], hp[nl - 1]
+                s0, s1 = ctx["z16b"], ctx["hpb"][nl - 1]
             else:
-                s0, s1 = dd[l - 1], a[nl - 1 - l]
+                s0, s1 = ctx["ddb"][l - 1], ctx["ab"][nl - 1 - l]
             c0, c1 = s0.shape[-1], s1.shape[-1]
             taps = tap_ranges("deconv_fwd", cout, cin, 4 * cout)
             dwp = dwp_all[:9 * 4 * cout * cin]
             dwp.zero_()
             n_tiles = 9 * (4 * cout // 128) * max(1, cin // 256)
-            run_w(g_ad, lin, SG_BF16, s0, s1, lin, 0, SG_F16, cin, 4 * cout, taps, dwp, B,
+            run_w(g_ad, lin, SG_BF16, s0, s1, lin, 0, SG_BF16, cin, 4 * cout, taps, dwp, B,
                   ksplit=wgrad_ksplit(B * lin, n_tiles), a0_c=c0, a1_c=c1, backend=self.backend)
             alpha = self.alpha_for_dec(l)
             galpha = self.gview("alpha_%d.skip_k" % (nl - 1 - l)).view(-1) if l > 0 else None
@@ -453,7 +467,7 @@ class GeneratorEngine(_NetEngine):
             dwp_l = dwp_all[:9 * cout * 4 * cin]
             dwp_l.zero_()
             n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
-            run_w(g_a, Lq[l], SG_BF16, hp[l - 1], None, Lq[l], 4, SG_F16, 4 * cin, cout, taps, dwp_l, B,
+            run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout, taps, dwp_l, B,
                   ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
             _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
                       _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, st)
@@ -494,7 +508,7 @@ class DiscriminatorEngine(_NetEngine):
         _lib.call("sg_pack_weights", 2, _p(w1), nout, C_, T, None, 0, _p(w1p), _p(w1d), SG_F16, SG_BF16, st)
         self.packed["W1p"], self.packed["W1dg"] = w1p, w1d
 
-    def forward(self, x0, x1, shifts, training=True, fresh=False):
+    def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True):
         """x0: candidate (B,1,L), x1: reference/noisy (B,1,L) -- the reference's cat((x_, ref), 1)
         (model.py:173-175) is never materialised.  shifts: nl signed phase shifts."""
         _require_cuda(x0, x1)
@@ -507,7 +521,7 @@ class DiscriminatorEngine(_NetEngine):
         x1 = x1.contiguous().float()
         Lq = [L // 4 ** (l + 1) for l in range(nl)]
         assert Lq[-1] * fm[-1] == self.pview("fc.0.weight").shape[1], "D expects L = 16384"
-        a, hp, ss, mi = [None] * nl, [None] * nl, [None] * nl, [None] * nl
+        a, hp, ss, mi, hpb = [None] * nl, [None] * nl, [None] * nl, [None] * nl, [None] * nl
         for l in range(nl):
             cout = fm[l]
             a[l] = buf.get("d.a%d" % l, (B, Lq[l], cout), F16, dev)
@@ -541,8 +555,10 @@ class DiscriminatorEngine(_NetEngine):
             halo = 16 if l < nl - 1 else 0
             roll = int(shifts[l + 1]) if l < nl - 1 else 0
             hp[l] = buf.get("d.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
+            hpb[l] = buf.get("d.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), BF16, dev) if twins else None
             _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, _p(ss[l]),
-                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, roll, halo, _p(hp[l]), st)
+                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, roll, halo, _p(hp[l]), _p(hpb[l]),
+                      None, st)
         # ---- FC head
         kin = Lq[-1] * fm[-1]
         acc = buf.get("d.fc0", (B, 256), F32, dev, zero=True)
@@ -555,7 +571,7 @@ class DiscriminatorEngine(_NetEngine):
         _lib.call("sg_fc_tail_fwd", _p(acc), _p(self.pview("fc.0.bias")), _p(self.pview("fc.1.weight")),
                   _p(self.pview("fc.2.weight")), _p(self.pview("fc.2.bias")), _p(self.pview("fc.3.weight")),
                   _p(self.pview("fc.4.weight")), _p(self.pview("fc.4.bias")), B, _p(z1), _p(z2), _p(logit), st)
-        ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, ss=ss, mi=mi, z1=z1, z2=z2, logit=logit,
+        ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, hpb=hpb, ss=ss, mi=mi, z1=z1, z2=z2, logit=logit,
                    shifts=[int(s) for s in shifts])
         return logit, ctx
 
@@ -583,7 +599,7 @@ class DiscriminatorEngine(_NetEngine):
             dwp = buf.get("d.dwp", (9 * 4 * fm[-2] * fm[-1],), F32, dev)
             dw1 = dwp[:256 * kin]
             dw1.zero_()
-            run_w(g_z1, 1, SG_BF16, hp[-1], None, 1, 0, SG_F16, kin, 256, tap_ranges("full", 0, kin, 256), dw1, B,
+            run_w(g_z1, 1, SG_BF16, ctx["hpb"][-1], None, 1, 0, SG_BF16, kin, 256, tap_ranges("full", 0, kin, 256), dw1, B,
                   d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
             _lib.call("sg_unpack_wgrad", 2, _p(dw1), 256, fm[-1], Lq[-1], None, None, 0,
                       _p(self.gview("fc.0.weight")), None, 1, st)
@@ -627,7 +643,7 @@ class DiscriminatorEngine(_NetEngine):
                 dwp_l = dwp[:9 * cout * 4 * cin]
                 dwp_l.zero_()
                 n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
-                run_w(g_a, Lq[l], SG_BF16, hp[l - 1], None, Lq[l], 4, SG_F16, 4 * cin, cout,
+                run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout,
                       tap_ranges("conv_fwd", cin, 4 * cin, cout), dwp_l, B,
                       ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
                 _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
