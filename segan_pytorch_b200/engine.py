@@ -29,7 +29,9 @@ def default_backend():
 
 
 def _p(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else None
+    if t is None or isinstance(t, C.c_void_p):
+        return t
+    return C.c_void_p(t.data_ptr())
 
 
 def _stream():
