@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of BASELINE.json: 16384-sample windows/s of one full SEGAN+
+G+D train step (batch 300 per GPU, synthetic clean/noisy pairs, RMSprop, LSGAN + L1).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port), host cores
+
+A "step" = the hot path over one batch: G fwd, D(real) fwd+bwd, D(fake) fwd+bwd, D RMSprop,
+D(fake) fwd + dgrad through the updated D, L1, G bwd, G RMSprop (segan/models/model.py:283-321).
+`value`  : device-timed (CUDA events), inputs already resident in HBM.
+`e2e`    : same step through SEGAN.train's per-batch path with pinned HOST buffers: H2D copy of the
+           batch and D2H read of the four losses inside the timed region.
+`roofline`: the dominant kernel (tcgen05 forward-form tap-GEMM), algorithmic FLOPs / CUDA-event time.
+`cpu_baseline`: the oracle (CPU restatement of the reference step) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+ALG_GFLOP_PER_WINDOW = 35.8          # algorithmic FLOPs of one G+D step per window
+WORKLOAD = "SEGAN+ G+D train step, batch 300/GPU, 16384-sample windows, synthetic pairs (BASELINE configs[1])"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
+                    hbm=float(d.get("hbm_gbs", 6650.0)), src="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def synth_batch(B, seed):
+    """clean = 0.3*randn, noisy = clean + 0.1*randn, clamped to [-1, 1]."""
+    g = torch.Generator().manual_seed(seed)
+    clean = (0.3 * torch.randn(B, 16384, generator=g)).clamp_(-1, 1)
+    noisy = (clean + 0.1 * torch.randn(B, 16384, generator=g)).clamp_(-1, 1)
+    return clean, noisy
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (CPU restatement of model.py:283-321) on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, B):
+    import random
+    from oracle import segan_oracle as O
+    from tests.util import build_segan, cpu_state
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = build_segan(batch_size=B)
+    sdG, sdD = cpu_state(s.G), cpu_state(s.D)
+    sqG = {k: torch.zeros_like(sdG[k]) for k in O._trainable(sdG)}
+    sqD = {k: torch.zeros_like(sdD[k]) for k in O._trainable(sdD)}
+    clean, noisy = synth_batch(B, 111)
+    clean, noisy = clean.unsqueeze(1), noisy.unsqueeze(1)
+    random.seed(111)
+    times = []
+    for it in range(warmup + steps):
+        z = torch.randn(B, 1024, 16)
+        shifts3 = [O.draw_phase_shifts(5, 5) for _ in range(3)]
+        t0 = time.perf_counter()
+        O.segan_train_step(sdG, sdD, sqG, sqD, clean, noisy, z, shifts3, l1_weight=100.0)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return B * len(times) / total, total / len(times), torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.ref_batch
+    wps, spstep, cores = cpu_reference_steps(args.steps, max(1, min(args.warmup, 2)), B)
+    line = {
+        "impl": "reference", "metric": "16384-sample windows/sec (G+D train step)", "value": wps,
+        "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU path = oracle port of segan/models/model.py:283-321 "
+                   "(the Python reference is not installable on the GPU box); each step is a bounded sample of "
+                   "%d windows of the batch-300 workload; windows/s is batch-normalised" % B},
+        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+                         "sample": "%d timed steps of a %d-window batch, oneDNN off (SURVEY.md F1)" % (args.steps, B)},
+        "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=300, help="windows per GPU (BASELINE: 300)")
+    ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample size of the reference arm")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--backend", default=None, help="tcgen05 (default) | ffma")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    if args.backend:
+        os.environ["SEGAN_B200_BACKEND"] = args.backend
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from segan_pytorch_b200 import _lib, engine as E
+    from tests.util import build_segan, load_opts
+    if not _lib.device_ok():
+        raise SystemExit("bench.py needs an sm_100-class GPU and libsegan_b200.so (no fallback path)")
+    B = args.batch
+    opts = load_opts(batch_size=B, z_device="cuda")
+    s = build_segan(seed=111, batch_size=B, z_device="cuda").to(dev)      # identical init on every rank
+    s.G.train()
+    s.D.train()
+    Gopt, Dopt = s.build_optimizers(opts)
+    clean_h, noisy_h = synth_batch(B, 111 + rank)                          # per-rank data shard
+    clean_h, noisy_h = clean_h.pin_memory(), noisy_h.pin_memory()
+    clean = clean_h.to(dev).unsqueeze(1)
+    noisy = noisy_h.to(dev).unsqueeze(1)
+    import random
+    random.seed(111 + rank)
+    torch.manual_seed(111 + rank)
+    losses = torch.zeros(4, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        s.train_step(clean, noisy, Gopt, Dopt, 100.0, losses=losses)
+    barrier()
+    # ---- timed region 1: device-resident inputs, live per-kernel profile
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    E.PROFILE = []
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        s.train_step(clean, noisy, Gopt, Dopt, 100.0, losses=losses)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - launches0
+    prof = E.PROFILE
+    E.PROFILE = None
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- timed region 2: end to end through the public per-batch path with host buffers
+    cbuf = torch.empty(B, 1, 16384, device=dev)
+    nbuf = torch.empty(B, 1, 16384, device=dev)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    host_loss = None
+    for _ in range(args.steps):
+        cbuf.copy_(clean_h.unsqueeze(1), non_blocking=True)                # H2D of this step's batch
+        nbuf.copy_(noisy_h.unsqueeze(1), non_blocking=True)
+        ls = s.train_step(cbuf, nbuf, Gopt, Dopt, 100.0, losses=losses)
+        host_loss = ls.tolist()                                            # D2H read of the step's losses
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # max over ranks
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_windows = B * world * args.steps
+    value = total_windows / (ms * 1e-3)
+    e2e_value = total_windows / (ms_e2e * 1e-3)
+    # ---- roofline of the dominant kernel from the live CUDA-event profile
+    peaks = measured_peaks()
+    agg = {}
+    for kind, s_ev, e_ev, flops in prof:
+        a = agg.setdefault(kind, [0.0, 0.0, 0])
+        a[0] += s_ev.elapsed_time(e_ev) * 1e-3
+        a[1] += flops
+        a[2] += 1
+    step_s = ms * 1e-3 / args.steps
+    dom = max(agg.items(), key=lambda kv: kv[1][0])[0] if agg else None
+    roof = None
+    kern = {}
+    for kind, (sec, fl, n) in agg.items():
+        kern[kind] = {"launches_per_step": n / args.steps, "ms_per_step": sec * 1e3 / args.steps,
+                      "share_of_step": sec / (ms * 1e-3), "tflops": fl / sec / 1e12 if sec > 0 else None}
+    if dom:
+        sec, fl, n = agg[dom]
+        ach = fl / sec / 1e12
+        roof = {"kernel": dom + "_tc (tcgen05 tap-GEMM)", "bound": "tensor", "achieved": ach, "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None,
+                "peak_source": peaks["src"], "avg_launch_ms": sec * 1e3 / n,
+                "alg_flops_per_launch": fl / n, "kernels": kern,
+                "whole_step_tflops": ALG_GFLOP_PER_WINDOW * 1e9 * B / step_s / 1e12}
+    cpu = None
+    if not args.no_cpu_baseline:
+        wps, spstep, cores = cpu_reference_steps(args.cpu_baseline_steps, 1, args.ref_batch)
+        cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
+               "sample": "%d timed steps of a %d-window batch of the same workload (oracle, oneDNN off)"
+                         % (args.cpu_baseline_steps, args.ref_batch)}
+    line = {
+        "metric": "16384-sample windows/sec (G+D train step)", "value": value, "unit": "windows/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate (bf16 gradient tensors)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "window": 16384,
+                   "parallelism": "dp%d" % world, "optimizer": "rmsprop lr 5e-5", "l1_weight": 100,
+                   "z": "device RNG (opts.z_device='cuda')", "backend": args.backend or "tcgen05",
+                   "l2": "per-step working set (packed weights 0.4 GB + activations > 2 GB) exceeds the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 2 * B * 16384 * 4, "d2h_bytes_per_step": 16, "last_losses": host_loss},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

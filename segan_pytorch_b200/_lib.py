@@ -103,8 +103,15 @@ def load():
     return lib
 
 
+# kernels launched per C-ABI call (memsets not counted); used for bench.py's gpu_launches claim
+LAUNCHES_PER_CALL = {"sg_colsum": 2, "sg_wave_deconv_bwd": 3, "sg_fc_tail_bwd": 2}
+launch_count = 0
+
+
 def call(name, *args):
+    global launch_count
     lib = load()
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise SeganB200Error("%s failed (%d): %s" % (name, rc, lib.sg_last_error().decode(errors="replace")))

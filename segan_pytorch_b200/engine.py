@@ -70,6 +70,37 @@ def tap_ranges(kind, c, kc, nc):
     return k_lo, k_hi, n_lo, n_hi
 
 
+# optional live profiling (bench.py): list of (kind, start_event, end_event, algorithmic_flops)
+PROFILE = None
+
+
+def _tap_flops(taps, d_lo, d_hi, n_lo, n_hi, rows):
+    f = 0
+    for d in range(d_lo, d_hi + 1):
+        i = d + 4
+        nn = max(0, min(n_hi, taps[3][i]) - max(n_lo, taps[2][i]))
+        f += 2 * rows * nn * (taps[1][i] - taps[0][i])
+    return f
+
+
+class _Prof(object):
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.kind, self.s, self.e, self.flops))
+        return False
+
+
 def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dtype, out_rows, out_halo,
           m_lo, m_hi, batch, bias=None, bias_mod=0, n_lo=0, n_hi=None, d_lo=-4, d_hi=4, w_tap0=0,
           out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0):
@@ -88,7 +119,8 @@ def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dt
     q.bias, q.bias_mod = _p(bias), bias_mod
     q.batch, q.ksplit = batch, ksplit
     q.backend = default_backend() if backend is None else backend
-    _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
+    with _Prof("tapgemm_f", _tap_flops(taps, d_lo, d_hi, q.n_lo, q.n_hi, (m_hi - m_lo) * batch)):
+        _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
 
 
 def run_w(g, g_rows, g_dtype, a0, a1, a_rows, a_halo, a_dtype, kc, nc, taps, dw, batch, d_lo=-4, d_hi=4,
@@ -105,7 +137,8 @@ def run_w(g, g_rows, g_dtype, a0, a1, a_rows, a_halo, a_dtype, kc, nc, taps, dw,
     q.dw, q.dw_tap0 = _p(dw), dw_tap0
     q.batch, q.ksplit = batch, ksplit
     q.backend = default_backend() if backend is None else backend
-    _lib.call("sg_tapgemm_w_run", C.byref(q), _stream())
+    with _Prof("tapgemm_w", _tap_flops(taps, d_lo, d_hi, 0, nc, g_rows * batch)):
+        _lib.call("sg_tapgemm_w_run", C.byref(q), _stream())
 
 
 def wgrad_ksplit(total_positions, n_tiles):
