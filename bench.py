@@ -106,8 +106,24 @@ def cpu_reference_steps(steps, warmup, B):
     import random
     from oracle import segan_oracle as O
     from tests.util import build_segan, cpu_state
-    torch.set_num_threads(os.cpu_count() or 1)
     s = build_segan(batch_size=B)
+    # "all the host threads it can use": the reference's CPU convs (slow_conv2d / im2col) stop scaling
+    # well before 128 threads; probe a few thread counts on one G forward and keep the fastest
+    ncpu = os.cpu_count() or 1
+    best_nt, best_t = 1, None
+    xs = torch.randn(2, 1, 16384)
+    zs = torch.randn(2, 1024, 16)
+    sd_probe = cpu_state(s.G)
+    for nt in sorted(set(min(ncpu, n) for n in (8, 16, 32, 64, 128))):
+        torch.set_num_threads(nt)
+        with O.oracle_mode(), torch.no_grad():
+            O.generator_forward(sd_probe, xs, zs)
+            t0 = time.perf_counter()
+            O.generator_forward(sd_probe, xs, zs)
+            dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_nt, best_t = nt, dt
+    torch.set_num_threads(best_nt)
     sdG, sdD = cpu_state(s.G), cpu_state(s.D)
     sqG = {k: torch.zeros_like(sdG[k]) for k in O._trainable(sdG)}
     sqD = {k: torch.zeros_like(sdD[k]) for k in O._trainable(sdD)}
@@ -211,6 +227,7 @@ def main():
     if rank == 0:
         sampler.start()
     E.PROFILE = []
+    _lib.call_profile = []
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -223,6 +240,8 @@ def main():
     launches = _lib.launch_count - launches0
     prof = E.PROFILE
     E.PROFILE = None
+    calls = _lib.call_profile
+    _lib.call_profile = None
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 2: end to end through the public per-batch path with host buffers
     cbuf = torch.empty(B, 1, 16384, device=dev)
@@ -265,13 +284,20 @@ def main():
     for kind, (sec, fl, n) in agg.items():
         kern[kind] = {"launches_per_step": n / args.steps, "ms_per_step": sec * 1e3 / args.steps,
                       "share_of_step": sec / (ms * 1e-3), "tflops": fl / sec / 1e12 if sec > 0 else None}
+    by_call = {}
+    for name, s_ev, e_ev in calls:
+        c = by_call.setdefault(name, [0.0, 0])
+        c[0] += s_ev.elapsed_time(e_ev)
+        c[1] += 1
+    call_ms = {k: {"ms_per_step": round(v[0] / args.steps, 4), "calls_per_step": v[1] / args.steps}
+               for k, v in sorted(by_call.items(), key=lambda kv: -kv[1][0])}
     if dom:
         sec, fl, n = agg[dom]
         ach = fl / sec / 1e12
         roof = {"kernel": dom + "_tc (tcgen05 tap-GEMM)", "bound": "tensor", "achieved": ach, "peak": peaks["tflops"],
                 "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None,
                 "peak_source": peaks["src"], "avg_launch_ms": sec * 1e3 / n,
-                "alg_flops_per_launch": fl / n, "kernels": kern,
+                "alg_flops_per_launch": fl / n, "kernels": kern, "abi_calls": call_ms,
                 "whole_step_tflops": ALG_GFLOP_PER_WINDOW * 1e9 * B / step_s / 1e12}
     cpu = None
     if not args.no_cpu_baseline:

@@ -108,11 +108,23 @@ LAUNCHES_PER_CALL = {"sg_colsum": 2, "sg_wave_deconv_bwd": 3, "sg_fc_tail_bwd": 
 launch_count = 0
 
 
+# optional live timing of every C-ABI call (bench.py): list of (name, start_event, end_event)
+call_profile = None
+
+
 def call(name, *args):
     global launch_count
     lib = load()
     launch_count += LAUNCHES_PER_CALL.get(name, 1)
-    rc = getattr(lib, name)(*args)
+    if call_profile is not None:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        call_profile.append((name, s, e))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise SeganB200Error("%s failed (%d): %s" % (name, rc, lib.sg_last_error().decode(errors="replace")))
 
