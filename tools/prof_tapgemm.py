@@ -1,0 +1,90 @@
+"""Launches representative SEGAN+ layer shapes of the two tcgen05 tap-GEMMs at batch 300 (for ncu /
+timing): conv fwd enc2 (Cin 128 -> 256), deconv fwd dec1 (1024 -> 256, two K sources), conv dgrad enc3,
+wgrad enc2, wgrad dec1.  Prints CUDA-event times and TFLOP/s."""
+import sys
+
+import torch
+
+from segan_pytorch_b200 import engine as E
+from segan_pytorch_b200._lib import SG_BF16, SG_F16
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+REP = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = "cuda"
+h = lambda *s: (torch.randn(*s, device=dev) * 0.5).half()
+b = lambda *s: (torch.randn(*s, device=dev) * 0.5).bfloat16()
+
+
+def timeit(name, fn, flops):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(REP):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / REP
+    print("%-28s %8.3f ms  %7.1f TFLOP/s" % (name, ms, flops / ms / 1e9))
+
+
+def conv_fwd(cin, cout, R):
+    a = h(B, R + 8, 4 * cin)
+    w = h(9, cout, 4 * cin)
+    out = torch.empty(B, R, cout, device=dev, dtype=torch.float16)
+    taps = E.tap_ranges("conv_fwd", cin, 4 * cin, cout)
+    fl = E._tap_flops(taps, -4, 4, 0, cout, R * B)
+    timeit("conv_fwd %d->%d R=%d" % (cin, cout, R),
+           lambda: E.run_f(a, None, R, 4, SG_F16, w, SG_F16, 4 * cin, cout, taps, out, SG_F16, R, 0, 0, R, B, backend=1), fl)
+
+
+def deconv_fwd(cin, cout, R):
+    a0, a1 = h(B, R, cin // 2), h(B, R, cin // 2)
+    w = h(9, 4 * cout, cin)
+    out = torch.empty(B, R, 4 * cout, device=dev, dtype=torch.float16)
+    taps = E.tap_ranges("deconv_fwd", cout, cin, 4 * cout)
+    fl = E._tap_flops(taps, -4, 4, 0, 4 * cout, R * B)
+    timeit("deconv_fwd %d->%d R=%d" % (cin, cout, R),
+           lambda: E.run_f(a0, a1, R, 0, SG_F16, w, SG_F16, cin, 4 * cout, taps, out, SG_F16, R, 0, 0, R, B,
+                           a0_c=cin // 2, a1_c=cin // 2, backend=1), fl)
+
+
+def conv_dgrad(cin, cout, R):
+    g = b(B, R, cout)
+    w = b(9, 4 * cin, cout)
+    out = torch.empty(B, R + 8, 4 * cin, device=dev, dtype=torch.bfloat16)
+    taps = E.tap_ranges("conv_dgrad", cin, cout, 4 * cin)
+    fl = E._tap_flops(taps, -4, 4, 0, 4 * cin, (R + 8) * B)
+    timeit("conv_dgrad %d<-%d R=%d" % (cin, cout, R),
+           lambda: E.run_f(g, None, R, 0, SG_BF16, w, SG_BF16, cout, 4 * cin, taps, out, SG_BF16, R, 4, -4, R + 4, B,
+                           backend=1), fl)
+
+
+def conv_wgrad(cin, cout, R):
+    g = b(B, R, cout)
+    a = b(B, R + 8, 4 * cin)
+    dw = torch.zeros(9, cout, 4 * cin, device=dev)
+    taps = E.tap_ranges("conv_fwd", cin, 4 * cin, cout)
+    fl = E._tap_flops(taps, -4, 4, 0, cout, R * B)
+    nt = 9 * (cout // 128) * max(1, 4 * cin // 256)
+    ks = E.wgrad_ksplit(B * R, nt)
+    timeit("conv_wgrad %d->%d R=%d ks=%d" % (cin, cout, R, ks),
+           lambda: E.run_w(g, R, SG_BF16, a, None, R, 4, SG_BF16, 4 * cin, cout, taps, dw, B, ksplit=ks, backend=1), fl)
+
+
+if __name__ == "__main__":
+    conv_fwd(64, 128, 1024)
+    conv_fwd(128, 256, 256)
+    conv_fwd(256, 512, 64)
+    conv_fwd(512, 1024, 16)
+    deconv_fwd(2048, 512, 16)
+    deconv_fwd(1024, 256, 64)
+    deconv_fwd(512, 128, 256)
+    deconv_fwd(256, 64, 1024)
+    conv_dgrad(256, 512, 64)
+    conv_dgrad(64, 128, 1024)
+    conv_wgrad(64, 128, 1024)
+    conv_wgrad(128, 256, 256)
+    conv_wgrad(256, 512, 64)
+    conv_wgrad(512, 1024, 16)
