@@ -224,7 +224,7 @@ int sg_fc_tail_fwd(const float* fc0_acc, const float* b0, const float* s1, const
 int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit,
                    const float* g_logit_in /* or NULL: use the fused MSE gradient below */, float target, float weight,
                    const float* s1, const float* w2, const float* s3, const float* w4, int batch,
-                   float* loss_out, void* g_z1_bf16, float* ws /* fp32 [B*(1+128+256)] */,
+                   float* loss_out, void* g_z1_bf16, float* ws /* fp32 [B*(1+128+256+256)] */,
                    float* g_b0, float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4,
                    float* g_b4, void* stream);
 /* G regression loss (model.py:318): loss = w * mean|y - clean| ; gy (+)= w*sign(y-clean)/(B*L) */

@@ -331,13 +331,14 @@ fc_tail_fwd_kernel(const float* __restrict__ fc0_acc, const float* __restrict__ 
   }
 }
 
-// per-row backward: g_z2 [B][128] and g_z1 [B][256] (fp32 workspaces) + bf16 copy of g_z1
+// per-row backward: g_z2 [B][128], g_z1 [B][256], g_h1 [B][256] (fp32 workspaces) + bf16 copy of g_z1
 __global__ void __launch_bounds__(256)
 fc_tail_bwd_rows_kernel(const float* __restrict__ z1, const float* __restrict__ z2, const float* __restrict__ logit,
-                        const float* __restrict__ g_logit_in, float target, float weight, const float* __restrict__ s1, const float* __restrict__ w2,
+                        const float* __restrict__ g_logit_in, float target, float weight,
+                        const float* __restrict__ s1, const float* __restrict__ w2,
                         const float* __restrict__ s3, const float* __restrict__ w4, int batch,
                         float* __restrict__ loss_out, float* __restrict__ g_logit_ws, float* __restrict__ g_z2_ws,
-                        float* __restrict__ g_z1_ws, void* __restrict__ g_z1_bf16) {
+                        float* __restrict__ g_z1_ws, float* __restrict__ g_h1_ws, void* __restrict__ g_z1_bf16) {
   __shared__ float gz2[FC2];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float diff = logit[b] - target;
@@ -359,74 +360,74 @@ fc_tail_bwd_rows_kernel(const float* __restrict__ z1, const float* __restrict__ 
   const float z = z1[(int64_t)b * FC1 + tid];
   const float g = z > 0.f ? gh1 : gh1 * s1[tid];
   g_z1_ws[(int64_t)b * FC1 + tid] = g;
+  g_h1_ws[(int64_t)b * FC1 + tid] = gh1;
   st16(g_z1_bf16, (int64_t)b * FC1 + tid, g, SG_BF16);
 }
 
-// parameter gradients of the head: one thread per output element, serial over the batch
-__global__ void fc_tail_bwd_params_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
-                                          const float* __restrict__ g_logit, const float* __restrict__ g_z2,
-                                          const float* __restrict__ g_z1, const float* __restrict__ s1,
-                                          const float* __restrict__ s3, const float* __restrict__ w2,
-                                          const float* __restrict__ w4, int batch, float* __restrict__ g_b0,
-                                          float* __restrict__ g_s1, float* __restrict__ g_w2, float* __restrict__ g_b2,
-                                          float* __restrict__ g_s3, float* __restrict__ g_w4, float* __restrict__ g_b4) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < FC2 * FC1) {                 // g_w2[j][i] = sum_b g_z2[b][j] * h1[b][i]
-    const int j = idx / FC1, i = idx % FC1;
-    const float sl = s1[i];
+// parameter gradients of the head: blockIdx.y = chunk of 16 batch rows, one thread per output
+// element, partial sums merged with one atomic per (element, chunk)
+constexpr int FC_CHUNK = 16;
+__global__ void __launch_bounds__(256)
+fc_tail_bwd_params_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                          const float* __restrict__ g_logit, const float* __restrict__ g_z2,
+                          const float* __restrict__ g_z1, const float* __restrict__ g_h1,
+                          const float* __restrict__ s1, const float* __restrict__ s3,
+                          const float* __restrict__ w4, int batch, float* __restrict__ g_b0, float* __restrict__ g_s1, float* __restrict__ g_w2,
+                          float* __restrict__ g_b2, float* __restrict__ g_s3, float* __restrict__ g_w4,
+                          float* __restrict__ g_b4) {
+  __shared__ float h1s[FC_CHUNK][FC1];
+  __shared__ float gz2s[FC_CHUNK][FC2];
+  const int b0 = blockIdx.y * FC_CHUNK;
+  const int nb = min(FC_CHUNK, batch - b0);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nb * FC1; i += 256) {
+    const int r = i / FC1, c = i % FC1;
+    const float z = z1[(int64_t)(b0 + r) * FC1 + c];
+    h1s[r][c] = z > 0.f ? z : s1[c] * z;
+  }
+  for (int i = tid; i < nb * FC2; i += 256) gz2s[i / FC2][i % FC2] = g_z2[(int64_t)(b0 + i / FC2) * FC2 + i % FC2];
+  __syncthreads();
+  if (blockIdx.x < FC2) {                  // g_w2 row j = blockIdx.x, column i = tid
+    const int j = blockIdx.x, i = tid;
     float s = 0.f;
-    for (int b = 0; b < batch; ++b) {
-      const float z = z1[(int64_t)b * FC1 + i];
-      const float h = z > 0.f ? z : sl * z;
-      s = fmaf(g_z2[(int64_t)b * FC2 + j], h, s);
-    }
-    g_w2[idx] += s;
+    for (int r = 0; r < nb; ++r) s = fmaf(gz2s[r][j], h1s[r][i], s);
+    atomicAdd(g_w2 + j * FC1 + i, s);
     return;
   }
-  int r = idx - FC2 * FC1;
-  if (r < FC1) {                         // g_b0, g_s1
+  // last x-block: the vector gradients
+  {
+    const int i = tid;                     // FC1 outputs: g_b0, g_s1
     float sb = 0.f, ss = 0.f;
-    const float sl = s1[r];
-    for (int b = 0; b < batch; ++b) {
-      const float g = g_z1[(int64_t)b * FC1 + r];
-      const float z = z1[(int64_t)b * FC1 + r];
-      sb += g;
-      // g_z1 = g_h1 * (z>0 ? 1 : s1)  =>  d s1 = sum g_h1 * z [z<=0]; recover g_h1 only where needed
-      if (z <= 0.f) {
-        // g_h1 = sum_j g_z2[b][j] * w2[j][r]
-        float gh = 0.f;
-        for (int j = 0; j < FC2; ++j) gh = fmaf(g_z2[(int64_t)b * FC2 + j], w2[j * FC1 + r], gh);
-        ss = fmaf(gh, z, ss);
-      }
+    for (int r = 0; r < nb; ++r) {
+      const int64_t o = (int64_t)(b0 + r) * FC1 + i;
+      sb += g_z1[o];
+      const float z = z1[o];
+      if (z <= 0.f) ss = fmaf(g_h1[o], z, ss);
     }
-    (void)sl;
-    g_b0[r] += sb;
-    g_s1[r] += ss;
-    return;
+    atomicAdd(g_b0 + i, sb);
+    atomicAdd(g_s1 + i, ss);
   }
-  r -= FC1;
-  if (r < FC2) {                         // g_b2, g_s3, g_w4
+  if (tid < FC2) {
+    const int j = tid;
     float sb = 0.f, ss = 0.f, sw = 0.f;
-    const float sl = s3[r];
-    const float w = w4[r];
-    for (int b = 0; b < batch; ++b) {
-      const float z = z2[(int64_t)b * FC2 + r];
-      const float gl = g_logit[b];
-      sb += g_z2[(int64_t)b * FC2 + r];
+    const float sl = s3[j];
+    for (int r = 0; r < nb; ++r) {
+      const float z = z2[(int64_t)(b0 + r) * FC2 + j];
+      const float gl = g_logit[b0 + r];
+      const float g = gz2s[r][j];
+      sb += g;
       const float h = z > 0.f ? z : sl * z;
       sw = fmaf(gl, h, sw);
-      if (z <= 0.f) ss = fmaf(gl * w, z, ss);
+      if (z <= 0.f) ss = fmaf(gl * w4[j], z, ss);        // d s3 = sum g_h2 * z [z<=0], g_h2 = g_logit*w4
     }
-    g_b2[r] += sb;
-    g_s3[r] += ss;
-    g_w4[r] += sw;
-    return;
+    atomicAdd(g_b2 + j, sb);
+    atomicAdd(g_s3 + j, ss);
+    atomicAdd(g_w4 + j, sw);
   }
-  r -= FC2;
-  if (r == 0) {
+  if (tid == 0) {
     float s = 0.f;
-    for (int b = 0; b < batch; ++b) s += g_logit[b];
-    g_b4[0] += s;
+    for (int r = 0; r < nb; ++r) s += g_logit[b0 + r];
+    atomicAdd(g_b4, s);
   }
 }
 
@@ -550,20 +551,21 @@ extern "C" int sg_fc_tail_fwd(const float* fc0_acc, const float* b0, const float
 extern "C" int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit, const float* g_logit_in,
                               float target, float weight,
                               const float* s1, const float* w2, const float* s3, const float* w4, int batch,
-                              float* loss_out, void* g_z1_bf16, float* ws /* [B*(1+128+256)] */, float* g_b0,
+                              float* loss_out, void* g_z1_bf16, float* ws /* [B*(1+128+256+256)] */, float* g_b0,
                               float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4, float* g_b4,
                               void* stream) {
   SG_CHECK_ARG(ws && g_z1_bf16);
   float* g_logit = ws;
   float* g_z2 = ws + batch;
   float* g_z1 = g_z2 + (int64_t)batch * FC2;
-  fc_tail_bwd_rows_kernel<<<batch, 256, 0, ST>>>(z1, z2, logit, g_logit_in, target, weight, s1, w2, s3, w4, batch, loss_out,
-                                                 g_logit, g_z2, g_z1, g_z1_bf16);
+  float* g_h1 = g_z1 + (int64_t)batch * FC1;
+  fc_tail_bwd_rows_kernel<<<batch, 256, 0, ST>>>(z1, z2, logit, g_logit_in, target, weight, s1, w2, s3, w4, batch,
+                                                 loss_out, g_logit, g_z2, g_z1, g_h1, g_z1_bf16);
   SG_CHECK_LAUNCH();
   if (g_w2) {
-    const int n = FC2 * FC1 + FC1 + FC2 + 1;
-    fc_tail_bwd_params_kernel<<<(n + 127) / 128, 128, 0, ST>>>(z1, z2, g_logit, g_z2, g_z1, s1, s3, w2, w4, batch,
-                                                               g_b0, g_s1, g_w2, g_b2, g_s3, g_w4, g_b4);
+    dim3 grid(FC2 + 1, (batch + FC_CHUNK - 1) / FC_CHUNK);
+    fc_tail_bwd_params_kernel<<<grid, 256, 0, ST>>>(z1, z2, g_logit, g_z2, g_z1, g_h1, s1, s3, w4, batch, g_b0, g_s1,
+                                                    g_w2, g_b2, g_s3, g_w4, g_b4);
     SG_CHECK_LAUNCH();
   }
   return SG_OK;

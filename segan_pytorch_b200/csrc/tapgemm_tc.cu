@@ -112,6 +112,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+// 16-byte vector reduction (sm_90+): one RED for four fp32 adds
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
@@ -317,7 +322,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                 *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(o + j, v[j]);
+              for (int j = 0; j < 32; j += 4) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else {
             uint32_t pk[16];
@@ -494,7 +499,9 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         if (kc0 + c0 + 32 <= p.tr.k_lo[ti] || kc0 + c0 >= p.tr.k_hi[ti]) continue;
         if (n0 + row < p.tr.n_lo[ti] || n0 + row >= p.tr.n_hi[ti]) continue;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(o + c0 + j, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(o + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                     __uint_as_float(r[j + 3]));
       }
       tc_fence_before();
       mbar_arrive(&ctl->tmem_empty[acc]);

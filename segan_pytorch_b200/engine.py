@@ -622,7 +622,7 @@ class DiscriminatorEngine(_NetEngine):
         dev = ctx["x0"].device
         kin = Lq[-1] * fm[-1]
         g_z1 = buf.get("d.gz1", (B, 256), BF16, dev)
-        ws = buf.get("d.fcws", (B * (1 + 128 + 256),), F32, dev)
+        ws = buf.get("d.fcws", (B * (1 + 128 + 256 + 256),), F32, dev)
         gv = (lambda n: _p(self.gview(n))) if param_grads else (lambda n: None)
         _lib.call("sg_fc_tail_bwd", _p(ctx["z1"]), _p(ctx["z2"]), _p(ctx["logit"]), _p(g_logit), float(target),
                   float(weight),

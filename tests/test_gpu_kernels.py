@@ -387,7 +387,7 @@ def test_fc_tail_and_losses():
     loss = 0.5 * F.mse_loss(ref.view(-1), torch.ones(B))
     loss.backward()
     gz1 = torch.zeros(B, 256, dtype=torch.bfloat16, device=DEV)
-    ws = torch.zeros(B * 385, device=DEV)
+    ws = torch.zeros(B * 641, device=DEV)
     gs = [torch.zeros_like(t) for t in (b0, s1, w2, b2, s3, w4, b4)]
     lo = torch.zeros(1, device=DEV)
     _lib.call("sg_fc_tail_bwd", _p(z1), _p(z2), _p(logit), None, 1.0, 0.5, _p(s1), _p(w2), _p(s3), _p(w4), B, _p(lo),
