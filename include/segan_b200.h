@@ -167,6 +167,19 @@ int sg_wave_deconv_bwd(const void* x0, int c0, const void* x1, int c1, int batch
                        const float* w_eff, const float* gy, const float* y, float* gpre_ws,
                        void* gx, float* dw_eff, float* dbias, void* stream);
 
+/* Tensor-core route for the same waveform-end layers: a 64-channel im2col of the waveform(s)
+ * (col[b][t][ci*32+k] = pad(v_ci)[4t+k-off], 16-bit, fp16 and/or bf16 copy) makes them single-tap
+ * tap-GEMMs with K = 64; the transposed forms are a GEMM followed by a shift-add. */
+int sg_wave_im2col(const float* v0, const float* v1, int cin, int batch, int L, int roll, int reflect,
+                   int off, void* col_f16, void* col_bf16, void* stream);
+/* y[b][4m+r] = tanh(bias + sum_d P[b][m+d][(d+4)*4+r]); P fp32 [B][Lin][64] (last decoder block) */
+int sg_wave_shiftadd_tanh(const float* P, int batch, int Lin, const float* bias, float* y, void* stream);
+/* gx[b][unroll(reflect(q))] += sum_{4t+k-14=q} P2[b][t][col0+k]; P2 bf16 [B][L/4][64] (D input gradient;
+ * col0 = 32*ci selects the input channel) */
+int sg_wave_col2im_fold(const void* P2, int col0, int batch, int L, int roll, float* gx, void* stream);
+/* gpre = gy*(1-y^2); dbias += sum(gpre) */
+int sg_tanh_bwd(const float* gy, const float* y, int64_t n, float* gpre, float* dbias, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Elementwise / reduction glue (HBM-bound).
  * ------------------------------------------------------------------------------------------ */

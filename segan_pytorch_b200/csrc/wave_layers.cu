@@ -322,3 +322,118 @@ extern "C" int sg_wave_deconv_bwd(const void* x0, int c0, const void* x1, int c1
   }
   return SG_OK;
 }
+
+// ==========================================================================================
+// Tensor-core route for the waveform-end layers: a 64-channel im2col of the waveform(s) turns
+// the K = Cin*31 convs into single-tap tap-GEMMs (K = 64) on the tcgen05 kernels; the
+// transposed forms are a GEMM followed by a shift-add ("col2im").  These three kernels are the
+// HBM-bound glue around those GEMMs.
+// ==========================================================================================
+namespace sg {
+
+// col[b][t][ci*32 + k] = pad(v_ci)[4t + k - off]   (k < 31; k = 31 and absent channels = 0)
+__global__ void __launch_bounds__(256)
+wave_im2col_kernel(const float* __restrict__ v0, const float* __restrict__ v1, int cin, int batch, int L, int roll,
+                   int mode, int off, void* __restrict__ col_f16, void* __restrict__ col_bf16) {
+  const int Lq = L / 4;
+  const int64_t total = (int64_t)batch * Lq * 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int seg = (int)(i % 8);
+    const int64_t row = i / 8;
+    const int t = (int)(row % Lq), b = (int)(row / Lq);
+    const int ci = seg / 4, k0 = (seg % 4) * 8;
+    V8 o16, ob;
+    const float* v = ci == 0 ? v0 : v1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      float x = 0.f;
+      if (ci < cin && k < KW) x = wave_at(v, (int64_t)b * L, 4 * t + k - off, L, mode, roll);
+      o16.v[j] = cvt16(x, SG_F16);
+      ob.v[j] = cvt16(x, SG_BF16);
+    }
+    if (col_f16) *reinterpret_cast<V8*>(reinterpret_cast<uint16_t*>(col_f16) + row * 64 + seg * 8) = o16;
+    if (col_bf16) *reinterpret_cast<V8*>(reinterpret_cast<uint16_t*>(col_bf16) + row * 64 + seg * 8) = ob;
+  }
+}
+
+// y[b][4m + r] = tanh(bias + sum_d P[b][m + d][(d+4)*4 + r]),  P fp32 [B][Lin][64]
+__global__ void __launch_bounds__(256)
+wave_shiftadd_tanh_kernel(const float* __restrict__ P, int batch, int Lin, const float* __restrict__ bias,
+                          float* __restrict__ y) {
+  const int64_t total = (int64_t)batch * Lin * 4;
+  const float bv = bias ? bias[0] : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % 4);
+    const int64_t mr = i / 4;
+    const int m = (int)(mr % Lin), b = (int)(mr / Lin);
+    float s = bv;
+#pragma unroll
+    for (int d = -4; d <= 4; ++d) {
+      const int mm = m + d;
+      if (mm >= 0 && mm < Lin) s += P[((int64_t)b * Lin + mm) * 64 + (d + 4) * 4 + r];
+    }
+    y[i] = tanhf(s);
+  }
+}
+
+// gx[b][src(q)] += sum_{t,k: 4t + k - 14 = q} P2[b][t][k]   (reflect fold + un-roll), P2 bf16 [B][Lq][64]
+__global__ void __launch_bounds__(256)
+wave_col2im_fold_kernel(const void* __restrict__ P2, int col0, int batch, int L, int roll, float* __restrict__ gx) {
+  const int Lq = L / 4;
+  const int span = L + 30;                         // q in [-14, L + 15]
+  const int64_t total = (int64_t)batch * span;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % span) - 14;
+    const int b = (int)(i / span);
+    const int e = q + 14;                          // = 4t + k
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = (e & 3) + 4 * j;
+      const int t = (e - k) / 4;
+      if (k < KW && t >= 0 && t < Lq) s += ld16(P2, ((int64_t)b * Lq + t) * 64 + col0 + k, SG_BF16);
+    }
+    const int src = unroll_idx(reflect_idx(q, L), roll, L);
+    atomicAdd(gx + (int64_t)b * L + src, s);
+  }
+}
+
+}  // namespace sg
+
+extern "C" int sg_wave_im2col(const float* v0, const float* v1, int cin, int batch, int L, int roll, int reflect,
+                              int off, void* col_f16, void* col_bf16, void* stream) {
+  SG_CHECK_ARG(v0 && (cin == 1 || (cin == 2 && v1)) && L % 4 == 0 && (col_f16 || col_bf16));
+  const int64_t total = (int64_t)batch * (L / 4) * 8;
+  int64_t g = cdiv(total, 256 * 4);
+  if (g > 16 * NUM_SMS) g = 16 * NUM_SMS;
+  wave_im2col_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(v0, v1, cin, batch, L, roll,
+                                                              reflect ? PAD_REFLECT : PAD_ZERO, off, col_f16, col_bf16);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_wave_shiftadd_tanh(const float* P, int batch, int Lin, const float* bias, float* y, void* stream) {
+  const int64_t total = (int64_t)batch * Lin * 4;
+  int64_t g = cdiv(total, 256 * 4);
+  if (g > 16 * NUM_SMS) g = 16 * NUM_SMS;
+  wave_shiftadd_tanh_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(P, batch, Lin, bias, y);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_wave_col2im_fold(const void* P2, int col0, int batch, int L, int roll, float* gx, void* stream) {
+  const int64_t total = (int64_t)batch * (L + 30);
+  int64_t g = cdiv(total, 256 * 4);
+  if (g > 16 * NUM_SMS) g = 16 * NUM_SMS;
+  wave_col2im_fold_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(P2, col0, batch, L, roll, gx);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+// gpre = gy * (1 - y^2), dbias += sum gpre   (tanh backward of the last decoder block)
+extern "C" int sg_tanh_bwd(const float* gy, const float* y, int64_t n, float* gpre, float* dbias, void* stream) {
+  tanh_bwd_kernel<<<2 * NUM_SMS, 256, 0, (cudaStream_t)stream>>>(gy, y, gpre, n, dbias);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}

@@ -23,6 +23,34 @@ from ._lib import (ACT_NONE, ACT_PRELU, BACKEND_FFMA, BACKEND_TCGEN05, SG_BF16, 
 KW = 31
 
 
+def wave_on_tensor_cores():
+    """Waveform-end layers through im2col + tcgen05 tap-GEMMs (default) or the CUDA-core kernels."""
+    return os.environ.get("SEGAN_B200_WAVE", "tc").lower() not in ("cuda", "ffma", "0")
+
+
+def wave_col_weights(w, dev):
+    """Conv1d weight [64][cin][31] -> single-tap operand Wcol[co][ci*32 + k] (fp32, [64][64])."""
+    wc = torch.zeros(w.shape[0], 2, 32, dtype=torch.float32, device=dev)
+    wc[:, :w.shape[1], :KW] = w
+    return wc.view(w.shape[0], 64)
+
+
+_DEC_LAST_KIDX = None
+
+
+def dec_last_tap_index(dev):
+    """jj = (d+4)*4 + r  ->  k = -4d + r + 13 (or -1): column order of the last decoder block's GEMM."""
+    global _DEC_LAST_KIDX
+    if _DEC_LAST_KIDX is None or _DEC_LAST_KIDX.device != dev:
+        idx = []
+        for jj in range(64):
+            d, r = jj // 4 - 4, jj % 4
+            k = -4 * d + r + 13
+            idx.append(k if (jj < 36 and 0 <= k < KW) else -1)
+        _DEC_LAST_KIDX = torch.tensor(idx, device=dev)
+    return _DEC_LAST_KIDX
+
+
 def default_backend():
     v = os.environ.get("SEGAN_B200_BACKEND", "tcgen05").lower()
     return BACKEND_FFMA if v in ("ffma", "ref", "0") else BACKEND_TCGEN05
@@ -295,6 +323,15 @@ class GeneratorEngine(_NetEngine):
         weff = w.clone()
         weff[half:] = weff[half:] * alpha.view(-1, 1)
         self.packed["w_last_eff"] = weff.contiguous()
+        # tensor-core route of the waveform-end layers: single-tap operands (tiny tensors, torch ops)
+        wcol = wave_col_weights(self.pview("enc_blocks.0.conv.weight"), dev)
+        self.packed["Wcol0"] = wcol.half().contiguous()
+        kidx = dec_last_tap_index(dev)
+        w2 = weff.t()[kidx.clamp(min=0)] * (kidx >= 0).float().unsqueeze(1)       # [64][cin]
+        self.packed["W2_last"] = w2.half().contiguous()
+        wg = torch.zeros(weff.shape[0], 64, dtype=torch.float32, device=dev)
+        wg[:, :KW] = weff
+        self.packed["Wg_last"] = wg.bfloat16().contiguous()
 
     def dwp_elems(self):
         fm, nl = self.fmaps, self.nl
@@ -335,7 +372,15 @@ class GeneratorEngine(_NetEngine):
             cout = fm[l]
             a[l] = buf.get("g.a%d" % l, (B, Lq[l], cout), F16, dev)
             bias = self.pview("enc_blocks.%d.conv.bias" % l) if self.enc_bias else None
-            if l == 0:
+            if l == 0 and wave_on_tensor_cores():
+                col16 = buf.get("g.col16", (B, Lq[0], 64), F16, dev)
+                colb = buf.get("g.colb", (B, Lq[0], 64), BF16, dev) if want_ctx else None
+                _lib.call("sg_wave_im2col", _p(x), None, 1, B, L, 0, 1, 14, _p(col16), _p(colb), st)
+                run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
+                      tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
+                      d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+            elif l == 0:
+                colb = None
                 _lib.call("sg_wave_conv_fwd", _p(x), None, 1, B, L, 0, _p(self.pview("enc_blocks.0.conv.weight")),
                           _p(bias), cout, _p(a[0]), None, None, st)
             else:
@@ -380,11 +425,19 @@ class GeneratorEngine(_NetEngine):
             lin *= 4
             src0, src1 = dd[l], a[nl - 2 - l]
         y = torch.empty(B, 1, L, dtype=F32, device=dev)
-        _lib.call("sg_wave_deconv_fwd", _p(src0), src0.shape[-1], _p(src1), src1.shape[-1], B, lin,
-                  _p(self.packed["w_last_eff"]), _p(self.pview("dec_blocks.%d.deconv.bias" % (nl - 1))),
-                  _p(y), st)
+        blast = self.pview("dec_blocks.%d.deconv.bias" % (nl - 1))
+        if wave_on_tensor_cores():
+            cl = src0.shape[-1] + src1.shape[-1]
+            P = buf.get("g.P", (B, lin, 64), F32, dev)
+            run_f(src0, src1, lin, 0, SG_F16, self.packed["W2_last"], SG_F16, cl, 64, tap_ranges("full", 0, cl, 64),
+                  P, SG_F32, lin, 0, 0, lin, B, d_lo=0, d_hi=0, w_tap0=4, a0_c=src0.shape[-1], a1_c=src1.shape[-1],
+                  backend=self.backend)
+            _lib.call("sg_wave_shiftadd_tanh", _p(P), B, lin, _p(blast), _p(y), st)
+        else:
+            _lib.call("sg_wave_deconv_fwd", _p(src0), src0.shape[-1], _p(src1), src1.shape[-1], B, lin,
+                      _p(self.packed["w_last_eff"]), _p(blast), _p(y), st)
         ctx = dict(x=x, B=B, L=L, Lq=Lq, a=a, hp=hp, z16=z16, ad=ad, dd=dd, y=y, hpb=hpb, ab=ab, ddb=ddb,
-                   z16b=z16b) if want_ctx else None
+                   z16b=z16b, colb=colb) if want_ctx else None
         return y, ctx
 
     def hidden_ncl(self, ctx):
@@ -431,8 +484,23 @@ class GeneratorEngine(_NetEngine):
         gb = self.gview("dec_blocks.%d.deconv.bias" % l)
         src0 = dd[l - 1]
         src1 = a[0]
-        _lib.call("sg_wave_deconv_bwd", _p(src0), half, _p(src1), half, B, lin, _p(self.packed["w_last_eff"]),
-                  _p(gy), _p(ctx["y"]), _p(gpre), _p(g_in), _p(dweff), _p(gb), st)
+        if wave_on_tensor_cores():
+            _lib.call("sg_tanh_bwd", _p(gy), _p(ctx["y"]), B * L, _p(gpre), _p(gb), st)
+            colg = buf.get("g.colg", (B, lin, 64), BF16, dev)
+            _lib.call("sg_wave_im2col", _p(gpre), None, 1, B, L, 0, 0, 13, None, _p(colg), st)
+            run_f(colg, None, lin, 0, SG_BF16, self.packed["Wg_last"], SG_BF16, 64, cin, tap_ranges("full", 0, 64, cin),
+                  g_in, SG_BF16, lin, 0, 0, lin, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+            # dW'[n=(s,k)][kc=(src,s',c)] over position pairs; the s == s' blocks are the gradient
+            dwq = dwp_all[:128 * 2 * cin]
+            dwq.zero_()
+            run_w(colg, lin // 2, SG_BF16, ctx["ddb"][l - 1], ctx["ab"][0], lin // 2, 0, SG_BF16, 2 * cin, 128,
+                  tap_ranges("full", 0, 2 * cin, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=74,
+                  a0_c=cin, a1_c=cin, backend=self.backend)
+            t5 = dwq.view(2, 64, 2, 2, half)
+            dweff.copy_((t5[0, :, :, 0, :] + t5[1, :, :, 1, :]).permute(1, 2, 0).reshape(cin, 64)[:, :KW])
+        else:
+            _lib.call("sg_wave_deconv_bwd", _p(src0), half, _p(src1), half, B, lin, _p(self.packed["w_last_eff"]),
+                      _p(gy), _p(ctx["y"]), _p(gpre), _p(g_in), _p(dweff), _p(gb), st)
         w_last = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
         alpha = self.alpha_for_dec(l)
         gw = self.gview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
@@ -494,8 +562,18 @@ class GeneratorEngine(_NetEngine):
             if self.enc_bias:
                 self.gview("enc_blocks.%d.conv.bias" % l).add_(red[1].float())
             if l == 0:
-                _lib.call("sg_wave_conv_wgrad", _p(ctx["x"]), None, 1, B, L, 0, _p(g_a), cout,
-                          _p(self.gview("enc_blocks.0.conv.weight")), None, st)
+                if ctx.get("colb") is not None:
+                    dwq = dwp_all[:128 * 128]
+                    dwq.zero_()
+                    run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
+                          tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
+                          backend=self.backend)
+                    t4 = dwq.view(2, 64, 2, 64)
+                    self.gview("enc_blocks.0.conv.weight").add_(
+                        (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :1, :KW])
+                else:
+                    _lib.call("sg_wave_conv_wgrad", _p(ctx["x"]), None, 1, B, L, 0, _p(g_a), cout,
+                              _p(self.gview("enc_blocks.0.conv.weight")), None, st)
                 break
             cin = fm[l - 1]
             taps = tap_ranges("conv_fwd", cin, 4 * cin, cout)
@@ -542,6 +620,9 @@ class DiscriminatorEngine(_NetEngine):
         w1d = self.buf.get("W1dg", (kin, nout), BF16, dev)
         _lib.call("sg_pack_weights", 2, _p(w1), nout, C_, T, None, 0, _p(w1p), _p(w1d), SG_F16, SG_BF16, st)
         self.packed["W1p"], self.packed["W1dg"] = w1p, w1d
+        wcol = wave_col_weights(self.pview("enc_blocks.0.conv.weight"), dev)
+        self.packed["Wcol0"] = wcol.half().contiguous()
+        self.packed["WcolT0"] = wcol.t().bfloat16().contiguous()
 
     def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True):
         """x0: candidate (B,1,L), x1: reference/noisy (B,1,L) -- the reference's cat((x_, ref), 1)
@@ -561,7 +642,16 @@ class DiscriminatorEngine(_NetEngine):
             cout = fm[l]
             a[l] = buf.get("d.a%d" % l, (B, Lq[l], cout), F16, dev)
             bias = self.pview("enc_blocks.%d.conv.bias" % l) if m.bias else None
-            if l == 0:
+            colb = None
+            if l == 0 and wave_on_tensor_cores():
+                col16 = buf.get("d.col16", (B, Lq[0], 64), F16, dev)
+                colb0 = buf.get("d.colb", (B, Lq[0], 64), BF16, dev) if twins else None
+                _lib.call("sg_wave_im2col", _p(x0), _p(x1), 2, B, L, int(shifts[0]), 1, 14, _p(col16), _p(colb0), st)
+                run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
+                      tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
+                      d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+            elif l == 0:
+                colb0 = None
                 _lib.call("sg_wave_conv_fwd", _p(x0), _p(x1), 2, B, L, int(shifts[0]),
                           _p(self.pview("enc_blocks.0.conv.weight")), _p(bias), cout, _p(a[0]), None, None, st)
             else:
@@ -606,7 +696,8 @@ class DiscriminatorEngine(_NetEngine):
         _lib.call("sg_fc_tail_fwd", _p(acc), _p(self.pview("fc.0.bias")), _p(self.pview("fc.1.weight")),
                   _p(self.pview("fc.2.weight")), _p(self.pview("fc.2.bias")), _p(self.pview("fc.3.weight")),
                   _p(self.pview("fc.4.weight")), _p(self.pview("fc.4.bias")), B, _p(z1), _p(z2), _p(logit), st)
-        ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, hpb=hpb, ss=ss, mi=mi, z1=z1, z2=z2, logit=logit,
+        ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, hpb=hpb, colb=colb0, ss=ss, mi=mi, z1=z1, z2=z2,
+                   logit=logit,
                    shifts=[int(s) for s in shifts])
         return logit, ctx
 
@@ -662,15 +753,35 @@ class DiscriminatorEngine(_NetEngine):
                     _lib.call("sg_colsum", _p(g_a), SG_BF16, B * Lq[l], cout, cout,
                               _p(self.gview("enc_blocks.%d.conv.bias" % l)), 1, _p(tmp), st)
             if l == 0:
-                if param_grads:
+                w0 = self.pview("enc_blocks.0.conv.weight")
+                if param_grads and ctx.get("colb") is not None:
+                    dwp = buf.get("d.dwp", (9 * 4 * fm[-2] * fm[-1],), F32, dev)
+                    dwq = dwp[:128 * 128]
+                    dwq.zero_()
+                    run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
+                          tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
+                          backend=self.backend)
+                    t4 = dwq.view(2, 64, 2, 64)
+                    self.gview("enc_blocks.0.conv.weight").add_(
+                        (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :, :KW])
+                elif param_grads:
                     _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a), cout,
                               _p(self.gview("enc_blocks.0.conv.weight")), None, st)
-                w0 = self.pview("enc_blocks.0.conv.weight")
-                if input_grad is not None:
-                    _lib.call("sg_wave_conv_dgrad", _p(g_a), B, L, shifts[0], _p(w0), 2, cout, _p(input_grad), 1, st)
-                if input_grad1 is not None:     # gradient w.r.t. the second input channel
-                    w1 = C.c_void_p(w0.data_ptr() + 4 * KW)
-                    _lib.call("sg_wave_conv_dgrad", _p(g_a), B, L, shifts[0], w1, 2, cout, _p(input_grad1), 1, st)
+                if (input_grad is not None or input_grad1 is not None) and wave_on_tensor_cores():
+                    P2 = buf.get("d.P2", (B, Lq[0], 64), BF16, dev)
+                    run_f(g_a, None, Lq[0], 0, SG_BF16, self.packed["WcolT0"], SG_BF16, 64, 64,
+                          tap_ranges("full", 0, 64, 64), P2, SG_BF16, Lq[0], 0, 0, Lq[0], B, d_lo=0, d_hi=0, w_tap0=4,
+                          backend=self.backend)
+                    if input_grad is not None:
+                        _lib.call("sg_wave_col2im_fold", _p(P2), 0, B, L, shifts[0], _p(input_grad), st)
+                    if input_grad1 is not None:
+                        _lib.call("sg_wave_col2im_fold", _p(P2), 32, B, L, shifts[0], _p(input_grad1), st)
+                else:
+                    if input_grad is not None:
+                        _lib.call("sg_wave_conv_dgrad", _p(g_a), B, L, shifts[0], _p(w0), 2, cout, _p(input_grad), 1, st)
+                    if input_grad1 is not None:     # gradient w.r.t. the second input channel
+                        w1 = C.c_void_p(w0.data_ptr() + 4 * KW)
+                        _lib.call("sg_wave_conv_dgrad", _p(g_a), B, L, shifts[0], w1, 2, cout, _p(input_grad1), 1, st)
                 break
             cin = fm[l - 1]
             if param_grads:
