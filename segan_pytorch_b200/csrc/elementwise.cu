@@ -38,23 +38,36 @@ __device__ __forceinline__ void block_reduce_channels(float (&part)[NS][8], int 
 }
 
 // ------------------------------------------------------------------------------------------
+constexpr int EW_UNROLL = 4;   // independent 16-byte loads in flight per thread
+
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const void* __restrict__ a, int dtype, int64_t rows, int C, double* __restrict__ stats) {
+bn_stats_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, double* __restrict__ stats) {
   __shared__ float red[256 * 8];
   const int cgs = C / 8;
   const int tid = threadIdx.x;
   const int cg = tid % cgs;
   const int rpb = 256 / cgs;             // rows per block iteration
+  const int rows = (int)rows64;
+  const int stride = gridDim.x * rpb;
   float part[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { part[0][j] = 0.f; part[1][j] = 0.f; }
-  for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
-    const V8 v = ldv8(a, r * C + cg * 8);
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
+    V8 v[EW_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x = up16(v.v[j], dtype);
-      part[0][j] += x;
-      part[1][j] = fmaf(x, x, part[1][j]);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int r = r0 + u * stride;
+      if (r < rows) v[u] = ldv8(a, (int64_t)r * C + cg * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      if (r0 + u * stride >= rows) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = up16(v[u].v[j], dtype);
+        part[0][j] += x;
+        part[1][j] = fmaf(x, x, part[1][j]);
+      }
     }
   }
   block_reduce_channels<2>(part, cgs, C, stats, red);
@@ -92,29 +105,51 @@ act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
                void* __restrict__ h, void* __restrict__ h_bf16, void* __restrict__ a_bf16) {
   const int cgs = C / 8;
   const int Lh = L + 2 * H;
-  const int64_t total = (int64_t)batch * Lh * cgs;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cgs);
-    const int64_t pr = i / cgs;
-    const int qh = (int)(pr % Lh);
-    const int b = (int)(pr / Lh);
-    const int src = unroll_idx(reflect_idx(qh - H, L), roll, L);
-    const V8 v = ldv8(a, ((int64_t)b * L + src) * C + cg * 8);
-    V8 o, ob, ab;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int rpb = 256 / cgs;
+  const int rows = batch * Lh;           // output rows (incl. halo)
+  const int stride = gridDim.x * rpb;
+  float sc[8], sh[8], sl[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      float y = up16(v.v[j], dtype);
-      ab.v[j] = cvt16(y, SG_BF16);
-      if (scale_shift) y = fmaf(y, scale_shift[c], scale_shift[C + c]);
-      if (act == SG_ACT_PRELU) y = y > 0.f ? y : slope[c] * y;
-      o.v[j] = cvt16(y, dtype);
-      ob.v[j] = cvt16(y, SG_BF16);
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    sc[j] = scale_shift ? scale_shift[c] : 1.f;
+    sh[j] = scale_shift ? scale_shift[C + c] : 0.f;
+    sl[j] = (act == SG_ACT_PRELU) ? slope[c] : 1.f;
+  }
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
+    V8 v[EW_UNROLL];
+    int srcs[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int r = r0 + u * stride;
+      if (r < rows) {
+        const int b = r / Lh, qh = r - b * Lh;
+        srcs[u] = b * L + unroll_idx(reflect_idx(qh - H, L), roll, L);
+        v[u] = ldv8(a, (int64_t)srcs[u] * C + cg * 8);
+      }
     }
-    stv8(h, ((int64_t)b * Lh + qh) * C + cg * 8, o);
-    // bf16 twins: operands of the weight-gradient tap-GEMM (tcgen05 kind::f16 cannot mix f16 x bf16)
-    if (h_bf16) stv8(h_bf16, ((int64_t)b * Lh + qh) * C + cg * 8, ob);
-    if (a_bf16 && qh >= H && qh < H + L) stv8(a_bf16, ((int64_t)b * L + src) * C + cg * 8, ab);
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int r = r0 + u * stride;
+      if (r >= rows) break;
+      const int b = r / Lh, qh = r - b * Lh;
+      V8 o, ob, ab;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = up16(v[u].v[j], dtype);
+        ab.v[j] = cvt16(y, SG_BF16);
+        y = fmaf(y, sc[j], sh[j]);
+        if (act == SG_ACT_PRELU) y = y > 0.f ? y : sl[j] * y;
+        o.v[j] = cvt16(y, dtype);
+        ob.v[j] = cvt16(y, SG_BF16);
+      }
+      stv8(h, (int64_t)r * C + cg * 8, o);
+      // bf16 twins: operands of the weight-gradient tap-GEMM (tcgen05 kind::f16 cannot mix f16 x bf16)
+      if (h_bf16) stv8(h_bf16, (int64_t)r * C + cg * 8, ob);
+      if (a_bf16 && qh >= H && qh < H + L) stv8(a_bf16, (int64_t)srcs[u] * C + cg * 8, ab);
+    }
   }
 }
 
@@ -193,36 +228,50 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
   for (int s = 0; s < 3; ++s)
 #pragma unroll
     for (int j = 0; j < 8; ++j) part[s][j] = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
-    const int b = (int)(r / L), l = (int)(r % L);
-    float gy[8], gsk[8];
-    gather_gy(g_h, ldh, H, roll, b, l, L, cg, gy);
-    gather_gadd(g_add, lda, b, l, L, cg, gsk);
-    const V8 av = ldv8(a, r * C + cg * 8);
-    V8 o;
+  const int stride = gridDim.x * rpb;
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < (int)rows; r0 += EW_UNROLL * stride) {
+    float gyu[EW_UNROLL][8], gsku[EW_UNROLL][8];
+    V8 avu[EW_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x = up16(av.v[j], dtype);
-      const float y = fmaf(x, sc[j], sh[j]);
-      const float ahat = (x - mu[j]) * is[j];
-      float gpre = gy[j];
-      if (act == SG_ACT_PRELU) {
-        if (y <= 0.f) {
-          if (MODE == 0) part[0][j] = fmaf(gy[j], y, part[0][j]);
-          gpre = gy[j] * sl[j];
-        }
-      }
-      gpre += gsk[j];
-      if (MODE == 0) {
-        part[1][j] += gpre;
-        part[2][j] = fmaf(gpre, ahat, part[2][j]);
-        o.v[j] = cvt16(gpre, SG_BF16);
-      } else {
-        const float ga = use_bn ? sc[j] * (gpre - r1[j] - ahat * r2[j]) : gpre;
-        o.v[j] = cvt16(ga, SG_BF16);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int r = r0 + u * stride;
+      if (r < (int)rows) {
+        const int b = r / L, l = r - b * L;
+        gather_gy(g_h, ldh, H, roll, b, l, L, cg, gyu[u]);
+        gather_gadd(g_add, lda, b, l, L, cg, gsku[u]);
+        avu[u] = ldv8(a, (int64_t)r * C + cg * 8);
       }
     }
-    if (g_a_out) stv8(g_a_out, r * C + cg * 8, o);
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int r = r0 + u * stride;
+      if (r >= (int)rows) break;
+      V8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = up16(avu[u].v[j], dtype);
+        const float y = fmaf(x, sc[j], sh[j]);
+        const float ahat = (x - mu[j]) * is[j];
+        const float gy = gyu[u][j];
+        float gpre = gy;
+        if (act == SG_ACT_PRELU) {
+          if (y <= 0.f) {
+            if (MODE == 0) part[0][j] = fmaf(gy, y, part[0][j]);
+            gpre = gy * sl[j];
+          }
+        }
+        gpre += gsku[u][j];
+        if (MODE == 0) {
+          part[1][j] += gpre;
+          part[2][j] = fmaf(gpre, ahat, part[2][j]);
+          o.v[j] = cvt16(gpre, SG_BF16);
+        } else {
+          const float ga = use_bn ? sc[j] * (gpre - r1[j] - ahat * r2[j]) : gpre;
+          o.v[j] = cvt16(ga, SG_BF16);
+        }
+      }
+      if (g_a_out) stv8(g_a_out, (int64_t)r * C + cg * 8, o);
+    }
   }
   if (MODE == 0) block_reduce_channels<3>(part, cgs, C, red, sred);
 }
@@ -448,7 +497,7 @@ __global__ void l1_loss_bwd_kernel(const float* __restrict__ y, const float* __r
 
 static inline int ew_grid(int64_t work_items, int per_block) {
   int64_t g = cdiv(work_items, per_block);
-  const int64_t cap = 8 * NUM_SMS;
+  const int64_t cap = 16 * NUM_SMS;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -461,7 +510,7 @@ using namespace sg;
 extern "C" int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && a && stats);
   const int rpb = 256 / (C / 8);
-  bn_stats_kernel<<<ew_grid(rows_total, rpb * 8), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
+  bn_stats_kernel<<<ew_grid(rows_total, rpb * EW_UNROLL), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -480,8 +529,9 @@ extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, con
                           void* a_bf16, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && (out_halo_pos == 0 || L >= 32));
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
-  const int64_t total = (int64_t)batch * (L + 2 * out_halo_pos) * (C / 8);
-  act_fwd_kernel<<<ew_grid(total, 256 * 4), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
+  const int rpb_f = 256 / (C / 8);
+  SG_CHECK_ARG(C <= 2048 && 256 % (C / 8) == 0);
+  act_fwd_kernel<<<ew_grid((int64_t)batch * (L + 2 * out_halo_pos), rpb_f * EW_UNROLL), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
                                                           out_halo_pos, h, h_bf16, a_bf16);
   SG_CHECK_LAUNCH();
   return SG_OK;
@@ -494,7 +544,7 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
                                  void* g_a_out, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red);
   const int rpb = 256 / (C / 8);
-  act_bwd_kernel<0><<<ew_grid((int64_t)batch * L, rpb * 8), 256, 0, ST>>>(
+  act_bwd_kernel<0><<<ew_grid((int64_t)batch * L, rpb * EW_UNROLL), 256, 0, ST>>>(
       g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
   SG_CHECK_LAUNCH();
@@ -508,7 +558,7 @@ extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, in
                                 int use_bn, void* g_a, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red && g_a);
   const int rpb = 256 / (C / 8);
-  act_bwd_kernel<1><<<ew_grid((int64_t)batch * L, rpb * 8), 256, 0, ST>>>(
+  act_bwd_kernel<1><<<ew_grid((int64_t)batch * L, rpb * EW_UNROLL), 256, 0, ST>>>(
       g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a);
   SG_CHECK_LAUNCH();

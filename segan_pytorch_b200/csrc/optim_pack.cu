@@ -10,7 +10,24 @@ namespace sg {
 // ------------------------------------------------------------------------------------------
 __global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
                                int64_t n, float lr, float alpha, float eps, float gscale) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* s4 = reinterpret_cast<float4*>(sq);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pv = p4[i], gv = g4[i], sv = s4[i];
+    float* pp = &pv.x; float* gp = &gv.x; float* sp = &sv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = gp[j] * gscale;
+      const float s = alpha * sp[j] + (1.f - alpha) * gi * gi;
+      sp[j] = s;
+      pp[j] = pp[j] - lr * (gi / (sqrtf(s) + eps));
+    }
+    p4[i] = pv;
+    s4[i] = sv;
+  }
+  for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     const float s = alpha * sq[i] + (1.f - alpha) * gi * gi;
     sq[i] = s;
@@ -44,27 +61,30 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 //   Wtd[d+4][ci][r*Cout + co] = a(ci) W[ci][co][ 4d + r + 13] (dgrad: K = (r,co), N = ci)
 // entries whose tap index falls outside [0, 30] are zero.
 // ------------------------------------------------------------------------------------------
+constexpr int PT = 32;                       // channel tile (both directions): 128-byte fp32 / 64-byte 16-bit segments
+constexpr int PACK_SMEM = PT * PT * (KW + 1) * 4;
+
 __global__ void __launch_bounds__(256)
 pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner, const float* __restrict__ alpha,
                  int alpha_from, void* __restrict__ w_fwd, void* __restrict__ w_dg, int dt_fwd, int dt_dg) {
   // master layout is [outer][inner][31]; kind 0: outer = co, inner = ci ; kind 1: outer = ci, inner = co
-  __shared__ float tile[16][16][KW + 1];
-  const int o0 = blockIdx.y * 16, i0 = blockIdx.x * 16;
+  extern __shared__ float tile_raw[];
+  float (*tile)[PT][KW + 1] = reinterpret_cast<float (*)[PT][KW + 1]>(tile_raw);
+  const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < 16 * 16 * KW; idx += 256) {
-    const int oo = idx / (16 * KW), rem = idx % (16 * KW);
+  for (int idx = tid; idx < PT * PT * KW; idx += 256) {
+    const int oo = idx / (PT * KW), rem = idx % (PT * KW);
     const int ii = rem / KW, k = rem % KW;
     float v = w[((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k];
     if (kind == 1 && alpha && (o0 + oo) >= alpha_from) v *= alpha[o0 + oo - alpha_from];
     tile[oo][ii][k] = v;
   }
   __syncthreads();
-  // 9 taps x 4 phases x 16 x 16 outputs per packed layout
-  for (int idx = tid; idx < NTAP * 4 * 256; idx += 256) {
-    const int lo = idx % 16;            // fastest index -> contiguous channel in the destination
-    const int hi = (idx / 16) % 16;
-    const int ph = (idx / 256) % 4;
-    const int ti = idx / 1024;          // d + 4
+  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 256) {
+    const int lo = idx % PT;            // fastest index -> contiguous channel in the destination
+    const int hi = (idx / PT) % PT;
+    const int ph = (idx / (PT * PT)) % 4;
+    const int ti = idx / (4 * PT * PT); // d + 4
     const int d = ti - 4;
     if (kind == 0) {
       const int Cout = c_outer, Cin = c_inner;
@@ -120,13 +140,14 @@ __global__ void __launch_bounds__(256)
 unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_inner, const float* __restrict__ w,
                    const float* __restrict__ alpha, int alpha_from, float* __restrict__ dw,
                    float* __restrict__ dalpha, int accumulate) {
-  __shared__ float tile[16][16][KW + 1];
-  __shared__ float ared[16];
-  const int o0 = blockIdx.y * 16, i0 = blockIdx.x * 16;
+  extern __shared__ float tile_raw[];
+  float (*tile)[PT][KW + 1] = reinterpret_cast<float (*)[PT][KW + 1]>(tile_raw);
+  __shared__ float ared[PT];
+  const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
   const int tid = threadIdx.x;
-  if (tid < 16) ared[tid] = 0.f;
-  for (int idx = tid; idx < NTAP * 4 * 256; idx += 256) {
-    const int lo = idx % 16, hi = (idx / 16) % 16, ph = (idx / 256) % 4, ti = idx / 1024;
+  if (tid < PT) ared[tid] = 0.f;
+  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 256) {
+    const int lo = idx % PT, hi = (idx / PT) % PT, ph = (idx / (PT * PT)) % 4, ti = idx / (4 * PT * PT);
     const int d = ti - 4;
     if (kind == 0) {
       const int Cout = c_outer, Cin = c_inner;
@@ -141,8 +162,8 @@ unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_i
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < 16 * 16 * KW; idx += 256) {
-    const int oo = idx / (16 * KW), rem = idx % (16 * KW);
+  for (int idx = tid; idx < PT * PT * KW; idx += 256) {
+    const int oo = idx / (PT * KW), rem = idx % (PT * KW);
     const int ii = rem / KW, k = rem % KW;
     const int64_t gi = ((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k;
     float v = tile[oo][ii][k];
@@ -153,7 +174,7 @@ unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_i
     dw[gi] = accumulate ? dw[gi] + v : v;
   }
   __syncthreads();
-  if (kind == 1 && alpha && dalpha && tid < 16 && (o0 + tid) >= alpha_from)
+  if (kind == 1 && alpha && dalpha && tid < PT && (o0 + tid) >= alpha_from)
     atomicAdd(dalpha + (o0 + tid - alpha_from), ared[tid]);
 }
 
@@ -246,7 +267,7 @@ using namespace sg;
 
 extern "C" int sg_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr, float alpha,
                                float eps, float grad_scale, void* stream) {
-  rmsprop_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(param, grad, square_avg, n, lr, alpha, eps, grad_scale);
+  rmsprop_kernel<<<8 * NUM_SMS, 256, 0, ST>>>(param, grad, square_avg, n, lr, alpha, eps, grad_scale);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -265,15 +286,22 @@ extern "C" int sg_pack_weights(int kind, const float* w, int c_out, int c_in, in
                                int alpha_from, void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad,
                                void* stream) {
   SG_CHECK_ARG(w && w_fwd && w_dgrad);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(pack_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SMEM));
+    SG_CHECK_CUDA(cudaFuncSetAttribute(unpack_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SMEM));
+    attr_set = true;
+  }
   if (kind == 0) {
-    SG_CHECK_ARG(c_out % 16 == 0 && c_in % 16 == 0);
-    dim3 grid(c_in / 16, c_out / 16);
-    pack_conv_kernel<<<grid, 256, 0, ST>>>(0, w, c_out, c_in, nullptr, 0, w_fwd, w_dgrad, dtype_fwd, dtype_dgrad);
+    SG_CHECK_ARG(c_out % PT == 0 && c_in % PT == 0);
+    dim3 grid(c_in / PT, c_out / PT);
+    pack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(0, w, c_out, c_in, nullptr, 0, w_fwd, w_dgrad, dtype_fwd,
+                                                   dtype_dgrad);
   } else if (kind == 1) {
-    SG_CHECK_ARG(c_out % 16 == 0 && c_in % 16 == 0);
-    dim3 grid(c_out / 16, c_in / 16);
-    pack_conv_kernel<<<grid, 256, 0, ST>>>(1, w, c_in, c_out, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
-                                           dtype_dgrad);
+    SG_CHECK_ARG(c_out % PT == 0 && c_in % PT == 0);
+    dim3 grid(c_out / PT, c_in / PT);
+    pack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(1, w, c_in, c_out, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
+                                                   dtype_dgrad);
   } else if (kind == 2) {
     pack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(w, c_out, c_in, t_len, w_fwd, w_dgrad, dtype_fwd, dtype_dgrad);
   } else {
@@ -287,12 +315,20 @@ extern "C" int sg_unpack_wgrad(int kind, const float* dwp, int c_out, int c_in, 
                                const float* alpha, int alpha_from, float* dw, float* dalpha, int accumulate,
                                void* stream) {
   SG_CHECK_ARG(dwp && dw);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SG_CHECK_CUDA(cudaFuncSetAttribute(pack_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SMEM));
+    SG_CHECK_CUDA(cudaFuncSetAttribute(unpack_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SMEM));
+    attr_set = true;
+  }
   if (kind == 0) {
-    dim3 grid(c_in / 16, c_out / 16);
-    unpack_conv_kernel<<<grid, 256, 0, ST>>>(0, dwp, c_out, c_in, nullptr, nullptr, 0, dw, nullptr, accumulate);
+    dim3 grid(c_in / PT, c_out / PT);
+    unpack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(0, dwp, c_out, c_in, nullptr, nullptr, 0, dw, nullptr,
+                                                     accumulate);
   } else if (kind == 1) {
-    dim3 grid(c_out / 16, c_in / 16);
-    unpack_conv_kernel<<<grid, 256, 0, ST>>>(1, dwp, c_in, c_out, w, alpha, alpha_from, dw, dalpha, accumulate);
+    dim3 grid(c_out / PT, c_in / PT);
+    unpack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(1, dwp, c_in, c_out, w, alpha, alpha_from, dw, dalpha,
+                                                     accumulate);
   } else if (kind == 2) {
     unpack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(dwp, c_out, c_in, t_len, dw, accumulate);
   } else {

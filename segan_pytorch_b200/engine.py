@@ -749,7 +749,10 @@ class DiscriminatorEngine(_NetEngine):
                 self.gview("enc_blocks.%d.act.weight" % l).add_(redl[0].float())
                 self.gview("enc_blocks.%d.norm.bias" % l).add_(redl[1].float())
                 self.gview("enc_blocks.%d.norm.weight" % l).add_(redl[2].float())
-                if m.bias:
+                # conv biases feed BatchNorm: their gradient is exactly zero (the BN backward output has
+                # zero mean per channel); the reference only sees rounding noise there.  Left at zero
+                # (SEGAN_B200_EXACT_BIAS_GRAD=1 computes the column sums anyway).
+                if m.bias and os.environ.get("SEGAN_B200_EXACT_BIAS_GRAD") == "1":
                     _lib.call("sg_colsum", _p(g_a), SG_BF16, B * Lq[l], cout, cout,
                               _p(self.gview("enc_blocks.%d.conv.bias" % l)), 1, _p(tmp), st)
             if l == 0:
