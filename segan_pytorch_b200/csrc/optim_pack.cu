@@ -62,14 +62,14 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // entries whose tap index falls outside [0, 30] are zero.
 // ------------------------------------------------------------------------------------------
 constexpr int PT = 32;                       // channel tile (both directions): 128-byte fp32 / 64-byte 16-bit segments
-constexpr int PACK_SMEM = PT * PT * (KW + 1) * 4;
+constexpr int PACK_SMEM = PT * PT * (KW + 2) * 4;   // last dim padded to 33 words: conflict-free transposes
 
 __global__ void __launch_bounds__(256)
 pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner, const float* __restrict__ alpha,
                  int alpha_from, void* __restrict__ w_fwd, void* __restrict__ w_dg, int dt_fwd, int dt_dg) {
   // master layout is [outer][inner][31]; kind 0: outer = co, inner = ci ; kind 1: outer = ci, inner = co
   extern __shared__ float tile_raw[];
-  float (*tile)[PT][KW + 1] = reinterpret_cast<float (*)[PT][KW + 1]>(tile_raw);
+  float (*tile)[PT][KW + 2] = reinterpret_cast<float (*)[PT][KW + 2]>(tile_raw);
   const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < PT * PT * KW; idx += 256) {
@@ -141,7 +141,7 @@ unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_i
                    const float* __restrict__ alpha, int alpha_from, float* __restrict__ dw,
                    float* __restrict__ dalpha, int accumulate) {
   extern __shared__ float tile_raw[];
-  float (*tile)[PT][KW + 1] = reinterpret_cast<float (*)[PT][KW + 1]>(tile_raw);
+  float (*tile)[PT][KW + 2] = reinterpret_cast<float (*)[PT][KW + 2]>(tile_raw);
   __shared__ float ared[PT];
   const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
   const int tid = threadIdx.x;
