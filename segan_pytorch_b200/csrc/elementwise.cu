@@ -495,11 +495,14 @@ __global__ void l1_loss_bwd_kernel(const float* __restrict__ y, const float* __r
   if ((threadIdx.x & 31) == 0 && loss_out) atomicAdd(loss_out, s * gscale);
 }
 
-static inline int ew_grid(int64_t work_items, int per_block) {
+static inline int ew_grid(int64_t work_items, int per_block, int cap_per_sm = 16) {
   int64_t g = cdiv(work_items, per_block);
-  const int64_t cap = 16 * NUM_SMS;
+  const int64_t cap = (int64_t)cap_per_sm * NUM_SMS;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
+// kernels that end in a per-block reduction (smem + one double atomic per channel and block):
+// keep the grid at 2 CTAs/SM so the same-address atomics stay in the hundreds, not thousands
+constexpr int RED_CAP = 2;
 
 }  // namespace sg
 
@@ -510,7 +513,7 @@ using namespace sg;
 extern "C" int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && a && stats);
   const int rpb = 256 / (C / 8);
-  bn_stats_kernel<<<ew_grid(rows_total, rpb * EW_UNROLL), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
+  bn_stats_kernel<<<ew_grid(rows_total, rpb * EW_UNROLL, RED_CAP), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -544,7 +547,7 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
                                  void* g_a_out, void* stream) {
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red);
   const int rpb = 256 / (C / 8);
-  act_bwd_kernel<0><<<ew_grid((int64_t)batch * L, rpb * EW_UNROLL), 256, 0, ST>>>(
+  act_bwd_kernel<0><<<ew_grid((int64_t)batch * L, rpb * EW_UNROLL, RED_CAP), 256, 0, ST>>>(
       g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
   SG_CHECK_LAUNCH();
@@ -583,7 +586,7 @@ extern "C" int sg_colsum(const void* a, int dtype, int64_t rows, int C, int mod,
   SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && tmp && C % mod == 0);
   SG_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * C, ST));
   const int rpb = 256 / (C / 8);
-  colsum_kernel<<<ew_grid(rows, rpb * 8), 256, 0, ST>>>(a, dtype, rows, C, tmp);
+  colsum_kernel<<<ew_grid(rows, rpb * 8, RED_CAP), 256, 0, ST>>>(a, dtype, rows, C, tmp);
   SG_CHECK_LAUNCH();
   colsum_fold_kernel<<<(mod + 127) / 128, 128, 0, ST>>>(tmp, C, mod, out, accumulate);
   SG_CHECK_LAUNCH();

@@ -64,7 +64,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 constexpr int PT = 32;                       // channel tile (both directions): 128-byte fp32 / 64-byte 16-bit segments
 constexpr int PACK_SMEM = PT * PT * (KW + 2) * 4;   // last dim padded to 33 words: conflict-free transposes
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner, const float* __restrict__ alpha,
                  int alpha_from, void* __restrict__ w_fwd, void* __restrict__ w_dg, int dt_fwd, int dt_dg) {
   // master layout is [outer][inner][31]; kind 0: outer = co, inner = ci ; kind 1: outer = ci, inner = co
@@ -72,7 +72,7 @@ pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner
   float (*tile)[PT][KW + 2] = reinterpret_cast<float (*)[PT][KW + 2]>(tile_raw);
   const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < PT * PT * KW; idx += 256) {
+  for (int idx = tid; idx < PT * PT * KW; idx += 1024) {
     const int oo = idx / (PT * KW), rem = idx % (PT * KW);
     const int ii = rem / KW, k = rem % KW;
     float v = w[((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k];
@@ -80,7 +80,7 @@ pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner
     tile[oo][ii][k] = v;
   }
   __syncthreads();
-  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 256) {
+  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 1024) {
     const int lo = idx % PT;            // fastest index -> contiguous channel in the destination
     const int hi = (idx / PT) % PT;
     const int ph = (idx / (PT * PT)) % 4;
@@ -136,7 +136,7 @@ __global__ void pack_fc_kernel(const float* __restrict__ w, int nout, int C, int
 //         dalpha[ci-alpha_from] = sum_{co,k} dWe * W
 // kind 2: dW[n][c*T+t] = dW1p[n][t*C+c]
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_inner, const float* __restrict__ w,
                    const float* __restrict__ alpha, int alpha_from, float* __restrict__ dw,
                    float* __restrict__ dalpha, int accumulate) {
@@ -146,7 +146,7 @@ unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_i
   const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
   const int tid = threadIdx.x;
   if (tid < PT) ared[tid] = 0.f;
-  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 256) {
+  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 1024) {
     const int lo = idx % PT, hi = (idx / PT) % PT, ph = (idx / (PT * PT)) % 4, ti = idx / (4 * PT * PT);
     const int d = ti - 4;
     if (kind == 0) {
@@ -162,7 +162,7 @@ unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_i
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < PT * PT * KW; idx += 256) {
+  for (int idx = tid; idx < PT * PT * KW; idx += 1024) {
     const int oo = idx / (PT * KW), rem = idx % (PT * KW);
     const int ii = rem / KW, k = rem % KW;
     const int64_t gi = ((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k;
@@ -295,12 +295,12 @@ extern "C" int sg_pack_weights(int kind, const float* w, int c_out, int c_in, in
   if (kind == 0) {
     SG_CHECK_ARG(c_out % PT == 0 && c_in % PT == 0);
     dim3 grid(c_in / PT, c_out / PT);
-    pack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(0, w, c_out, c_in, nullptr, 0, w_fwd, w_dgrad, dtype_fwd,
+    pack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(0, w, c_out, c_in, nullptr, 0, w_fwd, w_dgrad, dtype_fwd,
                                                    dtype_dgrad);
   } else if (kind == 1) {
     SG_CHECK_ARG(c_out % PT == 0 && c_in % PT == 0);
     dim3 grid(c_out / PT, c_in / PT);
-    pack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(1, w, c_in, c_out, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
+    pack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(1, w, c_in, c_out, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
                                                    dtype_dgrad);
   } else if (kind == 2) {
     pack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(w, c_out, c_in, t_len, w_fwd, w_dgrad, dtype_fwd, dtype_dgrad);
@@ -323,11 +323,11 @@ extern "C" int sg_unpack_wgrad(int kind, const float* dwp, int c_out, int c_in, 
   }
   if (kind == 0) {
     dim3 grid(c_in / PT, c_out / PT);
-    unpack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(0, dwp, c_out, c_in, nullptr, nullptr, 0, dw, nullptr,
+    unpack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(0, dwp, c_out, c_in, nullptr, nullptr, 0, dw, nullptr,
                                                      accumulate);
   } else if (kind == 1) {
     dim3 grid(c_out / PT, c_in / PT);
-    unpack_conv_kernel<<<grid, 256, PACK_SMEM, ST>>>(1, dwp, c_in, c_out, w, alpha, alpha_from, dw, dalpha,
+    unpack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(1, dwp, c_in, c_out, w, alpha, alpha_from, dw, dalpha,
                                                      accumulate);
   } else if (kind == 2) {
     unpack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(dwp, c_out, c_in, t_len, dw, accumulate);
