@@ -38,39 +38,97 @@ __device__ __forceinline__ void block_reduce_channels(float (&part)[NS][8], int 
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int EW_UNROLL = 4;   // independent 16-byte loads in flight per thread
+// ------------------------------------------------------------------------------------------
+// Streaming kernels: a warp owns one 64-channel chunk (lane = 2 adjacent channels, one 128-byte
+// line per row) and strides over rows, 4 rows in flight per thread.  Per-channel constants and
+// partial sums are 2 registers each, so 6+ CTAs are resident per SM and HBM latency is hidden by
+// occupancy x ILP rather than by wide per-thread vectors.
+// ------------------------------------------------------------------------------------------
+constexpr int EW_UNROLL = 4;
+
+__device__ __forceinline__ float2 ld2(const void* p, int64_t elem, int dtype) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p) + elem);
+  if (dtype == SG_F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ void st2(void* p, int64_t elem, float x, float y, int dtype) {
+  uint32_t u;
+  if (dtype == SG_F16) { __half2 h = __floats2half2_rn(x, y); u = *reinterpret_cast<uint32_t*>(&h); }
+  else { __nv_bfloat162 h = __floats2bfloat162_rn(x, y); u = *reinterpret_cast<uint32_t*>(&h); }
+  *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p) + elem) = u;
+}
+
+struct WarpWork {
+  int chunk, c, row0, row_stride, lane;
+};
+__device__ __forceinline__ WarpWork warp_work(int C) {
+  WarpWork w;
+  const int chunks = C / 64;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  w.lane = threadIdx.x & 31;
+  w.chunk = gw % chunks;
+  w.c = w.chunk * 64 + w.lane * 2;
+  w.row0 = gw / chunks;
+  w.row_stride = nw / chunks;
+  return w;
+}
+// merges per-lane partial sums of NS statistics for channels (c, c+1): warps of a block that own the
+// same chunk are combined in smem first (chunks <= 8), then one double atomic per channel
+template <int NS>
+__device__ __forceinline__ void warp_stats_flush(float (&part)[NS][2], const WarpWork& w, int C, double* out,
+                                                 float* smem /* [8][NS][64] */) {
+  const int chunks = C / 64;
+  const int wib = threadIdx.x >> 5;
+  if (chunks >= 8) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      atomicAdd(out + (int64_t)s * C + w.c, (double)part[s][0]);
+      atomicAdd(out + (int64_t)s * C + w.c + 1, (double)part[s][1]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    smem[(wib * NS + s) * 64 + w.lane * 2] = part[s][0];
+    smem[(wib * NS + s) * 64 + w.lane * 2 + 1] = part[s][1];
+  }
+  __syncthreads();
+  if (wib < chunks) {       // warp `wib` owns chunk (first_chunk + wib) % chunks == w.chunk
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      double a0 = 0, a1 = 0;
+      for (int o = wib; o < 8; o += chunks) {
+        a0 += (double)smem[(o * NS + s) * 64 + w.lane * 2];
+        a1 += (double)smem[(o * NS + s) * 64 + w.lane * 2 + 1];
+      }
+      atomicAdd(out + (int64_t)s * C + w.c, a0);
+      atomicAdd(out + (int64_t)s * C + w.c + 1, a1);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, double* __restrict__ stats) {
-  __shared__ float red[256 * 8];
-  const int cgs = C / 8;
-  const int tid = threadIdx.x;
-  const int cg = tid % cgs;
-  const int rpb = 256 / cgs;             // rows per block iteration
+  __shared__ float red[8 * 2 * 64];
+  const WarpWork w = warp_work(C);
   const int rows = (int)rows64;
-  const int stride = gridDim.x * rpb;
-  float part[2][8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { part[0][j] = 0.f; part[1][j] = 0.f; }
-  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
-    V8 v[EW_UNROLL];
+  float part[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
+    float2 v[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * stride;
-      if (r < rows) v[u] = ldv8(a, (int64_t)r * C + cg * 8);
+      const int r = r0 + u * w.row_stride;
+      v[u] = r < rows ? ld2(a, (int64_t)r * C + w.c, dtype) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      if (r0 + u * stride >= rows) break;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float x = up16(v[u].v[j], dtype);
-        part[0][j] += x;
-        part[1][j] = fmaf(x, x, part[1][j]);
-      }
+      part[0][0] += v[u].x; part[0][1] += v[u].y;
+      part[1][0] = fmaf(v[u].x, v[u].x, part[1][0]);
+      part[1][1] = fmaf(v[u].y, v[u].y, part[1][1]);
     }
   }
-  block_reduce_channels<2>(part, cgs, C, stats, red);
+  warp_stats_flush<2>(part, w, C, stats, red);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C,
@@ -103,99 +161,71 @@ __global__ void __launch_bounds__(256)
 act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ slope, int act, int roll, int H,
                void* __restrict__ h, void* __restrict__ h_bf16, void* __restrict__ a_bf16) {
-  const int cgs = C / 8;
+  const WarpWork w = warp_work(C);
   const int Lh = L + 2 * H;
-  const int tid = threadIdx.x;
-  const int cg = tid % cgs;
-  const int rpb = 256 / cgs;
   const int rows = batch * Lh;           // output rows (incl. halo)
-  const int stride = gridDim.x * rpb;
-  float sc[8], sh[8], sl[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    sc[j] = scale_shift ? scale_shift[c] : 1.f;
-    sh[j] = scale_shift ? scale_shift[C + c] : 0.f;
-    sl[j] = (act == SG_ACT_PRELU) ? slope[c] : 1.f;
-  }
-  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
-    V8 v[EW_UNROLL];
+  const float sc0 = scale_shift ? scale_shift[w.c] : 1.f, sc1 = scale_shift ? scale_shift[w.c + 1] : 1.f;
+  const float sh0 = scale_shift ? scale_shift[C + w.c] : 0.f, sh1 = scale_shift ? scale_shift[C + w.c + 1] : 0.f;
+  const float sl0 = act == SG_ACT_PRELU ? slope[w.c] : 1.f, sl1 = act == SG_ACT_PRELU ? slope[w.c + 1] : 1.f;
+  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
+    float2 v[EW_UNROLL];
     int srcs[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * stride;
+      const int r = r0 + u * w.row_stride;
+      srcs[u] = 0;
+      v[u] = make_float2(0.f, 0.f);
       if (r < rows) {
         const int b = r / Lh, qh = r - b * Lh;
         srcs[u] = b * L + unroll_idx(reflect_idx(qh - H, L), roll, L);
-        v[u] = ldv8(a, (int64_t)srcs[u] * C + cg * 8);
+        v[u] = ld2(a, (int64_t)srcs[u] * C + w.c, dtype);
       }
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * stride;
-      if (r >= rows) break;
-      const int b = r / Lh, qh = r - b * Lh;
-      V8 o, ob, ab;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float y = up16(v[u].v[j], dtype);
-        ab.v[j] = cvt16(y, SG_BF16);
-        y = fmaf(y, sc[j], sh[j]);
-        if (act == SG_ACT_PRELU) y = y > 0.f ? y : sl[j] * y;
-        o.v[j] = cvt16(y, dtype);
-        ob.v[j] = cvt16(y, SG_BF16);
+      const int r = r0 + u * w.row_stride;
+      if (r < rows) {
+        const int b = r / Lh, qh = r - b * Lh;
+        float y0 = fmaf(v[u].x, sc0, sh0), y1 = fmaf(v[u].y, sc1, sh1);
+        if (act == SG_ACT_PRELU) { y0 = y0 > 0.f ? y0 : sl0 * y0; y1 = y1 > 0.f ? y1 : sl1 * y1; }
+        st2(h, (int64_t)r * C + w.c, y0, y1, dtype);
+        // bf16 twins: operands of the weight-gradient tap-GEMM (tcgen05 kind::f16 cannot mix f16 x bf16)
+        if (h_bf16) st2(h_bf16, (int64_t)r * C + w.c, y0, y1, SG_BF16);
+        if (a_bf16 && qh >= H && qh < H + L) st2(a_bf16, (int64_t)srcs[u] * C + w.c, v[u].x, v[u].y, SG_BF16);
       }
-      stv8(h, (int64_t)r * C + cg * 8, o);
-      // bf16 twins: operands of the weight-gradient tap-GEMM (tcgen05 kind::f16 cannot mix f16 x bf16)
-      if (h_bf16) stv8(h_bf16, (int64_t)r * C + cg * 8, ob);
-      if (a_bf16 && qh >= H && qh < H + L) stv8(a_bf16, (int64_t)srcs[u] * C + cg * 8, ab);
     }
   }
 }
 
-// gradient w.r.t. the activation output at exact position l: gathers the consumer-view
-// gradient (rolled position + its reflect-halo mirrors) and the optional skip gradient
-__device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int roll, int b, int l, int L, int cg,
-                                          float (&gy)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) gy[j] = 0.f;
+// gradient w.r.t. the activation output at exact position l: the consumer-view gradient at the
+// rolled position plus its reflect-halo mirrors (row indices are warp-uniform)
+__device__ __forceinline__ float2 gather_gy(const void* g_h, int ldh, int H, int roll, int b, int l, int L, int c) {
+  float2 g = make_float2(0.f, 0.f);
   if (g_h) {
     const int Lh = L + 2 * H;
     int q0 = l + roll;
     if (q0 >= L) q0 -= L;
     if (q0 < 0) q0 += L;
     const int64_t base = (int64_t)b * Lh + H;
-    V8 v = ldv8(g_h, (base + q0) * ldh + cg * 8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+    g = ld2(g_h, (base + q0) * ldh + c, SG_BF16);
     if (H > 0) {
       if (q0 >= 1 && q0 <= H) {
-        v = ldv8(g_h, (base - q0) * ldh + cg * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+        const float2 m = ld2(g_h, (base - q0) * ldh + c, SG_BF16);
+        g.x += m.x; g.y += m.y;
       }
       if (q0 >= L - 1 - H && q0 <= L - 2) {
-        v = ldv8(g_h, (base + 2 * (L - 1) - q0) * ldh + cg * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gy[j] += up16(v.v[j], SG_BF16);
+        const float2 m = ld2(g_h, (base + 2 * (L - 1) - q0) * ldh + c, SG_BF16);
+        g.x += m.x; g.y += m.y;
       }
     }
   }
-}
-// skip-connection gradient: the Generator's skips carry the encoder PRE-activation
-// (generator.py:185,191), so this term joins after the activation derivative
-__device__ __forceinline__ void gather_gadd(const void* g_add, int lda, int b, int l, int L, int cg, float (&ga)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) ga[j] = 0.f;
-  if (g_add) {
-    const V8 v = ldv8(g_add, ((int64_t)b * L + l) * lda + cg * 8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ga[j] = up16(v.v[j], SG_BF16);
-  }
+  return g;
 }
 
-// MODE 0: reductions only (and, when g_a_out != null and no BN, the final g_a in the same pass)
+// MODE 0: reductions (and, when g_a_out != null, g_pre written in the same pass: final without BN)
 // MODE 1: apply (BN backward) using the reductions
+// The skip-connection gradient g_add is w.r.t. the PRE-activation (generator.py:185,191) and joins
+// after the activation derivative.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const void* __restrict__ g_add, int lda,
@@ -203,16 +233,13 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
                const float* __restrict__ scale_shift, const float* __restrict__ mean_invstd,
                const float* __restrict__ slope, int act, double* __restrict__ red, int use_bn,
                void* __restrict__ g_a_out) {
-  __shared__ float sred[256 * 8];
-  const int cgs = C / 8;
-  const int tid = threadIdx.x;
-  const int cg = tid % cgs;
-  const int rpb = 256 / cgs;
-  const int64_t rows = (int64_t)batch * L;
-  float sc[8], sh[8], mu[8], is[8], sl[8], r1[8], r2[8];
+  __shared__ float sred[8 * 3 * 64];
+  const WarpWork w = warp_work(C);
+  const int rows = batch * L;
+  float sc[2], sh[2], mu[2], is[2], sl[2], r1[2] = {0.f, 0.f}, r2[2] = {0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
+  for (int j = 0; j < 2; ++j) {
+    const int c = w.c + j;
     sc[j] = scale_shift ? scale_shift[c] : 1.f;
     sh[j] = scale_shift ? scale_shift[C + c] : 0.f;
     mu[j] = mean_invstd ? mean_invstd[c] : 0.f;
@@ -223,57 +250,49 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
       r2[j] = (float)(red[2 * C + c] / (double)rows);
     }
   }
-  float part[3][8];
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) part[s][j] = 0.f;
-  const int stride = gridDim.x * rpb;
-  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < (int)rows; r0 += EW_UNROLL * stride) {
-    float gyu[EW_UNROLL][8], gsku[EW_UNROLL][8];
-    V8 avu[EW_UNROLL];
+  float part[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
+    float2 gy[EW_UNROLL], gs[EW_UNROLL], av[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * stride;
-      if (r < (int)rows) {
+      const int r = r0 + u * w.row_stride;
+      gy[u] = gs[u] = av[u] = make_float2(0.f, 0.f);
+      if (r < rows) {
         const int b = r / L, l = r - b * L;
-        gather_gy(g_h, ldh, H, roll, b, l, L, cg, gyu[u]);
-        gather_gadd(g_add, lda, b, l, L, cg, gsku[u]);
-        avu[u] = ldv8(a, (int64_t)r * C + cg * 8);
+        gy[u] = gather_gy(g_h, ldh, H, roll, b, l, L, w.c);
+        if (g_add) gs[u] = ld2(g_add, (int64_t)r * lda + w.c, SG_BF16);
+        av[u] = ld2(a, (int64_t)r * C + w.c, dtype);
       }
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * stride;
-      if (r >= (int)rows) break;
-      V8 o;
+      const int r = r0 + u * w.row_stride;
+      if (r < rows) {
+        float out[2];
+        const float xs[2] = {av[u].x, av[u].y}, gys[2] = {gy[u].x, gy[u].y}, gss[2] = {gs[u].x, gs[u].y};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float x = up16(avu[u].v[j], dtype);
-        const float y = fmaf(x, sc[j], sh[j]);
-        const float ahat = (x - mu[j]) * is[j];
-        const float gy = gyu[u][j];
-        float gpre = gy;
-        if (act == SG_ACT_PRELU) {
-          if (y <= 0.f) {
-            if (MODE == 0) part[0][j] = fmaf(gy, y, part[0][j]);
-            gpre = gy * sl[j];
+        for (int j = 0; j < 2; ++j) {
+          const float y = fmaf(xs[j], sc[j], sh[j]);
+          const float ahat = (xs[j] - mu[j]) * is[j];
+          float gpre = gys[j];
+          if (act == SG_ACT_PRELU && y <= 0.f) {
+            if (MODE == 0) part[0][j] = fmaf(gys[j], y, part[0][j]);
+            gpre = gys[j] * sl[j];
+          }
+          gpre += gss[j];
+          if (MODE == 0) {
+            part[1][j] += gpre;
+            part[2][j] = fmaf(gpre, ahat, part[2][j]);
+            out[j] = gpre;
+          } else {
+            out[j] = use_bn ? sc[j] * (gpre - r1[j] - ahat * r2[j]) : gpre;
           }
         }
-        gpre += gsku[u][j];
-        if (MODE == 0) {
-          part[1][j] += gpre;
-          part[2][j] = fmaf(gpre, ahat, part[2][j]);
-          o.v[j] = cvt16(gpre, SG_BF16);
-        } else {
-          const float ga = use_bn ? sc[j] * (gpre - r1[j] - ahat * r2[j]) : gpre;
-          o.v[j] = cvt16(ga, SG_BF16);
-        }
+        if (g_a_out) st2(g_a_out, (int64_t)r * C + w.c, out[0], out[1], SG_BF16);
       }
-      if (g_a_out) stv8(g_a_out, (int64_t)r * C + cg * 8, o);
     }
   }
-  if (MODE == 0) block_reduce_channels<3>(part, cgs, C, red, sred);
+  if (MODE == 0) warp_stats_flush<3>(part, w, C, red, sred);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -311,21 +330,22 @@ __global__ void nlc_to_ncl_kernel(const void* __restrict__ src, int dtype, int C
 }
 
 __global__ void __launch_bounds__(256)
-colsum_kernel(const void* __restrict__ a, int dtype, int64_t rows, int C, double* __restrict__ tmp) {
-  __shared__ float red[256 * 8];
-  const int cgs = C / 8;
-  const int tid = threadIdx.x;
-  const int cg = tid % cgs;
-  const int rpb = 256 / cgs;
-  float part[1][8];
+colsum_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, double* __restrict__ tmp) {
+  __shared__ float red[8 * 64];
+  const WarpWork w = warp_work(C);
+  const int rows = (int)rows64;
+  float part[1][2] = {{0.f, 0.f}};
+  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
+    float2 v[EW_UNROLL];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) part[0][j] = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * rpb + tid / cgs; r < rows; r += (int64_t)gridDim.x * rpb) {
-    const V8 v = ldv8(a, r * C + cg * 8);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const int r = r0 + u * w.row_stride;
+      v[u] = r < rows ? ld2(a, (int64_t)r * C + w.c, dtype) : make_float2(0.f, 0.f);
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) part[0][j] += up16(v.v[j], dtype);
+    for (int u = 0; u < EW_UNROLL; ++u) { part[0][0] += v[u].x; part[0][1] += v[u].y; }
   }
-  block_reduce_channels<1>(part, cgs, C, tmp, red);
+  warp_stats_flush<1>(part, w, C, tmp, red);
 }
 __global__ void colsum_fold_kernel(const double* __restrict__ tmp, int C, int mod, float* __restrict__ out,
                                    int accumulate) {
@@ -502,7 +522,16 @@ static inline int ew_grid(int64_t work_items, int per_block, int cap_per_sm = 16
 }
 // kernels that end in a per-block reduction (smem + one double atomic per channel and block):
 // keep the grid at 2 CTAs/SM so the same-address atomics stay in the hundreds, not thousands
-constexpr int RED_CAP = 2;
+constexpr int RED_CAP = 4;
+// grid for the warp-per-64-channel-chunk streaming kernels: multiple of 4 so that warps/chunks is integral
+static inline int stream_grid(int64_t rows, int C, int cap_per_sm) {
+  const int64_t units = rows * (C / 64);
+  int64_t g = cdiv(units, 8 * EW_UNROLL);
+  const int64_t cap = (int64_t)cap_per_sm * NUM_SMS;
+  if (g > cap) g = cap;
+  g = cdiv(g, 4) * 4;
+  return (int)(g < 4 ? 4 : g);
+}
 
 }  // namespace sg
 
@@ -511,9 +540,8 @@ using namespace sg;
 #define ST ((cudaStream_t)stream)
 
 extern "C" int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream) {
-  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && a && stats);
-  const int rpb = 256 / (C / 8);
-  bn_stats_kernel<<<ew_grid(rows_total, rpb * EW_UNROLL, RED_CAP), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
+  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && a && stats && rows_total < (1ll << 31));
+  bn_stats_kernel<<<stream_grid(rows_total, C, RED_CAP), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -530,11 +558,9 @@ extern "C" int sg_bn_finalize(const double* stats, int64_t count, int C, const f
 extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
                           const float* slope, int act, int roll, int out_halo_pos, void* h, void* h_bf16,
                           void* a_bf16, void* stream) {
-  SG_CHECK_ARG(C % 8 == 0 && (out_halo_pos == 0 || L >= 32));
+  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && (out_halo_pos == 0 || L >= 32));
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
-  const int rpb_f = 256 / (C / 8);
-  SG_CHECK_ARG(C <= 2048 && 256 % (C / 8) == 0);
-  act_fwd_kernel<<<ew_grid((int64_t)batch * (L + 2 * out_halo_pos), rpb_f * EW_UNROLL), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
+  act_fwd_kernel<<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, 16), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
                                                           out_halo_pos, h, h_bf16, a_bf16);
   SG_CHECK_LAUNCH();
   return SG_OK;
@@ -545,9 +571,8 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
                                  int dtype, int batch, int L, int C, const float* scale_shift,
                                  const float* mean_invstd, const float* slope, int act, double* red,
                                  void* g_a_out, void* stream) {
-  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red);
-  const int rpb = 256 / (C / 8);
-  act_bwd_kernel<0><<<ew_grid((int64_t)batch * L, rpb * EW_UNROLL, RED_CAP), 256, 0, ST>>>(
+  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && red);
+  act_bwd_kernel<0><<<stream_grid((int64_t)batch * L, C, RED_CAP), 256, 0, ST>>>(
       g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
   SG_CHECK_LAUNCH();
@@ -559,9 +584,8 @@ extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, in
                                 int dtype, int batch, int L, int C, const float* scale_shift,
                                 const float* mean_invstd, const float* slope, int act, const double* red,
                                 int use_bn, void* g_a, void* stream) {
-  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && red && g_a);
-  const int rpb = 256 / (C / 8);
-  act_bwd_kernel<1><<<ew_grid((int64_t)batch * L, rpb * EW_UNROLL), 256, 0, ST>>>(
+  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && red && g_a);
+  act_bwd_kernel<1><<<stream_grid((int64_t)batch * L, C, 16), 256, 0, ST>>>(
       g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a);
   SG_CHECK_LAUNCH();
@@ -583,10 +607,9 @@ extern "C" int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L
 
 extern "C" int sg_colsum(const void* a, int dtype, int64_t rows, int C, int mod, float* out, int accumulate,
                          double* tmp, void* stream) {
-  SG_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && tmp && C % mod == 0);
+  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && tmp && C % mod == 0);
   SG_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * C, ST));
-  const int rpb = 256 / (C / 8);
-  colsum_kernel<<<ew_grid(rows, rpb * 8, RED_CAP), 256, 0, ST>>>(a, dtype, rows, C, tmp);
+  colsum_kernel<<<stream_grid(rows, C, RED_CAP), 256, 0, ST>>>(a, dtype, rows, C, tmp);
   SG_CHECK_LAUNCH();
   colsum_fold_kernel<<<(mod + 127) / 128, 128, 0, ST>>>(tmp, C, mod, out, accumulate);
   SG_CHECK_LAUNCH();
