@@ -54,6 +54,9 @@ int sg_abi_version(void);
 const char* sg_last_error(void);
 /* 1 if the loaded device is sm_100 class and the tcgen05 kernels can run */
 int sg_device_ok(void);
+/* 1 (default): forward-form tap-GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles);
+ * 0: single-CTA 128-row tiles.  Returns the previous setting. */
+int sg_set_cta_pair(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-GEMM, forward form ("F"):

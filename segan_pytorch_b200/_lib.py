@@ -75,7 +75,7 @@ _SIGS = {
     "sg_deemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_preemphasis": [_vp, _i64, _f, _vp, _vp],
 }
-EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok"] + list(_SIGS)
+EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair"] + list(_SIGS)
 
 _lib = None
 
@@ -97,6 +97,8 @@ def load():
     lib.sg_abi_version.restype = C.c_int
     lib.sg_last_error.restype = C.c_char_p
     lib.sg_device_ok.restype = C.c_int
+    lib.sg_set_cta_pair.restype = C.c_int
+    lib.sg_set_cta_pair.argtypes = [C.c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -14,12 +14,19 @@ int tapgemm_f_ffma_launch(const sg_tapgemm_f* q, cudaStream_t st);
 int tapgemm_w_ffma_launch(const sg_tapgemm_w* q, cudaStream_t st);
 int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st);
 int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st);
+extern int g_cta_pair;
 }  // namespace sg
 
 using namespace sg;
 
 extern "C" int sg_abi_version(void) { return SG_ABI_VERSION; }
 extern "C" const char* sg_last_error(void) { return g_err; }
+
+extern "C" int sg_set_cta_pair(int on) {
+  const int prev = g_cta_pair;
+  g_cta_pair = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int sg_device_ok(void) {
   int dev = 0;

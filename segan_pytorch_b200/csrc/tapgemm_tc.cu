@@ -359,6 +359,261 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------
+// form F on CTA pairs (tcgen05 cta_group::2): two CTAs of a cluster compute a 256 x TN tile.
+// Each CTA stages its own 128 rows of A and HALF of the weight tile; the leader's single thread
+// issues M = 256 UMMAs that read both CTAs' shared memory, so per-SM shared-memory traffic per
+// MMA drops from 12 KB to 8 KB and the weight tile is fetched from L2 once per pair.
+// (Measured on the 1-CTA kernel: UMMA operand reads + TMA fill ~ 192 B/clk against the 128 B/clk
+// shared-memory port capped the tensor pipe at 66 %, profiles/r1_v1_ncu_tapgemm_f.md.)
+// ------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int B2_STAGE_BYTES = 128 * 128;            // half of a 256-row weight tile
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;          // shared::cluster address of the even (leader) CTA
+
+struct SharedCtl2 {
+  uint64_t full[STAGES2];
+  uint64_t empty[STAGES2];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the same barrier in BOTH CTAs of the pair when the issued MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+// plain arrive on the LEADER's copy of a barrier
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+              const __grid_constant__ CUtensorMap tmW, const FTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SharedCtl2* ctl = reinterpret_cast<SharedCtl2*>(smem + STAGES2 * STAGE2_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(&ctl->tmem_base, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  const int m_tiles = p.m_tiles_per_b * p.b_tiles;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_tiles = m_pairs * p.n_tiles * p.ksplit;
+  const int npairs = gridDim.x / 2;
+  const int pair_id = blockIdx.x / 2;
+  const int half_n = p.TN / 2;
+  const uint32_t a_bytes = (uint32_t)p.TR * p.TB * 128u;
+  const uint32_t b_bytes = (uint32_t)half_n * 128u;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+        const int mp = tile % m_pairs;
+        const int rest = tile / m_pairs;
+        const int ks = rest % p.ksplit;
+        const int nt = rest / p.ksplit;
+        const int mt = 2 * mp + (int)rank;
+        const int b0 = (mt / p.m_tiles_per_b) * p.TB;
+        const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * p.TR;
+        const int n0 = p.n_lo + nt * p.TN;
+        int step = 0;
+        for (int d = p.d_lo; d <= p.d_hi; ++d) {
+          const int ti = d + 4;
+          if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
+          for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
+            if (step % p.ksplit != ks) continue;
+            mbar_wait(&ctl->empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * STAGE2_BYTES;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            if (leader) mbar_expect_tx(&ctl->full[stage], 2u * (a_bytes + b_bytes));
+            if (k0 < p.a0_c) tma_load_3d_pair(sa, &tmA0, &ctl->full[stage], k0, m0 + d + p.a_halo, b0);
+            else tma_load_3d_pair(sa, &tmA1, &ctl->full[stage], k0 - p.a0_c, m0 + d + p.a_halo, b0);
+            tma_load_2d_pair(sb, &tmW, &ctl->full[stage], k0, (ti - p.w_tap0) * p.nc + n0 + (int)rank * half_n);
+            if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && leader) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+        const int rest = tile / m_pairs;
+        const int ks = rest % p.ksplit;
+        const int nt = rest / p.ksplit;
+        const int n0 = p.n_lo + nt * p.TN;
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        uint32_t accum = 0;
+        int step = 0;
+        for (int d = p.d_lo; d <= p.d_hi; ++d) {
+          const int ti = d + 4;
+          if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
+          for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
+            if (step % p.ksplit != ks) continue;
+            mbar_wait(&ctl->full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+            const uint32_t sb = sa + A_STAGE_BYTES;
+            const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, accum);
+              accum = 1;
+            }
+            umma_commit_pair(&ctl->empty[stage]);     // frees the slot in both CTAs
+            if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit_pair(&ctl->tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5, both CTAs; each CTA owns 128 of the 256 rows) =========
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int out_buf_rows = p.out_rows + 2 * p.out_halo;
+    for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+      const int mp = tile % m_pairs;
+      const int rest = tile / m_pairs;
+      const int ks = rest % p.ksplit;
+      const int nt = rest / p.ksplit;
+      const int mt = 2 * mp + (int)rank;
+      const int b0 = (mt / p.m_tiles_per_b) * p.TB;
+      const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * p.TR;
+      const int n0 = p.n_lo + nt * p.TN;
+      const int tb = row / p.TR, tr = row % p.TR;
+      const int b = b0 + tb, m = m0 + tr;
+      const bool valid = (mt < m_tiles) && (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
+      for (int c0 = 0; c0 < p.TN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr && ks == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ((n0 + c0 + j) % p.bias_mod));
+          }
+          if (p.out_dtype == SG_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + obase + c0;
+            if (p.ksplit == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else {
+            uint32_t pk[16];
+            if (p.out_dtype == SG_F16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_leader(&ctl->tmem_empty[acc]);      // 2 x 128 arrivals release the accumulator
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // form W:  dWp[d+4][n][kc] += sum_{b,m} G[b,m,n] * A[b,m+d,kc]
 //   UMMA: M = 128 channels n (MN-major from G), N = TK channels kc (MN-major from A),
 //   K = 64 positions per stage (PB batches x PR rows).
@@ -571,6 +826,8 @@ static int make_map2(CUtensorMap* m, const void* base, int dtype, int C, int64_t
   return SG_OK;
 }
 
+int g_cta_pair = 1;   // sg_set_cta_pair(): use the cta_group::2 kernel for form F when there are >= 2 M tiles
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -620,7 +877,25 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   if (rc) return rc;
   rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)(q->d_hi + 4 - q->w_tap0 + 1) * q->nc, p.TN);
   if (rc) return rc;
-  const int total = p.m_tiles_per_b * p.b_tiles * p.n_tiles * p.ksplit;
+  const int m_tiles_all = p.m_tiles_per_b * p.b_tiles;
+  if (g_cta_pair && m_tiles_all >= 2) {
+    // CTA-pair kernel: A box per CTA as before, weight box = TN/2 rows per CTA, M = 256 UMMA
+    static bool attr2 = false;
+    if (!attr2) {
+      SG_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_f_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      attr2 = true;
+    }
+    rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)(q->d_hi + 4 - q->w_tap0 + 1) * q->nc, p.TN / 2);
+    if (rc) return rc;
+    p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 256, p.TN);
+    const int pairs = ((m_tiles_all + 1) / 2) * p.n_tiles * p.ksplit;
+    int npairs = num_sms() / 2;
+    if (pairs < npairs) npairs = pairs;
+    tapgemm_f_tc2<<<2 * npairs, NUM_THREADS, SMEM2_BYTES, st>>>(tmA0, tmA1, tmW, p);
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
+  const int total = m_tiles_all * p.n_tiles * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
   tapgemm_f_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA0, tmA1, tmW, p);
   SG_CHECK_LAUNCH();

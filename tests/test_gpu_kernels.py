@@ -46,9 +46,19 @@ def _ref_f(a_pad, halo, w, m_lo, m_hi, d_lo=-4, d_hi=4, w_tap0=0):
     return out
 
 
-@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
+@pytest.fixture(autouse=True)
+def _restore_cta_pair():
+    yield
+    _lib.load().sg_set_cta_pair(1)
+
+
+@pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05, 2])
 @pytest.mark.parametrize("case", ["conv_fwd", "conv_dgrad", "deconv_fwd_cat", "deconv_dgrad", "small_rows", "fc"])
 def test_tapgemm_f(backend, case):
+    """backend 1 = tcgen05 single-CTA tiles, 2 = tcgen05 CTA pairs (cta_group::2)."""
+    _lib.load().sg_set_cta_pair(1 if backend == 2 else 0)
+    if backend == 2:
+        backend = BACKEND_TCGEN05
     g = _gen(1)
     B = 3
     bias = None
