@@ -15,6 +15,7 @@
 // coordinates into the same NLC-row tensor.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace sg {
 
@@ -172,6 +173,7 @@ struct FTcParams {
   int TR, TB, TN;            // M tile = TB batches x TR rows (<= 128), N tile
   int m_tiles_per_b, b_tiles, n_tiles;
   uint32_t idesc;
+  int dbg;                   // timing experiments only (SEGAN_B200_DEBUG): 1 skip B loads, 2 skip A loads, 4 skip stores
 };
 
 struct SharedCtl {
@@ -232,10 +234,12 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
-            mbar_expect_tx(&ctl->full[stage], a_bytes + b_bytes);
-            if (k0 < p.a0_c) tma_load_3d(sa, &tmA0, &ctl->full[stage], k0, m0 + d + p.a_halo, b0);
-            else tma_load_3d(sa, &tmA1, &ctl->full[stage], k0 - p.a0_c, m0 + d + p.a_halo, b0);
-            tma_load_2d(sb, &tmW, &ctl->full[stage], k0, (ti - p.w_tap0) * p.nc + n0);
+            mbar_expect_tx(&ctl->full[stage], ((p.dbg & 2) ? 0u : a_bytes) + ((p.dbg & 1) ? 0u : b_bytes));
+            if (!(p.dbg & 2)) {
+              if (k0 < p.a0_c) tma_load_3d(sa, &tmA0, &ctl->full[stage], k0, m0 + d + p.a_halo, b0);
+              else tma_load_3d(sa, &tmA1, &ctl->full[stage], k0 - p.a0_c, m0 + d + p.a_halo, b0);
+            }
+            if (!(p.dbg & 1)) tma_load_2d(sb, &tmW, &ctl->full[stage], k0, (ti - p.w_tap0) * p.nc + n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -306,7 +310,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.dbg & 4)) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -561,7 +565,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.dbg & 4)) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -868,6 +872,10 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   p.b_tiles = (q->batch + p.TB - 1) / p.TB;
   p.n_tiles = ncols / p.TN;
   p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 128, p.TN);
+  {
+    const char* e = getenv("SEGAN_B200_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   CUtensorMap tmA0, tmA1, tmW;
   const int a_buf_rows = q->a_rows + 2 * q->a_halo;
   int rc = make_map3(&tmA0, q->a0, q->a_dtype, q->a0_c, a_buf_rows, q->batch, p.TR, p.TB);
