@@ -35,22 +35,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
+  if (mbar_try(addr, parity)) return;
+  // slow path.  watchdog: a pipeline bug must surface as a launch error, never as a hung GPU
   long long t0 = 0;
-  while (!done) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done) {
-      // watchdog: a pipeline bug must surface as a launch error, never as a hung GPU
+  uint32_t spins = 0;
+  while (!mbar_try(addr, parity)) {
+    if ((++spins & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 8000000000LL) __trap();
@@ -184,6 +189,17 @@ struct SharedCtl {
   uint32_t tmem_base;
 };
 
+// number of 64-channel K steps a tile with N range [n0, n0+TN) executes for K-split `ks`
+__device__ __forceinline__ int f_num_steps(const FTcParams& p, int n0, int ks) {
+  int total = 0;
+  for (int d = p.d_lo; d <= p.d_hi; ++d) {
+    const int ti = d + 4;
+    if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
+    total += (p.tr.k_hi[ti] - p.tr.k_lo[ti]) >> 6;
+  }
+  return p.ksplit == 1 ? total : (total - ks + p.ksplit - 1) / p.ksplit;
+}
+
 // ------------------------------------------------------------------------------------------
 // form F:  out[b,m,n] = bias + sum_d sum_kc A[b,m+d,kc] * Wp[d+4][n][kc]
 //   UMMA: M = 128 (rows: TB batches x TR rows), N = TN output channels, K = 64-channel blocks.
@@ -230,7 +246,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           const int ti = d + 4;
           if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
           for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
-            if (step % p.ksplit != ks) continue;
+            if (p.ksplit > 1 && step % p.ksplit != ks) continue;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
@@ -258,28 +274,22 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
-        uint32_t accum = 0;
-        int step = 0;
-        for (int d = p.d_lo; d <= p.d_hi; ++d) {
-          const int ti = d + 4;
-          if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
-          for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
-            if (step % p.ksplit != ks) continue;
-            mbar_wait(&ctl->full[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint32_t sb = sa + A_STAGE_BYTES;
-            const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // advance 16 elements (32 B) along K inside the 128 B swizzled row
-              umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, accum);
-              accum = 1;
-            }
-            umma_commit(&ctl->empty[stage]);   // frees the smem slot when these MMAs retire
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
+        // the issuer only needs the NUMBER of K steps (the producer decides what they contain):
+        // keep this single thread's loop as short as possible -- it paces the tensor pipe
+        const int nsteps = f_num_steps(p, n0, ks);
+        const uint32_t smem0 = smem_u32(smem);
+        for (int i = 0; i < nsteps; ++i) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES, 16, 1024);
+          umma_f16(tmem_d, adesc, bdesc, p.idesc, i > 0 ? 1u : 0u);
+          umma_f16(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
+          umma_f16(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
+          umma_f16(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
+          umma_commit(&ctl->empty[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&ctl->tmem_full[acc]);     // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -487,7 +497,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           const int ti = d + 4;
           if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
           for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
-            if (step % p.ksplit != ks) continue;
+            if (p.ksplit > 1 && step % p.ksplit != ks) continue;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE2_BYTES;
             uint8_t* sb = sa + A_STAGE_BYTES;
@@ -513,27 +523,20 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
-        uint32_t accum = 0;
-        int step = 0;
-        for (int d = p.d_lo; d <= p.d_hi; ++d) {
-          const int ti = d + 4;
-          if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
-          for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
-            if (step % p.ksplit != ks) continue;
-            mbar_wait(&ctl->full[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
-            const uint32_t sb = sa + A_STAGE_BYTES;
-            const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, accum);
-              accum = 1;
-            }
-            umma_commit_pair(&ctl->empty[stage]);     // frees the slot in both CTAs
-            if (++stage == STAGES2) { stage = 0; phase ^= 1; }
-          }
+        const int nsteps = f_num_steps(p, n0, ks);
+        const uint32_t smem0 = smem_u32(smem);
+        for (int i = 0; i < nsteps; ++i) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem0 + (uint32_t)stage * STAGE2_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES, 16, 1024);
+          umma_f16_pair(tmem_d, adesc, bdesc, p.idesc, i > 0 ? 1u : 0u);
+          umma_f16_pair(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
+          umma_f16_pair(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
+          umma_f16_pair(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
+          umma_commit_pair(&ctl->empty[stage]);     // frees the slot in both CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&ctl->tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
