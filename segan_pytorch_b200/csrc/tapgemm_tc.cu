@@ -723,14 +723,14 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 positions = 16 lines of 128 B = 2048 B along K
-            const uint64_t adesc = make_smem_desc(sa + k * 2048, 8192, 1024);
-            const uint64_t bdesc = make_smem_desc(sb + k * 2048, 8192, 1024);
-            umma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
-            accum = 1;
-          }
+          // 16 positions = 16 lines of 128 B = 2048 B along K: +128 in descriptor address units
+          const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+          umma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
+          umma_f16(tmem_d, adesc + 128, bdesc + 128, p.idesc, 1u);
+          umma_f16(tmem_d, adesc + 256, bdesc + 256, p.idesc, 1u);
+          umma_f16(tmem_d, adesc + 384, bdesc + 384, p.idesc, 1u);
+          accum = 1;
           umma_commit(&ctl->empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
