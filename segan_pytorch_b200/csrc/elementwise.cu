@@ -44,7 +44,7 @@ __device__ __forceinline__ void block_reduce_channels(float (&part)[NS][8], int 
 // partial sums are 2 registers each, so 6+ CTAs are resident per SM and HBM latency is hidden by
 // occupancy x ILP rather than by wide per-thread vectors.
 // ------------------------------------------------------------------------------------------
-constexpr int EW_UNROLL = 4;
+constexpr int EW_UNROLL = 8;   // rows in flight per thread (each a 128-byte warp request per stream)
 
 __device__ __forceinline__ float2 ld2(const void* p, int64_t elem, int dtype) {
   const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p) + elem);
