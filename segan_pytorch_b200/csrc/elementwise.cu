@@ -39,96 +39,96 @@ __device__ __forceinline__ void block_reduce_channels(float (&part)[NS][8], int 
 
 // ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
-// Streaming kernels: a warp owns one 64-channel chunk (lane = 2 adjacent channels, one 128-byte
-// line per row) and strides over rows, 4 rows in flight per thread.  Per-channel constants and
-// partial sums are 2 registers each, so 6+ CTAs are resident per SM and HBM latency is hidden by
-// occupancy x ILP rather than by wide per-thread vectors.
+// Streaming kernels.  Thread = 4 adjacent channels (one 8-byte load per stream) of a row, C/4
+// threads per row, 256/(C/4) rows per CTA iteration, two rows in flight per thread.  Measured
+// trade-off on B200: 2 channels/thread is instruction-bound (index math per element), 8 channels/
+// thread with all per-channel constants in registers drops to 1 CTA/SM; 4 channels keeps ~64
+// registers (4 CTAs/SM) with ~15 instructions per element.
 // ------------------------------------------------------------------------------------------
-constexpr int EW_UNROLL = 8;   // rows in flight per thread (each a 128-byte warp request per stream)
+constexpr int VEC = 4;
+constexpr int EW_UNROLL = 2;
 
-__device__ __forceinline__ float2 ld2(const void* p, int64_t elem, int dtype) {
-  const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(p) + elem);
-  if (dtype == SG_F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const void* p, int64_t elem, int dtype) {
+  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + elem);
+  F4 r;
+  if (dtype == SG_F16) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  } else {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  }
+  return r;
 }
-__device__ __forceinline__ void st2(void* p, int64_t elem, float x, float y, int dtype) {
-  uint32_t u;
-  if (dtype == SG_F16) { __half2 h = __floats2half2_rn(x, y); u = *reinterpret_cast<uint32_t*>(&h); }
-  else { __nv_bfloat162 h = __floats2bfloat162_rn(x, y); u = *reinterpret_cast<uint32_t*>(&h); }
-  *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p) + elem) = u;
+__device__ __forceinline__ void st4(void* p, int64_t elem, const float (&x)[4], int dtype) {
+  uint2 u;
+  if (dtype == SG_F16) {
+    __half2 a = __floats2half2_rn(x[0], x[1]), b = __floats2half2_rn(x[2], x[3]);
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  } else {
+    __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p) + elem) = u;
 }
 
-struct WarpWork {
-  int chunk, c, row0, row_stride, lane;
-};
-__device__ __forceinline__ WarpWork warp_work(int C) {
-  WarpWork w;
-  const int chunks = C / 64;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  w.lane = threadIdx.x & 31;
-  w.chunk = gw % chunks;
-  w.c = w.chunk * 64 + w.lane * 2;
-  w.row0 = gw / chunks;
-  w.row_stride = nw / chunks;
-  return w;
-}
-// merges per-lane partial sums of NS statistics for channels (c, c+1): warps of a block that own the
-// same chunk are combined in smem first (chunks <= 8), then one double atomic per channel
+// per-thread partial sums of NS statistics for 4 channels -> smem combine over the CTA's threads
+// that own the same channels -> one double atomic per channel and CTA
 template <int NS>
-__device__ __forceinline__ void warp_stats_flush(float (&part)[NS][2], const WarpWork& w, int C, double* out,
-                                                 float* smem /* [8][NS][64] */) {
-  const int chunks = C / 64;
-  const int wib = threadIdx.x >> 5;
-  if (chunks >= 8) {
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      atomicAdd(out + (int64_t)s * C + w.c, (double)part[s][0]);
-      atomicAdd(out + (int64_t)s * C + w.c + 1, (double)part[s][1]);
-    }
-    return;
-  }
-#pragma unroll
+__device__ __forceinline__ void block_stats_flush(float (&part)[NS][VEC], int cgs, int C, double* out,
+                                                  float* smem /* [256][VEC] */) {
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
   for (int s = 0; s < NS; ++s) {
-    smem[(wib * NS + s) * 64 + w.lane * 2] = part[s][0];
-    smem[(wib * NS + s) * 64 + w.lane * 2 + 1] = part[s][1];
-  }
-  __syncthreads();
-  if (wib < chunks) {       // warp `wib` owns chunk (first_chunk + wib) % chunks == w.chunk
+    __syncthreads();
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      double a0 = 0, a1 = 0;
-      for (int o = wib; o < 8; o += chunks) {
-        a0 += (double)smem[(o * NS + s) * 64 + w.lane * 2];
-        a1 += (double)smem[(o * NS + s) * 64 + w.lane * 2 + 1];
-      }
-      atomicAdd(out + (int64_t)s * C + w.c, a0);
-      atomicAdd(out + (int64_t)s * C + w.c + 1, a1);
+    for (int j = 0; j < VEC; ++j) smem[tid * VEC + j] = part[s][j];
+    __syncthreads();
+    if (tid < cgs) {
+      double acc[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] = 0;
+      for (int t = tid; t < (int)blockDim.x; t += cgs)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += (double)smem[t * VEC + j];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) atomicAdd(out + (int64_t)s * C + cg * VEC + j, acc[j]);
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, double* __restrict__ stats) {
-  __shared__ float red[8 * 2 * 64];
-  const WarpWork w = warp_work(C);
+  __shared__ float red[256 * VEC];
+  const int cgs = C / VEC;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int rpb = 256 / cgs;
   const int rows = (int)rows64;
-  float part[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
-    float2 v[EW_UNROLL];
+  const int stride = gridDim.x * rpb;
+  float part[2][VEC];
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * w.row_stride;
-      v[u] = r < rows ? ld2(a, (int64_t)r * C + w.c, dtype) : make_float2(0.f, 0.f);
+  for (int j = 0; j < VEC; ++j) { part[0][j] = 0.f; part[1][j] = 0.f; }
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += 4 * stride) {
+    F4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * stride;
+      if (r < rows) v[u] = ld4(a, (int64_t)r * C + cg * VEC, dtype);
+      else { v[u].v[0] = v[u].v[1] = v[u].v[2] = v[u].v[3] = 0.f; }
     }
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
-      part[0][0] += v[u].x; part[0][1] += v[u].y;
-      part[1][0] = fmaf(v[u].x, v[u].x, part[1][0]);
-      part[1][1] = fmaf(v[u].y, v[u].y, part[1][1]);
-    }
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        part[0][j] += v[u].v[j];
+        part[1][j] = fmaf(v[u].v[j], v[u].v[j], part[1][j]);
+      }
   }
-  warp_stats_flush<2>(part, w, C, stats, red);
+  block_stats_flush<2>(part, cgs, C, stats, red);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C,
@@ -161,61 +161,76 @@ __global__ void __launch_bounds__(256)
 act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ slope, int act, int roll, int H,
                void* __restrict__ h, void* __restrict__ h_bf16, void* __restrict__ a_bf16) {
-  const WarpWork w = warp_work(C);
+  const int cgs = C / VEC;
   const int Lh = L + 2 * H;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int rpb = 256 / cgs;
   const int rows = batch * Lh;           // output rows (incl. halo)
-  const float sc0 = scale_shift ? scale_shift[w.c] : 1.f, sc1 = scale_shift ? scale_shift[w.c + 1] : 1.f;
-  const float sh0 = scale_shift ? scale_shift[C + w.c] : 0.f, sh1 = scale_shift ? scale_shift[C + w.c + 1] : 0.f;
-  const float sl0 = act == SG_ACT_PRELU ? slope[w.c] : 1.f, sl1 = act == SG_ACT_PRELU ? slope[w.c + 1] : 1.f;
-  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
-    float2 v[EW_UNROLL];
-    int srcs[EW_UNROLL];
+  const int stride = gridDim.x * rpb;
+  float sc[VEC], sh[VEC], sl[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int c = cg * VEC + j;
+    sc[j] = scale_shift ? scale_shift[c] : 1.f;
+    sh[j] = scale_shift ? scale_shift[C + c] : 0.f;
+    sl[j] = (act == SG_ACT_PRELU) ? slope[c] : 1.f;
+  }
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
+    F4 v[EW_UNROLL];
+    int srcs[EW_UNROLL], qhs[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * w.row_stride;
-      srcs[u] = 0;
-      v[u] = make_float2(0.f, 0.f);
+      const int r = r0 + u * stride;
+      srcs[u] = 0; qhs[u] = 0;
       if (r < rows) {
-        const int b = r / Lh, qh = r - b * Lh;
-        srcs[u] = b * L + unroll_idx(reflect_idx(qh - H, L), roll, L);
-        v[u] = ld2(a, (int64_t)srcs[u] * C + w.c, dtype);
+        const int b = r / Lh;
+        qhs[u] = r - b * Lh;
+        srcs[u] = b * L + unroll_idx(reflect_idx(qhs[u] - H, L), roll, L);
+        v[u] = ld4(a, (int64_t)srcs[u] * C + cg * VEC, dtype);
       }
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * w.row_stride;
+      const int r = r0 + u * stride;
       if (r < rows) {
-        const int b = r / Lh, qh = r - b * Lh;
-        float y0 = fmaf(v[u].x, sc0, sh0), y1 = fmaf(v[u].y, sc1, sh1);
-        if (act == SG_ACT_PRELU) { y0 = y0 > 0.f ? y0 : sl0 * y0; y1 = y1 > 0.f ? y1 : sl1 * y1; }
-        st2(h, (int64_t)r * C + w.c, y0, y1, dtype);
+        float y[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          y[j] = fmaf(v[u].v[j], sc[j], sh[j]);
+          if (act == SG_ACT_PRELU) y[j] = y[j] > 0.f ? y[j] : sl[j] * y[j];
+        }
+        st4(h, (int64_t)r * C + cg * VEC, y, dtype);
         // bf16 twins: operands of the weight-gradient tap-GEMM (tcgen05 kind::f16 cannot mix f16 x bf16)
-        if (h_bf16) st2(h_bf16, (int64_t)r * C + w.c, y0, y1, SG_BF16);
-        if (a_bf16 && qh >= H && qh < H + L) st2(a_bf16, (int64_t)srcs[u] * C + w.c, v[u].x, v[u].y, SG_BF16);
+        if (h_bf16) st4(h_bf16, (int64_t)r * C + cg * VEC, y, SG_BF16);
+        if (a_bf16 && qhs[u] >= H && qhs[u] < H + L) st4(a_bf16, (int64_t)srcs[u] * C + cg * VEC, v[u].v, SG_BF16);
       }
     }
   }
 }
 
 // gradient w.r.t. the activation output at exact position l: the consumer-view gradient at the
-// rolled position plus its reflect-halo mirrors (row indices are warp-uniform)
-__device__ __forceinline__ float2 gather_gy(const void* g_h, int ldh, int H, int roll, int b, int l, int L, int c) {
-  float2 g = make_float2(0.f, 0.f);
+// rolled position plus its reflect-halo mirrors
+__device__ __forceinline__ F4 gather_gy(const void* g_h, int ldh, int H, int roll, int b, int l, int L, int c) {
+  F4 g;
+  g.v[0] = g.v[1] = g.v[2] = g.v[3] = 0.f;
   if (g_h) {
     const int Lh = L + 2 * H;
     int q0 = l + roll;
     if (q0 >= L) q0 -= L;
     if (q0 < 0) q0 += L;
     const int64_t base = (int64_t)b * Lh + H;
-    g = ld2(g_h, (base + q0) * ldh + c, SG_BF16);
+    g = ld4(g_h, (base + q0) * ldh + c, SG_BF16);
     if (H > 0) {
       if (q0 >= 1 && q0 <= H) {
-        const float2 m = ld2(g_h, (base - q0) * ldh + c, SG_BF16);
-        g.x += m.x; g.y += m.y;
+        const F4 m = ld4(g_h, (base - q0) * ldh + c, SG_BF16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g.v[j] += m.v[j];
       }
       if (q0 >= L - 1 - H && q0 <= L - 2) {
-        const float2 m = ld2(g_h, (base + 2 * (L - 1) - q0) * ldh + c, SG_BF16);
-        g.x += m.x; g.y += m.y;
+        const F4 m = ld4(g_h, (base + 2 * (L - 1) - q0) * ldh + c, SG_BF16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g.v[j] += m.v[j];
       }
     }
   }
@@ -233,66 +248,83 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
                const float* __restrict__ scale_shift, const float* __restrict__ mean_invstd,
                const float* __restrict__ slope, int act, double* __restrict__ red, int use_bn,
                void* __restrict__ g_a_out) {
-  __shared__ float sred[8 * 3 * 64];
-  const WarpWork w = warp_work(C);
+  __shared__ float sred[256 * VEC];
+  const int cgs = C / VEC;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int c0 = cg * VEC;
+  const int rpb = 256 / cgs;
   const int rows = batch * L;
-  float sc[2], sh[2], mu[2], is[2], sl[2], r1[2] = {0.f, 0.f}, r2[2] = {0.f, 0.f};
+  const int stride = gridDim.x * rpb;
+  // per-channel constants folded as far as possible:
+  //   y = x*sc + sh (sign only) ; ahat = x*is - mi ; MODE 1: ga = sc*gpre + ka*x + kb
+  float sc[VEC], sh[VEC], sl[VEC], p0[VEC], p1[VEC];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int c = w.c + j;
+  for (int j = 0; j < VEC; ++j) {
+    const int c = c0 + j;
     sc[j] = scale_shift ? scale_shift[c] : 1.f;
     sh[j] = scale_shift ? scale_shift[C + c] : 0.f;
-    mu[j] = mean_invstd ? mean_invstd[c] : 0.f;
-    is[j] = mean_invstd ? mean_invstd[C + c] : 1.f;
     sl[j] = (act == SG_ACT_PRELU) ? slope[c] : 1.f;
-    if (MODE == 1) {
-      r1[j] = (float)(red[C + c] / (double)rows);
-      r2[j] = (float)(red[2 * C + c] / (double)rows);
+    const float mu = mean_invstd ? mean_invstd[c] : 0.f;
+    const float is = mean_invstd ? mean_invstd[C + c] : 1.f;
+    if (MODE == 0) {
+      p0[j] = is;
+      p1[j] = mu * is;
+    } else {
+      const float r1 = (float)(red[C + c] / (double)rows);
+      const float r2 = (float)(red[2 * C + c] / (double)rows);
+      p0[j] = use_bn ? -sc[j] * r2 * is : 0.f;                       // ka
+      p1[j] = use_bn ? sc[j] * (r2 * is * mu - r1) : 0.f;           // kb
     }
   }
-  float part[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
-    float2 gy[EW_UNROLL], gs[EW_UNROLL], av[EW_UNROLL];
+  float part[3][VEC];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) part[s][j] = 0.f;
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
+    F4 gy[EW_UNROLL], gs[EW_UNROLL], av[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * w.row_stride;
-      gy[u] = gs[u] = av[u] = make_float2(0.f, 0.f);
+      const int r = r0 + u * stride;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gs[u].v[j] = 0.f;
       if (r < rows) {
         const int b = r / L, l = r - b * L;
-        gy[u] = gather_gy(g_h, ldh, H, roll, b, l, L, w.c);
-        if (g_add) gs[u] = ld2(g_add, (int64_t)r * lda + w.c, SG_BF16);
-        av[u] = ld2(a, (int64_t)r * C + w.c, dtype);
+        gy[u] = gather_gy(g_h, ldh, H, roll, b, l, L, c0);
+        if (g_add) gs[u] = ld4(g_add, (int64_t)r * lda + c0, SG_BF16);
+        av[u] = ld4(a, (int64_t)r * C + c0, dtype);
       }
     }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * w.row_stride;
+      const int r = r0 + u * stride;
       if (r < rows) {
-        float out[2];
-        const float xs[2] = {av[u].x, av[u].y}, gys[2] = {gy[u].x, gy[u].y}, gss[2] = {gs[u].x, gs[u].y};
+        float out[VEC];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float y = fmaf(xs[j], sc[j], sh[j]);
-          const float ahat = (xs[j] - mu[j]) * is[j];
-          float gpre = gys[j];
+        for (int j = 0; j < VEC; ++j) {
+          const float x = av[u].v[j];
+          const float y = fmaf(x, sc[j], sh[j]);
+          const float g = gy[u].v[j];
+          float gpre = g;
           if (act == SG_ACT_PRELU && y <= 0.f) {
-            if (MODE == 0) part[0][j] = fmaf(gys[j], y, part[0][j]);
-            gpre = gys[j] * sl[j];
+            if (MODE == 0) part[0][j] = fmaf(g, y, part[0][j]);
+            gpre = g * sl[j];
           }
-          gpre += gss[j];
+          gpre += gs[u].v[j];
           if (MODE == 0) {
             part[1][j] += gpre;
-            part[2][j] = fmaf(gpre, ahat, part[2][j]);
+            part[2][j] = fmaf(gpre, fmaf(x, p0[j], -p1[j]), part[2][j]);
             out[j] = gpre;
           } else {
-            out[j] = use_bn ? sc[j] * (gpre - r1[j] - ahat * r2[j]) : gpre;
+            out[j] = use_bn ? fmaf(sc[j], gpre, fmaf(p0[j], x, p1[j])) : gpre;
           }
         }
-        if (g_a_out) st2(g_a_out, (int64_t)r * C + w.c, out[0], out[1], SG_BF16);
+        if (g_a_out) st4(g_a_out, (int64_t)r * C + c0, out, SG_BF16);
       }
     }
   }
-  if (MODE == 0) warp_stats_flush<3>(part, w, C, red, sred);
+  if (MODE == 0) block_stats_flush<3>(part, cgs, C, red, sred);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -331,21 +363,20 @@ __global__ void nlc_to_ncl_kernel(const void* __restrict__ src, int dtype, int C
 
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, double* __restrict__ tmp) {
-  __shared__ float red[8 * 64];
-  const WarpWork w = warp_work(C);
+  __shared__ float red[256 * VEC];
+  const int cgs = C / VEC;
+  const int tid = threadIdx.x;
+  const int cg = tid % cgs;
+  const int rpb = 256 / cgs;
   const int rows = (int)rows64;
-  float part[1][2] = {{0.f, 0.f}};
-  for (int r0 = w.row0; r0 < rows; r0 += EW_UNROLL * w.row_stride) {
-    float2 v[EW_UNROLL];
+  const int stride = gridDim.x * rpb;
+  float part[1][VEC] = {{0.f, 0.f, 0.f, 0.f}};
+  for (int r = blockIdx.x * rpb + tid / cgs; r < rows; r += stride) {
+    const F4 v = ld4(a, (int64_t)r * C + cg * VEC, dtype);
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
-      const int r = r0 + u * w.row_stride;
-      v[u] = r < rows ? ld2(a, (int64_t)r * C + w.c, dtype) : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) { part[0][0] += v[u].x; part[0][1] += v[u].y; }
+    for (int j = 0; j < VEC; ++j) part[0][j] += v.v[j];
   }
-  warp_stats_flush<1>(part, w, C, tmp, red);
+  block_stats_flush<1>(part, cgs, C, tmp, red);
 }
 __global__ void colsum_fold_kernel(const double* __restrict__ tmp, int C, int mod, float* __restrict__ out,
                                    int accumulate) {
@@ -525,12 +556,11 @@ static inline int ew_grid(int64_t work_items, int per_block, int cap_per_sm = 16
 constexpr int RED_CAP = 4;
 // grid for the warp-per-64-channel-chunk streaming kernels: multiple of 4 so that warps/chunks is integral
 static inline int stream_grid(int64_t rows, int C, int cap_per_sm) {
-  const int64_t units = rows * (C / 64);
-  int64_t g = cdiv(units, 8 * EW_UNROLL);
+  const int rpb = 256 / (C / VEC);
+  int64_t g = cdiv(rows, (int64_t)rpb * EW_UNROLL);
   const int64_t cap = (int64_t)cap_per_sm * NUM_SMS;
   if (g > cap) g = cap;
-  g = cdiv(g, 4) * 4;
-  return (int)(g < 4 ? 4 : g);
+  return (int)(g < 1 ? 1 : g);
 }
 
 }  // namespace sg
@@ -540,7 +570,7 @@ using namespace sg;
 #define ST ((cudaStream_t)stream)
 
 extern "C" int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && a && stats && rows_total < (1ll << 31));
+  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && a && stats && rows_total < (1ll << 31));
   bn_stats_kernel<<<stream_grid(rows_total, C, RED_CAP), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
   SG_CHECK_LAUNCH();
   return SG_OK;
@@ -558,7 +588,7 @@ extern "C" int sg_bn_finalize(const double* stats, int64_t count, int C, const f
 extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
                           const float* slope, int act, int roll, int out_halo_pos, void* h, void* h_bf16,
                           void* a_bf16, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && (out_halo_pos == 0 || L >= 32));
+  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && (out_halo_pos == 0 || L >= 32));
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
   act_fwd_kernel<<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, 16), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
                                                           out_halo_pos, h, h_bf16, a_bf16);
@@ -571,7 +601,7 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
                                  int dtype, int batch, int L, int C, const float* scale_shift,
                                  const float* mean_invstd, const float* slope, int act, double* red,
                                  void* g_a_out, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && red);
+  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && red);
   act_bwd_kernel<0><<<stream_grid((int64_t)batch * L, C, RED_CAP), 256, 0, ST>>>(
       g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
@@ -584,7 +614,7 @@ extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, in
                                 int dtype, int batch, int L, int C, const float* scale_shift,
                                 const float* mean_invstd, const float* slope, int act, const double* red,
                                 int use_bn, void* g_a, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && red && g_a);
+  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && red && g_a);
   act_bwd_kernel<1><<<stream_grid((int64_t)batch * L, C, 16), 256, 0, ST>>>(
       g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a);
@@ -607,7 +637,7 @@ extern "C" int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L
 
 extern "C" int sg_colsum(const void* a, int dtype, int64_t rows, int C, int mod, float* out, int accumulate,
                          double* tmp, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 2048 && tmp && C % mod == 0);
+  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && tmp && C % mod == 0);
   SG_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * C, ST));
   colsum_kernel<<<stream_grid(rows, C, RED_CAP), 256, 0, ST>>>(a, dtype, rows, C, tmp);
   SG_CHECK_LAUNCH();
