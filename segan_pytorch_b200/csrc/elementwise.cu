@@ -553,7 +553,7 @@ static inline int ew_grid(int64_t work_items, int per_block, int cap_per_sm = 16
 }
 // kernels that end in a per-block reduction (smem + one double atomic per channel and block):
 // keep the grid at 2 CTAs/SM so the same-address atomics stay in the hundreds, not thousands
-constexpr int RED_CAP = 4;
+constexpr int RED_CAP = 3;
 // grid for the warp-per-64-channel-chunk streaming kernels: multiple of 4 so that warps/chunks is integral
 static inline int stream_grid(int64_t rows, int C, int cap_per_sm) {
   const int rpb = 256 / (C / VEC);
