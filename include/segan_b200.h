@@ -30,6 +30,11 @@ extern "C" {
 
 #define SG_ABI_VERSION 1
 
+/* Per-channel statistic buffers (sg_bn_stats `stats`, sg_act_bwd_* `red`, sg_colsum `tmp`) hold
+ * SG_STAT_SLICES interleaved partial copies: [SG_STAT_SLICES][n_stats][C] doubles, zeroed by the caller;
+ * the value of a statistic is the sum over the slices (spreads same-address atomics). */
+#define SG_STAT_SLICES 8
+
 /* status codes */
 #define SG_OK 0
 #define SG_ERR_INVALID -1
@@ -186,8 +191,8 @@ int sg_tanh_bwd(const float* gy, const float* y, int64_t n, float* gpre, float* 
 /* ------------------------------------------------------------------------------------------
  * Elementwise / reduction glue (HBM-bound).
  * ------------------------------------------------------------------------------------------ */
-/* per-channel sum / sum of squares of a [rows_total][C] 16-bit tensor into double stats[2][C]
- * (accumulated; caller zeroes).  BatchNorm1d batch statistics, modules.py:11,100. */
+/* per-channel sum / sum of squares of a [rows_total][C] 16-bit tensor into double
+ * stats[SG_STAT_SLICES][2][C] (accumulated; caller zeroes).  BatchNorm1d batch statistics, modules.py:11,100. */
 int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream);
 /* stats -> scale/shift (fp32 [2][C]: scale = gamma*invstd, shift = beta - mean*scale), saved
  * mean/invstd (fp32 [2][C]) and running-stat update (momentum 0.1, unbiased var, eps 1e-5). */

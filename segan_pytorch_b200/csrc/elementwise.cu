@@ -47,6 +47,10 @@ __device__ __forceinline__ void block_reduce_channels(float (&part)[NS][8], int 
 // ------------------------------------------------------------------------------------------
 constexpr int VEC = 4;
 constexpr int EW_UNROLL = 2;
+// per-channel statistics are accumulated into SG_STAT_SLICES interleaved copies (slice = CTA % 8):
+// ~450 CTAs hitting one fp64 address serialise at ~60 ns each (measured: ~30 us tail per launch);
+// consumers add the slices up.
+constexpr int SL = SG_STAT_SLICES;
 
 struct F4 { float v[4]; };
 __device__ __forceinline__ F4 ld4(const void* p, int64_t elem, int dtype) {
@@ -95,7 +99,8 @@ __device__ __forceinline__ void block_stats_flush(float (&part)[NS][VEC], int cg
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] += (double)smem[t * VEC + j];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) atomicAdd(out + (int64_t)s * C + cg * VEC + j, acc[j]);
+      for (int j = 0; j < VEC; ++j)
+        atomicAdd(out + ((int64_t)(blockIdx.x % SL) * NS + s) * C + cg * VEC + j, acc[j]);
     }
   }
 }
@@ -137,8 +142,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
                                    float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double mean = stats[c] / count;
-  double var = stats[C + c] / count - mean * mean;
+  double s0 = 0, s1 = 0;
+  for (int i = 0; i < SL; ++i) { s0 += stats[(int64_t)i * 2 * C + c]; s1 += stats[(int64_t)i * 2 * C + C + c]; }
+  const double mean = s0 / count;
+  double var = s1 / count - mean * mean;
   if (var < 0) var = 0;
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
   const float sc = gamma[c] * invstd;
@@ -271,8 +278,10 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
       p0[j] = is;
       p1[j] = mu * is;
     } else {
-      const float r1 = (float)(red[C + c] / (double)rows);
-      const float r2 = (float)(red[2 * C + c] / (double)rows);
+      double t1 = 0, t2 = 0;
+      for (int i = 0; i < SL; ++i) { t1 += red[((int64_t)i * 3 + 1) * C + c]; t2 += red[((int64_t)i * 3 + 2) * C + c]; }
+      const float r1 = (float)(t1 / (double)rows);
+      const float r2 = (float)(t2 / (double)rows);
       p0[j] = use_bn ? -sc[j] * r2 * is : 0.f;                       // ka
       p1[j] = use_bn ? sc[j] * (r2 * is * mu - r1) : 0.f;           // kb
     }
@@ -383,7 +392,8 @@ __global__ void colsum_fold_kernel(const double* __restrict__ tmp, int C, int mo
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= mod) return;
   double s = 0;
-  for (int c = m; c < C; c += mod) s += tmp[c];
+  for (int i = 0; i < SL; ++i)
+    for (int c = m; c < C; c += mod) s += tmp[(int64_t)i * C + c];
   out[m] = (accumulate ? out[m] : 0.f) + (float)s;
 }
 
@@ -638,7 +648,7 @@ extern "C" int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L
 extern "C" int sg_colsum(const void* a, int dtype, int64_t rows, int C, int mod, float* out, int accumulate,
                          double* tmp, void* stream) {
   SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && tmp && C % mod == 0);
-  SG_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * C, ST));
+  SG_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * C * SL, ST));
   colsum_kernel<<<stream_grid(rows, C, RED_CAP), 256, 0, ST>>>(a, dtype, rows, C, tmp);
   SG_CHECK_LAUNCH();
   colsum_fold_kernel<<<(mod + 127) / 128, 128, 0, ST>>>(tmp, C, mod, out, accumulate);

@@ -162,16 +162,24 @@ unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_i
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < PT * PT * KW; idx += 1024) {
-    const int oo = idx / (PT * KW), rem = idx % (PT * KW);
-    const int ii = rem / KW, k = rem % KW;
-    const int64_t gi = ((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k;
-    float v = tile[oo][ii][k];
-    if (kind == 1 && alpha && (o0 + oo) >= alpha_from) {
-      if (dalpha) atomicAdd(&ared[oo], v * w[gi]);
-      v *= alpha[o0 + oo - alpha_from];
+  // PT*KW = 992 consecutive elements share one outer channel `oo`: thread tid handles element
+  // (oo, tid) for every oo (tid < 992), so the alpha reduction is a per-warp shuffle + 31 smem adds
+  for (int oo = 0; oo < PT; ++oo) {
+    float contrib = 0.f;
+    if (tid < PT * KW) {
+      const int ii = tid / KW, k = tid % KW;
+      const int64_t gi = ((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k;
+      float v = tile[oo][ii][k];
+      if (kind == 1 && alpha && (o0 + oo) >= alpha_from) {
+        if (dalpha) contrib = v * w[gi];
+        v *= alpha[o0 + oo - alpha_from];
+      }
+      dw[gi] = accumulate ? dw[gi] + v : v;
     }
-    dw[gi] = accumulate ? dw[gi] + v : v;
+    if (kind == 1 && alpha && dalpha && (o0 + oo) >= alpha_from) {
+      contrib = warp_sum(contrib);
+      if ((tid & 31) == 0) atomicAdd(&ared[oo], contrib);
+    }
   }
   __syncthreads();
   if (kind == 1 && alpha && dalpha && tid < PT && (o0 + tid) >= alpha_from)

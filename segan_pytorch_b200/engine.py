@@ -196,6 +196,7 @@ class _Buffers:
 
 
 F16, BF16, F32, F64 = torch.float16, torch.bfloat16, torch.float32, torch.float64
+SL = 8   # SG_STAT_SLICES: statistic buffers are [SL][n_stats][C]; the statistic is the sum over slices
 
 
 def flatten_params(module):
@@ -515,11 +516,12 @@ class GeneratorEngine(_NetEngine):
             cnext = g_next.shape[-1]
             # PReLU backward on [B, 4*lin, cout]
             g_ad = buf.get("g.gad%d" % l, (B, lin, 4 * cout), BF16, dev)
-            red = buf.get("g.redd%d" % l, (3, cout), F64, dev, zero=True)
+            red = buf.get("g.redd%d" % l, (SL, 3, cout), F64, dev, zero=True)
             _lib.call("sg_act_bwd_reduce", _p(g_next), cnext, 0, 0, None, 0, _p(ad[l]), SG_F16, B, 4 * lin, cout,
                       None, None, _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, _p(red), _p(g_ad), st)
-            self.gview("dec_blocks.%d.act.weight" % l).add_(red[0].float())
-            self.gview("dec_blocks.%d.deconv.bias" % l).add_(red[1].float())
+            rsum = red.sum(0).float()
+            self.gview("dec_blocks.%d.act.weight" % l).add_(rsum[0])
+            self.gview("dec_blocks.%d.deconv.bias" % l).add_(rsum[1])
             if l == 0:
                 s0, s1 = ctx["z16b"], ctx["hpb"][nl - 1]
             else:
@@ -546,7 +548,7 @@ class GeneratorEngine(_NetEngine):
         for l in range(nl - 1, -1, -1):
             cout = fm[l]
             g_a = buf.get("g.ga%d" % l, (B, Lq[l], cout), BF16, dev)
-            red = buf.get("g.rede%d" % l, (3, cout), F64, dev, zero=True)
+            red = buf.get("g.rede%d" % l, (SL, 3, cout), F64, dev, zero=True)
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             if l == nl - 1:
                 gin0 = buf.t["g.gin0"]
@@ -558,9 +560,10 @@ class GeneratorEngine(_NetEngine):
                 gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * (gsk.shape[-1] // 2))
                 _lib.call("sg_act_bwd_reduce", _p(g_hp), cout, 16, 0, gadd_ptr, gsk.shape[-1], _p(a[l]), SG_F16,
                           B, Lq[l], cout, None, None, _p(slope), ACT_PRELU, _p(red), _p(g_a), st)
-            self.gview("enc_blocks.%d.act.weight" % l).add_(red[0].float())
+            rsum = red.sum(0).float()
+            self.gview("enc_blocks.%d.act.weight" % l).add_(rsum[0])
             if self.enc_bias:
-                self.gview("enc_blocks.%d.conv.bias" % l).add_(red[1].float())
+                self.gview("enc_blocks.%d.conv.bias" % l).add_(rsum[1])
             if l == 0:
                 if ctx.get("colb") is not None:
                     dwq = dwp_all[:128 * 128]
@@ -663,7 +666,7 @@ class DiscriminatorEngine(_NetEngine):
             ss[l] = buf.get("d.ss%d" % l, (2, cout), F32, dev)
             mi[l] = buf.get("d.mi%d" % l, (2, cout), F32, dev)
             if training:
-                st2 = buf.get("d.stats%d" % l, (2, cout), F64, dev, zero=True)
+                st2 = buf.get("d.stats%d" % l, (SL, 2, cout), F64, dev, zero=True)
                 _lib.call("sg_bn_stats", _p(a[l]), SG_F16, B * Lq[l], cout, _p(st2), st)
                 _lib.call("sg_bn_finalize", _p(st2), B * Lq[l], cout,
                           _p(self.pview("enc_blocks.%d.norm.weight" % l)),
@@ -733,22 +736,23 @@ class DiscriminatorEngine(_NetEngine):
         run_f(g_z1, None, 1, 0, SG_BF16, self.packed["W1dg"], SG_BF16, 256, kin, tap_ranges("full", 0, 256, kin),
               g_h, SG_BF16, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
         red = buf.get("d.red", (3, 2048), F64, dev)
-        tmp = buf.get("d.cstmp", (2048,), F64, dev)
+        tmp = buf.get("d.cstmp", (SL * 2048,), F64, dev)
         for l in range(nl - 1, -1, -1):
             cout = fm[l]
             halo = 16 if l < nl - 1 else 0
             roll = shifts[l + 1] if l < nl - 1 else 0
             g_a = buf.get("d.ga%d" % l, (B, Lq[l], cout), BF16, dev)
-            redl = buf.get("d.red%d" % l, (3, cout), F64, dev, zero=True)
+            redl = buf.get("d.red%d" % l, (SL, 3, cout), F64, dev, zero=True)
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
             _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
             if param_grads:
-                self.gview("enc_blocks.%d.act.weight" % l).add_(redl[0].float())
-                self.gview("enc_blocks.%d.norm.bias" % l).add_(redl[1].float())
-                self.gview("enc_blocks.%d.norm.weight" % l).add_(redl[2].float())
+                rsum = redl.sum(0).float()
+                self.gview("enc_blocks.%d.act.weight" % l).add_(rsum[0])
+                self.gview("enc_blocks.%d.norm.bias" % l).add_(rsum[1])
+                self.gview("enc_blocks.%d.norm.weight" % l).add_(rsum[2])
                 # conv biases feed BatchNorm: their gradient is exactly zero (the BN backward output has
                 # zero mean per channel); the reference only sees rounding noise there.  Left at zero
                 # (SEGAN_B200_EXACT_BIAS_GRAD=1 computes the column sums anyway).

@@ -320,7 +320,7 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo):
     beta = (0.1 * torch.randn(C_, generator=g)).to(DEV)
     slope = (0.2 * torch.rand(C_, generator=g)).to(DEV)
     rm, rv = torch.zeros(C_, device=DEV), torch.ones(C_, device=DEV)
-    stats = torch.zeros(2, C_, dtype=torch.float64, device=DEV)
+    stats = torch.zeros(8, 2, C_, dtype=torch.float64, device=DEV)
     ss = torch.zeros(2, C_, device=DEV)
     mi = torch.zeros(2, C_, device=DEV)
     _lib.call("sg_bn_stats", _p(a), SG_F16, B * L, C_, _p(stats), _stream())
@@ -347,7 +347,7 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo):
     # backward: gradient arrives in the consumer view (incl. halo)
     gh = (torch.randn(B, L + 2 * halo, C_, generator=g)).to(torch.bfloat16).to(DEV)
     yr.backward(gh.float().permute(0, 2, 1).cpu())
-    red = torch.zeros(3, C_, dtype=torch.float64, device=DEV)
+    red = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
     ga = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
     _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
               _p(slope), 1, _p(red), None, _stream())
@@ -358,21 +358,23 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo):
     y2 = F.prelu(a2, sl2)
     y2p = F.pad(y2, (halo, halo), mode="reflect") if halo else y2
     (y2p * gh.float().permute(0, 2, 1).cpu()).sum().add((a2 * gsk[:, :, C_:].float().permute(0, 2, 1).cpu()).sum()).backward()
-    red2 = torch.zeros(3, C_, dtype=torch.float64, device=DEV)
+    red2 = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
     ga2 = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
     gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * C_)
     _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, gadd_ptr, 2 * C_, _p(a), SG_F16, B, L, C_, None, None,
               _p(slope), 1, _p(red2), _p(ga2), _stream())
     torch.cuda.synchronize()
     assert rel_err(ga2.float().permute(0, 2, 1).cpu(), a2.grad) <= 1e-2
-    assert rel_err(red2[0].float().cpu(), sl2.grad) <= 2e-3
-    assert rel_err(red2[1].float().cpu(), a2.grad.sum((0, 2))) <= 2e-3
+    rs2 = red2.sum(0)
+    assert rel_err(rs2[0].float().cpu(), sl2.grad) <= 2e-3
+    assert rel_err(rs2[1].float().cpu(), a2.grad.sum((0, 2))) <= 2e-3
     _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
               _p(slope), 1, _p(red), 1, _p(ga), _stream())
     torch.cuda.synchronize()
-    assert rel_err(red[0].float().cpu(), sl.grad) <= 2e-3
-    assert rel_err(red[1].float().cpu(), bt.grad) <= 2e-3
-    assert rel_err(red[2].float().cpu(), gm.grad) <= 2e-3
+    rs = red.sum(0)
+    assert rel_err(rs[0].float().cpu(), sl.grad) <= 2e-3
+    assert rel_err(rs[1].float().cpu(), bt.grad) <= 2e-3
+    assert rel_err(rs[2].float().cpu(), gm.grad) <= 2e-3
     assert rel_err(ga.float().permute(0, 2, 1).cpu(), an.grad) <= 1e-2
 
 
