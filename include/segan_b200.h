@@ -216,7 +216,8 @@ int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* s
  *   red[2][C] = sum g_pre * ahat (d gamma), where y = a*scale+shift, g_pre = g_y*act'(y).
  *   Without BatchNorm g_a = g_pre is final and pass 1 writes it when g_a_out_or_null != NULL.
  * pass 2 (sg_act_bwd_apply): g_a (bf16 exact) = no BN: g_pre ;
- *   BN: scale * (g_pre - red1/N - ahat*red2/N). */
+ *   BN: scale * (g_pre - red1/N - ahat*red2/N).  `red` of pass 2 is the slice-SUMMED [3][C] buffer
+ *   (the caller adds the SG_STAT_SLICES partial copies written by pass 1). */
 /* g_h_ld / g_add_ld: row pitch in elements of g_h / g_add (>= C; lets a consumer read one half of
  * a channel-concatenated gradient in place; the pointers are pre-offset by the caller) */
 int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add, int g_add_ld,

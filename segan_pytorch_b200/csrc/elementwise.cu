@@ -278,10 +278,9 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
       p0[j] = is;
       p1[j] = mu * is;
     } else {
-      double t1 = 0, t2 = 0;
-      for (int i = 0; i < SL; ++i) { t1 += red[((int64_t)i * 3 + 1) * C + c]; t2 += red[((int64_t)i * 3 + 2) * C + c]; }
-      const float r1 = (float)(t1 / (double)rows);
-      const float r2 = (float)(t2 / (double)rows);
+      // MODE 1 receives the slice-SUMMED statistics [3][C] (the caller adds the slices of pass 1)
+      const float r1 = (float)(red[C + c] / (double)rows);
+      const float r2 = (float)(red[2 * C + c] / (double)rows);
       p0[j] = use_bn ? -sc[j] * r2 * is : 0.f;                       // ka
       p1[j] = use_bn ? sc[j] * (r2 * is * mu - r1) : 0.f;           // kb
     }

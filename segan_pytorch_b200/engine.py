@@ -746,10 +746,11 @@ class DiscriminatorEngine(_NetEngine):
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
+            rsum64 = redl.sum(0)
             _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
-                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
+                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(rsum64), 1, _p(g_a), st)
             if param_grads:
-                rsum = redl.sum(0).float()
+                rsum = rsum64.float()
                 self.gview("enc_blocks.%d.act.weight" % l).add_(rsum[0])
                 self.gview("enc_blocks.%d.norm.bias" % l).add_(rsum[1])
                 self.gview("enc_blocks.%d.norm.weight" % l).add_(rsum[2])

@@ -368,8 +368,9 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo):
     rs2 = red2.sum(0)
     assert rel_err(rs2[0].float().cpu(), sl2.grad) <= 2e-3
     assert rel_err(rs2[1].float().cpu(), a2.grad.sum((0, 2))) <= 2e-3
+    red_sum = red.sum(0).contiguous()
     _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
-              _p(slope), 1, _p(red), 1, _p(ga), _stream())
+              _p(slope), 1, _p(red_sum), 1, _p(ga), _stream())
     torch.cuda.synchronize()
     rs = red.sum(0)
     assert rel_err(rs[0].float().cpu(), sl.grad) <= 2e-3
