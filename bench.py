@@ -277,6 +277,12 @@ def main():
         a[0] += s_ev.elapsed_time(e_ev) * 1e-3
         a[1] += flops
         a[2] += 1
+    if os.environ.get("SEGAN_B200_DUMP_CALLS"):
+        per = len(prof) // args.steps
+        with open(os.environ["SEGAN_B200_DUMP_CALLS"], "w") as f:
+            for i, (kind, s_ev, e_ev, flops) in enumerate(prof[-per:]):
+                t = s_ev.elapsed_time(e_ev)
+                f.write("%3d %-10s %8.3f ms %9.2f GFLOP %7.1f TFLOP/s\n" % (i, kind, t, flops / 1e9, flops / t / 1e9))
     step_s = ms * 1e-3 / args.steps
     dom = max(agg.items(), key=lambda kv: kv[1][0])[0] if agg else None
     roof = None
