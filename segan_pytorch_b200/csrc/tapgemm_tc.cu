@@ -667,10 +667,14 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
 
   // tile -> (d, n0, kc0, split); returns false when the (tap, n, kc) block is structurally zero
   auto decode = [&](int tile, int& d, int& n0, int& kc0, int& sp) -> bool {
-    sp = tile % p.ksplit; tile /= p.ksplit;
+    // taps fastest: the CTAs that run at the same time work on the SAME position range with
+    // different taps / channel tiles, so G and the (row-shifted) A rows are shared through L2
+    // instead of being streamed from HBM once per tap
+    const int ntaps_ = p.d_hi - p.d_lo + 1;
+    d = p.d_lo + tile % ntaps_; tile /= ntaps_;
     const int kt = tile % p.k_tiles; tile /= p.k_tiles;
     const int nt = tile % p.n_tiles; tile /= p.n_tiles;
-    d = p.d_lo + tile;
+    sp = tile;
     n0 = nt * 128; kc0 = kt * p.TK;
     const int ti = d + 4;
     if (n0 + 128 <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) return false;
@@ -868,11 +872,22 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   p.batch = q->batch; p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
   const int rows_m = q->m_hi - q->m_lo;
   const int ncols = q->n_hi - q->n_lo;
-  p.TN = (ncols % 256 == 0) ? 256 : (ncols % 128 == 0 ? 128 : 64);
   if (rows_m >= 128) { p.TR = 128; p.TB = 1; }
   else { p.TR = rows_m; p.TB = 128 / rows_m; if (p.TB > q->batch) p.TB = q->batch; if (p.TB > 256) p.TB = 256; }
   p.m_tiles_per_b = (rows_m + p.TR - 1) / p.TR;
   p.b_tiles = (q->batch + p.TB - 1) / p.TB;
+  p.TN = (ncols % 256 == 0) ? 256 : (ncols % 128 == 0 ? 128 : 64);
+  if (p.TN == 256) {
+    // wave quantisation: with T uniform tiles on U units the step takes ceil(T/U) rounds.  A 128-wide
+    // tile costs ~0.55 of a 256-wide one (same A traffic, half the MMA time); take the cheaper schedule.
+    const int units = g_cta_pair ? num_sms() / 2 : num_sms();
+    const int mt = p.m_tiles_per_b * p.b_tiles;
+    const int m_units = g_cta_pair ? (mt + 1) / 2 : mt;
+    const int t256 = m_units * (ncols / 256) * p.ksplit, t128 = m_units * (ncols / 128) * p.ksplit;
+    const double c256 = (double)((t256 + units - 1) / units) * 1.0;
+    const double c128 = (double)((t128 + units - 1) / units) * 0.55;
+    if (c128 < c256) p.TN = 128;
+  }
   p.n_tiles = ncols / p.TN;
   p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 128, p.TN);
   {
