@@ -877,17 +877,8 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   p.m_tiles_per_b = (rows_m + p.TR - 1) / p.TR;
   p.b_tiles = (q->batch + p.TB - 1) / p.TB;
   p.TN = (ncols % 256 == 0) ? 256 : (ncols % 128 == 0 ? 128 : 64);
-  if (p.TN == 256) {
-    // wave quantisation: with T uniform tiles on U units the step takes ceil(T/U) rounds.  A 128-wide
-    // tile costs ~0.55 of a 256-wide one (same A traffic, half the MMA time); take the cheaper schedule.
-    const int units = g_cta_pair ? num_sms() / 2 : num_sms();
-    const int mt = p.m_tiles_per_b * p.b_tiles;
-    const int m_units = g_cta_pair ? (mt + 1) / 2 : mt;
-    const int t256 = m_units * (ncols / 256) * p.ksplit, t128 = m_units * (ncols / 128) * p.ksplit;
-    const double c256 = (double)((t256 + units - 1) / units) * 1.0;
-    const double c128 = (double)((t128 + units - 1) / units) * 0.55;
-    if (c128 < c256) p.TN = 128;
-  }
+  // (measured: 128-wide tiles to soften wave quantisation lose more to the 256-cycle issue
+  //  cadence and doubled A traffic than they gain -- 8.7 -> 10.6 ms/step -- so stay at 256)
   p.n_tiles = ncols / p.TN;
   p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 128, p.TN);
   {
@@ -945,7 +936,7 @@ int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st) {
   p.PR = q->g_rows >= 64 ? 64 : q->g_rows;
   p.PB = 64 / p.PR;
   p.TK = q->kc >= 256 ? 256 : q->kc;
-  if (q->a1 && q->a0_c < 256 && p.TK > q->a0_c) p.TK = q->a0_c;   // a kc tile never straddles the two sources unevenly
+  // a kc tile may straddle the two sources: every 64-channel box picks its own tensor map
   p.n_tiles = q->nc / 128;
   p.k_tiles = q->kc / p.TK;
   p.row_chunks = (q->g_rows + p.PR - 1) / p.PR;
