@@ -258,6 +258,26 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    # ---- BASELINE config 5 (secondary metric): G-only streaming inference, fp16, batches of B windows,
+    #      host->device copy of every batch and device->host copy of the enhanced windows included
+    s.G.eval()
+    n_inf = 4
+    out_h = torch.empty(B, 1, 16384).pin_memory()
+    zinf = torch.randn(B, 1024, 16, device=dev)
+    with torch.no_grad():
+        for _ in range(2):
+            s.G(cbuf, z=zinf)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(n_inf):
+            nbuf.copy_(noisy_h.unsqueeze(1), non_blocking=True)
+            y = s.G(nbuf, z=zinf)
+            out_h.copy_(y, non_blocking=True)
+        g1.record()
+        barrier()
+    ms_inf = g0.elapsed_time(g1)
+    s.G.train()
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # max over ranks
@@ -323,6 +343,10 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 2 * B * 16384 * 4, "d2h_bytes_per_step": 16, "last_losses": host_loss},
+        "g_only_inference": {"value": B * n_inf / (ms_inf * 1e-3), "unit": "windows/s per GPU",
+                             "what": "G forward (clean.py path), fp16 operands, batches of %d windows, "
+                                     "H2D + D2H of every batch inside the timed region" % B,
+                             "ms_per_batch": ms_inf / n_inf},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
