@@ -361,8 +361,8 @@ class SEGAN(Model):
 
 
 class WSEGAN(SEGAN):
-    """Whisper-SEGAN (model.py:509-766).  Constructor / init parity is built; the fused WSEGAN step
-    (extra misaligned-pair D pass + STFT log-power L1) is the next row."""
+    """Whisper-SEGAN (model.py:509-766): xavier init, one weighted D loss over real / fake /
+    [misaligned] pairs, G loss = adversarial + STFT log-power L1 + masked L1."""
 
     def __init__(self, opts, name='WSEGAN', generator=None, discriminator=None):
         self.lbd = 1
@@ -378,6 +378,111 @@ class WSEGAN(SEGAN):
 
     def infer_G(self, nwav, cwav=None, z=None, ret_hid=False):
         return self.G(nwav, z=z, ret_hid=ret_hid)
+
+    def sample_dloader(self, dloader, device='cuda'):
+        """model.py:526-535 -- a fresh iterator every step (the reference's behaviour)."""
+        uttname, clean, noisy, slice_idx = next(iter(dloader))
+        clean = clean.unsqueeze(1).to(device).float()
+        noisy = noisy.unsqueeze(1).to(device).float()
+        return uttname, clean, noisy, slice_idx
+
+    @staticmethod
+    def stft_logpow(x, n_fft):
+        """model.py:640-646: |STFT| (n_fft 2048, hop 160, win 320 rectangular, normalized) -> 10 log10(.^2+1e-19).
+        Library-backed (cuFFT through torch.stft): the spectral term is <1 % of the step's FLOPs."""
+        st = torch.stft(x.squeeze(1), n_fft=min(x.size(-1), n_fft), hop_length=160, win_length=320,
+                        normalized=True, return_complex=True)
+        mod = torch.norm(torch.view_as_real(st), 2, dim=3)
+        return 10 * torch.log10(mod ** 2 + 10e-20)
+
+    def train_step(self, clean, noisy, Gopt, Dopt, l1_weight, uttname=None, z=None, shifts=None, perm=None,
+                   losses=None):
+        """One WSEGAN step (model.py:572-669) with optional --misalign_pair.  Returns the device tensor
+        [d_loss, g_adv, pow_loss, den_loss].  Draw order of python `random` as in the reference:
+        D(real) shifts, [z], D(fake) shifts, shuffle, D(misaligned) shifts, D(fake) shifts."""
+        if self.interf_pair or self.vanilla_gan:
+            raise NotImplementedError("--interf_pair / --vanilla_gan are SURVEY.md 8(f)-N4 'next' rows")
+        ge, de = self.G.engine, self.D.engine
+        B, _, L = clean.shape
+        dev = clean.device
+        nl = len(self.D.enc_blocks)
+        losses = torch.zeros(4, dtype=torch.float32, device=dev) if losses is None else losses.zero_()
+        lptr = lambda i: C.c_void_p(losses.data_ptr() + 4 * i)
+        nsh = iter(shifts) if shifts is not None else None
+        draw = (lambda: next(nsh)) if nsh is not None else (lambda: draw_phase_shifts(nl, self.D.phase_shift))
+        d_weight = (1.0 / 3) if self.misalign_pair else 0.5
+        Dopt.zero_grad()
+        _, c = de.forward(clean, noisy, draw(), training=True)
+        de.backward(c, 1.0, d_weight, param_grads=True, loss_out=lptr(0))
+        if z is None:
+            z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+        Genh, gctx = ge.forward(noisy, z)
+        _, c = de.forward(Genh, noisy, draw(), training=True)
+        de.backward(c, 0.0, d_weight, param_grads=True, loss_out=lptr(0))
+        if self.misalign_pair:
+            if perm is None:
+                perm = list(range(B))
+                random.shuffle(perm)                                       # model.py:598-600
+            clean_shuf = clean[torch.as_tensor(perm, device=dev)]
+            _, c = de.forward(clean, clean_shuf, draw(), training=True)
+            de.backward(c, 0.0, d_weight, param_grads=True, loss_out=lptr(0))
+        Dopt.step(allreduce_grads(de))
+        Gopt.zero_grad()
+        _, c = de.forward(Genh, noisy, draw(), training=True, twins=False)
+        gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
+        de.backward(c, 1.0, 1.0, param_grads=False, input_grad=gy, loss_out=lptr(1))
+        # spectral power loss (model.py:638-653)
+        gt = Genh.detach().requires_grad_(True)
+        with torch.enable_grad():
+            pow_loss = self.pow_weight * F.l1_loss(self.stft_logpow(gt, self.n_fft), self.stft_logpow(clean, self.n_fft))
+            tot = pow_loss
+            if l1_weight > 0 and uttname is not None and any('additive' in u for u in uttname):
+                mask = torch.zeros(B, 1, L, device=dev)                    # model.py:655-665
+                for i, u in enumerate(uttname):
+                    if 'additive' in u:
+                        mask[i, 0, :] = 1.
+                den = l1_weight * F.l1_loss(gt * mask, clean * mask)
+                losses[3] += den.detach()
+                tot = tot + den
+            tot.backward()
+        losses[2] += pow_loss.detach()
+        gy.add_(gt.grad)
+        ge.backward(gctx, gy)
+        Gopt.step(allreduce_grads(ge))
+        return losses
+
+    def train(self, opts, dloader, criterion, l1_init, l1_dec_step, l1_dec_epoch, log_freq, va_dloader=None,
+              device='cuda'):
+        """model.py:537-753: iteration-based loop (a fresh loader iterator per step), EOE checkpoints."""
+        rank0 = _dist() is None or _dist().get_rank() == 0
+        self.writer = SummaryWriter(os.path.join(opts.save_path, 'train')) if rank0 else SummaryWriter()
+        self.z_device = getattr(opts, 'z_device', self.z_device)
+        Gopt, Dopt = self.build_optimizers(opts)
+        self.G.optim, self.D.optim = Gopt, Dopt
+        eoe_g_saver = Saver(self.G, opts.save_path, max_ckpts=3, optimizer=self.G.optim, prefix='EOE_G-')
+        eoe_d_saver = Saver(self.D, opts.save_path, max_ckpts=3, optimizer=self.D.optim, prefix='EOE_D-')
+        l1_weight = l1_init
+        timings = []
+        losses = None
+        self.G.train()
+        self.D.train()
+        for iteration in range(1, opts.epoch * len(dloader) + 1):
+            beg_t = timeit.default_timer()
+            uttname, clean, noisy, slice_idx = self.sample_dloader(dloader, device)
+            losses = self.train_step(clean, noisy, Gopt, Dopt, l1_weight, uttname=uttname, losses=losses)
+            timings.append(timeit.default_timer() - beg_t)
+            if iteration % log_freq == 0:
+                lv = losses.tolist()
+                if rank0:
+                    print('Iter {}/{} ({} bpe) d_loss:{:.4f}, g_loss: {:.4f}, pow_loss: {:.4f}, den_loss: {:.4f} '
+                          'btime: {:.4f} s, mbtime: {:.4f} s'.format(iteration, len(dloader) * opts.epoch, len(dloader),
+                                                                     lv[0], lv[1] + lv[2] + lv[3], lv[2], lv[3],
+                                                                     timings[-1], np.mean(timings)))
+            if iteration % len(dloader) == 0 and rank0:
+                self.G.save(self.save_path, iteration, saver=eoe_g_saver)
+                self.D.save(self.save_path, iteration, saver=eoe_d_saver)
+        self.last_losses = losses
+        return timings
 
     def generate(self, inwav, z=None):
         """model.py:755-766: un-chunked inference on the utterance zero-padded to a multiple of 1024
