@@ -184,8 +184,8 @@ struct FTcParams {
 struct SharedCtl {
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[8];      // up to 512 / TN accumulator stages (2 x 256 ... 8 x 64 columns)
+  uint64_t tmem_empty[8];
   uint32_t tmem_base;
 };
 
@@ -215,7 +215,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 128); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&ctl->tmem_base, 512);
@@ -228,6 +228,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   const int total_tiles = m_tiles * p.n_tiles * p.ksplit;
   const uint32_t a_bytes = (uint32_t)p.TR * p.TB * 128u;
   const uint32_t b_bytes = (uint32_t)p.TN * 128u;
+  const int nacc = 512 / p.TN;     // accumulator stages in TMEM: short-K tiles are bound by this ping-pong depth
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -273,7 +274,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         const int n0 = p.n_lo + nt * p.TN;
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.TN);
         // the issuer only needs the NUMBER of K steps (the producer decides what they contain):
         // keep this single thread's loop as short as possible -- it paces the tensor pipe
         const int nsteps = f_num_steps(p, n0, ks);
@@ -292,7 +293,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&ctl->tmem_full[acc]);     // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -314,7 +315,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       const bool valid = (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.TN);
       const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
       for (int c0 = 0; c0 < p.TN; c0 += 32) {
         uint32_t r[32];
@@ -361,7 +362,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       }
       tc_fence_before();
       mbar_arrive(&ctl->tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
@@ -389,8 +390,8 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;          // shared::cluster address 
 struct SharedCtl2 {
   uint64_t full[STAGES2];
   uint64_t empty[STAGES2];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[8];      // up to 512 / TN accumulator stages (2 x 256 ... 8 x 64 columns)
+  uint64_t tmem_empty[8];
   uint32_t tmem_base;
 };
 
@@ -461,7 +462,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
     for (int s = 0; s < STAGES2; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 256); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 256); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(&ctl->tmem_base, 512);
@@ -478,6 +479,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const int half_n = p.TN / 2;
   const uint32_t a_bytes = (uint32_t)p.TR * p.TB * 128u;
   const uint32_t b_bytes = (uint32_t)half_n * 128u;
+  const int nacc = 512 / p.TN;
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
@@ -522,7 +524,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         const int n0 = p.n_lo + nt * p.TN;
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.TN);
         const int nsteps = f_num_steps(p, n0, ks);
         const uint32_t smem0 = smem_u32(smem);
         for (int i = 0; i < nsteps; ++i) {
@@ -539,7 +541,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&ctl->tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -562,7 +564,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const bool valid = (mt < m_tiles) && (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.TN);
       const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
       for (int c0 = 0; c0 < p.TN; c0 += 32) {
         uint32_t r[32];
@@ -609,7 +611,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
       tc_fence_before();
       mbar_arrive_leader(&ctl->tmem_empty[acc]);      // 2 x 128 arrivals release the accumulator
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
