@@ -326,8 +326,11 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias != nullptr && ks == 0) {
+            // bias_mod is a multiple of 64 and the chunk is 32-aligned: one modulo per chunk
+            // (scalar loads: bias vectors are 4-byte-aligned views of the flat parameter buffer)
+            const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ((n0 + c0 + j) % p.bias_mod));
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
           }
           if (p.out_dtype == SG_F32) {
             float* o = reinterpret_cast<float*>(p.out) + obase + c0;
@@ -575,8 +578,11 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias != nullptr && ks == 0) {
+            // bias_mod is a multiple of 64 and the chunk is 32-aligned: one modulo per chunk
+            // (scalar loads: bias vectors are 4-byte-aligned views of the flat parameter buffer)
+            const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + ((n0 + c0 + j) % p.bias_mod));
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
           }
           if (p.out_dtype == SG_F32) {
             float* o = reinterpret_cast<float*>(p.out) + obase + c0;
