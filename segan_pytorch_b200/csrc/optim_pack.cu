@@ -61,54 +61,52 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 //   Wtd[d+4][ci][r*Cout + co] = a(ci) W[ci][co][ 4d + r + 13] (dgrad: K = (r,co), N = ci)
 // entries whose tap index falls outside [0, 30] are zero.
 // ------------------------------------------------------------------------------------------
-constexpr int PT = 32;                       // channel tile (both directions): 128-byte fp32 / 64-byte 16-bit segments
-constexpr int PACK_SMEM = PT * PT * (KW + 2) * 4;   // last dim padded to 33 words: conflict-free transposes
+constexpr int PO = 16, PI = 32;              // tile: 16 outer x 32 inner channels x 31 taps (3 CTAs/SM)
+constexpr int PACK_THREADS = 512;
+constexpr int PACK_SMEM = PO * PI * (KW + 2) * 4;   // last dim padded to 33 words: conflict-free transposes
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(PACK_THREADS)
 pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner, const float* __restrict__ alpha,
                  int alpha_from, void* __restrict__ w_fwd, void* __restrict__ w_dg, int dt_fwd, int dt_dg) {
   // master layout is [outer][inner][31]; kind 0: outer = co, inner = ci ; kind 1: outer = ci, inner = co
   extern __shared__ float tile_raw[];
-  float (*tile)[PT][KW + 2] = reinterpret_cast<float (*)[PT][KW + 2]>(tile_raw);
-  const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
+  float (*tile)[PI][KW + 2] = reinterpret_cast<float (*)[PI][KW + 2]>(tile_raw);
+  const int o0 = blockIdx.y * PO, i0 = blockIdx.x * PI;
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < PT * PT * KW; idx += 1024) {
-    const int oo = idx / (PT * KW), rem = idx % (PT * KW);
+  for (int idx = tid; idx < PO * PI * KW; idx += PACK_THREADS) {
+    const int oo = idx / (PI * KW), rem = idx % (PI * KW);
     const int ii = rem / KW, k = rem % KW;
     float v = w[((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k];
     if (kind == 1 && alpha && (o0 + oo) >= alpha_from) v *= alpha[o0 + oo - alpha_from];
     tile[oo][ii][k] = v;
   }
   __syncthreads();
-  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 1024) {
-    const int lo = idx % PT;            // fastest index -> contiguous channel in the destination
-    const int hi = (idx / PT) % PT;
-    const int ph = (idx / (PT * PT)) % 4;
-    const int ti = idx / (4 * PT * PT); // d + 4
-    const int d = ti - 4;
-    if (kind == 0) {
-      const int Cout = c_outer, Cin = c_inner;
-      {  // Wf[ti][co = hi][ph*Cin + ci = lo]
+  // destination A: contiguous along the INNER channel (32 wide); destination B: along the OUTER (16 wide)
+  for (int idx = tid; idx < NTAP * 4 * PO * PI; idx += PACK_THREADS) {
+    {  // A: lo = inner
+      const int lo = idx % PI, hi = (idx / PI) % PO, ph = (idx / (PI * PO)) % 4, ti = idx / (4 * PI * PO);
+      const int d = ti - 4;
+      if (kind == 0) {   // Wf[ti][co = hi][ph*Cin + ci = lo],  k = 4d + ph + 14
         const int k = 4 * d + ph + 14;
         const float v = (k >= 0 && k < KW) ? tile[hi][lo][k] : 0.f;
-        st16(w_fwd, ((int64_t)ti * Cout + (o0 + hi)) * (4 * Cin) + ph * Cin + (i0 + lo), v, dt_fwd);
-      }
-      {  // Wdg[ti][ph*Cin + ci = hi][co = lo]
-        const int k = -4 * d + ph + 14;
-        const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
-        st16(w_dg, ((int64_t)ti * (4 * Cin) + ph * Cin + (i0 + hi)) * Cout + (o0 + lo), v, dt_dg);
-      }
-    } else {
-      const int Cin = c_outer, Cout = c_inner;
-      {  // Wt[ti][ph*Cout + co = hi][ci = lo]
-        const int k = -4 * d + ph + 13;
-        const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
-        st16(w_fwd, ((int64_t)ti * (4 * Cout) + ph * Cout + (i0 + hi)) * Cin + (o0 + lo), v, dt_fwd);
-      }
-      {  // Wtd[ti][ci = hi][ph*Cout + co = lo]
+        st16(w_fwd, ((int64_t)ti * c_outer + (o0 + hi)) * (4 * c_inner) + ph * c_inner + (i0 + lo), v, dt_fwd);
+      } else {           // Wtd[ti][ci = hi][ph*Cout + co = lo],  k = 4d + ph + 13
         const int k = 4 * d + ph + 13;
         const float v = (k >= 0 && k < KW) ? tile[hi][lo][k] : 0.f;
-        st16(w_dg, ((int64_t)ti * Cin + (o0 + hi)) * (4 * Cout) + ph * Cout + (i0 + lo), v, dt_dg);
+        st16(w_dg, ((int64_t)ti * c_outer + (o0 + hi)) * (4 * c_inner) + ph * c_inner + (i0 + lo), v, dt_dg);
+      }
+    }
+    {  // B: lo = outer
+      const int lo = idx % PO, hi = (idx / PO) % PI, ph = (idx / (PI * PO)) % 4, ti = idx / (4 * PI * PO);
+      const int d = ti - 4;
+      if (kind == 0) {   // Wdg[ti][ph*Cin + ci = hi][co = lo],  k = -4d + ph + 14
+        const int k = -4 * d + ph + 14;
+        const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
+        st16(w_dg, ((int64_t)ti * (4 * c_inner) + ph * c_inner + (i0 + hi)) * c_outer + (o0 + lo), v, dt_dg);
+      } else {           // Wt[ti][ph*Cout + co = hi][ci = lo],  k = -4d + ph + 13
+        const int k = -4 * d + ph + 13;
+        const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
+        st16(w_fwd, ((int64_t)ti * (4 * c_inner) + ph * c_inner + (i0 + hi)) * c_outer + (o0 + lo), v, dt_fwd);
       }
     }
   }
@@ -136,53 +134,51 @@ __global__ void pack_fc_kernel(const float* __restrict__ w, int nout, int C, int
 //         dalpha[ci-alpha_from] = sum_{co,k} dWe * W
 // kind 2: dW[n][c*T+t] = dW1p[n][t*C+c]
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(PACK_THREADS)
 unpack_conv_kernel(int kind, const float* __restrict__ dwp, int c_outer, int c_inner, const float* __restrict__ w,
                    const float* __restrict__ alpha, int alpha_from, float* __restrict__ dw,
                    float* __restrict__ dalpha, int accumulate) {
   extern __shared__ float tile_raw[];
-  float (*tile)[PT][KW + 2] = reinterpret_cast<float (*)[PT][KW + 2]>(tile_raw);
-  __shared__ float ared[PT];
-  const int o0 = blockIdx.y * PT, i0 = blockIdx.x * PT;
+  float (*tile)[PI][KW + 2] = reinterpret_cast<float (*)[PI][KW + 2]>(tile_raw);
+  __shared__ float ared[PO];
+  const int o0 = blockIdx.y * PO, i0 = blockIdx.x * PI;
   const int tid = threadIdx.x;
-  if (tid < PT) ared[tid] = 0.f;
-  for (int idx = tid; idx < NTAP * 4 * PT * PT; idx += 1024) {
-    const int lo = idx % PT, hi = (idx / PT) % PT, ph = (idx / (PT * PT)) % 4, ti = idx / (4 * PT * PT);
-    const int d = ti - 4;
-    if (kind == 0) {
-      const int Cout = c_outer, Cin = c_inner;
-      const int k = 4 * d + ph + 14;
+  if (tid < PO) ared[tid] = 0.f;
+  for (int idx = tid; idx < NTAP * 4 * PO * PI; idx += PACK_THREADS) {
+    if (kind == 0) {   // dWf[ti][co = hi][ph*Cin + ci = lo]: contiguous along the inner channel
+      const int lo = idx % PI, hi = (idx / PI) % PO, ph = (idx / (PI * PO)) % 4, ti = idx / (4 * PI * PO);
+      const int k = 4 * (ti - 4) + ph + 14;
       if (k >= 0 && k < KW)
-        tile[hi][lo][k] = dwp[((int64_t)ti * Cout + (o0 + hi)) * (4 * Cin) + ph * Cin + (i0 + lo)];
-    } else {
-      const int Cin = c_outer, Cout = c_inner;
-      const int k = -4 * d + ph + 13;
+        tile[hi][lo][k] = dwp[((int64_t)ti * c_outer + (o0 + hi)) * (4 * c_inner) + ph * c_inner + (i0 + lo)];
+    } else {           // dWt[ti][ph*Cout + co = hi][ci = lo]: contiguous along the outer channel
+      const int lo = idx % PO, hi = (idx / PO) % PI, ph = (idx / (PI * PO)) % 4, ti = idx / (4 * PI * PO);
+      const int k = -4 * (ti - 4) + ph + 13;
       if (k >= 0 && k < KW)
-        tile[lo][hi][k] = dwp[((int64_t)ti * (4 * Cout) + ph * Cout + (i0 + hi)) * Cin + (o0 + lo)];
+        tile[lo][hi][k] = dwp[((int64_t)ti * (4 * c_inner) + ph * c_inner + (i0 + hi)) * c_outer + (o0 + lo)];
     }
   }
   __syncthreads();
-  // PT*KW = 992 consecutive elements share one outer channel `oo`: thread tid handles element
-  // (oo, tid) for every oo (tid < 992), so the alpha reduction is a per-warp shuffle + 31 smem adds
-  for (int oo = 0; oo < PT; ++oo) {
-    float contrib = 0.f;
-    if (tid < PT * KW) {
-      const int ii = tid / KW, k = tid % KW;
+  // PI*KW = 992 consecutive master elements share one outer channel `oo`
+  for (int oo = 0; oo < PO; ++oo) {
+    for (int e = tid; e < PI * KW; e += PACK_THREADS) {
+      const int ii = e / KW, k = e % KW;
       const int64_t gi = ((int64_t)(o0 + oo) * c_inner + (i0 + ii)) * KW + k;
       float v = tile[oo][ii][k];
-      if (kind == 1 && alpha && (o0 + oo) >= alpha_from) {
+      float contrib = 0.f;
+      const bool al = kind == 1 && alpha && (o0 + oo) >= alpha_from;
+      if (al) {
         if (dalpha) contrib = v * w[gi];
         v *= alpha[o0 + oo - alpha_from];
       }
       dw[gi] = accumulate ? dw[gi] + v : v;
-    }
-    if (kind == 1 && alpha && dalpha && (o0 + oo) >= alpha_from) {
-      contrib = warp_sum(contrib);
-      if ((tid & 31) == 0) atomicAdd(&ared[oo], contrib);
+      if (al && dalpha) {
+        contrib = warp_sum(contrib);
+        if ((tid & 31) == 0) atomicAdd(&ared[oo], contrib);
+      }
     }
   }
   __syncthreads();
-  if (kind == 1 && alpha && dalpha && tid < PT && (o0 + tid) >= alpha_from)
+  if (kind == 1 && alpha && dalpha && tid < PO && (o0 + tid) >= alpha_from)
     atomicAdd(dalpha + (o0 + tid - alpha_from), ared[tid]);
 }
 
@@ -301,14 +297,14 @@ extern "C" int sg_pack_weights(int kind, const float* w, int c_out, int c_in, in
     attr_set = true;
   }
   if (kind == 0) {
-    SG_CHECK_ARG(c_out % PT == 0 && c_in % PT == 0);
-    dim3 grid(c_in / PT, c_out / PT);
-    pack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(0, w, c_out, c_in, nullptr, 0, w_fwd, w_dgrad, dtype_fwd,
+    SG_CHECK_ARG(c_out % PO == 0 && c_in % PI == 0);
+    dim3 grid(c_in / PI, c_out / PO);
+    pack_conv_kernel<<<grid, PACK_THREADS, PACK_SMEM, ST>>>(0, w, c_out, c_in, nullptr, 0, w_fwd, w_dgrad, dtype_fwd,
                                                    dtype_dgrad);
   } else if (kind == 1) {
-    SG_CHECK_ARG(c_out % PT == 0 && c_in % PT == 0);
-    dim3 grid(c_out / PT, c_in / PT);
-    pack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(1, w, c_in, c_out, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
+    SG_CHECK_ARG(c_out % PI == 0 && c_in % PO == 0);
+    dim3 grid(c_out / PI, c_in / PO);
+    pack_conv_kernel<<<grid, PACK_THREADS, PACK_SMEM, ST>>>(1, w, c_in, c_out, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
                                                    dtype_dgrad);
   } else if (kind == 2) {
     pack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(w, c_out, c_in, t_len, w_fwd, w_dgrad, dtype_fwd, dtype_dgrad);
@@ -330,12 +326,12 @@ extern "C" int sg_unpack_wgrad(int kind, const float* dwp, int c_out, int c_in, 
     attr_set = true;
   }
   if (kind == 0) {
-    dim3 grid(c_in / PT, c_out / PT);
-    unpack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(0, dwp, c_out, c_in, nullptr, nullptr, 0, dw, nullptr,
+    dim3 grid(c_in / PI, c_out / PO);
+    unpack_conv_kernel<<<grid, PACK_THREADS, PACK_SMEM, ST>>>(0, dwp, c_out, c_in, nullptr, nullptr, 0, dw, nullptr,
                                                      accumulate);
   } else if (kind == 1) {
-    dim3 grid(c_out / PT, c_in / PT);
-    unpack_conv_kernel<<<grid, 1024, PACK_SMEM, ST>>>(1, dwp, c_in, c_out, w, alpha, alpha_from, dw, dalpha,
+    dim3 grid(c_out / PI, c_in / PO);
+    unpack_conv_kernel<<<grid, PACK_THREADS, PACK_SMEM, ST>>>(1, dwp, c_in, c_out, w, alpha, alpha_from, dw, dalpha,
                                                      accumulate);
   } else if (kind == 2) {
     unpack_fc_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(dwp, c_out, c_in, t_len, dw, accumulate);
