@@ -486,7 +486,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
-    if (lane == 0) {
+    if (lane < 2) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair_id; tile < total_tiles; tile += npairs) {
         const int mp = tile % m_pairs;
@@ -505,11 +505,14 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             if (p.ksplit > 1 && step % p.ksplit != ks) continue;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE2_BYTES;
-            uint8_t* sb = sa + A_STAGE_BYTES;
-            if (leader) mbar_expect_tx(&ctl->full[stage], 2u * (a_bytes + b_bytes));
-            if (k0 < p.a0_c) tma_load_3d_pair(sa, &tmA0, &ctl->full[stage], k0, m0 + d + p.a_halo, b0);
-            else tma_load_3d_pair(sa, &tmA1, &ctl->full[stage], k0 - p.a0_c, m0 + d + p.a_halo, b0);
-            tma_load_2d_pair(sb, &tmW, &ctl->full[stage], k0, (ti - p.w_tap0) * p.nc + n0 + (int)rank * half_n);
+            if (leader && lane == 0) mbar_expect_tx(&ctl->full[stage], 2u * (a_bytes + b_bytes));
+            // lane 0: this CTA's A box; lane 1: its half of the weight box -- one warp instruction
+            const bool in0 = k0 < p.a0_c;
+            const CUtensorMap* map = lane == 0 ? (in0 ? &tmA0 : &tmA1) : &tmW;
+            const int c0 = (lane == 0 && !in0) ? k0 - p.a0_c : k0;
+            const int c1 = lane == 0 ? m0 + d + p.a_halo : (ti - p.w_tap0) * p.nc + n0 + (int)rank * half_n;
+            const int c2 = lane == 0 ? b0 : 0;
+            tma_load_3d_pair(lane == 0 ? sa : sa + A_STAGE_BYTES, map, &ctl->full[stage], c0, c1, c2);
             if (++stage == STAGES2) { stage = 0; phase ^= 1; }
           }
         }
@@ -691,27 +694,29 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: lane j issues box j (lanes 0,1: the two 64-channel G boxes; lanes 2..: the A boxes),
+    // so the 3..6 bulk copies of a stage leave as ONE warp instruction instead of a serial chain
+    if (lane < 2 + kboxes) {
       int stage = 0; uint32_t phase = 0;
+      const bool is_g = lane < 2;
+      const int j = is_g ? lane : lane - 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int d, n0, kc0, sp;
         if (!decode(tile, d, n0, kc0, sp)) continue;
         const int s_lo = sp * steps_per_split;
         const int s_hi = min(pos_steps, s_lo + steps_per_split);
+        // this lane's box: tensor map, channel coordinate, row shift, smem offset
+        const int kk = kc0 + 64 * j;
+        const CUtensorMap* map = is_g ? &tmG : (kk < p.a0_c ? &tmA0 : &tmA1);
+        const int c0 = is_g ? n0 + 64 * j : (kk < p.a0_c ? kk : kk - p.a0_c);
+        const int rshift = is_g ? 0 : d + p.a_halo;
+        const uint32_t off = is_g ? 8192u * j : (uint32_t)A_STAGE_BYTES + 8192u * j;
+        int rc = s_lo % p.row_chunks, bc = s_lo / p.row_chunks;
         for (int s = s_lo; s < s_hi; ++s) {
-          const int r0 = (s % p.row_chunks) * p.PR;
-          const int b0 = (s / p.row_chunks) * p.PB;
           mbar_wait(&ctl->empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;      // G boxes (2 x 8 KB)
-          uint8_t* sb = sa + A_STAGE_BYTES;              // A boxes (kboxes x 8 KB)
-          mbar_expect_tx(&ctl->full[stage], stage_tx);
-          tma_load_3d(sa, &tmG, &ctl->full[stage], n0, r0, b0);
-          tma_load_3d(sa + 8192, &tmG, &ctl->full[stage], n0 + 64, r0, b0);
-          for (int j = 0; j < kboxes; ++j) {
-            const int kk = kc0 + 64 * j;
-            if (kk < p.a0_c) tma_load_3d(sb + 8192 * j, &tmA0, &ctl->full[stage], kk, r0 + d + p.a_halo, b0);
-            else tma_load_3d(sb + 8192 * j, &tmA1, &ctl->full[stage], kk - p.a0_c, r0 + d + p.a_halo, b0);
-          }
+          if (lane == 0) mbar_expect_tx(&ctl->full[stage], stage_tx);
+          tma_load_3d(smem + stage * STAGE_BYTES + off, map, &ctl->full[stage], c0, rc * p.PR + rshift, bc * p.PB);
+          if (++rc == p.row_chunks) { rc = 0; ++bc; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -910,7 +915,7 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
       SG_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_f_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
       attr2 = true;
     }
-    rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)(q->d_hi + 4 - q->w_tap0 + 1) * q->nc, p.TN / 2);
+    rc = make_map3(&tmW, q->w, q->w_dtype, q->kc, (q->d_hi + 4 - q->w_tap0 + 1) * q->nc, 1, p.TN / 2, 1);
     if (rc) return rc;
     p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 256, p.TN);
     const int pairs = ((m_tiles_all + 1) / 2) * p.n_tiles * p.ksplit;
