@@ -62,6 +62,19 @@ int sg_device_ok(void);
 /* 1 (default): forward-form tap-GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles);
  * 0: single-CTA 128-row tiles.  Returns the previous setting. */
 int sg_set_cta_pair(int on);
+/* Tuning knobs of the HBM-bound streaming kernels, one per kernel family (`kind`):
+ *   SG_EW_ACT_FWD (sg_act_fwd), SG_EW_BN_STATS (sg_bn_stats), SG_EW_BWD_REDUCE (sg_act_bwd_reduce),
+ *   SG_EW_BWD_APPLY (sg_act_bwd_apply).
+ * vec: channels per thread (4 | 8); unroll: rows in flight per thread and input stream (2 | 4 | 8 with
+ * vec*unroll <= 32); cap: CTAs per SM (persistent grid beyond that).  For the two backward kinds vec == 8
+ * selects the tiled kernel (unroll 2 | 4), vec == 4 the generic one.  Every variant computes the same values
+ * (up to fp32 summation order).  Also read once from the environment: SEGAN_B200_EW="kind,vec,unroll,cap[;...]".
+ * Returns SG_OK or SG_ERR_INVALID. */
+#define SG_EW_ACT_FWD 1
+#define SG_EW_BN_STATS 2
+#define SG_EW_BWD_REDUCE 3
+#define SG_EW_BWD_APPLY 4
+int sg_set_ew_variant(int kind, int vec, int unroll, int cap);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-GEMM, forward form ("F"):
@@ -216,8 +229,10 @@ int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* s
  *   red[2][C] = sum g_pre * ahat (d gamma), where y = a*scale+shift, g_pre = g_y*act'(y).
  *   Without BatchNorm g_a = g_pre is final and pass 1 writes it when g_a_out_or_null != NULL.
  * pass 2 (sg_act_bwd_apply): g_a (bf16 exact) = no BN: g_pre ;
- *   BN: scale * (g_pre - red1/N - ahat*red2/N).  `red` of pass 2 is the slice-SUMMED [3][C] buffer
- *   (the caller adds the SG_STAT_SLICES partial copies written by pass 1). */
+ *   BN: scale * (g_pre - red1/N - ahat*red2/N).  `red` of pass 2 is the buffer pass 1 wrote
+ *   ([SG_STAT_SLICES][3][C]; the kernel adds the slices up).
+ * sg_stat_grads: g_s[c] += sum over slices of red[slice][s][c] for s < n_stats (g_s may be NULL):
+ *   the PReLU-slope / bias (beta) / gamma gradients of model.py:299,306,320 from the pass-1 statistics. */
 /* g_h_ld / g_add_ld: row pitch in elements of g_h / g_add (>= C; lets a consumer read one half of
  * a channel-concatenated gradient in place; the pointers are pre-offset by the caller) */
 int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add, int g_add_ld,
@@ -228,6 +243,7 @@ int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, con
                      const void* a, int dtype, int batch, int L, int C,
                      const float* scale_shift, const float* mean_invstd, const float* slope,
                      int act, const double* red, int use_bn, void* g_a, void* stream);
+int sg_stat_grads(const double* red, int C, int n_stats, float* g0, float* g1, float* g2, void* stream);
 /* fp32 NCL [B][C][L] <-> 16-bit NLC [B][L][C] (z input, generator.py:195-205; ret_hid outputs) */
 int sg_ncl_to_nlc(const float* src, int batch, int C, int L, void* dst, int dtype, void* stream);
 int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L, float* dst, void* stream);

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libsegan_b200.so")
 
 SG_F32, SG_F16, SG_BF16 = 0, 1, 2
 ACT_NONE, ACT_PRELU, ACT_TANH = 0, 1, 2
+EW_ACT_FWD, EW_BN_STATS, EW_BWD_REDUCE, EW_BWD_APPLY = 1, 2, 3, 4
 BACKEND_FFMA, BACKEND_TCGEN05 = 0, 1
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -64,6 +65,7 @@ _SIGS = {
     "sg_act_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "sg_act_bwd_reduce": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "sg_act_bwd_apply": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
+    "sg_stat_grads": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "sg_ncl_to_nlc": [_vp, _i, _i, _i, _vp, _i, _vp],
     "sg_nlc_to_ncl": [_vp, _i, _i, _i, _i, _vp, _vp],
     "sg_colsum": [_vp, _i, _i64, _i, _i, _vp, _i, _vp, _vp],
@@ -75,7 +77,7 @@ _SIGS = {
     "sg_deemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_preemphasis": [_vp, _i64, _f, _vp, _vp],
 }
-EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair"] + list(_SIGS)
+EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair", "sg_set_ew_variant"] + list(_SIGS)
 
 _lib = None
 
@@ -99,6 +101,8 @@ def load():
     lib.sg_device_ok.restype = C.c_int
     lib.sg_set_cta_pair.restype = C.c_int
     lib.sg_set_cta_pair.argtypes = [C.c_int]
+    lib.sg_set_ew_variant.restype = C.c_int
+    lib.sg_set_ew_variant.argtypes = [C.c_int] * 4
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

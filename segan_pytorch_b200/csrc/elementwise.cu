@@ -4,84 +4,86 @@
 // All 16-bit tensors are NLC ([positions][C], C innermost); threads own 8 consecutive channels
 // (one 16-byte vector) so every access is a coalesced 128-bit transaction.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace sg {
 
-__device__ __forceinline__ V8 ldv8(const void* p, int64_t elem_off) {
-  return *reinterpret_cast<const V8*>(reinterpret_cast<const uint16_t*>(p) + elem_off);
-}
-__device__ __forceinline__ void stv8(void* p, int64_t elem_off, const V8& v) {
-  *reinterpret_cast<V8*>(reinterpret_cast<uint16_t*>(p) + elem_off) = v;
-}
-
-// block-level reduction of per-thread 8-channel partials: threads with the same channel group
-// (tid % cgs) are summed, then one double atomic per channel.
-template <int NS>
-__device__ __forceinline__ void block_reduce_channels(float (&part)[NS][8], int cgs, int C, double* out,
-                                                      float* smem /* [256][8] */) {
-  const int tid = threadIdx.x;
-  const int cg = tid % cgs;
-  for (int s = 0; s < NS; ++s) {
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) smem[tid * 8 + j] = part[s][j];
-    __syncthreads();
-    if (tid < cgs) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int t = tid; t < blockDim.x; t += cgs)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += (double)smem[t * 8 + j];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(out + (int64_t)s * C + cg * 8 + j, acc[j]);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
+// Streaming kernels.  Thread = VEC adjacent channels (one 8- or 16-byte load per stream) of a row,
+// C/VEC threads per row, 256/(C/VEC) rows per CTA iteration, UNROLL rows in flight per thread.
+// The per-thread bytes in flight (loads x VEC x 2 B x UNROLL) are what matters on B200: these
+// kernels also run CONCURRENTLY with the persistent tap-GEMMs (engine.py side streams), where only
+// 2-3 of their CTAs fit next to a GEMM CTA on an SM, so memory-level parallelism has to come from
+// the thread, not from occupancy.  The variant (VEC, UNROLL, grid caps) is a runtime tuning knob
+// (sg_set_ew_variant / SEGAN_B200_EW); every variant computes identical values.
 // ------------------------------------------------------------------------------------------
-// Streaming kernels.  Thread = 4 adjacent channels (one 8-byte load per stream) of a row, C/4
-// threads per row, 256/(C/4) rows per CTA iteration, two rows in flight per thread.  Measured
-// trade-off on B200: 2 channels/thread is instruction-bound (index math per element), 8 channels/
-// thread with all per-channel constants in registers drops to 1 CTA/SM; 4 channels keeps ~64
-// registers (4 CTAs/SM) with ~15 instructions per element.
-// ------------------------------------------------------------------------------------------
-constexpr int VEC = 4;
-constexpr int EW_UNROLL = 2;
 // per-channel statistics are accumulated into SG_STAT_SLICES interleaved copies (slice = CTA % 8):
 // ~450 CTAs hitting one fp64 address serialise at ~60 ns each (measured: ~30 us tail per launch);
 // consumers add the slices up.
 constexpr int SL = SG_STAT_SLICES;
 
-struct F4 { float v[4]; };
-__device__ __forceinline__ F4 ld4(const void* p, int64_t elem, int dtype) {
-  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + elem);
-  F4 r;
-  if (dtype == SG_F16) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+template <int VEC> struct FV { float v[VEC]; };
+// packed 16-bit vector as loaded (kept packed while in flight: VEC/2 registers instead of VEC)
+template <int VEC> struct RV { uint32_t w[VEC / 2]; };
+
+template <int VEC>
+__device__ __forceinline__ RV<VEC> ldr(const void* p, int64_t elem) {
+  RV<VEC> r;
+  const uint16_t* q = reinterpret_cast<const uint16_t*>(p) + elem;
+  if constexpr (VEC == 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(q);
+    r.w[0] = u.x; r.w[1] = u.y; r.w[2] = u.z; r.w[3] = u.w;
   } else {
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+    const uint2 u = *reinterpret_cast<const uint2*>(q);
+    r.w[0] = u.x; r.w[1] = u.y;
   }
   return r;
 }
-__device__ __forceinline__ void st4(void* p, int64_t elem, const float (&x)[4], int dtype) {
-  uint2 u;
-  if (dtype == SG_F16) {
-    __half2 a = __floats2half2_rn(x[0], x[1]), b = __floats2half2_rn(x[2], x[3]);
-    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-  } else {
-    __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
-    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+template <int VEC>
+__device__ __forceinline__ RV<VEC> zero_rv() {
+  RV<VEC> r;
+#pragma unroll
+  for (int i = 0; i < VEC / 2; ++i) r.w[i] = 0u;
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ FV<VEC> up(const RV<VEC>& x, int dtype) {
+  FV<VEC> r;
+#pragma unroll
+  for (int i = 0; i < VEC / 2; ++i) {
+    float2 f;
+    if (dtype == SG_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&x.w[i]));
+    else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&x.w[i]));
+    r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
   }
-  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p) + elem) = u;
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ FV<VEC> ldv(const void* p, int64_t elem, int dtype) {
+  return up<VEC>(ldr<VEC>(p, elem), dtype);
+}
+template <int VEC>
+__device__ __forceinline__ void stv(void* p, int64_t elem, const float (&x)[VEC], int dtype) {
+  uint32_t w[VEC / 2];
+#pragma unroll
+  for (int i = 0; i < VEC / 2; ++i) {
+    if (dtype == SG_F16) {
+      __half2 a = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&a);
+    } else {
+      __nv_bfloat162 a = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&a);
+    }
+  }
+  uint16_t* q = reinterpret_cast<uint16_t*>(p) + elem;
+  if constexpr (VEC == 8) *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+  else *reinterpret_cast<uint2*>(q) = make_uint2(w[0], w[1]);
 }
 
-// per-thread partial sums of NS statistics for 4 channels -> smem combine over the CTA's threads
+// per-thread partial sums of NS statistics for VEC channels -> smem combine over the CTA's threads
 // that own the same channels -> one double atomic per channel and CTA
-template <int NS>
+template <int NS, int VEC>
 __device__ __forceinline__ void block_stats_flush(float (&part)[NS][VEC], int cgs, int C, double* out,
                                                   float* smem /* [256][VEC] */) {
   const int tid = threadIdx.x;
@@ -105,7 +107,8 @@ __device__ __forceinline__ void block_stats_flush(float (&part)[NS][VEC], int cg
   }
 }
 
-__global__ void __launch_bounds__(256)
+template <int VEC, int UNROLL>
+__global__ void __launch_bounds__(256, (VEC == 4 && UNROLL <= 4) ? 3 : 2)
 bn_stats_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, double* __restrict__ stats) {
   __shared__ float red[256 * VEC];
   const int cgs = C / VEC;
@@ -114,26 +117,28 @@ bn_stats_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, do
   const int rpb = 256 / cgs;
   const int rows = (int)rows64;
   const int stride = gridDim.x * rpb;
+  constexpr int U = 2 * UNROLL;            // a single input stream: twice the rows in flight
   float part[2][VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { part[0][j] = 0.f; part[1][j] = 0.f; }
-  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += 4 * stride) {
-    F4 v[4];
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += U * stride) {
+    RV<VEC> raw[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = r0 + u * stride;
-      if (r < rows) v[u] = ld4(a, (int64_t)r * C + cg * VEC, dtype);
-      else { v[u].v[0] = v[u].v[1] = v[u].v[2] = v[u].v[3] = 0.f; }
+      raw[u] = (r < rows) ? ldr<VEC>(a, (int64_t)r * C + cg * VEC) : zero_rv<VEC>();
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u) {
+      const FV<VEC> v = up<VEC>(raw[u], dtype);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        part[0][j] += v[u].v[j];
-        part[1][j] = fmaf(v[u].v[j], v[u].v[j], part[1][j]);
+        part[0][j] += v.v[j];
+        part[1][j] = fmaf(v.v[j], v.v[j], part[1][j]);
       }
+    }
   }
-  block_stats_flush<2>(part, cgs, C, stats, red);
+  block_stats_flush<2, VEC>(part, cgs, C, stats, red);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C,
@@ -164,10 +169,12 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 // h[b][q + H][c] = act(a[b][src(q)][c] * scale + shift),  q in [-H, L + H),
 // src(q) = unroll(reflect(q))
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int VEC, int UNROLL>
+__global__ void __launch_bounds__(256, (VEC == 4 && UNROLL <= 4) ? 3 : 2)
 act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ slope, int act, int roll, int H,
                void* __restrict__ h, void* __restrict__ h_bf16, void* __restrict__ a_bf16) {
+  constexpr int U = 2 * UNROLL;            // a single input stream: twice the rows in flight
   const int cgs = C / VEC;
   const int Lh = L + 2 * H;
   const int tid = threadIdx.x;
@@ -183,79 +190,78 @@ act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
     sh[j] = scale_shift ? scale_shift[C + c] : 0.f;
     sl[j] = (act == SG_ACT_PRELU) ? slope[c] : 1.f;
   }
-  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
-    F4 v[EW_UNROLL];
-    int srcs[EW_UNROLL], qhs[EW_UNROLL];
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += U * stride) {
+    RV<VEC> raw[U];
+    int srcs[U];                 // source row, or -1 - source row for halo rows (no a_bf16 copy)
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = r0 + u * stride;
-      srcs[u] = 0; qhs[u] = 0;
+      srcs[u] = 0;
+      raw[u] = zero_rv<VEC>();
       if (r < rows) {
         const int b = r / Lh;
-        qhs[u] = r - b * Lh;
-        srcs[u] = b * L + unroll_idx(reflect_idx(qhs[u] - H, L), roll, L);
-        v[u] = ld4(a, (int64_t)srcs[u] * C + cg * VEC, dtype);
+        const int qh = r - b * Lh;
+        const int src = b * L + unroll_idx(reflect_idx(qh - H, L), roll, L);
+        srcs[u] = (qh >= H && qh < H + L) ? src : -1 - src;
+        raw[u] = ldr<VEC>(a, (int64_t)src * C + cg * VEC);
       }
     }
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = r0 + u * stride;
       if (r < rows) {
+        const FV<VEC> v = up<VEC>(raw[u], dtype);
         float y[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          y[j] = fmaf(v[u].v[j], sc[j], sh[j]);
+          y[j] = fmaf(v.v[j], sc[j], sh[j]);
           if (act == SG_ACT_PRELU) y[j] = y[j] > 0.f ? y[j] : sl[j] * y[j];
         }
-        st4(h, (int64_t)r * C + cg * VEC, y, dtype);
+        stv<VEC>(h, (int64_t)r * C + cg * VEC, y, dtype);
         // bf16 twins: operands of the weight-gradient tap-GEMM (tcgen05 kind::f16 cannot mix f16 x bf16)
-        if (h_bf16) st4(h_bf16, (int64_t)r * C + cg * VEC, y, SG_BF16);
-        if (a_bf16 && qhs[u] >= H && qhs[u] < H + L) st4(a_bf16, (int64_t)srcs[u] * C + cg * VEC, v[u].v, SG_BF16);
+        if (h_bf16) stv<VEC>(h_bf16, (int64_t)r * C + cg * VEC, y, SG_BF16);
+        if (a_bf16 && srcs[u] >= 0) stv<VEC>(a_bf16, (int64_t)srcs[u] * C + cg * VEC, v.v, SG_BF16);
       }
     }
   }
 }
 
 // gradient w.r.t. the activation output at exact position l: the consumer-view gradient at the
-// rolled position plus its reflect-halo mirrors
-__device__ __forceinline__ F4 gather_gy(const void* g_h, int ldh, int H, int roll, int b, int l, int L, int c) {
-  F4 g;
-  g.v[0] = g.v[1] = g.v[2] = g.v[3] = 0.f;
-  if (g_h) {
-    const int Lh = L + 2 * H;
-    int q0 = l + roll;
-    if (q0 >= L) q0 -= L;
-    if (q0 < 0) q0 += L;
-    const int64_t base = (int64_t)b * Lh + H;
-    g = ld4(g_h, (base + q0) * ldh + c, SG_BF16);
-    if (H > 0) {
-      if (q0 >= 1 && q0 <= H) {
-        const F4 m = ld4(g_h, (base - q0) * ldh + c, SG_BF16);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) g.v[j] += m.v[j];
-      }
-      if (q0 >= L - 1 - H && q0 <= L - 2) {
-        const F4 m = ld4(g_h, (base + 2 * (L - 1) - q0) * ldh + c, SG_BF16);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) g.v[j] += m.v[j];
-      }
+// rolled position plus its reflect-halo mirror (at most one of the two mirrors applies: the host
+// checks L >= 2H + 3).  Returns the two packed vectors; `has_m` says whether the mirror is live.
+template <int VEC>
+__device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int roll, int b, int l, int L, int c,
+                                          RV<VEC>& g, RV<VEC>& m, bool& has_m) {
+  const int Lh = L + 2 * H;
+  int q0 = l + roll;
+  if (q0 >= L) q0 -= L;
+  if (q0 < 0) q0 += L;
+  const int64_t base = (int64_t)b * Lh + H;
+  g = ldr<VEC>(g_h, (base + q0) * ldh + c);
+  has_m = false;
+  if (H > 0) {
+    int64_t mrow = -1;
+    if (q0 >= 1 && q0 <= H) mrow = base - q0;
+    else if (q0 >= L - 1 - H && q0 <= L - 2) mrow = base + 2 * (L - 1) - q0;
+    if (mrow >= 0) {
+      m = ldr<VEC>(g_h, mrow * ldh + c);
+      has_m = true;
     }
   }
-  return g;
 }
 
 // MODE 0: reductions (and, when g_a_out != null, g_pre written in the same pass: final without BN)
 // MODE 1: apply (BN backward) using the reductions
 // The skip-connection gradient g_add is w.r.t. the PRE-activation (generator.py:185,191) and joins
 // after the activation derivative.
-template <int MODE>
-__global__ void __launch_bounds__(256)
+template <int MODE, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256, (VEC == 4 && UNROLL <= 4) ? 3 : 2)
 act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const void* __restrict__ g_add, int lda,
                const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ mean_invstd,
                const float* __restrict__ slope, int act, double* __restrict__ red, int use_bn,
                void* __restrict__ g_a_out) {
-  __shared__ float sred[256 * VEC];
+  __shared__ float sred[MODE == 0 ? 256 * VEC : 1];
   const int cgs = C / VEC;
   const int tid = threadIdx.x;
   const int cg = tid % cgs;
@@ -278,9 +284,16 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
       p0[j] = is;
       p1[j] = mu * is;
     } else {
-      // MODE 1 receives the slice-SUMMED statistics [3][C] (the caller adds the slices of pass 1)
-      const float r1 = (float)(red[C + c] / (double)rows);
-      const float r2 = (float)(red[2 * C + c] / (double)rows);
+      // MODE 1 reads the SG_STAT_SLICES partial copies [SL][3][C] written by pass 1 and adds them up
+      double d1 = 0, d2 = 0;
+      if (use_bn) {
+        for (int i = 0; i < SL; ++i) {
+          d1 += red[((int64_t)i * 3 + 1) * C + c];
+          d2 += red[((int64_t)i * 3 + 2) * C + c];
+        }
+      }
+      const float r1 = (float)(d1 / (double)rows);
+      const float r2 = (float)(d2 / (double)rows);
       p0[j] = use_bn ? -sc[j] * r2 * is : 0.f;                       // ka
       p1[j] = use_bn ? sc[j] * (r2 * is * mu - r1) : 0.f;           // kb
     }
@@ -290,36 +303,45 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
   for (int s = 0; s < 3; ++s)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) part[s][j] = 0.f;
-  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += EW_UNROLL * stride) {
-    F4 gy[EW_UNROLL], gs[EW_UNROLL], av[EW_UNROLL];
+  for (int r0 = blockIdx.x * rpb + tid / cgs; r0 < rows; r0 += UNROLL * stride) {
+    RV<VEC> gy[UNROLL], gm[UNROLL], gs[UNROLL], av[UNROLL];
+    bool hm[UNROLL];
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       const int r = r0 + u * stride;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) gs[u].v[j] = 0.f;
+      gy[u] = zero_rv<VEC>(); gm[u] = zero_rv<VEC>(); gs[u] = zero_rv<VEC>(); av[u] = zero_rv<VEC>();
+      hm[u] = false;
       if (r < rows) {
         const int b = r / L, l = r - b * L;
-        gy[u] = gather_gy(g_h, ldh, H, roll, b, l, L, c0);
-        if (g_add) gs[u] = ld4(g_add, (int64_t)r * lda + c0, SG_BF16);
-        av[u] = ld4(a, (int64_t)r * C + c0, dtype);
+        if (g_h) gather_gy<VEC>(g_h, ldh, H, roll, b, l, L, c0, gy[u], gm[u], hm[u]);
+        if (g_add) gs[u] = ldr<VEC>(g_add, (int64_t)r * lda + c0);
+        av[u] = ldr<VEC>(a, (int64_t)r * C + c0);
       }
     }
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       const int r = r0 + u * stride;
       if (r < rows) {
+        const FV<VEC> xa = up<VEC>(av[u], dtype);
+        FV<VEC> gf = up<VEC>(gy[u], SG_BF16);
+        if (hm[u]) {
+          const FV<VEC> mf = up<VEC>(gm[u], SG_BF16);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) gf.v[j] += mf.v[j];
+        }
+        const FV<VEC> sf = up<VEC>(gs[u], SG_BF16);     // zero bits -> 0.f when there is no skip gradient
         float out[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          const float x = av[u].v[j];
+          const float x = xa.v[j];
           const float y = fmaf(x, sc[j], sh[j]);
-          const float g = gy[u].v[j];
+          const float g = gf.v[j];
           float gpre = g;
           if (act == SG_ACT_PRELU && y <= 0.f) {
             if (MODE == 0) part[0][j] = fmaf(g, y, part[0][j]);
             gpre = g * sl[j];
           }
-          gpre += gs[u].v[j];
+          gpre += sf.v[j];
           if (MODE == 0) {
             part[1][j] += gpre;
             part[2][j] = fmaf(gpre, fmaf(x, p0[j], -p1[j]), part[2][j]);
@@ -328,11 +350,234 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const voi
             out[j] = use_bn ? fmaf(sc[j], gpre, fmaf(p0[j], x, p1[j])) : gpre;
           }
         }
-        if (g_a_out) st4(g_a_out, (int64_t)r * C + c0, out, SG_BF16);
+        if (g_a_out) stv<VEC>(g_a_out, (int64_t)r * C + c0, out, SG_BF16);
       }
     }
   }
-  if (MODE == 0) block_stats_flush<3>(part, cgs, C, red, sred);
+  if (MODE == 0) block_stats_flush<3, VEC>(part, cgs, C, red, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tiled activation backward (the default for sg_act_bwd_reduce / sg_act_bwd_apply).
+// The generic kernel above spends ~50 instructions per element on index arithmetic (a division
+// per row, 64-bit address chains, 4 channels per thread) and holds all per-channel constants in
+// registers; measured 1.5-2.3 TB/s.  Here:
+//   * a CTA walks a CONTIGUOUS range of tiles, a tile = U x RPB rows of ONE batch element, so
+//     (batch, row) advance incrementally and row offsets are 32-bit relative to per-tile bases;
+//   * threads own 8 channels (16-byte loads / stores), C/8 threads per row;
+//   * per-channel constants live in shared memory (6 x LDS.128 per row instead of 40 registers),
+//     which keeps the kernel at <= 128 registers so that two CTAs fit next to a tap-GEMM CTA;
+//   * sum(g_pre * ahat) is accumulated as sum(g_pre * x) and centred in double at the flush.
+// ------------------------------------------------------------------------------------------
+struct RV8 { uint32_t w[4]; };
+__device__ __forceinline__ RV8 ld8(const uint16_t* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  RV8 r; r.w[0] = u.x; r.w[1] = u.y; r.w[2] = u.z; r.w[3] = u.w;
+  return r;
+}
+__device__ __forceinline__ void up8(const RV8& x, bool f16, float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f;
+    if (f16) f = __half22float2(*reinterpret_cast<const __half2*>(&x.w[i]));
+    else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&x.w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void ld_f8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <int MODE, int U>
+__global__ void __launch_bounds__(256, 2)
+act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll,
+                     const uint16_t* __restrict__ g_add, int lda, const uint16_t* __restrict__ a, int a_f16,
+                     int batch, int L, int C, int cgs_log2, const float* __restrict__ scale_shift,
+                     const float* __restrict__ mean_invstd, const float* __restrict__ slope, int act,
+                     const double* __restrict__ red_in, double* __restrict__ red_out, int use_bn,
+                     uint16_t* __restrict__ g_a_out, int tiles_per_b, int tiles_per_cta) {
+  extern __shared__ __align__(16) float smf[];
+  float* s_sc = smf;                 // y = x*sc + sh (sign test, slope gradient)
+  float* s_sh = smf + C;
+  float* s_sl = smf + 2 * C;         // PReLU slope (1 when act == NONE)
+  float* s_so = smf + 3 * C;         // MODE 1: out = so*gpre + ka*x + kb
+  float* s_ka = smf + 4 * C;
+  float* s_kb = smf + 5 * C;
+  const int tid = threadIdx.x;
+  const int rows_total = batch * L;
+  for (int c = tid; c < C; c += 256) {
+    const float sc = scale_shift ? scale_shift[c] : 1.f;
+    s_sc[c] = sc;
+    s_sh[c] = scale_shift ? scale_shift[C + c] : 0.f;
+    s_sl[c] = (act == SG_ACT_PRELU) ? slope[c] : 1.f;
+    if (MODE == 1) {
+      float so = 1.f, ka = 0.f, kb = 0.f;
+      if (use_bn) {
+        double d1 = 0, d2 = 0;
+        for (int i = 0; i < SL; ++i) {
+          d1 += red_in[((int64_t)i * 3 + 1) * C + c];
+          d2 += red_in[((int64_t)i * 3 + 2) * C + c];
+        }
+        const float r1 = (float)(d1 / (double)rows_total);
+        const float r2 = (float)(d2 / (double)rows_total);
+        const float mu = mean_invstd[c], is = mean_invstd[C + c];
+        so = sc;
+        ka = -sc * r2 * is;
+        kb = sc * (r2 * is * mu - r1);
+      }
+      s_so[c] = so; s_ka[c] = ka; s_kb[c] = kb;
+    }
+  }
+  __syncthreads();
+
+  const int cgs = 1 << cgs_log2;
+  const int cg = tid & (cgs - 1);
+  const int rr = tid >> cgs_log2;
+  const int c0 = cg * 8;
+  const int RPB = 256 >> cgs_log2;
+  const int TILE = RPB * U;
+  const int Lh = L + 2 * H;
+  const bool f16 = a_f16 != 0;
+  const bool prelu = act == SG_ACT_PRELU;
+
+  float part[3][8];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[s][j] = 0.f;
+
+  int t = blockIdx.x * tiles_per_cta;
+  const int t_end = min(t + tiles_per_cta, batch * tiles_per_b);
+  int b = t / tiles_per_b;
+  int lt = t - b * tiles_per_b;
+  for (; t < t_end; ++t) {
+    // 32-bit element offsets from the tensor bases (the host checks every tensor has < 2^31 elements)
+    const int rb_a = b * L;                 // first row of this batch element in a / g_add / g_a
+    const int rb_g = b * Lh + H;            // row of position 0 in the consumer-view gradient
+    const int l0 = lt * TILE + rr;
+    RV8 gy[U], gm[U], gs[U], av[U];
+    unsigned hm = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int l = l0 + u * RPB;
+      if (l < L) {
+        int q0 = l + roll;
+        q0 -= (q0 >= L) ? L : 0;
+        q0 += (q0 < 0) ? L : 0;
+        gy[u] = ld8(g_h + ((rb_g + q0) * ldh + c0));
+        if (H > 0) {
+          // reflect-halo mirror of position q0 (at most one applies: L >= 2H + 3)
+          int m = 0;
+          bool has = false;
+          if ((unsigned)(q0 - 1) < (unsigned)H) { m = -q0; has = true; }
+          else if ((unsigned)(L - 2 - q0) < (unsigned)H) { m = 2 * (L - 1) - q0; has = true; }
+          if (has) { gm[u] = ld8(g_h + ((rb_g + m) * ldh + c0)); hm |= 1u << u; }
+        }
+        if (g_add) gs[u] = ld8(g_add + ((rb_a + l) * lda + c0));
+        av[u] = ld8(a + ((rb_a + l) * C + c0));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int l = l0 + u * RPB;
+      if (l < L) {
+        float x[8], g[8], sc[8], sh[8], sl[8], out[8];
+        up8(av[u], f16, x);
+        up8(gy[u], false, g);
+        if (hm & (1u << u)) {
+          float m[8];
+          up8(gm[u], false, m);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += m[j];
+        }
+        ld_f8(s_sc + c0, sc); ld_f8(s_sh + c0, sh); ld_f8(s_sl + c0, sl);
+        float gpre[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf(x[j], sc[j], sh[j]);
+          const bool neg = prelu && y <= 0.f;
+          if (MODE == 0 && neg) part[0][j] = fmaf(g[j], y, part[0][j]);
+          gpre[j] = neg ? g[j] * sl[j] : g[j];
+        }
+        if (g_add) {
+          float sk[8];
+          up8(gs[u], false, sk);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gpre[j] += sk[j];
+        }
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            part[1][j] += gpre[j];
+            part[2][j] = fmaf(gpre[j], x[j], part[2][j]);
+            out[j] = gpre[j];
+          }
+        } else {
+          float so[8], ka[8], kb[8];
+          ld_f8(s_so + c0, so); ld_f8(s_ka + c0, ka); ld_f8(s_kb + c0, kb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) out[j] = fmaf(so[j], gpre[j], fmaf(ka[j], x[j], kb[j]));
+        }
+        if (g_a_out) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(out[2 * i], out[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          *reinterpret_cast<uint4*>(g_a_out + ((rb_a + l) * C + c0)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    if (++lt == tiles_per_b) { lt = 0; ++b; }
+  }
+
+  if (MODE == 0) {
+    // block combine (threads with the same channel group), centre sum(g_pre*x) in double, one atomic
+    // per channel, statistic and CTA into slice (CTA % SL)
+    __syncthreads();                  // the constants in smf are dead from here on
+    double tot[3][8];
+    for (int s = 0; s < 3; ++s) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) smf[tid * 8 + j] = part[s][j];
+      __syncthreads();
+      if (tid < cgs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tot[s][j] = 0;
+        for (int q = tid; q < 256; q += cgs)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tot[s][j] += (double)smf[q * 8 + j];
+      }
+    }
+    if (tid < cgs) {
+      double* o = red_out + (int64_t)(blockIdx.x % SL) * 3 * C + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double mu = mean_invstd ? (double)mean_invstd[c0 + j] : 0.0;
+        const double is = mean_invstd ? (double)mean_invstd[C + c0 + j] : 1.0;
+        atomicAdd(o + j, tot[0][j]);
+        atomicAdd(o + C + j, tot[1][j]);
+        atomicAdd(o + 2 * C + j, is * (tot[2][j] - mu * tot[1][j]));      // sum g_pre * ahat
+      }
+    }
+  }
+}
+
+// g_s[c] += sum over slices of red[slice][s][c]  (PReLU slope / bias|beta / gamma gradients)
+__global__ void stat_grads_kernel(const double* __restrict__ red, int C, int n_stats, float* __restrict__ g0,
+                                  float* __restrict__ g1, float* __restrict__ g2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float* outs[3] = {g0, g1, g2};
+  for (int s = 0; s < n_stats && s < 3; ++s) {
+    if (!outs[s]) continue;
+    double acc = 0;
+    for (int i = 0; i < SL; ++i) acc += red[((int64_t)i * n_stats + s) * C + c];
+    outs[s][c] += (float)acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -371,6 +616,7 @@ __global__ void nlc_to_ncl_kernel(const void* __restrict__ src, int dtype, int C
 
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, double* __restrict__ tmp) {
+  constexpr int VEC = 4;
   __shared__ float red[256 * VEC];
   const int cgs = C / VEC;
   const int tid = threadIdx.x;
@@ -380,11 +626,11 @@ colsum_kernel(const void* __restrict__ a, int dtype, int64_t rows64, int C, doub
   const int stride = gridDim.x * rpb;
   float part[1][VEC] = {{0.f, 0.f, 0.f, 0.f}};
   for (int r = blockIdx.x * rpb + tid / cgs; r < rows; r += stride) {
-    const F4 v = ld4(a, (int64_t)r * C + cg * VEC, dtype);
+    const FV<VEC> v = ldv<VEC>(a, (int64_t)r * C + cg * VEC, dtype);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) part[0][j] += v.v[j];
   }
-  block_stats_flush<1>(part, cgs, C, tmp, red);
+  block_stats_flush<1, VEC>(part, cgs, C, tmp, red);
 }
 __global__ void colsum_fold_kernel(const double* __restrict__ tmp, int C, int mod, float* __restrict__ out,
                                    int accumulate) {
@@ -555,22 +801,87 @@ __global__ void l1_loss_bwd_kernel(const float* __restrict__ y, const float* __r
   if ((threadIdx.x & 31) == 0 && loss_out) atomicAdd(loss_out, s * gscale);
 }
 
-static inline int ew_grid(int64_t work_items, int per_block, int cap_per_sm = 16) {
-  int64_t g = cdiv(work_items, per_block);
-  const int64_t cap = (int64_t)cap_per_sm * NUM_SMS;
-  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+// ---- streaming-kernel variants (runtime tuning knobs, one per kernel family) -----------------
+// vec: channels per thread (4 | 8); unroll: rows in flight per thread and input stream (2 | 4 | 8,
+// vec*unroll <= 32); cap: CTAs per SM (the grid is persistent beyond that).  For the two activation-
+// backward kernels vec == 8 selects the tiled kernel (unroll 2 | 4), vec == 4 the generic one.
+// Kernels that end in a per-block reduction (smem + one double atomic per channel and block) keep
+// the grid small so the same-address atomics stay in the hundreds, not thousands.
+// Defaults = the best of tools/ew_sweep.py on B200 (profiles/r1_v4_ew_sweep.txt).
+struct EwVariant { int vec, unroll, cap; };
+enum { EW_ACT_FWD = 1, EW_BN_STATS = 2, EW_BWD_REDUCE = 3, EW_BWD_APPLY = 4, EW_KINDS = 5 };
+static EwVariant g_ew[EW_KINDS] = {{0, 0, 0}, {8, 4, 2}, {4, 4, 3}, {8, 2, 2}, {8, 2, 4}};
+static bool g_ew_env_read = false;
+static bool ew_valid(int kind, int vec, int unroll, int cap) {
+  if (kind < 1 || kind >= EW_KINDS) return false;
+  if (!((vec == 4 || vec == 8) && (unroll == 2 || unroll == 4 || unroll == 8) && vec * unroll <= 32)) return false;
+  if ((kind == EW_BWD_REDUCE || kind == EW_BWD_APPLY) && vec == 8 && unroll > 4) return false;
+  return cap >= 1 && cap <= 32;
 }
-// kernels that end in a per-block reduction (smem + one double atomic per channel and block):
-// keep the grid at 2 CTAs/SM so the same-address atomics stay in the hundreds, not thousands
-constexpr int RED_CAP = 3;
-// grid for the warp-per-64-channel-chunk streaming kernels: multiple of 4 so that warps/chunks is integral
-static inline int stream_grid(int64_t rows, int C, int cap_per_sm) {
-  const int rpb = 256 / (C / VEC);
-  int64_t g = cdiv(rows, (int64_t)rpb * EW_UNROLL);
+static const EwVariant& ew(int kind) {
+  if (!g_ew_env_read) {
+    g_ew_env_read = true;
+    // SEGAN_B200_EW="kind,vec,unroll,cap[;kind,vec,unroll,cap...]"
+    const char* e = getenv("SEGAN_B200_EW");
+    while (e && *e) {
+      int k, v, u, c;
+      if (sscanf(e, "%d,%d,%d,%d", &k, &v, &u, &c) == 4 && ew_valid(k, v, u, c)) g_ew[k] = {v, u, c};
+      e = strchr(e, ';');
+      if (e) ++e;
+    }
+  }
+  return g_ew[kind];
+}
+// grid: enough CTAs to cover the rows once, capped at cap_per_sm CTAs per SM (persistent beyond that)
+static inline int stream_grid(int64_t rows, int C, int vec, int rows_in_flight, int cap_per_sm) {
+  const int rpb = 256 / (C / vec);
+  int64_t g = cdiv(rows, (int64_t)rpb * rows_in_flight);
   const int64_t cap = (int64_t)cap_per_sm * NUM_SMS;
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
+// C / vec threads share a row and 256 must be a multiple of that
+static inline bool ew_shape_ok(int C) { return C >= 64 && C <= 1024 && (C & (C - 1)) == 0; }
+
+template <int MODE>
+static int launch_act_bwd_tiled(const void* g_h, int ldh, int H, int roll, const void* g_add, int lda, const void* a,
+                                int dtype, int batch, int L, int C, const float* scale_shift,
+                                const float* mean_invstd, const float* slope, int act, const double* red_in,
+                                double* red_out, int use_bn, void* g_a_out, int unroll, int cap_per_sm, cudaStream_t st) {
+  // 32-bit element offsets inside the kernel
+  SG_CHECK_ARG((int64_t)batch * (L + 2 * H) * (ldh > lda ? ldh : lda) < (1ll << 31) && (int64_t)batch * L * C < (1ll << 31));
+  int cgs_log2 = 0;
+  while ((8 << cgs_log2) < C) ++cgs_log2;               // C / 8 threads per row (C is a power of two >= 64)
+  const int RPB = 256 >> cgs_log2;
+  const int U = unroll >= 4 ? 4 : 2;
+  const int TILE = RPB * U;
+  const int tiles_per_b = (L + TILE - 1) / TILE;
+  const int64_t total = (int64_t)batch * tiles_per_b;
+  int64_t grid = (int64_t)cap_per_sm * NUM_SMS;
+  if (grid > total) grid = total;
+  const int tiles_per_cta = (int)((total + grid - 1) / grid);
+  grid = (total + tiles_per_cta - 1) / tiles_per_cta;
+  const size_t smem_const = (size_t)(MODE == 1 ? 6 : 3) * C * sizeof(float);
+  const size_t smem_red = MODE == 0 ? 256 * 8 * sizeof(float) : 0;
+  const size_t smem = smem_const > smem_red ? smem_const : smem_red;
+#define SG_LAUNCH_TILED(UU)                                                                                   \
+  act_bwd_tiled_kernel<MODE, UU><<<(int)grid, 256, smem, st>>>(                                                \
+      (const uint16_t*)g_h, ldh, H, roll, (const uint16_t*)g_add, lda, (const uint16_t*)a, dtype == SG_F16,   \
+      batch, L, C, cgs_log2, scale_shift, mean_invstd, slope, act, red_in, red_out, use_bn, (uint16_t*)g_a_out, \
+      tiles_per_b, tiles_per_cta)
+  if (U == 4) SG_LAUNCH_TILED(4); else SG_LAUNCH_TILED(2);
+#undef SG_LAUNCH_TILED
+  return SG_OK;
+}
+
+#define EW_DISPATCH(V, U, CALL)                                   \
+  do {                                                            \
+    if (V == 8 && U == 4) { constexpr int VEC = 8, UNR = 4; CALL; } \
+    else if (V == 8 && U == 2) { constexpr int VEC = 8, UNR = 2; CALL; } \
+    else if (V == 4 && U == 8) { constexpr int VEC = 4, UNR = 8; CALL; } \
+    else if (V == 4 && U == 4) { constexpr int VEC = 4, UNR = 4; CALL; } \
+    else { constexpr int VEC = 4, UNR = 2; CALL; }                \
+  } while (0)
 
 }  // namespace sg
 
@@ -578,9 +889,21 @@ using namespace sg;
 
 #define ST ((cudaStream_t)stream)
 
+extern "C" int sg_set_ew_variant(int kind, int vec, int unroll, int cap) {
+  if (!ew_valid(kind, vec, unroll, cap)) {
+    set_error("sg_set_ew_variant(%d,%d,%d,%d): unsupported variant", kind, vec, unroll, cap);
+    return SG_ERR_INVALID;
+  }
+  ew(kind);                      // make sure the environment was read first (explicit calls win)
+  g_ew[kind] = {vec, unroll, cap};
+  return SG_OK;
+}
+
 extern "C" int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && a && stats && rows_total < (1ll << 31));
-  bn_stats_kernel<<<stream_grid(rows_total, C, RED_CAP), 256, 0, ST>>>(a, dtype, rows_total, C, stats);
+  SG_CHECK_ARG(ew_shape_ok(C) && a && stats && rows_total < (1ll << 31));
+  const EwVariant v = ew(EW_BN_STATS);
+  EW_DISPATCH(v.vec, v.unroll, (bn_stats_kernel<VEC, UNR><<<stream_grid(rows_total, C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(
+      a, dtype, rows_total, C, stats)));
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -597,10 +920,11 @@ extern "C" int sg_bn_finalize(const double* stats, int64_t count, int C, const f
 extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
                           const float* slope, int act, int roll, int out_halo_pos, void* h, void* h_bf16,
                           void* a_bf16, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && (out_halo_pos == 0 || L >= 32));
+  SG_CHECK_ARG(ew_shape_ok(C) && (out_halo_pos == 0 || L >= 32));
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
-  act_fwd_kernel<<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, 16), 256, 0, ST>>>(a, dtype, batch, L, C, scale_shift, slope, act, roll,
-                                                          out_halo_pos, h, h_bf16, a_bf16);
+  const EwVariant v = ew(EW_ACT_FWD);
+  EW_DISPATCH(v.vec, v.unroll, (act_fwd_kernel<VEC, UNR><<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(
+      a, dtype, batch, L, C, scale_shift, slope, act, roll, out_halo_pos, h, h_bf16, a_bf16)));
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -610,10 +934,20 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
                                  int dtype, int batch, int L, int C, const float* scale_shift,
                                  const float* mean_invstd, const float* slope, int act, double* red,
                                  void* g_a_out, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && red);
-  act_bwd_kernel<0><<<stream_grid((int64_t)batch * L, C, RED_CAP), 256, 0, ST>>>(
-      g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
-      scale_shift, mean_invstd, slope, act, red, 0, g_a_out);
+  SG_CHECK_ARG(ew_shape_ok(C) && red && a && (in_halo_pos == 0 || L >= 2 * in_halo_pos + 3));
+  SG_CHECK_ARG(dtype == SG_F16 || dtype == SG_BF16);
+  const EwVariant v = ew(EW_BWD_REDUCE);
+  const int ldh = g_h_ld > 0 ? g_h_ld : C, lda = g_add_ld > 0 ? g_add_ld : C;
+  if (v.vec == 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
+    int rc = launch_act_bwd_tiled<0>(g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C, scale_shift,
+                                     mean_invstd, slope, act, nullptr, red, 0, g_a_out, v.unroll, v.cap, ST);
+    if (rc) return rc;
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
+  EW_DISPATCH(4, v.unroll, (act_bwd_kernel<0, VEC, UNR><<<stream_grid((int64_t)batch * L, C, VEC, UNR, v.cap), 256, 0, ST>>>(
+      g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C,
+      scale_shift, mean_invstd, slope, act, red, 0, g_a_out)));
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -623,10 +957,28 @@ extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, in
                                 int dtype, int batch, int L, int C, const float* scale_shift,
                                 const float* mean_invstd, const float* slope, int act, const double* red,
                                 int use_bn, void* g_a, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && red && g_a);
-  act_bwd_kernel<1><<<stream_grid((int64_t)batch * L, C, 16), 256, 0, ST>>>(
-      g_h, g_h_ld > 0 ? g_h_ld : C, in_halo_pos, roll, g_add, g_add_ld > 0 ? g_add_ld : C, a, dtype, batch, L, C,
-      scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a);
+  SG_CHECK_ARG(ew_shape_ok(C) && red && g_a && a && (in_halo_pos == 0 || L >= 2 * in_halo_pos + 3));
+  SG_CHECK_ARG(dtype == SG_F16 || dtype == SG_BF16);
+  SG_CHECK_ARG(!use_bn || (scale_shift && mean_invstd));
+  const EwVariant v = ew(EW_BWD_APPLY);
+  const int ldh = g_h_ld > 0 ? g_h_ld : C, lda = g_add_ld > 0 ? g_add_ld : C;
+  if (v.vec == 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
+    int rc = launch_act_bwd_tiled<1>(g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C, scale_shift,
+                                     mean_invstd, slope, act, red, nullptr, use_bn, g_a, v.unroll, v.cap, ST);
+    if (rc) return rc;
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
+  EW_DISPATCH(4, v.unroll, (act_bwd_kernel<1, VEC, UNR><<<stream_grid((int64_t)batch * L, C, VEC, UNR, v.cap), 256, 0, ST>>>(
+      g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C,
+      scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a)));
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_stat_grads(const double* red, int C, int n_stats, float* g0, float* g1, float* g2, void* stream) {
+  SG_CHECK_ARG(red && C > 0 && n_stats >= 1 && n_stats <= 3);
+  stat_grads_kernel<<<(C + 127) / 128, 128, 0, ST>>>(red, C, n_stats, g0, g1, g2);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -646,9 +998,9 @@ extern "C" int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L
 
 extern "C" int sg_colsum(const void* a, int dtype, int64_t rows, int C, int mod, float* out, int accumulate,
                          double* tmp, void* stream) {
-  SG_CHECK_ARG(C % 64 == 0 && C <= 1024 && tmp && C % mod == 0);
+  SG_CHECK_ARG(ew_shape_ok(C) && tmp && C % mod == 0);
   SG_CHECK_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * C * SL, ST));
-  colsum_kernel<<<stream_grid(rows, C, RED_CAP), 256, 0, ST>>>(a, dtype, rows, C, tmp);
+  colsum_kernel<<<stream_grid(rows, C, 4, 1, 3), 256, 0, ST>>>(a, dtype, rows, C, tmp);
   SG_CHECK_LAUNCH();
   colsum_fold_kernel<<<(mod + 127) / 128, 128, 0, ST>>>(tmp, C, mod, out, accumulate);
   SG_CHECK_LAUNCH();

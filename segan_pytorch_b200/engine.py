@@ -66,6 +66,59 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# --------------------------------------------------------------------------------------------
+# side streams: the HBM-bound glue kernels run concurrently with the tensor-bound tap-GEMMs
+# --------------------------------------------------------------------------------------------
+# A persistent tap-GEMM CTA leaves ~45 K registers and ~29 KB of shared memory per SM unused, and
+# the tensor pipe does not compete with HBM streaming: the weight-gradient chain (wgrad GEMM +
+# unpack) of a backward pass therefore runs on side stream 0 while the data-gradient chain (dgrad
+# GEMM -> activation backward) continues on the caller's stream, and the Generator forward of a
+# train step runs on side stream 1 next to the Discriminator's real pass.  SEGAN_B200_OVERLAP=0
+# (or engine.OVERLAP = False) serialises everything on the caller's stream (bench.py does that for
+# its per-call profile so that per-kernel times are exclusive).
+OVERLAP = os.environ.get("SEGAN_B200_OVERLAP", "1").lower() not in ("0", "off", "no", "false")
+_SIDE = {}
+
+
+def side_stream(dev, which):
+    """Side stream `which` of device `dev`, or None when overlap is disabled."""
+    if not OVERLAP:
+        return None
+    key = (torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device(), which)
+    st = _SIDE.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=key[0])
+        _SIDE[key] = st
+    return st
+
+
+class on_side(object):
+    """`with on_side(side):` enqueues the enclosed launches on `side`, ordered after everything
+    enqueued so far on the current stream (fork).  side=None: plain in-line execution."""
+
+    def __init__(self, side):
+        self.side = side
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+        return False
+
+
+def join_side(side):
+    """The current stream waits for everything enqueued on `side` (join)."""
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -334,12 +387,6 @@ class GeneratorEngine(_NetEngine):
         wg[:, :KW] = weff
         self.packed["Wg_last"] = wg.bfloat16().contiguous()
 
-    def dwp_elems(self):
-        fm, nl = self.fmaps, self.nl
-        sizes = [9 * 4 * self.dec_cout(l) * self.dec_cin(l) for l in range(nl - 1)]
-        sizes += [9 * fm[l] * 4 * fm[l - 1] for l in range(1, nl)]
-        return max(sizes)
-
     def dec_cin(self, l):
         return 2 * self.fmaps[-1] if l == 0 else 2 * self.fmaps[self.nl - 1 - l]
 
@@ -473,7 +520,7 @@ class GeneratorEngine(_NetEngine):
         gy = gy.contiguous().float()
         if not accumulate:
             self.grad.zero_()
-        dwp_all = buf.get("g.dwp", (self.dwp_elems(),), F32, dev)
+        side = side_stream(dev, 0)       # weight-gradient chain (wgrad GEMM + unpack) of every layer
         # ---- last decoder block (tanh, Cout = 1)
         l = nl - 1
         lin = Lq[0]
@@ -492,7 +539,7 @@ class GeneratorEngine(_NetEngine):
             run_f(colg, None, lin, 0, SG_BF16, self.packed["Wg_last"], SG_BF16, 64, cin, tap_ranges("full", 0, 64, cin),
                   g_in, SG_BF16, lin, 0, 0, lin, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
             # dW'[n=(s,k)][kc=(src,s',c)] over position pairs; the s == s' blocks are the gradient
-            dwq = dwp_all[:128 * 2 * cin]
+            dwq = buf.get("g.dwq_last", (128 * 2 * cin,), F32, dev)
             dwq.zero_()
             run_w(colg, lin // 2, SG_BF16, ctx["ddb"][l - 1], ctx["ab"][0], lin // 2, 0, SG_BF16, 2 * cin, 128,
                   tap_ranges("full", 0, 2 * cin, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=74,
@@ -519,24 +566,25 @@ class GeneratorEngine(_NetEngine):
             red = buf.get("g.redd%d" % l, (SL, 3, cout), F64, dev, zero=True)
             _lib.call("sg_act_bwd_reduce", _p(g_next), cnext, 0, 0, None, 0, _p(ad[l]), SG_F16, B, 4 * lin, cout,
                       None, None, _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, _p(red), _p(g_ad), st)
-            rsum = red.sum(0).float()
-            self.gview("dec_blocks.%d.act.weight" % l).add_(rsum[0])
-            self.gview("dec_blocks.%d.deconv.bias" % l).add_(rsum[1])
+            _lib.call("sg_stat_grads", _p(red), cout, 3, _p(self.gview("dec_blocks.%d.act.weight" % l)),
+                      _p(self.gview("dec_blocks.%d.deconv.bias" % l)), None, st)
             if l == 0:
                 s0, s1 = ctx["z16b"], ctx["hpb"][nl - 1]
             else:
                 s0, s1 = ctx["ddb"][l - 1], ctx["ab"][nl - 1 - l]
             c0, c1 = s0.shape[-1], s1.shape[-1]
             taps = tap_ranges("deconv_fwd", cout, cin, 4 * cout)
-            dwp = dwp_all[:9 * 4 * cout * cin]
-            dwp.zero_()
-            n_tiles = 9 * (4 * cout // 128) * max(1, cin // 256)
-            run_w(g_ad, lin, SG_BF16, s0, s1, lin, 0, SG_BF16, cin, 4 * cout, taps, dwp, B,
-                  ksplit=wgrad_ksplit(B * lin, n_tiles), a0_c=c0, a1_c=c1, backend=self.backend)
-            alpha = self.alpha_for_dec(l)
-            galpha = self.gview("alpha_%d.skip_k" % (nl - 1 - l)).view(-1) if l > 0 else None
-            _lib.call("sg_unpack_wgrad", 1, _p(dwp), cout, cin, 0, _p(self.pview("dec_blocks.%d.deconv.weight" % l)),
-                      _p(alpha), cin // 2, _p(self.gview("dec_blocks.%d.deconv.weight" % l)), _p(galpha), 1, st)
+            dwp = buf.get("g.dwpd%d" % l, (9 * 4 * cout * cin,), F32, dev)
+            with on_side(side):
+                dwp.zero_()
+                n_tiles = 9 * (4 * cout // 128) * max(1, cin // 256)
+                run_w(g_ad, lin, SG_BF16, s0, s1, lin, 0, SG_BF16, cin, 4 * cout, taps, dwp, B,
+                      ksplit=wgrad_ksplit(B * lin, n_tiles), a0_c=c0, a1_c=c1, backend=self.backend)
+                alpha = self.alpha_for_dec(l)
+                galpha = self.gview("alpha_%d.skip_k" % (nl - 1 - l)).view(-1) if l > 0 else None
+                _lib.call("sg_unpack_wgrad", 1, _p(dwp), cout, cin, 0,
+                          _p(self.pview("dec_blocks.%d.deconv.weight" % l)), _p(alpha), cin // 2,
+                          _p(self.gview("dec_blocks.%d.deconv.weight" % l)), _p(galpha), 1, _stream())
             # data gradient w.r.t. cat(s0, s1); block 0 only needs the encoder half (z gets no gradient)
             g_in = buf.get("g.gin%d" % l, (B, lin, cin), BF16, dev)
             run_f(g_ad, None, lin, 0, SG_BF16, self.packed["Wtd%d" % l], SG_BF16, 4 * cout, cin,
@@ -560,37 +608,38 @@ class GeneratorEngine(_NetEngine):
                 gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * (gsk.shape[-1] // 2))
                 _lib.call("sg_act_bwd_reduce", _p(g_hp), cout, 16, 0, gadd_ptr, gsk.shape[-1], _p(a[l]), SG_F16,
                           B, Lq[l], cout, None, None, _p(slope), ACT_PRELU, _p(red), _p(g_a), st)
-            rsum = red.sum(0).float()
-            self.gview("enc_blocks.%d.act.weight" % l).add_(rsum[0])
-            if self.enc_bias:
-                self.gview("enc_blocks.%d.conv.bias" % l).add_(rsum[1])
+            _lib.call("sg_stat_grads", _p(red), cout, 3, _p(self.gview("enc_blocks.%d.act.weight" % l)),
+                      _p(self.gview("enc_blocks.%d.conv.bias" % l)) if self.enc_bias else None, None, st)
             if l == 0:
-                if ctx.get("colb") is not None:
-                    dwq = dwp_all[:128 * 128]
-                    dwq.zero_()
-                    run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
-                          tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
-                          backend=self.backend)
-                    t4 = dwq.view(2, 64, 2, 64)
-                    self.gview("enc_blocks.0.conv.weight").add_(
-                        (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :1, :KW])
-                else:
-                    _lib.call("sg_wave_conv_wgrad", _p(ctx["x"]), None, 1, B, L, 0, _p(g_a), cout,
-                              _p(self.gview("enc_blocks.0.conv.weight")), None, st)
+                dwq = buf.get("g.dwq0", (128 * 128,), F32, dev)
+                with on_side(side):
+                    if ctx.get("colb") is not None:
+                        dwq.zero_()
+                        run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
+                              tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
+                              backend=self.backend)
+                        t4 = dwq.view(2, 64, 2, 64)
+                        self.gview("enc_blocks.0.conv.weight").add_(
+                            (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :1, :KW])
+                    else:
+                        _lib.call("sg_wave_conv_wgrad", _p(ctx["x"]), None, 1, B, L, 0, _p(g_a), cout,
+                                  _p(self.gview("enc_blocks.0.conv.weight")), None, _stream())
                 break
             cin = fm[l - 1]
             taps = tap_ranges("conv_fwd", cin, 4 * cin, cout)
-            dwp_l = dwp_all[:9 * cout * 4 * cin]
-            dwp_l.zero_()
-            n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
-            run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout, taps, dwp_l, B,
-                  ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
-            _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
-                      _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, st)
+            dwp_l = buf.get("g.dwpe%d" % l, (9 * cout * 4 * cin,), F32, dev)
+            with on_side(side):
+                dwp_l.zero_()
+                n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
+                run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout, taps, dwp_l, B,
+                      ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
+                _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
+                          _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
             g_hp = buf.get("g.ghp%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
             run_f(g_a, None, Lq[l], 0, SG_BF16, self.packed["Wdg%d" % l], SG_BF16, cout, 4 * cin,
                   tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_hp, SG_BF16, Lq[l], 4, -4, Lq[l] + 4, B,
                   backend=self.backend)
+        join_side(side)
         return self.grad
 
 
@@ -724,18 +773,20 @@ class DiscriminatorEngine(_NetEngine):
                   _p(self.pview("fc.4.weight")), B, _p(loss_out), _p(g_z1), _p(ws),
                   gv("fc.0.bias"), gv("fc.1.weight"), gv("fc.2.weight"), gv("fc.2.bias"), gv("fc.3.weight"),
                   gv("fc.4.weight"), gv("fc.4.bias"), st)
+        # weight-gradient chain (wgrad GEMM + unpack) of every layer: side stream 0, next to the
+        # data-gradient chain (dgrad GEMM -> BatchNorm/PReLU backward) on the caller's stream
+        side = side_stream(dev, 0) if param_grads else None
         if param_grads:
-            dwp = buf.get("d.dwp", (9 * 4 * fm[-2] * fm[-1],), F32, dev)
-            dw1 = dwp[:256 * kin]
-            dw1.zero_()
-            run_w(g_z1, 1, SG_BF16, ctx["hpb"][-1], None, 1, 0, SG_BF16, kin, 256, tap_ranges("full", 0, kin, 256), dw1, B,
-                  d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
-            _lib.call("sg_unpack_wgrad", 2, _p(dw1), 256, fm[-1], Lq[-1], None, None, 0,
-                      _p(self.gview("fc.0.weight")), None, 1, st)
+            dw1 = buf.get("d.dwpfc", (256 * kin,), F32, dev)
+            with on_side(side):
+                dw1.zero_()
+                run_w(g_z1, 1, SG_BF16, ctx["hpb"][-1], None, 1, 0, SG_BF16, kin, 256, tap_ranges("full", 0, kin, 256),
+                      dw1, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
+                _lib.call("sg_unpack_wgrad", 2, _p(dw1), 256, fm[-1], Lq[-1], None, None, 0,
+                          _p(self.gview("fc.0.weight")), None, 1, _stream())
         g_h = buf.get("d.gh%d" % (nl - 1), (B, Lq[-1], fm[-1]), BF16, dev)
         run_f(g_z1, None, 1, 0, SG_BF16, self.packed["W1dg"], SG_BF16, 256, kin, tap_ranges("full", 0, 256, kin),
               g_h, SG_BF16, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
-        red = buf.get("d.red", (3, 2048), F64, dev)
         tmp = buf.get("d.cstmp", (SL * 2048,), F64, dev)
         for l in range(nl - 1, -1, -1):
             cout = fm[l]
@@ -746,14 +797,12 @@ class DiscriminatorEngine(_NetEngine):
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
-            rsum64 = redl.sum(0)
             _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
-                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(rsum64), 1, _p(g_a), st)
+                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
             if param_grads:
-                rsum = rsum64.float()
-                self.gview("enc_blocks.%d.act.weight" % l).add_(rsum[0])
-                self.gview("enc_blocks.%d.norm.bias" % l).add_(rsum[1])
-                self.gview("enc_blocks.%d.norm.weight" % l).add_(rsum[2])
+                _lib.call("sg_stat_grads", _p(redl), cout, 3, _p(self.gview("enc_blocks.%d.act.weight" % l)),
+                          _p(self.gview("enc_blocks.%d.norm.bias" % l)),
+                          _p(self.gview("enc_blocks.%d.norm.weight" % l)), st)
                 # conv biases feed BatchNorm: their gradient is exactly zero (the BN backward output has
                 # zero mean per channel); the reference only sees rounding noise there.  Left at zero
                 # (SEGAN_B200_EXACT_BIAS_GRAD=1 computes the column sums anyway).
@@ -763,18 +812,19 @@ class DiscriminatorEngine(_NetEngine):
             if l == 0:
                 w0 = self.pview("enc_blocks.0.conv.weight")
                 if param_grads and ctx.get("colb") is not None:
-                    dwp = buf.get("d.dwp", (9 * 4 * fm[-2] * fm[-1],), F32, dev)
-                    dwq = dwp[:128 * 128]
-                    dwq.zero_()
-                    run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
-                          tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
-                          backend=self.backend)
-                    t4 = dwq.view(2, 64, 2, 64)
-                    self.gview("enc_blocks.0.conv.weight").add_(
-                        (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :, :KW])
+                    dwq = buf.get("d.dwq0", (128 * 128,), F32, dev)
+                    with on_side(side):
+                        dwq.zero_()
+                        run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
+                              tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
+                              backend=self.backend)
+                        t4 = dwq.view(2, 64, 2, 64)
+                        self.gview("enc_blocks.0.conv.weight").add_(
+                            (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :, :KW])
                 elif param_grads:
-                    _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a), cout,
-                              _p(self.gview("enc_blocks.0.conv.weight")), None, st)
+                    with on_side(side):
+                        _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a),
+                                  cout, _p(self.gview("enc_blocks.0.conv.weight")), None, _stream())
                 if (input_grad is not None or input_grad1 is not None) and wave_on_tensor_cores():
                     P2 = buf.get("d.P2", (B, Lq[0], 64), BF16, dev)
                     run_f(g_a, None, Lq[0], 0, SG_BF16, self.packed["WcolT0"], SG_BF16, 64, 64,
@@ -793,17 +843,18 @@ class DiscriminatorEngine(_NetEngine):
                 break
             cin = fm[l - 1]
             if param_grads:
-                dwp = buf.get("d.dwp", (9 * 4 * fm[-2] * fm[-1],), F32, dev)
-                dwp_l = dwp[:9 * cout * 4 * cin]
-                dwp_l.zero_()
-                n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
-                run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout,
-                      tap_ranges("conv_fwd", cin, 4 * cin, cout), dwp_l, B,
-                      ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
-                _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
-                          _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, st)
+                dwp_l = buf.get("d.dwp%d" % l, (9 * cout * 4 * cin,), F32, dev)
+                with on_side(side):
+                    dwp_l.zero_()
+                    n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
+                    run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout,
+                          tap_ranges("conv_fwd", cin, 4 * cin, cout), dwp_l, B,
+                          ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
+                    _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
+                              _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
             g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
             run_f(g_a, None, Lq[l], 0, SG_BF16, self.packed["Wdg%d" % l], SG_BF16, cout, 4 * cin,
                   tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_h, SG_BF16, Lq[l], 4, -4, Lq[l] + 4, B,
                   backend=self.backend)
+        join_side(side)
         return self.grad

@@ -278,13 +278,16 @@ class SEGAN(Model):
         if z is None:
             z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
         lptr = lambda i: C.c_void_p(losses.data_ptr() + 4 * i)
-        # G forward (model.py:295)
-        Genh, gctx = ge.forward(noisy, z)
+        # G forward (model.py:295): independent of the D(real) pass, so it runs on side stream 1 next to it
+        gside = _engine.side_stream(dev, 1)
+        with _engine.on_side(gside):
+            Genh, gctx = ge.forward(noisy, z)
         # (1) D real (model.py:297-299) and (2) D fake (model.py:303-306)
         Dopt.zero_grad()
         sh = shifts3[0] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
         _, c = de.forward(clean, noisy, sh, training=True)
         de.backward(c, 1.0, 1.0, param_grads=True, loss_out=lptr(0))
+        _engine.join_side(gside)
         sh = shifts3[1] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
         _, c = de.forward(Genh, noisy, sh, training=True)
         de.backward(c, 0.0, 1.0, param_grads=True, loss_out=lptr(1))
@@ -292,7 +295,7 @@ class SEGAN(Model):
         # (3) G update against the UPDATED D (model.py:313-321)
         Gopt.zero_grad()
         sh = shifts3[2] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
-        _, c = de.forward(Genh, noisy, sh, training=True)
+        _, c = de.forward(Genh, noisy, sh, training=True, twins=False)    # no weight gradients in this pass
         gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
         de.backward(c, 1.0, 1.0, param_grads=False, input_grad=gy, loss_out=lptr(2))
         if self.reg_loss_name != 'l1_loss':
@@ -411,12 +414,18 @@ class WSEGAN(SEGAN):
         nsh = iter(shifts) if shifts is not None else None
         draw = (lambda: next(nsh)) if nsh is not None else (lambda: draw_phase_shifts(nl, self.D.phase_shift))
         d_weight = (1.0 / 3) if self.misalign_pair else 0.5
+        # the G forward (model.py:583) does not depend on the D(real) pass before it: side stream 1.
+        # (z comes from torch's generator, the phase shifts from python's `random`: drawing z first
+        # changes neither sequence.)
+        if z is None:
+            z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+        gside = _engine.side_stream(dev, 1)
+        with _engine.on_side(gside):
+            Genh, gctx = ge.forward(noisy, z)
         Dopt.zero_grad()
         _, c = de.forward(clean, noisy, draw(), training=True)
         de.backward(c, 1.0, d_weight, param_grads=True, loss_out=lptr(0))
-        if z is None:
-            z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
-        Genh, gctx = ge.forward(noisy, z)
+        _engine.join_side(gside)
         _, c = de.forward(Genh, noisy, draw(), training=True)
         de.backward(c, 0.0, d_weight, param_grads=True, loss_out=lptr(0))
         if self.misalign_pair:

@@ -46,10 +46,15 @@ def _ref_f(a_pad, halo, w, m_lo, m_hi, d_lo=-4, d_hi=4, w_tap0=0):
     return out
 
 
+EW_DEFAULT = {1: (8, 4, 2), 2: (4, 4, 3), 3: (8, 2, 2), 4: (8, 2, 4)}      # elementwise.cu g_ew
+
+
 @pytest.fixture(autouse=True)
 def _restore_cta_pair():
     yield
     _lib.load().sg_set_cta_pair(1)
+    for kind, v in EW_DEFAULT.items():
+        _lib.load().sg_set_ew_variant(kind, *v)
 
 
 @pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05, 2])
@@ -311,8 +316,16 @@ def test_wave_deconv_fwd_and_bwd():
     assert rel_err(gx.float().permute(0, 2, 1).cpu(), xin.grad) <= 1e-2      # bf16 output
 
 
-@pytest.mark.parametrize("C_,L,roll,halo", [(64, 256, 2, 16), (256, 64, -5, 16), (1024, 16, 0, 0)])
-def test_bn_act_fwd_bwd(C_, L, roll, halo):
+@pytest.mark.parametrize("variant", [(4, 2, 3), (4, 4, 16), (4, 8, 2), (8, 2, 8), (8, 4, 1)])
+@pytest.mark.parametrize("C_,L,roll,halo", [(64, 256, 2, 16), (256, 64, -5, 16), (1024, 16, 0, 0), (128, 96, 4, 16)])
+def test_bn_act_fwd_bwd(C_, L, roll, halo, variant):
+    """Every streaming-kernel variant (channels/thread, rows in flight, grid cap; for the backward
+    kernels vec 8 = the tiled kernel, vec 4 = the generic one) against fp32 torch."""
+    lib = _lib.load()
+    for kind in (1, 2, 3, 4):
+        v = variant if not (kind >= 3 and variant == (4, 8, 2)) else (4, 4, 2)
+        assert lib.sg_set_ew_variant(kind, *v) == 0
+    assert lib.sg_set_ew_variant(1, 3, 2, 3) != 0 and lib.sg_set_ew_variant(9, 4, 2, 3) != 0   # rejected
     g = _gen(6)
     B = 4
     a = torch.randn(B, L, C_, generator=g).to(torch.float16).to(DEV)
@@ -368,11 +381,14 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo):
     rs2 = red2.sum(0)
     assert rel_err(rs2[0].float().cpu(), sl2.grad) <= 2e-3
     assert rel_err(rs2[1].float().cpu(), a2.grad.sum((0, 2))) <= 2e-3
-    red_sum = red.sum(0).contiguous()
     _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
-              _p(slope), 1, _p(red_sum), 1, _p(ga), _stream())
+              _p(slope), 1, _p(red), 1, _p(ga), _stream())
+    gp = torch.ones(3, C_, device=DEV)
+    _lib.call("sg_stat_grads", _p(red), C_, 3, _p(gp[0]), None, _p(gp[2]), _stream())
     torch.cuda.synchronize()
     rs = red.sum(0)
+    assert rel_err(gp[0] - 1, rs[0].float()) <= 1e-6 and rel_err(gp[2] - 1, rs[2].float()) <= 1e-6
+    assert float((gp[1] - 1).abs().max()) == 0.0
     assert rel_err(rs[0].float().cpu(), sl.grad) <= 2e-3
     assert rel_err(rs[1].float().cpu(), bt.grad) <= 2e-3
     assert rel_err(rs[2].float().cpu(), gm.grad) <= 2e-3

@@ -159,6 +159,52 @@ def test_train_step_vs_reference(backend):
                 assert mism <= (0.2 if name == "D." else 0.35), (name + k, mism)
 
 
+def test_overlapped_step_matches_serial_step():
+    """The side-stream schedule (weight-gradient chain and Generator forward on side streams,
+    engine.OVERLAP) computes the same step as the single-stream schedule.  The weight gradients are
+    summed with fp32 atomics, so two runs of the SAME schedule already differ in the last bits and
+    RMSprop's sign-like first step amplifies that into the second step; the serial schedule run
+    twice gives the noise floor the overlapped schedule is held to."""
+    from segan_pytorch_b200 import engine as E
+    from tests.util import load_opts
+    t = golden("train_step_b4.npz")
+    B = t["clean"].shape[0]
+    clean = torch.from_numpy(t["clean"]).unsqueeze(1).to(DEV)
+    noisy = torch.from_numpy(t["noisy"]).unsqueeze(1).to(DEV)
+    z = torch.from_numpy(t["z"]).to(DEV)
+    random.seed(7)
+    shifts3 = [O.draw_phase_shifts(5, 5) for _ in range(3)]
+
+    def run(mode):
+        prev = E.OVERLAP
+        E.OVERLAP = mode
+        try:
+            s = build_segan(batch_size=B).to(DEV)
+            s.G.train()
+            s.D.train()
+            Gopt, Dopt = s.build_optimizers(load_opts(batch_size=B))
+            out = []
+            for _ in range(2):          # second step: packed weights / buffers are re-used across steps
+                losses = s.train_step(clean, noisy, Gopt, Dopt, 100.0, z=z, shifts3=shifts3)
+                torch.cuda.synchronize()
+                out.append((losses.tolist(), s.G.engine.grad.clone(), s.D.engine.grad.clone()))
+            return out
+        finally:
+            E.OVERLAP = prev
+
+    ser1, ser2, ovl = run(False), run(False), run(True)
+    for step in (0, 1):
+        (l0, gG0, gD0), (l1, gG1, gD1), (l2, gG2, gD2) = ser1[step], ser2[step], ovl[step]
+        floor_l = max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(l0, l1))
+        floor_g = max(rel_err(gG1, gG0), rel_err(gD1, gD0))
+        err_l = max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(l0, l2))
+        err_g = max(rel_err(gG2, gG0), rel_err(gD2, gD0))
+        print("step %d: serial-vs-serial loss %.2e grad %.2e | overlapped-vs-serial loss %.2e grad %.2e"
+              % (step, floor_l, floor_g, err_l, err_g))
+        assert err_l <= 4 * floor_l + 1e-4, (step, l0, l2)
+        assert err_g <= 4 * floor_g + 1e-3, (step, err_g, floor_g)
+
+
 def test_generate_chunked_vs_reference(segan):
     g = golden("generate_40000.npz")
     if hasattr(segan.G, "z"):
