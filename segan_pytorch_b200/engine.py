@@ -654,6 +654,24 @@ class DiscriminatorEngine(_NetEngine):
         self.packed = {}
         self.eps = 1e-5
         self.momentum = 0.1
+        # lane 1: a second workspace + gradient bucket so that one pass (the real pair of a train step)
+        # can run on its own stream concurrently with another pass of the same network
+        self.buf1 = _Buffers()
+        self.grad1 = None
+
+    def lane_grad(self, lane):
+        """Flat gradient bucket of `lane` (lane 1's is allocated on first use and starts zeroed)."""
+        if lane == 0:
+            return self.grad
+        if self.grad1 is None or self.grad1.shape != self.grad.shape or self.grad1.device != self.grad.device:
+            self.grad1 = torch.zeros_like(self.grad)
+        return self.grad1
+
+    def merge_lane_grads(self):
+        """grad += grad1 ; grad1 = 0 (after both lanes' passes have been joined)."""
+        if self.grad1 is not None:
+            self.grad.add_(self.grad1)
+            self.grad1.zero_()
 
     def pack(self):
         dev, fm, st = self.flat.device, self.fmaps, _stream()
@@ -676,7 +694,7 @@ class DiscriminatorEngine(_NetEngine):
         self.packed["Wcol0"] = wcol.half().contiguous()
         self.packed["WcolT0"] = wcol.t().bfloat16().contiguous()
 
-    def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True):
+    def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True, lane=0):
         """x0: candidate (B,1,L), x1: reference/noisy (B,1,L) -- the reference's cat((x_, ref), 1)
         (model.py:173-175) is never materialised.  shifts: nl signed phase shifts."""
         _require_cuda(x0, x1)
@@ -684,7 +702,7 @@ class DiscriminatorEngine(_NetEngine):
         m = self.module
         B, _, L = x0.shape
         fm, nl, dev, st = self.fmaps, self.nl, x0.device, _stream()
-        buf = _Buffers() if fresh else self.buf
+        buf = _Buffers() if fresh else (self.buf1 if lane == 1 else self.buf)
         x0 = x0.contiguous().float()
         x1 = x1.contiguous().float()
         Lq = [L // 4 ** (l + 1) for l in range(nl)]
@@ -749,7 +767,7 @@ class DiscriminatorEngine(_NetEngine):
                   _p(self.pview("fc.2.weight")), _p(self.pview("fc.2.bias")), _p(self.pview("fc.3.weight")),
                   _p(self.pview("fc.4.weight")), _p(self.pview("fc.4.bias")), B, _p(z1), _p(z2), _p(logit), st)
         ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, hpb=hpb, colb=colb0, ss=ss, mi=mi, z1=z1, z2=z2,
-                   logit=logit,
+                   logit=logit, lane=lane,
                    shifts=[int(s) for s in shifts])
         return logit, ctx
 
@@ -759,14 +777,20 @@ class DiscriminatorEngine(_NetEngine):
         param_grads: accumulate parameter gradients into self.grad (D steps) or skip them (G step).
         input_grad: optional fp32 (B,1,L) buffer that receives (+=) the gradient w.r.t. x0."""
         m = self.module
-        fm, nl, st, buf = self.fmaps, self.nl, _stream(), self.buf
+        lane = ctx.get("lane", 0)
+        fm, nl, st, buf = self.fmaps, self.nl, _stream(), (self.buf1 if lane == 1 else self.buf)
+        grad_flat = self.lane_grad(lane) if param_grads else None
+
+        def gview(name):
+            off, n, shape = self.index[name]
+            return grad_flat[off:off + n].view(shape)
         B, L, Lq = ctx["B"], ctx["L"], ctx["Lq"]
         a, hp, ss, mi, shifts = ctx["a"], ctx["hp"], ctx["ss"], ctx["mi"], ctx["shifts"]
         dev = ctx["x0"].device
         kin = Lq[-1] * fm[-1]
         g_z1 = buf.get("d.gz1", (B, 256), BF16, dev)
         ws = buf.get("d.fcws", (B * (1 + 128 + 256 + 256),), F32, dev)
-        gv = (lambda n: _p(self.gview(n))) if param_grads else (lambda n: None)
+        gv = (lambda n: _p(gview(n))) if param_grads else (lambda n: None)
         _lib.call("sg_fc_tail_bwd", _p(ctx["z1"]), _p(ctx["z2"]), _p(ctx["logit"]), _p(g_logit), float(target),
                   float(weight),
                   _p(self.pview("fc.1.weight")), _p(self.pview("fc.2.weight")), _p(self.pview("fc.3.weight")),
@@ -775,7 +799,7 @@ class DiscriminatorEngine(_NetEngine):
                   gv("fc.4.weight"), gv("fc.4.bias"), st)
         # weight-gradient chain (wgrad GEMM + unpack) of every layer: side stream 0, next to the
         # data-gradient chain (dgrad GEMM -> BatchNorm/PReLU backward) on the caller's stream
-        side = side_stream(dev, 0) if param_grads else None
+        side = side_stream(dev, 3 if lane == 1 else 0) if param_grads else None
         if param_grads:
             dw1 = buf.get("d.dwpfc", (256 * kin,), F32, dev)
             with on_side(side):
@@ -783,7 +807,7 @@ class DiscriminatorEngine(_NetEngine):
                 run_w(g_z1, 1, SG_BF16, ctx["hpb"][-1], None, 1, 0, SG_BF16, kin, 256, tap_ranges("full", 0, kin, 256),
                       dw1, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
                 _lib.call("sg_unpack_wgrad", 2, _p(dw1), 256, fm[-1], Lq[-1], None, None, 0,
-                          _p(self.gview("fc.0.weight")), None, 1, _stream())
+                          _p(gview("fc.0.weight")), None, 1, _stream())
         g_h = buf.get("d.gh%d" % (nl - 1), (B, Lq[-1], fm[-1]), BF16, dev)
         run_f(g_z1, None, 1, 0, SG_BF16, self.packed["W1dg"], SG_BF16, 256, kin, tap_ranges("full", 0, 256, kin),
               g_h, SG_BF16, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
@@ -800,15 +824,15 @@ class DiscriminatorEngine(_NetEngine):
             _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
             if param_grads:
-                _lib.call("sg_stat_grads", _p(redl), cout, 3, _p(self.gview("enc_blocks.%d.act.weight" % l)),
-                          _p(self.gview("enc_blocks.%d.norm.bias" % l)),
-                          _p(self.gview("enc_blocks.%d.norm.weight" % l)), st)
+                _lib.call("sg_stat_grads", _p(redl), cout, 3, _p(gview("enc_blocks.%d.act.weight" % l)),
+                          _p(gview("enc_blocks.%d.norm.bias" % l)),
+                          _p(gview("enc_blocks.%d.norm.weight" % l)), st)
                 # conv biases feed BatchNorm: their gradient is exactly zero (the BN backward output has
                 # zero mean per channel); the reference only sees rounding noise there.  Left at zero
                 # (SEGAN_B200_EXACT_BIAS_GRAD=1 computes the column sums anyway).
                 if m.bias and os.environ.get("SEGAN_B200_EXACT_BIAS_GRAD") == "1":
                     _lib.call("sg_colsum", _p(g_a), SG_BF16, B * Lq[l], cout, cout,
-                              _p(self.gview("enc_blocks.%d.conv.bias" % l)), 1, _p(tmp), st)
+                              _p(gview("enc_blocks.%d.conv.bias" % l)), 1, _p(tmp), st)
             if l == 0:
                 w0 = self.pview("enc_blocks.0.conv.weight")
                 if param_grads and ctx.get("colb") is not None:
@@ -819,12 +843,12 @@ class DiscriminatorEngine(_NetEngine):
                               tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
                               backend=self.backend)
                         t4 = dwq.view(2, 64, 2, 64)
-                        self.gview("enc_blocks.0.conv.weight").add_(
+                        gview("enc_blocks.0.conv.weight").add_(
                             (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :, :KW])
                 elif param_grads:
                     with on_side(side):
                         _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a),
-                                  cout, _p(self.gview("enc_blocks.0.conv.weight")), None, _stream())
+                                  cout, _p(gview("enc_blocks.0.conv.weight")), None, _stream())
                 if (input_grad is not None or input_grad1 is not None) and wave_on_tensor_cores():
                     P2 = buf.get("d.P2", (B, Lq[0], 64), BF16, dev)
                     run_f(g_a, None, Lq[0], 0, SG_BF16, self.packed["WcolT0"], SG_BF16, 64, 64,
@@ -851,10 +875,10 @@ class DiscriminatorEngine(_NetEngine):
                           tap_ranges("conv_fwd", cin, 4 * cin, cout), dwp_l, B,
                           ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
                     _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
-                              _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
+                              _p(gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
             g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
             run_f(g_a, None, Lq[l], 0, SG_BF16, self.packed["Wdg%d" % l], SG_BF16, cout, 4 * cin,
                   tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_h, SG_BF16, Lq[l], 4, -4, Lq[l] + 4, B,
                   backend=self.backend)
         join_side(side)
-        return self.grad
+        return grad_flat

@@ -1,4 +1,5 @@
 from .se_dataset import (collate_fn, normalize_wave_minmax, pre_emphasize, de_emphasize,
-                         SyntheticSEDataset)
+                         SyntheticSEDataset, DevicePrefetcher)
 
-__all__ = ["collate_fn", "normalize_wave_minmax", "pre_emphasize", "de_emphasize", "SyntheticSEDataset"]
+__all__ = ["collate_fn", "normalize_wave_minmax", "pre_emphasize", "de_emphasize", "SyntheticSEDataset",
+           "DevicePrefetcher"]

@@ -55,3 +55,62 @@ class SyntheticSEDataset(Dataset):
 
     def __getitem__(self, i):
         return ['synthetic_%d' % i, self.clean[i], self.noisy[i], 0]
+
+
+class DevicePrefetcher(object):
+    """Wraps a loader of collated batches [names, clean(B,L), noisy(B,L), slice_idx] and stages the
+    windows of batch n+1 on the GPU (a dedicated copy stream, double-buffered device slots) while
+    batch n trains, replacing the blocking `.to(device)` at the top of the reference's step
+    (segan/models/model.py:288-290).  Yields [names, clean(B,1,L), noisy(B,1,L), slice_idx] with the
+    two tensors resident on `device` and the consumer's stream ordered after their copies.
+    Pinned source tensors (DataLoader(pin_memory=True)) make the copies truly asynchronous."""
+
+    def __init__(self, loader, device, depth=2):
+        self.loader = loader
+        self.device = torch.device(device)
+        self.depth = max(2, int(depth))
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.h2d_bytes = 0
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, batch, slot):
+        names, clean, noisy, slice_idx = batch
+        clean, noisy = torch.as_tensor(clean), torch.as_tensor(noisy)
+        if clean.dtype != torch.float32:
+            clean, noisy = clean.float(), noisy.float()
+        shape = (clean.shape[0], 1, clean.shape[-1])
+        if slot.get("clean") is None or tuple(slot["clean"].shape) != shape:
+            slot["clean"] = torch.empty(shape, dtype=torch.float32, device=self.device)
+            slot["noisy"] = torch.empty(shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if slot.get("free") is not None:
+                self.copy_stream.wait_event(slot["free"])      # the step that read this slot has finished
+            slot["clean"].copy_(clean.reshape(shape), non_blocking=True)
+            slot["noisy"].copy_(noisy.reshape(shape), non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        self.h2d_bytes += 2 * clean.numel() * 4
+        return names, slot, slice_idx, ready
+
+    def __iter__(self):
+        it = iter(self.loader)
+        slots = [dict() for _ in range(self.depth)]
+        n = 0
+        try:
+            staged = self._stage(next(it), slots[0])
+        except StopIteration:
+            return
+        while staged is not None:
+            names, slot, slice_idx, ready = staged
+            n += 1
+            try:
+                staged = self._stage(next(it), slots[n % self.depth])      # batch n+1 copies while batch n trains
+            except StopIteration:
+                staged = None
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            yield [names, slot["clean"], slot["noisy"], slice_idx]
+            free = torch.cuda.Event()
+            free.record(torch.cuda.current_stream(self.device))            # everything enqueued for this batch
+            slot["free"] = free

@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from .core import Model, Saver
 from .discriminator import Discriminator, draw_phase_shifts
 from .generator import Generator
+from ..datasets.se_dataset import DevicePrefetcher
 from ... import _lib
 from ... import engine as _engine
 from ...engine import _p, _stream
@@ -278,19 +279,30 @@ class SEGAN(Model):
         if z is None:
             z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
         lptr = lambda i: C.c_void_p(losses.data_ptr() + 4 * i)
-        # G forward (model.py:295): independent of the D(real) pass, so it runs on side stream 1 next to it
-        gside = _engine.side_stream(dev, 1)
-        with _engine.on_side(gside):
-            Genh, gctx = ge.forward(noisy, z)
-        # (1) D real (model.py:297-299) and (2) D fake (model.py:303-306)
+        # Schedule (engine.OVERLAP): the D(real) pass (model.py:297-299) depends on neither G nor the fake
+        # pass, so it runs as lane 1 of the D engine (own workspace + gradient bucket) on side stream 2,
+        # concurrently with the G forward (model.py:295) and the D(fake) pass (model.py:303-306) on the
+        # caller's stream; its HBM-bound BatchNorm / PReLU kernels fill the gaps of their tap-GEMMs.
+        sh_real = shifts3[0] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
+        sh_fake = shifts3[1] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
         Dopt.zero_grad()
-        sh = shifts3[0] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
-        _, c = de.forward(clean, noisy, sh, training=True)
-        de.backward(c, 1.0, 1.0, param_grads=True, loss_out=lptr(0))
-        _engine.join_side(gside)
-        sh = shifts3[1] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
-        _, c = de.forward(Genh, noisy, sh, training=True)
+        rside = _engine.side_stream(dev, 2)
+        lane = 1 if rside is not None else 0
+        with _engine.on_side(rside):
+            _, c = de.forward(clean, noisy, sh_real, training=True, lane=lane)
+            fwd_real_done = torch.cuda.Event() if rside is not None else None
+            if fwd_real_done is not None:
+                fwd_real_done.record()
+            de.backward(c, 1.0, 1.0, param_grads=True, loss_out=lptr(0))
+        Genh, gctx = ge.forward(noisy, z)
+        if fwd_real_done is not None:
+            # BatchNorm running statistics are updated real pass first, fake pass second (model.py:297,303)
+            torch.cuda.current_stream().wait_event(fwd_real_done)
+        _, c = de.forward(Genh, noisy, sh_fake, training=True)
         de.backward(c, 0.0, 1.0, param_grads=True, loss_out=lptr(1))
+        _engine.join_side(rside)
+        if lane == 1:
+            de.merge_lane_grads()
         Dopt.step(allreduce_grads(de))                                   # model.py:308
         # (3) G update against the UPDATED D (model.py:313-321)
         Gopt.zero_grad()
@@ -327,7 +339,8 @@ class SEGAN(Model):
             beg_t = timeit.default_timer()
             self.G.train()
             self.D.train()
-            for bidx, batch in enumerate(dloader, start=1):
+            # batch n+1 is staged on the GPU (copy stream) while batch n trains
+            for bidx, batch in enumerate(DevicePrefetcher(dloader, device), start=1):
                 if epoch >= l1_dec_epoch:
                     if l1_weight > 0:
                         l1_weight -= l1_dec_step
@@ -335,8 +348,6 @@ class SEGAN(Model):
                 if len(batch) != 4:
                     raise ValueError('Returned {} elements per sample?'.format(len(batch)))
                 uttname, clean, noisy, slice_idx = batch
-                clean = clean.unsqueeze(1).to(device, non_blocking=True).float()
-                noisy = noisy.unsqueeze(1).to(device, non_blocking=True).float()
                 losses = self.train_step(clean, noisy, Gopt, Dopt, l1_weight, losses=losses)
                 end_t = timeit.default_timer()
                 timings.append(end_t - beg_t)

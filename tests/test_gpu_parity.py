@@ -205,6 +205,41 @@ def test_overlapped_step_matches_serial_step():
         assert err_g <= 4 * floor_g + 1e-3, (step, err_g, floor_g)
 
 
+def test_train_loop_with_prefetcher_matches_manual_steps(tmp_path):
+    """SEGAN.train (train.py:95-98 path) over a DataLoader, batches staged by DevicePrefetcher one step
+    ahead on a copy stream, against the same steps fed by blocking .to(device) copies."""
+    from torch.utils.data import DataLoader
+    from segan_pytorch_b200.segan.datasets import SyntheticSEDataset, collate_fn
+    from tests.util import load_opts, seed_all
+    B, n_items = 2, 6
+    dset = SyntheticSEDataset(n_items, 16384, seed=3)
+
+    def loader():
+        return DataLoader(dset, batch_size=B, shuffle=False, num_workers=0, pin_memory=True, collate_fn=collate_fn,
+                          drop_last=True)
+    opts = load_opts(batch_size=B, epoch=1, save_path=str(tmp_path), z_device="cuda")
+    s1 = build_segan(batch_size=B, save_path=str(tmp_path), z_device="cuda").to(DEV)
+    seed_all(5)
+    torch.cuda.manual_seed_all(5)
+    s1.train(opts, loader(), torch.nn.MSELoss(), 100.0, 1e-5, 100, log_freq=1000, device=DEV)
+    torch.cuda.synchronize()
+    l1 = s1.last_losses.tolist()
+    s2 = build_segan(batch_size=B, z_device="cuda").to(DEV)
+    s2.G.train()
+    s2.D.train()
+    Gopt, Dopt = s2.build_optimizers(opts)
+    seed_all(5)
+    torch.cuda.manual_seed_all(5)
+    for _, clean, noisy, _ in loader():
+        losses = s2.train_step(clean.unsqueeze(1).to(DEV), noisy.unsqueeze(1).to(DEV), Gopt, Dopt, 100.0)
+    torch.cuda.synchronize()
+    l2 = losses.tolist()
+    print("train loop", l1, "manual", l2)
+    for a, b in zip(l1, l2):
+        assert abs(a - b) <= 0.25 * max(1.0, abs(b)), (l1, l2)      # 3 chaotic GAN steps apart by atomics order
+    assert rel_err(s1.G.engine.flat, s2.G.engine.flat) <= 1e-3
+
+
 def test_generate_chunked_vs_reference(segan):
     g = golden("generate_40000.npz")
     if hasattr(segan.G, "z"):
