@@ -356,7 +356,7 @@ def main():
         kern[kind] = {"launches_per_step": n / args.steps, "ms_per_step": sec * 1e3 / args.steps,
                       "share_of_step": sec / (ms_prof * 1e-3), "tflops": fl / sec / 1e12 if sec > 0 else None}
     by_call = {}
-    for name, s_ev, e_ev in calls:
+    for name, s_ev, e_ev, _ in calls:
         c = by_call.setdefault(name, [0.0, 0])
         c[0] += s_ev.elapsed_time(e_ev)
         c[1] += 1

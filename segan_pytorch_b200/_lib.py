@@ -118,7 +118,8 @@ LAUNCHES_PER_CALL = {"sg_colsum": 2, "sg_wave_deconv_bwd": 3, "sg_fc_tail_bwd": 
 launch_count = 0
 
 
-# optional live timing of every C-ABI call (bench.py): list of (name, start_event, end_event)
+# optional live timing of every C-ABI call (bench.py, tools/timeline.py): list of
+# (name, start_event, end_event, stream handle)
 call_profile = None
 
 
@@ -132,7 +133,7 @@ def call(name, *args):
         s.record()
         rc = getattr(lib, name)(*args)
         e.record()
-        call_profile.append((name, s, e))
+        call_profile.append((name, s, e, torch.cuda.current_stream().cuda_stream))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

