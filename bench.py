@@ -245,8 +245,9 @@ def main():
     #      This region runs the SERIAL schedule (engine.OVERLAP off: everything on one stream) so that
     #      the per-kernel times are exclusive; the headline region above overlaps the HBM-bound glue
     #      kernels with the tap-GEMMs on side streams.
-    overlap_on = E.OVERLAP
+    overlap_on, graphs_on = E.OVERLAP, E.GRAPHS
     E.OVERLAP = False
+    E.GRAPHS = False
     for _ in range(2):
         s.train_step(clean, noisy, Gopt, Dopt, 100.0, losses=losses)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,7 +272,7 @@ def main():
     E.PROFILE = None
     calls = _lib.call_profile
     _lib.call_profile = None
-    E.OVERLAP = overlap_on
+    E.OVERLAP, E.GRAPHS = overlap_on, graphs_on
     # ---- timed region 2: end to end through the public data path with HOST buffers: every step's batch
     #      is copied from pinned host memory by segan.datasets.DevicePrefetcher (the loader wrapper
     #      SEGAN.train uses: batch n+1 is staged on a copy stream while batch n trains) and the step's
@@ -386,8 +387,9 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": B * world, "window": 16384,
                    "parallelism": "dp%d" % world, "optimizer": "rmsprop lr 5e-5", "l1_weight": 100,
                    "z": "device RNG (opts.z_device='cuda')", "backend": args.backend or "tcgen05",
-                   "schedule": ("side streams: wgrad chain + G forward overlap the dgrad chain / D(real) pass"
-                                if overlap_on else "single stream"),
+                   "schedule": (("side streams (wgrad chains, D(real) pass next to G forward + D(fake) pass)"
+                                 if overlap_on else "single stream") +
+                                (", step replayed from 3 CUDA graphs" if graphs_on else ", eager launches")),
                    "l2": "per-step working set (packed weights 0.4 GB + activations > 2 GB) exceeds the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": ms_e2e / args.steps,

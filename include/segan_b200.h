@@ -18,6 +18,11 @@
  * conv inputs, 0 otherwise).  [B][L][C] and [B][L/4][4C] are the same bytes, which is what turns
  * the K=31 / stride-4 (transposed) convolutions into stride-1, 9-tap "tap-GEMMs" (DESIGN.md).
  * Waveform ends (C = 1) are fp32 [B][L], identical to the reference's NCL tensors.
+ *
+ * Phase shifts: every entry point with a `roll` argument also takes `roll_dev` (device int32*, or NULL).
+ * When non-NULL the kernel reads the shift from *roll_dev and ignores `roll`: the launch then has no
+ * per-step scalar, so a whole train step can be captured once in a CUDA graph and replayed while
+ * the host only rewrites the small shift table (discriminator.py:160-172 draws new shifts every pass).
  */
 #ifndef SEGAN_B200_H
 #define SEGAN_B200_H
@@ -28,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 1
+#define SG_ABI_VERSION 2
 
 /* Per-channel statistic buffers (sg_bn_stats `stats`, sg_act_bwd_* `red`, sg_colsum `tmp`) hold
  * SG_STAT_SLICES interleaved partial copies: [SG_STAT_SLICES][n_stats][C] doubles, zeroed by the caller;
@@ -191,13 +196,14 @@ int sg_wave_deconv_bwd(const void* x0, int c0, const void* x1, int c1, int batch
 /* Tensor-core route for the same waveform-end layers: a 64-channel im2col of the waveform(s)
  * (col[b][t][ci*32+k] = pad(v_ci)[4t+k-off], 16-bit, fp16 and/or bf16 copy) makes them single-tap
  * tap-GEMMs with K = 64; the transposed forms are a GEMM followed by a shift-add. */
-int sg_wave_im2col(const float* v0, const float* v1, int cin, int batch, int L, int roll, int reflect,
-                   int off, void* col_f16, void* col_bf16, void* stream);
+int sg_wave_im2col(const float* v0, const float* v1, int cin, int batch, int L, int roll, const int32_t* roll_dev,
+                   int reflect, int off, void* col_f16, void* col_bf16, void* stream);
 /* y[b][4m+r] = tanh(bias + sum_d P[b][m+d][(d+4)*4+r]); P fp32 [B][Lin][64] (last decoder block) */
 int sg_wave_shiftadd_tanh(const float* P, int batch, int Lin, const float* bias, float* y, void* stream);
 /* gx[b][unroll(reflect(q))] += sum_{4t+k-14=q} P2[b][t][col0+k]; P2 bf16 [B][L/4][64] (D input gradient;
  * col0 = 32*ci selects the input channel) */
-int sg_wave_col2im_fold(const void* P2, int col0, int batch, int L, int roll, float* gx, void* stream);
+int sg_wave_col2im_fold(const void* P2, int col0, int batch, int L, int roll, const int32_t* roll_dev, float* gx,
+                        void* stream);
 /* gpre = gy*(1-y^2); dbias += sum(gpre) */
 int sg_tanh_bwd(const float* gy, const float* y, int64_t n, float* gpre, float* dbias, void* stream);
 
@@ -218,7 +224,7 @@ int sg_bn_finalize(const double* stats, int64_t count, int C, const float* gamma
  * The bf16 twins feed the weight-gradient tap-GEMM, whose two operands must share one 16-bit
  * format (tcgen05 kind::f16 rejects f16 x bf16; gradients are bf16 for range). */
 int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
-               const float* slope, int act, int roll, int out_halo_pos, void* h,
+               const float* slope, int act, int roll, const int32_t* roll_dev, int out_halo_pos, void* h,
                void* h_bf16 /* optional bf16 twin of h (same geometry) */,
                void* a_bf16 /* optional bf16 copy of a (exact geometry) */, void* stream);
 /* backward of sg_act_fwd (+ optional BatchNorm backward).  g_h: gradient w.r.t. the consumer
@@ -235,12 +241,12 @@ int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* s
  *   the PReLU-slope / bias (beta) / gamma gradients of model.py:299,306,320 from the pass-1 statistics. */
 /* g_h_ld / g_add_ld: row pitch in elements of g_h / g_add (>= C; lets a consumer read one half of
  * a channel-concatenated gradient in place; the pointers are pre-offset by the caller) */
-int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add, int g_add_ld,
-                      const void* a, int dtype, int batch, int L, int C,
+int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const int32_t* roll_dev,
+                      const void* g_add, int g_add_ld, const void* a, int dtype, int batch, int L, int C,
                       const float* scale_shift, const float* mean_invstd, const float* slope,
                       int act, double* red, void* g_a_out_or_null, void* stream);
-int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add, int g_add_ld,
-                     const void* a, int dtype, int batch, int L, int C,
+int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const int32_t* roll_dev,
+                     const void* g_add, int g_add_ld, const void* a, int dtype, int batch, int L, int C,
                      const float* scale_shift, const float* mean_invstd, const float* slope,
                      int act, const double* red, int use_bn, void* g_a, void* stream);
 int sg_stat_grads(const double* red, int C, int n_stats, float* g0, float* g1, float* g2, void* stream);

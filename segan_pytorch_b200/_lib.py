@@ -56,15 +56,15 @@ _SIGS = {
     "sg_wave_conv_dgrad": [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp],
     "sg_wave_deconv_fwd": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "sg_wave_deconv_bwd": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "sg_wave_im2col": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "sg_wave_im2col": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp],
     "sg_wave_shiftadd_tanh": [_vp, _i, _i, _vp, _vp, _vp],
-    "sg_wave_col2im_fold": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "sg_wave_col2im_fold": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "sg_tanh_bwd": [_vp, _vp, _i64, _vp, _vp, _vp],
     "sg_bn_stats": [_vp, _i, _i64, _i, _vp, _vp],
     "sg_bn_finalize": [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp],
-    "sg_act_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
-    "sg_act_bwd_reduce": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-    "sg_act_bwd_apply": [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
+    "sg_act_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
+    "sg_act_bwd_reduce": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "sg_act_bwd_apply": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "sg_stat_grads": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "sg_ncl_to_nlc": [_vp, _i, _i, _i, _vp, _i, _vp],
     "sg_nlc_to_ncl": [_vp, _i, _i, _i, _i, _vp, _vp],
@@ -107,7 +107,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
-    if lib.sg_abi_version() != 1:
+    if lib.sg_abi_version() != 2:
         raise SeganB200Error("ABI version mismatch")
     _lib = lib
     return lib

@@ -172,8 +172,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 template <int VEC, int UNROLL>
 __global__ void __launch_bounds__(256, (VEC == 4 && UNROLL <= 4) ? 3 : 2)
 act_fwd_kernel(const void* __restrict__ a, int dtype, int batch, int L, int C,
-               const float* __restrict__ scale_shift, const float* __restrict__ slope, int act, int roll, int H,
+               const float* __restrict__ scale_shift, const float* __restrict__ slope, int act, int roll,
+               const int* __restrict__ roll_dev, int H,
                void* __restrict__ h, void* __restrict__ h_bf16, void* __restrict__ a_bf16) {
+  if (roll_dev) roll = *roll_dev;
   constexpr int U = 2 * UNROLL;            // a single input stream: twice the rows in flight
   const int cgs = C / VEC;
   const int Lh = L + 2 * H;
@@ -256,11 +258,13 @@ __device__ __forceinline__ void gather_gy(const void* g_h, int ldh, int H, int r
 // after the activation derivative.
 template <int MODE, int VEC, int UNROLL>
 __global__ void __launch_bounds__(256, (VEC == 4 && UNROLL <= 4) ? 3 : 2)
-act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const void* __restrict__ g_add, int lda,
+act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const int* __restrict__ roll_dev,
+               const void* __restrict__ g_add, int lda,
                const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ mean_invstd,
                const float* __restrict__ slope, int act, double* __restrict__ red, int use_bn,
                void* __restrict__ g_a_out) {
+  if (roll_dev) roll = *roll_dev;
   __shared__ float sred[MODE == 0 ? 256 * VEC : 1];
   const int cgs = C / VEC;
   const int tid = threadIdx.x;
@@ -392,13 +396,14 @@ __device__ __forceinline__ void ld_f8(const float* p, float (&v)[8]) {
 
 template <int MODE, int U>
 __global__ void __launch_bounds__(256, 2)
-act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll,
+act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll, const int* __restrict__ roll_dev,
                      const uint16_t* __restrict__ g_add, int lda, const uint16_t* __restrict__ a, int a_f16,
                      int batch, int L, int C, int cgs_log2, const float* __restrict__ scale_shift,
                      const float* __restrict__ mean_invstd, const float* __restrict__ slope, int act,
                      const double* __restrict__ red_in, double* __restrict__ red_out, int use_bn,
                      uint16_t* __restrict__ g_a_out, int tiles_per_b, int tiles_per_cta) {
   extern __shared__ __align__(16) float smf[];
+  if (roll_dev) roll = *roll_dev;
   float* s_sc = smf;                 // y = x*sc + sh (sign test, slope gradient)
   float* s_sh = smf + C;
   float* s_sl = smf + 2 * C;         // PReLU slope (1 when act == NONE)
@@ -844,7 +849,8 @@ static inline int stream_grid(int64_t rows, int C, int vec, int rows_in_flight, 
 static inline bool ew_shape_ok(int C) { return C >= 64 && C <= 1024 && (C & (C - 1)) == 0; }
 
 template <int MODE>
-static int launch_act_bwd_tiled(const void* g_h, int ldh, int H, int roll, const void* g_add, int lda, const void* a,
+static int launch_act_bwd_tiled(const void* g_h, int ldh, int H, int roll, const int32_t* roll_dev, const void* g_add,
+                                int lda, const void* a,
                                 int dtype, int batch, int L, int C, const float* scale_shift,
                                 const float* mean_invstd, const float* slope, int act, const double* red_in,
                                 double* red_out, int use_bn, void* g_a_out, int unroll, int cap_per_sm, cudaStream_t st) {
@@ -866,7 +872,8 @@ static int launch_act_bwd_tiled(const void* g_h, int ldh, int H, int roll, const
   const size_t smem = smem_const > smem_red ? smem_const : smem_red;
 #define SG_LAUNCH_TILED(UU)                                                                                   \
   act_bwd_tiled_kernel<MODE, UU><<<(int)grid, 256, smem, st>>>(                                                \
-      (const uint16_t*)g_h, ldh, H, roll, (const uint16_t*)g_add, lda, (const uint16_t*)a, dtype == SG_F16,   \
+      (const uint16_t*)g_h, ldh, H, roll, roll_dev, (const uint16_t*)g_add, lda, (const uint16_t*)a,          \
+      dtype == SG_F16,                                                                                       \
       batch, L, C, cgs_log2, scale_shift, mean_invstd, slope, act, red_in, red_out, use_bn, (uint16_t*)g_a_out, \
       tiles_per_b, tiles_per_cta)
   if (U == 4) SG_LAUNCH_TILED(4); else SG_LAUNCH_TILED(2);
@@ -918,19 +925,19 @@ extern "C" int sg_bn_finalize(const double* stats, int64_t count, int C, const f
 }
 
 extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
-                          const float* slope, int act, int roll, int out_halo_pos, void* h, void* h_bf16,
-                          void* a_bf16, void* stream) {
+                          const float* slope, int act, int roll, const int32_t* roll_dev, int out_halo_pos, void* h,
+                          void* h_bf16, void* a_bf16, void* stream) {
   SG_CHECK_ARG(ew_shape_ok(C) && (out_halo_pos == 0 || L >= 32));
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
   const EwVariant v = ew(EW_ACT_FWD);
   EW_DISPATCH(v.vec, v.unroll, (act_fwd_kernel<VEC, UNR><<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(
-      a, dtype, batch, L, C, scale_shift, slope, act, roll, out_halo_pos, h, h_bf16, a_bf16)));
+      a, dtype, batch, L, C, scale_shift, slope, act, roll, roll_dev, out_halo_pos, h, h_bf16, a_bf16)));
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
 
-extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add,
-                                 int g_add_ld, const void* a,
+extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const int32_t* roll_dev,
+                                 const void* g_add, int g_add_ld, const void* a,
                                  int dtype, int batch, int L, int C, const float* scale_shift,
                                  const float* mean_invstd, const float* slope, int act, double* red,
                                  void* g_a_out, void* stream) {
@@ -939,21 +946,21 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
   const EwVariant v = ew(EW_BWD_REDUCE);
   const int ldh = g_h_ld > 0 ? g_h_ld : C, lda = g_add_ld > 0 ? g_add_ld : C;
   if (v.vec == 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
-    int rc = launch_act_bwd_tiled<0>(g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C, scale_shift,
+    int rc = launch_act_bwd_tiled<0>(g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C, scale_shift,
                                      mean_invstd, slope, act, nullptr, red, 0, g_a_out, v.unroll, v.cap, ST);
     if (rc) return rc;
     SG_CHECK_LAUNCH();
     return SG_OK;
   }
   EW_DISPATCH(4, v.unroll, (act_bwd_kernel<0, VEC, UNR><<<stream_grid((int64_t)batch * L, C, VEC, UNR, v.cap), 256, 0, ST>>>(
-      g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C,
+      g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, red, 0, g_a_out)));
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
 
-extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const void* g_add,
-                                int g_add_ld, const void* a,
+extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, const int32_t* roll_dev,
+                                const void* g_add, int g_add_ld, const void* a,
                                 int dtype, int batch, int L, int C, const float* scale_shift,
                                 const float* mean_invstd, const float* slope, int act, const double* red,
                                 int use_bn, void* g_a, void* stream) {
@@ -963,14 +970,14 @@ extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, in
   const EwVariant v = ew(EW_BWD_APPLY);
   const int ldh = g_h_ld > 0 ? g_h_ld : C, lda = g_add_ld > 0 ? g_add_ld : C;
   if (v.vec == 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
-    int rc = launch_act_bwd_tiled<1>(g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C, scale_shift,
+    int rc = launch_act_bwd_tiled<1>(g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C, scale_shift,
                                      mean_invstd, slope, act, red, nullptr, use_bn, g_a, v.unroll, v.cap, ST);
     if (rc) return rc;
     SG_CHECK_LAUNCH();
     return SG_OK;
   }
   EW_DISPATCH(4, v.unroll, (act_bwd_kernel<1, VEC, UNR><<<stream_grid((int64_t)batch * L, C, VEC, UNR, v.cap), 256, 0, ST>>>(
-      g_h, ldh, in_halo_pos, roll, g_add, lda, a, dtype, batch, L, C,
+      g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C,
       scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a)));
   SG_CHECK_LAUNCH();
   return SG_OK;

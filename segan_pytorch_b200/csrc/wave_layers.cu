@@ -334,7 +334,9 @@ namespace sg {
 // col[b][t][ci*32 + k] = pad(v_ci)[4t + k - off]   (k < 31; k = 31 and absent channels = 0)
 __global__ void __launch_bounds__(256)
 wave_im2col_kernel(const float* __restrict__ v0, const float* __restrict__ v1, int cin, int batch, int L, int roll,
+                   const int* __restrict__ roll_dev,
                    int mode, int off, void* __restrict__ col_f16, void* __restrict__ col_bf16) {
+  if (roll_dev) roll = *roll_dev;
   const int Lq = L / 4;
   const int64_t total = (int64_t)batch * Lq * 8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -379,7 +381,9 @@ wave_shiftadd_tanh_kernel(const float* __restrict__ P, int batch, int Lin, const
 
 // gx[b][src(q)] += sum_{t,k: 4t + k - 14 = q} P2[b][t][k]   (reflect fold + un-roll), P2 bf16 [B][Lq][64]
 __global__ void __launch_bounds__(256)
-wave_col2im_fold_kernel(const void* __restrict__ P2, int col0, int batch, int L, int roll, float* __restrict__ gx) {
+wave_col2im_fold_kernel(const void* __restrict__ P2, int col0, int batch, int L, int roll,
+                        const int* __restrict__ roll_dev, float* __restrict__ gx) {
+  if (roll_dev) roll = *roll_dev;
   const int Lq = L / 4;
   const int span = L + 30;                         // q in [-14, L + 15]
   const int64_t total = (int64_t)batch * span;
@@ -401,13 +405,14 @@ wave_col2im_fold_kernel(const void* __restrict__ P2, int col0, int batch, int L,
 
 }  // namespace sg
 
-extern "C" int sg_wave_im2col(const float* v0, const float* v1, int cin, int batch, int L, int roll, int reflect,
+extern "C" int sg_wave_im2col(const float* v0, const float* v1, int cin, int batch, int L, int roll,
+                              const int32_t* roll_dev, int reflect,
                               int off, void* col_f16, void* col_bf16, void* stream) {
   SG_CHECK_ARG(v0 && (cin == 1 || (cin == 2 && v1)) && L % 4 == 0 && (col_f16 || col_bf16));
   const int64_t total = (int64_t)batch * (L / 4) * 8;
   int64_t g = cdiv(total, 256 * 4);
   if (g > 16 * NUM_SMS) g = 16 * NUM_SMS;
-  wave_im2col_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(v0, v1, cin, batch, L, roll,
+  wave_im2col_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(v0, v1, cin, batch, L, roll, roll_dev,
                                                               reflect ? PAD_REFLECT : PAD_ZERO, off, col_f16, col_bf16);
   SG_CHECK_LAUNCH();
   return SG_OK;
@@ -422,11 +427,12 @@ extern "C" int sg_wave_shiftadd_tanh(const float* P, int batch, int Lin, const f
   return SG_OK;
 }
 
-extern "C" int sg_wave_col2im_fold(const void* P2, int col0, int batch, int L, int roll, float* gx, void* stream) {
+extern "C" int sg_wave_col2im_fold(const void* P2, int col0, int batch, int L, int roll, const int32_t* roll_dev,
+                                   float* gx, void* stream) {
   const int64_t total = (int64_t)batch * (L + 30);
   int64_t g = cdiv(total, 256 * 4);
   if (g > 16 * NUM_SMS) g = 16 * NUM_SMS;
-  wave_col2im_fold_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(P2, col0, batch, L, roll, gx);
+  wave_col2im_fold_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(P2, col0, batch, L, roll, roll_dev, gx);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

@@ -77,6 +77,10 @@ def _stream():
 # (or engine.OVERLAP = False) serialises everything on the caller's stream (bench.py does that for
 # its per-call profile so that per-kernel times are exclusive).
 OVERLAP = os.environ.get("SEGAN_B200_OVERLAP", "1").lower() not in ("0", "off", "no", "false")
+# CUDA graphs: SEGAN.train_step captures the whole step after GRAPH_WARMUP eager steps of the same shape
+# and replays it (SEGAN_B200_GRAPH=0 keeps the eager schedule).
+GRAPHS = os.environ.get("SEGAN_B200_GRAPH", "1").lower() not in ("0", "off", "no", "false")
+GRAPH_WARMUP = 2
 _SIDE = {}
 
 
@@ -423,7 +427,7 @@ class GeneratorEngine(_NetEngine):
             if l == 0 and wave_on_tensor_cores():
                 col16 = buf.get("g.col16", (B, Lq[0], 64), F16, dev)
                 colb = buf.get("g.colb", (B, Lq[0], 64), BF16, dev) if want_ctx else None
-                _lib.call("sg_wave_im2col", _p(x), None, 1, B, L, 0, 1, 14, _p(col16), _p(colb), st)
+                _lib.call("sg_wave_im2col", _p(x), None, 1, B, L, 0, None, 1, 14, _p(col16), _p(colb), st)
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
                       d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
@@ -443,7 +447,7 @@ class GeneratorEngine(_NetEngine):
                 if l < nl - 1:
                     ab[l] = buf.get("g.ab%d" % l, (B, Lq[l], cout), BF16, dev)
             _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, None,
-                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, 0, halo, _p(hp[l]), _p(hpb[l]),
+                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, 0, None, halo, _p(hp[l]), _p(hpb[l]),
                       _p(ab[l]), st)
         # ---- z
         zc = z.shape[1]
@@ -469,7 +473,7 @@ class GeneratorEngine(_NetEngine):
             if want_ctx:
                 ddb[l] = buf.get("g.ddb%d" % l, (B, 4 * lin, cout), BF16, dev)
             _lib.call("sg_act_fwd", _p(ad[l]), SG_F16, B, 4 * lin, cout, None,
-                      _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, 0, _p(dd[l]), _p(ddb[l]), None, st)
+                      _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, None, 0, _p(dd[l]), _p(ddb[l]), None, st)
             lin *= 4
             src0, src1 = dd[l], a[nl - 2 - l]
         y = torch.empty(B, 1, L, dtype=F32, device=dev)
@@ -535,7 +539,7 @@ class GeneratorEngine(_NetEngine):
         if wave_on_tensor_cores():
             _lib.call("sg_tanh_bwd", _p(gy), _p(ctx["y"]), B * L, _p(gpre), _p(gb), st)
             colg = buf.get("g.colg", (B, lin, 64), BF16, dev)
-            _lib.call("sg_wave_im2col", _p(gpre), None, 1, B, L, 0, 0, 13, None, _p(colg), st)
+            _lib.call("sg_wave_im2col", _p(gpre), None, 1, B, L, 0, None, 0, 13, None, _p(colg), st)
             run_f(colg, None, lin, 0, SG_BF16, self.packed["Wg_last"], SG_BF16, 64, cin, tap_ranges("full", 0, 64, cin),
                   g_in, SG_BF16, lin, 0, 0, lin, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
             # dW'[n=(s,k)][kc=(src,s',c)] over position pairs; the s == s' blocks are the gradient
@@ -564,7 +568,7 @@ class GeneratorEngine(_NetEngine):
             # PReLU backward on [B, 4*lin, cout]
             g_ad = buf.get("g.gad%d" % l, (B, lin, 4 * cout), BF16, dev)
             red = buf.get("g.redd%d" % l, (SL, 3, cout), F64, dev, zero=True)
-            _lib.call("sg_act_bwd_reduce", _p(g_next), cnext, 0, 0, None, 0, _p(ad[l]), SG_F16, B, 4 * lin, cout,
+            _lib.call("sg_act_bwd_reduce", _p(g_next), cnext, 0, 0, None, None, 0, _p(ad[l]), SG_F16, B, 4 * lin, cout,
                       None, None, _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, _p(red), _p(g_ad), st)
             _lib.call("sg_stat_grads", _p(red), cout, 3, _p(self.gview("dec_blocks.%d.act.weight" % l)),
                       _p(self.gview("dec_blocks.%d.deconv.bias" % l)), None, st)
@@ -601,12 +605,12 @@ class GeneratorEngine(_NetEngine):
             if l == nl - 1:
                 gin0 = buf.t["g.gin0"]
                 gh_ptr = C.c_void_p(gin0.data_ptr() + 2 * (gin0.shape[-1] // 2))
-                _lib.call("sg_act_bwd_reduce", gh_ptr, gin0.shape[-1], 0, 0, None, 0, _p(a[l]), SG_F16, B, Lq[l],
+                _lib.call("sg_act_bwd_reduce", gh_ptr, gin0.shape[-1], 0, 0, None, None, 0, _p(a[l]), SG_F16, B, Lq[l],
                           cout, None, None, _p(slope), ACT_PRELU, _p(red), _p(g_a), st)
             else:
                 gsk = buf.t["g.gin%d" % (nl - 1 - l)]
                 gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * (gsk.shape[-1] // 2))
-                _lib.call("sg_act_bwd_reduce", _p(g_hp), cout, 16, 0, gadd_ptr, gsk.shape[-1], _p(a[l]), SG_F16,
+                _lib.call("sg_act_bwd_reduce", _p(g_hp), cout, 16, 0, None, gadd_ptr, gsk.shape[-1], _p(a[l]), SG_F16,
                           B, Lq[l], cout, None, None, _p(slope), ACT_PRELU, _p(red), _p(g_a), st)
             _lib.call("sg_stat_grads", _p(red), cout, 3, _p(self.gview("enc_blocks.%d.act.weight" % l)),
                       _p(self.gview("enc_blocks.%d.conv.bias" % l)) if self.enc_bias else None, None, st)
@@ -694,9 +698,11 @@ class DiscriminatorEngine(_NetEngine):
         self.packed["Wcol0"] = wcol.half().contiguous()
         self.packed["WcolT0"] = wcol.t().bfloat16().contiguous()
 
-    def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True, lane=0):
+    def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True, lane=0, shifts_dev=None):
         """x0: candidate (B,1,L), x1: reference/noisy (B,1,L) -- the reference's cat((x_, ref), 1)
-        (model.py:173-175) is never materialised.  shifts: nl signed phase shifts."""
+        (model.py:173-175) is never materialised.  shifts: nl signed phase shifts.  shifts_dev: optional
+        device int32 tensor holding the same nl shifts; the kernels then read them from memory (no
+        per-step scalar in the launches, so the step can be replayed from a CUDA graph)."""
         _require_cuda(x0, x1)
         self.ensure_packed()
         m = self.module
@@ -707,6 +713,11 @@ class DiscriminatorEngine(_NetEngine):
         x1 = x1.contiguous().float()
         Lq = [L // 4 ** (l + 1) for l in range(nl)]
         assert Lq[-1] * fm[-1] == self.pview("fc.0.weight").shape[1], "D expects L = 16384"
+        if shifts_dev is not None and not wave_on_tensor_cores():
+            raise _lib.SeganB200Error("device-resident phase shifts need the tensor-core waveform route")
+
+        def rptr(i):
+            return None if shifts_dev is None else C.c_void_p(shifts_dev.data_ptr() + 4 * i)
         a, hp, ss, mi, hpb = [None] * nl, [None] * nl, [None] * nl, [None] * nl, [None] * nl
         for l in range(nl):
             cout = fm[l]
@@ -716,7 +727,7 @@ class DiscriminatorEngine(_NetEngine):
             if l == 0 and wave_on_tensor_cores():
                 col16 = buf.get("d.col16", (B, Lq[0], 64), F16, dev)
                 colb0 = buf.get("d.colb", (B, Lq[0], 64), BF16, dev) if twins else None
-                _lib.call("sg_wave_im2col", _p(x0), _p(x1), 2, B, L, int(shifts[0]), 1, 14, _p(col16), _p(colb0), st)
+                _lib.call("sg_wave_im2col", _p(x0), _p(x1), 2, B, L, int(shifts[0]), rptr(0), 1, 14, _p(col16), _p(colb0), st)
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
                       d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
@@ -752,8 +763,8 @@ class DiscriminatorEngine(_NetEngine):
             hp[l] = buf.get("d.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
             hpb[l] = buf.get("d.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), BF16, dev) if twins else None
             _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, _p(ss[l]),
-                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, roll, halo, _p(hp[l]), _p(hpb[l]),
-                      None, st)
+                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, roll, rptr(l + 1) if l < nl - 1 else None,
+                      halo, _p(hp[l]), _p(hpb[l]), None, st)
         # ---- FC head
         kin = Lq[-1] * fm[-1]
         acc = buf.get("d.fc0", (B, 256), F32, dev, zero=True)
@@ -767,7 +778,7 @@ class DiscriminatorEngine(_NetEngine):
                   _p(self.pview("fc.2.weight")), _p(self.pview("fc.2.bias")), _p(self.pview("fc.3.weight")),
                   _p(self.pview("fc.4.weight")), _p(self.pview("fc.4.bias")), B, _p(z1), _p(z2), _p(logit), st)
         ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, hpb=hpb, colb=colb0, ss=ss, mi=mi, z1=z1, z2=z2,
-                   logit=logit, lane=lane,
+                   logit=logit, lane=lane, shifts_dev=shifts_dev,
                    shifts=[int(s) for s in shifts])
         return logit, ctx
 
@@ -778,6 +789,10 @@ class DiscriminatorEngine(_NetEngine):
         input_grad: optional fp32 (B,1,L) buffer that receives (+=) the gradient w.r.t. x0."""
         m = self.module
         lane = ctx.get("lane", 0)
+        shifts_dev = ctx.get("shifts_dev")
+
+        def rptr(i):
+            return None if shifts_dev is None else C.c_void_p(shifts_dev.data_ptr() + 4 * i)
         fm, nl, st, buf = self.fmaps, self.nl, _stream(), (self.buf1 if lane == 1 else self.buf)
         grad_flat = self.lane_grad(lane) if param_grads else None
 
@@ -816,12 +831,13 @@ class DiscriminatorEngine(_NetEngine):
             cout = fm[l]
             halo = 16 if l < nl - 1 else 0
             roll = shifts[l + 1] if l < nl - 1 else 0
+            rp = rptr(l + 1) if l < nl - 1 else None
             g_a = buf.get("d.ga%d" % l, (B, Lq[l], cout), BF16, dev)
             redl = buf.get("d.red%d" % l, (SL, 3, cout), F64, dev, zero=True)
             slope = self.pview("enc_blocks.%d.act.weight" % l)
-            _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
+            _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
-            _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
+            _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
             if param_grads:
                 _lib.call("sg_stat_grads", _p(redl), cout, 3, _p(gview("enc_blocks.%d.act.weight" % l)),
@@ -855,9 +871,9 @@ class DiscriminatorEngine(_NetEngine):
                           tap_ranges("full", 0, 64, 64), P2, SG_BF16, Lq[0], 0, 0, Lq[0], B, d_lo=0, d_hi=0, w_tap0=4,
                           backend=self.backend)
                     if input_grad is not None:
-                        _lib.call("sg_wave_col2im_fold", _p(P2), 0, B, L, shifts[0], _p(input_grad), st)
+                        _lib.call("sg_wave_col2im_fold", _p(P2), 0, B, L, shifts[0], rptr(0), _p(input_grad), st)
                     if input_grad1 is not None:
-                        _lib.call("sg_wave_col2im_fold", _p(P2), 32, B, L, shifts[0], _p(input_grad1), st)
+                        _lib.call("sg_wave_col2im_fold", _p(P2), 32, B, L, shifts[0], rptr(0), _p(input_grad1), st)
                 else:
                     if input_grad is not None:
                         _lib.call("sg_wave_conv_dgrad", _p(g_a), B, L, shifts[0], _p(w0), 2, cout, _p(input_grad), 1, st)

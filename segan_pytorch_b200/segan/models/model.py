@@ -8,6 +8,7 @@ import ctypes as C
 import os
 import random
 import timeit
+import types
 
 import numpy as np
 import torch
@@ -266,56 +267,187 @@ class SEGAN(Model):
 
     def train_step(self, clean, noisy, Gopt, Dopt, l1_weight, z=None, shifts3=None, losses=None):
         """clean / noisy: (B,1,L) fp32 cuda.  Returns the device tensor of the four losses
-        [d_real, d_fake, g_adv, g_l1] (no host sync)."""
+        [d_real, d_fake, g_adv, g_l1] (no host sync).
+
+        After `engine.GRAPH_WARMUP` eager steps of the same shape the step is captured once into three
+        CUDA graphs (D phase | D optimiser + G phase | G optimiser; the two gradient all-reduces of a
+        data-parallel run sit between them) and replayed: the ~300 launches of a step then cost no host
+        time and the side-stream schedule (engine.OVERLAP) becomes real concurrency on the device.  The
+        per-step phase shifts live in a small device table the host rewrites before each replay."""
         ge, de = self.G.engine, self.D.engine
         B, _, L = clean.shape
         dev = clean.device
-        st = _stream()
         nl = len(self.D.enc_blocks)
-        if losses is None:
-            losses = torch.zeros(4, dtype=torch.float32, device=dev)
-        else:
-            losses.zero_()
-        if z is None:
+        if self.reg_loss_name != 'l1_loss':
+            raise NotImplementedError("reg_loss %r: only 'l1_loss' (train.py:179 default) is built" % self.reg_loss_name)
+        if shifts3 is None:        # python `random` draw order of the reference: real, fake, G-step pass
+            shifts3 = [draw_phase_shifts(nl, self.D.phase_shift) for _ in range(3)]
+        if z is None and self.z_device == 'cpu':
             z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+        st = self._graph_state(clean, noisy, Gopt, Dopt, l1_weight, z is None)
+        if st is None:
+            # ---- eager schedule
+            if losses is None:
+                losses = torch.zeros(4, dtype=torch.float32, device=dev)
+            if z is None:
+                z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+            Genh, gctx = self._seg_d(clean, noisy, z, shifts3, None, losses, Dopt, sample_z=False)
+            dscale = allreduce_grads(de)                                   # before model.py:308
+            self._seg_g(clean, noisy, Genh, gctx, shifts3, None, losses, l1_weight, Gopt, Dopt, dscale)
+            gscale = allreduce_grads(ge)                                   # before model.py:321
+            Gopt.step(gscale)                                              # model.py:321
+            return losses
+        # ---- CUDA-graph schedule: refresh the static inputs, replay
+        if st.clean.data_ptr() != clean.data_ptr():
+            st.clean.copy_(clean, non_blocking=True)
+        if st.noisy.data_ptr() != noisy.data_ptr():
+            st.noisy.copy_(noisy, non_blocking=True)
+        if z is not None:
+            st.z.copy_(z, non_blocking=True)
+            if not hasattr(self.G, 'z'):
+                self.G.z = z
+        flat = [int(v) for sh in shifts3 for v in sh]
+        st.shifts.copy_(torch.tensor(flat, dtype=torch.int32).pin_memory(), non_blocking=True)
+        if st.graphs is None:
+            self._capture_step(st, z is None, shifts3, l1_weight, Gopt, Dopt)
+        else:
+            if de._version() != de._packed_version:
+                de.ensure_packed()             # parameters were touched outside the step (checkpoint load ...)
+            st.graphs[0].replay()
+            allreduce_grads(de)
+            st.graphs[1].replay()
+            allreduce_grads(ge)
+            st.graphs[2].replay()
+            Dopt.t += 1
+            Gopt.t += 1
+            ge.mark_dirty()                    # the replayed G optimiser step changed the master weights
+            _lib.launch_count += st.launches
+        if losses is not None and losses.data_ptr() != st.losses.data_ptr():
+            losses.copy_(st.losses, non_blocking=True)
+            return losses
+        return st.losses
+
+    # -- step segments (shared by the eager and the graph schedule) -------------------------------
+    def _seg_d(self, clean, noisy, z, shifts3, shifts_dev, losses, Dopt, sample_z):
+        """G forward (model.py:295), D real (model.py:297-299) and D fake (model.py:303-306) passes.
+        Schedule (engine.OVERLAP): the D(real) pass depends on neither G nor the fake pass, so it runs as
+        lane 1 of the D engine (own workspace + gradient bucket) on side stream 2, concurrently with the
+        G forward and the D(fake) pass on the caller's stream."""
+        ge, de = self.G.engine, self.D.engine
+        dev = clean.device
+        nl = len(self.D.enc_blocks)
         lptr = lambda i: C.c_void_p(losses.data_ptr() + 4 * i)
-        # Schedule (engine.OVERLAP): the D(real) pass (model.py:297-299) depends on neither G nor the fake
-        # pass, so it runs as lane 1 of the D engine (own workspace + gradient bucket) on side stream 2,
-        # concurrently with the G forward (model.py:295) and the D(fake) pass (model.py:303-306) on the
-        # caller's stream; its HBM-bound BatchNorm / PReLU kernels fill the gaps of their tap-GEMMs.
-        sh_real = shifts3[0] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
-        sh_fake = shifts3[1] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
+        sdev = (lambda i: None) if shifts_dev is None else (lambda i: shifts_dev[i * nl:(i + 1) * nl])
+        losses.zero_()
+        if sample_z:
+            z.normal_()                                                    # generator.py:197-199 on the device
         Dopt.zero_grad()
         rside = _engine.side_stream(dev, 2)
         lane = 1 if rside is not None else 0
+        fwd_real_done = None
         with _engine.on_side(rside):
-            _, c = de.forward(clean, noisy, sh_real, training=True, lane=lane)
-            fwd_real_done = torch.cuda.Event() if rside is not None else None
-            if fwd_real_done is not None:
+            _, c = de.forward(clean, noisy, shifts3[0], training=True, lane=lane, shifts_dev=sdev(0))
+            if rside is not None:
+                fwd_real_done = torch.cuda.Event()
                 fwd_real_done.record()
             de.backward(c, 1.0, 1.0, param_grads=True, loss_out=lptr(0))
         Genh, gctx = ge.forward(noisy, z)
         if fwd_real_done is not None:
             # BatchNorm running statistics are updated real pass first, fake pass second (model.py:297,303)
             torch.cuda.current_stream().wait_event(fwd_real_done)
-        _, c = de.forward(Genh, noisy, sh_fake, training=True)
+        _, c = de.forward(Genh, noisy, shifts3[1], training=True, shifts_dev=sdev(1))
         de.backward(c, 0.0, 1.0, param_grads=True, loss_out=lptr(1))
         _engine.join_side(rside)
         if lane == 1:
             de.merge_lane_grads()
-        Dopt.step(allreduce_grads(de))                                   # model.py:308
-        # (3) G update against the UPDATED D (model.py:313-321)
+        return Genh, gctx
+
+    def _seg_g(self, clean, noisy, Genh, gctx, shifts3, shifts_dev, losses, l1_weight, Gopt, Dopt, dscale):
+        """D optimiser step (model.py:308), then the G update against the UPDATED D (model.py:313-320)."""
+        ge, de = self.G.engine, self.D.engine
+        B, _, L = clean.shape
+        dev = clean.device
+        nl = len(self.D.enc_blocks)
+        lptr = lambda i: C.c_void_p(losses.data_ptr() + 4 * i)
+        Dopt.step(dscale)
         Gopt.zero_grad()
-        sh = shifts3[2] if shifts3 is not None else draw_phase_shifts(nl, self.D.phase_shift)
-        _, c = de.forward(Genh, noisy, sh, training=True, twins=False)    # no weight gradients in this pass
+        sdev = None if shifts_dev is None else shifts_dev[2 * nl:3 * nl]
+        _, c = de.forward(Genh, noisy, shifts3[2], training=True, twins=False, shifts_dev=sdev)   # no weight gradients here
         gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
         de.backward(c, 1.0, 1.0, param_grads=False, input_grad=gy, loss_out=lptr(2))
-        if self.reg_loss_name != 'l1_loss':
-            raise NotImplementedError("reg_loss %r: only 'l1_loss' (train.py:179 default) is built" % self.reg_loss_name)
-        _lib.call("sg_l1_loss_bwd", _p(Genh), _p(clean.contiguous()), B * L, float(l1_weight), lptr(3), _p(gy), 1, st)
+        _lib.call("sg_l1_loss_bwd", _p(Genh), _p(clean.contiguous()), B * L, float(l1_weight), lptr(3), _p(gy), 1,
+                  _stream())
         ge.backward(gctx, gy)
-        Gopt.step(allreduce_grads(ge))                                   # model.py:321
-        return losses
+
+    # -- CUDA graphs ------------------------------------------------------------------------------
+    def _graph_state(self, clean, noisy, Gopt, Dopt, l1_weight, sample_z):
+        """Static tensors + graphs of the step for this (shape, hyper-parameter) key, or None while the
+        eager schedule should run (graphs disabled, profiling active, optimiser with a per-step scalar,
+        or fewer than GRAPH_WARMUP eager steps seen for the key)."""
+        if not _engine.GRAPHS or _engine.PROFILE is not None or _lib.call_profile is not None:
+            return None
+        if Gopt.kind != 'rmsprop' or Dopt.kind != 'rmsprop' or not _engine.wave_on_tensor_cores():
+            return None                         # Adam passes its step count by value
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        ge, de = self.G.engine, self.D.engine
+        world = _dist().get_world_size() if _dist() is not None else 1
+        B, _, L = clean.shape
+        key = (B, L, float(l1_weight), Gopt.param_groups[0]['lr'], Dopt.param_groups[0]['lr'], world,
+               ge.flat.data_ptr() if ge.flat is not None else 0, de.flat.data_ptr() if de.flat is not None else 0,
+               _engine.OVERLAP, self.z_device, bool(sample_z), ge.backend, de.backend)
+        cache = self.__dict__.setdefault('_step_graphs', {})
+        st = cache.get(key)
+        if st is None:
+            if len(cache) >= 4:
+                cache.clear()                   # hyper-parameters that change every step: stay eager-ish
+            st = cache[key] = types.SimpleNamespace(seen=0, graphs=None)
+        st.seen += 1
+        if st.seen <= _engine.GRAPH_WARMUP:
+            return None
+        if st.graphs is None and not hasattr(st, 'clean'):
+            dev = clean.device
+            nl = len(self.D.enc_blocks)
+            st.clean = torch.empty_like(clean)
+            st.noisy = torch.empty_like(noisy)
+            st.z = torch.empty(B, self.G.z_dim, L // (4 ** len(self.G.enc_blocks)), device=dev)
+            st.losses = torch.zeros(4, dtype=torch.float32, device=dev)
+            st.shifts = torch.zeros(3 * nl, dtype=torch.int32, device=dev)
+            st.launches = 0
+        return st
+
+    def _capture_step(self, st, sample_z, shifts3, l1_weight, Gopt, Dopt):
+        """Runs one step under stream capture (the captured work is NOT executed: the three graphs are
+        replayed right after) -- see train_step."""
+        ge, de = self.G.engine, self.D.engine
+        dscale = 1.0 / (_dist().get_world_size() if _dist() is not None else 1)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        t_d, t_g = Dopt.t, Gopt.t
+        with torch.cuda.graph(g1):
+            Genh, gctx = self._seg_d(st.clean, st.noisy, st.z, shifts3, st.shifts, st.losses, Dopt, sample_z=sample_z)
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self._seg_g(st.clean, st.noisy, Genh, gctx, shifts3, st.shifts, st.losses, l1_weight, Gopt, Dopt, dscale)
+        with torch.cuda.graph(g3, pool=g1.pool()):
+            Gopt.step(dscale)
+        Dopt.t, Gopt.t = t_d, t_g               # capture only recorded the launches
+        st.launches = _lib.launch_count - n0
+        _lib.launch_count = n0
+        st.keep = (Genh, gctx)                  # tensors of the graphs' private pool referenced by later nodes
+        st.graphs = (g1, g2, g3)
+        # the step itself: replay
+        g1.replay()
+        allreduce_grads(de)
+        g2.replay()
+        allreduce_grads(ge)
+        g3.replay()
+        Dopt.t += 1
+        Gopt.t += 1
+        ge.mark_dirty()
+        _lib.launch_count += st.launches
+        if sample_z and not hasattr(self.G, 'z'):
+            self.G.z = st.z
 
     def train(self, opts, dloader, criterion, l1_init, l1_dec_step, l1_dec_epoch, log_freq, va_dloader=None,
               device='cuda'):

@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, n), "header declares %s but the library does not export it" % n
     from segan_pytorch_b200 import _lib
     assert sorted(set(_lib.EXPORTS)) == names
-    assert lib.sg_abi_version() == 1
+    assert lib.sg_abi_version() == 2
 
 
 def test_ctypes_structs_match_c_layout(lib):

@@ -342,8 +342,15 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo, variant):
     h = torch.zeros(B, L + 2 * halo, C_, dtype=torch.float16, device=DEV)
     hb = torch.zeros(B, L + 2 * halo, C_, dtype=torch.bfloat16, device=DEV)
     abf = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
-    _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, roll, halo, _p(h), _p(hb), _p(abf),
+    _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, roll, None, halo, _p(h), _p(hb), _p(abf),
               _stream())
+    # the same launch with the shift read from device memory (CUDA-graph mode): identical result
+    roll_dev = torch.tensor([7, roll], dtype=torch.int32, device=DEV)
+    rptr = C.c_void_p(roll_dev.data_ptr() + 4)
+    h_d = torch.zeros_like(h)
+    _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, 0, rptr, halo, _p(h_d), None, None,
+              _stream())
+    assert torch.equal(h_d, h)
     # reference: NCL fp32
     an = a.float().permute(0, 2, 1).cpu().requires_grad_(True)
     gm, bt, sl = (t.cpu().clone().requires_grad_(True) for t in (gamma, beta, slope))
@@ -362,7 +369,7 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo, variant):
     yr.backward(gh.float().permute(0, 2, 1).cpu())
     red = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
     ga = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
-    _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+    _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
               _p(slope), 1, _p(red), None, _stream())
     # no-BN variant with a skip gradient on the pre-activation (Generator encoder), strided sources
     gsk = (torch.randn(B, L, 2 * C_, generator=g)).to(torch.bfloat16).to(DEV)
@@ -374,19 +381,26 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo, variant):
     red2 = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
     ga2 = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
     gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * C_)
-    _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, gadd_ptr, 2 * C_, _p(a), SG_F16, B, L, C_, None, None,
+    _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, None, gadd_ptr, 2 * C_, _p(a), SG_F16, B, L, C_, None, None,
               _p(slope), 1, _p(red2), _p(ga2), _stream())
     torch.cuda.synchronize()
     assert rel_err(ga2.float().permute(0, 2, 1).cpu(), a2.grad) <= 1e-2
     rs2 = red2.sum(0)
     assert rel_err(rs2[0].float().cpu(), sl2.grad) <= 2e-3
     assert rel_err(rs2[1].float().cpu(), a2.grad.sum((0, 2))) <= 2e-3
-    _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+    _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
               _p(slope), 1, _p(red), 1, _p(ga), _stream())
+    ga_d = torch.zeros_like(ga)
+    _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, 0, rptr, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+              _p(slope), 1, _p(red), 1, _p(ga_d), _stream())
+    red_d = torch.zeros_like(red)
+    _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, rptr, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+              _p(slope), 1, _p(red_d), None, _stream())
     gp = torch.ones(3, C_, device=DEV)
     _lib.call("sg_stat_grads", _p(red), C_, 3, _p(gp[0]), None, _p(gp[2]), _stream())
     torch.cuda.synchronize()
     rs = red.sum(0)
+    assert torch.equal(ga_d, ga) and rel_err(red_d.sum(0), rs) <= 1e-6
     assert rel_err(gp[0] - 1, rs[0].float()) <= 1e-6 and rel_err(gp[2] - 1, rs[2].float()) <= 1e-6
     assert float((gp[1] - 1).abs().max()) == 0.0
     assert rel_err(rs[0].float().cpu(), sl.grad) <= 2e-3

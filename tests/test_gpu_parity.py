@@ -205,6 +205,54 @@ def test_overlapped_step_matches_serial_step():
         assert err_g <= 4 * floor_g + 1e-3, (step, err_g, floor_g)
 
 
+def test_graph_replayed_steps_match_eager_steps():
+    """SEGAN.train_step captures the step into CUDA graphs after engine.GRAPH_WARMUP eager steps (phase
+    shifts then come from a device table) and replays it.  Four steps from the same state and inputs:
+    eager vs eager gives the noise floor (fp32-atomics summation order amplified by RMSprop's sign-like
+    steps), graph-replayed steps are held to it; the replayed steps must also really be replays."""
+    from segan_pytorch_b200 import engine as E
+    from tests.util import load_opts
+    t = golden("train_step_b4.npz")
+    B = t["clean"].shape[0]
+    clean = torch.from_numpy(t["clean"]).unsqueeze(1).to(DEV)
+    noisy = torch.from_numpy(t["noisy"]).unsqueeze(1).to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    zs = [torch.randn(B, 1024, 16, generator=gen).to(DEV) for _ in range(4)]
+    random.seed(11)
+    shifts = [[O.draw_phase_shifts(5, 5) for _ in range(3)] for _ in range(4)]
+
+    def run(graphs):
+        prev = E.GRAPHS
+        E.GRAPHS = graphs
+        try:
+            s = build_segan(batch_size=B).to(DEV)
+            s.G.train()
+            s.D.train()
+            Gopt, Dopt = s.build_optimizers(load_opts(batch_size=B))
+            out = []
+            for i in range(4):
+                losses = s.train_step(clean, noisy, Gopt, Dopt, 100.0, z=zs[i], shifts3=shifts[i])
+                torch.cuda.synchronize()
+                out.append((losses.tolist(), s.G.engine.grad.clone(), s.D.engine.grad.clone()))
+            n_graphs = sum(1 for v in getattr(s, "_step_graphs", {}).values() if v.graphs is not None)
+            return out, n_graphs, Gopt.t
+        finally:
+            E.GRAPHS = prev
+
+    (e1, n1, _), (e2, n2, _), (gr, n3, t3) = run(False), run(False), run(True)
+    assert n1 == 0 and n2 == 0 and n3 == 1 and t3 == 4
+    for step in range(4):
+        (l0, gG0, gD0), (l1, gG1, gD1), (l2, gG2, gD2) = e1[step], e2[step], gr[step]
+        floor_l = max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(l0, l1))
+        floor_g = max(rel_err(gG1, gG0), rel_err(gD1, gD0))
+        err_l = max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(l0, l2))
+        err_g = max(rel_err(gG2, gG0), rel_err(gD2, gD0))
+        print("step %d: eager-vs-eager loss %.2e grad %.2e | graph-vs-eager loss %.2e grad %.2e"
+              % (step, floor_l, floor_g, err_l, err_g))
+        assert err_l <= 4 * floor_l + 1e-4, (step, l0, l2)
+        assert err_g <= 4 * floor_g + 1e-3, (step, err_g, floor_g)
+
+
 def test_train_loop_with_prefetcher_matches_manual_steps(tmp_path):
     """SEGAN.train (train.py:95-98 path) over a DataLoader, batches staged by DevicePrefetcher one step
     ahead on a copy stream, against the same steps fed by blocking .to(device) copies."""

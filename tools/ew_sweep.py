@@ -98,15 +98,15 @@ for C_, L in SHAPES:
     nh = B * (L + 2 * halo) * C_ * 2
     kernels = {
         "bn_stats": (2, lambda: _lib.call("sg_bn_stats", _p(a), SG_F16, B * L, C_, _p(stats), _stream()), n),
-        "act_fwd(D: h+twin)": (1, lambda: _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, roll, halo,
+        "act_fwd(D: h+twin)": (1, lambda: _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, roll, None, halo,
                                                  _p(h), _p(hb), None, _stream()), n + 2 * nh),
-        "act_fwd(D3: h)": (1, lambda: _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, roll, halo,
+        "act_fwd(D3: h)": (1, lambda: _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, roll, None, halo,
                                              _p(h), None, None, _stream()), n + nh),
-        "bwd_reduce(D)": (3, lambda: _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_,
+        "bwd_reduce(D)": (3, lambda: _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, None, 0, _p(a), SG_F16, B, L, C_,
                                             _p(ss), _p(mi), _p(slope), 1, _p(red), None, _stream()), n + nh),
-        "bwd_apply(D)": (4, lambda: _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, 0, _p(a), SG_F16, B, L, C_,
+        "bwd_apply(D)": (4, lambda: _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, roll, None, None, 0, _p(a), SG_F16, B, L, C_,
                                            _p(ss), _p(mi), _p(slope), 1, _p(red), 1, _p(ga), _stream()), 2 * n + nh),
-        "bwd_reduce(G enc: +skip,+out)": (3, lambda: _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, gadd_ptr, 2 * C_, _p(a),
+        "bwd_reduce(G enc: +skip,+out)": (3, lambda: _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, None, gadd_ptr, 2 * C_, _p(a),
                                                             SG_F16, B, L, C_, None, None, _p(slope), 1, _p(red), _p(ga),
                                                             _stream()), 3 * n + nh),
     }
