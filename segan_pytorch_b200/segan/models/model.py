@@ -306,8 +306,16 @@ class SEGAN(Model):
             st.z.copy_(z, non_blocking=True)
             if not hasattr(self.G, 'z'):
                 self.G.z = z
-        flat = [int(v) for sh in shifts3 for v in sh]
-        st.shifts.copy_(torch.tensor(flat, dtype=torch.int32).pin_memory(), non_blocking=True)
+        # this step's phase shifts -> device table, through a ring of pinned rows (a fresh pinned allocation
+        # per step would hit cudaHostAlloc whenever the host runs ahead of the device)
+        i = st.ring_i % st.ring.shape[0]
+        st.ring_i += 1
+        if st.ring_ev[i] is not None:
+            st.ring_ev[i].synchronize()        # the copy that last used this row (ring-size steps ago) is done
+        st.ring[i].copy_(torch.tensor([int(v) for sh in shifts3 for v in sh], dtype=torch.int32))
+        st.shifts.copy_(st.ring[i], non_blocking=True)
+        st.ring_ev[i] = torch.cuda.Event()
+        st.ring_ev[i].record()
         if st.graphs is None:
             self._capture_step(st, z is None, shifts3, l1_weight, Gopt, Dopt)
         else:
@@ -413,6 +421,9 @@ class SEGAN(Model):
             st.z = torch.empty(B, self.G.z_dim, L // (4 ** len(self.G.enc_blocks)), device=dev)
             st.losses = torch.zeros(4, dtype=torch.float32, device=dev)
             st.shifts = torch.zeros(3 * nl, dtype=torch.int32, device=dev)
+            st.ring = torch.zeros(32, 3 * nl, dtype=torch.int32).pin_memory()
+            st.ring_ev = [None] * 32
+            st.ring_i = 0
             st.launches = 0
         return st
 
