@@ -142,7 +142,7 @@ def cpu_reference_steps(steps, warmup, B):
     return B * len(times) / total, total / len(times), torch.get_num_threads()
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -161,13 +161,27 @@ def run_reference_arm(args):
         "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout: native libraries (NCCL prints its version banner
+    there) are pointed at stderr for the whole run; the returned writer emits on the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text):
+        sys.stdout.flush()
+        os.write(real, (text + "\n").encode())
+    return emit
+
+
 def main():
+    emit = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -182,7 +196,7 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, emit)
 
     if args.backend:
         os.environ["SEGAN_B200_BACKEND"] = args.backend
@@ -403,7 +417,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -116,6 +116,8 @@ typedef struct sg_tapgemm_f {
   int32_t batch;
   int32_t ksplit;     /* >1 only with out_dtype == SG_F32 */
   int32_t backend;    /* SG_BACKEND_* */
+  int32_t tile_n;     /* N tile of the tcgen05 kernel: 0 = widest of 256/128/64 dividing n_hi-n_lo; 64|128|256 =
+                         narrower tiles for the tail of a launch split against wave quantisation (148 SMs) */
 } sg_tapgemm_f;
 
 int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream);

@@ -890,6 +890,8 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   p.m_tiles_per_b = (rows_m + p.TR - 1) / p.TR;
   p.b_tiles = (q->batch + p.TB - 1) / p.TB;
   p.TN = (ncols % 256 == 0) ? 256 : (ncols % 128 == 0 ? 128 : 64);
+  if ((q->tile_n == 64 || q->tile_n == 128 || q->tile_n == 256) && ncols % q->tile_n == 0 && q->tile_n < p.TN)
+    p.TN = q->tile_n;      // narrow tiles: the caller split this launch off as the tail of a larger one
   // (measured: 128-wide tiles to soften wave quantisation lose more to the 256-cycle issue
   //  cadence and doubled A traffic than they gain -- 8.7 -> 10.6 ms/step -- so stay at 256)
   p.n_tiles = ncols / p.TN;

@@ -186,26 +186,88 @@ class _Prof(object):
         return False
 
 
+NUM_SMS = 148
+SPLIT_WAVES = os.environ.get("SEGAN_B200_WAVE_SPLIT", "1").lower() not in ("0", "off", "no", "false")
+
+
+def _f_tiling(rows_m, batch, ncols, tile_n=0):
+    """Mirror of tapgemm_f_tc_launch's tiling: (TB, m_tiles_per_b, TN, CTA-pair tiles, batch granularity of a
+    pair-aligned group)."""
+    if rows_m >= 128:
+        tb, mpb = 1, (rows_m + 127) // 128
+    else:
+        tb, mpb = max(1, min(128 // rows_m, batch, 256)), 1
+    tn = 256 if ncols % 256 == 0 else (128 if ncols % 128 == 0 else 64)
+    if tile_n in (64, 128, 256) and ncols % tile_n == 0 and tile_n < tn:
+        tn = tile_n
+    m_tiles = mpb * ((batch + tb - 1) // tb)
+    tiles = ((m_tiles + 1) // 2) * (ncols // tn)
+    gran = 2 * tb if mpb % 2 else tb          # batch elements per group of whole CTA pairs
+    return tb, mpb, tn, tiles, gran
+
+
+def _plan_f_split(rows_m, batch, ncols):
+    """Wave quantisation: batch 300 puts most layers just over a multiple of the 74 CTA pairs (300 pair
+    tiles = 4.05 waves -> 5).  Returns (B1, tail_tile_n): the launch is split into the first B1 batch
+    elements as whole waves of full-width tiles and the rest as one short wave of narrow tiles; (batch, 0)
+    when splitting does not pay."""
+    pairs_hw = NUM_SMS // 2
+    tb, mpb, tn, tiles, gran = _f_tiling(rows_m, batch, ncols)
+    waves = -(-tiles // pairs_hw)
+    if tiles <= pairs_hw or tiles % pairs_hw == 0 or waves > 12:
+        return batch, 0
+    per_gran = _f_tiling(rows_m, gran, ncols)[3]              # tiles of one pair-aligned batch group
+    full_tiles = (tiles // pairs_hw) * pairs_hw
+    b1 = min(batch, (full_tiles // per_gran) * gran)
+    if b1 <= 0 or b1 >= batch:
+        return batch, 0
+    best = None
+    for t, penalty in ((64, 1.3), (128, 1.15), (256, 1.0)):
+        if ncols % t or t > tn:
+            continue
+        tt = _f_tiling(rows_m, batch - b1, ncols, t)[3]
+        cost = -(-tt // pairs_hw) * (t / float(tn)) * penalty
+        if best is None or cost < best[0]:
+            best = (cost, t)
+    head_waves = -(-_f_tiling(rows_m, b1, ncols)[3] // pairs_hw)
+    if head_waves + best[0] + 0.05 >= waves * 0.97:
+        return batch, 0
+    return b1, (best[1] if best[1] < tn else 0)
+
+
 def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dtype, out_rows, out_halo,
           m_lo, m_hi, batch, bias=None, bias_mod=0, n_lo=0, n_hi=None, d_lo=-4, d_hi=4, w_tap0=0,
           out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0):
-    q = TapGemmF()
-    q.a0, q.a1 = _p(a0), _p(a1)
-    q.a0_c = kc if a0_c is None else a0_c
-    q.a1_c = a1_c
-    q.a_rows, q.a_halo, q.a_dtype = a_rows, a_halo, a_dtype
-    q.w, q.w_dtype, q.w_tap0 = _p(w), w_dtype, w_tap0
-    q.kc, q.nc, q.d_lo, q.d_hi = kc, nc, d_lo, d_hi
-    for i in range(9):
-        q.tap_k_lo[i], q.tap_k_hi[i], q.tap_n_lo[i], q.tap_n_hi[i] = taps[0][i], taps[1][i], taps[2][i], taps[3][i]
-    q.out, q.out_ld, q.out_col0 = _p(out), out_ld, out_col0
-    q.out_dtype, q.out_rows, q.out_halo = out_dtype, out_rows, out_halo
-    q.m_lo, q.m_hi, q.n_lo, q.n_hi = m_lo, m_hi, n_lo, (nc if n_hi is None else n_hi)
-    q.bias, q.bias_mod = _p(bias), bias_mod
-    q.batch, q.ksplit = batch, ksplit
-    q.backend = default_backend() if backend is None else backend
-    with _Prof("tapgemm_f", _tap_flops(taps, d_lo, d_hi, q.n_lo, q.n_hi, (m_hi - m_lo) * batch)):
-        _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
+    n_hi = nc if n_hi is None else n_hi
+    a0_c = kc if a0_c is None else a0_c
+    backend = default_backend() if backend is None else backend
+    b1, tail_tn = batch, 0
+    if SPLIT_WAVES and backend == BACKEND_TCGEN05 and ksplit == 1 and batch > 1:
+        b1, tail_tn = _plan_f_split(m_hi - m_lo, batch, n_hi - n_lo)
+    esz = 4 if out_dtype == SG_F32 else 2
+    old = (out_ld if out_ld > 0 else nc)
+    for b_off, nb, tn in ((0, b1, 0), (b1, batch - b1, tail_tn)):
+        if nb <= 0:
+            continue
+        q = TapGemmF()
+        a_stride = (a_rows + 2 * a_halo) * 2
+        q.a0 = _p(a0) if b_off == 0 else C.c_void_p(a0.data_ptr() + b_off * a_stride * a0_c)
+        q.a1 = _p(a1) if (a1 is None or b_off == 0) else C.c_void_p(a1.data_ptr() + b_off * a_stride * a1_c)
+        q.a0_c, q.a1_c = a0_c, a1_c
+        q.a_rows, q.a_halo, q.a_dtype = a_rows, a_halo, a_dtype
+        q.w, q.w_dtype, q.w_tap0 = _p(w), w_dtype, w_tap0
+        q.kc, q.nc, q.d_lo, q.d_hi = kc, nc, d_lo, d_hi
+        for i in range(9):
+            q.tap_k_lo[i], q.tap_k_hi[i], q.tap_n_lo[i], q.tap_n_hi[i] = taps[0][i], taps[1][i], taps[2][i], taps[3][i]
+        q.out = _p(out) if b_off == 0 else C.c_void_p(out.data_ptr() + b_off * (out_rows + 2 * out_halo) * old * esz)
+        q.out_ld, q.out_col0 = out_ld, out_col0
+        q.out_dtype, q.out_rows, q.out_halo = out_dtype, out_rows, out_halo
+        q.m_lo, q.m_hi, q.n_lo, q.n_hi = m_lo, m_hi, n_lo, n_hi
+        q.bias, q.bias_mod = _p(bias), bias_mod
+        q.batch, q.ksplit = nb, ksplit
+        q.backend, q.tile_n = backend, tn
+        with _Prof("tapgemm_f", _tap_flops(taps, d_lo, d_hi, q.n_lo, q.n_hi, (m_hi - m_lo) * nb)):
+            _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
 
 
 def run_w(g, g_rows, g_dtype, a0, a1, a_rows, a_halo, a_dtype, kc, nc, taps, dw, batch, d_lo=-4, d_hi=4,
@@ -226,11 +288,39 @@ def run_w(g, g_rows, g_dtype, a0, a1, a_rows, a_halo, a_dtype, kc, nc, taps, dw,
         _lib.call("sg_tapgemm_w_run", C.byref(q), _stream())
 
 
-def wgrad_ksplit(total_positions, n_tiles):
-    """Position-range splits so that a weight-gradient tap-GEMM fills ~2 waves of 148 SMs."""
+def wgrad_ksplit(total_positions, n_tiles, taps=None, kc=None, nc=None, d_lo=-4, d_hi=4):
+    """Position-range splits of a weight-gradient tap-GEMM.  With the tap table the number of non-empty
+    (tap, n, kc) tiles is counted exactly (mirror of tapgemm_w_tc's decode()) and the split count is the
+    one that minimises waves / splits over the 148 SMs (297 tiles = 2.007 waves would run as 3); without
+    it: about two waves."""
     steps = max(1, total_positions // 64)
-    want = max(1, (2 * 148 + n_tiles - 1) // max(1, n_tiles))
-    return int(max(1, min(want, steps)))
+    if taps is None:
+        want = max(1, (2 * NUM_SMS + n_tiles - 1) // max(1, n_tiles))
+        return int(max(1, min(want, steps)))
+    tk = 256 if kc >= 256 else kc
+    valid = 0
+    for d in range(d_lo, d_hi + 1):
+        i = d + 4
+        for n0 in range(0, nc, 128):
+            if n0 + 128 <= taps[2][i] or n0 >= taps[3][i]:
+                continue
+            for k0 in range(0, kc, tk):
+                if k0 + tk <= taps[0][i] or k0 >= taps[1][i]:
+                    continue
+                valid += 1
+    valid = max(1, valid)
+    # time ~ waves / ks (a tile's work shrinks with the split count); small preferences: at least ~1.5 waves
+    # (so a CTA's epilogue overlaps its next tile) and fewer splits (every split adds a pass of fp32 atomics)
+    best = None
+    for ks in range(1, min(steps, max(1, -(-8 * NUM_SMS // valid))) + 1):
+        tiles = valid * ks
+        cost = (-(-tiles // NUM_SMS)) / float(ks)
+        if tiles < 1.5 * NUM_SMS:
+            cost *= 1.15
+        cost *= 1.0 + 0.004 * ks
+        if best is None or cost < best[0] - 1e-12:
+            best = (cost, ks)
+    return best[1]
 
 
 class _Buffers:
@@ -583,7 +673,8 @@ class GeneratorEngine(_NetEngine):
                 dwp.zero_()
                 n_tiles = 9 * (4 * cout // 128) * max(1, cin // 256)
                 run_w(g_ad, lin, SG_BF16, s0, s1, lin, 0, SG_BF16, cin, 4 * cout, taps, dwp, B,
-                      ksplit=wgrad_ksplit(B * lin, n_tiles), a0_c=c0, a1_c=c1, backend=self.backend)
+                      ksplit=wgrad_ksplit(B * lin, n_tiles, taps, cin, 4 * cout), a0_c=c0, a1_c=c1,
+                      backend=self.backend)
                 alpha = self.alpha_for_dec(l)
                 galpha = self.gview("alpha_%d.skip_k" % (nl - 1 - l)).view(-1) if l > 0 else None
                 _lib.call("sg_unpack_wgrad", 1, _p(dwp), cout, cin, 0,
@@ -636,7 +727,7 @@ class GeneratorEngine(_NetEngine):
                 dwp_l.zero_()
                 n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
                 run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout, taps, dwp_l, B,
-                      ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
+                      ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps, 4 * cin, cout), backend=self.backend)
                 _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
                           _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
             g_hp = buf.get("g.ghp%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
@@ -887,9 +978,9 @@ class DiscriminatorEngine(_NetEngine):
                 with on_side(side):
                     dwp_l.zero_()
                     n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
-                    run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout,
-                          tap_ranges("conv_fwd", cin, 4 * cin, cout), dwp_l, B,
-                          ksplit=wgrad_ksplit(B * Lq[l], n_tiles), backend=self.backend)
+                    taps_w = tap_ranges("conv_fwd", cin, 4 * cin, cout)
+                    run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout, taps_w, dwp_l, B,
+                          ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps_w, 4 * cin, cout), backend=self.backend)
                     _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
                               _p(gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
             g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)

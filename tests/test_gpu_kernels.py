@@ -143,6 +143,70 @@ def test_tapgemm_f(backend, case):
         assert float(out[:, :, :n_lo].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("sms,case,B", [(8, "deconv_cat", 17), (8, "deconv_cat", 21), (8, "small_rows", 33),
+                                        (8, "dgrad_halo", 9), (8, "dgrad_halo", 10)])
+def test_tapgemm_f_wave_split(monkeypatch, sms, case, B):
+    """engine.run_f splits a launch whose tile count is just over a multiple of the CTA pairs into whole
+    waves of full-width tiles plus a tail of narrow tiles on a batch sub-range (pointer offsets, tile_n
+    hint).  The SM count is patched down so that small test shapes take that path."""
+    monkeypatch.setattr(E, "NUM_SMS", sms)
+    monkeypatch.setattr(E, "SPLIT_WAVES", True)
+    g = _gen(4)
+    a1, a1_c, bias = None, 0, None
+    if case == "deconv_cat":
+        cout, R, halo = 64, 64, 0
+        kc, nc = 256, 4 * cout
+        w, taps = _packed_random("deconv_fwd", cout, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1_c = 128
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        bias = torch.randn(cout, generator=g).to(DEV)
+        adt, odt, tdt = SG_F16, SG_F16, torch.float16
+    elif case == "small_rows":
+        cin, cout, R, halo = 128, 512, 16, 4
+        kc, nc = 4 * cin, cout
+        w, taps = _packed_random("conv_fwd", cin, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        adt, odt, tdt = SG_F16, SG_F16, torch.float16
+    else:   # conv dgrad into a halo'd consumer view, bf16
+        cin, cout, R, halo = 64, 128, 160, 0
+        kc, nc = cout, 4 * cin
+        w, taps = _packed_random("conv_dgrad", cin, kc, nc, g, torch.bfloat16)
+        a0 = torch.randn(B, R, kc, generator=g).to(torch.bfloat16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = -4, R + 4, R, 4
+        adt, odt, tdt = SG_BF16, SG_BF16, torch.bfloat16
+    b1, tn = E._plan_f_split(m_hi - m_lo, B, nc)
+    assert 0 < b1 < B, (b1, tn)                       # the split path is what this test exercises
+    out = torch.zeros(B, out_rows + 2 * out_halo, nc, dtype=tdt, device=DEV)
+    E.run_f(a0, a1, R, halo, adt, w, adt, kc, nc, taps, out, odt, out_rows, out_halo, m_lo, m_hi, B,
+            bias=bias, bias_mod=(bias.numel() if bias is not None else 0), backend=BACKEND_TCGEN05,
+            a0_c=a0.shape[-1], a1_c=a1_c)
+    torch.cuda.synchronize()
+    a_full = a0.float() if a1 is None else torch.cat((a0.float(), a1.float()), -1)
+    ref = _ref_f(a_full, halo, w, m_lo, m_hi)
+    if bias is not None:
+        ref = ref + bias.repeat(nc // bias.numel())
+    got = out[:, out_halo + m_lo: out_halo + m_hi, :].float()
+    err = max_abs(got, ref)
+    assert err <= 3e-2 * max(1.0, float(ref.abs().max())), (case, sms, b1, tn, err)
+
+
+def test_wgrad_split_plan_fills_whole_waves():
+    """The weight-gradient split count is chosen from the exact number of non-empty (tap, n, kc) tiles."""
+    fm = [64, 128, 256, 512, 1024]
+    for l in range(1, 5):
+        cin, cout, Lq = fm[l - 1], fm[l], 16384 // 4 ** (l + 1)
+        taps = E.tap_ranges("conv_fwd", cin, 4 * cin, cout)
+        ks = E.wgrad_ksplit(300 * Lq, 0, taps, 4 * cin, cout)
+        tk = 256 if 4 * cin >= 256 else 4 * cin
+        valid = sum(1 for d in range(9) for n0 in range(0, cout, 128) for k0 in range(0, 4 * cin, tk)
+                    if not (n0 + 128 <= taps[2][d] or n0 >= taps[3][d] or k0 + tk <= taps[0][d] or k0 >= taps[1][d]))
+        tiles = valid * ks
+        assert tiles / float(-(-tiles // 148) * 148) >= 0.8, (l, ks, tiles)
+
+
 @pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
 @pytest.mark.parametrize("case", ["conv", "deconv_cat", "small_rows", "fc"])
 def test_tapgemm_w(backend, case):
