@@ -42,6 +42,18 @@ def measured_peaks():
     return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_v4_ncu_tapgemm_f.json: dram__bytes_read.sum + dram__bytes_write.sum, average of the captured
+    launches), or None when the summary is missing."""
+    p = os.path.join(ROOT, "profiles", "r1_v4_ncu_tapgemm_f.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["dram_bytes_per_launch_avg"])
+    except Exception:
+        return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -381,7 +393,7 @@ def main():
         sec, fl, n = agg[dom]
         ach = fl / sec / 1e12
         roof = {"kernel": dom + "_tc (tcgen05 tap-GEMM)", "bound": "tensor", "achieved": ach, "peak": peaks["tflops"],
-                "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": ncu_traffic(),
                 "peak_source": peaks["src"], "avg_launch_ms": sec * 1e3 / n,
                 "alg_flops_per_launch": fl / n, "kernels": kern, "abi_calls": call_ms,
                 "profiled_ms_per_step": ms_prof / args.steps,

@@ -187,7 +187,10 @@ class _Prof(object):
 
 
 NUM_SMS = 148
-SPLIT_WAVES = os.environ.get("SEGAN_B200_WAVE_SPLIT", "1").lower() not in ("0", "off", "no", "false")
+# Off by default: measured per layer at batch 300 (profiles/r1_v4_layers_split.txt) the narrow-tile tail costs
+# about as much as the wave it replaces -- a tile's A-operand fill does not shrink with its width, so a
+# 64-wide tile is shared-memory-fill bound -- and only 1 of 12 shapes gained.
+SPLIT_WAVES = os.environ.get("SEGAN_B200_WAVE_SPLIT", "0").lower() not in ("0", "off", "no", "false")
 
 
 def _f_tiling(rows_m, batch, ncols, tile_n=0):

@@ -10,6 +10,7 @@ from segan_pytorch_b200._lib import SG_BF16, SG_F16
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 REP = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+COMPARE = len(sys.argv) > 3 and sys.argv[3] == "compare"      # time every shape with and without the wave split
 dev = "cuda"
 h = lambda *s: (torch.randn(*s, device=dev) * 0.5).half()
 b = lambda *s: (torch.randn(*s, device=dev) * 0.5).bfloat16()
@@ -19,14 +20,20 @@ def timeit(name, fn, flops):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(REP):
+    res = []
+    for split in ((True, False) if COMPARE else (E.SPLIT_WAVES,)):
+        E.SPLIT_WAVES = split
         fn()
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / REP
-    print("%-28s %8.3f ms  %7.1f TFLOP/s" % (name, ms, flops / ms / 1e9))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(REP):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        res.append(s.elapsed_time(e) / REP)
+    ms = res[0]
+    extra = ("   | unsplit %8.3f ms  %7.1f TFLOP/s" % (res[1], flops / res[1] / 1e9)) if COMPARE else ""
+    print("%-28s %8.3f ms  %7.1f TFLOP/s%s" % (name, ms, flops / ms / 1e9, extra))
 
 
 def conv_fwd(cin, cout, R):
@@ -82,7 +89,9 @@ if __name__ == "__main__":
     deconv_fwd(1024, 256, 64)
     deconv_fwd(512, 128, 256)
     deconv_fwd(256, 64, 1024)
+    conv_dgrad(512, 1024, 16)
     conv_dgrad(256, 512, 64)
+    conv_dgrad(128, 256, 256)
     conv_dgrad(64, 128, 1024)
     conv_wgrad(64, 128, 1024)
     conv_wgrad(128, 256, 256)
