@@ -64,8 +64,10 @@ int sg_abi_version(void);
 const char* sg_last_error(void);
 /* 1 if the loaded device is sm_100 class and the tcgen05 kernels can run */
 int sg_device_ok(void);
-/* 1 (default): forward-form tap-GEMMs run on CTA pairs (tcgen05 cta_group::2, 256-row tiles);
- * 0: single-CTA 128-row tiles.  Returns the previous setting. */
+/* Forward-form tap-GEMM kernel: 0 = single-CTA 128-row tiles; 1 = CTA pairs (tcgen05 cta_group::2, 256-row
+ * tiles); 2 = CTA pairs with the activation tile staged once per k-block and reused by all taps through
+ * row-shifted UMMA descriptors (layers with >= 128 rows per batch element; others fall back to 1).
+ * Returns the previous setting.  Environment default: SEGAN_B200_CTA_PAIR. */
 int sg_set_cta_pair(int on);
 /* Tuning knobs of the HBM-bound streaming kernels, one per kernel family (`kind`):
  *   SG_EW_ACT_FWD (sg_act_fwd), SG_EW_BN_STATS (sg_bn_stats), SG_EW_BWD_REDUCE (sg_act_bwd_reduce),

@@ -109,6 +109,8 @@ def load():
         fn.restype = C.c_int
     if lib.sg_abi_version() != 2:
         raise SeganB200Error("ABI version mismatch")
+    if os.environ.get("SEGAN_B200_CTA_PAIR", "") in ("0", "1", "2"):
+        lib.sg_set_cta_pair(int(os.environ["SEGAN_B200_CTA_PAIR"]))
     _lib = lib
     return lib
 

@@ -24,7 +24,7 @@ extern "C" const char* sg_last_error(void) { return g_err; }
 
 extern "C" int sg_set_cta_pair(int on) {
   const int prev = g_cta_pair;
-  g_cta_pair = on ? 1 : 0;
+  g_cta_pair = on < 0 ? 0 : (on > 2 ? 2 : on);
   return prev;
 }
 

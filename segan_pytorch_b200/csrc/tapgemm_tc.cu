@@ -632,6 +632,234 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// form F on CTA pairs with the A tile REUSED across the taps (tapgemm_f_tc3).
+// tapgemm_f_tc2 fills (A 16 KB + B 16 KB) per CTA and k-step and its UMMAs read 48 KB of shared memory per
+// SM and k-step: 156 B/clk against the 128 B/clk port, i.e. an 82 % cap on the tensor pipe (measured:
+// 1.92 of 2.38 PFLOP/s at boost clocks).  The 9 taps of a k-block read the SAME activation rows shifted by
+// d = -4..4, so here a k-block's rows [m0 + d_lo, m0 + 127 + d_hi] (<= 136 rows, 17 KB) are staged ONCE and
+// every tap's UMMA uses a descriptor whose start address is shifted by (d - d_lo) x 128 B (the 128B-swizzle
+// phase of a non-1024-aligned start goes into the descriptor's base-offset field, make_smem_desc).  Fill
+// per k-block drops from 9 x 32 KB to 17 KB + 9 x 16 KB.  Two rings: A (per k-block) and B (per tap).
+// Requires 128-row M tiles (rows_m >= 128) and ksplit == 1.
+// ------------------------------------------------------------------------------------------
+constexpr int A3_STAGES = 3;
+constexpr int A3_STAGE_BYTES = 136 * 128;            // 17 KB = 17 x 1024: stages stay 1024 B aligned
+constexpr int B3_STAGES = 8;
+constexpr int B3_STAGE_BYTES = 128 * 128;            // half of a 256-row weight tile
+constexpr int SMEM3_BYTES = A3_STAGES * A3_STAGE_BYTES + B3_STAGES * B3_STAGE_BYTES + 1024 + 512;
+constexpr int NUM_THREADS3 = 224;                    // warp 0: A producer, 1: MMA, 2..5: epilogue, 6: B producer
+
+struct SharedCtl3 {
+  uint64_t full_a[A3_STAGES];
+  uint64_t empty_a[A3_STAGES];
+  uint64_t full_b[B3_STAGES];
+  uint64_t empty_b[B3_STAGES];
+  uint64_t tmem_full[8];
+  uint64_t tmem_empty[8];
+  uint32_t tmem_base;
+};
+
+// tap `ti` contributes to (k-block kc0, N tile [n0, n0+TN))
+__device__ __forceinline__ bool f3_tap_valid(const FTcParams& p, int ti, int kc0, int n0) {
+  return !(n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) && kc0 >= p.tr.k_lo[ti] && kc0 < p.tr.k_hi[ti];
+}
+__device__ __forceinline__ uint32_t f3_tap_mask(const FTcParams& p, int kc0, int n0) {
+  uint32_t m = 0;
+  for (int d = p.d_lo; d <= p.d_hi; ++d)
+    if (f3_tap_valid(p, d + 4, kc0, n0)) m |= 1u << (d + 4);
+  return m;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS3, 1)
+tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+              const __grid_constant__ CUtensorMap tmW, const FTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + A3_STAGES * A3_STAGE_BYTES;
+  SharedCtl3* ctl = reinterpret_cast<SharedCtl3*>(smem_b + B3_STAGES * B3_STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
+    for (int s = 0; s < A3_STAGES; ++s) { mbar_init(&ctl->full_a[s], 1); mbar_init(&ctl->empty_a[s], 1); }
+    for (int s = 0; s < B3_STAGES; ++s) { mbar_init(&ctl->full_b[s], 1); mbar_init(&ctl->empty_b[s], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(&ctl->tmem_base, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  const int m_tiles = p.m_tiles_per_b * p.b_tiles;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total_tiles = m_pairs * p.n_tiles;
+  const int npairs = gridDim.x / 2;
+  const int pair_id = blockIdx.x / 2;
+  const int half_n = p.TN / 2;
+  const int a_rows_box = 128 + (p.d_hi - p.d_lo);
+  const uint32_t a_bytes = (uint32_t)a_rows_box * 128u;
+  const uint32_t b_bytes = (uint32_t)half_n * 128u;
+  const int nacc = 512 / p.TN;
+
+  if (warp == 0) {
+    // ================= A producer (both CTAs): one box per used k-block =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+        const int mp = tile % m_pairs;
+        const int nt = tile / m_pairs;
+        const int mt = 2 * mp + (int)rank;
+        const int b0 = mt / p.m_tiles_per_b;
+        const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * 128;
+        const int n0 = p.n_lo + nt * p.TN;
+        for (int kc0 = 0; kc0 < p.kc; kc0 += 64) {
+          if (f3_tap_mask(p, kc0, n0) == 0) continue;
+          mbar_wait(&ctl->empty_a[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&ctl->full_a[stage], 2u * a_bytes);
+          const bool in0 = kc0 < p.a0_c;
+          tma_load_3d_pair(smem + stage * A3_STAGE_BYTES, in0 ? &tmA0 : &tmA1, &ctl->full_a[stage],
+                           in0 ? kc0 : kc0 - p.a0_c, m0 + p.d_lo + p.a_halo, b0);
+          if (++stage == A3_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ================= B producer (both CTAs): this CTA's half of the weight tile, one box per tap ========
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+        const int nt = tile / m_pairs;
+        const int n0 = p.n_lo + nt * p.TN;
+        for (int kc0 = 0; kc0 < p.kc; kc0 += 64) {
+          const uint32_t mask = f3_tap_mask(p, kc0, n0);
+          for (int ti = p.d_lo + 4; ti <= p.d_hi + 4; ++ti) {
+            if (!((mask >> ti) & 1u)) continue;
+            mbar_wait(&ctl->empty_b[stage], phase ^ 1);
+            if (leader) mbar_expect_tx(&ctl->full_b[stage], 2u * b_bytes);
+            tma_load_3d_pair(smem_b + stage * B3_STAGE_BYTES, &tmW, &ctl->full_b[stage], kc0,
+                             (ti - p.w_tap0) * p.nc + n0 + (int)rank * half_n, 0);
+            if (++stage == B3_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && leader) {
+      int sa = 0; uint32_t pa = 0;
+      int sb = 0; uint32_t pb = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t smem_a0 = smem_u32(smem);
+      const uint32_t smem_b0 = smem_u32(smem_b);
+      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+        const int nt = tile / m_pairs;
+        const int n0 = p.n_lo + nt * p.TN;
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.TN);
+        uint32_t accum = 0;
+        for (int kc0 = 0; kc0 < p.kc; kc0 += 64) {
+          const uint32_t mask = f3_tap_mask(p, kc0, n0);
+          if (mask == 0) continue;
+          mbar_wait(&ctl->full_a[sa], pa);
+          const uint32_t a_base = smem_a0 + (uint32_t)sa * A3_STAGE_BYTES;
+          for (int ti = p.d_lo + 4; ti <= p.d_hi + 4; ++ti) {
+            if (!((mask >> ti) & 1u)) continue;
+            mbar_wait(&ctl->full_b[sb], pb);
+            tc_fence_after();
+            // rows [d - d_lo, d - d_lo + 128) of the staged A rows: start address shifted by whole 128 B lines
+            const uint64_t adesc = make_smem_desc(a_base + (uint32_t)(ti - 4 - p.d_lo) * 128u, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(smem_b0 + (uint32_t)sb * B3_STAGE_BYTES, 16, 1024);
+            umma_f16_pair(tmem_d, adesc, bdesc, p.idesc, accum);
+            umma_f16_pair(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
+            umma_f16_pair(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
+            umma_f16_pair(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
+            accum = 1u;
+            umma_commit_pair(&ctl->empty_b[sb]);       // frees the weight slot in both CTAs
+            if (++sb == B3_STAGES) { sb = 0; pb ^= 1; }
+          }
+          umma_commit_pair(&ctl->empty_a[sa]);         // every tap of this k-block has been issued
+          if (++sa == A3_STAGES) { sa = 0; pa ^= 1; }
+        }
+        umma_commit_pair(&ctl->tmem_full[acc]);
+        if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5, both CTAs; each CTA owns 128 of the 256 rows) =========
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int out_buf_rows = p.out_rows + 2 * p.out_halo;
+    for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+      const int mp = tile % m_pairs;
+      const int nt = tile / m_pairs;
+      const int mt = 2 * mp + (int)rank;
+      const int b = mt / p.m_tiles_per_b;
+      const int m = p.m_lo + (mt % p.m_tiles_per_b) * 128 + row;
+      const int n0 = p.n_lo + nt * p.TN;
+      const bool valid = (mt < m_tiles) && (b < p.batch) && (m < p.m_hi);
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.TN);
+      const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
+      for (int c0 = 0; c0 < p.TN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+            const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
+          }
+          if (p.out_dtype == SG_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + obase + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            uint32_t pk[16];
+            if (p.out_dtype == SG_F16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_leader(&ctl->tmem_empty[acc]);
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // form W:  dWp[d+4][n][kc] += sum_{b,m} G[b,m,n] * A[b,m+d,kc]
 //   UMMA: M = 128 channels n (MN-major from G), N = TK channels kc (MN-major from A),
 //   K = 64 positions per stage (PB batches x PR rows).
@@ -850,7 +1078,7 @@ static int make_map2(CUtensorMap* m, const void* base, int dtype, int C, int64_t
   return SG_OK;
 }
 
-int g_cta_pair = 1;   // sg_set_cta_pair(): use the cta_group::2 kernel for form F when there are >= 2 M tiles
+int g_cta_pair = 1;   // sg_set_cta_pair(): 0 single-CTA tiles, 1 cta_group::2 pairs, 2 pairs + A reuse across taps (tc3)
 
 static int num_sms() {
   static int n = 0;
@@ -910,6 +1138,29 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)(q->d_hi + 4 - q->w_tap0 + 1) * q->nc, p.TN);
   if (rc) return rc;
   const int m_tiles_all = p.m_tiles_per_b * p.b_tiles;
+  if (g_cta_pair == 2 && m_tiles_all >= 2 && p.TR == 128 && p.TB == 1 && p.ksplit == 1 && q->d_hi - q->d_lo >= 2) {
+    // A tile staged once per k-block and reused by every tap (tapgemm_f_tc3)
+    static bool attr3 = false;
+    if (!attr3) {
+      SG_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_f_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES));
+      attr3 = true;
+    }
+    const int box_rows = 128 + (q->d_hi - q->d_lo);
+    rc = make_map3(&tmA0, q->a0, q->a_dtype, q->a0_c, a_buf_rows, q->batch, box_rows, 1);
+    if (rc) return rc;
+    if (q->a1) rc = make_map3(&tmA1, q->a1, q->a_dtype, q->a1_c, a_buf_rows, q->batch, box_rows, 1);
+    else tmA1 = tmA0;
+    if (rc) return rc;
+    rc = make_map3(&tmW, q->w, q->w_dtype, q->kc, (q->d_hi + 4 - q->w_tap0 + 1) * q->nc, 1, p.TN / 2, 1);
+    if (rc) return rc;
+    p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 256, p.TN);
+    const int pairs = ((m_tiles_all + 1) / 2) * p.n_tiles;
+    int npairs = num_sms() / 2;
+    if (pairs < npairs) npairs = pairs;
+    tapgemm_f_tc3<<<2 * npairs, NUM_THREADS3, SMEM3_BYTES, st>>>(tmA0, tmA1, tmW, p);
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
   if (g_cta_pair && m_tiles_all >= 2) {
     // CTA-pair kernel: A box per CTA as before, weight box = TN/2 rows per CTA, M = 256 UMMA
     static bool attr2 = false;

@@ -143,6 +143,68 @@ def test_tapgemm_f(backend, case):
         assert float(out[:, :, :n_lo].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("case", ["conv_fwd", "conv_fwd_n512", "deconv_cat", "conv_dgrad_halo", "deconv_dgrad_sub", "taps3"])
+def test_tapgemm_f_a_reuse(case):
+    """sg_set_cta_pair(2): the activation rows of a k-block are staged once (<= 136 rows) and each tap's UMMA
+    reads them through a row-shifted descriptor (tapgemm_f_tc3).  Shapes with >= 128 rows per batch element,
+    a partial last M tile, an odd number of M tiles, two K sources, halo'd outputs and N sub-ranges."""
+    _lib.load().sg_set_cta_pair(2)
+    g = _gen(8)
+    B = 5
+    a1, a1_c, bias = None, 0, None
+    n_lo, n_hi, d_lo, d_hi = 0, None, -4, 4
+    adt, odt, tdt = SG_F16, SG_F16, torch.float16
+    if case in ("conv_fwd", "conv_fwd_n512", "taps3"):
+        cin, cout, R, halo = (64, 128, 328, 4) if case != "conv_fwd_n512" else (128, 512, 136, 4)
+        kc, nc = 4 * cin, cout
+        w, taps = _packed_random("conv_fwd", cin, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        bias = torch.randn(nc, generator=g).to(DEV)
+        if case == "taps3":
+            d_lo, d_hi = -1, 1
+    elif case == "deconv_cat":
+        cout, R, halo = 64, 256, 0
+        kc, nc = 256, 4 * cout
+        w, taps = _packed_random("deconv_fwd", cout, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1 = torch.randn(B, R, 128, generator=g).to(torch.float16).to(DEV)
+        a1_c = 128
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        bias = torch.randn(cout, generator=g).to(DEV)
+    elif case == "conv_dgrad_halo":
+        cin, cout, R, halo = 64, 128, 256, 0
+        kc, nc = cout, 4 * cin
+        w, taps = _packed_random("conv_dgrad", cin, kc, nc, g, torch.bfloat16)
+        a0 = torch.randn(B, R, kc, generator=g).to(torch.bfloat16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = -4, R + 4, R, 4
+        adt, odt, tdt = SG_BF16, SG_BF16, torch.bfloat16
+    else:   # deconv dgrad, upper half of the columns only (z gets no gradient)
+        cin, cout, R, halo = 512, 64, 192, 0
+        kc, nc = 4 * cout, cin
+        w, taps = _packed_random("deconv_dgrad", cout, kc, nc, g, torch.bfloat16)
+        a0 = torch.randn(B, R, kc, generator=g).to(torch.bfloat16).to(DEV)
+        m_lo, m_hi, out_rows, out_halo = 0, R, R, 0
+        n_lo, n_hi = 256, 512
+        adt, odt, tdt = SG_BF16, SG_BF16, torch.bfloat16
+    nhi = nc if n_hi is None else n_hi
+    out = torch.zeros(B, out_rows + 2 * out_halo, nc, dtype=tdt, device=DEV)
+    E.run_f(a0, a1, R, halo, adt, w, adt, kc, nc, taps, out, odt, out_rows, out_halo, m_lo, m_hi, B,
+            bias=bias, bias_mod=(bias.numel() if bias is not None else 0), n_lo=n_lo, n_hi=n_hi, d_lo=d_lo, d_hi=d_hi,
+            backend=BACKEND_TCGEN05, a0_c=a0.shape[-1], a1_c=a1_c)
+    torch.cuda.synchronize()
+    a_full = a0.float() if a1 is None else torch.cat((a0.float(), a1.float()), -1)
+    ref = _ref_f(a_full, halo, w, m_lo, m_hi, d_lo, d_hi)
+    if bias is not None:
+        ref = ref + bias.repeat(nc // bias.numel())
+    got = out[:, out_halo + m_lo: out_halo + m_hi, n_lo:nhi].float()
+    ref = ref[:, :, n_lo:nhi]
+    err = max_abs(got, ref)
+    assert err <= 3e-2 * max(1.0, float(ref.abs().max())), (case, err, float(ref.abs().max()))
+    if n_lo > 0:
+        assert float(out[:, :, :n_lo].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("sms,case,B", [(8, "deconv_cat", 17), (8, "deconv_cat", 21), (8, "small_rows", 33),
                                         (8, "dgrad_halo", 9), (8, "dgrad_halo", 10)])
 def test_tapgemm_f_wave_split(monkeypatch, sms, case, B):

@@ -10,20 +10,28 @@ from segan_pytorch_b200._lib import SG_BF16, SG_F16
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 REP = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-COMPARE = len(sys.argv) > 3 and sys.argv[3] == "compare"      # time every shape with and without the wave split
+COMPARE = sys.argv[3] if len(sys.argv) > 3 else ""
 dev = "cuda"
 h = lambda *s: (torch.randn(*s, device=dev) * 0.5).half()
 b = lambda *s: (torch.randn(*s, device=dev) * 0.5).bfloat16()
 
 
 def timeit(name, fn, flops):
-    for _ in range(2):
-        fn()
-    torch.cuda.synchronize()
+    """COMPARE = "compare": wave split on / off;  "areuse": sg_set_cta_pair(2) (A reuse) vs (1)."""
+    from segan_pytorch_b200 import _lib
+    lib = _lib.load()
+    if COMPARE == "areuse":
+        settings = [("areuse", lambda: lib.sg_set_cta_pair(2)), ("pair", lambda: lib.sg_set_cta_pair(1))]
+    elif COMPARE == "compare":
+        settings = [("split", lambda: setattr(E, "SPLIT_WAVES", True)), ("unsplit", lambda: setattr(E, "SPLIT_WAVES", False))]
+    else:
+        settings = [("", lambda: None)]
     res = []
-    for split in ((True, False) if COMPARE else (E.SPLIT_WAVES,)):
-        E.SPLIT_WAVES = split
-        fn()
+    for _, setup in settings:
+        setup()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(REP):
@@ -31,9 +39,8 @@ def timeit(name, fn, flops):
         e.record()
         torch.cuda.synchronize()
         res.append(s.elapsed_time(e) / REP)
-    ms = res[0]
-    extra = ("   | unsplit %8.3f ms  %7.1f TFLOP/s" % (res[1], flops / res[1] / 1e9)) if COMPARE else ""
-    print("%-28s %8.3f ms  %7.1f TFLOP/s%s" % (name, ms, flops / ms / 1e9, extra))
+    print("%-28s %s" % (name, "   | ".join("%-7s %8.3f ms  %7.1f TFLOP/s" % (settings[i][0], ms, flops / ms / 1e9)
+                                          for i, ms in enumerate(res))))
 
 
 def conv_fwd(cin, cout, R):
