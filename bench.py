@@ -325,21 +325,22 @@ def main():
     # ---- BASELINE config 5 (secondary metric): G-only streaming inference, fp16, batches of B windows,
     #      host->device copy of every batch and device->host copy of the enhanced windows included
     s.G.eval()
-    n_inf = 4
-    out_h = torch.empty(B, 1, 16384).pin_memory()
+    n_inf = 8
     zinf = torch.randn(B, 1024, 16, device=dev)
     with torch.no_grad():
         for _ in range(2):
             s.G(cbuf, z=zinf)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(n_inf):
-            nbuf.copy_(noisy_h.unsqueeze(1), non_blocking=True)
-            y = s.G(nbuf, z=zinf)
-            out_h.copy_(y, non_blocking=True)
-        g1.record()
-        barrier()
+    for _ in s.generate_stream([noisy_h.unsqueeze(1)] * 2, z=zinf):       # warm the pinned output buffers
+        pass
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    n_out = 0
+    for out_h in s.generate_stream((noisy_h.unsqueeze(1) for _ in range(n_inf)), z=zinf):
+        n_out += out_h.shape[0]                                            # enhanced windows, in pinned host memory
+    g1.record()
+    barrier()
+    assert n_out == B * n_inf
     ms_inf = g0.elapsed_time(g1)
     with torch.no_grad():                  # the same batches without the host copies (device-resident)
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -400,7 +401,7 @@ def main():
                 "serial_ms_per_step": ms_serial / args.steps,
                 "whole_step_tflops": ALG_GFLOP_PER_WINDOW * 1e9 * B / step_s / 1e12}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # reported on rank 0 at N=1 only
         wps, spstep, cores = cpu_reference_steps(args.cpu_baseline_steps, 1, args.ref_batch)
         cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
                "sample": "%d timed steps of a %d-window batch of the same workload (oracle, oneDNN off)"
@@ -422,8 +423,9 @@ def main():
                 "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": 16, "last_losses": host_loss,
                 "path": "DevicePrefetcher (pinned host batch -> copy stream, one step ahead) + train_step + losses.tolist()"},
         "g_only_inference": {"value": B * n_inf / (ms_inf * 1e-3), "unit": "windows/s per GPU",
-                             "what": "G forward (clean.py path), fp16 operands, batches of %d windows, "
-                                     "H2D + D2H of every batch inside the timed region" % B,
+                             "what": "SEGAN.generate_stream: G forward (clean.py path), fp16 operands, %d batches of %d "
+                                     "windows from pinned host memory back to pinned host memory; H2D of batch n+1, G "
+                                     "on batch n and D2H of batch n-1 overlap on three streams" % (n_inf, B),
                              "ms_per_batch": ms_inf / n_inf, "ms_per_batch_device_resident": ms_inf_dev / n_inf},
         "gpu_launches": launches,
         "roofline": roof,

@@ -124,6 +124,23 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// One lane of a fully converged warp.  The MMA warps run their loops warp-uniformly and only ISSUE through
+// the elected lane: descriptors, barrier addresses and counters computed in uniform control flow reach the
+// UTCHMMA / UTCBAR instructions through uniform registers.  With the whole loop under `if (lane == 0)` every
+// operand went through an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY "waterfall" (cuobjdump), ~90 cycles per
+// tcgen05.mma, and that single thread paced the tensor pipe (measured: 940 cycles per 4-MMA step with 256-512
+// cycles of tensor work).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // descriptors
@@ -263,8 +280,8 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
+    {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -275,8 +292,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.TN);
-        // the issuer only needs the NUMBER of K steps (the producer decides what they contain):
-        // keep this single thread's loop as short as possible -- it paces the tensor pipe
+        // the issuer only needs the NUMBER of K steps (the producer decides what they contain)
         const int nsteps = f_num_steps(p, n0, ks);
         const uint32_t smem0 = smem_u32(smem);
         for (int i = 0; i < nsteps; ++i) {
@@ -285,14 +301,18 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES, 16, 1024);
-          umma_f16(tmem_d, adesc, bdesc, p.idesc, i > 0 ? 1u : 0u);
-          umma_f16(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
-          umma_f16(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
-          umma_f16(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
-          umma_commit(&ctl->empty[stage]);   // frees the smem slot when these MMAs retire
+          if (elect_one()) {
+            umma_f16(tmem_d, adesc, bdesc, p.idesc, i > 0 ? 1u : 0u);
+            umma_f16(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
+            umma_f16(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
+            umma_f16(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
+            umma_commit(&ctl->empty[stage]);   // frees the smem slot when these MMAs retire
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&ctl->tmem_full[acc]);     // accumulator complete
+        if (elect_one()) umma_commit(&ctl->tmem_full[acc]);     // accumulator complete
+        __syncwarp();
         if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -520,7 +540,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    if (lane == 0 && leader) {
+    if (leader) {      // warp-uniform loop, one elected lane issues (see elect_one)
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = pair_id; tile < total_tiles; tile += npairs) {
@@ -539,14 +559,18 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           const uint32_t sa = smem0 + (uint32_t)stage * STAGE2_BYTES;
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sa + A_STAGE_BYTES, 16, 1024);
-          umma_f16_pair(tmem_d, adesc, bdesc, p.idesc, i > 0 ? 1u : 0u);
-          umma_f16_pair(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
-          umma_f16_pair(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
-          umma_f16_pair(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
-          umma_commit_pair(&ctl->empty[stage]);     // frees the slot in both CTAs
+          if (elect_one()) {
+            umma_f16_pair(tmem_d, adesc, bdesc, p.idesc, i > 0 ? 1u : 0u);
+            umma_f16_pair(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
+            umma_f16_pair(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
+            umma_f16_pair(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
+            umma_commit_pair(&ctl->empty[stage]);     // frees the slot in both CTAs
+          }
+          __syncwarp();
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&ctl->tmem_full[acc]);
+        if (elect_one()) umma_commit_pair(&ctl->tmem_full[acc]);
+        __syncwarp();
         if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -644,16 +668,16 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 constexpr int A3_STAGES = 3;
 constexpr int A3_STAGE_BYTES = 136 * 128;            // 17 KB = 17 x 1024: stages stay 1024 B aligned
-constexpr int B3_STAGES = 8;
-constexpr int B3_STAGE_BYTES = 128 * 128;            // half of a 256-row weight tile
-constexpr int SMEM3_BYTES = A3_STAGES * A3_STAGE_BYTES + B3_STAGES * B3_STAGE_BYTES + 1024 + 512;
+constexpr int B3_RING_BYTES = 10 * 128 * 128;        // weight ring: 10 stages of a 256-wide tile's half (16 KB),
+constexpr int B3_MAX_STAGES = 32;                    // 20 of a 128-wide one, 32 of a 64-wide one
+constexpr int SMEM3_BYTES = A3_STAGES * A3_STAGE_BYTES + B3_RING_BYTES + 1024 + 1024;
 constexpr int NUM_THREADS3 = 224;                    // warp 0: A producer, 1: MMA, 2..5: epilogue, 6: B producer
 
 struct SharedCtl3 {
   uint64_t full_a[A3_STAGES];
   uint64_t empty_a[A3_STAGES];
-  uint64_t full_b[B3_STAGES];
-  uint64_t empty_b[B3_STAGES];
+  uint64_t full_b[B3_MAX_STAGES];
+  uint64_t empty_b[B3_MAX_STAGES];
   uint64_t tmem_full[8];
   uint64_t tmem_empty[8];
   uint32_t tmem_base;
@@ -676,7 +700,7 @@ tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + A3_STAGES * A3_STAGE_BYTES;
-  SharedCtl3* ctl = reinterpret_cast<SharedCtl3*>(smem_b + B3_STAGES * B3_STAGE_BYTES);
+  SharedCtl3* ctl = reinterpret_cast<SharedCtl3*>(smem_b + B3_RING_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -684,7 +708,7 @@ tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
     for (int s = 0; s < A3_STAGES; ++s) { mbar_init(&ctl->full_a[s], 1); mbar_init(&ctl->empty_a[s], 1); }
-    for (int s = 0; s < B3_STAGES; ++s) { mbar_init(&ctl->full_b[s], 1); mbar_init(&ctl->empty_b[s], 1); }
+    for (int s = 0; s < B3_MAX_STAGES; ++s) { mbar_init(&ctl->full_b[s], 1); mbar_init(&ctl->empty_b[s], 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 256); }
     fence_barrier_init();
   }
@@ -704,6 +728,11 @@ tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const uint32_t a_bytes = (uint32_t)a_rows_box * 128u;
   const uint32_t b_bytes = (uint32_t)half_n * 128u;
   const int nacc = 512 / p.TN;
+  // weight ring depth: as many stages as fit (the ring's round trip -- commit -> empty -> TMA -> full -- is
+  // several thousand cycles, so short k-steps need many slots in flight)
+  int nb = B3_RING_BYTES / (int)b_bytes;
+  if (nb > B3_MAX_STAGES) nb = B3_MAX_STAGES;
+  if ((p.dbg >> 8) & 63) nb = min(nb, (p.dbg >> 8) & 63);        // timing experiments: cap the ring depth
 
   if (warp == 0) {
     // ================= A producer (both CTAs): one box per used k-block =================
@@ -719,10 +748,11 @@ tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         for (int kc0 = 0; kc0 < p.kc; kc0 += 64) {
           if (f3_tap_mask(p, kc0, n0) == 0) continue;
           mbar_wait(&ctl->empty_a[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&ctl->full_a[stage], 2u * a_bytes);
+          if (leader) mbar_expect_tx(&ctl->full_a[stage], (p.dbg & 64) ? 0u : 2u * a_bytes);
           const bool in0 = kc0 < p.a0_c;
-          tma_load_3d_pair(smem + stage * A3_STAGE_BYTES, in0 ? &tmA0 : &tmA1, &ctl->full_a[stage],
-                           in0 ? kc0 : kc0 - p.a0_c, m0 + p.d_lo + p.a_halo, b0);
+          if (!(p.dbg & 64))
+            tma_load_3d_pair(smem + stage * A3_STAGE_BYTES, in0 ? &tmA0 : &tmA1, &ctl->full_a[stage],
+                             in0 ? kc0 : kc0 - p.a0_c, m0 + p.d_lo + p.a_halo, b0);
           if (++stage == A3_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -739,17 +769,18 @@ tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           for (int ti = p.d_lo + 4; ti <= p.d_hi + 4; ++ti) {
             if (!((mask >> ti) & 1u)) continue;
             mbar_wait(&ctl->empty_b[stage], phase ^ 1);
-            if (leader) mbar_expect_tx(&ctl->full_b[stage], 2u * b_bytes);
-            tma_load_3d_pair(smem_b + stage * B3_STAGE_BYTES, &tmW, &ctl->full_b[stage], kc0,
-                             (ti - p.w_tap0) * p.nc + n0 + (int)rank * half_n, 0);
-            if (++stage == B3_STAGES) { stage = 0; phase ^= 1; }
+            if (leader) mbar_expect_tx(&ctl->full_b[stage], (p.dbg & 32) ? 0u : 2u * b_bytes);
+            if (!(p.dbg & 32))
+              tma_load_3d_pair(smem_b + stage * b_bytes, &tmW, &ctl->full_b[stage], kc0,
+                               (ti - p.w_tap0) * p.nc + n0 + (int)rank * half_n, 0);
+            if (++stage == nb) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    if (lane == 0 && leader) {
+    if (leader) {      // warp-uniform loop, one elected lane issues (see elect_one)
       int sa = 0; uint32_t pa = 0;
       int sb = 0; uint32_t pb = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -772,20 +803,31 @@ tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             mbar_wait(&ctl->full_b[sb], pb);
             tc_fence_after();
             // rows [d - d_lo, d - d_lo + 128) of the staged A rows: start address shifted by whole 128 B lines
-            const uint64_t adesc = make_smem_desc(a_base + (uint32_t)(ti - 4 - p.d_lo) * 128u, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(smem_b0 + (uint32_t)sb * B3_STAGE_BYTES, 16, 1024);
-            umma_f16_pair(tmem_d, adesc, bdesc, p.idesc, accum);
-            umma_f16_pair(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
-            umma_f16_pair(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
-            umma_f16_pair(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
+            // The swizzle pattern itself starts at the 1024 B aligned stage base (TMA wrote it), so the
+            // descriptor's base-offset field stays 0 although the start address is not 1024 B aligned
+            // (measured: base offset = (addr >> 7) & 7 gives wrong results, 0 is bit-correct).
+            uint64_t adesc = make_smem_desc(a_base + ((p.dbg & 16) ? 0u : (uint32_t)(ti - 4 - p.d_lo) * 128u), 16, 1024);
+            adesc &= ~((uint64_t)7 << 49);
+            const uint64_t bdesc = make_smem_desc(smem_b0 + (uint32_t)sb * b_bytes, 16, 1024);
+            if (elect_one()) {
+              if (!(p.dbg & 128)) {
+                umma_f16_pair(tmem_d, adesc, bdesc, p.idesc, accum);
+                umma_f16_pair(tmem_d, adesc + 2, bdesc + 2, p.idesc, 1u);
+                umma_f16_pair(tmem_d, adesc + 4, bdesc + 4, p.idesc, 1u);
+                umma_f16_pair(tmem_d, adesc + 6, bdesc + 6, p.idesc, 1u);
+              }
+              umma_commit_pair(&ctl->empty_b[sb]);       // frees the weight slot in both CTAs
+            }
+            __syncwarp();
             accum = 1u;
-            umma_commit_pair(&ctl->empty_b[sb]);       // frees the weight slot in both CTAs
-            if (++sb == B3_STAGES) { sb = 0; pb ^= 1; }
+            if (++sb == nb) { sb = 0; pb ^= 1; }
           }
-          umma_commit_pair(&ctl->empty_a[sa]);         // every tap of this k-block has been issued
+          if (elect_one()) umma_commit_pair(&ctl->empty_a[sa]);         // every tap of this k-block has been issued
+          __syncwarp();
           if (++sa == A3_STAGES) { sa = 0; pa ^= 1; }
         }
-        umma_commit_pair(&ctl->tmem_full[acc]);
+        if (elect_one()) umma_commit_pair(&ctl->tmem_full[acc]);
+        __syncwarp();
         if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -950,7 +992,7 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                  // warp-uniform loop, one elected lane issues (see elect_one)
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -971,15 +1013,19 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
           // 16 positions = 16 lines of 128 B = 2048 B along K: +128 in descriptor address units
           const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
           const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
-          umma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
-          umma_f16(tmem_d, adesc + 128, bdesc + 128, p.idesc, 1u);
-          umma_f16(tmem_d, adesc + 256, bdesc + 256, p.idesc, 1u);
-          umma_f16(tmem_d, adesc + 384, bdesc + 384, p.idesc, 1u);
+          if (elect_one()) {
+            umma_f16(tmem_d, adesc, bdesc, p.idesc, accum);
+            umma_f16(tmem_d, adesc + 128, bdesc + 128, p.idesc, 1u);
+            umma_f16(tmem_d, adesc + 256, bdesc + 256, p.idesc, 1u);
+            umma_f16(tmem_d, adesc + 384, bdesc + 384, p.idesc, 1u);
+            umma_commit(&ctl->empty[stage]);
+          }
+          __syncwarp();
           accum = 1;
-          umma_commit(&ctl->empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&ctl->tmem_full[acc]);
+        if (elect_one()) umma_commit(&ctl->tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -497,11 +497,14 @@ class GeneratorEngine(_NetEngine):
         return self.pview("alpha_%d.skip_k" % (self.nl - 1 - l)).reshape(-1)
 
     # -- forward ----------------------------------------------------------------------------
-    def forward(self, x, z, want_ctx=True, fresh=False):
+    def forward(self, x, z, want_ctx=True, fresh=False, twins=None):
         """x: (B,1,L) fp32 cuda, z: (B, C4, L/1024) fp32 cuda.  Returns y (B,1,L) fp32.
+        twins (default = want_ctx): also write the bf16 copies of the activations that only the weight-gradient
+        tap-GEMMs read; inference passes False (one store per activation instead of two or three).
         fresh=True gives the saved activations their own storage (generic autograd use, where several
         forwards may precede a backward); the fused train step reuses one persistent workspace."""
         _require_cuda(x, z)
+        twins = want_ctx if twins is None else (twins and want_ctx)
         self.ensure_packed()
         B, _, L = x.shape
         fm, nl, dev, st = self.fmaps, self.nl, x.device, _stream()
@@ -519,7 +522,7 @@ class GeneratorEngine(_NetEngine):
             bias = self.pview("enc_blocks.%d.conv.bias" % l) if self.enc_bias else None
             if l == 0 and wave_on_tensor_cores():
                 col16 = buf.get("g.col16", (B, Lq[0], 64), F16, dev)
-                colb = buf.get("g.colb", (B, Lq[0], 64), BF16, dev) if want_ctx else None
+                colb = buf.get("g.colb", (B, Lq[0], 64), BF16, dev) if twins else None
                 _lib.call("sg_wave_im2col", _p(x), None, 1, B, L, 0, None, 1, 14, _p(col16), _p(colb), st)
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
@@ -535,7 +538,7 @@ class GeneratorEngine(_NetEngine):
                       bias=bias, bias_mod=cout, backend=self.backend)
             halo = 16 if l < nl - 1 else 0
             hp[l] = buf.get("g.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
-            if want_ctx:
+            if twins:
                 hpb[l] = buf.get("g.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), BF16, dev)
                 if l < nl - 1:
                     ab[l] = buf.get("g.ab%d" % l, (B, Lq[l], cout), BF16, dev)
@@ -547,7 +550,7 @@ class GeneratorEngine(_NetEngine):
         z16 = buf.get("g.z16", (B, Lq[-1], zc), F16, dev)
         zf = z.contiguous().float()
         _lib.call("sg_ncl_to_nlc", _p(zf), B, zc, Lq[-1], _p(z16), SG_F16, st)
-        if want_ctx:
+        if twins:
             z16b = buf.get("g.z16b", (B, Lq[-1], zc), BF16, dev)
             _lib.call("sg_ncl_to_nlc", _p(zf), B, zc, Lq[-1], _p(z16b), SG_BF16, st)
         # ---- decoder
@@ -563,7 +566,7 @@ class GeneratorEngine(_NetEngine):
                   bias=self.pview("dec_blocks.%d.deconv.bias" % l), bias_mod=cout,
                   a0_c=src0.shape[-1], a1_c=src1.shape[-1], backend=self.backend)
             dd[l] = buf.get("g.dd%d" % l, (B, 4 * lin, cout), F16, dev)
-            if want_ctx:
+            if twins:
                 ddb[l] = buf.get("g.ddb%d" % l, (B, 4 * lin, cout), BF16, dev)
             _lib.call("sg_act_fwd", _p(ad[l]), SG_F16, B, 4 * lin, cout, None,
                       _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, None, 0, _p(dd[l]), _p(ddb[l]), None, st)
@@ -585,8 +588,8 @@ class GeneratorEngine(_NetEngine):
                    z16b=z16b, colb=colb) if want_ctx else None
         return y, ctx
 
-    def hidden_ncl(self, ctx):
-        """`hall` of generator.py:186-227 as fp32 NCL tensors (inspection path)."""
+    def hidden_ncl(self, ctx, only=None):
+        """`hall` of generator.py:186-227 as fp32 NCL tensors (inspection path).  only: optional set of keys."""
         nl, st = self.nl, _stream()
         B, Lq = ctx["B"], ctx["Lq"]
         hall = {}
@@ -595,16 +598,21 @@ class GeneratorEngine(_NetEngine):
             out = torch.empty(B, C_, L_, dtype=F32, device=t16.device)
             _lib.call("sg_nlc_to_ncl", _p(t16), SG_F16, B, C_, L_, _p(out), st)
             return out
+        want = (lambda k: True) if only is None else (lambda k: k in only)
         for l in range(nl):
-            a = to_ncl(ctx["a"][l], self.fmaps[l], Lq[l])
-            hall["enc_%d" % l] = torch.nn.functional.prelu(a, self.pview("enc_blocks.%d.act.weight" % l))
-        zc = ctx["z16"].shape[-1]
-        hall["enc_zc"] = torch.cat((to_ncl(ctx["z16"], zc, Lq[-1]), hall["enc_%d" % (nl - 1)]), 1)
+            if want("enc_%d" % l) or (l == nl - 1 and want("enc_zc")):
+                a = to_ncl(ctx["a"][l], self.fmaps[l], Lq[l])
+                hall["enc_%d" % l] = torch.nn.functional.prelu(a, self.pview("enc_blocks.%d.act.weight" % l))
+        if want("enc_zc"):
+            zc = ctx["z16"].shape[-1]
+            hall["enc_zc"] = torch.cat((to_ncl(ctx["z16"], zc, Lq[-1]), hall["enc_%d" % (nl - 1)]), 1)
         lin = Lq[-1]
         for l in range(nl - 1):
-            hall["dec_%d" % l] = to_ncl(ctx["dd"][l], self.dec_cout(l), 4 * lin)
+            if want("dec_%d" % l):
+                hall["dec_%d" % l] = to_ncl(ctx["dd"][l], self.dec_cout(l), 4 * lin)
             lin *= 4
-        hall["dec_%d" % (nl - 1)] = ctx["y"]
+        if want("dec_%d" % (nl - 1)):
+            hall["dec_%d" % (nl - 1)] = ctx["y"]
         return hall
 
     # -- backward ---------------------------------------------------------------------------

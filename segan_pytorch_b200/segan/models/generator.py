@@ -165,7 +165,9 @@ class Generator(Model):
             ectx = eng._last_ctx          # hidden activations are exposed detached (inspection only)
             eng._last_ctx = None
         else:
-            y, ectx = eng.forward(x, z)
+            y, ectx = eng.forward(x, z, twins=False)      # inference: no bf16 twins for weight gradients
         if ret_hid:
-            return y, eng.hidden_ncl(ectx)
+            # ret_hid may be an iterable of keys (additive): only those activations are converted to NCL
+            only = None if ret_hid is True else set(ret_hid)
+            return y, eng.hidden_ncl(ectx, only)
         return y

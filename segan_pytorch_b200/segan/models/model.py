@@ -207,9 +207,10 @@ class SEGAN(Model):
                 self.G.z = z0
             zrest = z0
         zb = torch.cat([z0[:1]] + [zrest[:1]] * (nchunks - 1), 0) if nchunks > 1 else z0[:1]
+        last = 'enc_{}'.format(len(self.G.enc_blocks) - 1)
         with torch.no_grad():
-            y, hall = self.G(x, z=zb, ret_hid=True)
-        g_c = hall['enc_{}'.format(len(self.G.enc_blocks) - 1)][-1:]
+            y, hall = self.G(x, z=zb, ret_hid=(last,))     # only the code of model.py:149 is converted to NCL
+        g_c = hall[last][-1:]
         c = y.reshape(-1)[:T].contiguous()
         out = torch.empty_like(c)
         if self.preemph > 0:
@@ -224,6 +225,64 @@ class SEGAN(Model):
         self.G.eval()
         with torch.no_grad():
             return self.G(windows, z=z)
+
+    def generate_stream(self, host_batches, z=None):
+        """Streaming inference over HOST batches (BASELINE config 5; the clean.py:59-82 loop batched across
+        files): yields one pinned host tensor of enhanced windows per input batch of (N,1,16384) pre-emphasised
+        windows.  Three streams: the H2D copy of batch n+1, G on batch n and the D2H copy of batch n-1 overlap,
+        so a slow host link hides behind the Generator.  A yielded tensor is valid until the next-but-one
+        batch is requested (two pinned output buffers alternate)."""
+        self.G.eval()
+        dev = next(super(Model, self.G).parameters()).device
+        main = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        slots = [dict(), dict()]
+
+        def stage(hb, slot):
+            hb = torch.as_tensor(hb).float()
+            if slot.get("x") is None or slot["x"].shape != hb.shape:
+                slot["x"] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
+                slot["out"] = torch.empty(hb.shape, dtype=torch.float32).pin_memory()
+            with torch.cuda.stream(h2d):
+                if slot.get("free") is not None:
+                    h2d.wait_event(slot["free"])
+                slot["x"].copy_(hb, non_blocking=True)
+                slot["ready"] = torch.cuda.Event()
+                slot["ready"].record(h2d)
+            return slot
+
+        it = iter(host_batches)
+        try:
+            cur = stage(next(it), slots[0])
+        except StopIteration:
+            return
+        n, prev = 0, None
+        while cur is not None:
+            n += 1
+            try:
+                nxt = stage(next(it), slots[n % 2])
+            except StopIteration:
+                nxt = None
+            main.wait_event(cur["ready"])
+            if cur.get("out_done") is not None:
+                cur["out_done"].synchronize()          # its previous output has been handed out and copied
+            with torch.no_grad():
+                y = self.G(cur["x"], z=z)
+            cur["free"] = torch.cuda.Event()
+            cur["free"].record(main)
+            d2h.wait_event(cur["free"])
+            with torch.cuda.stream(d2h):
+                cur["out"].copy_(y, non_blocking=True)
+                y.record_stream(d2h)
+                cur["out_done"] = torch.cuda.Event()
+                cur["out_done"].record(d2h)
+            if prev is not None:
+                prev["out_done"].synchronize()
+                yield prev["out"]
+            prev, cur = cur, nxt
+        if prev is not None:
+            prev["out_done"].synchronize()
+            yield prev["out"]
 
     def discriminate(self, cwav, nwav):
         self.D.eval()

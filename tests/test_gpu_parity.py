@@ -304,6 +304,21 @@ def test_generate_chunked_vs_reference(segan):
     assert tuple(g_c.shape) == (1, 1024, 16)
 
 
+def test_generate_stream_matches_direct_forward(segan):
+    """Streaming inference (BASELINE config 5): batches go host -> device -> G -> host on three overlapping
+    streams; every yielded batch equals the direct forward of the same windows."""
+    gen = torch.Generator().manual_seed(12)
+    batches = [(0.3 * torch.randn(3, 1, 16384, generator=gen)).pin_memory() for _ in range(5)]
+    z = torch.randn(3, 1024, 16, generator=gen).to(DEV)
+    segan.G.eval()
+    outs = [o.clone() for o in segan.generate_stream(iter(batches), z=z)]
+    assert len(outs) == len(batches)
+    with torch.no_grad():
+        for hb, o in zip(batches, outs):
+            ref = segan.G(hb.to(DEV), z=z).cpu()
+            assert max_abs(o, ref) <= 1e-6, max_abs(o, ref)
+
+
 def test_autograd_path_matches_fused_step(segan):
     """Generator / Discriminator used as ordinary autograd modules give the same gradients as the
     fused step's engines (API compatibility path)."""

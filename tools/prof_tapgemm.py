@@ -88,6 +88,12 @@ def conv_wgrad(cin, cout, R):
 
 
 if __name__ == "__main__":
+    if COMPARE == "areuse3":          # three representative shapes only (timing experiments)
+        COMPARE = "areuse"
+        conv_fwd(64, 128, 1024)
+        deconv_fwd(512, 128, 256)
+        conv_dgrad(128, 256, 256)
+        sys.exit(0)
     conv_fwd(64, 128, 1024)
     conv_fwd(128, 256, 256)
     conv_fwd(256, 512, 64)
