@@ -345,6 +345,18 @@ class _Buffers:
         return cur
 
 
+def stat_arena(buf, name, shapes, device):
+    """One zero-fill for all per-channel statistic buffers of a pass: views of shapes[i] (float64) into a
+    single tensor that is zeroed once (each buffer used to get its own tiny fill launch on the critical chain)."""
+    sizes = [int(torch.Size(sh).numel()) for sh in shapes]
+    flat = buf.get(name, (sum(sizes),), torch.float64, device, zero=True)
+    out, off = [], 0
+    for sh, n in zip(shapes, sizes):
+        out.append(flat[off:off + n].view(sh))
+        off += n
+    return out
+
+
 F16, BF16, F32, F64 = torch.float16, torch.bfloat16, torch.float32, torch.float64
 SL = 8   # SG_STAT_SLICES: statistic buffers are [SL][n_stats][C]; the statistic is the sum over slices
 
@@ -626,6 +638,8 @@ class GeneratorEngine(_NetEngine):
         if not accumulate:
             self.grad.zero_()
         side = side_stream(dev, 0)       # weight-gradient chain (wgrad GEMM + unpack) of every layer
+        red_dec = stat_arena(buf, "g.red_dec", [(SL, 3, self.dec_cout(l)) for l in range(nl - 1)], dev)
+        red_enc = stat_arena(buf, "g.red_enc", [(SL, 3, fm[l]) for l in range(nl)], dev)
         # ---- last decoder block (tanh, Cout = 1)
         l = nl - 1
         lin = Lq[0]
@@ -668,7 +682,7 @@ class GeneratorEngine(_NetEngine):
             cnext = g_next.shape[-1]
             # PReLU backward on [B, 4*lin, cout]
             g_ad = buf.get("g.gad%d" % l, (B, lin, 4 * cout), BF16, dev)
-            red = buf.get("g.redd%d" % l, (SL, 3, cout), F64, dev, zero=True)
+            red = red_dec[l]
             _lib.call("sg_act_bwd_reduce", _p(g_next), cnext, 0, 0, None, None, 0, _p(ad[l]), SG_F16, B, 4 * lin, cout,
                       None, None, _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, _p(red), _p(g_ad), st)
             _lib.call("sg_stat_grads", _p(red), cout, 3, _p(self.gview("dec_blocks.%d.act.weight" % l)),
@@ -702,7 +716,7 @@ class GeneratorEngine(_NetEngine):
         for l in range(nl - 1, -1, -1):
             cout = fm[l]
             g_a = buf.get("g.ga%d" % l, (B, Lq[l], cout), BF16, dev)
-            red = buf.get("g.rede%d" % l, (SL, 3, cout), F64, dev, zero=True)
+            red = red_enc[l]
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             if l == nl - 1:
                 gin0 = buf.t["g.gin0"]
@@ -821,6 +835,7 @@ class DiscriminatorEngine(_NetEngine):
         def rptr(i):
             return None if shifts_dev is None else C.c_void_p(shifts_dev.data_ptr() + 4 * i)
         a, hp, ss, mi, hpb = [None] * nl, [None] * nl, [None] * nl, [None] * nl, [None] * nl
+        stats = stat_arena(buf, "d.stats", [(SL, 2, fm[l]) for l in range(nl)], dev) if training else None
         for l in range(nl):
             cout = fm[l]
             a[l] = buf.get("d.a%d" % l, (B, Lq[l], cout), F16, dev)
@@ -846,7 +861,7 @@ class DiscriminatorEngine(_NetEngine):
             ss[l] = buf.get("d.ss%d" % l, (2, cout), F32, dev)
             mi[l] = buf.get("d.mi%d" % l, (2, cout), F32, dev)
             if training:
-                st2 = buf.get("d.stats%d" % l, (SL, 2, cout), F64, dev, zero=True)
+                st2 = stats[l]
                 _lib.call("sg_bn_stats", _p(a[l]), SG_F16, B * Lq[l], cout, _p(st2), st)
                 _lib.call("sg_bn_finalize", _p(st2), B * Lq[l], cout,
                           _p(self.pview("enc_blocks.%d.norm.weight" % l)),
@@ -929,13 +944,14 @@ class DiscriminatorEngine(_NetEngine):
         run_f(g_z1, None, 1, 0, SG_BF16, self.packed["W1dg"], SG_BF16, 256, kin, tap_ranges("full", 0, 256, kin),
               g_h, SG_BF16, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
         tmp = buf.get("d.cstmp", (SL * 2048,), F64, dev)
+        reds = stat_arena(buf, "d.red", [(SL, 3, fm[l]) for l in range(nl)], dev)
         for l in range(nl - 1, -1, -1):
             cout = fm[l]
             halo = 16 if l < nl - 1 else 0
             roll = shifts[l + 1] if l < nl - 1 else 0
             rp = rptr(l + 1) if l < nl - 1 else None
             g_a = buf.get("d.ga%d" % l, (B, Lq[l], cout), BF16, dev)
-            redl = buf.get("d.red%d" % l, (SL, 3, cout), F64, dev, zero=True)
+            redl = reds[l]
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
                       _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
