@@ -427,11 +427,37 @@ class _NetEngine:
         self._packed_version = None
 
     def ensure_packed(self):
+        """Re-packs the 16-bit operands when the master weights changed.  With overlap on, the pack kernels go
+        to side stream 4 and record one event per operand: the forward that triggered the pack waits for
+        each layer's event right before that layer's tap-GEMM (`wait_packed`), so the 0.25-0.45 ms of packing
+        hides behind the first layers instead of preceding them on the critical chain."""
         self.bind()
         v = self._version()
         if v != self._packed_version:
-            self.pack()
+            self.pack_ev = {}
+            self._pack_side = side_stream(self.flat.device, 4)
+            with on_side(self._pack_side):
+                self.pack()
             self._packed_version = self._version()
+
+    def _mark_packed(self, *keys):
+        if getattr(self, "_pack_side", None) is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            for k in keys:
+                self.pack_ev[k] = ev
+
+    def wait_packed(self, key):
+        ev = getattr(self, "pack_ev", {}).get(key)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def packs_consumed(self):
+        """End of the forward that triggered a pack: later users are ordered after it by their streams."""
+        if getattr(self, "_pack_side", None) is not None:
+            join_side(self._pack_side)
+            self._pack_side = None
+        self.pack_ev = {}
 
     def export_grads(self):
         """Copies the flat gradient bucket into per-parameter .grad tensors (API compatibility)."""
@@ -461,23 +487,6 @@ class GeneratorEngine(_NetEngine):
         dev = self.flat.device
         fm = self.fmaps
         st = _stream()
-        for l in range(1, self.nl):
-            cin, cout = fm[l - 1], fm[l]
-            wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
-            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), BF16, dev)
-            _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
-                      None, 0, _p(wf), _p(wd), SG_F16, SG_BF16, st)
-            self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
-        for l in range(self.nl - 1):
-            cin = self.dec_cin(l)
-            cout = self.dec_cout(l)
-            w = self.pview("dec_blocks.%d.deconv.weight" % l)
-            alpha = self.alpha_for_dec(l)
-            wt = self.buf.get("Wt%d" % l, (9, 4 * cout, cin), F16, dev)
-            wtd = self.buf.get("Wtd%d" % l, (9, cin, 4 * cout), BF16, dev)
-            _lib.call("sg_pack_weights", 1, _p(w), cout, cin, 0, _p(alpha), cin // 2,
-                      _p(wt), _p(wtd), SG_F16, SG_BF16, st)
-            self.packed["Wt%d" % l], self.packed["Wtd%d" % l] = wt, wtd
         # last decoder layer (Cout = 1): fp32 [cin][31] with alpha folded (tiny: torch ops)
         l = self.nl - 1
         w = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
@@ -495,6 +504,26 @@ class GeneratorEngine(_NetEngine):
         wg = torch.zeros(weff.shape[0], 64, dtype=torch.float32, device=dev)
         wg[:, :KW] = weff
         self.packed["Wg_last"] = wg.bfloat16().contiguous()
+        self._mark_packed("small")
+        for l in range(1, self.nl):
+            cin, cout = fm[l - 1], fm[l]
+            wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
+            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), BF16, dev)
+            _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
+                      None, 0, _p(wf), _p(wd), SG_F16, SG_BF16, st)
+            self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
+            self._mark_packed("Wf%d" % l)
+        for l in range(self.nl - 1):
+            cin = self.dec_cin(l)
+            cout = self.dec_cout(l)
+            w = self.pview("dec_blocks.%d.deconv.weight" % l)
+            alpha = self.alpha_for_dec(l)
+            wt = self.buf.get("Wt%d" % l, (9, 4 * cout, cin), F16, dev)
+            wtd = self.buf.get("Wtd%d" % l, (9, cin, 4 * cout), BF16, dev)
+            _lib.call("sg_pack_weights", 1, _p(w), cout, cin, 0, _p(alpha), cin // 2,
+                      _p(wt), _p(wtd), SG_F16, SG_BF16, st)
+            self.packed["Wt%d" % l], self.packed["Wtd%d" % l] = wt, wtd
+            self._mark_packed("Wt%d" % l)
 
     def dec_cin(self, l):
         return 2 * self.fmaps[-1] if l == 0 else 2 * self.fmaps[self.nl - 1 - l]
@@ -518,6 +547,7 @@ class GeneratorEngine(_NetEngine):
         _require_cuda(x, z)
         twins = want_ctx if twins is None else (twins and want_ctx)
         self.ensure_packed()
+        self.wait_packed("small")
         B, _, L = x.shape
         fm, nl, dev, st = self.fmaps, self.nl, x.device, _stream()
         buf = _Buffers() if fresh else self.buf
@@ -536,6 +566,7 @@ class GeneratorEngine(_NetEngine):
                 col16 = buf.get("g.col16", (B, Lq[0], 64), F16, dev)
                 colb = buf.get("g.colb", (B, Lq[0], 64), BF16, dev) if twins else None
                 _lib.call("sg_wave_im2col", _p(x), None, 1, B, L, 0, None, 1, 14, _p(col16), _p(colb), st)
+                self.wait_packed("small")
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
                       d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
@@ -545,6 +576,7 @@ class GeneratorEngine(_NetEngine):
                           _p(bias), cout, _p(a[0]), None, None, st)
             else:
                 cin = fm[l - 1]
+                self.wait_packed("Wf%d" % l)
                 run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
                       tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
                       bias=bias, bias_mod=cout, backend=self.backend)
@@ -573,6 +605,7 @@ class GeneratorEngine(_NetEngine):
             cin, cout = self.dec_cin(l), self.dec_cout(l)
             assert src0.shape[-1] + src1.shape[-1] == cin
             ad[l] = buf.get("g.ad%d" % l, (B, lin, 4 * cout), F16, dev)
+            self.wait_packed("Wt%d" % l)
             run_f(src0, src1, lin, 0, SG_F16, self.packed["Wt%d" % l], SG_F16, cin, 4 * cout,
                   tap_ranges("deconv_fwd", cout, cin, 4 * cout), ad[l], SG_F16, lin, 0, 0, lin, B,
                   bias=self.pview("dec_blocks.%d.deconv.bias" % l), bias_mod=cout,
@@ -596,6 +629,7 @@ class GeneratorEngine(_NetEngine):
         else:
             _lib.call("sg_wave_deconv_fwd", _p(src0), src0.shape[-1], _p(src1), src1.shape[-1], B, lin,
                       _p(self.packed["w_last_eff"]), _p(blast), _p(y), st)
+        self.packs_consumed()
         ctx = dict(x=x, B=B, L=L, Lq=Lq, a=a, hp=hp, z16=z16, ad=ad, dd=dd, y=y, hpb=hpb, ab=ab, ddb=ddb,
                    z16b=z16b, colb=colb) if want_ctx else None
         return y, ctx
@@ -795,6 +829,10 @@ class DiscriminatorEngine(_NetEngine):
 
     def pack(self):
         dev, fm, st = self.flat.device, self.fmaps, _stream()
+        wcol = wave_col_weights(self.pview("enc_blocks.0.conv.weight"), dev)
+        self.packed["Wcol0"] = wcol.half().contiguous()
+        self.packed["WcolT0"] = wcol.t().bfloat16().contiguous()
+        self._mark_packed("small")
         for l in range(1, self.nl):
             cin, cout = fm[l - 1], fm[l]
             wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
@@ -802,6 +840,7 @@ class DiscriminatorEngine(_NetEngine):
             _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
                       None, 0, _p(wf), _p(wd), SG_F16, SG_BF16, st)
             self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
+            self._mark_packed("Wf%d" % l)
         w1 = self.pview("fc.0.weight")
         nout, kin = w1.shape
         C_ = fm[-1]
@@ -810,9 +849,7 @@ class DiscriminatorEngine(_NetEngine):
         w1d = self.buf.get("W1dg", (kin, nout), BF16, dev)
         _lib.call("sg_pack_weights", 2, _p(w1), nout, C_, T, None, 0, _p(w1p), _p(w1d), SG_F16, SG_BF16, st)
         self.packed["W1p"], self.packed["W1dg"] = w1p, w1d
-        wcol = wave_col_weights(self.pview("enc_blocks.0.conv.weight"), dev)
-        self.packed["Wcol0"] = wcol.half().contiguous()
-        self.packed["WcolT0"] = wcol.t().bfloat16().contiguous()
+        self._mark_packed("W1p")
 
     def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True, lane=0, shifts_dev=None):
         """x0: candidate (B,1,L), x1: reference/noisy (B,1,L) -- the reference's cat((x_, ref), 1)
@@ -821,6 +858,7 @@ class DiscriminatorEngine(_NetEngine):
         per-step scalar in the launches, so the step can be replayed from a CUDA graph)."""
         _require_cuda(x0, x1)
         self.ensure_packed()
+        self.wait_packed("small")
         m = self.module
         B, _, L = x0.shape
         fm, nl, dev, st = self.fmaps, self.nl, x0.device, _stream()
@@ -845,6 +883,7 @@ class DiscriminatorEngine(_NetEngine):
                 col16 = buf.get("d.col16", (B, Lq[0], 64), F16, dev)
                 colb0 = buf.get("d.colb", (B, Lq[0], 64), BF16, dev) if twins else None
                 _lib.call("sg_wave_im2col", _p(x0), _p(x1), 2, B, L, int(shifts[0]), rptr(0), 1, 14, _p(col16), _p(colb0), st)
+                self.wait_packed("small")
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
                       d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
@@ -854,6 +893,7 @@ class DiscriminatorEngine(_NetEngine):
                           _p(self.pview("enc_blocks.0.conv.weight")), _p(bias), cout, _p(a[0]), None, None, st)
             else:
                 cin = fm[l - 1]
+                self.wait_packed("Wf%d" % l)
                 run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
                       tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
                       bias=bias, bias_mod=cout, backend=self.backend)
@@ -885,6 +925,7 @@ class DiscriminatorEngine(_NetEngine):
         # ---- FC head
         kin = Lq[-1] * fm[-1]
         acc = buf.get("d.fc0", (B, 256), F32, dev, zero=True)
+        self.wait_packed("W1p")
         run_f(hp[-1], None, 1, 0, SG_F16, self.packed["W1p"], SG_F16, kin, 256,
               tap_ranges("full", 0, kin, 256), acc, SG_F32, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4,
               ksplit=16, backend=self.backend)
@@ -894,6 +935,7 @@ class DiscriminatorEngine(_NetEngine):
         _lib.call("sg_fc_tail_fwd", _p(acc), _p(self.pview("fc.0.bias")), _p(self.pview("fc.1.weight")),
                   _p(self.pview("fc.2.weight")), _p(self.pview("fc.2.bias")), _p(self.pview("fc.3.weight")),
                   _p(self.pview("fc.4.weight")), _p(self.pview("fc.4.bias")), B, _p(z1), _p(z2), _p(logit), st)
+        self.packs_consumed()
         ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, hpb=hpb, colb=colb0, ss=ss, mi=mi, z1=z1, z2=z2,
                    logit=logit, lane=lane, shifts_dev=shifts_dev,
                    shifts=[int(s) for s in shifts])
