@@ -120,6 +120,10 @@ typedef struct sg_tapgemm_f {
   int32_t backend;    /* SG_BACKEND_* */
   int32_t tile_n;     /* N tile of the tcgen05 kernel: 0 = widest of 256/128/64 dividing n_hi-n_lo; 64|128|256 =
                          narrower tiles for the tail of a launch split against wave quantisation (148 SMs) */
+  double* bn_stats;   /* or NULL.  Fused nn.BatchNorm1d batch statistics (modules.py:11,100) of the output: per
+                         column sum and sum of squares of the stored (rounded) values over all computed rows,
+                         accumulated into [SG_STAT_SLICES][2][nc] doubles (same buffer sg_bn_stats fills; caller
+                         zeroes).  tcgen05 backend, 16-bit out, ksplit 1, n_lo = 0, n_hi = nc, >= 2 M tiles. */
 } sg_tapgemm_f;
 
 int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream);

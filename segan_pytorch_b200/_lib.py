@@ -29,7 +29,7 @@ class TapGemmF(C.Structure):
         ("out_dtype", C.c_int32), ("out_rows", C.c_int32), ("out_halo", C.c_int32),
         ("m_lo", C.c_int32), ("m_hi", C.c_int32), ("n_lo", C.c_int32), ("n_hi", C.c_int32),
         ("bias", _vp), ("bias_mod", C.c_int32), ("batch", C.c_int32), ("ksplit", C.c_int32),
-        ("backend", C.c_int32), ("tile_n", C.c_int32),
+        ("backend", C.c_int32), ("tile_n", C.c_int32), ("bn_stats", _vp),
     ]
 
 

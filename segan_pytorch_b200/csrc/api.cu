@@ -65,7 +65,13 @@ extern "C" int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream) {
     SG_CHECK_ARG(p->a_dtype == p->w_dtype);
     return tapgemm_f_tc_launch(p, (cudaStream_t)stream);
   }
-  if (p->backend == SG_BACKEND_FFMA) return tapgemm_f_ffma_launch(p, (cudaStream_t)stream);
+  if (p->backend == SG_BACKEND_FFMA) {
+    if (p->bn_stats != nullptr) {
+      set_error("bn_stats (fused BatchNorm statistics) needs the tcgen05 backend");
+      return SG_ERR_UNSUPPORTED;
+    }
+    return tapgemm_f_ffma_launch(p, (cudaStream_t)stream);
+  }
   set_error("unknown backend %d", p->backend);
   return SG_ERR_UNSUPPORTED;
 }

@@ -142,6 +142,24 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// x[j] of lane l = value (row l, column j)  ->  returns for lane l the sum over the 32 rows of column l.
+// 31 shuffles instead of 32 x 5: at every halving step a lane keeps the half of the columns its bit selects
+// and sends the other half to its partner.
+__device__ __forceinline__ float warp_transpose_reduce(float (&x)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? x[i] : x[i + off];
+      const float keep = up ? x[i + off] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return x[0];
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // descriptors
 // ------------------------------------------------------------------------------------------
@@ -196,6 +214,7 @@ struct FTcParams {
   int m_tiles_per_b, b_tiles, n_tiles;
   uint32_t idesc;
   int dbg;                   // timing experiments only (SEGAN_B200_DEBUG): 1 skip B loads, 2 skip A loads, 4 skip stores
+  double* stats;             // fused BatchNorm statistics [SG_STAT_SLICES][2][nc] (CTA-pair kernel), or nullptr
 };
 
 struct SharedCtl {
@@ -407,7 +426,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 constexpr int STAGES2 = 6;
 constexpr int B2_STAGE_BYTES = 128 * 128;            // half of a 256-row weight tile
 constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + 2048;   // + per-CTA column statistics [2][256] fp32
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;          // shared::cluster address of the even (leader) CTA
 
 struct SharedCtl2 {
@@ -580,6 +599,28 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     const int row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const int out_buf_rows = p.out_rows + 2 * p.out_halo;
+    // fused BatchNorm statistics (modules.py:100): per-column sum / sum of squares of the stored (rounded)
+    // outputs, accumulated per CTA in shared memory across its tiles of one N tile, flushed with one double
+    // atomic per column when the N tile changes and at the end
+    float* colstat = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES + 256);
+    const int et = threadIdx.x - 64;           // 0..127 within the epilogue warps
+    int stat_nt = -1;
+    auto flush_stats = [&](int nt_done) {
+      epi_bar_sync();
+      const int n0s = p.n_lo + nt_done * p.TN;
+      double* o = p.stats + (int64_t)(blockIdx.x % SG_STAT_SLICES) * 2 * p.nc;
+      for (int c = et; c < p.TN; c += 128) {
+        atomicAdd(o + n0s + c, (double)colstat[c]);
+        atomicAdd(o + p.nc + n0s + c, (double)colstat[256 + c]);
+        colstat[c] = 0.f;
+        colstat[256 + c] = 0.f;
+      }
+      epi_bar_sync();
+    };
+    if (p.stats != nullptr) {
+      for (int c = et; c < 512; c += 128) colstat[c] = 0.f;
+      epi_bar_sync();
+    }
     for (int tile = pair_id; tile < total_tiles; tile += npairs) {
       const int mp = tile % m_pairs;
       const int rest = tile / m_pairs;
@@ -592,6 +633,10 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int tb = row / p.TR, tr = row % p.TR;
       const int b = b0 + tb, m = m0 + tr;
       const bool valid = (mt < m_tiles) && (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
+      if (p.stats != nullptr && nt != stat_nt) {
+        if (stat_nt >= 0) flush_stats(stat_nt);
+        stat_nt = nt;
+      }
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.TN);
@@ -600,17 +645,17 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr && ks == 0) {
+          // bias_mod is a multiple of 64 and the chunk is 32-aligned: one modulo per chunk
+          // (scalar loads: bias vectors are 4-byte-aligned views of the flat parameter buffer)
+          const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
+        }
         if (valid && !(p.dbg & 4)) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr && ks == 0) {
-            // bias_mod is a multiple of 64 and the chunk is 32-aligned: one modulo per chunk
-            // (scalar loads: bias vectors are 4-byte-aligned views of the flat parameter buffer)
-            const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
-          }
           if (p.out_dtype == SG_F32) {
             float* o = reinterpret_cast<float*>(p.out) + obase + c0;
             if (p.ksplit == 1) {
@@ -641,11 +686,29 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
         }
+        if (p.stats != nullptr) {                      // warp-uniform branch: the reduction is warp-collective
+          float q[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j];
+            // the statistics describe the tensor the next kernel reads: round like the store did
+            if (p.out_dtype == SG_F16) x = __half2float(__float2half_rn(x));
+            else if (p.out_dtype == SG_BF16) x = __bfloat162float(__float2bfloat16_rn(x));
+            x = valid ? x : 0.f;
+            v[j] = x;
+            q[j] = x * x;
+          }
+          const float sx = warp_transpose_reduce(v, lane);
+          const float sq = warp_transpose_reduce(q, lane);
+          atomicAdd(colstat + c0 + lane, sx);
+          atomicAdd(colstat + 256 + c0 + lane, sq);
+        }
       }
       tc_fence_before();
       mbar_arrive_leader(&ctl->tmem_empty[acc]);      // 2 x 128 arrivals release the accumulator
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.stats != nullptr && stat_nt >= 0) flush_stats(stat_nt);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1174,6 +1237,7 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     const char* e = getenv("SEGAN_B200_DEBUG");
     p.dbg = e ? atoi(e) : 0;
   }
+  p.stats = q->bn_stats;
   CUtensorMap tmA0, tmA1, tmW;
   const int a_buf_rows = q->a_rows + 2 * q->a_halo;
   int rc = make_map3(&tmA0, q->a0, q->a_dtype, q->a0_c, a_buf_rows, q->batch, p.TR, p.TB);
@@ -1184,7 +1248,12 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   rc = make_map2(&tmW, q->w, q->w_dtype, q->kc, (int64_t)(q->d_hi + 4 - q->w_tap0 + 1) * q->nc, p.TN);
   if (rc) return rc;
   const int m_tiles_all = p.m_tiles_per_b * p.b_tiles;
-  if (g_cta_pair == 2 && m_tiles_all >= 2 && p.TR == 128 && p.TB == 1 && p.ksplit == 1 && q->d_hi - q->d_lo >= 2) {
+  if (q->bn_stats != nullptr) {
+    // fused BatchNorm statistics live in the CTA-pair kernel's epilogue
+    SG_CHECK_ARG(m_tiles_all >= 2 && p.ksplit == 1 && q->out_dtype != SG_F32 && q->n_lo == 0 && q->n_hi == q->nc);
+  }
+  if (g_cta_pair == 2 && m_tiles_all >= 2 && p.TR == 128 && p.TB == 1 && p.ksplit == 1 && q->d_hi - q->d_lo >= 2 &&
+      q->bn_stats == nullptr) {
     // A tile staged once per k-block and reused by every tap (tapgemm_f_tc3)
     static bool attr3 = false;
     if (!attr3) {
@@ -1207,7 +1276,7 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     SG_CHECK_LAUNCH();
     return SG_OK;
   }
-  if (g_cta_pair && m_tiles_all >= 2) {
+  if ((g_cta_pair || q->bn_stats != nullptr) && m_tiles_all >= 2) {
     // CTA-pair kernel: A box per CTA as before, weight box = TN/2 rows per CTA, M = 256 UMMA
     static bool attr2 = false;
     if (!attr2) {

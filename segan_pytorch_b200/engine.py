@@ -240,7 +240,9 @@ def _plan_f_split(rows_m, batch, ncols):
 
 def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dtype, out_rows, out_halo,
           m_lo, m_hi, batch, bias=None, bias_mod=0, n_lo=0, n_hi=None, d_lo=-4, d_hi=4, w_tap0=0,
-          out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0):
+          out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0, stats=None):
+    """stats: optional [SL][2][nc] float64 tensor: BatchNorm batch statistics of the output, fused into the
+    epilogue of the tcgen05 CTA-pair kernel (see sg_tapgemm_f.bn_stats)."""
     n_hi = nc if n_hi is None else n_hi
     a0_c = kc if a0_c is None else a0_c
     backend = default_backend() if backend is None else backend
@@ -269,6 +271,7 @@ def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dt
         q.bias, q.bias_mod = _p(bias), bias_mod
         q.batch, q.ksplit = nb, ksplit
         q.backend, q.tile_n = backend, tn
+        q.bn_stats = _p(stats)
         with _Prof("tapgemm_f", _tap_flops(taps, d_lo, d_hi, q.n_lo, q.n_hi, (m_hi - m_lo) * nb)):
             _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
 
@@ -874,6 +877,9 @@ class DiscriminatorEngine(_NetEngine):
             return None if shifts_dev is None else C.c_void_p(shifts_dev.data_ptr() + 4 * i)
         a, hp, ss, mi, hpb = [None] * nl, [None] * nl, [None] * nl, [None] * nl, [None] * nl
         stats = stat_arena(buf, "d.stats", [(SL, 2, fm[l]) for l in range(nl)], dev) if training else None
+        # BatchNorm statistics in the conv epilogue (tcgen05 CTA-pair kernel; needs >= 2 M tiles: B * L/4 >= 256)
+        eff_backend = default_backend() if self.backend is None else self.backend
+        fuse_stats = (training and FUSE_BN_STATS and eff_backend == BACKEND_TCGEN05 and B * Lq[-1] >= 256)
         for l in range(nl):
             cout = fm[l]
             a[l] = buf.get("d.a%d" % l, (B, Lq[l], cout), F16, dev)
@@ -886,7 +892,7 @@ class DiscriminatorEngine(_NetEngine):
                 self.wait_packed("small")
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
-                      d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+                      d_lo=0, d_hi=0, w_tap0=4, backend=self.backend, stats=stats[0] if fuse_stats else None)
             elif l == 0:
                 colb0 = None
                 _lib.call("sg_wave_conv_fwd", _p(x0), _p(x1), 2, B, L, int(shifts[0]),
@@ -896,13 +902,14 @@ class DiscriminatorEngine(_NetEngine):
                 self.wait_packed("Wf%d" % l)
                 run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
                       tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
-                      bias=bias, bias_mod=cout, backend=self.backend)
+                      bias=bias, bias_mod=cout, backend=self.backend, stats=stats[l] if fuse_stats else None)
             bn = m.enc_blocks[l].norm
             ss[l] = buf.get("d.ss%d" % l, (2, cout), F32, dev)
             mi[l] = buf.get("d.mi%d" % l, (2, cout), F32, dev)
             if training:
                 st2 = stats[l]
-                _lib.call("sg_bn_stats", _p(a[l]), SG_F16, B * Lq[l], cout, _p(st2), st)
+                if not (fuse_stats and (l > 0 or wave_on_tensor_cores())):
+                    _lib.call("sg_bn_stats", _p(a[l]), SG_F16, B * Lq[l], cout, _p(st2), st)
                 _lib.call("sg_bn_finalize", _p(st2), B * Lq[l], cout,
                           _p(self.pview("enc_blocks.%d.norm.weight" % l)),
                           _p(self.pview("enc_blocks.%d.norm.bias" % l)), self.eps, self.momentum,

@@ -205,6 +205,49 @@ def test_tapgemm_f_a_reuse(case):
         assert float(out[:, :, :n_lo].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("case", ["conv_fwd", "small_rows_two_ntiles", "wave_single_tap"])
+def test_tapgemm_f_fused_bn_stats(case):
+    """sg_tapgemm_f.bn_stats: the CTA-pair kernel's epilogue accumulates per-column sum / sum of squares of the
+    stored fp16 outputs (BatchNorm1d batch statistics) -- against the same statistics computed from the output."""
+    g = _gen(9)
+    d_lo, d_hi, w_tap0 = -4, 4, 0
+    if case == "conv_fwd":
+        B, cin, cout, R, halo = 5, 64, 128, 160, 4
+        kc, nc = 4 * cin, cout
+        w, taps = _packed_random("conv_fwd", cin, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+    elif case == "small_rows_two_ntiles":
+        B, cin, cout, R, halo = 33, 128, 512, 16, 4
+        kc, nc = 4 * cin, cout
+        w, taps = _packed_random("conv_fwd", cin, kc, nc, g, torch.float16)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+    else:
+        B, R, halo, kc, nc = 3, 512, 0, 64, 64
+        taps = E.tap_ranges("full", 0, kc, nc)
+        w = (torch.randn(1, nc, kc, generator=g) * 0.2).to(torch.float16).to(DEV)
+        a0 = torch.randn(B, R, kc, generator=g).to(torch.float16).to(DEV)
+        d_lo = d_hi = 0
+        w_tap0 = 4
+    bias = torch.randn(nc, generator=g).to(DEV)
+    out = torch.zeros(B, R, nc, dtype=torch.float16, device=DEV)
+    stats = torch.zeros(8, 2, nc, dtype=torch.float64, device=DEV)
+    E.run_f(a0, None, R, halo, SG_F16, w, SG_F16, kc, nc, taps, out, SG_F16, R, 0, 0, R, B, bias=bias, bias_mod=nc,
+            d_lo=d_lo, d_hi=d_hi, w_tap0=w_tap0, backend=BACKEND_TCGEN05, stats=stats)
+    ref_stats = torch.zeros(8, 2, nc, dtype=torch.float64, device=DEV)
+    _lib.call("sg_bn_stats", _p(out), SG_F16, B * R, nc, _p(ref_stats), _stream())
+    torch.cuda.synchronize()
+    o64 = out.double().reshape(-1, nc)
+    got = stats.sum(0)
+    assert rel_err(got[0], o64.sum(0)) <= 1e-5 and rel_err(got[1], (o64 * o64).sum(0)) <= 1e-5
+    assert rel_err(got, ref_stats.sum(0)) <= 1e-5
+    # and the output itself is what the un-fused launch writes
+    out2 = torch.zeros_like(out)
+    E.run_f(a0, None, R, halo, SG_F16, w, SG_F16, kc, nc, taps, out2, SG_F16, R, 0, 0, R, B, bias=bias, bias_mod=nc,
+            d_lo=d_lo, d_hi=d_hi, w_tap0=w_tap0, backend=BACKEND_TCGEN05)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("sms,case,B", [(8, "deconv_cat", 17), (8, "deconv_cat", 21), (8, "small_rows", 33),
                                         (8, "dgrad_halo", 9), (8, "dgrad_halo", 10)])
 def test_tapgemm_f_wave_split(monkeypatch, sms, case, B):
