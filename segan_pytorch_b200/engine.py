@@ -187,6 +187,7 @@ class _Prof(object):
 
 
 NUM_SMS = 148
+FUSE_BN_STATS = os.environ.get("SEGAN_B200_FUSE_BN_STATS", "1").lower() not in ("0", "off", "no", "false")
 # Off by default: measured per layer at batch 300 (profiles/r1_v4_layers_split.txt) the narrow-tile tail costs
 # about as much as the wave it replaces -- a tile's A-operand fill does not shrink with its width, so a
 # 64-wide tile is shared-memory-fill bound -- and only 1 of 12 shapes gained.
