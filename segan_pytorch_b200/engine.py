@@ -187,7 +187,10 @@ class _Prof(object):
 
 
 NUM_SMS = 148
-FUSE_BN_STATS = os.environ.get("SEGAN_B200_FUSE_BN_STATS", "1").lower() not in ("0", "off", "no", "false")
+# BatchNorm statistics in the conv epilogue (sg_tapgemm_f.bn_stats).  Off by default: measured in-process
+# (profiles/r1_v6_ab_bn_fusion.txt) the extra epilogue work costs what the separate 0.3 ms of bn_stats launches
+# cost -- the D conv GEMMs with short K are epilogue-bound -- so the fused path is kept tested but not used.
+FUSE_BN_STATS = os.environ.get("SEGAN_B200_FUSE_BN_STATS", "0").lower() not in ("0", "off", "no", "false")
 # Off by default: measured per layer at batch 300 (profiles/r1_v4_layers_split.txt) the narrow-tile tail costs
 # about as much as the wave it replaces -- a tile's A-operand fill does not shrink with its width, so a
 # 64-wide tile is shared-memory-fill bound -- and only 1 of 12 shapes gained.
