@@ -299,6 +299,10 @@ int sg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  * ------------------------------------------------------------------------------------------ */
 int sg_deemphasis(const float* y, int64_t n, float coef, float* x, void* stream);
 int sg_preemphasis(const float* x, int64_t n, float coef, float* y, void* stream);
+/* Input contract on the device (se_dataset.py:108-117,355-368): int16 PCM windows [n_windows][L] ->
+ * normalize_wave_minmax -> per-window pre_emphasize(coef) -> fp32 [n_windows][L] (coef <= 0: no pre-emphasis).
+ * Lets the loader ship 2 bytes per sample over PCIe and drops the host-side preprocessing. */
+int sg_pcm16_to_wave(const int16_t* pcm, int64_t n_windows, int L, float coef, float* out, void* stream);
 
 #ifdef __cplusplus
 }

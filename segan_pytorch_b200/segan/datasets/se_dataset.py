@@ -63,13 +63,18 @@ class DevicePrefetcher(object):
     batch n trains, replacing the blocking `.to(device)` at the top of the reference's step
     (segan/models/model.py:288-290).  Yields [names, clean(B,1,L), noisy(B,1,L), slice_idx] with the
     two tensors resident on `device` and the consumer's stream ordered after their copies.
-    Pinned source tensors (DataLoader(pin_memory=True)) make the copies truly asynchronous."""
+    Pinned source tensors (DataLoader(pin_memory=True)) make the copies truly asynchronous.
+    Batches may also arrive as int16 PCM (what the wav files hold): they cross the link at 2 bytes per sample
+    and are normalised + pre-emphasised per window on the device (`sg_pcm16_to_wave`)."""
 
-    def __init__(self, loader, device, depth=2):
+    def __init__(self, loader, device, depth=2, preemph=0.95):
+        """preemph: pre-emphasis coefficient applied ON THE DEVICE to batches that arrive as int16 PCM (see
+        `_stage`); float batches are taken as already normalised + pre-emphasised, like SEDataset's."""
         self.loader = loader
         self.device = torch.device(device)
         self.depth = max(2, int(depth))
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.preemph = float(preemph)
         self.h2d_bytes = 0
 
     def __len__(self):
@@ -78,20 +83,35 @@ class DevicePrefetcher(object):
     def _stage(self, batch, slot):
         names, clean, noisy, slice_idx = batch
         clean, noisy = torch.as_tensor(clean), torch.as_tensor(noisy)
-        if clean.dtype != torch.float32:
+        pcm = clean.dtype == torch.int16
+        if not pcm and clean.dtype != torch.float32:
             clean, noisy = clean.float(), noisy.float()
         shape = (clean.shape[0], 1, clean.shape[-1])
         if slot.get("clean") is None or tuple(slot["clean"].shape) != shape:
             slot["clean"] = torch.empty(shape, dtype=torch.float32, device=self.device)
             slot["noisy"] = torch.empty(shape, dtype=torch.float32, device=self.device)
+        if pcm and (slot.get("pcm") is None or tuple(slot["pcm"].shape) != (2,) + shape):
+            slot["pcm"] = torch.empty((2,) + shape, dtype=torch.int16, device=self.device)
         with torch.cuda.stream(self.copy_stream):
             if slot.get("free") is not None:
                 self.copy_stream.wait_event(slot["free"])      # the step that read this slot has finished
-            slot["clean"].copy_(clean.reshape(shape), non_blocking=True)
-            slot["noisy"].copy_(noisy.reshape(shape), non_blocking=True)
+            if pcm:
+                # int16 PCM over the link (2 B/sample), normalisation + per-window pre-emphasis on the device
+                # (se_dataset.py:108-117 done by sg_pcm16_to_wave instead of the host)
+                from ... import _lib
+                import ctypes as C
+                slot["pcm"][0].copy_(clean.reshape(shape), non_blocking=True)
+                slot["pcm"][1].copy_(noisy.reshape(shape), non_blocking=True)
+                st = C.c_void_p(self.copy_stream.cuda_stream)
+                for i, dst in enumerate((slot["clean"], slot["noisy"])):
+                    _lib.call("sg_pcm16_to_wave", C.c_void_p(slot["pcm"][i].data_ptr()), shape[0], shape[2],
+                              self.preemph, C.c_void_p(dst.data_ptr()), st)
+            else:
+                slot["clean"].copy_(clean.reshape(shape), non_blocking=True)
+                slot["noisy"].copy_(noisy.reshape(shape), non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
-        self.h2d_bytes += 2 * clean.numel() * 4
+        self.h2d_bytes += 2 * clean.numel() * (2 if pcm else 4)
         return names, slot, slice_idx, ready
 
     def __iter__(self):

@@ -304,6 +304,25 @@ def test_generate_chunked_vs_reference(segan):
     assert tuple(g_c.shape) == (1, 1024, 16)
 
 
+def test_prefetcher_pcm16_path_matches_host_preprocessing():
+    """int16 PCM batches staged by DevicePrefetcher are normalised + pre-emphasised per window on the device
+    (sg_pcm16_to_wave) exactly like se_dataset.py:108-117 does on the host."""
+    from segan_pytorch_b200.segan.datasets import DevicePrefetcher, normalize_wave_minmax, pre_emphasize
+    rng = np.random.RandomState(4)
+    batches = []
+    for _ in range(3):
+        c = rng.randint(-32768, 32768, size=(4, 16384)).astype(np.int16)
+        n = rng.randint(-32768, 32768, size=(4, 16384)).astype(np.int16)
+        batches.append([None, torch.from_numpy(c).pin_memory(), torch.from_numpy(n).pin_memory(), None])
+    got = [(c.cpu().clone(), n.cpu().clone()) for _, c, n, _ in DevicePrefetcher(iter(batches), DEV, preemph=0.95)]
+    assert len(got) == 3
+    for (gc, gn), (_, c, n, _) in zip(got, batches):
+        for g, src in ((gc, c), (gn, n)):
+            ref = np.stack([pre_emphasize(normalize_wave_minmax(w.astype(np.float32)), 0.95) for w in src.numpy()])
+            assert g.shape == (4, 1, 16384)
+            assert max_abs(g[:, 0], ref) <= 2e-6
+
+
 def test_generate_stream_matches_direct_forward(segan):
     """Streaming inference (BASELINE config 5): batches go host -> device -> G -> host on three overlapping
     streams; every yielded batch equals the direct forward of the same windows."""
