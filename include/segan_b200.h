@@ -258,6 +258,10 @@ int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, int roll, con
                      const float* scale_shift, const float* mean_invstd, const float* slope,
                      int act, const double* red, int use_bn, void* g_a, void* stream);
 int sg_stat_grads(const double* red, int C, int n_stats, float* g0, float* g1, float* g2, void* stream);
+/* out[r][col0 + c] = (16-bit) ws[r][col0 + c], c < ncols: ws (fp32) and out share the geometry [rows][ld].  Final
+ * step of a split-K tail launch of sg_tapgemm_f_run (fp32 partial sums accumulated with ksplit > 1). */
+int sg_convert_f32_rows(const float* ws, void* out, int dtype, int64_t rows, int ld, int col0, int ncols,
+                        void* stream);
 /* fp32 NCL [B][C][L] <-> 16-bit NLC [B][L][C] (z input, generator.py:195-205; ret_hid outputs) */
 int sg_ncl_to_nlc(const float* src, int batch, int C, int L, void* dst, int dtype, void* stream);
 int sg_nlc_to_ncl(const void* src, int dtype, int batch, int C, int L, float* dst, void* stream);

@@ -66,6 +66,7 @@ _SIGS = {
     "sg_act_bwd_reduce": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "sg_act_bwd_apply": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "sg_stat_grads": [_vp, _i, _i, _vp, _vp, _vp, _vp],
+    "sg_convert_f32_rows": [_vp, _vp, _i, _i64, _i, _i, _i, _vp],
     "sg_ncl_to_nlc": [_vp, _i, _i, _i, _vp, _i, _vp],
     "sg_nlc_to_ncl": [_vp, _i, _i, _i, _i, _vp, _vp],
     "sg_colsum": [_vp, _i, _i64, _i, _i, _vp, _i, _vp, _vp],

@@ -990,6 +990,33 @@ extern "C" int sg_stat_grads(const double* red, int C, int n_stats, float* g0, f
   return SG_OK;
 }
 
+// out[r][col0 + c] = (16-bit) ws[r][col0 + c]: final step of a split-K tail (fp32 partial sums -> the layer's tensor)
+__global__ void convert_f32_rows_kernel(const float* __restrict__ ws, void* __restrict__ out, int dtype, int64_t rows,
+                                        int ld, int col0, int ncols) {
+  const int64_t total = rows * (ncols / 8);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (ncols / 8);
+    const int c = (int)(i % (ncols / 8)) * 8;
+    const int64_t off = r * ld + col0 + c;
+    const float4 a = *reinterpret_cast<const float4*>(ws + off);
+    const float4 b = *reinterpret_cast<const float4*>(ws + off + 4);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    stv<8>(out, off, x, dtype);
+  }
+}
+
+extern "C" int sg_convert_f32_rows(const float* ws, void* out, int dtype, int64_t rows, int ld, int col0, int ncols,
+                                   void* stream) {
+  SG_CHECK_ARG(ws && out && rows > 0 && ncols > 0 && ncols % 8 == 0 && col0 % 8 == 0 && ld % 8 == 0);
+  SG_CHECK_ARG(dtype == SG_F16 || dtype == SG_BF16);
+  const int64_t total = rows * (ncols / 8);
+  int64_t g = (total + 255) / 256;
+  if (g > 8 * NUM_SMS) g = 8 * NUM_SMS;
+  convert_f32_rows_kernel<<<(int)g, 256, 0, ST>>>(ws, out, dtype, rows, ld, col0, ncols);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
 extern "C" int sg_ncl_to_nlc(const float* src, int batch, int C, int L, void* dst, int dtype, void* stream) {
   dim3 grid((L + 31) / 32, (C + 31) / 32, batch), block(32, 8);
   ncl_to_nlc_kernel<<<grid, block, 0, ST>>>(src, C, L, dst, dtype);

@@ -242,6 +242,32 @@ def _plan_f_split(rows_m, batch, ncols):
     return b1, (best[1] if best[1] < tn else 0)
 
 
+SPLITK_TAIL = os.environ.get("SEGAN_B200_SPLITK_TAIL", "0").lower() not in ("0", "off", "no", "false")
+
+
+def _plan_f_tail_splitk(rows_m, batch, ncols, ksteps):
+    """Split-K tail against wave quantisation: (B1, s).  The first B1 batch elements run as whole waves; the
+    leftover tiles (fewer than half a wave) run as a second launch whose k-steps are split s ways over the idle
+    CTA pairs, accumulating fp32 partial sums that a small kernel converts.  Unlike narrow tiles, a split's
+    operand fill shrinks with its work.  (batch, 0) when it does not apply."""
+    pairs_hw = NUM_SMS // 2
+    tb, mpb, tn, tiles, gran = _f_tiling(rows_m, batch, ncols)
+    waves = -(-tiles // pairs_hw)
+    rem = tiles % pairs_hw
+    if tiles <= pairs_hw or rem == 0 or waves > 10:
+        return batch, 0
+    per_gran = _f_tiling(rows_m, gran, ncols)[3]
+    full_tiles = (tiles // pairs_hw) * pairs_hw
+    b1 = min(batch, (full_tiles // per_gran) * gran)
+    if b1 <= 0 or b1 >= batch:
+        return batch, 0
+    tail_tiles = _f_tiling(rows_m, batch - b1, ncols)[3]
+    s = min(pairs_hw // max(1, tail_tiles), ksteps // 4, 32)
+    if s < 2:
+        return batch, 0
+    return b1, s
+
+
 def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dtype, out_rows, out_halo,
           m_lo, m_hi, batch, bias=None, bias_mod=0, n_lo=0, n_hi=None, d_lo=-4, d_hi=4, w_tap0=0,
           out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0, stats=None):
@@ -250,14 +276,25 @@ def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dt
     n_hi = nc if n_hi is None else n_hi
     a0_c = kc if a0_c is None else a0_c
     backend = default_backend() if backend is None else backend
-    b1, tail_tn = batch, 0
-    if SPLIT_WAVES and backend == BACKEND_TCGEN05 and ksplit == 1 and batch > 1:
-        b1, tail_tn = _plan_f_split(m_hi - m_lo, batch, n_hi - n_lo)
+    b1, tail_tn, tail_ks = batch, 0, 0
+    if backend == BACKEND_TCGEN05 and ksplit == 1 and batch > 1 and stats is None:
+        if SPLITK_TAIL and out_dtype != SG_F32 and m_lo == -out_halo and m_hi == out_rows + out_halo:
+            ksteps = sum((taps[1][d + 4] - taps[0][d + 4]) // 64 for d in range(d_lo, d_hi + 1))
+            b1, tail_ks = _plan_f_tail_splitk(m_hi - m_lo, batch, n_hi - n_lo, ksteps)
+        elif SPLIT_WAVES:
+            b1, tail_tn = _plan_f_split(m_hi - m_lo, batch, n_hi - n_lo)
     esz = 4 if out_dtype == SG_F32 else 2
     old = (out_ld if out_ld > 0 else nc)
+    out_brows = out_rows + 2 * out_halo
+    ws = None
+    if tail_ks:
+        # fp32 workspace with the geometry of the tail's slice of `out` (from the caching allocator: per stream,
+        # static inside a captured graph)
+        ws = torch.zeros((batch - b1) * out_brows * old, dtype=torch.float32, device=out.device)
     for b_off, nb, tn in ((0, b1, 0), (b1, batch - b1, tail_tn)):
         if nb <= 0:
             continue
+        tail = b_off > 0 and tail_ks > 0
         q = TapGemmF()
         a_stride = (a_rows + 2 * a_halo) * 2
         q.a0 = _p(a0) if b_off == 0 else C.c_void_p(a0.data_ptr() + b_off * a_stride * a0_c)
@@ -268,16 +305,24 @@ def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dt
         q.kc, q.nc, q.d_lo, q.d_hi = kc, nc, d_lo, d_hi
         for i in range(9):
             q.tap_k_lo[i], q.tap_k_hi[i], q.tap_n_lo[i], q.tap_n_hi[i] = taps[0][i], taps[1][i], taps[2][i], taps[3][i]
-        q.out = _p(out) if b_off == 0 else C.c_void_p(out.data_ptr() + b_off * (out_rows + 2 * out_halo) * old * esz)
+        if tail:
+            q.out = _p(ws)
+        else:
+            q.out = _p(out) if b_off == 0 else C.c_void_p(out.data_ptr() + b_off * out_brows * old * esz)
         q.out_ld, q.out_col0 = out_ld, out_col0
-        q.out_dtype, q.out_rows, q.out_halo = out_dtype, out_rows, out_halo
+        q.out_dtype, q.out_rows, q.out_halo = (SG_F32 if tail else out_dtype), out_rows, out_halo
         q.m_lo, q.m_hi, q.n_lo, q.n_hi = m_lo, m_hi, n_lo, n_hi
         q.bias, q.bias_mod = _p(bias), bias_mod
-        q.batch, q.ksplit = nb, ksplit
+        q.batch, q.ksplit = nb, (tail_ks if tail else ksplit)
         q.backend, q.tile_n = backend, tn
         q.bn_stats = _p(stats)
         with _Prof("tapgemm_f", _tap_flops(taps, d_lo, d_hi, q.n_lo, q.n_hi, (m_hi - m_lo) * nb)):
             _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
+        if tail:
+            # columns the launch wrote: [col_lo, col_lo + n_hi - n_lo) of every row of the slice
+            col_lo = out_col0 if out_ld > 0 else n_lo
+            _lib.call("sg_convert_f32_rows", _p(ws), C.c_void_p(out.data_ptr() + b_off * out_brows * old * esz),
+                      out_dtype, nb * out_brows, old, col_lo, n_hi - n_lo, _stream())
 
 
 def run_w(g, g_rows, g_dtype, a0, a1, a_rows, a_halo, a_dtype, kc, nc, taps, dw, batch, d_lo=-4, d_hi=4,

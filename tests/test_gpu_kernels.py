@@ -248,14 +248,16 @@ def test_tapgemm_f_fused_bn_stats(case):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("mode", ["narrow", "splitk"])
 @pytest.mark.parametrize("sms,case,B", [(8, "deconv_cat", 17), (8, "deconv_cat", 21), (8, "small_rows", 33),
                                         (8, "dgrad_halo", 9), (8, "dgrad_halo", 10)])
-def test_tapgemm_f_wave_split(monkeypatch, sms, case, B):
+def test_tapgemm_f_wave_split(monkeypatch, sms, case, B, mode):
     """engine.run_f splits a launch whose tile count is just over a multiple of the CTA pairs into whole
     waves of full-width tiles plus a tail of narrow tiles on a batch sub-range (pointer offsets, tile_n
     hint).  The SM count is patched down so that small test shapes take that path."""
     monkeypatch.setattr(E, "NUM_SMS", sms)
-    monkeypatch.setattr(E, "SPLIT_WAVES", True)
+    monkeypatch.setattr(E, "SPLIT_WAVES", mode == "narrow")
+    monkeypatch.setattr(E, "SPLITK_TAIL", mode == "splitk")     # tail = split-K into fp32 + convert kernel
     g = _gen(4)
     a1, a1_c, bias = None, 0, None
     if case == "deconv_cat":
@@ -282,7 +284,13 @@ def test_tapgemm_f_wave_split(monkeypatch, sms, case, B):
         a0 = torch.randn(B, R, kc, generator=g).to(torch.bfloat16).to(DEV)
         m_lo, m_hi, out_rows, out_halo = -4, R + 4, R, 4
         adt, odt, tdt = SG_BF16, SG_BF16, torch.bfloat16
-    b1, tn = E._plan_f_split(m_hi - m_lo, B, nc)
+    if mode == "narrow":
+        b1, tn = E._plan_f_split(m_hi - m_lo, B, nc)
+    else:
+        ksteps = sum((taps[1][i] - taps[0][i]) // 64 for i in range(9))
+        b1, tn = E._plan_f_tail_splitk(m_hi - m_lo, B, nc, ksteps)
+        if not (0 < b1 < B):
+            pytest.skip("no split-K tail for this shape")
     assert 0 < b1 < B, (b1, tn)                       # the split path is what this test exercises
     out = torch.zeros(B, out_rows + 2 * out_halo, nc, dtype=tdt, device=DEV)
     E.run_f(a0, a1, R, halo, adt, w, adt, kc, nc, taps, out, odt, out_rows, out_halo, m_lo, m_hi, B,

@@ -22,6 +22,8 @@ def timeit(name, fn, flops):
     lib = _lib.load()
     if COMPARE == "areuse":
         settings = [("areuse", lambda: lib.sg_set_cta_pair(2)), ("pair", lambda: lib.sg_set_cta_pair(1))]
+    elif COMPARE == "splitk":
+        settings = [("splitk", lambda: setattr(E, "SPLITK_TAIL", True)), ("plain", lambda: setattr(E, "SPLITK_TAIL", False))]
     elif COMPARE == "compare":
         settings = [("split", lambda: setattr(E, "SPLIT_WAVES", True)), ("unsplit", lambda: setattr(E, "SPLIT_WAVES", False))]
     else:
