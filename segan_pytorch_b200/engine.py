@@ -242,6 +242,8 @@ def _plan_f_split(rows_m, batch, ncols):
     return b1, (best[1] if best[1] < tn else 0)
 
 
+# Off by default: bit-correct, but the two extra launches (tail GEMM + convert) and the tail kernel's own prologue
+# cost more than the partial wave they remove (profiles/r1_v6_splitk_tail.txt: 0-10 % slower per layer).
 SPLITK_TAIL = os.environ.get("SEGAN_B200_SPLITK_TAIL", "0").lower() not in ("0", "off", "no", "false")
 
 
