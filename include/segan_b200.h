@@ -303,10 +303,14 @@ int sg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  * ------------------------------------------------------------------------------------------ */
 int sg_deemphasis(const float* y, int64_t n, float coef, float* x, void* stream);
 int sg_preemphasis(const float* x, int64_t n, float coef, float* y, void* stream);
-/* Input contract on the device (se_dataset.py:108-117,355-368): int16 PCM windows [n_windows][L] ->
- * normalize_wave_minmax -> per-window pre_emphasize(coef) -> fp32 [n_windows][L] (coef <= 0: no pre-emphasis).
- * Lets the loader ship 2 bytes per sample over PCIe and drops the host-side preprocessing. */
-int sg_pcm16_to_wave(const int16_t* pcm, int64_t n_windows, int L, float coef, float* out, void* stream);
+/* Input contract on the device (se_dataset.py:108-117,191-199,355-368): int16 PCM windows [n_windows][L] ->
+ * normalize_wave_minmax -> pre_emphasize(coef) -> fp32 [n_windows][L] (coef <= 0: no pre-emphasis).  The reference
+ * pre-emphasises the whole file before slicing: prev[w] (int32, or NULL) is the PCM sample that precedes window w in
+ * its file, SG_PCM_NO_PREV when the window starts the file (y[0] = x[0]).  Lets the loader ship 2 bytes per sample
+ * over PCIe and drops the host-side preprocessing. */
+#define SG_PCM_NO_PREV 0x7fffffff
+int sg_pcm16_to_wave(const int16_t* pcm, const int32_t* prev, int64_t n_windows, int L, float coef, float* out,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libsegan_b200.so")
 SG_F32, SG_F16, SG_BF16 = 0, 1, 2
 ACT_NONE, ACT_PRELU, ACT_TANH = 0, 1, 2
 EW_ACT_FWD, EW_BN_STATS, EW_BWD_REDUCE, EW_BWD_APPLY = 1, 2, 3, 4
+PCM_NO_PREV = 0x7fffffff
 BACKEND_FFMA, BACKEND_TCGEN05 = 0, 1
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -77,7 +78,7 @@ _SIGS = {
     "sg_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp],
     "sg_deemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_preemphasis": [_vp, _i64, _f, _vp, _vp],
-    "sg_pcm16_to_wave": [_vp, _i64, _i, _f, _vp, _vp],
+    "sg_pcm16_to_wave": [_vp, _vp, _i64, _i, _f, _vp, _vp],
 }
 EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair", "sg_set_ew_variant"] + list(_SIGS)
 

@@ -347,24 +347,30 @@ extern "C" int sg_deemphasis(const float* y, int64_t n, float coef, float* x, vo
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
-// int16 PCM windows -> network input: normalize_wave_minmax (se_dataset.py:108-109) then, per window,
-// pre_emphasize (se_dataset.py:111-117): y[0] = x[0], y[n] = x[n] - coef * x[n-1].
-__global__ void pcm16_to_wave_kernel(const int16_t* __restrict__ pcm, int64_t total, int L, float coef,
-                                     float* __restrict__ out) {
+// int16 PCM windows -> network input: normalize_wave_minmax (se_dataset.py:108-109) then pre_emphasize
+// (se_dataset.py:111-117): y[n] = x[n] - coef * x[n-1].  The reference pre-emphasises the WHOLE file before
+// slicing (read_wav_file, se_dataset.py:191-199), so the sample before a window matters: prev[w] holds it (int32;
+// SG_PCM_NO_PREV = the window starts the file, y[0] = x[0]); prev == NULL treats every window as a file start.
+__global__ void pcm16_to_wave_kernel(const int16_t* __restrict__ pcm, const int32_t* __restrict__ prev, int64_t total,
+                                     int L, float coef, float* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const float x = (2.f / 65535.f) * ((float)pcm[i] - 32767.f) + 1.f;
     float y = x;
-    if (coef > 0.f && (i % L) != 0) {
-      const float xp = (2.f / 65535.f) * ((float)pcm[i - 1] - 32767.f) + 1.f;
-      y = x - coef * xp;
+    if (coef > 0.f) {
+      const int n = (int)(i % L);
+      int p = SG_PCM_NO_PREV;
+      if (n != 0) p = pcm[i - 1];
+      else if (prev) p = prev[i / L];
+      if (p != SG_PCM_NO_PREV) y = x - coef * ((2.f / 65535.f) * ((float)p - 32767.f) + 1.f);
     }
     out[i] = y;
   }
 }
 
-extern "C" int sg_pcm16_to_wave(const int16_t* pcm, int64_t n_windows, int L, float coef, float* out, void* stream) {
+extern "C" int sg_pcm16_to_wave(const int16_t* pcm, const int32_t* prev, int64_t n_windows, int L, float coef,
+                                float* out, void* stream) {
   SG_CHECK_ARG(pcm && out && n_windows > 0 && L > 0);
-  pcm16_to_wave_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(pcm, n_windows * L, L, coef, out);
+  pcm16_to_wave_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(pcm, prev, n_windows * L, L, coef, out);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

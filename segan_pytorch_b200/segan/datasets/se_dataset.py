@@ -2,8 +2,14 @@
 int16 PCM -> normalize_wave_minmax -> pre_emphasize(0.95) -> 16384-sample (clean, noisy) windows,
 collated as [names, clean(B,16384), noisy(B,16384), slice_idx(B)].
 
-The wav-directory dataset itself (pickle cache + per-sample WAV reads) is a SURVEY.md 8(f)-N3
-"next" row; BASELINE.json's configs use synthetic pairs, provided here by SyntheticSEDataset."""
+SEDataset is the wav-directory dataset: the reference's slicing and preprocessing
+(se_dataset.py:66-94,128-368) without its per-item pickle + double WAV read -- decoded files are kept in a
+small cache -- and with an int16 mode whose windows are normalised + pre-emphasised on the GPU.
+BASELINE.json's configs use synthetic pairs, provided by SyntheticSEDataset."""
+import glob
+import os
+import random
+from collections import OrderedDict
 import numpy as np
 import torch
 from torch.utils.data.dataset import Dataset
@@ -81,7 +87,8 @@ class DevicePrefetcher(object):
         return len(self.loader)
 
     def _stage(self, batch, slot):
-        names, clean, noisy, slice_idx = batch
+        names, clean, noisy, slice_idx = batch[:4]
+        prevs = batch[4] if len(batch) > 4 else None          # (B, 2) int32: sample before each clean / noisy window
         clean, noisy = torch.as_tensor(clean), torch.as_tensor(noisy)
         pcm = clean.dtype == torch.int16
         if not pcm and clean.dtype != torch.float32:
@@ -102,9 +109,15 @@ class DevicePrefetcher(object):
                 import ctypes as C
                 slot["pcm"][0].copy_(clean.reshape(shape), non_blocking=True)
                 slot["pcm"][1].copy_(noisy.reshape(shape), non_blocking=True)
+                pv = None
+                if prevs is not None:
+                    # (2, B) int32 on the device: the PCM sample preceding every window in its file
+                    pv = torch.as_tensor(prevs, dtype=torch.int32).t().contiguous().to(self.device, non_blocking=True)
+                    slot["prev"] = pv
                 st = C.c_void_p(self.copy_stream.cuda_stream)
                 for i, dst in enumerate((slot["clean"], slot["noisy"])):
-                    _lib.call("sg_pcm16_to_wave", C.c_void_p(slot["pcm"][i].data_ptr()), shape[0], shape[2],
+                    _lib.call("sg_pcm16_to_wave", C.c_void_p(slot["pcm"][i].data_ptr()),
+                              C.c_void_p(pv[i].data_ptr()) if pv is not None else None, shape[0], shape[2],
                               self.preemph, C.c_void_p(dst.data_ptr()), st)
             else:
                 slot["clean"].copy_(clean.reshape(shape), non_blocking=True)
@@ -134,3 +147,90 @@ class DevicePrefetcher(object):
             free = torch.cuda.Event()
             free.record(torch.cuda.current_stream(self.device))            # everything enqueued for this batch
             slot["free"] = free
+
+
+class SEDataset(Dataset):
+    """Wav-directory speech-enhancement dataset with the reference's semantics (se_dataset.py:128-368):
+    pairs of 16 kHz wavs from `clean_dir` / `noisy_dir` (matched by sorted file name), every file normalised with
+    normalize_wave_minmax and pre-emphasised AS A WHOLE (read_wav_file, :191-199; `preemph_norm` swaps the
+    order), sliced into `slice_size` windows every int(slice_size * stride) samples (slice_signal_index, :66-94:
+    no partial tail window), one random scale per item.  Items: [basename, clean, noisy, slice_idx].
+
+    pcm16=True returns the windows as int16 PCM plus the sample preceding each window ([..., prev(2,)]):
+    DevicePrefetcher ships them at 2 bytes per sample and sg_pcm16_to_wave applies the same normalisation and
+    whole-file pre-emphasis on the GPU (random_scale must be [1] and preemph_norm False in that mode).
+    Differences from the reference: no pickle cache on disk (`cache_dir` is accepted and ignored), decoded files
+    are kept in a per-process LRU, file pairs are matched by sorted name instead of glob order."""
+
+    NO_PREV = 0x7fffffff
+
+    def __init__(self, clean_dir, noisy_dir, preemph, cache_dir='.', split='train', slice_size=2 ** 14, stride=0.5,
+                 max_samples=None, do_cache=False, verbose=False, slice_workers=2, preemph_norm=False,
+                 random_scale=[1], pcm16=False, cache_files=64):
+        super(SEDataset, self).__init__()
+        from scipy.io import wavfile
+        self._wavfile = wavfile
+        self.clean_names = sorted(glob.glob(os.path.join(clean_dir, '*.wav')))
+        self.noisy_names = sorted(glob.glob(os.path.join(noisy_dir, '*.wav')))
+        if len(self.clean_names) != len(self.noisy_names) or len(self.clean_names) == 0:
+            raise ValueError('No wav data found! Check your data path please')
+        if max_samples is not None:
+            self.clean_names = self.clean_names[:max_samples]
+            self.noisy_names = self.noisy_names[:max_samples]
+        self.slice_size, self.stride, self.split = int(slice_size), stride, split
+        self.preemph, self.preemph_norm, self.random_scale = preemph, preemph_norm, list(random_scale)
+        self.pcm16 = bool(pcm16)
+        if self.pcm16 and (preemph_norm or any(r != 1 for r in self.random_scale)):
+            raise ValueError('pcm16=True needs preemph_norm=False and random_scale=[1]')
+        assert 0 < stride <= 1, stride
+        self._cache, self._cache_files = OrderedDict(), int(cache_files)
+        # slice_signal_index (se_dataset.py:66-94): windows [beg, beg + slice_size), beg += int(slice_size * stride)
+        offset = int(self.slice_size * stride)
+        self.idx2slice = []
+        for w_i, (c_path, n_path) in enumerate(zip(self.clean_names, self.noisy_names)):
+            n_samples = self._raw(c_path).shape[0]
+            for t_i, beg in enumerate(range(0, n_samples - self.slice_size + 1, offset)):
+                self.idx2slice.append((w_i, t_i, beg))
+
+    def __len__(self):
+        return len(self.idx2slice)
+
+    def _raw(self, path):
+        wav = self._cache.get(path)
+        if wav is None:
+            rate, wav = self._wavfile.read(path)
+            if wav.ndim != 1:
+                raise ValueError('mono wavs expected: %s' % path)
+            if wav.dtype != np.int16:
+                raise ValueError('16-bit PCM wavs expected: %s (%s)' % (path, wav.dtype))
+            self._cache[path] = wav
+            while len(self._cache) > self._cache_files:
+                self._cache.popitem(last=False)
+        else:
+            self._cache.move_to_end(path)
+        return wav
+
+    def read_wav_file(self, path):
+        """se_dataset.py:191-199 on the decoded int16 samples."""
+        wav = self._raw(path)
+        if self.preemph_norm:
+            return normalize_wave_minmax(pre_emphasize(wav, self.preemph))
+        return pre_emphasize(normalize_wave_minmax(wav), self.preemph)
+
+    def __getitem__(self, index):
+        w_i, t_i, beg = self.idx2slice[index]
+        c_path, n_path = self.clean_names[w_i], self.noisy_names[w_i]
+        bname = os.path.splitext(os.path.basename(n_path))[0]
+        end = beg + self.slice_size
+        if self.pcm16:
+            c, n = self._raw(c_path), self._raw(n_path)
+            prev = np.array([int(c[beg - 1]) if beg > 0 else self.NO_PREV,
+                             int(n[beg - 1]) if beg > 0 else self.NO_PREV], dtype=np.int32)
+            return [bname, torch.from_numpy(np.ascontiguousarray(c[beg:end])),
+                    torch.from_numpy(np.ascontiguousarray(n[beg:end])), t_i, torch.from_numpy(prev)]
+        c_slice = self.read_wav_file(c_path)[beg:end]
+        n_slice = self.read_wav_file(n_path)[beg:end]
+        rscale = random.choice(self.random_scale)
+        if rscale != 1:
+            c_slice, n_slice = rscale * c_slice, rscale * n_slice
+        return [bname, torch.FloatTensor(c_slice), torch.FloatTensor(n_slice), t_i]

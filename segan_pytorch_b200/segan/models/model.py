@@ -541,8 +541,11 @@ class SEGAN(Model):
             beg_t = timeit.default_timer()
             self.G.train()
             self.D.train()
+            if hasattr(getattr(dloader, 'sampler', None), 'set_epoch'):
+                dloader.sampler.set_epoch(epoch)                 # DistributedSampler: a new shuffle every epoch
             # batch n+1 is staged on the GPU (copy stream) while batch n trains
-            for bidx, batch in enumerate(DevicePrefetcher(dloader, device), start=1):
+            for bidx, batch in enumerate(DevicePrefetcher(dloader, device, preemph=getattr(opts, 'preemph', 0.95)),
+                                         start=1):
                 if epoch >= l1_dec_epoch:
                     if l1_weight > 0:
                         l1_weight -= l1_dec_step

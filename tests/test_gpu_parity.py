@@ -323,6 +323,25 @@ def test_prefetcher_pcm16_path_matches_host_preprocessing():
             assert max_abs(g[:, 0], ref) <= 2e-6
 
 
+def test_wav_dataset_pcm16_through_prefetcher_matches_float_mode(tmp_path):
+    """SEDataset(pcm16=True) -> DataLoader -> DevicePrefetcher: int16 windows + the sample before each window
+    cross the link and sg_pcm16_to_wave reproduces the reference's whole-file normalise + pre-emphasise windows
+    (SEDataset float mode = se_dataset.py:191-199,355-368, pinned against the reference in tests/test_dataset.py)."""
+    from torch.utils.data import DataLoader
+    from segan_pytorch_b200.segan.datasets import DevicePrefetcher, SEDataset, collate_fn
+    from tests.test_dataset import _make_wavs
+    cdir, ndir = _make_wavs(str(tmp_path), seed=5)
+    kw = dict(batch_size=3, shuffle=False, num_workers=0, collate_fn=collate_fn, drop_last=False)
+    ref_batches = list(DataLoader(SEDataset(cdir, ndir, 0.95), **kw))
+    pcm_loader = DataLoader(SEDataset(cdir, ndir, 0.95, pcm16=True), pin_memory=True, **kw)
+    n = 0
+    for (names, c, nz, idx), (rn, rc, rz, ridx) in zip(DevicePrefetcher(pcm_loader, DEV, preemph=0.95), ref_batches):
+        assert list(names) == list(rn) and c.shape == (rc.shape[0], 1, 16384)
+        assert max_abs(c[:, 0].cpu(), rc) <= 2e-6 and max_abs(nz[:, 0].cpu(), rz) <= 2e-6
+        n += 1
+    assert n == len(ref_batches) == 4
+
+
 def test_generate_stream_matches_direct_forward(segan):
     """Streaming inference (BASELINE config 5): batches go host -> device -> G -> host on three overlapping
     streams; every yielded batch equals the direct forward of the same windows."""

@@ -15,6 +15,21 @@ rng = np.random.RandomState(0)
 wavfile.write(sys.argv[1] + "/wavs/a.wav", 16000, (rng.randn(40000) * 3000).astype(np.int16))
 wavfile.write(sys.argv[1] + "/wavs/b.wav", 16000, (rng.randn(16384) * 3000).astype(np.int16))
 PY
+# the same entry point on wav directories (SEDataset, int16 windows preprocessed on the device)
+python - "$OUT" <<'PY'
+import os, sys, numpy as np
+from scipy.io import wavfile
+rng = np.random.RandomState(1)
+for d in ("clean_trainset", "noisy_trainset"):
+    os.makedirs(os.path.join(sys.argv[1], d))
+for i in range(6):
+    c = (rng.randn(60000) * 3000).astype(np.int16)
+    wavfile.write(os.path.join(sys.argv[1], "clean_trainset", "u%d.wav" % i), 16000, c)
+    wavfile.write(os.path.join(sys.argv[1], "noisy_trainset", "u%d.wav" % i), 16000,
+                  (c + rng.randn(60000) * 500).clip(-32768, 32767).astype(np.int16))
+PY
+python train.py --save_path "$OUT/ckpt_wav" --clean_trainset "$OUT/clean_trainset" --noisy_trainset "$OUT/noisy_trainset" \
+    --batch_size 8 --epoch 1 --save_freq 2 --num_workers 0
 G=$(ls "$OUT"/ckpt/*G*.ckpt | head -1)
 python clean.py --g_pretrained_ckpt "$G" --cfg_file "$OUT/ckpt/train.opts" --test_files "$OUT/wavs" --synthesis_path "$OUT/clean"
 python - "$OUT" <<'PY'

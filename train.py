@@ -2,8 +2,8 @@
 """train.py -- drop-in for the reference entry point (train.py:14-258): same flag names and
 defaults, same seeding, writes <save_path>/train.opts, trains SEGAN+ on the B200 engine.
 
-Additive flags only: --synthetic N (N synthetic windows instead of a wav directory -- the
-wav-directory dataset is a SURVEY.md 8(f)-N3 'next' row), --z_device {cpu,cuda}.
+Additive flags only: --synthetic N (N synthetic windows instead of --clean_trainset / --noisy_trainset wav
+directories), --z_device {cpu,cuda}.
 Data-parallel: launch with torchrun (one process per GPU); each rank trains on its own shard and
 gradients are all-reduced once per optimiser step."""
 import argparse
@@ -17,7 +17,7 @@ import torch.nn as nn
 from torch.utils.data import DataLoader
 
 from segan_pytorch_b200.segan.models import SEGAN, WSEGAN
-from segan_pytorch_b200.segan.datasets import SyntheticSEDataset, collate_fn
+from segan_pytorch_b200.segan.datasets import SEDataset, SyntheticSEDataset, collate_fn
 
 # (name, type, default) -- the reference's flag surface (train.py:102-245)
 FLAGS = [
@@ -80,13 +80,24 @@ def main(opts):
         segan.G.load_pretrained(opts.g_pretrained_ckpt, True)
     if opts.d_pretrained_ckpt is not None:
         segan.D.load_pretrained(opts.d_pretrained_ckpt, True)
-    if opts.synthetic <= 0:
-        raise SystemExit("wav-directory SEDataset is a SURVEY.md 8(f)-N3 'next' row: pass --synthetic N")
     random.seed(opts.seed + rank)          # per-rank data / z / phase-shift streams
     torch.manual_seed(opts.seed + rank)
-    dset = SyntheticSEDataset(opts.synthetic, opts.slice_size, seed=opts.seed + rank)
-    dloader = DataLoader(dset, batch_size=opts.batch_size, shuffle=True, num_workers=opts.num_workers,
-                         pin_memory=True, collate_fn=collate_fn, drop_last=True)
+    sampler = None
+    if opts.synthetic > 0:
+        dset = SyntheticSEDataset(opts.synthetic, opts.slice_size, seed=opts.seed + rank)
+    else:
+        # wav directories (train.py:52-60): int16 windows over the link, normalisation + pre-emphasis on the GPU
+        # whenever the options allow it (no random scaling, norm before pre-emphasis)
+        pcm16 = list(opts.random_scale) == [1] and not opts.preemph_norm
+        dset = SEDataset(opts.clean_trainset, opts.noisy_trainset, opts.preemph, cache_dir=opts.cache_dir,
+                         split='train', stride=opts.data_stride, slice_size=opts.slice_size,
+                         max_samples=opts.max_samples, preemph_norm=opts.preemph_norm,
+                         random_scale=opts.random_scale, pcm16=pcm16)
+        if world > 1:
+            from torch.utils.data.distributed import DistributedSampler
+            sampler = DistributedSampler(dset, num_replicas=world, rank=rank, shuffle=True, seed=opts.seed)
+    dloader = DataLoader(dset, batch_size=opts.batch_size, shuffle=(sampler is None), sampler=sampler,
+                         num_workers=opts.num_workers, pin_memory=True, collate_fn=collate_fn, drop_last=True)
     criterion = nn.MSELoss()
     segan.train(opts, dloader, criterion, opts.l1_weight, opts.l1_dec_step, opts.l1_dec_epoch, opts.save_freq,
                 va_dloader=None, device=device)
