@@ -257,31 +257,52 @@ def stft_logpow(x, n_fft=2048):
     return 10 * torch.log10(mod ** 2 + 10e-20)
 
 
+def interferer_squares(picks, length):
+    """model.py:606-622: per sample a square wave a * square(2 pi f t), t = linspace(0, 2, 32000), cut to
+    `length`; picks = [(f, a), ...] in the order `random.choice(freqs)`, `random.choice(amps)` are drawn."""
+    from scipy import signal
+    t = np.linspace(0, 2, 32000)
+    sq = [torch.FloatTensor((a_ * signal.square(2 * np.pi * f_ * t))[:length].reshape((1, -1))) for f_, a_ in picks]
+    return torch.cat(sq, dim=0).unsqueeze(1)
+
+
 def wsegan_train_step(sdG, sdD, optG, optD, clean, noisy, z, shifts4, perm, pow_weight=0.001,
-                      l1_weight=100.0, additive_mask=None, lr=5e-5, betas=(0.0, 0.9), opt="rmsprop"):
-    """One WSEGAN step with misalign_pair.  shifts4: D(real), D(fake.detach), D(clean,shuffled),
-    D(fake) in the order model.py consumes python `random` (the shuffle at :599 is passed in as
-    `perm`, a list of indices).  optG/optD: dict name -> state (square_avg for rmsprop)."""
+                      l1_weight=100.0, additive_mask=None, lr=5e-5, betas=(0.0, 0.9), opt="rmsprop",
+                      interf=None, vanilla_gan=False):
+    """One WSEGAN step (model.py:572-669).  shifts4: the D passes in the order model.py consumes python `random`:
+    D(real), D(fake.detach), [D(clean, shuffled) when perm is given (misalign_pair, :598-604)],
+    [D(clean + interf, noisy) when `interf` (the squares of :606-622) is given], D(fake).  vanilla_gan: BCE with
+    logits instead of MSE (:583-586).  optG/optD: dict name -> state (square_avg for rmsprop)."""
+    cost = F.binary_cross_entropy_with_logits if vanilla_gan else F.mse_loss
     with oracle_mode():
         pD = {k: sdD[k].detach().clone().requires_grad_(True) for k in _trainable(sdD)}
         pG = {k: sdG[k].detach().clone().requires_grad_(True) for k in _trainable(sdG)}
         fullD = lambda: {**sdD, **pD}
         fullG = lambda: {**sdG, **pG}
-        d_real = discriminator_forward(fullD(), torch.cat((clean, noisy), 1), shifts4[0])
-        d_real_loss = F.mse_loss(d_real, torch.ones_like(d_real))
+        sh = iter(shifts4)
+        d_real = discriminator_forward(fullD(), torch.cat((clean, noisy), 1), next(sh))
+        d_real_loss = cost(d_real, torch.ones_like(d_real))
         Genh = generator_forward(fullG(), noisy, z)
-        d_fake = discriminator_forward(fullD(), torch.cat((Genh.detach(), noisy), 1), shifts4[1])
-        d_fake_loss = F.mse_loss(d_fake, torch.zeros_like(d_fake))
-        clean_shuf = clean[perm]
-        d_shuf = discriminator_forward(fullD(), torch.cat((clean, clean_shuf), 1), shifts4[2])
-        d_shuf_loss = F.mse_loss(d_shuf, torch.zeros_like(d_shuf))
-        d_loss = (1.0 / 3) * (d_fake_loss + d_real_loss + d_shuf_loss)
+        d_fake = discriminator_forward(fullD(), torch.cat((Genh.detach(), noisy), 1), next(sh))
+        d_fake_loss = cost(d_fake, torch.zeros_like(d_fake))
+        d_weight = 0.5
+        d_loss = d_fake_loss + d_real_loss
+        if perm is not None:
+            clean_shuf = clean[perm]
+            d_shuf = discriminator_forward(fullD(), torch.cat((clean, clean_shuf), 1), next(sh))
+            d_weight = 1.0 / 3
+            d_loss = d_loss + cost(d_shuf, torch.zeros_like(d_shuf))
+        if interf is not None:
+            d_int = discriminator_forward(fullD(), torch.cat((clean + interf, noisy), 1), next(sh))
+            d_weight = 1.0 / 4                         # model.py:626: set to 1/4 whether or not misalign is on
+            d_loss = d_loss + cost(d_int, torch.zeros_like(d_int))
+        d_loss = d_weight * d_loss
         gD = dict(zip(pD.keys(), torch.autograd.grad(d_loss, list(pD.values()))))
         with torch.no_grad():
             for k in pD:
                 rmsprop_step(pD[k], gD[k], optD[k], lr)
-        d_fake_ = discriminator_forward(fullD(), torch.cat((Genh, noisy), 1), shifts4[3])
-        g_adv = F.mse_loss(d_fake_, torch.ones_like(d_fake_))
+        d_fake_ = discriminator_forward(fullD(), torch.cat((Genh, noisy), 1), next(sh))
+        g_adv = cost(d_fake_, torch.ones_like(d_fake_))
         pow_loss = pow_weight * F.l1_loss(stft_logpow(Genh), stft_logpow(clean))
         G_cost = g_adv + pow_loss
         den_loss = torch.zeros(1)

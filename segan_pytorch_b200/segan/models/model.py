@@ -614,22 +614,52 @@ class WSEGAN(SEGAN):
         mod = torch.norm(torch.view_as_real(st), 2, dim=3)
         return 10 * torch.log10(mod ** 2 + 10e-20)
 
+    def _d_pass(self, x0, x1, shifts, target, weight, losses, slot, input_grad=None, param_grads=True,
+                twins=True):
+        """One D forward + backward of `weight * cost(D(x0 | x1), target)`: LSGAN (MSE, fused into the head
+        backward kernel) or, with --vanilla_gan, BCE with logits (model.py:583-586; its gradient
+        (sigmoid(logit) - target) * weight / B is handed to the same backward)."""
+        de = self.D.engine
+        lptr = C.c_void_p(losses.data_ptr() + 4 * slot)
+        logit, c = de.forward(x0, x1, shifts, training=True, twins=twins)
+        if not self.vanilla_gan:
+            de.backward(c, target, weight, param_grads=param_grads, input_grad=input_grad, loss_out=lptr)
+            return
+        lg = logit.detach().view(-1)
+        tg = torch.full_like(lg, float(target))
+        losses[slot] += weight * F.binary_cross_entropy_with_logits(lg, tg)
+        g_logit = ((torch.sigmoid(lg) - tg) * (float(weight) / lg.numel())).contiguous()
+        de.backward(c, target, weight, param_grads=param_grads, input_grad=input_grad, loss_out=None, g_logit=g_logit)
+
+    @staticmethod
+    def interferer_squares(B, L, picks=None):
+        """model.py:606-622: per sample a square wave of random frequency {250, 1000, 4000} Hz and amplitude
+        {0.01, 0.05, 0.1, 1} (python `random.choice`, frequency first), t = linspace(0, 2, 32000), cut to L."""
+        from scipy import signal
+        freqs, amps = [250, 1000, 4000], [0.01, 0.05, 0.1, 1]
+        t = np.linspace(0, 2, 32000)
+        rows = []
+        for i in range(B):
+            f_, a_ = picks[i] if picks is not None else (random.choice(freqs), random.choice(amps))
+            rows.append(torch.FloatTensor((a_ * signal.square(2 * np.pi * f_ * t))[:L].reshape((1, -1))))
+        return torch.cat(rows, dim=0).unsqueeze(1)
+
     def train_step(self, clean, noisy, Gopt, Dopt, l1_weight, uttname=None, z=None, shifts=None, perm=None,
-                   losses=None):
-        """One WSEGAN step (model.py:572-669) with optional --misalign_pair.  Returns the device tensor
-        [d_loss, g_adv, pow_loss, den_loss].  Draw order of python `random` as in the reference:
-        D(real) shifts, [z], D(fake) shifts, shuffle, D(misaligned) shifts, D(fake) shifts."""
-        if self.interf_pair or self.vanilla_gan:
-            raise NotImplementedError("--interf_pair / --vanilla_gan are SURVEY.md 8(f)-N4 'next' rows")
+                   losses=None, interf=None):
+        """One WSEGAN step (model.py:572-669) with optional --misalign_pair / --interf_pair / --vanilla_gan.
+        Returns the device tensor [d_loss, g_adv, pow_loss, den_loss].  Draw order of python `random` as in the
+        reference: D(real) shifts, [z], D(fake) shifts, [shuffle, D(misaligned) shifts], [per sample: interferer
+        frequency, amplitude; D(interfered) shifts], D(fake) shifts.  `perm` / `interf` (the squares, (B,1,L))
+        override the draws (tests)."""
         ge, de = self.G.engine, self.D.engine
         B, _, L = clean.shape
         dev = clean.device
         nl = len(self.D.enc_blocks)
         losses = torch.zeros(4, dtype=torch.float32, device=dev) if losses is None else losses.zero_()
-        lptr = lambda i: C.c_void_p(losses.data_ptr() + 4 * i)
         nsh = iter(shifts) if shifts is not None else None
         draw = (lambda: next(nsh)) if nsh is not None else (lambda: draw_phase_shifts(nl, self.D.phase_shift))
-        d_weight = (1.0 / 3) if self.misalign_pair else 0.5
+        # model.py:595,603,626: 1/2, 1/3 with the misaligned pair, 1/4 whenever the interferer pair is on
+        d_weight = 0.25 if self.interf_pair else ((1.0 / 3) if self.misalign_pair else 0.5)
         # the G forward (model.py:583) does not depend on the D(real) pass before it: side stream 1.
         # (z comes from torch's generator, the phase shifts from python's `random`: drawing z first
         # changes neither sequence.)
@@ -639,23 +669,23 @@ class WSEGAN(SEGAN):
         with _engine.on_side(gside):
             Genh, gctx = ge.forward(noisy, z)
         Dopt.zero_grad()
-        _, c = de.forward(clean, noisy, draw(), training=True)
-        de.backward(c, 1.0, d_weight, param_grads=True, loss_out=lptr(0))
+        self._d_pass(clean, noisy, draw(), 1.0, d_weight, losses, 0)
         _engine.join_side(gside)
-        _, c = de.forward(Genh, noisy, draw(), training=True)
-        de.backward(c, 0.0, d_weight, param_grads=True, loss_out=lptr(0))
+        self._d_pass(Genh, noisy, draw(), 0.0, d_weight, losses, 0)
         if self.misalign_pair:
             if perm is None:
                 perm = list(range(B))
                 random.shuffle(perm)                                       # model.py:598-600
             clean_shuf = clean[torch.as_tensor(perm, device=dev)]
-            _, c = de.forward(clean, clean_shuf, draw(), training=True)
-            de.backward(c, 0.0, d_weight, param_grads=True, loss_out=lptr(0))
+            self._d_pass(clean, clean_shuf, draw(), 0.0, d_weight, losses, 0)
+        if self.interf_pair:
+            if interf is None:
+                interf = self.interferer_squares(B, L)                     # model.py:606-622
+            self._d_pass(clean + interf.to(dev), noisy, draw(), 0.0, d_weight, losses, 0)
         Dopt.step(allreduce_grads(de))
         Gopt.zero_grad()
-        _, c = de.forward(Genh, noisy, draw(), training=True, twins=False)
         gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
-        de.backward(c, 1.0, 1.0, param_grads=False, input_grad=gy, loss_out=lptr(1))
+        self._d_pass(Genh, noisy, draw(), 1.0, 1.0, losses, 1, input_grad=gy, param_grads=False, twins=False)
         # spectral power loss (model.py:638-653)
         gt = Genh.detach().requires_grad_(True)
         with torch.enable_grad():

@@ -390,15 +390,20 @@ def test_autograd_path_matches_fused_step(segan):
         assert v <= 8e-2, (k, v)
 
 
-def test_wsegan_step_vs_oracle():
-    """WSEGAN --misalign_pair step (model.py:572-669).  The reference's own WSEGAN.train cannot run on
-    CPU / torch>=2, so this compares with the oracle restatement (whose G / D / loss
-    building blocks are pinned): parity of this row is 'unpinned by the reference'."""
+@pytest.mark.parametrize("variant", ["misalign", "misalign+interf", "vanilla_gan"])
+def test_wsegan_step_vs_oracle(variant):
+    """WSEGAN step (model.py:572-669) with --misalign_pair, with --misalign_pair --interf_pair, and with
+    --vanilla_gan (BCE-with-logits D cost).  The reference's own WSEGAN.train cannot run on CPU / torch>=2
+    (SURVEY.md F4), so this compares with the oracle restatement (whose G / D / loss building blocks are
+    pinned): parity of this row is 'unpinned by the reference'."""
     from segan_pytorch_b200.segan.models import WSEGAN
     from tests.util import load_opts, seed_all
     B = 3
     seed_all(111)
-    opts = load_opts(batch_size=B, wsegan=True, misalign_pair=True)
+    misalign = variant != "vanilla_gan"
+    interf_on = variant == "misalign+interf"
+    vanilla = variant == "vanilla_gan"
+    opts = load_opts(batch_size=B, wsegan=True, misalign_pair=misalign, interf_pair=interf_on, vanilla_gan=vanilla)
     s = WSEGAN(opts)
     sdG, sdD = cpu_state(s.G), cpu_state(s.D)
     s = s.to(DEV)
@@ -409,17 +414,20 @@ def test_wsegan_step_vs_oracle():
     noisy = (clean + 0.1 * torch.randn(B, 1, 16384, generator=gen)).clamp(-1, 1)
     z = torch.randn(B, 1024, 16, generator=gen)
     random.seed(5)
-    shifts = [O.draw_phase_shifts(5, 5) for _ in range(4)]
-    perm = [2, 0, 1]
+    n_pass = 3 + int(misalign) + int(interf_on)
+    shifts = [O.draw_phase_shifts(5, 5) for _ in range(n_pass)]
+    perm = [2, 0, 1] if misalign else None
+    interf = O.interferer_squares([(250, 0.1), (4000, 0.05), (1000, 1)], 16384) if interf_on else None
     Gopt, Dopt = s.build_optimizers(opts)
     losses = s.train_step(clean.to(DEV), noisy.to(DEV), Gopt, Dopt, 100.0, uttname=["a", "b", "c"], z=z.to(DEV),
-                          shifts=shifts, perm=perm).tolist()
+                          shifts=shifts, perm=perm, interf=interf).tolist()
     sqG = {k: torch.zeros_like(sdG[k]) for k in O._trainable(sdG)}
     sqD = {k: torch.zeros_like(sdD[k]) for k in O._trainable(sdD)}
-    ref = O.wsegan_train_step(sdG, sdD, sqG, sqD, clean, noisy, z, shifts, perm, pow_weight=0.001, l1_weight=100.0)
-    print("wsegan losses", losses, [ref[k] for k in ("d_loss", "g_adv_loss", "pow_loss", "den_loss")])
+    ref = O.wsegan_train_step(sdG, sdD, sqG, sqD, clean, noisy, z, shifts, perm, pow_weight=0.001, l1_weight=100.0,
+                              interf=interf, vanilla_gan=vanilla)
+    print("wsegan", variant, "losses", losses, [ref[k] for k in ("d_loss", "g_adv_loss", "pow_loss", "den_loss")])
     for got, k in zip(losses, ("d_loss", "g_adv_loss", "pow_loss", "den_loss")):
-        assert abs(got - ref[k]) <= 3e-2 * max(1.0, abs(ref[k])), (k, got, ref[k])
+        assert abs(got - ref[k]) <= 3e-2 * max(1.0, abs(ref[k])), (variant, k, got, ref[k])
     rep = {k: rel_err(s.D.engine.gview(k).cpu(), g) for k, g in ref["gradsD"].items()
            if not (k.startswith("enc_blocks") and k.endswith("conv.bias"))}
     print("wsegan D grad rel errs (max):", max(rep.values()))
