@@ -219,8 +219,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        # NCCL_DEBUG is left as the launcher set it: fd 1 already points at stderr (_claim_stdout), so NCCL's INFO
+        # lines (communicator / rank evidence the driver greps for) cannot pollute the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from segan_pytorch_b200 import _lib, engine as E
     from tests.util import build_segan, load_opts
@@ -416,7 +416,7 @@ def main():
         "metric": "16384-sample windows/sec (G+D train step)", "value": value, "unit": "windows/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 operands / f32 accumulate (bf16 gradient tensors)", "data": "synthetic",
+        "dtype": "f16 operands / f32 accumulate (%s gradient tensors%s)" % (("f16", ", loss scale %g" % E.LOSS_SCALE) if E.GS == 1 else ("bf16", "")), "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "window": 16384,
                    "parallelism": "dp%d" % world, "optimizer": "rmsprop lr 5e-5", "l1_weight": 100,
                    "z": "device RNG (opts.z_device='cuda')", "backend": args.backend or "tcgen05",

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 2
+#define SG_ABI_VERSION 3
 
 /* Per-channel statistic buffers (sg_bn_stats `stats`, sg_act_bwd_* `red`, sg_colsum `tmp`) hold
  * SG_STAT_SLICES interleaved partial copies: [SG_STAT_SLICES][n_stats][C] doubles, zeroed by the caller;
@@ -82,6 +82,16 @@ int sg_set_cta_pair(int on);
 #define SG_EW_BWD_REDUCE 3
 #define SG_EW_BWD_APPLY 4
 int sg_set_ew_variant(int kind, int vec, int unroll, int cap);
+/* 16-bit format of every GRADIENT tensor the library reads or writes (the `g_*` arguments below, the col2im input,
+ * the D head's g_z1): SG_F16 (default) or SG_BF16.  Returns the previous setting.
+ * fp16 gradients carry 11 significant bits (bf16: 8) and share the forward tensors' format, so the weight-gradient
+ * tap-GEMM reads the forward activations directly (tcgen05 kind::f16 cannot mix f16 x bf16 operands: with bf16
+ * gradients every forward activation needs a bf16 twin).  Their narrower range is covered by a loss scale: the
+ * `grad_scale` argument of sg_fc_tail_bwd / sg_l1_loss_bwd multiplies the loss gradients at their source, every
+ * parameter gradient then carries the factor and the optimiser's `grad_scale` divides it out; 16-bit stores
+ * saturate at +-65504.  (autograd in model.py:299,306,320 keeps fp32 gradients: this is the precision contract
+ * of north_star's "fp16/bf16 sample windows".) */
+int sg_set_grad_dtype(int dtype);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-GEMM, forward form ("F"):
@@ -282,10 +292,10 @@ int sg_fc_tail_bwd(const float* z1, const float* z2, const float* logit,
                    const float* s1, const float* w2, const float* s3, const float* w4, int batch,
                    float* loss_out, void* g_z1_bf16, float* ws /* fp32 [B*(1+128+256+256)] */,
                    float* g_b0, float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4,
-                   float* g_b4, void* stream);
-/* G regression loss (model.py:318): loss = w * mean|y - clean| ; gy (+)= w*sign(y-clean)/(B*L) */
+                   float* g_b4, float grad_scale /* loss scale: multiplies g_logit (not loss_out) */, void* stream);
+/* G regression loss (model.py:318): loss = w * mean|y - clean| ; gy (+)= grad_scale*w*sign(y-clean)/(B*L) */
 int sg_l1_loss_bwd(const float* y, const float* clean, int64_t n, float weight, float* loss_out,
-                   float* gy, int accumulate, void* stream);
+                   float* gy, int accumulate, float grad_scale /* multiplies gy only */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimisers on flat fp32 buffers (torch.optim.RMSprop / Adam as used at model.py:221-225).

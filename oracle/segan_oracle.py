@@ -40,6 +40,35 @@ def oracle_mode():
 
 
 # --------------------------------------------------------------------------------------
+# operand-precision control (tests only).  The B200 path feeds its tensor cores 16-bit operands (fp16
+# activations and weights, fp32 accumulation) and stores layer outputs in fp16.  Inside
+# `with operand_precision(torch.float16):` the three contraction primitives below round their inputs, weights
+# and outputs the same way while everything else stays the fp32 reference arithmetic: the distance between this
+# control and the plain oracle is what the 16-bit operand FORMAT costs, independent of any kernel.  The parity
+# tests print it next to the kernels' own error.
+# --------------------------------------------------------------------------------------
+_OPERAND_DTYPE = None
+
+
+@contextlib.contextmanager
+def operand_precision(dtype):
+    global _OPERAND_DTYPE
+    prev = _OPERAND_DTYPE
+    _OPERAND_DTYPE = dtype
+    try:
+        yield
+    finally:
+        _OPERAND_DTYPE = prev
+
+
+def _q(t):
+    """Round-trip through the control's operand dtype (straight-through for autograd)."""
+    if _OPERAND_DTYPE is None or t is None:
+        return t
+    return t + (t.detach().to(_OPERAND_DTYPE).to(t.dtype) - t.detach())
+
+
+# --------------------------------------------------------------------------------------
 # blocks (segan/models/modules.py)
 # --------------------------------------------------------------------------------------
 def gconv_linear(x, weight, bias, stride=STRIDE):
@@ -47,8 +76,8 @@ def gconv_linear(x, weight, bias, stride=STRIDE):
     modules.py:91-99 -- P = (k//2 - 1, k//2) for stride > 1, (k//2, k//2) otherwise."""
     k = weight.shape[2]
     pad = (k // 2 - 1, k // 2) if stride > 1 else (k // 2, k // 2)
-    xp = F.pad(x, pad, mode="reflect")
-    return F.conv1d(xp, weight, bias, stride=stride)
+    xp = F.pad(_q(x), pad, mode="reflect")
+    return _q(F.conv1d(xp, _q(weight), bias, stride=stride))
 
 
 def prelu(a, w):
@@ -73,7 +102,9 @@ def gdeconv_linear(x, weight, bias, stride=STRIDE):
     the last output sample is dropped when k is odd."""
     k = weight.shape[2]
     pad = max(0, (stride - k) // -2)
-    h = F.conv_transpose1d(x, weight, bias, stride=stride, padding=pad)
+    h = F.conv_transpose1d(_q(x), _q(weight), bias, stride=stride, padding=pad)
+    if weight.shape[1] > 1:
+        h = _q(h)                             # hidden layers are stored in fp16; the waveform output is fp32
     if k % 2 != 0:
         h = h[:, :, :-1]
     return h
@@ -163,7 +194,7 @@ def discriminator_forward(sd, x, shifts, training=True, ret_act=False):
         h = prelu(a, sd[p + "act.weight"])
         acts["h_%d" % l] = h
     h = h.view(h.size(0), -1)                                     # discriminator.py:180-182
-    h = F.linear(h, sd["fc.0.weight"], sd["fc.0.bias"])
+    h = F.linear(_q(h), _q(sd["fc.0.weight"]), sd["fc.0.bias"])
     h = F.prelu(h, sd["fc.1.weight"])
     h = F.linear(h, sd["fc.2.weight"], sd["fc.2.bias"])
     h = F.prelu(h, sd["fc.3.weight"])
@@ -178,6 +209,21 @@ def discriminator_forward(sd, x, shifts, training=True, ret_act=False):
 def rmsprop_step(param, grad, square_avg, lr, alpha=0.99, eps=1e-8):
     square_avg.mul_(alpha).addcmul_(grad, grad, value=1 - alpha)
     param.addcdiv_(grad, square_avg.sqrt().add_(eps), value=-lr)
+
+
+def adam_step(param, grad, state, lr, betas=(0.0, 0.9), eps=1e-8):
+    """torch.optim.Adam (amsgrad False, no weight decay) as used at model.py:224-225 (betas (0, 0.9)).
+    state: dict with 'step', 'exp_avg', 'exp_avg_sq' (created on first use)."""
+    if "step" not in state:
+        state["step"], state["exp_avg"], state["exp_avg_sq"] = 0, torch.zeros_like(param), torch.zeros_like(param)
+    state["step"] += 1
+    b1, b2 = betas
+    state["exp_avg"].mul_(b1).add_(grad, alpha=1 - b1)
+    state["exp_avg_sq"].mul_(b2).addcmul_(grad, grad, value=1 - b2)
+    bc1 = 1 - b1 ** state["step"]
+    bc2 = 1 - b2 ** state["step"]
+    denom = (state["exp_avg_sq"].sqrt() / math.sqrt(bc2)).add_(eps)
+    param.addcdiv_(state["exp_avg"], denom, value=-lr / bc1)
 
 
 # --------------------------------------------------------------------------------------
@@ -272,8 +318,15 @@ def wsegan_train_step(sdG, sdD, optG, optD, clean, noisy, z, shifts4, perm, pow_
     """One WSEGAN step (model.py:572-669).  shifts4: the D passes in the order model.py consumes python `random`:
     D(real), D(fake.detach), [D(clean, shuffled) when perm is given (misalign_pair, :598-604)],
     [D(clean + interf, noisy) when `interf` (the squares of :606-622) is given], D(fake).  vanilla_gan: BCE with
-    logits instead of MSE (:583-586).  optG/optD: dict name -> state (square_avg for rmsprop)."""
+    logits instead of MSE (:583-586).  optG/optD: dict name -> state (the square_avg tensor for rmsprop; a dict
+    filled by adam_step for opt='adam', model.py:224-225)."""
     cost = F.binary_cross_entropy_with_logits if vanilla_gan else F.mse_loss
+
+    def opt_step(p, g, states, k):
+        if opt == "adam":
+            adam_step(p, g, states.setdefault(k, {}), lr, betas)
+        else:
+            rmsprop_step(p, g, states[k], lr)
     with oracle_mode():
         pD = {k: sdD[k].detach().clone().requires_grad_(True) for k in _trainable(sdD)}
         pG = {k: sdG[k].detach().clone().requires_grad_(True) for k in _trainable(sdG)}
@@ -300,7 +353,7 @@ def wsegan_train_step(sdG, sdD, optG, optD, clean, noisy, z, shifts4, perm, pow_
         gD = dict(zip(pD.keys(), torch.autograd.grad(d_loss, list(pD.values()))))
         with torch.no_grad():
             for k in pD:
-                rmsprop_step(pD[k], gD[k], optD[k], lr)
+                opt_step(pD[k], gD[k], optD, k)
         d_fake_ = discriminator_forward(fullD(), torch.cat((Genh, noisy), 1), next(sh))
         g_adv = cost(d_fake_, torch.ones_like(d_fake_))
         pow_loss = pow_weight * F.l1_loss(stft_logpow(Genh), stft_logpow(clean))
@@ -313,7 +366,7 @@ def wsegan_train_step(sdG, sdD, optG, optD, clean, noisy, z, shifts4, perm, pow_
         gG = dict(zip(pG.keys(), torch.autograd.grad(G_cost, list(pG.values()))))
         with torch.no_grad():
             for k in pG:
-                rmsprop_step(pG[k], gG[k], optG[k], lr)
+                opt_step(pG[k], gG[k], optG, k)
             for k in pD:
                 sdD[k].copy_(pD[k])
             for k in pG:

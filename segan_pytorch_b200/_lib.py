@@ -72,15 +72,16 @@ _SIGS = {
     "sg_nlc_to_ncl": [_vp, _i, _i, _i, _i, _vp, _vp],
     "sg_colsum": [_vp, _i, _i64, _i, _i, _vp, _i, _vp, _vp],
     "sg_fc_tail_fwd": [_vp] * 8 + [_i, _vp, _vp, _vp, _vp],
-    "sg_fc_tail_bwd": [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp] + [_vp] * 7 + [_vp],
-    "sg_l1_loss_bwd": [_vp, _vp, _i64, _f, _vp, _vp, _i, _vp],
+    "sg_fc_tail_bwd": [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp] + [_vp] * 7 + [_f, _vp],
+    "sg_l1_loss_bwd": [_vp, _vp, _i64, _f, _vp, _vp, _i, _f, _vp],
     "sg_rmsprop_step": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "sg_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp],
     "sg_deemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_preemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_pcm16_to_wave": [_vp, _vp, _i64, _i, _f, _vp, _vp],
 }
-EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair", "sg_set_ew_variant"] + list(_SIGS)
+EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair", "sg_set_ew_variant",
+           "sg_set_grad_dtype"] + list(_SIGS)
 
 _lib = None
 
@@ -106,14 +107,17 @@ def load():
     lib.sg_set_cta_pair.argtypes = [C.c_int]
     lib.sg_set_ew_variant.restype = C.c_int
     lib.sg_set_ew_variant.argtypes = [C.c_int] * 4
+    lib.sg_set_grad_dtype.restype = C.c_int
+    lib.sg_set_grad_dtype.argtypes = [C.c_int]
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
-    if lib.sg_abi_version() != 2:
+    if lib.sg_abi_version() != 3:
         raise SeganB200Error("ABI version mismatch")
     if os.environ.get("SEGAN_B200_CTA_PAIR", "") in ("0", "1", "2"):
         lib.sg_set_cta_pair(int(os.environ["SEGAN_B200_CTA_PAIR"]))
+    lib.sg_set_grad_dtype(SG_BF16 if os.environ.get("SEGAN_B200_GRAD_DTYPE", "f16").lower() == "bf16" else SG_F16)
     _lib = lib
     return lib
 

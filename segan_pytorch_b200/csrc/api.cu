@@ -15,6 +15,7 @@ int tapgemm_w_ffma_launch(const sg_tapgemm_w* q, cudaStream_t st);
 int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st);
 int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st);
 extern int g_cta_pair;
+int g_grad_dtype = SG_F16;
 }  // namespace sg
 
 using namespace sg;
@@ -25,6 +26,12 @@ extern "C" const char* sg_last_error(void) { return g_err; }
 extern "C" int sg_set_cta_pair(int on) {
   const int prev = g_cta_pair;
   g_cta_pair = on < 0 ? 0 : (on > 2 ? 2 : on);
+  return prev;
+}
+
+extern "C" int sg_set_grad_dtype(int dtype) {
+  const int prev = g_grad_dtype;
+  if (dtype == SG_F16 || dtype == SG_BF16) g_grad_dtype = dtype;
   return prev;
 }
 

@@ -11,6 +11,8 @@
 namespace sg {
 
 void set_error(const char* fmt, ...);
+// 16-bit format of every GRADIENT tensor the kernels read or write (sg_set_grad_dtype; default SG_F16)
+extern int g_grad_dtype;
 
 #define SG_CHECK_ARG(cond, ...)                                   \
   do {                                                            \
@@ -45,6 +47,14 @@ constexpr int NTAP = 9;     // row taps d in [-4, 4] of the stride-1 "row" formu
 constexpr int NUM_SMS = 148;
 
 __host__ __device__ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// two fp32 -> packed fp16x2 (lo in the low half), round-to-nearest, saturating to +-65504 instead of inf: a
+// loss-scaled fp16 gradient that overflows clips instead of poisoning the step (one F2FP.SATFINITE)
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // ---- 16-bit element access, runtime dtype ------------------------------------------------
 __device__ __forceinline__ float ld16(const void* p, int64_t i, int dtype) {

@@ -69,8 +69,7 @@ __device__ __forceinline__ void stv(void* p, int64_t elem, const float (&x)[VEC]
 #pragma unroll
   for (int i = 0; i < VEC / 2; ++i) {
     if (dtype == SG_F16) {
-      __half2 a = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&a);
+      w[i] = pack_half2_sat(x[2 * i], x[2 * i + 1]);
     } else {
       __nv_bfloat162 a = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t*>(&a);
@@ -263,7 +262,7 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const int
                const void* __restrict__ a, int dtype, int batch, int L, int C,
                const float* __restrict__ scale_shift, const float* __restrict__ mean_invstd,
                const float* __restrict__ slope, int act, double* __restrict__ red, int use_bn,
-               void* __restrict__ g_a_out) {
+               void* __restrict__ g_a_out, int gdt) {
   if (roll_dev) roll = *roll_dev;
   __shared__ float sred[MODE == 0 ? 256 * VEC : 1];
   const int cgs = C / VEC;
@@ -327,13 +326,13 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const int
       const int r = r0 + u * stride;
       if (r < rows) {
         const FV<VEC> xa = up<VEC>(av[u], dtype);
-        FV<VEC> gf = up<VEC>(gy[u], SG_BF16);
+        FV<VEC> gf = up<VEC>(gy[u], gdt);
         if (hm[u]) {
-          const FV<VEC> mf = up<VEC>(gm[u], SG_BF16);
+          const FV<VEC> mf = up<VEC>(gm[u], gdt);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) gf.v[j] += mf.v[j];
         }
-        const FV<VEC> sf = up<VEC>(gs[u], SG_BF16);     // zero bits -> 0.f when there is no skip gradient
+        const FV<VEC> sf = up<VEC>(gs[u], gdt);     // zero bits -> 0.f when there is no skip gradient
         float out[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -354,7 +353,7 @@ act_bwd_kernel(const void* __restrict__ g_h, int ldh, int H, int roll, const int
             out[j] = use_bn ? fmaf(sc[j], gpre, fmaf(p0[j], x, p1[j])) : gpre;
           }
         }
-        if (g_a_out) stv<VEC>(g_a_out, (int64_t)r * C + c0, out, SG_BF16);
+        if (g_a_out) stv<VEC>(g_a_out, (int64_t)r * C + c0, out, gdt);
       }
     }
   }
@@ -401,7 +400,7 @@ act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll,
                      int batch, int L, int C, int cgs_log2, const float* __restrict__ scale_shift,
                      const float* __restrict__ mean_invstd, const float* __restrict__ slope, int act,
                      const double* __restrict__ red_in, double* __restrict__ red_out, int use_bn,
-                     uint16_t* __restrict__ g_a_out, int tiles_per_b, int tiles_per_cta) {
+                     uint16_t* __restrict__ g_a_out, int tiles_per_b, int tiles_per_cta, int g_f16) {
   extern __shared__ __align__(16) float smf[];
   if (roll_dev) roll = *roll_dev;
   float* s_sc = smf;                 // y = x*sc + sh (sign test, slope gradient)
@@ -445,6 +444,7 @@ act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll,
   const int TILE = RPB * U;
   const int Lh = L + 2 * H;
   const bool f16 = a_f16 != 0;
+  const bool gf16 = g_f16 != 0;           // 16-bit format of the gradient tensors (sg_set_grad_dtype)
   const bool prelu = act == SG_ACT_PRELU;
 
   float part[3][8];
@@ -490,10 +490,10 @@ act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll,
       if (l < L) {
         float x[8], g[8], sc[8], sh[8], sl[8], out[8];
         up8(av[u], f16, x);
-        up8(gy[u], false, g);
+        up8(gy[u], gf16, g);
         if (hm & (1u << u)) {
           float m[8];
-          up8(gm[u], false, m);
+          up8(gm[u], gf16, m);
 #pragma unroll
           for (int j = 0; j < 8; ++j) g[j] += m[j];
         }
@@ -508,7 +508,7 @@ act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll,
         }
         if (g_add) {
           float sk[8];
-          up8(gs[u], false, sk);
+          up8(gs[u], gf16, sk);
 #pragma unroll
           for (int j = 0; j < 8; ++j) gpre[j] += sk[j];
         }
@@ -529,8 +529,12 @@ act_bwd_tiled_kernel(const uint16_t* __restrict__ g_h, int ldh, int H, int roll,
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(out[2 * i], out[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&h2);
+            if (gf16) {
+              w[i] = pack_half2_sat(out[2 * i], out[2 * i + 1]);
+            } else {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(out[2 * i], out[2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h2);
+            }
           }
           *reinterpret_cast<uint4*>(g_a_out + ((rb_a + l) * C + c0)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -698,11 +702,13 @@ fc_tail_bwd_rows_kernel(const float* __restrict__ z1, const float* __restrict__ 
                         const float* __restrict__ s1, const float* __restrict__ w2,
                         const float* __restrict__ s3, const float* __restrict__ w4, int batch,
                         float* __restrict__ loss_out, float* __restrict__ g_logit_ws, float* __restrict__ g_z2_ws,
-                        float* __restrict__ g_z1_ws, float* __restrict__ g_h1_ws, void* __restrict__ g_z1_bf16) {
+                        float* __restrict__ g_z1_ws, float* __restrict__ g_h1_ws, void* __restrict__ g_z1_bf16,
+                        float gscale, int gdt) {
   __shared__ float gz2[FC2];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float diff = logit[b] - target;
-  const float gl = g_logit_in ? g_logit_in[b] : 2.f * diff / (float)batch * weight;
+  // gscale: loss scale of the fp16 gradient tensors (every gradient downstream carries it; the loss does not)
+  const float gl = g_logit_in ? g_logit_in[b] * gscale : 2.f * diff / (float)batch * weight * gscale;
   if (tid == 0) {
     g_logit_ws[b] = gl;
     if (loss_out) atomicAdd(loss_out, diff * diff / (float)batch * weight);
@@ -721,7 +727,7 @@ fc_tail_bwd_rows_kernel(const float* __restrict__ z1, const float* __restrict__ 
   const float g = z > 0.f ? gh1 : gh1 * s1[tid];
   g_z1_ws[(int64_t)b * FC1 + tid] = g;
   g_h1_ws[(int64_t)b * FC1 + tid] = gh1;
-  st16(g_z1_bf16, (int64_t)b * FC1 + tid, g, SG_BF16);
+  st16(g_z1_bf16, (int64_t)b * FC1 + tid, g, gdt);
 }
 
 // parameter gradients of the head: blockIdx.y = chunk of 16 batch rows, one thread per output
@@ -793,9 +799,10 @@ fc_tail_bwd_params_kernel(const float* __restrict__ z1, const float* __restrict_
 
 __global__ void l1_loss_bwd_kernel(const float* __restrict__ y, const float* __restrict__ clean, int64_t n,
                                    float weight, float* __restrict__ loss_out, float* __restrict__ gy,
-                                   int accumulate) {
+                                   int accumulate, float grad_scale) {
   float s = 0.f;
-  const float gscale = weight / (float)n;
+  const float lscale = weight / (float)n;
+  const float gscale = lscale * grad_scale;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = y[i] - clean[i];
     s += fabsf(d);
@@ -803,7 +810,7 @@ __global__ void l1_loss_bwd_kernel(const float* __restrict__ y, const float* __r
     if (gy) gy[i] = accumulate ? gy[i] + g : g;
   }
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0 && loss_out) atomicAdd(loss_out, s * gscale);
+  if ((threadIdx.x & 31) == 0 && loss_out) atomicAdd(loss_out, s * lscale);
 }
 
 // ---- streaming-kernel variants (runtime tuning knobs, one per kernel family) -----------------
@@ -875,7 +882,7 @@ static int launch_act_bwd_tiled(const void* g_h, int ldh, int H, int roll, const
       (const uint16_t*)g_h, ldh, H, roll, roll_dev, (const uint16_t*)g_add, lda, (const uint16_t*)a,          \
       dtype == SG_F16,                                                                                       \
       batch, L, C, cgs_log2, scale_shift, mean_invstd, slope, act, red_in, red_out, use_bn, (uint16_t*)g_a_out, \
-      tiles_per_b, tiles_per_cta)
+      tiles_per_b, tiles_per_cta, g_grad_dtype == SG_F16)
   if (U == 4) SG_LAUNCH_TILED(4); else SG_LAUNCH_TILED(2);
 #undef SG_LAUNCH_TILED
   return SG_OK;
@@ -954,7 +961,7 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
   }
   EW_DISPATCH(4, v.unroll, (act_bwd_kernel<0, VEC, UNR><<<stream_grid((int64_t)batch * L, C, VEC, UNR, v.cap), 256, 0, ST>>>(
       g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C,
-      scale_shift, mean_invstd, slope, act, red, 0, g_a_out)));
+      scale_shift, mean_invstd, slope, act, red, 0, g_a_out, g_grad_dtype)));
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -978,7 +985,7 @@ extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, in
   }
   EW_DISPATCH(4, v.unroll, (act_bwd_kernel<1, VEC, UNR><<<stream_grid((int64_t)batch * L, C, VEC, UNR, v.cap), 256, 0, ST>>>(
       g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C,
-      scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a)));
+      scale_shift, mean_invstd, slope, act, const_cast<double*>(red), use_bn, g_a, g_grad_dtype)));
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -1054,14 +1061,15 @@ extern "C" int sg_fc_tail_bwd(const float* z1, const float* z2, const float* log
                               const float* s1, const float* w2, const float* s3, const float* w4, int batch,
                               float* loss_out, void* g_z1_bf16, float* ws /* [B*(1+128+256+256)] */, float* g_b0,
                               float* g_s1, float* g_w2, float* g_b2, float* g_s3, float* g_w4, float* g_b4,
-                              void* stream) {
+                              float grad_scale, void* stream) {
   SG_CHECK_ARG(ws && g_z1_bf16);
   float* g_logit = ws;
   float* g_z2 = ws + batch;
   float* g_z1 = g_z2 + (int64_t)batch * FC2;
   float* g_h1 = g_z1 + (int64_t)batch * FC1;
   fc_tail_bwd_rows_kernel<<<batch, 256, 0, ST>>>(z1, z2, logit, g_logit_in, target, weight, s1, w2, s3, w4, batch,
-                                                 loss_out, g_logit, g_z2, g_z1, g_h1, g_z1_bf16);
+                                                 loss_out, g_logit, g_z2, g_z1, g_h1, g_z1_bf16, grad_scale,
+                                                 g_grad_dtype);
   SG_CHECK_LAUNCH();
   if (g_w2) {
     dim3 grid(FC2 + 1, (batch + FC_CHUNK - 1) / FC_CHUNK);
@@ -1073,8 +1081,8 @@ extern "C" int sg_fc_tail_bwd(const float* z1, const float* z2, const float* log
 }
 
 extern "C" int sg_l1_loss_bwd(const float* y, const float* clean, int64_t n, float weight, float* loss_out,
-                              float* gy, int accumulate, void* stream) {
-  l1_loss_bwd_kernel<<<2 * NUM_SMS, 256, 0, ST>>>(y, clean, n, weight, loss_out, gy, accumulate);
+                              float* gy, int accumulate, float grad_scale, void* stream) {
+  l1_loss_bwd_kernel<<<2 * NUM_SMS, 256, 0, ST>>>(y, clean, n, weight, loss_out, gy, accumulate, grad_scale);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

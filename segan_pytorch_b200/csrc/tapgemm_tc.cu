@@ -386,8 +386,7 @@ tapgemm_f_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             if (p.out_dtype == SG_F16) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                pk[j] = pack_half2_sat(v[2 * j], v[2 * j + 1]);
               }
             } else {
 #pragma unroll
@@ -671,8 +670,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             if (p.out_dtype == SG_F16) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                pk[j] = pack_half2_sat(v[2 * j], v[2 * j + 1]);
               }
             } else {
 #pragma unroll
@@ -935,8 +933,7 @@ tapgemm_f_tc3(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             if (p.out_dtype == SG_F16) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                pk[j] = pack_half2_sat(v[2 * j], v[2 * j + 1]);
               }
             } else {
 #pragma unroll

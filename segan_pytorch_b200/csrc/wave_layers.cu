@@ -254,7 +254,7 @@ extern "C" int sg_wave_conv_wgrad(const float* x0, const float* x1, int cin, int
                                   const void* g_a, int cout, float* dw, float* dbias, void* stream) {
   SG_CHECK_ARG(cout == 64 && (cin == 1 || cin == 2) && L % 64 == 0);
   wave_correlate_kernel<64><<<grid_persistent(), 256, 0, (cudaStream_t)stream>>>(
-      g_a, 64, nullptr, SG_BF16, x0, x1, cin, batch, L, roll, PAD_REFLECT, 14, dw, dbias);
+      g_a, 64, nullptr, g_grad_dtype, x0, x1, cin, batch, L, roll, PAD_REFLECT, 14, dw, dbias);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -266,7 +266,7 @@ extern "C" int sg_wave_conv_dgrad(const void* g_a, int batch, int L, int roll, c
   if (!accumulate) SG_CHECK_CUDA(cudaMemsetAsync(gx0, 0, sizeof(float) * (size_t)batch * L, st));
   const int Lq = L / 4;
   dim3 grid((unsigned)cdiv(Lq + 8, 32), batch);
-  wave_synthesis_kernel<64><<<grid, 256, 0, st>>>(g_a, 64, nullptr, SG_BF16, Lq, w, cin * KW, 14, nullptr, -4,
+  wave_synthesis_kernel<64><<<grid, 256, 0, st>>>(g_a, 64, nullptr, g_grad_dtype, Lq, w, cin * KW, 14, nullptr, -4,
                                                   Lq + 4, 1, roll, gx0, L);
   SG_CHECK_LAUNCH();
   return SG_OK;
@@ -312,7 +312,7 @@ extern "C" int sg_wave_deconv_bwd(const void* x0, int c0, const void* x1, int c1
     // gx[b][j][ci] = sum_k gpre[4j + k - 13] * w_eff[ci][k]   (zero padding)
     dim3 grid((unsigned)cdiv(Lin, 32), batch);
     wave_analysis_kernel<128><<<grid, 256, 0, st>>>(gpre_ws, nullptr, 1, L, 0, PAD_ZERO, 13, w_eff, nullptr, gx,
-                                                    SG_BF16, nullptr, nullptr);
+                                                    g_grad_dtype, nullptr, nullptr);
     SG_CHECK_LAUNCH();
   }
   if (dw_eff) {
@@ -379,9 +379,9 @@ wave_shiftadd_tanh_kernel(const float* __restrict__ P, int batch, int Lin, const
   }
 }
 
-// gx[b][src(q)] += sum_{t,k: 4t + k - 14 = q} P2[b][t][k]   (reflect fold + un-roll), P2 bf16 [B][Lq][64]
+// gx[b][src(q)] += sum_{t,k: 4t + k - 14 = q} P2[b][t][k]   (reflect fold + un-roll), P2 16-bit (gradient dtype) [B][Lq][64]
 __global__ void __launch_bounds__(256)
-wave_col2im_fold_kernel(const void* __restrict__ P2, int col0, int batch, int L, int roll,
+wave_col2im_fold_kernel(const void* __restrict__ P2, int gdt, int col0, int batch, int L, int roll,
                         const int* __restrict__ roll_dev, float* __restrict__ gx) {
   if (roll_dev) roll = *roll_dev;
   const int Lq = L / 4;
@@ -396,7 +396,7 @@ wave_col2im_fold_kernel(const void* __restrict__ P2, int col0, int batch, int L,
     for (int j = 0; j < 8; ++j) {
       const int k = (e & 3) + 4 * j;
       const int t = (e - k) / 4;
-      if (k < KW && t >= 0 && t < Lq) s += ld16(P2, ((int64_t)b * Lq + t) * 64 + col0 + k, SG_BF16);
+      if (k < KW && t >= 0 && t < Lq) s += ld16(P2, ((int64_t)b * Lq + t) * 64 + col0 + k, gdt);
     }
     const int src = unroll_idx(reflect_idx(q, L), roll, L);
     atomicAdd(gx + (int64_t)b * L + src, s);
@@ -432,7 +432,7 @@ extern "C" int sg_wave_col2im_fold(const void* P2, int col0, int batch, int L, i
   const int64_t total = (int64_t)batch * (L + 30);
   int64_t g = cdiv(total, 256 * 4);
   if (g > 16 * NUM_SMS) g = 16 * NUM_SMS;
-  wave_col2im_fold_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(P2, col0, batch, L, roll, roll_dev, gx);
+  wave_col2im_fold_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(P2, g_grad_dtype, col0, batch, L, roll, roll_dev, gx);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

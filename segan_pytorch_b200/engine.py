@@ -414,6 +414,36 @@ def stat_arena(buf, name, shapes, device):
 F16, BF16, F32, F64 = torch.float16, torch.bfloat16, torch.float32, torch.float64
 SL = 8   # SG_STAT_SLICES: statistic buffers are [SL][n_stats][C]; the statistic is the sum over slices
 
+# ---- gradient precision -------------------------------------------------------------------------
+# Gradient tensors are fp16 (11 significant bits) with a static loss scale: the loss gradients are multiplied by
+# LOSS_SCALE at their source (sg_fc_tail_bwd / sg_l1_loss_bwd), every gradient tensor and the flat parameter-
+# gradient buckets carry the factor, and the optimiser kernels divide it out (their grad_scale argument).  16-bit
+# stores saturate at +-65504.  With fp16 gradients the weight-gradient tap-GEMMs read the forward activations
+# directly (same 16-bit format on both tcgen05 operands), so no bf16 twins are written.
+# SEGAN_B200_GRAD_DTYPE=bf16 (or set_grad_dtype('bf16')) restores round 1's bf16 gradient tensors + twins
+# (loss scale 1): the measured control for the parity gates.
+if os.environ.get("SEGAN_B200_GRAD_DTYPE", "f16").lower() == "bf16":     # _lib.load() applies the same variable
+    GT, GS, LOSS_SCALE = BF16, SG_BF16, 1.0
+else:
+    GT, GS, LOSS_SCALE = F16, SG_F16, float(os.environ.get("SEGAN_B200_LOSS_SCALE", "1024"))
+
+
+def set_grad_dtype(kind, loss_scale=None):
+    """kind: 'f16' | 'bf16'.  Affects engines built afterwards (packed dgrad operands are re-made on the next pack)."""
+    global GT, GS, LOSS_SCALE
+    if kind in ("bf16", BF16):
+        GT, GS = BF16, SG_BF16
+        LOSS_SCALE = 1.0 if loss_scale is None else float(loss_scale)
+    else:
+        GT, GS = F16, SG_F16
+        LOSS_SCALE = float(os.environ.get("SEGAN_B200_LOSS_SCALE", "1024")) if loss_scale is None else float(loss_scale)
+    _lib.load().sg_set_grad_dtype(GS)
+
+
+def grad_twins():
+    """bf16 gradient tensors need bf16 copies of the forward activations for the weight-gradient GEMMs."""
+    return GS == SG_BF16
+
 
 def flatten_params(module):
     """Re-points every parameter of `module` at a slice of one flat fp32 buffer (and the same for
@@ -513,13 +543,17 @@ class _NetEngine:
             self._pack_side = None
         self.pack_ev = {}
 
+    def grad_of(self, name):
+        """Gradient of parameter `name` in true units (the bucket carries LOSS_SCALE)."""
+        return self.gview(name) * (1.0 / LOSS_SCALE)
+
     def export_grads(self):
         """Copies the flat gradient bucket into per-parameter .grad tensors (API compatibility)."""
         for name, p in self.module.named_parameters():
             if p.requires_grad:
-                g = self.gview(name)
+                g = self.grad_of(name)
                 if p.grad is None:
-                    p.grad = g.clone()
+                    p.grad = g
                 else:
                     p.grad.copy_(g)
 
@@ -557,14 +591,14 @@ class GeneratorEngine(_NetEngine):
         self.packed["W2_last"] = w2.half().contiguous()
         wg = torch.zeros(weff.shape[0], 64, dtype=torch.float32, device=dev)
         wg[:, :KW] = weff
-        self.packed["Wg_last"] = wg.bfloat16().contiguous()
+        self.packed["Wg_last"] = wg.to(GT).contiguous()
         self._mark_packed("small")
         for l in range(1, self.nl):
             cin, cout = fm[l - 1], fm[l]
             wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
-            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), BF16, dev)
+            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), GT, dev)
             _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
-                      None, 0, _p(wf), _p(wd), SG_F16, SG_BF16, st)
+                      None, 0, _p(wf), _p(wd), SG_F16, GS, st)
             self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
             self._mark_packed("Wf%d" % l)
         for l in range(self.nl - 1):
@@ -573,9 +607,9 @@ class GeneratorEngine(_NetEngine):
             w = self.pview("dec_blocks.%d.deconv.weight" % l)
             alpha = self.alpha_for_dec(l)
             wt = self.buf.get("Wt%d" % l, (9, 4 * cout, cin), F16, dev)
-            wtd = self.buf.get("Wtd%d" % l, (9, cin, 4 * cout), BF16, dev)
+            wtd = self.buf.get("Wtd%d" % l, (9, cin, 4 * cout), GT, dev)
             _lib.call("sg_pack_weights", 1, _p(w), cout, cin, 0, _p(alpha), cin // 2,
-                      _p(wt), _p(wtd), SG_F16, SG_BF16, st)
+                      _p(wt), _p(wtd), SG_F16, GS, st)
             self.packed["Wt%d" % l], self.packed["Wtd%d" % l] = wt, wtd
             self._mark_packed("Wt%d" % l)
 
@@ -600,6 +634,8 @@ class GeneratorEngine(_NetEngine):
         forwards may precede a backward); the fused train step reuses one persistent workspace."""
         _require_cuda(x, z)
         twins = want_ctx if twins is None else (twins and want_ctx)
+        alias = twins and not grad_twins()        # fp16 gradients: the weight-gradient GEMMs read the forward tensors
+        twins = twins and grad_twins()
         self.ensure_packed()
         self.wait_packed("small")
         B, _, L = x.shape
@@ -618,8 +654,10 @@ class GeneratorEngine(_NetEngine):
             bias = self.pview("enc_blocks.%d.conv.bias" % l) if self.enc_bias else None
             if l == 0 and wave_on_tensor_cores():
                 col16 = buf.get("g.col16", (B, Lq[0], 64), F16, dev)
-                colb = buf.get("g.colb", (B, Lq[0], 64), BF16, dev) if twins else None
+                colb = buf.get("g.colb", (B, Lq[0], 64), GT, dev) if twins else None
                 _lib.call("sg_wave_im2col", _p(x), None, 1, B, L, 0, None, 1, 14, _p(col16), _p(colb), st)
+                if alias:
+                    colb = col16
                 self.wait_packed("small")
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
@@ -637,20 +675,24 @@ class GeneratorEngine(_NetEngine):
             halo = 16 if l < nl - 1 else 0
             hp[l] = buf.get("g.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
             if twins:
-                hpb[l] = buf.get("g.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), BF16, dev)
+                hpb[l] = buf.get("g.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), GT, dev)
                 if l < nl - 1:
-                    ab[l] = buf.get("g.ab%d" % l, (B, Lq[l], cout), BF16, dev)
+                    ab[l] = buf.get("g.ab%d" % l, (B, Lq[l], cout), GT, dev)
             _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, None,
                       _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, 0, None, halo, _p(hp[l]), _p(hpb[l]),
                       _p(ab[l]), st)
+            if alias:
+                hpb[l], ab[l] = hp[l], a[l]
         # ---- z
         zc = z.shape[1]
         z16 = buf.get("g.z16", (B, Lq[-1], zc), F16, dev)
         zf = z.contiguous().float()
         _lib.call("sg_ncl_to_nlc", _p(zf), B, zc, Lq[-1], _p(z16), SG_F16, st)
         if twins:
-            z16b = buf.get("g.z16b", (B, Lq[-1], zc), BF16, dev)
-            _lib.call("sg_ncl_to_nlc", _p(zf), B, zc, Lq[-1], _p(z16b), SG_BF16, st)
+            z16b = buf.get("g.z16b", (B, Lq[-1], zc), GT, dev)
+            _lib.call("sg_ncl_to_nlc", _p(zf), B, zc, Lq[-1], _p(z16b), GS, st)
+        elif alias:
+            z16b = z16
         # ---- decoder
         ad, dd = [None] * nl, [None] * nl
         src0, src1 = z16, hp[nl - 1]
@@ -666,9 +708,11 @@ class GeneratorEngine(_NetEngine):
                   a0_c=src0.shape[-1], a1_c=src1.shape[-1], backend=self.backend)
             dd[l] = buf.get("g.dd%d" % l, (B, 4 * lin, cout), F16, dev)
             if twins:
-                ddb[l] = buf.get("g.ddb%d" % l, (B, 4 * lin, cout), BF16, dev)
+                ddb[l] = buf.get("g.ddb%d" % l, (B, 4 * lin, cout), GT, dev)
             _lib.call("sg_act_fwd", _p(ad[l]), SG_F16, B, 4 * lin, cout, None,
                       _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, None, 0, _p(dd[l]), _p(ddb[l]), None, st)
+            if alias:
+                ddb[l] = dd[l]
             lin *= 4
             src0, src1 = dd[l], a[nl - 2 - l]
         y = torch.empty(B, 1, L, dtype=F32, device=dev)
@@ -733,7 +777,7 @@ class GeneratorEngine(_NetEngine):
         lin = Lq[0]
         cin = self.dec_cin(l)
         half = cin // 2
-        g_in = buf.get("g.gin%d" % l, (B, lin, cin), BF16, dev)
+        g_in = buf.get("g.gin%d" % l, (B, lin, cin), GT, dev)
         gpre = buf.get("g.gpre", (B, L), F32, dev)
         dweff = buf.get("g.dweff", (cin, KW), F32, dev, zero=True)
         gb = self.gview("dec_blocks.%d.deconv.bias" % l)
@@ -741,14 +785,15 @@ class GeneratorEngine(_NetEngine):
         src1 = a[0]
         if wave_on_tensor_cores():
             _lib.call("sg_tanh_bwd", _p(gy), _p(ctx["y"]), B * L, _p(gpre), _p(gb), st)
-            colg = buf.get("g.colg", (B, lin, 64), BF16, dev)
-            _lib.call("sg_wave_im2col", _p(gpre), None, 1, B, L, 0, None, 0, 13, None, _p(colg), st)
-            run_f(colg, None, lin, 0, SG_BF16, self.packed["Wg_last"], SG_BF16, 64, cin, tap_ranges("full", 0, 64, cin),
-                  g_in, SG_BF16, lin, 0, 0, lin, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+            colg = buf.get("g.colg", (B, lin, 64), GT, dev)
+            _lib.call("sg_wave_im2col", _p(gpre), None, 1, B, L, 0, None, 0, 13, _p(colg) if GS == SG_F16 else None,
+                      _p(colg) if GS != SG_F16 else None, st)
+            run_f(colg, None, lin, 0, GS, self.packed["Wg_last"], GS, 64, cin, tap_ranges("full", 0, 64, cin),
+                  g_in, GS, lin, 0, 0, lin, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
             # dW'[n=(s,k)][kc=(src,s',c)] over position pairs; the s == s' blocks are the gradient
             dwq = buf.get("g.dwq_last", (128 * 2 * cin,), F32, dev)
             dwq.zero_()
-            run_w(colg, lin // 2, SG_BF16, ctx["ddb"][l - 1], ctx["ab"][0], lin // 2, 0, SG_BF16, 2 * cin, 128,
+            run_w(colg, lin // 2, GS, ctx["ddb"][l - 1], ctx["ab"][0], lin // 2, 0, GS, 2 * cin, 128,
                   tap_ranges("full", 0, 2 * cin, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=74,
                   a0_c=cin, a1_c=cin, backend=self.backend)
             t5 = dwq.view(2, 64, 2, 2, half)
@@ -769,7 +814,7 @@ class GeneratorEngine(_NetEngine):
             lin = Lq[nl - 1 - l]
             cnext = g_next.shape[-1]
             # PReLU backward on [B, 4*lin, cout]
-            g_ad = buf.get("g.gad%d" % l, (B, lin, 4 * cout), BF16, dev)
+            g_ad = buf.get("g.gad%d" % l, (B, lin, 4 * cout), GT, dev)
             red = red_dec[l]
             _lib.call("sg_act_bwd_reduce", _p(g_next), cnext, 0, 0, None, None, 0, _p(ad[l]), SG_F16, B, 4 * lin, cout,
                       None, None, _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, _p(red), _p(g_ad), st)
@@ -785,7 +830,7 @@ class GeneratorEngine(_NetEngine):
             with on_side(side):
                 dwp.zero_()
                 n_tiles = 9 * (4 * cout // 128) * max(1, cin // 256)
-                run_w(g_ad, lin, SG_BF16, s0, s1, lin, 0, SG_BF16, cin, 4 * cout, taps, dwp, B,
+                run_w(g_ad, lin, GS, s0, s1, lin, 0, GS, cin, 4 * cout, taps, dwp, B,
                       ksplit=wgrad_ksplit(B * lin, n_tiles, taps, cin, 4 * cout), a0_c=c0, a1_c=c1,
                       backend=self.backend)
                 alpha = self.alpha_for_dec(l)
@@ -794,16 +839,16 @@ class GeneratorEngine(_NetEngine):
                           _p(self.pview("dec_blocks.%d.deconv.weight" % l)), _p(alpha), cin // 2,
                           _p(self.gview("dec_blocks.%d.deconv.weight" % l)), _p(galpha), 1, _stream())
             # data gradient w.r.t. cat(s0, s1); block 0 only needs the encoder half (z gets no gradient)
-            g_in = buf.get("g.gin%d" % l, (B, lin, cin), BF16, dev)
-            run_f(g_ad, None, lin, 0, SG_BF16, self.packed["Wtd%d" % l], SG_BF16, 4 * cout, cin,
-                  tap_ranges("deconv_dgrad", cout, 4 * cout, cin), g_in, SG_BF16, lin, 0, 0, lin, B,
+            g_in = buf.get("g.gin%d" % l, (B, lin, cin), GT, dev)
+            run_f(g_ad, None, lin, 0, GS, self.packed["Wtd%d" % l], GS, 4 * cout, cin,
+                  tap_ranges("deconv_dgrad", cout, 4 * cout, cin), g_in, GS, lin, 0, 0, lin, B,
                   n_lo=(cin // 2 if l == 0 else 0), n_hi=cin, backend=self.backend)
             g_next = g_in
         # ---- encoder blocks nl-1 .. 0
         g_hp = None
         for l in range(nl - 1, -1, -1):
             cout = fm[l]
-            g_a = buf.get("g.ga%d" % l, (B, Lq[l], cout), BF16, dev)
+            g_a = buf.get("g.ga%d" % l, (B, Lq[l], cout), GT, dev)
             red = red_enc[l]
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             if l == nl - 1:
@@ -823,7 +868,7 @@ class GeneratorEngine(_NetEngine):
                 with on_side(side):
                     if ctx.get("colb") is not None:
                         dwq.zero_()
-                        run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
+                        run_w(g_a, Lq[0] // 2, GS, ctx["colb"], None, Lq[0] // 2, 0, GS, 128, 128,
                               tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
                               backend=self.backend)
                         t4 = dwq.view(2, 64, 2, 64)
@@ -839,13 +884,13 @@ class GeneratorEngine(_NetEngine):
             with on_side(side):
                 dwp_l.zero_()
                 n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
-                run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout, taps, dwp_l, B,
+                run_w(g_a, Lq[l], GS, ctx["hpb"][l - 1], None, Lq[l], 4, GS, 4 * cin, cout, taps, dwp_l, B,
                       ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps, 4 * cin, cout), backend=self.backend)
                 _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
                           _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
-            g_hp = buf.get("g.ghp%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
-            run_f(g_a, None, Lq[l], 0, SG_BF16, self.packed["Wdg%d" % l], SG_BF16, cout, 4 * cin,
-                  tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_hp, SG_BF16, Lq[l], 4, -4, Lq[l] + 4, B,
+            g_hp = buf.get("g.ghp%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), GT, dev)
+            run_f(g_a, None, Lq[l], 0, GS, self.packed["Wdg%d" % l], GS, cout, 4 * cin,
+                  tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_hp, GS, Lq[l], 4, -4, Lq[l] + 4, B,
                   backend=self.backend)
         join_side(side)
         return self.grad
@@ -885,14 +930,14 @@ class DiscriminatorEngine(_NetEngine):
         dev, fm, st = self.flat.device, self.fmaps, _stream()
         wcol = wave_col_weights(self.pview("enc_blocks.0.conv.weight"), dev)
         self.packed["Wcol0"] = wcol.half().contiguous()
-        self.packed["WcolT0"] = wcol.t().bfloat16().contiguous()
+        self.packed["WcolT0"] = wcol.t().to(GT).contiguous()
         self._mark_packed("small")
         for l in range(1, self.nl):
             cin, cout = fm[l - 1], fm[l]
             wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
-            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), BF16, dev)
+            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), GT, dev)
             _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
-                      None, 0, _p(wf), _p(wd), SG_F16, SG_BF16, st)
+                      None, 0, _p(wf), _p(wd), SG_F16, GS, st)
             self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
             self._mark_packed("Wf%d" % l)
         w1 = self.pview("fc.0.weight")
@@ -900,8 +945,8 @@ class DiscriminatorEngine(_NetEngine):
         C_ = fm[-1]
         T = kin // C_
         w1p = self.buf.get("W1p", (nout, kin), F16, dev)
-        w1d = self.buf.get("W1dg", (kin, nout), BF16, dev)
-        _lib.call("sg_pack_weights", 2, _p(w1), nout, C_, T, None, 0, _p(w1p), _p(w1d), SG_F16, SG_BF16, st)
+        w1d = self.buf.get("W1dg", (kin, nout), GT, dev)
+        _lib.call("sg_pack_weights", 2, _p(w1), nout, C_, T, None, 0, _p(w1p), _p(w1d), SG_F16, GS, st)
         self.packed["W1p"], self.packed["W1dg"] = w1p, w1d
         self._mark_packed("W1p")
 
@@ -911,6 +956,8 @@ class DiscriminatorEngine(_NetEngine):
         device int32 tensor holding the same nl shifts; the kernels then read them from memory (no
         per-step scalar in the launches, so the step can be replayed from a CUDA graph)."""
         _require_cuda(x0, x1)
+        alias = twins and not grad_twins()
+        twins = twins and grad_twins()
         self.ensure_packed()
         self.wait_packed("small")
         m = self.module
@@ -938,8 +985,10 @@ class DiscriminatorEngine(_NetEngine):
             colb = None
             if l == 0 and wave_on_tensor_cores():
                 col16 = buf.get("d.col16", (B, Lq[0], 64), F16, dev)
-                colb0 = buf.get("d.colb", (B, Lq[0], 64), BF16, dev) if twins else None
+                colb0 = buf.get("d.colb", (B, Lq[0], 64), GT, dev) if twins else None
                 _lib.call("sg_wave_im2col", _p(x0), _p(x1), 2, B, L, int(shifts[0]), rptr(0), 1, 14, _p(col16), _p(colb0), st)
+                if alias:
+                    colb0 = col16
                 self.wait_packed("small")
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
@@ -976,10 +1025,12 @@ class DiscriminatorEngine(_NetEngine):
             halo = 16 if l < nl - 1 else 0
             roll = int(shifts[l + 1]) if l < nl - 1 else 0
             hp[l] = buf.get("d.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
-            hpb[l] = buf.get("d.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), BF16, dev) if twins else None
+            hpb[l] = buf.get("d.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), GT, dev) if twins else None
             _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, _p(ss[l]),
                       _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, roll, rptr(l + 1) if l < nl - 1 else None,
                       halo, _p(hp[l]), _p(hpb[l]), None, st)
+            if alias:
+                hpb[l] = hp[l]
         # ---- FC head
         kin = Lq[-1] * fm[-1]
         acc = buf.get("d.fc0", (B, 256), F32, dev, zero=True)
@@ -1020,7 +1071,7 @@ class DiscriminatorEngine(_NetEngine):
         a, hp, ss, mi, shifts = ctx["a"], ctx["hp"], ctx["ss"], ctx["mi"], ctx["shifts"]
         dev = ctx["x0"].device
         kin = Lq[-1] * fm[-1]
-        g_z1 = buf.get("d.gz1", (B, 256), BF16, dev)
+        g_z1 = buf.get("d.gz1", (B, 256), GT, dev)
         ws = buf.get("d.fcws", (B * (1 + 128 + 256 + 256),), F32, dev)
         gv = (lambda n: _p(gview(n))) if param_grads else (lambda n: None)
         _lib.call("sg_fc_tail_bwd", _p(ctx["z1"]), _p(ctx["z2"]), _p(ctx["logit"]), _p(g_logit), float(target),
@@ -1028,7 +1079,7 @@ class DiscriminatorEngine(_NetEngine):
                   _p(self.pview("fc.1.weight")), _p(self.pview("fc.2.weight")), _p(self.pview("fc.3.weight")),
                   _p(self.pview("fc.4.weight")), B, _p(loss_out), _p(g_z1), _p(ws),
                   gv("fc.0.bias"), gv("fc.1.weight"), gv("fc.2.weight"), gv("fc.2.bias"), gv("fc.3.weight"),
-                  gv("fc.4.weight"), gv("fc.4.bias"), st)
+                  gv("fc.4.weight"), gv("fc.4.bias"), float(LOSS_SCALE), st)
         # weight-gradient chain (wgrad GEMM + unpack) of every layer: side stream 0, next to the
         # data-gradient chain (dgrad GEMM -> BatchNorm/PReLU backward) on the caller's stream
         side = side_stream(dev, 3 if lane == 1 else 0) if param_grads else None
@@ -1036,13 +1087,13 @@ class DiscriminatorEngine(_NetEngine):
             dw1 = buf.get("d.dwpfc", (256 * kin,), F32, dev)
             with on_side(side):
                 dw1.zero_()
-                run_w(g_z1, 1, SG_BF16, ctx["hpb"][-1], None, 1, 0, SG_BF16, kin, 256, tap_ranges("full", 0, kin, 256),
+                run_w(g_z1, 1, GS, ctx["hpb"][-1], None, 1, 0, GS, kin, 256, tap_ranges("full", 0, kin, 256),
                       dw1, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
                 _lib.call("sg_unpack_wgrad", 2, _p(dw1), 256, fm[-1], Lq[-1], None, None, 0,
                           _p(gview("fc.0.weight")), None, 1, _stream())
-        g_h = buf.get("d.gh%d" % (nl - 1), (B, Lq[-1], fm[-1]), BF16, dev)
-        run_f(g_z1, None, 1, 0, SG_BF16, self.packed["W1dg"], SG_BF16, 256, kin, tap_ranges("full", 0, 256, kin),
-              g_h, SG_BF16, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+        g_h = buf.get("d.gh%d" % (nl - 1), (B, Lq[-1], fm[-1]), GT, dev)
+        run_f(g_z1, None, 1, 0, GS, self.packed["W1dg"], GS, 256, kin, tap_ranges("full", 0, 256, kin),
+              g_h, GS, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
         tmp = buf.get("d.cstmp", (SL * 2048,), F64, dev)
         reds = stat_arena(buf, "d.red", [(SL, 3, fm[l]) for l in range(nl)], dev)
         for l in range(nl - 1, -1, -1):
@@ -1050,7 +1101,7 @@ class DiscriminatorEngine(_NetEngine):
             halo = 16 if l < nl - 1 else 0
             roll = shifts[l + 1] if l < nl - 1 else 0
             rp = rptr(l + 1) if l < nl - 1 else None
-            g_a = buf.get("d.ga%d" % l, (B, Lq[l], cout), BF16, dev)
+            g_a = buf.get("d.ga%d" % l, (B, Lq[l], cout), GT, dev)
             redl = reds[l]
             slope = self.pview("enc_blocks.%d.act.weight" % l)
             _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
@@ -1065,7 +1116,7 @@ class DiscriminatorEngine(_NetEngine):
                 # zero mean per channel); the reference only sees rounding noise there.  Left at zero
                 # (SEGAN_B200_EXACT_BIAS_GRAD=1 computes the column sums anyway).
                 if m.bias and os.environ.get("SEGAN_B200_EXACT_BIAS_GRAD") == "1":
-                    _lib.call("sg_colsum", _p(g_a), SG_BF16, B * Lq[l], cout, cout,
+                    _lib.call("sg_colsum", _p(g_a), GS, B * Lq[l], cout, cout,
                               _p(gview("enc_blocks.%d.conv.bias" % l)), 1, _p(tmp), st)
             if l == 0:
                 w0 = self.pview("enc_blocks.0.conv.weight")
@@ -1073,7 +1124,7 @@ class DiscriminatorEngine(_NetEngine):
                     dwq = buf.get("d.dwq0", (128 * 128,), F32, dev)
                     with on_side(side):
                         dwq.zero_()
-                        run_w(g_a, Lq[0] // 2, SG_BF16, ctx["colb"], None, Lq[0] // 2, 0, SG_BF16, 128, 128,
+                        run_w(g_a, Lq[0] // 2, GS, ctx["colb"], None, Lq[0] // 2, 0, GS, 128, 128,
                               tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
                               backend=self.backend)
                         t4 = dwq.view(2, 64, 2, 64)
@@ -1084,9 +1135,9 @@ class DiscriminatorEngine(_NetEngine):
                         _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a),
                                   cout, _p(gview("enc_blocks.0.conv.weight")), None, _stream())
                 if (input_grad is not None or input_grad1 is not None) and wave_on_tensor_cores():
-                    P2 = buf.get("d.P2", (B, Lq[0], 64), BF16, dev)
-                    run_f(g_a, None, Lq[0], 0, SG_BF16, self.packed["WcolT0"], SG_BF16, 64, 64,
-                          tap_ranges("full", 0, 64, 64), P2, SG_BF16, Lq[0], 0, 0, Lq[0], B, d_lo=0, d_hi=0, w_tap0=4,
+                    P2 = buf.get("d.P2", (B, Lq[0], 64), GT, dev)
+                    run_f(g_a, None, Lq[0], 0, GS, self.packed["WcolT0"], GS, 64, 64,
+                          tap_ranges("full", 0, 64, 64), P2, GS, Lq[0], 0, 0, Lq[0], B, d_lo=0, d_hi=0, w_tap0=4,
                           backend=self.backend)
                     if input_grad is not None:
                         _lib.call("sg_wave_col2im_fold", _p(P2), 0, B, L, shifts[0], rptr(0), _p(input_grad), st)
@@ -1106,13 +1157,13 @@ class DiscriminatorEngine(_NetEngine):
                     dwp_l.zero_()
                     n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
                     taps_w = tap_ranges("conv_fwd", cin, 4 * cin, cout)
-                    run_w(g_a, Lq[l], SG_BF16, ctx["hpb"][l - 1], None, Lq[l], 4, SG_BF16, 4 * cin, cout, taps_w, dwp_l, B,
+                    run_w(g_a, Lq[l], GS, ctx["hpb"][l - 1], None, Lq[l], 4, GS, 4 * cin, cout, taps_w, dwp_l, B,
                           ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps_w, 4 * cin, cout), backend=self.backend)
                     _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
                               _p(gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
-            g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), BF16, dev)
-            run_f(g_a, None, Lq[l], 0, SG_BF16, self.packed["Wdg%d" % l], SG_BF16, cout, 4 * cin,
-                  tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_h, SG_BF16, Lq[l], 4, -4, Lq[l] + 4, B,
+            g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), GT, dev)
+            run_f(g_a, None, Lq[l], 0, GS, self.packed["Wdg%d" % l], GS, cout, 4 * cin,
+                  tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_h, GS, Lq[l], 4, -4, Lq[l] + 4, B,
                   backend=self.backend)
         join_side(side)
         return grad_flat

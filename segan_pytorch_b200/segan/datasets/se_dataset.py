@@ -189,6 +189,12 @@ class SEDataset(Dataset):
         self.idx2slice = []
         for w_i, (c_path, n_path) in enumerate(zip(self.clean_names, self.noisy_names)):
             n_samples = self._raw(c_path).shape[0]
+            if self.pcm16 and self._raw(n_path).shape[0] < n_samples:
+                # a noisy file shorter than its clean twin gets trimmed + zero-padded windows (_common_window); the
+                # padding lives in the pre-emphasised domain, which raw PCM cannot express: serve float windows
+                print('SEDataset: %s is shorter than %s -> float windows instead of int16 PCM'
+                      % (os.path.basename(n_path), os.path.basename(c_path)))
+                self.pcm16 = False
             for t_i, beg in enumerate(range(0, n_samples - self.slice_size + 1, offset)):
                 self.idx2slice.append((w_i, t_i, beg))
 
@@ -217,6 +223,16 @@ class SEDataset(Dataset):
             return normalize_wave_minmax(pre_emphasize(wav, self.preemph))
         return pre_emphasize(normalize_wave_minmax(wav), self.preemph)
 
+    def _common_window(self, c_slice, n_slice, pad_value):
+        """extract_slice, se_dataset.py:338-347: the pair is cut to the shorter of the two (a noisy file may be
+        shorter than its clean twin) and zero-padded up to slice_size."""
+        m = min(len(c_slice), len(n_slice))
+        c_slice, n_slice = c_slice[:m], n_slice[:m]
+        if m < self.slice_size:
+            pad = np.full((self.slice_size - m,), pad_value, dtype=c_slice.dtype)
+            c_slice, n_slice = np.concatenate((c_slice, pad)), np.concatenate((n_slice, pad))
+        return c_slice, n_slice
+
     def __getitem__(self, index):
         w_i, t_i, beg = self.idx2slice[index]
         c_path, n_path = self.clean_names[w_i], self.noisy_names[w_i]
@@ -228,8 +244,8 @@ class SEDataset(Dataset):
                              int(n[beg - 1]) if beg > 0 else self.NO_PREV], dtype=np.int32)
             return [bname, torch.from_numpy(np.ascontiguousarray(c[beg:end])),
                     torch.from_numpy(np.ascontiguousarray(n[beg:end])), t_i, torch.from_numpy(prev)]
-        c_slice = self.read_wav_file(c_path)[beg:end]
-        n_slice = self.read_wav_file(n_path)[beg:end]
+        c_slice, n_slice = self._common_window(self.read_wav_file(c_path)[beg:end],
+                                               self.read_wav_file(n_path)[beg:end], 0.0)
         rscale = random.choice(self.random_scale)
         if rscale != 1:
             c_slice, n_slice = rscale * c_slice, rscale * n_slice

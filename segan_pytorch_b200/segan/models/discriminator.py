@@ -50,11 +50,12 @@ class _DiscriminatorFn(torch.autograd.Function):
         eng.grad.zero_()
         eng.backward(ectx, 0.0, 1.0, param_grads=True, input_grad=g0, input_grad1=g1,
                      g_logit=g_logit.contiguous().float().view(-1))
+        inv = 1.0 / _engine.LOSS_SCALE            # the engine's gradients carry the fp16 loss scale
         if ctx.need_x:
-            gx = torch.cat((g0, g1), dim=1)
+            gx = torch.cat((g0, g1), dim=1) * inv
         grads = []
         for n, p in eng.module.named_parameters():
-            grads.append(eng.gview(n).clone() if p.requires_grad else None)
+            grads.append(eng.gview(n) * inv if p.requires_grad else None)
         return (None, gx, None, None) + tuple(grads)
 
 

@@ -55,10 +55,11 @@ class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         eng = ctx.eng
-        eng.backward(ctx.ectx, gy)
+        scale = _engine.LOSS_SCALE                # the engine's gradient tensors carry the fp16 loss scale
+        eng.backward(ctx.ectx, gy * scale if scale != 1.0 else gy)
         grads = []
         for n, p in eng.module.named_parameters():
-            grads.append(eng.gview(n).clone() if p.requires_grad else None)
+            grads.append(eng.gview(n) * (1.0 / scale) if p.requires_grad else None)
         return (None, None, None) + tuple(grads)
 
 

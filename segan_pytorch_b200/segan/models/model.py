@@ -95,6 +95,7 @@ class FusedOptimizer(object):
         lr = self.param_groups[0]['lr']
         self.t += 1
         n = flat.numel()
+        grad_scale = float(grad_scale) / _engine.LOSS_SCALE      # the bucket carries the fp16 loss scale
         if self.kind == 'rmsprop':
             _lib.call("sg_rmsprop_step", _p(flat), _p(self.eng.grad), _p(self.s1), n, lr, self.alpha, self.eps,
                       float(grad_scale), _stream())
@@ -103,23 +104,41 @@ class FusedOptimizer(object):
                       self.betas[1], self.eps, self.t, float(grad_scale), _stream())
         self.eng.mark_dirty()
 
+    def _trainable(self):
+        """(name, parameter) in torch's optimiser order: the requires_grad parameters only (core.py:196-197)."""
+        return [(n, p) for n, p in self.eng.module.named_parameters() if p.requires_grad]
+
     def state_dict(self):
+        """Same structure as torch.optim.RMSprop / Adam .state_dict() over Model.parameters(): per-parameter state
+        tensors in reference layout, indices over the trainable parameters, full hyper-parameter groups -- a
+        checkpoint written here loads into the reference's optimiser and vice versa."""
         self._state()
         state = {}
-        for i, (name, p) in enumerate(self.eng.module.named_parameters()):
+        names = self._trainable()
+        for i, (name, p) in enumerate(names):
             off, n, shape = self.eng.index[name]
+            view = lambda t: t[off:off + n].view(shape).detach().to('cpu', copy=True)
+            step = torch.tensor(float(self.t))
             if self.kind == 'rmsprop':
-                state[i] = {'step': self.t, 'square_avg': self.s1[off:off + n].view(shape).detach().cpu().clone()}
+                state[i] = {'step': step, 'square_avg': view(self.s1)}
             else:
-                state[i] = {'step': self.t, 'exp_avg': self.s1[off:off + n].view(shape).detach().cpu().clone(),
-                            'exp_avg_sq': self.s2[off:off + n].view(shape).detach().cpu().clone()}
-        return {'state': state if self.t > 0 else {},
-                'param_groups': [dict(lr=self.param_groups[0]['lr'], kind=self.kind,
-                                      params=list(range(len(self.eng.index))))]}
+                state[i] = {'step': step, 'exp_avg': view(self.s1), 'exp_avg_sq': view(self.s2)}
+        lr = self.param_groups[0]['lr']
+        if self.kind == 'rmsprop':
+            group = dict(lr=lr, momentum=0, alpha=self.alpha, eps=self.eps, centered=False, weight_decay=0,
+                         capturable=False, foreach=None, maximize=False, differentiable=False)
+        else:
+            group = dict(lr=lr, betas=tuple(float(b) for b in self.betas), eps=self.eps, weight_decay=0, amsgrad=False, maximize=False,
+                         foreach=None, capturable=False, differentiable=False, fused=None)
+        group['params'] = list(range(len(names)))
+        return {'state': state if self.t > 0 else {}, 'param_groups': [group]}
 
     def load_state_dict(self, sd):
         self._state()
-        for i, (name, p) in enumerate(self.eng.module.named_parameters()):
+        groups = sd.get('param_groups') or [{}]
+        if 'lr' in groups[0]:
+            self.param_groups[0]['lr'] = float(groups[0]['lr'])
+        for i, (name, p) in enumerate(self._trainable()):
             st = sd.get('state', {}).get(i)
             if st is None:
                 continue
@@ -230,8 +249,9 @@ class SEGAN(Model):
         """Streaming inference over HOST batches (BASELINE config 5; the clean.py:59-82 loop batched across
         files): yields one pinned host tensor of enhanced windows per input batch of (N,1,16384) pre-emphasised
         windows.  Three streams: the H2D copy of batch n+1, G on batch n and the D2H copy of batch n-1 overlap,
-        so a slow host link hides behind the Generator.  A yielded tensor is valid until the next-but-one
-        batch is requested (two pinned output buffers alternate)."""
+        so a slow host link hides behind the Generator.  A yielded tensor is valid only until the NEXT batch is
+        requested (two pinned output buffers alternate and the following iteration already copies into the
+        other slot's successor): consume or copy it before calling next() again."""
         self.G.eval()
         dev = next(super(Model, self.G).parameters()).device
         main = torch.cuda.current_stream(dev)
@@ -443,7 +463,7 @@ class SEGAN(Model):
         gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
         de.backward(c, 1.0, 1.0, param_grads=False, input_grad=gy, loss_out=lptr(2))
         _lib.call("sg_l1_loss_bwd", _p(Genh), _p(clean.contiguous()), B * L, float(l1_weight), lptr(3), _p(gy), 1,
-                  _stream())
+                  float(_engine.LOSS_SCALE), _stream())
         ge.backward(gctx, gy)
 
     # -- CUDA graphs ------------------------------------------------------------------------------
@@ -462,7 +482,8 @@ class SEGAN(Model):
         B, _, L = clean.shape
         key = (B, L, float(l1_weight), Gopt.param_groups[0]['lr'], Dopt.param_groups[0]['lr'], world,
                ge.flat.data_ptr() if ge.flat is not None else 0, de.flat.data_ptr() if de.flat is not None else 0,
-               _engine.OVERLAP, self.z_device, bool(sample_z), ge.backend, de.backend)
+               _engine.OVERLAP, self.z_device, bool(sample_z), ge.backend, de.backend, _engine.GS,
+               _engine.LOSS_SCALE)
         cache = self.__dict__.setdefault('_step_graphs', {})
         st = cache.get(key)
         if st is None:
@@ -492,6 +513,11 @@ class SEGAN(Model):
         ge, de = self.G.engine, self.D.engine
         dscale = 1.0 / (_dist().get_world_size() if _dist() is not None else 1)
         torch.cuda.synchronize()
+        # the pack kernels of BOTH networks must be part of the captured step: a G forward between the last eager
+        # step and this capture (generate(), sample logging) would otherwise leave G "clean" here, nothing would be
+        # captured and every replay would run on the stale 16-bit operands (D is re-packed after Dopt.step anyway)
+        ge.mark_dirty()
+        de.mark_dirty()
         n0 = _lib.launch_count
         g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         t_d, t_g = Dopt.t, Gopt.t
@@ -599,11 +625,28 @@ class WSEGAN(SEGAN):
         return self.G(nwav, z=z, ret_hid=ret_hid)
 
     def sample_dloader(self, dloader, device='cuda'):
-        """model.py:526-535 -- a fresh iterator every step (the reference's behaviour)."""
-        uttname, clean, noisy, slice_idx = next(iter(dloader))
-        clean = clean.unsqueeze(1).to(device).float()
-        noisy = noisy.unsqueeze(1).to(device).float()
-        return uttname, clean, noisy, slice_idx
+        """model.py:526-535 -- one batch from a FRESH iterator of the loader (the reference's per-step behaviour),
+        staged like every other batch: float windows as they are, int16 PCM windows (SEDataset(pcm16=True), five
+        fields) normalised + pre-emphasised on the device.  `train` does not use this: it keeps one persistent
+        prefetching iterator."""
+        uttname, clean, noisy, slice_idx = next(iter(DevicePrefetcher(dloader, device, preemph=self.preemph)))
+        return uttname, clean.clone(), noisy.clone(), slice_idx
+
+    @staticmethod
+    def _endless(dloader):
+        """Epoch after epoch of `dloader` (a shuffling loader reshuffles each pass; DistributedSampler gets its
+        epoch set) -- the persistent replacement of the reference's `next(iter(dloader))` per step."""
+        epoch = 0
+        while True:
+            epoch += 1
+            if hasattr(getattr(dloader, 'sampler', None), 'set_epoch'):
+                dloader.sampler.set_epoch(epoch)
+            n = 0
+            for batch in dloader:
+                n += 1
+                yield batch
+            if n == 0:
+                raise ValueError('empty data loader')
 
     @staticmethod
     def stft_logpow(x, n_fft):
@@ -701,7 +744,7 @@ class WSEGAN(SEGAN):
                 tot = tot + den
             tot.backward()
         losses[2] += pow_loss.detach()
-        gy.add_(gt.grad)
+        gy.add_(gt.grad, alpha=_engine.LOSS_SCALE)
         ge.backward(gctx, gy)
         Gopt.step(allreduce_grads(ge))
         return losses
@@ -721,9 +764,12 @@ class WSEGAN(SEGAN):
         losses = None
         self.G.train()
         self.D.train()
+        # one persistent iterator, the next batch staged on a copy stream while this one trains (the reference
+        # builds a new DataLoader iterator -- and its worker processes -- every step, model.py:527)
+        batches = iter(DevicePrefetcher(self._endless(dloader), device, preemph=getattr(opts, 'preemph', 0.95)))
         for iteration in range(1, opts.epoch * len(dloader) + 1):
             beg_t = timeit.default_timer()
-            uttname, clean, noisy, slice_idx = self.sample_dloader(dloader, device)
+            uttname, clean, noisy, slice_idx = next(batches)
             losses = self.train_step(clean, noisy, Gopt, Dopt, l1_weight, uttname=uttname, losses=losses)
             timings.append(timeit.default_timer() - beg_t)
             if iteration % log_freq == 0:

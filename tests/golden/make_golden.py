@@ -218,6 +218,28 @@ def golden_generate(ref, segan, out):
     np.savez_compressed(os.path.join(out, "emphasis.npz"), x=x, norm=xn, pre=pe, de=de)
 
 
+def golden_wsegan_generate(ref, out):
+    """WSEGAN.generate (model.py:755-766): un-chunked inference on a 20000-sample utterance (make_divN pads it
+    to 20480, utils.py:26-38), xavier-initialised WSEGAN built from the seed."""
+    seed_all(SEED)
+    with quiet():
+        w = ref.WSEGAN(reference_opts(wsegan=True, misalign_pair=True))
+    g = torch.Generator().manual_seed(SEED + 4)
+    wav = 0.3 * torch.randn(1, 1, 20000, generator=g)
+    z = torch.randn(1, 1024, 20, generator=g)
+    with torch.no_grad():
+        c_res, hall = w.generate(wav, z=z)
+    d = dict(wav=wav.numpy(), z=z.numpy(), out=np.asarray(c_res), sha_G=np.array(sd_sha(w.G.state_dict())),
+             enc_zc_shape=np.array(hall["enc_zc"].shape))
+    # and a length that already is a multiple of 1024: make_divN still appends a whole block
+    wav2 = 0.3 * torch.randn(1, 1, 4096, generator=g)
+    z2 = torch.randn(1, 1024, 5, generator=g)
+    with torch.no_grad():
+        c2, _ = w.generate(wav2, z=z2)
+    d.update(wav2=wav2.numpy(), z2=z2.numpy(), out2=np.asarray(c2))
+    np.savez_compressed(os.path.join(out, "wsegan_generate.npz"), **d)
+
+
 def main():
     torch.set_num_threads(8)
     ref = load_reference()
@@ -229,6 +251,7 @@ def main():
     segan = build_reference_segan(ref)       # fresh D (BN buffers untouched)
     golden_generate(ref, segan, out)
     golden_train_step(ref, out, B=4)
+    golden_wsegan_generate(ref, out)
     for f in sorted(os.listdir(out)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(out, f)))

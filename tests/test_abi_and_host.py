@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, n), "header declares %s but the library does not export it" % n
     from segan_pytorch_b200 import _lib
     assert sorted(set(_lib.EXPORTS)) == names
-    assert lib.sg_abi_version() == 2
+    assert lib.sg_abi_version() == 3
 
 
 def test_ctypes_structs_match_c_layout(lib):
@@ -121,3 +121,70 @@ def test_cpu_forward_fails_loudly():
         s.G(torch.zeros(1, 1, 16384))
     with pytest.raises(RuntimeError):
         s.D(torch.zeros(1, 2, 16384))
+
+
+def test_saver_index_rolls_and_partial_load(tmp_path):
+    """Checkpoint format of core.py: JSON index with 'latest' / 'current', the oldest file dropped once the index
+    lists more than max_ckpts entries, load_pretrained skipping the file's last two keys unless load_last."""
+    import json
+    from segan_pytorch_b200.segan.models.core import Saver
+    s = build_segan()
+    d = str(tmp_path)
+    sv = Saver(s.D, d, max_ckpts=2, prefix="EOE_D-")
+    for step in (1, 2, 3, 4):
+        sv.save("Discriminator", step)
+    idx = json.load(open(os.path.join(d, "EOE_D-checkpoints")))
+    assert idx["current"] == "EOE_D-Discriminator-4.ckpt"
+    assert idx["latest"] == ["EOE_D-Discriminator-%d.ckpt" % i for i in (2, 3, 4)]
+    assert not os.path.exists(os.path.join(d, "weights_EOE_D-Discriminator-1.ckpt"))
+    assert sv.read_latest_checkpoint() == "EOE_D-Discriminator-4.ckpt"
+    sv.save("Discriminator", 9, best_val=True)
+    assert os.path.exists(os.path.join(d, "weights_EOE_D-best_Discriminator-9.ckpt"))
+    # partial load: everything but the last two keys (fc.4.weight / fc.4.bias)
+    s2 = build_segan(seed=7)
+    before = {k: v.clone() for k, v in s2.D.state_dict().items()}
+    s2.D.load_pretrained(os.path.join(d, "weights_EOE_D-Discriminator-4.ckpt"), load_last=False)
+    after, src = s2.D.state_dict(), s.D.state_dict()
+    assert torch.equal(after["fc.4.weight"], before["fc.4.weight"]) and torch.equal(after["fc.4.bias"], before["fc.4.bias"])
+    assert torch.equal(after["fc.0.weight"], src["fc.0.weight"]) and torch.equal(after["enc_blocks.3.conv.weight"], src["enc_blocks.3.conv.weight"])
+    # legacy file = bare state dict
+    torch.save(s.D.state_dict(), os.path.join(d, "legacy.ckpt"))
+    s3 = build_segan(seed=9)
+    s3.D.load_pretrained(os.path.join(d, "legacy.ckpt"), load_last=True)
+    assert sd_sha(s3.D.state_dict()) == sd_sha(s.D.state_dict())
+
+
+@pytest.mark.parametrize("kind", ["rmsprop", "adam"])
+def test_fused_optimizer_state_dict_is_torch_compatible(kind):
+    """FusedOptimizer.state_dict() must load into torch.optim.RMSprop / Adam built over
+    Model.parameters() (trainable parameters only, full param_groups) and back, lr included."""
+    from segan_pytorch_b200.segan.models.model import FusedOptimizer
+    s = build_segan(skip_type="constant")             # frozen alphas: indices must skip them
+    eng = s.G.engine.bind()
+    opt = FusedOptimizer(eng, kind, 5e-5, betas=(0, 0.9))
+    opt._state()
+    opt.t = 3
+    opt.s1.uniform_(0.1, 1.0)
+    if kind == "adam":
+        opt.s2.uniform_(0.1, 1.0)
+    sd = opt.state_dict()
+    params = list(s.G.parameters())
+    assert len(sd["state"]) == len(params) == len(sd["param_groups"][0]["params"])
+    assert all(not n.startswith("alpha_") for n, _ in opt._trainable())
+    ref = torch.optim.RMSprop(params, lr=1e-3) if kind == "rmsprop" else torch.optim.Adam(params, lr=1e-3, betas=(0.0, 0.9))
+    ref.load_state_dict(sd)
+    assert ref.param_groups[0]["lr"] == 5e-5
+    for p in params:
+        p.grad = torch.zeros_like(p)
+    ref.step()                                        # KeyError here if a hyper-parameter were missing
+    key = "square_avg" if kind == "rmsprop" else "exp_avg"
+    off, n, shape = eng.index["enc_blocks.1.conv.weight"]
+    i = [k for k, _ in opt._trainable()].index("enc_blocks.1.conv.weight")
+    assert ref.state_dict()["state"][i][key].shape == torch.Size(shape)
+    # and back, with a changed lr
+    sd2 = ref.state_dict()
+    sd2["param_groups"][0]["lr"] = 2e-5
+    opt2 = FusedOptimizer(eng, kind, 5e-5, betas=(0, 0.9))
+    opt2.load_state_dict(sd2)
+    assert opt2.param_groups[0]["lr"] == 2e-5 and opt2.t == 4
+    assert torch.allclose(opt2.s1[off:off + n].view(shape), ref.state_dict()["state"][i][key])

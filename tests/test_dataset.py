@@ -79,3 +79,34 @@ def test_sedataset_matches_reference(tmp_path):
         name, c, n, t_i = rds[i][:4]
         mine = got[(name, int(t_i))]
         assert torch.equal(mine[1], c) and torch.equal(mine[2], n)
+
+
+def test_sedataset_short_noisy_file_is_trimmed_and_padded(tmp_path):
+    """a noisy wav shorter than its clean twin -> the reference's extract_slice (se_dataset.py:338-347)
+    cuts the pair to the common length and zero-pads to slice_size; int16 mode falls back to float windows."""
+    root = str(tmp_path)
+    cdir, ndir = os.path.join(root, "clean"), os.path.join(root, "noisy")
+    os.makedirs(cdir)
+    os.makedirs(ndir)
+    rng = np.random.RandomState(2)
+    c = (rng.randn(20000) * 3000).astype(np.int16)
+    n = (rng.randn(19000) * 3000).astype(np.int16)          # 1000 samples short
+    wavfile.write(os.path.join(cdir, "a.wav"), 16000, c)
+    wavfile.write(os.path.join(ndir, "a.wav"), 16000, n)
+    for pcm in (False, True):
+        ds = SEDataset(cdir, ndir, 0.95, slice_size=16384, stride=1, pcm16=pcm)
+        assert len(ds) == 1 and ds.pcm16 is False
+        name, cw, nw, t_i = ds[0]
+        assert cw.shape == nw.shape == (16384,) and cw.dtype == torch.float32
+        assert np.abs(cw.numpy() - pre_emphasize(normalize_wave_minmax(c), 0.95)[:16384]).max() <= 1e-6
+    # second window of a stride-0.5 slicing runs past the noisy file: trimmed to 19000-8192, padded with zeros
+    c2 = (rng.randn(24576) * 3000).astype(np.int16)
+    wavfile.write(os.path.join(cdir, "a.wav"), 16000, c2)
+    ds = SEDataset(cdir, ndir, 0.95, slice_size=16384, stride=0.5)
+    assert len(ds) == 2
+    _, cw, nw, _ = ds[1]
+    m = 19000 - 8192
+    assert cw.shape == nw.shape == (16384,)
+    assert float(cw[m:].abs().max()) == 0.0 and float(nw[m:].abs().max()) == 0.0 and float(nw[:m].abs().max()) > 0
+    b = collate_fn([ds[0], ds[1]])
+    assert b[1].shape == (2, 16384)

@@ -19,6 +19,15 @@ DEV = "cuda"
 _p, _stream = E._p, E._stream
 
 
+@pytest.fixture(params=["f16", "bf16"])
+def grad_dtype(request):
+    """Runs a test once per 16-bit gradient format (sg_set_grad_dtype): fp16 (default) and round 1's bf16."""
+    prev = "bf16" if E.GS == SG_BF16 else "f16"
+    E.set_grad_dtype(request.param)
+    yield request.param
+    E.set_grad_dtype(prev)
+
+
 def _gen(seed):
     return torch.Generator(device="cpu").manual_seed(seed)
 
@@ -425,7 +434,7 @@ def test_pack_and_unpack_roundtrip():
             assert max_abs(dalpha, (weff16[ci // 2:] * w[ci // 2:]).sum((1, 2))) <= 1e-3
 
 
-def test_wave_conv_fwd_and_grads():
+def test_wave_conv_fwd_and_grads(grad_dtype):
     g = _gen(4)
     B, L, roll = 3, 4096, -3
     x0 = (0.3 * torch.randn(B, L, generator=g)).to(DEV)
@@ -448,7 +457,7 @@ def test_wave_conv_fwd_and_grads():
     torch.cuda.synchronize()
     assert max_abs(hp.float().permute(0, 2, 1).cpu(), h_ref) <= 2e-3 * float(h_ref.abs().max())
     # gradients of the 2-channel rolled conv
-    ga = (0.1 * torch.randn(B, L // 4, 64, generator=g)).to(torch.bfloat16).to(DEV)
+    ga = (0.1 * torch.randn(B, L // 4, 64, generator=g)).to(E.GT).to(DEV)
     dw = torch.zeros_like(w)
     db = torch.zeros(64, device=DEV)
     _lib.call("sg_wave_conv_wgrad", _p(x0), _p(x1), 2, B, L, roll, _p(ga), 64, _p(dw), _p(db), _stream())
@@ -464,7 +473,7 @@ def test_wave_conv_fwd_and_grads():
     assert rel_err(gx0.cpu(), xin_r.grad[:, 0]) <= 1e-4
 
 
-def test_wave_deconv_fwd_and_bwd():
+def test_wave_deconv_fwd_and_bwd(grad_dtype):
     g = _gen(5)
     B, Lin = 2, 1024
     x0 = (torch.randn(B, Lin, 64, generator=g)).to(torch.float16).to(DEV)
@@ -481,7 +490,7 @@ def test_wave_deconv_fwd_and_bwd():
     assert max_abs(y.cpu(), ref[:, 0].detach()) <= 1e-4
     gy = (torch.randn(B, 4 * Lin, generator=g)).to(DEV)
     gpre = torch.zeros_like(gy)
-    gx = torch.zeros(B, Lin, 128, dtype=torch.bfloat16, device=DEV)
+    gx = torch.zeros(B, Lin, 128, dtype=E.GT, device=DEV)
     dw = torch.zeros_like(w)
     db = torch.zeros(1, device=DEV)
     _lib.call("sg_wave_deconv_bwd", _p(x0), 64, _p(x1), 64, B, Lin, _p(w), _p(gy), _p(y), _p(gpre), _p(gx),
@@ -495,7 +504,7 @@ def test_wave_deconv_fwd_and_bwd():
 
 @pytest.mark.parametrize("variant", [(4, 2, 3), (4, 4, 16), (4, 8, 2), (8, 2, 8), (8, 4, 1)])
 @pytest.mark.parametrize("C_,L,roll,halo", [(64, 256, 2, 16), (256, 64, -5, 16), (1024, 16, 0, 0), (128, 96, 4, 16)])
-def test_bn_act_fwd_bwd(C_, L, roll, halo, variant):
+def test_bn_act_fwd_bwd(C_, L, roll, halo, variant, grad_dtype):
     """Every streaming-kernel variant (channels/thread, rows in flight, grid cap; for the backward
     kernels vec 8 = the tiled kernel, vec 4 = the generic one) against fp32 torch."""
     lib = _lib.load()
@@ -542,21 +551,21 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo, variant):
     assert max_abs(hb.float(), h.float()) <= 4e-2 and max_abs(abf.float(), a.float()) <= 4e-2
     assert max_abs(rm.cpu(), rm_r) <= 1e-5 and max_abs(rv.cpu(), rv_r) <= 1e-4
     # backward: gradient arrives in the consumer view (incl. halo)
-    gh = (torch.randn(B, L + 2 * halo, C_, generator=g)).to(torch.bfloat16).to(DEV)
+    gh = (torch.randn(B, L + 2 * halo, C_, generator=g)).to(E.GT).to(DEV)
     yr.backward(gh.float().permute(0, 2, 1).cpu())
     red = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
-    ga = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
+    ga = torch.zeros(B, L, C_, dtype=E.GT, device=DEV)
     _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
               _p(slope), 1, _p(red), None, _stream())
     # no-BN variant with a skip gradient on the pre-activation (Generator encoder), strided sources
-    gsk = (torch.randn(B, L, 2 * C_, generator=g)).to(torch.bfloat16).to(DEV)
+    gsk = (torch.randn(B, L, 2 * C_, generator=g)).to(E.GT).to(DEV)
     a2 = a.float().permute(0, 2, 1).cpu().requires_grad_(True)
     sl2 = slope.cpu().clone().requires_grad_(True)
     y2 = F.prelu(a2, sl2)
     y2p = F.pad(y2, (halo, halo), mode="reflect") if halo else y2
     (y2p * gh.float().permute(0, 2, 1).cpu()).sum().add((a2 * gsk[:, :, C_:].float().permute(0, 2, 1).cpu()).sum()).backward()
     red2 = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
-    ga2 = torch.zeros(B, L, C_, dtype=torch.bfloat16, device=DEV)
+    ga2 = torch.zeros(B, L, C_, dtype=E.GT, device=DEV)
     gadd_ptr = C.c_void_p(gsk.data_ptr() + 2 * C_)
     _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, None, gadd_ptr, 2 * C_, _p(a), SG_F16, B, L, C_, None, None,
               _p(slope), 1, _p(red2), _p(ga2), _stream())
@@ -586,7 +595,7 @@ def test_bn_act_fwd_bwd(C_, L, roll, halo, variant):
     assert rel_err(ga.float().permute(0, 2, 1).cpu(), an.grad) <= 1e-2
 
 
-def test_fc_tail_and_losses():
+def test_fc_tail_and_losses(grad_dtype):
     g = _gen(7)
     B = 6
     acc = torch.randn(B, 256, generator=g).to(DEV)
@@ -606,27 +615,27 @@ def test_fc_tail_and_losses():
     assert max_abs(logit.cpu(), ref.detach()) <= 1e-5
     loss = 0.5 * F.mse_loss(ref.view(-1), torch.ones(B))
     loss.backward()
-    gz1 = torch.zeros(B, 256, dtype=torch.bfloat16, device=DEV)
+    gz1 = torch.zeros(B, 256, dtype=E.GT, device=DEV)
     ws = torch.zeros(B * 641, device=DEV)
     gs = [torch.zeros_like(t) for t in (b0, s1, w2, b2, s3, w4, b4)]
     lo = torch.zeros(1, device=DEV)
     _lib.call("sg_fc_tail_bwd", _p(z1), _p(z2), _p(logit), None, 1.0, 0.5, _p(s1), _p(w2), _p(s3), _p(w4), B, _p(lo),
-              _p(gz1), _p(ws), *[_p(t) for t in gs], _stream())
+              _p(gz1), _p(ws), *[_p(t) for t in gs], 8.0, _stream())
     torch.cuda.synchronize()
-    assert abs(float(lo) - float(loss)) <= 1e-5
-    assert rel_err(gz1.float().cpu(), ps[0].grad) <= 1e-2
+    assert abs(float(lo) - float(loss)) <= 1e-5                      # the loss itself is not scaled
+    assert rel_err(gz1.float().cpu() / 8.0, ps[0].grad) <= 1e-2      # grad_scale = 8 on every gradient
     for got, p in zip(gs, ps[1:]):
-        assert rel_err(got.cpu().reshape(-1), p.grad.reshape(-1)) <= 1e-4
+        assert rel_err(got.cpu().reshape(-1) / 8.0, p.grad.reshape(-1)) <= 1e-4
     # L1
     y, c = torch.randn(B, 64, generator=g).to(DEV), torch.randn(B, 64, generator=g).to(DEV)
     gy = torch.zeros_like(y)
     lo.zero_()
-    _lib.call("sg_l1_loss_bwd", _p(y), _p(c), y.numel(), 100.0, _p(lo), _p(gy), 0, _stream())
+    _lib.call("sg_l1_loss_bwd", _p(y), _p(c), y.numel(), 100.0, _p(lo), _p(gy), 0, 4.0, _stream())
     yr = y.cpu().requires_grad_(True)
     l = 100.0 * F.l1_loss(yr, c.cpu())
     l.backward()
     torch.cuda.synchronize()
-    assert abs(float(lo) - float(l)) <= 1e-3 and max_abs(gy.cpu(), yr.grad) <= 1e-7
+    assert abs(float(lo) - float(l)) <= 1e-3 and max_abs(gy.cpu() / 4.0, yr.grad) <= 1e-7
 
 
 def test_optimizers_and_emphasis():

@@ -138,7 +138,7 @@ def test_train_step_vs_reference(backend):
         for name, p in eng.module.named_parameters():
             if tag == "gD." and name.startswith("enc_blocks") and name.endswith("conv.bias"):
                 continue       # gradient is zero in exact arithmetic (bias feeds BatchNorm)
-            err, rms = _check_sampled(t, tag, name, eng.gview(name), 0)
+            err, rms = _check_sampled(t, tag, name, eng.grad_of(name), 0)
             worst[tag + name] = err / (rms + 1e-12)
     bad = {k: v for k, v in worst.items()
            if v > (GRAD_TOL_D if k.startswith("gD.") else GRAD_TOL_G_THROUGH_UPDATED_D)}
@@ -428,7 +428,7 @@ def test_wsegan_step_vs_oracle(variant):
     print("wsegan", variant, "losses", losses, [ref[k] for k in ("d_loss", "g_adv_loss", "pow_loss", "den_loss")])
     for got, k in zip(losses, ("d_loss", "g_adv_loss", "pow_loss", "den_loss")):
         assert abs(got - ref[k]) <= 3e-2 * max(1.0, abs(ref[k])), (variant, k, got, ref[k])
-    rep = {k: rel_err(s.D.engine.gview(k).cpu(), g) for k, g in ref["gradsD"].items()
+    rep = {k: rel_err(s.D.engine.grad_of(k).cpu(), g) for k, g in ref["gradsD"].items()
            if not (k.startswith("enc_blocks") and k.endswith("conv.bias"))}
     print("wsegan D grad rel errs (max):", max(rep.values()))
     assert max(rep.values()) <= 0.2, rep
