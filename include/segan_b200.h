@@ -134,9 +134,25 @@ typedef struct sg_tapgemm_f {
                          column sum and sum of squares of the stored (rounded) values over all computed rows,
                          accumulated into [SG_STAT_SLICES][2][nc] doubles (same buffer sg_bn_stats fills; caller
                          zeroes).  tcgen05 backend, 16-bit out, ksplit 1, n_lo = 0, n_hi = nc, >= 2 M tiles. */
+  void* out2;         /* or NULL.  Fused second output out2[b][out2_halo + m][n] = PReLU_slope[n % slope_mod](out value), same
+                         dtype / row pitch / column mapping as `out`, own halo: the consumer-ready activation of a Generator
+                         block whose contraction feeds PReLU directly (modules.py:99-101,139-141; no norm layer), stored
+                         next to the raw pre-activation the skip connection needs (generator.py:185,191).  With
+                         out2_halo > 0 (reflect padding of the next conv, modules.py:92-98) position m is also written to
+                         its mirror row -m or 2(out_rows-1)-m when it lies within out2_halo of an end; needs m_lo = 0,
+                         m_hi = out_rows, out_rows >= 2*out2_halo + 3.  tcgen05 backend, CTA-pair kernel, 16-bit out. */
+  int32_t out2_halo;
+  const float* slope; /* with out2 == NULL and slope != NULL the PReLU is applied to `out` itself (inference decoder) */
+  int32_t slope_mod;
+  void* sk_ws;        /* or NULL.  Zero-initialised workspace of sg_tapgemm_f_workspace_bytes() bytes that lets the
+                         CTA-pair kernel split the tiles of its last, partial wave along K over all SMs (fp32 partial sums +
+                         counters; the kernel leaves it zeroed).  One workspace per stream: launches that may run
+                         concurrently must not share it. */
 } sg_tapgemm_f;
 
 int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream);
+/* size of sg_tapgemm_f.sk_ws (device memory, zero-filled once by the caller) */
+int64_t sg_tapgemm_f_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-GEMM, weight-gradient form ("W"):

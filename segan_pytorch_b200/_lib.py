@@ -31,6 +31,7 @@ class TapGemmF(C.Structure):
         ("m_lo", C.c_int32), ("m_hi", C.c_int32), ("n_lo", C.c_int32), ("n_hi", C.c_int32),
         ("bias", _vp), ("bias_mod", C.c_int32), ("batch", C.c_int32), ("ksplit", C.c_int32),
         ("backend", C.c_int32), ("tile_n", C.c_int32), ("bn_stats", _vp),
+        ("out2", _vp), ("out2_halo", C.c_int32), ("slope", _vp), ("slope_mod", C.c_int32), ("sk_ws", _vp),
     ]
 
 
@@ -81,7 +82,7 @@ _SIGS = {
     "sg_pcm16_to_wave": [_vp, _vp, _i64, _i, _f, _vp, _vp],
 }
 EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair", "sg_set_ew_variant",
-           "sg_set_grad_dtype"] + list(_SIGS)
+           "sg_set_grad_dtype", "sg_tapgemm_f_workspace_bytes"] + list(_SIGS)
 
 _lib = None
 
@@ -107,6 +108,8 @@ def load():
     lib.sg_set_cta_pair.argtypes = [C.c_int]
     lib.sg_set_ew_variant.restype = C.c_int
     lib.sg_set_ew_variant.argtypes = [C.c_int] * 4
+    lib.sg_tapgemm_f_workspace_bytes.restype = C.c_int64
+    lib.sg_tapgemm_f_workspace_bytes.argtypes = []
     lib.sg_set_grad_dtype.restype = C.c_int
     lib.sg_set_grad_dtype.argtypes = [C.c_int]
     for name, args in _SIGS.items():

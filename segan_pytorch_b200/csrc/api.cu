@@ -14,6 +14,7 @@ int tapgemm_f_ffma_launch(const sg_tapgemm_f* q, cudaStream_t st);
 int tapgemm_w_ffma_launch(const sg_tapgemm_w* q, cudaStream_t st);
 int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st);
 int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st);
+int64_t tapgemm_f_workspace_bytes();
 extern int g_cta_pair;
 int g_grad_dtype = SG_F16;
 }  // namespace sg
@@ -53,6 +54,8 @@ static int check_taps(const int32_t* k_lo, const int32_t* k_hi, const int32_t* n
   return 1;
 }
 
+extern "C" int64_t sg_tapgemm_f_workspace_bytes(void) { return tapgemm_f_workspace_bytes(); }
+
 extern "C" int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream) {
   SG_CHECK_ARG(p != nullptr);
   SG_CHECK_ARG(p->a0 && p->w && p->out);
@@ -68,13 +71,18 @@ extern "C" int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream) {
   SG_CHECK_ARG(p->ksplit <= 1 || p->out_dtype == SG_F32);
   SG_CHECK_ARG(p->m_lo >= -p->out_halo && p->m_hi <= p->out_rows + p->out_halo && p->m_lo < p->m_hi);
   SG_CHECK_ARG(p->batch > 0 && p->a_rows > 0 && p->a_halo >= 0);
+  if (p->out2 != nullptr || p->slope != nullptr) {
+    SG_CHECK_ARG(p->slope != nullptr && p->slope_mod > 0 && p->slope_mod % 64 == 0 && p->out_dtype != SG_F32);
+    SG_CHECK_ARG(p->ksplit <= 1 && p->out2_halo >= 0);
+    SG_CHECK_ARG(p->out2_halo == 0 || (p->m_lo == 0 && p->m_hi == p->out_rows && p->out_rows >= 2 * p->out2_halo + 3));
+  }
   if (p->backend == SG_BACKEND_TCGEN05) {
     SG_CHECK_ARG(p->a_dtype == p->w_dtype);
     return tapgemm_f_tc_launch(p, (cudaStream_t)stream);
   }
   if (p->backend == SG_BACKEND_FFMA) {
-    if (p->bn_stats != nullptr) {
-      set_error("bn_stats (fused BatchNorm statistics) needs the tcgen05 backend");
+    if (p->bn_stats != nullptr || p->out2 != nullptr || p->slope != nullptr) {
+      set_error("bn_stats / out2 (fused epilogues) need the tcgen05 backend");
       return SG_ERR_UNSUPPORTED;
     }
     return tapgemm_f_ffma_launch(p, (cudaStream_t)stream);

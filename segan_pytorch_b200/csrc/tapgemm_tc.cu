@@ -215,6 +215,13 @@ struct FTcParams {
   uint32_t idesc;
   int dbg;                   // timing experiments only (SEGAN_B200_DEBUG): 1 skip B loads, 2 skip A loads, 4 skip stores
   double* stats;             // fused BatchNorm statistics [SG_STAT_SLICES][2][nc] (CTA-pair kernel), or nullptr
+  // CTA-pair kernel only:
+  int sk_dp_tiles;           // tiles [0, sk_dp_tiles) are tile-strided; the rest is split along K over all pairs
+  float* sk_ws;              // stream-K workspace [npairs][2][128][TN] fp32 (zero between launches)
+  unsigned int* sk_cnt;      // k-step counters [npairs][2][4] (zero between launches)
+  void* out2;                // fused PReLU output (16-bit, out's dtype and column geometry), or nullptr
+  int out2_halo;             // reflect halo rows of out2 (its buffer has out_rows + 2 * out2_halo rows per batch element)
+  const float* slope; int slope_mod;
 };
 
 struct SharedCtl {
@@ -490,6 +497,116 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
 
+// ---- work decomposition of tapgemm_f_tc2 ------------------------------------------------------------
+// Tiles [0, sk_dp_tiles) are scheduled tile-strided over the CTA pairs as before.  With batch 300 nearly every
+// layer has a tile count just above a multiple of the 74 pairs (300 = 4 x 75: 76, 150, 300, 600, 1200 tiles), so
+// the last wave ran 2-16 tiles on 74 pairs.  The leftover tiles [sk_dp_tiles, total) are therefore split along K
+// ("stream-K"): their k-steps are laid end to end and cut into npairs equal contiguous ranges, one per pair.  A pair
+// whose range covers a whole tile takes the normal epilogue; otherwise it adds its fp32 partial sums into a
+// workspace tile (vector red) and bumps the tile's k-step counter; the warp whose bump completes the count reads the
+// sums back, applies bias / conversion, stores, and leaves workspace and counter zeroed for the next launch.  No
+// pair ever waits for another one.
+struct Piece {
+  int tile;      // tile index (legacy decode: mp fastest, then ksplit, then nt)
+  int kb, ke;    // k-step range [kb, ke) of the tile's `total` steps (stream-K pieces; whole tile otherwise)
+  int total;
+};
+
+struct PieceIter {
+  int m_pairs, npairs, dp_end, total_tiles;
+  int next_dp, t_sk, acc, u_lo, u_hi;
+
+  __device__ __forceinline__ int steps_of(const FTcParams& p, int tile) const {
+    const int rest = tile / m_pairs;
+    return f_num_steps(p, p.n_lo + (rest / p.ksplit) * p.TN, rest % p.ksplit);
+  }
+  __device__ __forceinline__ void init(const FTcParams& p, int m_pairs_, int total_tiles_, int pair_id, int npairs_) {
+    m_pairs = m_pairs_; npairs = npairs_; total_tiles = total_tiles_;
+    dp_end = p.sk_dp_tiles < total_tiles_ ? p.sk_dp_tiles : total_tiles_;
+    next_dp = pair_id; t_sk = dp_end; acc = 0; u_lo = u_hi = 0;
+    if (dp_end < total_tiles) {
+      int U = 0;
+      for (int t = dp_end; t < total_tiles; ++t) U += steps_of(p, t);
+      u_lo = (int)((long long)U * pair_id / npairs);
+      u_hi = (int)((long long)U * (pair_id + 1) / npairs);
+    }
+  }
+  __device__ __forceinline__ bool next(const FTcParams& p, Piece& pc) {
+    if (next_dp < dp_end) {
+      pc.tile = next_dp; pc.kb = 0; pc.total = pc.ke = steps_of(p, next_dp);
+      next_dp += npairs;
+      return true;
+    }
+    while (t_sk < total_tiles && acc < u_hi) {
+      const int s = steps_of(p, t_sk);
+      const int lo = u_lo > acc ? u_lo : acc;
+      const int hi = u_hi < acc + s ? u_hi : acc + s;
+      const int t = t_sk, a0 = acc;
+      acc += s; ++t_sk;
+      if (lo < hi) { pc.tile = t; pc.kb = lo - a0; pc.ke = hi - a0; pc.total = s; return true; }
+    }
+    return false;
+  }
+};
+
+// one 32-column chunk of an output row: bias / conversion / stores, and the fused second output
+//   out2[b][row2][n] = PReLU(v) (16-bit), the consumer-ready activation of the Generator's conv / deconv blocks
+//   (modules.py:99-101,139-141: no norm layer between the contraction and the PReLU), written next to the raw
+//   pre-activation (`out`, the skip connection's source, generator.py:185,191) with its reflect halo
+//   (modules.py:92-98): position m also lands on its mirror row when it lies within `out2_halo` of an end.
+__device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32], int64_t obase, int c0, int n_abs,
+                                              bool atomic, int64_t o2base, int64_t o2mirror) {
+  if (p.out_dtype == SG_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + obase + c0;
+    if (!atomic) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    return;
+  }
+  uint32_t pk[16];
+  if (p.out2 == nullptr && p.slope != nullptr) {
+    // PReLU applied to the (only) output: blocks whose pre-activation nobody reads (inference decoder)
+    const float* sp = p.slope + (n_abs % p.slope_mod);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : __ldg(sp + j) * v[j];
+  }
+  if (p.out_dtype == SG_F16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_half2_sat(v[2 * j], v[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + c0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  if (p.out2 != nullptr) {
+    const float* sp = p.slope + (n_abs % p.slope_mod);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x0 = v[2 * j], x1 = v[2 * j + 1];
+      const float y0 = x0 > 0.f ? x0 : __ldg(sp + 2 * j) * x0;
+      const float y1 = x1 > 0.f ? x1 : __ldg(sp + 2 * j + 1) * x1;
+      pk[j] = pack_half2_sat(y0, y1);
+    }
+    uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + o2base + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o2[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    if (o2mirror >= 0) {
+      uint4* o3 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + o2mirror + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o3[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmW, const FTcParams p) {
@@ -521,26 +638,31 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   const uint32_t a_bytes = (uint32_t)p.TR * p.TB * 128u;
   const uint32_t b_bytes = (uint32_t)half_n * 128u;
   const int nacc = 512 / p.TN;
+  PieceIter it;
+  it.init(p, m_pairs, total_tiles, pair_id, npairs);
+  Piece pc;
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
     if (lane < 2) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
-        const int mp = tile % m_pairs;
-        const int rest = tile / m_pairs;
+      while (it.next(p, pc)) {
+        const int mp = pc.tile % m_pairs;
+        const int rest = pc.tile / m_pairs;
         const int ks = rest % p.ksplit;
         const int nt = rest / p.ksplit;
         const int mt = 2 * mp + (int)rank;
         const int b0 = (mt / p.m_tiles_per_b) * p.TB;
         const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * p.TR;
         const int n0 = p.n_lo + nt * p.TN;
-        int step = 0;
+        int step = 0, sel = 0;              // step: every (tap, k-block) of the tile; sel: those of this k-split
         for (int d = p.d_lo; d <= p.d_hi; ++d) {
           const int ti = d + 4;
           if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
           for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
             if (p.ksplit > 1 && step % p.ksplit != ks) continue;
+            const int mine = sel++;
+            if (mine < pc.kb || mine >= pc.ke) continue;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE2_BYTES;
             if (leader && lane == 0) mbar_expect_tx(&ctl->full[stage], 2u * (a_bytes + b_bytes));
@@ -561,16 +683,12 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     if (leader) {      // warp-uniform loop, one elected lane issues (see elect_one)
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
-        const int rest = tile / m_pairs;
-        const int ks = rest % p.ksplit;
-        const int nt = rest / p.ksplit;
-        const int n0 = p.n_lo + nt * p.TN;
+      const uint32_t smem0 = smem_u32(smem);
+      while (it.next(p, pc)) {
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.TN);
-        const int nsteps = f_num_steps(p, n0, ks);
-        const uint32_t smem0 = smem_u32(smem);
+        const int nsteps = pc.ke - pc.kb;
         for (int i = 0; i < nsteps; ++i) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
@@ -598,6 +716,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     const int row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const int out_buf_rows = p.out_rows + 2 * p.out_halo;
+    const int out2_buf_rows = p.out_rows + 2 * p.out2_halo;
     // fused BatchNorm statistics (modules.py:100): per-column sum / sum of squares of the stored (rounded)
     // outputs, accumulated per CTA in shared memory across its tiles of one N tile, flushed with one double
     // atomic per column when the N tile changes and at the end
@@ -620,9 +739,9 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       for (int c = et; c < 512; c += 128) colstat[c] = 0.f;
       epi_bar_sync();
     }
-    for (int tile = pair_id; tile < total_tiles; tile += npairs) {
-      const int mp = tile % m_pairs;
-      const int rest = tile / m_pairs;
+    while (it.next(p, pc)) {
+      const int mp = pc.tile % m_pairs;
+      const int rest = pc.tile / m_pairs;
       const int ks = rest % p.ksplit;
       const int nt = rest / p.ksplit;
       const int mt = 2 * mp + (int)rank;
@@ -632,6 +751,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int tb = row / p.TR, tr = row % p.TR;
       const int b = b0 + tb, m = m0 + tr;
       const bool valid = (mt < m_tiles) && (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
+      const bool partial = pc.kb != 0 || pc.ke != pc.total;         // a stream-K piece of a split tile
       if (p.stats != nullptr && nt != stat_nt) {
         if (stat_nt >= 0) flush_stats(stat_nt);
         stat_nt = nt;
@@ -640,6 +760,26 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.TN);
       const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
+      // second (activated) output: same column geometry, its own halo; reflect mirror row of position m, if any
+      int64_t o2base = 0, o2mirror = -1;
+      if (p.out2 != nullptr) {
+        const int64_t rb = (int64_t)b * out2_buf_rows + p.out2_halo;
+        o2base = (rb + m) * p.out_ld + (n0 - p.n_lo + p.out_col0);
+        if (p.out2_halo > 0) {
+          int mm = -1;
+          if (m >= 1 && m <= p.out2_halo) mm = -m;
+          else if (m >= p.out_rows - 1 - p.out2_halo && m <= p.out_rows - 2) mm = 2 * (p.out_rows - 1) - m;
+          if (mm != -1) o2mirror = (rb + mm) * p.out_ld + (n0 - p.n_lo + p.out_col0);
+        }
+      }
+      // stream-K workspace of this (tile, CTA): [128 rows][TN] fp32, and this warp's k-step counter
+      const int slot = pc.tile - it.dp_end;
+      float* wsrow = nullptr;
+      unsigned int* cnt = nullptr;
+      if (partial) {
+        wsrow = p.sk_ws + (((int64_t)slot * 2 + rank) * 128 + row) * p.TN;
+        cnt = p.sk_cnt + ((slot * 2 + (int)rank) * 4 + quad);
+      }
       for (int c0 = 0; c0 < p.TN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
@@ -647,6 +787,13 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (partial) {
+          if (valid && (mt < m_tiles)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) red_add_v4(wsrow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          continue;
+        }
         if (p.bias != nullptr && ks == 0) {
           // bias_mod is a multiple of 64 and the chunk is 32-aligned: one modulo per chunk
           // (scalar loads: bias vectors are 4-byte-aligned views of the flat parameter buffer)
@@ -654,36 +801,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
         }
-        if (valid && !(p.dbg & 4)) {
-          if (p.out_dtype == SG_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + obase + c0;
-            if (p.ksplit == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          } else {
-            uint32_t pk[16];
-            if (p.out_dtype == SG_F16) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                pk[j] = pack_half2_sat(v[2 * j], v[2 * j + 1]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-            }
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-        }
+        if (valid) f_store_chunk(p, v, obase, c0, n0 + c0, p.ksplit > 1, o2base, o2mirror);
         if (p.stats != nullptr) {                      // warp-uniform branch: the reduction is warp-collective
           float q[32];
 #pragma unroll
@@ -705,6 +823,36 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive_leader(&ctl->tmem_empty[acc]);      // 2 x 128 arrivals release the accumulator
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+      if (partial && mt < m_tiles) {
+        // publish this warp's partial sums, count its k-steps; the warp that completes the tile finishes it
+        __threadfence();
+        __syncwarp();
+        unsigned int old = 0;
+        if (lane == 0) old = atomicAdd(cnt, (unsigned int)(pc.ke - pc.kb));
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old + (unsigned int)(pc.ke - pc.kb) == (unsigned int)pc.total) {
+          __threadfence();
+          if (valid) {
+            for (int c0 = 0; c0 < p.TN; c0 += 32) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(wsrow + c0 + j));
+                v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+                *reinterpret_cast<float4*>(wsrow + c0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);   // clean for the next launch
+              }
+              if (p.bias != nullptr) {
+                const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
+              }
+              f_store_chunk(p, v, obase, c0, n0 + c0, false, o2base, o2mirror);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) *cnt = 0u;
+        }
+      }
     }
     if (p.stats != nullptr && stat_nt >= 0) flush_stats(stat_nt);
   }
@@ -1184,6 +1332,13 @@ static int make_map2(CUtensorMap* m, const void* base, int dtype, int C, int64_t
   return SG_OK;
 }
 
+// stream-K workspace: counters [SK_MAX_PAIRS][2][4] u32 (padded to 4 KB), then partial sums [SK_MAX_PAIRS][2][128][256] fp32
+constexpr int SK_MAX_PAIRS = 96;
+constexpr int64_t SK_CNT_BYTES = 4096;
+constexpr int64_t SK_WS_BYTES = SK_CNT_BYTES + (int64_t)SK_MAX_PAIRS * 2 * 128 * 256 * 4;
+int64_t tapgemm_f_workspace_bytes() { return SK_WS_BYTES; }
+int g_stream_k = [] { const char* e = getenv("SEGAN_B200_STREAMK"); return (e && e[0] == '0') ? 0 : 1; }();
+
 int g_cta_pair = 1;   // sg_set_cta_pair(): 0 single-CTA tiles, 1 cta_group::2 pairs, 2 pairs + A reuse across taps (tc3)
 
 static int num_sms() {
@@ -1231,10 +1386,12 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   p.n_tiles = ncols / p.TN;
   p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 128, p.TN);
   {
-    const char* e = getenv("SEGAN_B200_DEBUG");
-    p.dbg = e ? atoi(e) : 0;
+    static const int dbg_env = [] { const char* e = getenv("SEGAN_B200_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg_env;
   }
   p.stats = q->bn_stats;
+  p.sk_dp_tiles = 0x7fffffff; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  p.out2 = q->out2; p.out2_halo = q->out2_halo; p.slope = q->slope; p.slope_mod = q->slope_mod;
   CUtensorMap tmA0, tmA1, tmW;
   const int a_buf_rows = q->a_rows + 2 * q->a_halo;
   int rc = make_map3(&tmA0, q->a0, q->a_dtype, q->a0_c, a_buf_rows, q->batch, p.TR, p.TB);
@@ -1273,7 +1430,12 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     SG_CHECK_LAUNCH();
     return SG_OK;
   }
-  if ((g_cta_pair || q->bn_stats != nullptr) && m_tiles_all >= 2) {
+  const bool fused_act = q->out2 != nullptr || q->slope != nullptr;
+  if (fused_act && !(m_tiles_all >= 2 && g_cta_pair != 2)) {
+    set_error("slope / out2 (fused PReLU) need the CTA-pair kernel (>= 2 M tiles)");
+    return SG_ERR_UNSUPPORTED;
+  }
+  if ((g_cta_pair || q->bn_stats != nullptr || fused_act) && m_tiles_all >= 2) {
     // CTA-pair kernel: A box per CTA as before, weight box = TN/2 rows per CTA, M = 256 UMMA
     static bool attr2 = false;
     if (!attr2) {
@@ -1286,6 +1448,13 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     const int pairs = ((m_tiles_all + 1) / 2) * p.n_tiles * p.ksplit;
     int npairs = num_sms() / 2;
     if (pairs < npairs) npairs = pairs;
+    // stream-K over the last, partial wave (see PieceIter)
+    if (q->sk_ws != nullptr && g_stream_k && p.ksplit == 1 && q->bn_stats == nullptr && npairs <= SK_MAX_PAIRS &&
+        pairs > npairs && pairs % npairs != 0) {
+      p.sk_dp_tiles = (pairs / npairs) * npairs;
+      p.sk_cnt = reinterpret_cast<unsigned int*>(q->sk_ws);
+      p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->sk_ws) + SK_CNT_BYTES);
+    }
     tapgemm_f_tc2<<<2 * npairs, NUM_THREADS, SMEM2_BYTES, st>>>(tmA0, tmA1, tmW, p);
     SG_CHECK_LAUNCH();
     return SG_OK;

@@ -245,6 +245,8 @@ def _plan_f_split(rows_m, batch, ncols):
 # Off by default: bit-correct, but the two extra launches (tail GEMM + convert) and the tail kernel's own prologue
 # cost more than the partial wave they remove (profiles/r1_v6_splitk_tail.txt: 0-10 % slower per layer).
 SPLITK_TAIL = os.environ.get("SEGAN_B200_SPLITK_TAIL", "0").lower() not in ("0", "off", "no", "false")
+# PReLU (+ reflect halo) of the Generator's blocks in the tap-GEMM epilogue (sg_tapgemm_f.out2 / .slope)
+FUSE_ACT = os.environ.get("SEGAN_B200_FUSE_ACT", "1").lower() not in ("0", "off", "no", "false")
 
 
 def _plan_f_tail_splitk(rows_m, batch, ncols, ksteps):
@@ -270,11 +272,37 @@ def _plan_f_tail_splitk(rows_m, batch, ncols, ksteps):
     return b1, s
 
 
+_SK_WS = {}
+STREAM_K = os.environ.get("SEGAN_B200_STREAMK", "1").lower() not in ("0", "off", "no", "false")
+
+
+def sk_workspace(dev):
+    """Stream-K workspace of the CURRENT stream (sg_tapgemm_f.sk_ws): zero-filled once, left zeroed by every launch;
+    one per stream because launches on different streams may run concurrently."""
+    if not STREAM_K:
+        return None
+    key = (torch.device(dev).index, torch.cuda.current_stream().cuda_stream)
+    ws = _SK_WS.get(key)
+    if ws is None:
+        ws = _SK_WS[key] = torch.zeros(int(_lib.load().sg_tapgemm_f_workspace_bytes()), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def f_pair_tiles(rows_m, batch):
+    """M tiles of a form-F launch (mirror of tapgemm_f_tc_launch): the fused-activation epilogue lives in the
+    CTA-pair kernel, which needs at least two."""
+    tb, mpb = _f_tiling(rows_m, batch, 64)[:2]
+    return mpb * ((batch + tb - 1) // tb)
+
+
 def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dtype, out_rows, out_halo,
           m_lo, m_hi, batch, bias=None, bias_mod=0, n_lo=0, n_hi=None, d_lo=-4, d_hi=4, w_tap0=0,
-          out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0, stats=None):
+          out_ld=0, out_col0=0, ksplit=1, backend=None, a0_c=None, a1_c=0, stats=None,
+          out2=None, out2_halo=0, slope=None, slope_mod=0):
     """stats: optional [SL][2][nc] float64 tensor: BatchNorm batch statistics of the output, fused into the
-    epilogue of the tcgen05 CTA-pair kernel (see sg_tapgemm_f.bn_stats)."""
+    epilogue of the tcgen05 CTA-pair kernel (see sg_tapgemm_f.bn_stats).
+    slope (+ out2): PReLU fused into the epilogue -- into `out2` (with reflect halo) next to the raw `out`, or,
+    without out2, into `out` itself (see sg_tapgemm_f.out2)."""
     n_hi = nc if n_hi is None else n_hi
     a0_c = kc if a0_c is None else a0_c
     backend = default_backend() if backend is None else backend
@@ -318,6 +346,9 @@ def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dt
         q.batch, q.ksplit = nb, (tail_ks if tail else ksplit)
         q.backend, q.tile_n = backend, tn
         q.bn_stats = _p(stats)
+        assert (out2 is None and slope is None) or b1 == batch, "fused activation outputs are not split"
+        q.out2, q.out2_halo, q.slope, q.slope_mod = _p(out2), out2_halo, _p(slope), slope_mod
+        q.sk_ws = _p(sk_workspace(out.device)) if backend == BACKEND_TCGEN05 else None
         with _Prof("tapgemm_f", _tap_flops(taps, d_lo, d_hi, q.n_lo, q.n_hi, (m_hi - m_lo) * nb)):
             _lib.call("sg_tapgemm_f_run", C.byref(q), _stream())
         if tail:
@@ -634,6 +665,7 @@ class GeneratorEngine(_NetEngine):
         forwards may precede a backward); the fused train step reuses one persistent workspace."""
         _require_cuda(x, z)
         twins = want_ctx if twins is None else (twins and want_ctx)
+        bwd = twins                               # a backward pass will read this forward's saved tensors
         alias = twins and not grad_twins()        # fp16 gradients: the weight-gradient GEMMs read the forward tensors
         twins = twins and grad_twins()
         self.ensure_packed()
@@ -647,11 +679,25 @@ class GeneratorEngine(_NetEngine):
         a, hp = [None] * nl, [None] * nl
         # bf16 twins (only when a backward will follow): operands of the weight-gradient tap-GEMMs
         hpb, ab, ddb, z16b = [None] * nl, [None] * nl, [None] * nl, None
+        # The Generator has no norm layer between a contraction and its PReLU, so the activation (and the reflect
+        # halo of the next conv) is written by the tap-GEMM epilogue next to the raw pre-activation: no separate
+        # pass over the tensor.  Needs the tcgen05 CTA-pair kernel (>= 2 M tiles), no bf16 twins, and tensors long
+        # enough for the mirror logic; otherwise sg_act_fwd does it as before.
+        eff_backend = default_backend() if self.backend is None else self.backend
+        fuse_ok = FUSE_ACT and eff_backend == BACKEND_TCGEN05 and not twins
+
+        def fused(rows_m, halo):
+            return fuse_ok and f_pair_tiles(rows_m, B) >= 2 and (halo == 0 or rows_m >= 2 * halo + 3)
         # ---- encoder
         for l in range(nl):
             cout = fm[l]
             a[l] = buf.get("g.a%d" % l, (B, Lq[l], cout), F16, dev)
             bias = self.pview("enc_blocks.%d.conv.bias" % l) if self.enc_bias else None
+            halo = 16 if l < nl - 1 else 0
+            hp[l] = buf.get("g.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
+            slope = self.pview("enc_blocks.%d.act.weight" % l)
+            fz = fused(Lq[l], halo) and (l > 0 or wave_on_tensor_cores())
+            fkw = dict(out2=hp[l], out2_halo=halo, slope=slope, slope_mod=cout) if fz else {}
             if l == 0 and wave_on_tensor_cores():
                 col16 = buf.get("g.col16", (B, Lq[0], 64), F16, dev)
                 colb = buf.get("g.colb", (B, Lq[0], 64), GT, dev) if twins else None
@@ -661,7 +707,7 @@ class GeneratorEngine(_NetEngine):
                 self.wait_packed("small")
                 run_f(col16, None, Lq[0], 0, SG_F16, self.packed["Wcol0"], SG_F16, 64, 64,
                       tap_ranges("full", 0, 64, 64), a[0], SG_F16, Lq[0], 0, 0, Lq[0], B, bias=bias, bias_mod=64,
-                      d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
+                      d_lo=0, d_hi=0, w_tap0=4, backend=self.backend, **fkw)
             elif l == 0:
                 colb = None
                 _lib.call("sg_wave_conv_fwd", _p(x), None, 1, B, L, 0, _p(self.pview("enc_blocks.0.conv.weight")),
@@ -671,16 +717,14 @@ class GeneratorEngine(_NetEngine):
                 self.wait_packed("Wf%d" % l)
                 run_f(hp[l - 1], None, Lq[l], 4, SG_F16, self.packed["Wf%d" % l], SG_F16, 4 * cin, cout,
                       tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
-                      bias=bias, bias_mod=cout, backend=self.backend)
-            halo = 16 if l < nl - 1 else 0
-            hp[l] = buf.get("g.hp%d" % l, (B, Lq[l] + 2 * halo, cout), F16, dev)
+                      bias=bias, bias_mod=cout, backend=self.backend, **fkw)
             if twins:
                 hpb[l] = buf.get("g.hpb%d" % l, (B, Lq[l] + 2 * halo, cout), GT, dev)
                 if l < nl - 1:
                     ab[l] = buf.get("g.ab%d" % l, (B, Lq[l], cout), GT, dev)
-            _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, None,
-                      _p(self.pview("enc_blocks.%d.act.weight" % l)), ACT_PRELU, 0, None, halo, _p(hp[l]), _p(hpb[l]),
-                      _p(ab[l]), st)
+            if not fz:
+                _lib.call("sg_act_fwd", _p(a[l]), SG_F16, B, Lq[l], cout, None, _p(slope), ACT_PRELU, 0, None, halo,
+                          _p(hp[l]), _p(hpb[l]), _p(ab[l]), st)
             if alias:
                 hpb[l], ab[l] = hp[l], a[l]
         # ---- z
@@ -700,17 +744,28 @@ class GeneratorEngine(_NetEngine):
         for l in range(nl - 1):
             cin, cout = self.dec_cin(l), self.dec_cout(l)
             assert src0.shape[-1] + src1.shape[-1] == cin
-            ad[l] = buf.get("g.ad%d" % l, (B, lin, 4 * cout), F16, dev)
+            dd[l] = buf.get("g.dd%d" % l, (B, 4 * lin, cout), F16, dev)
+            slope = self.pview("dec_blocks.%d.act.weight" % l)
+            fz = fused(lin, 0)
+            if fz and not bwd:
+                # inference: nobody reads the decoder's pre-activation -- PReLU applied to the only output
+                ad[l] = None
+                fkw = dict(slope=slope, slope_mod=cout)
+                dst = dd[l]
+            else:
+                ad[l] = buf.get("g.ad%d" % l, (B, lin, 4 * cout), F16, dev)
+                fkw = dict(out2=dd[l], slope=slope, slope_mod=cout) if fz else {}
+                dst = ad[l]
             self.wait_packed("Wt%d" % l)
             run_f(src0, src1, lin, 0, SG_F16, self.packed["Wt%d" % l], SG_F16, cin, 4 * cout,
-                  tap_ranges("deconv_fwd", cout, cin, 4 * cout), ad[l], SG_F16, lin, 0, 0, lin, B,
+                  tap_ranges("deconv_fwd", cout, cin, 4 * cout), dst, SG_F16, lin, 0, 0, lin, B,
                   bias=self.pview("dec_blocks.%d.deconv.bias" % l), bias_mod=cout,
-                  a0_c=src0.shape[-1], a1_c=src1.shape[-1], backend=self.backend)
-            dd[l] = buf.get("g.dd%d" % l, (B, 4 * lin, cout), F16, dev)
+                  a0_c=src0.shape[-1], a1_c=src1.shape[-1], backend=self.backend, **fkw)
             if twins:
                 ddb[l] = buf.get("g.ddb%d" % l, (B, 4 * lin, cout), GT, dev)
-            _lib.call("sg_act_fwd", _p(ad[l]), SG_F16, B, 4 * lin, cout, None,
-                      _p(self.pview("dec_blocks.%d.act.weight" % l)), ACT_PRELU, 0, None, 0, _p(dd[l]), _p(ddb[l]), None, st)
+            if not fz:
+                _lib.call("sg_act_fwd", _p(ad[l]), SG_F16, B, 4 * lin, cout, None, _p(slope), ACT_PRELU, 0, None, 0,
+                          _p(dd[l]), _p(ddb[l]), None, st)
             if alias:
                 ddb[l] = dd[l]
             lin *= 4

@@ -675,3 +675,119 @@ def test_cpu_tensor_rejected_loudly():
     s = build_segan()
     with pytest.raises(RuntimeError):
         s.G(torch.zeros(1, 1, 16384))
+
+
+# ------------------------------------------------------------------------------------------------------
+# round 2: stream-K over the last partial wave and the fused PReLU (+ reflect halo) output of the CTA-pair
+# forward-form kernel
+# ------------------------------------------------------------------------------------------------------
+def _sk_case(case, g):
+    """Shapes with MORE CTA-pair tiles than the 74 pairs of a B200 and a ragged last wave."""
+    if case == "conv_fwd":          # 1024 rows x 12 batches = 96 M tiles = 48 pairs x 2 N tiles = 96 = 74 + 22
+        B, cin, cout, R, halo = 12, 64, 512, 1024, 4
+        kc, nc, kind, c = 4 * cin, cout, "conv_fwd", cin
+        m_lo, m_hi, out_halo = 0, R, 0
+    elif case == "deconv_fwd":      # tap-dependent N ranges: tiles of different N have different k-step counts
+        B, cin, cout, R, halo = 41, 128, 128, 256, 0       # 82 M tiles = 41 pairs x 2 N tiles = 82 = 74 + 8
+        kc, nc, kind, c = cin, 4 * cout, "deconv_fwd", cout
+        m_lo, m_hi, out_halo = 0, R, 0
+    else:                           # conv_dgrad into a halo'd view, odd M-tile count (last pair has one CTA idle)
+        B, cin, cout, R, halo = 77, 64, 128, 128, 0        # rows -4..132 = 136 -> 2 M tiles x 77 = 154 -> 77 pairs
+        kc, nc, kind, c = cout, 4 * cin, "conv_dgrad", cin
+        m_lo, m_hi, out_halo = -4, R + 4, 4
+    w, taps = _packed_random(kind, c, kc, nc, g, torch.float16)
+    a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+    return B, kc, nc, R, halo, m_lo, m_hi, out_halo, w, taps, a0
+
+
+@pytest.mark.parametrize("case", ["conv_fwd", "deconv_fwd", "conv_dgrad"])
+def test_tapgemm_f_stream_k(case):
+    """The leftover tiles of the last wave are split along K over all CTA pairs (fp32 partial sums through the
+    workspace, finished by the warp that completes a tile): same result as the unsplit schedule, workspace left
+    zeroed, repeatable."""
+    g = _gen(21)
+    B, kc, nc, R, halo, m_lo, m_hi, out_halo, w, taps, a0 = _sk_case(case, g)
+    bias = torch.randn(nc, generator=g).to(DEV)
+    outs = []
+    ws = E.sk_workspace(DEV)
+    assert ws is not None and int(ws.count_nonzero()) == 0
+    for sk in (False, True, True):
+        prev = E.STREAM_K
+        E.STREAM_K = sk
+        try:
+            out = torch.zeros(B, R + 2 * out_halo, nc, dtype=torch.float16, device=DEV)
+            E.run_f(a0, None, R, halo, SG_F16, w, SG_F16, kc, nc, taps, out, SG_F16, R, out_halo, m_lo, m_hi, B,
+                    bias=bias, bias_mod=nc, backend=BACKEND_TCGEN05)
+            torch.cuda.synchronize()
+            outs.append(out.float().cpu())
+        finally:
+            E.STREAM_K = prev
+    assert int(ws.count_nonzero()) == 0, "stream-K workspace / counters must be left zeroed"
+    ref = _ref_f(F.pad(a0.float().cpu(), (0, 0, 0, 0)), halo, w.cpu(), m_lo, m_hi) + bias.cpu()
+    lo = out_halo + m_lo
+    for o in outs:
+        assert rel_err(o[:, lo:lo + (m_hi - m_lo)], ref) <= 2e-3
+    # split vs unsplit: only the fp32 summation order of the split tiles differs (then one fp16 rounding)
+    assert max_abs(outs[1], outs[0]) <= 4e-3 * float(ref.abs().max())
+    assert torch.equal(outs[1], outs[2])
+
+
+@pytest.mark.parametrize("halo", [16, 0])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_tapgemm_f_fused_prelu_output(halo, inplace):
+    """sg_tapgemm_f.out2 / .slope: PReLU(out) written by the epilogue, with the reflect halo of the next conv
+    (modules.py:92-101), next to the raw output -- or into the only output (inference decoder) -- also on tiles
+    finished through the stream-K path."""
+    if inplace and halo:
+        pytest.skip("in-place activation has no halo")
+    g = _gen(22)
+    B, cin, cout, R = 12, 64, 512, 1024            # 96 pair tiles: 22 of them take the stream-K path
+    kc, nc = 4 * cin, cout
+    w, taps = _packed_random("conv_fwd", cin, kc, nc, g, torch.float16)
+    a0 = torch.randn(B, R + 8, kc, generator=g).to(torch.float16).to(DEV)
+    bias = torch.randn(nc, generator=g).to(DEV)
+    slope = (0.3 * torch.rand(128, generator=g)).to(DEV)        # slope index = n % 128
+    out = torch.zeros(B, R, nc, dtype=torch.float16, device=DEV)
+    out2 = torch.zeros(B, R + 2 * halo, nc, dtype=torch.float16, device=DEV)
+    if inplace:
+        E.run_f(a0, None, R, 4, SG_F16, w, SG_F16, kc, nc, taps, out, SG_F16, R, 0, 0, R, B, bias=bias, bias_mod=nc,
+                backend=BACKEND_TCGEN05, slope=slope, slope_mod=128)
+    else:
+        E.run_f(a0, None, R, 4, SG_F16, w, SG_F16, kc, nc, taps, out, SG_F16, R, 0, 0, R, B, bias=bias, bias_mod=nc,
+                backend=BACKEND_TCGEN05, out2=out2, out2_halo=halo, slope=slope, slope_mod=128)
+    torch.cuda.synchronize()
+    ref = _ref_f(a0.float().cpu(), 4, w.cpu(), 0, R) + bias.cpu()                       # (B, R, nc)
+    sl = slope.cpu().repeat(nc // 128)
+    act = torch.where(ref > 0, ref, ref * sl)
+    if inplace:
+        assert rel_err(out.float().cpu(), act) <= 2e-3
+        return
+    assert rel_err(out.float().cpu(), ref) <= 2e-3
+    if halo:
+        act = F.pad(act.permute(0, 2, 1), (halo, halo), mode="reflect").permute(0, 2, 1)
+    assert rel_err(out2.float().cpu(), act) <= 2e-3
+    # the halo rows are bit-copies of their mirror positions
+    if halo:
+        o2 = out2.cpu()
+        assert torch.equal(o2[:, 0], o2[:, 2 * halo]) and torch.equal(o2[:, halo + R + halo - 1], o2[:, halo + R - 1 - halo])
+
+
+def test_generator_forward_fused_vs_unfused_activation():
+    """Generator forward with the activation in the GEMM epilogue vs the separate sg_act_fwd pass: the fused path
+    rounds PReLU(fp32 accumulator) once, the separate pass rounds the pre-activation first -- one fp16 ulp apart."""
+    from tests.util import build_segan
+    s = build_segan().to(DEV)
+    g = _gen(23)
+    x = (0.3 * torch.randn(5, 1, 16384, generator=g)).to(DEV)
+    z = torch.randn(5, 1024, 16, generator=g).to(DEV)
+    s.G.eval()
+    outs = []
+    for fuse in (True, False):
+        prev = E.FUSE_ACT
+        E.FUSE_ACT = fuse
+        try:
+            with torch.no_grad():
+                outs.append(s.G(x, z=z).cpu())
+        finally:
+            E.FUSE_ACT = prev
+    assert max_abs(outs[0], outs[1]) <= 3e-4
