@@ -92,6 +92,11 @@ int sg_set_ew_variant(int kind, int vec, int unroll, int cap);
  * saturate at +-65504.  (autograd in model.py:299,306,320 keeps fp32 gradients: this is the precision contract
  * of north_star's "fp16/bf16 sample windows".) */
 int sg_set_grad_dtype(int dtype);
+/* Split-K over the last, partial wave of sg_tapgemm_f_run's CTA-pair kernel (needs sg_tapgemm_f.sk_ws):
+ * max_split = largest number of CTA pairs one leftover tile is split over (0 | 1 = off, default 16; < 0 keeps it);
+ * atomic_steps = cost-model constant, the L2-atomic cost of one partial tile in k-steps (<= 0 keeps it).
+ * Returns the previous max_split.  Environment: SEGAN_B200_STREAMK, SEGAN_B200_SK_ATOMIC. */
+int sg_set_stream_k(int max_split, float atomic_steps);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-GEMM, forward form ("F"):
@@ -316,12 +321,34 @@ int sg_l1_loss_bwd(const float* y, const float* clean, int64_t n, float weight, 
 /* ------------------------------------------------------------------------------------------
  * Optimisers on flat fp32 buffers (torch.optim.RMSprop / Adam as used at model.py:221-225).
  * grad_scale multiplies the gradient first (1/world_size after an all-reduce SUM).
+ * clear_grad != 0 zeroes `grad` as it is read (the next backward pass accumulates from zero: no separate fill).
  * ------------------------------------------------------------------------------------------ */
-int sg_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr,
-                    float alpha, float eps, float grad_scale, void* stream);
-int sg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                 float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+int sg_rmsprop_step(float* param, float* grad, float* square_avg, int64_t n, float lr,
+                    float alpha, float eps, float grad_scale, int clear_grad, void* stream);
+int sg_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, int step, float grad_scale, int clear_grad,
                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Packed-master path (training): master weights, optimiser state and gradients of a tap-GEMM layer stay in the
+ * layout of its forward operand, M[n_taps][nc][kc] fp32 -- what sg_tapgemm_w_run produces and what the elementwise
+ * optimisers above do not care about -- so a step needs no reference-layout round trip:
+ *   sg_emit_operands : F[t][n][k] = M[t][n][k]*a(k) (forward operand), Dg[t][k][n] = M[T-1-t][n][k]*a(k) (data-
+ *                      gradient operand), a(k) = alpha[k - alpha_from] for k >= alpha_from (GSkip, generator.py:68-69)
+ *                      else 1; either destination may be NULL; dtypes SG_F16 | SG_BF16 | SG_F32.
+ *   sg_alpha_grad    : in place dWp[t][n][k] *= alpha(k) for k >= alpha_from (the tap-GEMM differentiated w.r.t. the
+ *                      alpha-scaled weights) and dalpha[k - alpha_from] += sum_{t,n} dWp*M (before the scaling).
+ *   sg_pack_weights(kind, w, ..., w_fwd = M, w_dgrad = NULL, SG_F32, ...) imports a reference-layout tensor and
+ *   sg_unpack_wgrad(kind, M, ..., alpha = NULL, ..., accumulate = 0) exports one (state_dict, checkpoints).
+ * sg_wave_wgrad_fold / sg_last_deconv_wgrad_fold: the waveform-end layers' weight gradients out of their single-tap
+ * GEMM results (dwq, see engine.py), accumulated atomically into reference-layout gradients. */
+int sg_emit_operands(const float* master, int n_taps, int nc, int kc, const float* alpha, int alpha_from,
+                     void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad, void* stream);
+int sg_alpha_grad(float* dwp, const float* master, int n_taps, int nc, int kc, const float* alpha, int alpha_from,
+                  float* dalpha, void* stream);
+int sg_wave_wgrad_fold(const float* dwq, int cin, float* dw, void* stream);
+int sg_last_deconv_wgrad_fold(const float* dwq, int half, const float* w, const float* alpha, float* dw,
+                              float* dalpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Inference tail (clean.py:72 -> model.py:156 -> se_dataset.py:119-126): de-emphasis

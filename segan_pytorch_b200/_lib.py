@@ -75,14 +75,18 @@ _SIGS = {
     "sg_fc_tail_fwd": [_vp] * 8 + [_i, _vp, _vp, _vp, _vp],
     "sg_fc_tail_bwd": [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp] + [_vp] * 7 + [_f, _vp],
     "sg_l1_loss_bwd": [_vp, _vp, _i64, _f, _vp, _vp, _i, _f, _vp],
-    "sg_rmsprop_step": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
-    "sg_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp],
+    "sg_rmsprop_step": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp],
+    "sg_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _i, _vp],
+    "sg_emit_operands": [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp],
+    "sg_alpha_grad": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp],
+    "sg_wave_wgrad_fold": [_vp, _i, _vp, _vp],
+    "sg_last_deconv_wgrad_fold": [_vp, _i, _vp, _vp, _vp, _vp, _vp],
     "sg_deemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_preemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_pcm16_to_wave": [_vp, _vp, _i64, _i, _f, _vp, _vp],
 }
 EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair", "sg_set_ew_variant",
-           "sg_set_grad_dtype", "sg_tapgemm_f_workspace_bytes"] + list(_SIGS)
+           "sg_set_grad_dtype", "sg_set_stream_k", "sg_tapgemm_f_workspace_bytes"] + list(_SIGS)
 
 _lib = None
 
@@ -110,6 +114,8 @@ def load():
     lib.sg_set_ew_variant.argtypes = [C.c_int] * 4
     lib.sg_tapgemm_f_workspace_bytes.restype = C.c_int64
     lib.sg_tapgemm_f_workspace_bytes.argtypes = []
+    lib.sg_set_stream_k.restype = C.c_int
+    lib.sg_set_stream_k.argtypes = [C.c_int, C.c_float]
     lib.sg_set_grad_dtype.restype = C.c_int
     lib.sg_set_grad_dtype.argtypes = [C.c_int]
     for name, args in _SIGS.items():

@@ -16,6 +16,8 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st);
 int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st);
 int64_t tapgemm_f_workspace_bytes();
 extern int g_cta_pair;
+extern int g_stream_k;
+extern double g_sk_atomic_steps;
 int g_grad_dtype = SG_F16;
 }  // namespace sg
 
@@ -27,6 +29,13 @@ extern "C" const char* sg_last_error(void) { return g_err; }
 extern "C" int sg_set_cta_pair(int on) {
   const int prev = g_cta_pair;
   g_cta_pair = on < 0 ? 0 : (on > 2 ? 2 : on);
+  return prev;
+}
+
+extern "C" int sg_set_stream_k(int max_split, float atomic_steps) {
+  const int prev = g_stream_k;
+  if (max_split >= 0) g_stream_k = max_split;
+  if (atomic_steps > 0.f) g_sk_atomic_steps = atomic_steps;
   return prev;
 }
 

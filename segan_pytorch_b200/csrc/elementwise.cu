@@ -585,7 +585,7 @@ __global__ void stat_grads_kernel(const double* __restrict__ red, int C, int n_s
     if (!outs[s]) continue;
     double acc = 0;
     for (int i = 0; i < SL; ++i) acc += red[((int64_t)i * n_stats + s) * C + c];
-    outs[s][c] += (float)acc;
+    atomicAdd(outs[s] + c, (float)acc);       // two passes of one network (D real / fake lanes) may run concurrently
   }
 }
 

@@ -4,18 +4,25 @@
 
 namespace sg {
 
+// 16-bit or fp32 destination element (the packed fp32 MASTER is written with SG_F32)
+__device__ __forceinline__ void st_any(void* p, int64_t i, float v, int dtype) {
+  if (dtype == SG_F32) reinterpret_cast<float*>(p)[i] = v;
+  else st16(p, i, v, dtype);
+}
+
 // ------------------------------------------------------------------------------------------
 // torch.optim.RMSprop (centered=False, momentum=0, weight_decay=0):
 //   sq = alpha*sq + (1-alpha)*g*g ; p -= lr * g / (sqrt(sq) + eps)
 // ------------------------------------------------------------------------------------------
-__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
-                               int64_t n, float lr, float alpha, float eps, float gscale) {
+__global__ void rmsprop_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ sq,
+                               int64_t n, float lr, float alpha, float eps, float gscale, int clear) {
   const int64_t n4 = n / 4;
   float4* p4 = reinterpret_cast<float4*>(p);
-  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* g4 = reinterpret_cast<float4*>(g);
   float4* s4 = reinterpret_cast<float4*>(sq);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pv = p4[i], gv = g4[i], sv = s4[i];
+    if (clear) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);      // clear-on-read: the next backward accumulates from zero
     float* pp = &pv.x; float* gp = &gv.x; float* sp = &sv.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -29,17 +36,19 @@ __global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ 
   }
   for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
+    if (clear) g[i] = 0.f;
     const float s = alpha * sq[i] + (1.f - alpha) * gi * gi;
     sq[i] = s;
     p[i] = p[i] - lr * (gi / (sqrtf(s) + eps));
   }
 }
 // torch.optim.Adam (amsgrad=False, weight_decay=0)
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                            float bc1, float bc2_sqrt, float gscale) {
+                            float bc1, float bc2_sqrt, float gscale, int clear) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
+    if (clear) g[i] = 0.f;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
@@ -89,11 +98,11 @@ pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner
       if (kind == 0) {   // Wf[ti][co = hi][ph*Cin + ci = lo],  k = 4d + ph + 14
         const int k = 4 * d + ph + 14;
         const float v = (k >= 0 && k < KW) ? tile[hi][lo][k] : 0.f;
-        st16(w_fwd, ((int64_t)ti * c_outer + (o0 + hi)) * (4 * c_inner) + ph * c_inner + (i0 + lo), v, dt_fwd);
+        if (w_fwd) st_any(w_fwd, ((int64_t)ti * c_outer + (o0 + hi)) * (4 * c_inner) + ph * c_inner + (i0 + lo), v, dt_fwd);
       } else {           // Wtd[ti][ci = hi][ph*Cout + co = lo],  k = 4d + ph + 13
         const int k = 4 * d + ph + 13;
         const float v = (k >= 0 && k < KW) ? tile[hi][lo][k] : 0.f;
-        st16(w_dg, ((int64_t)ti * c_outer + (o0 + hi)) * (4 * c_inner) + ph * c_inner + (i0 + lo), v, dt_dg);
+        if (w_dg) st_any(w_dg, ((int64_t)ti * c_outer + (o0 + hi)) * (4 * c_inner) + ph * c_inner + (i0 + lo), v, dt_dg);
       }
     }
     {  // B: lo = outer
@@ -102,11 +111,11 @@ pack_conv_kernel(int kind, const float* __restrict__ w, int c_outer, int c_inner
       if (kind == 0) {   // Wdg[ti][ph*Cin + ci = hi][co = lo],  k = -4d + ph + 14
         const int k = -4 * d + ph + 14;
         const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
-        st16(w_dg, ((int64_t)ti * (4 * c_inner) + ph * c_inner + (i0 + hi)) * c_outer + (o0 + lo), v, dt_dg);
+        if (w_dg) st_any(w_dg, ((int64_t)ti * (4 * c_inner) + ph * c_inner + (i0 + hi)) * c_outer + (o0 + lo), v, dt_dg);
       } else {           // Wt[ti][ph*Cout + co = hi][ci = lo],  k = -4d + ph + 13
         const int k = -4 * d + ph + 13;
         const float v = (k >= 0 && k < KW) ? tile[lo][hi][k] : 0.f;
-        st16(w_fwd, ((int64_t)ti * (4 * c_inner) + ph * c_inner + (i0 + hi)) * c_outer + (o0 + lo), v, dt_fwd);
+        if (w_fwd) st_any(w_fwd, ((int64_t)ti * (4 * c_inner) + ph * c_inner + (i0 + hi)) * c_outer + (o0 + lo), v, dt_fwd);
       }
     }
   }
@@ -122,8 +131,8 @@ __global__ void pack_fc_kernel(const float* __restrict__ w, int nout, int C, int
     const int kk = (int)(i % ((int64_t)C * T));
     const int t = kk / C, c = kk % C;
     const float v = w[(int64_t)n * C * T + (int64_t)c * T + t];
-    st16(w_fwd, i, v, dt_fwd);
-    st16(w_dg, (int64_t)kk * nout + n, v, dt_dg);
+    if (w_fwd) st_any(w_fwd, i, v, dt_fwd);
+    if (w_dg) st_any(w_dg, (int64_t)kk * nout + n, v, dt_dg);
   }
 }
 
@@ -192,6 +201,102 @@ __global__ void unpack_fc_kernel(const float* __restrict__ dwp, int nout, int C,
     const int64_t o = (int64_t)n * C * T + (int64_t)c * T + t;
     dw[o] = accumulate ? dw[o] + dwp[i] : dwp[i];
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Packed-master path.  The fp32 master weights, the optimiser state and the gradients of every tap-GEMM layer
+// live in the layout of the layer's FORWARD operand, M[T][nc][kc] (T = 9 taps, or 1 for the Linear): the
+// weight-gradient tap-GEMM already produces that layout, RMSprop / Adam are elementwise, and the two 16-bit
+// operands are one elementwise copy and one per-tap transpose of it:
+//     F [t][n][k]  = M[t][n][k] * colscale[k]                     (forward operand)
+//     Dg[t][k][n]  = M[T-1-t][n][k] * colscale[k]                 (data-gradient operand: tap d <-> -d)
+// colscale = the GSkip alpha of the decoder's skip half (generator.py:68-69), 1 elsewhere.
+// One block = one 64 x 64 (n, k) tile of one tap.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+emit_operands_kernel(const float* __restrict__ m, int T, int nc, int kc, const float* __restrict__ alpha,
+                     int alpha_from, void* __restrict__ f, void* __restrict__ dg, int dt_f, int dt_dg) {
+  __shared__ float tile[64][65];
+  const int t = blockIdx.z;
+  const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
+  const float sc = (alpha && k0 + tx >= alpha_from) ? alpha[k0 + tx - alpha_from] : 1.f;
+  const int64_t mbase = ((int64_t)t * nc + n0) * kc + k0;
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) {
+    const float v = m[mbase + (int64_t)r * kc + tx] * sc;
+    tile[r][tx] = v;
+    if (f) st_any(f, mbase + (int64_t)r * kc + tx, v, dt_f);
+  }
+  if (!dg) return;
+  __syncthreads();
+  const int64_t dbase = ((int64_t)(T - 1 - t) * kc + k0) * nc + n0;
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) st_any(dg, dbase + (int64_t)r * nc + tx, tile[tx][r], dt_dg);
+}
+
+// dWeff (packed, w.r.t. alpha-scaled weights) -> dW = alpha * dWeff in place and
+// dalpha[k - alpha_from] += sum_{t, n} dWeff[t][n][k] * M[t][n][k]   for the columns k >= alpha_from.
+// Block = 32 columns x (256/32 = 8) row lanes striding all T*nc rows.
+__global__ void __launch_bounds__(256)
+alpha_grad_kernel(float* __restrict__ dwp, const float* __restrict__ m, int64_t rows, int kc,
+                  const float* __restrict__ alpha, int alpha_from, float* __restrict__ dalpha) {
+  __shared__ float red[8][33];
+  const int c = alpha_from + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_r = threadIdx.x >> 5;
+  const int64_t r_lo = (int64_t)blockIdx.y * 8 + lane_r;
+  const float a = alpha[c - alpha_from];
+  float acc = 0.f;
+  for (int64_t r = r_lo; r < rows; r += (int64_t)gridDim.y * 8) {
+    const int64_t i = r * kc + c;
+    const float g = dwp[i];
+    acc = fmaf(g, m[i], acc);
+    dwp[i] = g * a;
+  }
+  red[lane_r][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    if (dalpha) atomicAdd(dalpha + (c - alpha_from), s);
+  }
+}
+
+// Waveform-end layer gradients out of their single-tap GEMM results (both tiny):
+//   first conv (Cin = 1 | 2): dwq[2][64][2][64] (position-pair s x co x pair s' x (ci*32 + k)); the s == s' blocks
+//   are the gradient:  dW[co][ci][k] += dwq[0][co][0][ci*32+k] + dwq[1][co][1][ci*32+k]
+__global__ void wave_wgrad_fold_kernel(const float* __restrict__ dwq, int cin, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * cin * KW) return;
+  const int co = i / (cin * KW), rem = i % (cin * KW);
+  const int ci = rem / KW, k = rem % KW;
+  const int col = ci * 32 + k;
+  const float v = dwq[((0 * 64 + co) * 2 + 0) * 64 + col] + dwq[((1 * 64 + co) * 2 + 1) * 64 + col];
+  atomicAdd(dw + i, v);
+}
+//   last deconv (Cout = 1, alpha folded into its effective weight): dwq[2][64][2][2][half] (s, k-slot, source,
+//   s', c); dWeff[src*half + c][k] = dwq[0][k][src][0][c] + dwq[1][k][src][1][c]; dW += dWeff (* alpha for the skip
+//   half), dalpha[c] += sum_k dWeff[half + c][k] * W[half + c][k]
+__global__ void last_deconv_wgrad_fold_kernel(const float* __restrict__ dwq, int half, const float* __restrict__ w,
+                                              const float* __restrict__ alpha, float* __restrict__ dw,
+                                              float* __restrict__ dalpha) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;       // channel of cat(decoder, skip): [0, 2*half)
+  if (ch >= 2 * half) return;
+  const int src = ch / half, c = ch % half;
+  float da = 0.f;
+  for (int k = 0; k < KW; ++k) {
+    const float v = dwq[((((int64_t)0 * 64 + k) * 2 + src) * 2 + 0) * half + c] +
+                    dwq[((((int64_t)1 * 64 + k) * 2 + src) * 2 + 1) * half + c];
+    const int64_t wi = (int64_t)ch * KW + k;
+    if (src == 1) {
+      da = fmaf(v, w[wi], da);
+      atomicAdd(dw + wi, v * alpha[c]);
+    } else {
+      atomicAdd(dw + wi, v);
+    }
+  }
+  if (src == 1 && dalpha) atomicAdd(dalpha + c, da);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -269,19 +374,20 @@ __global__ void preemph_kernel(const float* __restrict__ x, int64_t n, float c, 
 using namespace sg;
 #define ST ((cudaStream_t)stream)
 
-extern "C" int sg_rmsprop_step(float* param, const float* grad, float* square_avg, int64_t n, float lr, float alpha,
-                               float eps, float grad_scale, void* stream) {
-  rmsprop_kernel<<<8 * NUM_SMS, 256, 0, ST>>>(param, grad, square_avg, n, lr, alpha, eps, grad_scale);
+extern "C" int sg_rmsprop_step(float* param, float* grad, float* square_avg, int64_t n, float lr, float alpha,
+                               float eps, float grad_scale, int clear_grad, void* stream) {
+  rmsprop_kernel<<<8 * NUM_SMS, 256, 0, ST>>>(param, grad, square_avg, n, lr, alpha, eps, grad_scale, clear_grad);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
 
-extern "C" int sg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                            float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+extern "C" int sg_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                            float beta1, float beta2, float eps, int step, float grad_scale, int clear_grad,
+                            void* stream) {
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1,
-                                           sqrtf(bc2), grad_scale);
+                                           sqrtf(bc2), grad_scale, clear_grad);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -289,7 +395,7 @@ extern "C" int sg_adam_step(float* param, const float* grad, float* exp_avg, flo
 extern "C" int sg_pack_weights(int kind, const float* w, int c_out, int c_in, int t_len, const float* alpha,
                                int alpha_from, void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad,
                                void* stream) {
-  SG_CHECK_ARG(w && w_fwd && w_dgrad);
+  SG_CHECK_ARG(w && (w_fwd || w_dgrad));
   static bool attr_set = false;
   if (!attr_set) {
     SG_CHECK_CUDA(cudaFuncSetAttribute(pack_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PACK_SMEM));
@@ -338,6 +444,45 @@ extern "C" int sg_unpack_wgrad(int kind, const float* dwp, int c_out, int c_in, 
   } else {
     SG_CHECK_ARG(false);
   }
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_emit_operands(const float* master, int n_taps, int nc, int kc, const float* alpha, int alpha_from,
+                                void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad, void* stream) {
+  SG_CHECK_ARG(master && (w_fwd || w_dgrad) && n_taps >= 1 && nc % 64 == 0 && kc % 64 == 0);
+  SG_CHECK_ARG(!alpha || (alpha_from >= 0 && alpha_from < kc));
+  dim3 grid(kc / 64, nc / 64, n_taps);
+  emit_operands_kernel<<<grid, 256, 0, ST>>>(master, n_taps, nc, kc, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
+                                             dtype_dgrad);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_alpha_grad(float* dwp, const float* master, int n_taps, int nc, int kc, const float* alpha,
+                             int alpha_from, float* dalpha, void* stream) {
+  SG_CHECK_ARG(dwp && master && alpha && alpha_from >= 0 && alpha_from < kc && (kc - alpha_from) % 32 == 0);
+  const int64_t rows = (int64_t)n_taps * nc;
+  int gy = (int)((rows + 8 * 64 - 1) / (8 * 64));
+  if (gy < 1) gy = 1;
+  if (gy > 64) gy = 64;
+  dim3 grid((kc - alpha_from) / 32, gy);
+  alpha_grad_kernel<<<grid, 256, 0, ST>>>(dwp, master, rows, kc, alpha, alpha_from, dalpha);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_wave_wgrad_fold(const float* dwq, int cin, float* dw, void* stream) {
+  SG_CHECK_ARG(dwq && dw && (cin == 1 || cin == 2));
+  wave_wgrad_fold_kernel<<<(64 * cin * KW + 255) / 256, 256, 0, ST>>>(dwq, cin, dw);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+
+extern "C" int sg_last_deconv_wgrad_fold(const float* dwq, int half, const float* w, const float* alpha, float* dw,
+                                         float* dalpha, void* stream) {
+  SG_CHECK_ARG(dwq && w && alpha && dw && half > 0);
+  last_deconv_wgrad_fold_kernel<<<(2 * half + 127) / 128, 128, 0, ST>>>(dwq, half, w, alpha, dw, dalpha);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

@@ -216,7 +216,8 @@ struct FTcParams {
   int dbg;                   // timing experiments only (SEGAN_B200_DEBUG): 1 skip B loads, 2 skip A loads, 4 skip stores
   double* stats;             // fused BatchNorm statistics [SG_STAT_SLICES][2][nc] (CTA-pair kernel), or nullptr
   // CTA-pair kernel only:
-  int sk_dp_tiles;           // tiles [0, sk_dp_tiles) are tile-strided; the rest is split along K over all pairs
+  int sk_dp_tiles;           // tiles [0, sk_dp_tiles) are tile-strided; each of the rest is split along K over
+  int sk_split;              // sk_split CTA pairs
   float* sk_ws;              // stream-K workspace [npairs][2][128][TN] fp32 (zero between launches)
   unsigned int* sk_cnt;      // k-step counters [npairs][2][4] (zero between launches)
   void* out2;                // fused PReLU output (16-bit, out's dtype and column geometry), or nullptr
@@ -500,12 +501,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 // ---- work decomposition of tapgemm_f_tc2 ------------------------------------------------------------
 // Tiles [0, sk_dp_tiles) are scheduled tile-strided over the CTA pairs as before.  With batch 300 nearly every
 // layer has a tile count just above a multiple of the 74 pairs (300 = 4 x 75: 76, 150, 300, 600, 1200 tiles), so
-// the last wave ran 2-16 tiles on 74 pairs.  The leftover tiles [sk_dp_tiles, total) are therefore split along K
-// ("stream-K"): their k-steps are laid end to end and cut into npairs equal contiguous ranges, one per pair.  A pair
-// whose range covers a whole tile takes the normal epilogue; otherwise it adds its fp32 partial sums into a
-// workspace tile (vector red) and bumps the tile's k-step counter; the warp whose bump completes the count reads the
-// sums back, applies bias / conversion, stores, and leaves workspace and counter zeroed for the next launch.  No
-// pair ever waits for another one.
+// the last wave ran 2-16 tiles on 74 pairs.  Each leftover tile [sk_dp_tiles, total) is therefore split along K
+// over sk_split pairs (pair p takes k-range p % sk_split of leftover tile p / sk_split): every one of them adds its
+// fp32 partial sums into a workspace tile (vector red) and bumps the tile's k-step counter; the warp whose bump
+// completes the count reads the sums back, applies bias / conversion, stores, and leaves workspace and counter
+// zeroed for the next launch.  No pair ever waits for another one.  The split factor is chosen by the host: the
+// partial sums cost L2 atomics in proportion to sk_split, the tail shrinks as 1 / sk_split (tapgemm_f_tc_launch).
 struct Piece {
   int tile;      // tile index (legacy decode: mp fastest, then ksplit, then nt)
   int kb, ke;    // k-step range [kb, ke) of the tile's `total` steps (stream-K pieces; whole tile otherwise)
@@ -513,23 +514,19 @@ struct Piece {
 };
 
 struct PieceIter {
-  int m_pairs, npairs, dp_end, total_tiles;
-  int next_dp, t_sk, acc, u_lo, u_hi;
+  int m_pairs, npairs, dp_end, total_tiles, pair_id;
+  int next_dp;
+  bool sk_done;
 
   __device__ __forceinline__ int steps_of(const FTcParams& p, int tile) const {
     const int rest = tile / m_pairs;
     return f_num_steps(p, p.n_lo + (rest / p.ksplit) * p.TN, rest % p.ksplit);
   }
-  __device__ __forceinline__ void init(const FTcParams& p, int m_pairs_, int total_tiles_, int pair_id, int npairs_) {
-    m_pairs = m_pairs_; npairs = npairs_; total_tiles = total_tiles_;
+  __device__ __forceinline__ void init(const FTcParams& p, int m_pairs_, int total_tiles_, int pair_id_, int npairs_) {
+    m_pairs = m_pairs_; npairs = npairs_; total_tiles = total_tiles_; pair_id = pair_id_;
     dp_end = p.sk_dp_tiles < total_tiles_ ? p.sk_dp_tiles : total_tiles_;
-    next_dp = pair_id; t_sk = dp_end; acc = 0; u_lo = u_hi = 0;
-    if (dp_end < total_tiles) {
-      int U = 0;
-      for (int t = dp_end; t < total_tiles; ++t) U += steps_of(p, t);
-      u_lo = (int)((long long)U * pair_id / npairs);
-      u_hi = (int)((long long)U * (pair_id + 1) / npairs);
-    }
+    next_dp = pair_id_;
+    sk_done = false;
   }
   __device__ __forceinline__ bool next(const FTcParams& p, Piece& pc) {
     if (next_dp < dp_end) {
@@ -537,15 +534,16 @@ struct PieceIter {
       next_dp += npairs;
       return true;
     }
-    while (t_sk < total_tiles && acc < u_hi) {
-      const int s = steps_of(p, t_sk);
-      const int lo = u_lo > acc ? u_lo : acc;
-      const int hi = u_hi < acc + s ? u_hi : acc + s;
-      const int t = t_sk, a0 = acc;
-      acc += s; ++t_sk;
-      if (lo < hi) { pc.tile = t; pc.kb = lo - a0; pc.ke = hi - a0; pc.total = s; return true; }
-    }
-    return false;
+    if (sk_done || dp_end >= total_tiles) return false;
+    sk_done = true;
+    const int t = dp_end + pair_id / p.sk_split;
+    if (t >= total_tiles) return false;
+    const int part = pair_id % p.sk_split;
+    const int s = steps_of(p, t);
+    pc.tile = t; pc.total = s;
+    pc.kb = (int)((long long)s * part / p.sk_split);
+    pc.ke = (int)((long long)s * (part + 1) / p.sk_split);
+    return pc.kb < pc.ke;
   }
 };
 
@@ -766,10 +764,11 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         const int64_t rb = (int64_t)b * out2_buf_rows + p.out2_halo;
         o2base = (rb + m) * p.out_ld + (n0 - p.n_lo + p.out_col0);
         if (p.out2_halo > 0) {
-          int mm = -1;
-          if (m >= 1 && m <= p.out2_halo) mm = -m;
-          else if (m >= p.out_rows - 1 - p.out2_halo && m <= p.out_rows - 2) mm = 2 * (p.out_rows - 1) - m;
-          if (mm != -1) o2mirror = (rb + mm) * p.out_ld + (n0 - p.n_lo + p.out_col0);
+          int mm = 0;
+          bool has = false;
+          if (m >= 1 && m <= p.out2_halo) { mm = -m; has = true; }
+          else if (m >= p.out_rows - 1 - p.out2_halo && m <= p.out_rows - 2) { mm = 2 * (p.out_rows - 1) - m; has = true; }
+          if (has) o2mirror = (rb + mm) * p.out_ld + (n0 - p.n_lo + p.out_col0);
         }
       }
       // stream-K workspace of this (tile, CTA): [128 rows][TN] fp32, and this warp's k-step counter
@@ -1337,7 +1336,10 @@ constexpr int SK_MAX_PAIRS = 96;
 constexpr int64_t SK_CNT_BYTES = 4096;
 constexpr int64_t SK_WS_BYTES = SK_CNT_BYTES + (int64_t)SK_MAX_PAIRS * 2 * 128 * 256 * 4;
 int64_t tapgemm_f_workspace_bytes() { return SK_WS_BYTES; }
-int g_stream_k = [] { const char* e = getenv("SEGAN_B200_STREAMK"); return (e && e[0] == '0') ? 0 : 1; }();
+// SEGAN_B200_STREAMK: 0 = off, n = largest split factor per leftover tile (default 16);
+// SEGAN_B200_SK_ATOMIC: cost of one partial tile's atomics in k-steps (cost model of tapgemm_f_tc_launch)
+int g_stream_k = [] { const char* e = getenv("SEGAN_B200_STREAMK"); return e ? atoi(e) : 16; }();
+double g_sk_atomic_steps = [] { const char* e = getenv("SEGAN_B200_SK_ATOMIC"); return e ? atof(e) : 2.5; }();
 
 int g_cta_pair = 1;   // sg_set_cta_pair(): 0 single-CTA tiles, 1 cta_group::2 pairs, 2 pairs + A reuse across taps (tc3)
 
@@ -1390,7 +1392,7 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     p.dbg = dbg_env;
   }
   p.stats = q->bn_stats;
-  p.sk_dp_tiles = 0x7fffffff; p.sk_ws = nullptr; p.sk_cnt = nullptr;
+  p.sk_dp_tiles = 0x7fffffff; p.sk_split = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   p.out2 = q->out2; p.out2_halo = q->out2_halo; p.slope = q->slope; p.slope_mod = q->slope_mod;
   CUtensorMap tmA0, tmA1, tmW;
   const int a_buf_rows = q->a_rows + 2 * q->a_halo;
@@ -1448,12 +1450,28 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     const int pairs = ((m_tiles_all + 1) / 2) * p.n_tiles * p.ksplit;
     int npairs = num_sms() / 2;
     if (pairs < npairs) npairs = pairs;
-    // stream-K over the last, partial wave (see PieceIter)
-    if (q->sk_ws != nullptr && g_stream_k && p.ksplit == 1 && q->bn_stats == nullptr && npairs <= SK_MAX_PAIRS &&
+    // split-K over the last, partial wave (see PieceIter).  Cost model (times in units of one k-step = 256 rows x
+    // TN x 64 MACs on a pair): leaving the r leftover tiles whole costs `steps`; splitting each S ways costs
+    // steps / S for the MMAs plus the L2 atomics of S * r partial tiles, measured at about SK_ATOMIC_STEPS k-steps
+    // per partial tile (profiles/r2_streamk_sweep.txt).  Short-K layers are left alone.
+    if (q->sk_ws != nullptr && g_stream_k > 1 && p.ksplit == 1 && q->bn_stats == nullptr && npairs <= SK_MAX_PAIRS &&
         pairs > npairs && pairs % npairs != 0) {
-      p.sk_dp_tiles = (pairs / npairs) * npairs;
-      p.sk_cnt = reinterpret_cast<unsigned int*>(q->sk_ws);
-      p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->sk_ws) + SK_CNT_BYTES);
+      const int r = pairs % npairs;
+      int steps = 0;                                  // k-steps of a leftover tile (the last N tile: the longest)
+      for (int d = q->d_lo; d <= q->d_hi; ++d) steps += (q->tap_k_hi[d + 4] - q->tap_k_lo[d + 4]) / 64;
+      int best_s = 1;
+      double best = (double)steps;
+      const int s_max = npairs / r < g_stream_k ? npairs / r : g_stream_k;
+      for (int S = 2; S <= s_max; ++S) {
+        const double c = (double)steps / S + g_sk_atomic_steps * S * r;
+        if (c < best * 0.9) { best = c; best_s = S; }
+      }
+      if (best_s > 1 && steps >= 2 * best_s) {
+        p.sk_dp_tiles = (pairs / npairs) * npairs;
+        p.sk_split = best_s;
+        p.sk_cnt = reinterpret_cast<unsigned int*>(q->sk_ws);
+        p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->sk_ws) + SK_CNT_BYTES);
+      }
     }
     tapgemm_f_tc2<<<2 * npairs, NUM_THREADS, SMEM2_BYTES, st>>>(tmA0, tmA1, tmW, p);
     SG_CHECK_LAUNCH();

@@ -11,6 +11,7 @@ from segan_pytorch_b200._lib import SG_BF16, SG_F16
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 REP = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 COMPARE = sys.argv[3] if len(sys.argv) > 3 else ""
+MODEL_ATOMIC = float(sys.argv[4]) if len(sys.argv) > 4 else 2.5
 dev = "cuda"
 h = lambda *s: (torch.randn(*s, device=dev) * 0.5).half()
 b = lambda *s: (torch.randn(*s, device=dev) * 0.5).bfloat16()
@@ -24,6 +25,11 @@ def timeit(name, fn, flops):
         settings = [("areuse", lambda: lib.sg_set_cta_pair(2)), ("pair", lambda: lib.sg_set_cta_pair(1))]
     elif COMPARE == "splitk":
         settings = [("splitk", lambda: setattr(E, "SPLITK_TAIL", True)), ("plain", lambda: setattr(E, "SPLITK_TAIL", False))]
+    elif COMPARE == "streamk":
+        # split factor of the leftover tiles of the last wave: off, forced 2..37 (cost constant ~0), then the model
+        settings = [("off", lambda: lib.sg_set_stream_k(0, -1.0))] + \
+                   [("S<=%d" % S, (lambda S=S: lib.sg_set_stream_k(S, 1e-6))) for S in (2, 4, 8, 16, 37)] + \
+                   [("model", lambda: lib.sg_set_stream_k(16, MODEL_ATOMIC))]
     elif COMPARE == "compare":
         settings = [("split", lambda: setattr(E, "SPLIT_WAVES", True)), ("unsplit", lambda: setattr(E, "SPLIT_WAVES", False))]
     else:
@@ -41,6 +47,9 @@ def timeit(name, fn, flops):
         e.record()
         torch.cuda.synchronize()
         res.append(s.elapsed_time(e) / REP)
+    if COMPARE == "streamk":
+        print("%-28s %s" % (name, " | ".join("%s %.3f" % (settings[i][0], ms) for i, ms in enumerate(res))))
+        return
     print("%-28s %s" % (name, "   | ".join("%-7s %8.3f ms  %7.1f TFLOP/s" % (settings[i][0], ms, flops / ms / 1e9)
                                           for i, ms in enumerate(res))))
 
@@ -90,6 +99,13 @@ def conv_wgrad(cin, cout, R):
 
 
 if __name__ == "__main__":
+    if COMPARE == "streamk":
+        for fn, args in ((conv_fwd, (64, 128, 1024)), (conv_fwd, (128, 256, 256)), (conv_fwd, (256, 512, 64)),
+                         (conv_fwd, (512, 1024, 16)), (deconv_fwd, (2048, 512, 16)), (deconv_fwd, (1024, 256, 64)),
+                         (deconv_fwd, (512, 128, 256)), (deconv_fwd, (256, 64, 1024)), (conv_dgrad, (512, 1024, 16)),
+                         (conv_dgrad, (256, 512, 64)), (conv_dgrad, (128, 256, 256)), (conv_dgrad, (64, 128, 1024))):
+            fn(*args)
+        sys.exit(0)
     if COMPARE == "areuse3":          # three representative shapes only (timing experiments)
         COMPARE = "areuse"
         conv_fwd(64, 128, 1024)
