@@ -346,8 +346,8 @@ int sg_emit_operands(const float* master, int n_taps, int nc, int kc, const floa
                      void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad, void* stream);
 int sg_alpha_grad(float* dwp, const float* master, int n_taps, int nc, int kc, const float* alpha, int alpha_from,
                   float* dalpha, void* stream);
-int sg_wave_wgrad_fold(const float* dwq, int cin, float* dw, void* stream);
-int sg_last_deconv_wgrad_fold(const float* dwq, int half, const float* w, const float* alpha, float* dw,
+int sg_wave_wgrad_fold(float* dwq /* the blocks read are cleared */, int cin, float* dw, void* stream);
+int sg_last_deconv_wgrad_fold(float* dwq /* the blocks read are cleared */, int half, const float* w, const float* alpha, float* dw,
                               float* dalpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -934,7 +934,7 @@ extern "C" int sg_bn_finalize(const double* stats, int64_t count, int C, const f
 extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, const float* scale_shift,
                           const float* slope, int act, int roll, const int32_t* roll_dev, int out_halo_pos, void* h,
                           void* h_bf16, void* a_bf16, void* stream) {
-  SG_CHECK_ARG(ew_shape_ok(C) && (out_halo_pos == 0 || L >= 32));
+  SG_CHECK_ARG(ew_shape_ok(C) && (out_halo_pos == 0 || L > out_halo_pos));      // reflect padding needs pad < L
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
   const EwVariant v = ew(EW_ACT_FWD);
   EW_DISPATCH(v.vec, v.unroll, (act_fwd_kernel<VEC, UNR><<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(

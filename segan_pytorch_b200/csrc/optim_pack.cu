@@ -266,19 +266,24 @@ alpha_grad_kernel(float* __restrict__ dwp, const float* __restrict__ m, int64_t 
 // Waveform-end layer gradients out of their single-tap GEMM results (both tiny):
 //   first conv (Cin = 1 | 2): dwq[2][64][2][64] (position-pair s x co x pair s' x (ci*32 + k)); the s == s' blocks
 //   are the gradient:  dW[co][ci][k] += dwq[0][co][0][ci*32+k] + dwq[1][co][1][ci*32+k]
-__global__ void wave_wgrad_fold_kernel(const float* __restrict__ dwq, int cin, float* __restrict__ dw) {
+//   (the blocks read are zeroed again: dwq needs no fill before the next weight-gradient GEMM accumulates into it)
+__global__ void wave_wgrad_fold_kernel(float* __restrict__ dwq, int cin, float* __restrict__ dw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * cin * KW) return;
   const int co = i / (cin * KW), rem = i % (cin * KW);
   const int ci = rem / KW, k = rem % KW;
   const int col = ci * 32 + k;
-  const float v = dwq[((0 * 64 + co) * 2 + 0) * 64 + col] + dwq[((1 * 64 + co) * 2 + 1) * 64 + col];
+  float* p0 = dwq + ((0 * 64 + co) * 2 + 0) * 64 + col;
+  float* p1 = dwq + ((1 * 64 + co) * 2 + 1) * 64 + col;
+  const float v = *p0 + *p1;
+  *p0 = 0.f;
+  *p1 = 0.f;
   atomicAdd(dw + i, v);
 }
 //   last deconv (Cout = 1, alpha folded into its effective weight): dwq[2][64][2][2][half] (s, k-slot, source,
 //   s', c); dWeff[src*half + c][k] = dwq[0][k][src][0][c] + dwq[1][k][src][1][c]; dW += dWeff (* alpha for the skip
 //   half), dalpha[c] += sum_k dWeff[half + c][k] * W[half + c][k]
-__global__ void last_deconv_wgrad_fold_kernel(const float* __restrict__ dwq, int half, const float* __restrict__ w,
+__global__ void last_deconv_wgrad_fold_kernel(float* __restrict__ dwq, int half, const float* __restrict__ w,
                                               const float* __restrict__ alpha, float* __restrict__ dw,
                                               float* __restrict__ dalpha) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;       // channel of cat(decoder, skip): [0, 2*half)
@@ -286,8 +291,11 @@ __global__ void last_deconv_wgrad_fold_kernel(const float* __restrict__ dwq, int
   const int src = ch / half, c = ch % half;
   float da = 0.f;
   for (int k = 0; k < KW; ++k) {
-    const float v = dwq[((((int64_t)0 * 64 + k) * 2 + src) * 2 + 0) * half + c] +
-                    dwq[((((int64_t)1 * 64 + k) * 2 + src) * 2 + 1) * half + c];
+    float* p0 = dwq + ((((int64_t)0 * 64 + k) * 2 + src) * 2 + 0) * half + c;
+    float* p1 = dwq + ((((int64_t)1 * 64 + k) * 2 + src) * 2 + 1) * half + c;
+    const float v = *p0 + *p1;
+    *p0 = 0.f;
+    *p1 = 0.f;
     const int64_t wi = (int64_t)ch * KW + k;
     if (src == 1) {
       da = fmaf(v, w[wi], da);
@@ -472,14 +480,14 @@ extern "C" int sg_alpha_grad(float* dwp, const float* master, int n_taps, int nc
   return SG_OK;
 }
 
-extern "C" int sg_wave_wgrad_fold(const float* dwq, int cin, float* dw, void* stream) {
+extern "C" int sg_wave_wgrad_fold(float* dwq, int cin, float* dw, void* stream) {
   SG_CHECK_ARG(dwq && dw && (cin == 1 || cin == 2));
   wave_wgrad_fold_kernel<<<(64 * cin * KW + 255) / 256, 256, 0, ST>>>(dwq, cin, dw);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
 
-extern "C" int sg_last_deconv_wgrad_fold(const float* dwq, int half, const float* w, const float* alpha, float* dw,
+extern "C" int sg_last_deconv_wgrad_fold(float* dwq, int half, const float* w, const float* alpha, float* dw,
                                          float* dalpha, void* stream) {
   SG_CHECK_ARG(dwq && w && alpha && dw && half > 0);
   last_deconv_wgrad_fold_kernel<<<(2 * half + 127) / 128, 128, 0, ST>>>(dwq, half, w, alpha, dw, dalpha);

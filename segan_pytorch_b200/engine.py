@@ -476,40 +476,81 @@ def grad_twins():
     return GS == SG_BF16
 
 
-def flatten_params(module):
-    """Re-points every parameter of `module` at a slice of one flat fp32 buffer (and the same for
-    gradients) so that the optimiser, the NCCL all-reduce and the weight-gradient kernels see one
-    contiguous bucket.  Safe to call again after .to(device)."""
-    params = [p for _, p in module.named_parameters()]
-    if not params:
-        return None, None, {}
-    dev = params[0].device
-    total = sum(p.numel() for p in params)
-    flat = torch.empty(total, dtype=torch.float32, device=dev)
-    grad = torch.zeros(total, dtype=torch.float32, device=dev)
-    off = 0
-    index = {}
-    for name, p in module.named_parameters():
-        n = p.numel()
-        flat[off:off + n].copy_(p.data.reshape(-1))
-        p.data = flat[off:off + n].view(p.shape)
-        p.grad = None
-        index[name] = (off, n, tuple(p.shape))
-        off += n
-    return flat, grad, index
+class PackedLayer(object):
+    """One tap-GEMM layer whose fp32 master, optimiser state and gradient live in the layout of its forward
+    operand, M[T][nc][kc] (include/segan_b200.h "Packed-master path").
+      kind 0: Conv1d W[cout][cin][31]          -> M[9][cout][4cin]
+      kind 1: ConvTranspose1d W[cin][cout][31] -> M[9][4cout][cin]   (alpha: GSkip scale of the columns >= alpha_from)
+      kind 2: Linear W[nout][C*T]              -> M[1][nout][T*C]"""
+
+    def __init__(self, name, kind, c_out, c_in, t_len, f_key, dg_key, alpha_name=None):
+        self.name, self.kind, self.c_out, self.c_in, self.t_len = name, kind, c_out, c_in, t_len
+        self.f_key, self.dg_key, self.alpha_name = f_key, dg_key, alpha_name
+        if kind == 0:
+            self.T, self.nc, self.kc = 9, c_out, 4 * c_in
+        elif kind == 1:
+            self.T, self.nc, self.kc = 9, 4 * c_out, c_in
+        else:
+            self.T, self.nc, self.kc = 1, c_out, c_in * t_len
+        self.alpha_from = c_in // 2 if alpha_name is not None else 0
+        self.numel = self.T * self.nc * self.kc
+        self.off = 0
+
+
+def pack_reference(kind, w, c_out, c_in, t_len):
+    """Reference layout -> packed master layout M[T][nc][kc], as tensor algebra (host-side twin of sg_pack_weights:
+    used for CPU-resident modules -- optimiser state dicts, checkpoints -- and as the kernels' cross-check)."""
+    if kind == 0:        # M[d+4][co][p*Cin+ci] = W[co][ci][4d+p+14]
+        wp = torch.nn.functional.pad(w.reshape(c_out, c_in, KW), (2, 3))
+        return wp.view(c_out, c_in, 9, 4).permute(2, 0, 3, 1).reshape(9, c_out, 4 * c_in).contiguous()
+    if kind == 1:        # M[d+4][r*Cout+co][ci] = W[ci][co][-4d+r+13]
+        wp = torch.nn.functional.pad(w.reshape(c_in, c_out, KW), (3, 2))
+        return wp.view(c_in, c_out, 9, 4).flip(2).permute(2, 3, 1, 0).reshape(9, 4 * c_out, c_in).contiguous()
+    return w.reshape(c_out, c_in, t_len).permute(0, 2, 1).reshape(1, c_out, t_len * c_in).contiguous()
+
+
+def unpack_reference(kind, m, c_out, c_in, t_len):
+    """Inverse of pack_reference (host-side twin of sg_unpack_wgrad without alpha)."""
+    if kind == 0:
+        return m.reshape(9, c_out, 4, c_in).permute(1, 3, 0, 2).reshape(c_out, c_in, 36)[..., 2:2 + KW].contiguous()
+    if kind == 1:
+        return m.reshape(9, 4, c_out, c_in).permute(3, 2, 0, 1).flip(2).reshape(c_in, c_out, 36)[..., 3:3 + KW].contiguous()
+    return m.reshape(c_out, t_len, c_in).permute(0, 2, 1).reshape(c_out, c_in * t_len).contiguous()
+
+
+# Gradient buckets are cleared by the optimiser kernels as they read them (sg_rmsprop_step clear_grad): a step
+# needs no fill launches.  KEEP_GRADS = True (tests, inspection) leaves the gradients in place after a step; the
+# next backward then zeroes the bucket itself.
+KEEP_GRADS = os.environ.get("SEGAN_B200_KEEP_GRADS", "0").lower() not in ("0", "off", "no", "false")
 
 
 class _NetEngine:
-    """Shared machinery: flat parameter / gradient buckets and lazily re-packed 16-bit weights."""
+    """Shared machinery: ONE fp32 bucket per network holding the packed masters of the tap-GEMM layers followed by
+    every other ("small") parameter in reference layout, a gradient bucket of the same layout (the NCCL buffer),
+    and the lazily re-emitted 16-bit operands.
+
+    The nn.Parameters of the module keep the reference's names and shapes: small parameters ARE views into the
+    bucket; the big weights are reference-layout MIRRORS that are refreshed from the packed master only when
+    somebody looks (state_dict(), checkpoints, .to(), grad_of()) and imported into the master when somebody wrote
+    them (load_state_dict, init functions: detected through the tensors' version counters)."""
 
     def __init__(self, module):
         self.module = module
-        self.flat = None
+        self.flat = None            # packed masters | small parameters
         self.grad = None
-        self.index = {}
+        self.index = {}             # small parameter name -> (offset, numel, shape) in the bucket
+        self.layers = []            # PackedLayer descriptors (offsets into the bucket)
+        self.by_name = {}
         self.buf = _Buffers()
-        self._packed_version = None
         self.backend = None
+        self._mirror_stale = False  # the packed masters are newer than the reference-layout mirrors
+        self._ops_stale = True      # the 16-bit operands are older than the masters / small parameters
+        self._seen = None           # version counters of the module's parameters at the last look
+        self._grad_dirty = False    # the gradient bucket holds something
+        self._alpha_fixed = False   # sg_alpha_grad has been applied to the current gradients
+
+    def packed_layers(self):
+        raise NotImplementedError
 
     # -- parameters -------------------------------------------------------------------------
     def bind(self):
@@ -518,42 +559,183 @@ class _NetEngine:
         ok = self.flat is not None and self.flat.device == dev
         if ok:
             for name, p in ps:
-                off, n, _ = self.index[name]
-                if p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                ent = self.index.get(name)
+                if ent is not None and p.data_ptr() != self.flat.data_ptr() + 4 * ent[0]:
+                    ok = False
+                    break
+                if ent is None and (p.device != dev or self._mirror_ptr.get(name) != p.data_ptr()):
                     ok = False
                     break
         if not ok:
-            self.flat, self.grad, self.index = flatten_params(self.module)
-            self._packed_version = None
+            self._build(ps, dev)
         return self
 
+    def _build(self, ps, dev):
+        """(Re)creates the buckets from the module's parameters (first use, or after .to(device))."""
+        self.layers = self.packed_layers()
+        self.by_name = {l.name: l for l in self.layers}
+        off = 0
+        for l in self.layers:
+            l.off = off
+            off += l.numel
+        self.index = {}
+        for name, p in ps:
+            if name not in self.by_name:
+                self.index[name] = (off, p.numel(), tuple(p.shape))
+                off += (p.numel() + 3) // 4 * 4                  # 16-byte aligned views
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self._mirror_ptr = {}
+        for name, p in ps:
+            p.grad = None
+            if name in self.by_name:
+                p.data = p.data.contiguous().float()
+                self._mirror_ptr[name] = p.data_ptr()
+            else:
+                o, n, shape = self.index[name]
+                self.flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + n].view(shape)
+        for l in self.layers:
+            self._import(l)
+        self._mirror_stale, self._ops_stale = False, True
+        self._grad_dirty, self._alpha_fixed = False, False
+        self._seen = self._versions()
+
+    def _versions(self):
+        return tuple(p._version for _, p in self.module.named_parameters())
+
+    def mview(self, l):
+        """Packed master of layer `l` (fp32 [T][nc][kc])."""
+        return self.flat[l.off:l.off + l.numel]
+
+    def mgrad(self, l):
+        return self.grad[l.off:l.off + l.numel]
+
+    def _param(self, name):
+        return dict(self.module.named_parameters())[name]
+
+    def _import(self, l, src=None, dst=None):
+        """reference layout -> packed (master by default)."""
+        src = self._param(l.name).data if src is None else src
+        dst = self.mview(l) if dst is None else dst
+        if not dst.is_cuda:
+            dst.copy_(pack_reference(l.kind, src.float(), l.c_out, l.c_in, l.t_len).reshape(-1))
+            return
+        _lib.call("sg_pack_weights", l.kind, _p(src), l.c_out, l.c_in, l.t_len, None, 0, _p(dst), None, SG_F32, SG_F32,
+                  _stream())
+
+    def _export(self, l, src, dst):
+        """packed -> reference layout (pure layout transform)."""
+        if not src.is_cuda:
+            dst.copy_(unpack_reference(l.kind, src, l.c_out, l.c_in, l.t_len).reshape(dst.shape))
+            return
+        _lib.call("sg_unpack_wgrad", l.kind, _p(src), l.c_out, l.c_in, l.t_len, None, None, 0, _p(dst), None, 0, _stream())
+
+    def notice_external_writes(self):
+        """Parameters written through torch since the last look (load_state_dict, init functions, p.data.copy_):
+        big weights are imported into their packed master, everything marks the operands stale."""
+        v = self._versions()
+        if v == self._seen:
+            return
+        for (name, p), new, old in zip(self.module.named_parameters(), v, self._seen):
+            if new != old:
+                self._ops_stale = True
+                if name in self.by_name:
+                    self._import(self.by_name[name])
+        self._seen = v
+
+    def sync_to_reference(self):
+        """Refreshes the reference-layout mirrors of the big weights from the packed masters (no-op when nothing
+        changed).  Called by state_dict() / save / .to() / grad_of()."""
+        if self.flat is None:
+            return
+        self.notice_external_writes()
+        if self._mirror_stale:
+            for l in self.layers:
+                self._export(l, self.mview(l), self._param(l.name).data)
+            self._mirror_stale = False
+
     def pview(self, name):
-        off, n, shape = self.index[name]
-        return self.flat[off:off + n].view(shape)
+        """Current value of a parameter: bucket view (small parameters) or the reference-layout mirror."""
+        ent = self.index.get(name)
+        if ent is not None:
+            off, n, shape = ent
+            return self.flat[off:off + n].view(shape)
+        return self._param(name).data
 
     def gview(self, name):
+        """Gradient slot of a SMALL parameter (bucket view, carries LOSS_SCALE)."""
         off, n, shape = self.index[name]
         return self.grad[off:off + n].view(shape)
 
-    def _version(self):
-        return tuple(p._version for _, p in self.module.named_parameters()) + (self.flat.data_ptr(),)
+    def master_updated(self):
+        """An optimiser step changed the bucket in place."""
+        self._mirror_stale = True
+        self._ops_stale = True
 
     def mark_dirty(self):
-        self._packed_version = None
+        self._ops_stale = True
 
+    # -- gradients --------------------------------------------------------------------------
+    def zero_grad(self):
+        if self._grad_dirty:
+            self.grad.zero_()
+        self._grad_dirty, self._alpha_fixed = False, False
+
+    def finish_grads(self):
+        """Hook between the (all-reduced) raw gradients and the optimiser: the decoder's alpha-scaled layers turn
+        their dWeff into dW and produce the alpha gradients (linear in the gradients: safe after the all-reduce)."""
+        self._alpha_fixed = True
+
+    def grads_consumed(self, cleared):
+        if cleared:
+            self._grad_dirty, self._alpha_fixed = False, False
+
+    def grad_of(self, name):
+        """Gradient of parameter `name` in true units and reference layout (tests, autograd API)."""
+        if not self._alpha_fixed:
+            self.finish_grads()
+        l = self.by_name.get(name)
+        if l is None:
+            return self.gview(name) * (1.0 / LOSS_SCALE)
+        out = torch.empty_like(self._param(name).data)
+        self._export(l, self.mgrad(l), out)
+        return out.mul_(1.0 / LOSS_SCALE)
+
+    def export_grads(self):
+        """Copies the gradients into per-parameter .grad tensors (API compatibility)."""
+        for name, p in self.module.named_parameters():
+            if p.requires_grad:
+                g = self.grad_of(name)
+                if p.grad is None:
+                    p.grad = g
+                else:
+                    p.grad.copy_(g)
+
+    # -- 16-bit operands ----------------------------------------------------------------------
     def ensure_packed(self):
-        """Re-packs the 16-bit operands when the master weights changed.  With overlap on, the pack kernels go
-        to side stream 4 and record one event per operand: the forward that triggered the pack waits for
-        each layer's event right before that layer's tap-GEMM (`wait_packed`), so the 0.25-0.45 ms of packing
-        hides behind the first layers instead of preceding them on the critical chain."""
+        """Re-emits the 16-bit operands when the masters changed.  With overlap on, the kernels go to side
+        stream 4 and record one event per operand: the forward that triggered them waits for each layer's event
+        right before that layer's tap-GEMM (`wait_packed`), so the emission hides behind the first layers
+        instead of preceding them on the critical chain."""
         self.bind()
-        v = self._version()
-        if v != self._packed_version:
+        self.notice_external_writes()
+        if self._ops_stale:
             self.pack_ev = {}
             self._pack_side = side_stream(self.flat.device, 4)
             with on_side(self._pack_side):
                 self.pack()
-            self._packed_version = self._version()
+            self._ops_stale = False
+
+    def emit(self, l, alpha=None):
+        """Forward + data-gradient operand of packed layer `l` out of its master."""
+        dev = self.flat.device
+        wf = self.buf.get(l.f_key, (l.T, l.nc, l.kc), F16, dev)
+        wd = self.buf.get(l.dg_key, (l.T, l.kc, l.nc), GT, dev)
+        _lib.call("sg_emit_operands", _p(self.mview(l)), l.T, l.nc, l.kc, _p(alpha), l.alpha_from, _p(wf), _p(wd),
+                  SG_F16, GS, _stream())
+        self.packed[l.f_key], self.packed[l.dg_key] = wf, wd
+        self._mark_packed(l.f_key)
 
     def _mark_packed(self, *keys):
         if getattr(self, "_pack_side", None) is not None:
@@ -574,20 +756,6 @@ class _NetEngine:
             self._pack_side = None
         self.pack_ev = {}
 
-    def grad_of(self, name):
-        """Gradient of parameter `name` in true units (the bucket carries LOSS_SCALE)."""
-        return self.gview(name) * (1.0 / LOSS_SCALE)
-
-    def export_grads(self):
-        """Copies the flat gradient bucket into per-parameter .grad tensors (API compatibility)."""
-        for name, p in self.module.named_parameters():
-            if p.requires_grad:
-                g = self.grad_of(name)
-                if p.grad is None:
-                    p.grad = g
-                else:
-                    p.grad.copy_(g)
-
 
 # ============================================================================================
 # Generator
@@ -602,10 +770,18 @@ class GeneratorEngine(_NetEngine):
         self.packed = {}
 
     # -- weights ----------------------------------------------------------------------------
+    def packed_layers(self):
+        fm, nl = self.fmaps, self.nl
+        ls = [PackedLayer("enc_blocks.%d.conv.weight" % l, 0, fm[l], fm[l - 1], 0, "Wf%d" % l, "Wdg%d" % l)
+              for l in range(1, nl)]
+        for l in range(nl - 1):
+            ls.append(PackedLayer("dec_blocks.%d.deconv.weight" % l, 1, self.dec_cout(l), self.dec_cin(l), 0,
+                                  "Wt%d" % l, "Wtd%d" % l,
+                                  alpha_name=("alpha_%d.skip_k" % (nl - 1 - l)) if l > 0 else None))
+        return ls
+
     def pack(self):
         dev = self.flat.device
-        fm = self.fmaps
-        st = _stream()
         # last decoder layer (Cout = 1): fp32 [cin][31] with alpha folded (tiny: torch ops)
         l = self.nl - 1
         w = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
@@ -624,25 +800,19 @@ class GeneratorEngine(_NetEngine):
         wg[:, :KW] = weff
         self.packed["Wg_last"] = wg.to(GT).contiguous()
         self._mark_packed("small")
-        for l in range(1, self.nl):
-            cin, cout = fm[l - 1], fm[l]
-            wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
-            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), GT, dev)
-            _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
-                      None, 0, _p(wf), _p(wd), SG_F16, GS, st)
-            self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
-            self._mark_packed("Wf%d" % l)
-        for l in range(self.nl - 1):
-            cin = self.dec_cin(l)
-            cout = self.dec_cout(l)
-            w = self.pview("dec_blocks.%d.deconv.weight" % l)
-            alpha = self.alpha_for_dec(l)
-            wt = self.buf.get("Wt%d" % l, (9, 4 * cout, cin), F16, dev)
-            wtd = self.buf.get("Wtd%d" % l, (9, cin, 4 * cout), GT, dev)
-            _lib.call("sg_pack_weights", 1, _p(w), cout, cin, 0, _p(alpha), cin // 2,
-                      _p(wt), _p(wtd), SG_F16, GS, st)
-            self.packed["Wt%d" % l], self.packed["Wtd%d" % l] = wt, wtd
-            self._mark_packed("Wt%d" % l)
+        for pl in self.layers:
+            self.emit(pl, self.pview(pl.alpha_name).reshape(-1) if pl.alpha_name else None)
+
+    def finish_grads(self):
+        if self._alpha_fixed:
+            return
+        for pl in self.layers:
+            if pl.alpha_name is not None:
+                trainable = self._param(pl.alpha_name).requires_grad
+                _lib.call("sg_alpha_grad", _p(self.mgrad(pl)), _p(self.mview(pl)), pl.T, pl.nc, pl.kc,
+                          _p(self.pview(pl.alpha_name).reshape(-1)), pl.alpha_from,
+                          _p(self.gview(pl.alpha_name).view(-1)) if trainable else None, _stream())
+        self._alpha_fixed = True
 
     def dec_cin(self, l):
         return 2 * self.fmaps[-1] if l == 0 else 2 * self.fmaps[self.nl - 1 - l]
@@ -823,8 +993,9 @@ class GeneratorEngine(_NetEngine):
         dev = gy.device
         gy = gy.contiguous().float()
         if not accumulate:
-            self.grad.zero_()
-        side = side_stream(dev, 0)       # weight-gradient chain (wgrad GEMM + unpack) of every layer
+            self.zero_grad()
+        self._grad_dirty = True
+        side = side_stream(dev, 0)       # weight-gradient tap-GEMM of every layer (writes the packed gradient bucket)
         red_dec = stat_arena(buf, "g.red_dec", [(SL, 3, self.dec_cout(l)) for l in range(nl - 1)], dev)
         red_enc = stat_arena(buf, "g.red_enc", [(SL, 3, fm[l]) for l in range(nl)], dev)
         # ---- last decoder block (tanh, Cout = 1)
@@ -834,7 +1005,6 @@ class GeneratorEngine(_NetEngine):
         half = cin // 2
         g_in = buf.get("g.gin%d" % l, (B, lin, cin), GT, dev)
         gpre = buf.get("g.gpre", (B, L), F32, dev)
-        dweff = buf.get("g.dweff", (cin, KW), F32, dev, zero=True)
         gb = self.gview("dec_blocks.%d.deconv.bias" % l)
         src0 = dd[l - 1]
         src1 = a[0]
@@ -845,23 +1015,27 @@ class GeneratorEngine(_NetEngine):
                       _p(colg) if GS != SG_F16 else None, st)
             run_f(colg, None, lin, 0, GS, self.packed["Wg_last"], GS, 64, cin, tap_ranges("full", 0, 64, cin),
                   g_in, GS, lin, 0, 0, lin, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
-            # dW'[n=(s,k)][kc=(src,s',c)] over position pairs; the s == s' blocks are the gradient
+            # dW'[n=(s,k)][kc=(src,s',c)] over position pairs; the s == s' blocks are the gradient: folded (and
+            # cleared for the next step) by sg_last_deconv_wgrad_fold into dW (alpha on the skip half) and dalpha
             dwq = buf.get("g.dwq_last", (128 * 2 * cin,), F32, dev)
-            dwq.zero_()
-            run_w(colg, lin // 2, GS, ctx["ddb"][l - 1], ctx["ab"][0], lin // 2, 0, GS, 2 * cin, 128,
-                  tap_ranges("full", 0, 2 * cin, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=74,
-                  a0_c=cin, a1_c=cin, backend=self.backend)
-            t5 = dwq.view(2, 64, 2, 2, half)
-            dweff.copy_((t5[0, :, :, 0, :] + t5[1, :, :, 1, :]).permute(1, 2, 0).reshape(cin, 64)[:, :KW])
+            a_train = self._param("alpha_0.skip_k").requires_grad
+            with on_side(side):
+                run_w(colg, lin // 2, GS, ctx["ddb"][l - 1], ctx["ab"][0], lin // 2, 0, GS, 2 * cin, 128,
+                      tap_ranges("full", 0, 2 * cin, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=74,
+                      a0_c=cin, a1_c=cin, backend=self.backend)
+                _lib.call("sg_last_deconv_wgrad_fold", _p(dwq), half, _p(self.pview("dec_blocks.%d.deconv.weight" % l)),
+                          _p(self.alpha_for_dec(l)), _p(self.gview("dec_blocks.%d.deconv.weight" % l)),
+                          _p(self.gview("alpha_0.skip_k").view(-1)) if a_train else None, _stream())
         else:
+            dweff = buf.get("g.dweff", (cin, KW), F32, dev, zero=True)
             _lib.call("sg_wave_deconv_bwd", _p(src0), half, _p(src1), half, B, lin, _p(self.packed["w_last_eff"]),
                       _p(gy), _p(ctx["y"]), _p(gpre), _p(g_in), _p(dweff), _p(gb), st)
-        w_last = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
-        alpha = self.alpha_for_dec(l)
-        gw = self.gview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
-        gw[:half] += dweff[:half]
-        gw[half:] += dweff[half:] * alpha.view(-1, 1)
-        self.gview("alpha_0.skip_k").view(-1).add_((dweff[half:] * w_last[half:]).sum(1))
+            w_last = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
+            alpha = self.alpha_for_dec(l)
+            gw = self.gview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
+            gw[:half] += dweff[:half]
+            gw[half:] += dweff[half:] * alpha.view(-1, 1)
+            self.gview("alpha_0.skip_k").view(-1).add_((dweff[half:] * w_last[half:]).sum(1))
         # ---- decoder blocks nl-2 .. 0
         g_next = g_in            # gradient w.r.t. cat(dd[l-1], alpha*a_skip) of block l
         for l in range(nl - 2, -1, -1):
@@ -881,18 +1055,12 @@ class GeneratorEngine(_NetEngine):
                 s0, s1 = ctx["ddb"][l - 1], ctx["ab"][nl - 1 - l]
             c0, c1 = s0.shape[-1], s1.shape[-1]
             taps = tap_ranges("deconv_fwd", cout, cin, 4 * cout)
-            dwp = buf.get("g.dwpd%d" % l, (9 * 4 * cout * cin,), F32, dev)
+            dwp = self.mgrad(self.by_name["dec_blocks.%d.deconv.weight" % l])     # packed gradient slot (dWeff)
             with on_side(side):
-                dwp.zero_()
                 n_tiles = 9 * (4 * cout // 128) * max(1, cin // 256)
                 run_w(g_ad, lin, GS, s0, s1, lin, 0, GS, cin, 4 * cout, taps, dwp, B,
                       ksplit=wgrad_ksplit(B * lin, n_tiles, taps, cin, 4 * cout), a0_c=c0, a1_c=c1,
                       backend=self.backend)
-                alpha = self.alpha_for_dec(l)
-                galpha = self.gview("alpha_%d.skip_k" % (nl - 1 - l)).view(-1) if l > 0 else None
-                _lib.call("sg_unpack_wgrad", 1, _p(dwp), cout, cin, 0,
-                          _p(self.pview("dec_blocks.%d.deconv.weight" % l)), _p(alpha), cin // 2,
-                          _p(self.gview("dec_blocks.%d.deconv.weight" % l)), _p(galpha), 1, _stream())
             # data gradient w.r.t. cat(s0, s1); block 0 only needs the encoder half (z gets no gradient)
             g_in = buf.get("g.gin%d" % l, (B, lin, cin), GT, dev)
             run_f(g_ad, None, lin, 0, GS, self.packed["Wtd%d" % l], GS, 4 * cout, cin,
@@ -922,27 +1090,21 @@ class GeneratorEngine(_NetEngine):
                 dwq = buf.get("g.dwq0", (128 * 128,), F32, dev)
                 with on_side(side):
                     if ctx.get("colb") is not None:
-                        dwq.zero_()
                         run_w(g_a, Lq[0] // 2, GS, ctx["colb"], None, Lq[0] // 2, 0, GS, 128, 128,
                               tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
                               backend=self.backend)
-                        t4 = dwq.view(2, 64, 2, 64)
-                        self.gview("enc_blocks.0.conv.weight").add_(
-                            (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :1, :KW])
+                        _lib.call("sg_wave_wgrad_fold", _p(dwq), 1, _p(self.gview("enc_blocks.0.conv.weight")), _stream())
                     else:
                         _lib.call("sg_wave_conv_wgrad", _p(ctx["x"]), None, 1, B, L, 0, _p(g_a), cout,
                                   _p(self.gview("enc_blocks.0.conv.weight")), None, _stream())
                 break
             cin = fm[l - 1]
             taps = tap_ranges("conv_fwd", cin, 4 * cin, cout)
-            dwp_l = buf.get("g.dwpe%d" % l, (9 * cout * 4 * cin,), F32, dev)
+            dwp_l = self.mgrad(self.by_name["enc_blocks.%d.conv.weight" % l])
             with on_side(side):
-                dwp_l.zero_()
                 n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
                 run_w(g_a, Lq[l], GS, ctx["hpb"][l - 1], None, Lq[l], 4, GS, 4 * cin, cout, taps, dwp_l, B,
                       ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps, 4 * cin, cout), backend=self.backend)
-                _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
-                          _p(self.gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
             g_hp = buf.get("g.ghp%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), GT, dev)
             run_f(g_a, None, Lq[l], 0, GS, self.packed["Wdg%d" % l], GS, cout, 4 * cin,
                   tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_hp, GS, Lq[l], 4, -4, Lq[l] + 4, B,
@@ -962,48 +1124,30 @@ class DiscriminatorEngine(_NetEngine):
         self.packed = {}
         self.eps = 1e-5
         self.momentum = 0.1
-        # lane 1: a second workspace + gradient bucket so that one pass (the real pair of a train step)
-        # can run on its own stream concurrently with another pass of the same network
+        # lane 1: a second workspace so that one pass (the real pair of a train step) can run on its own stream
+        # concurrently with another pass of the same network.  Both lanes accumulate into the SAME gradient
+        # bucket: every parameter-gradient writer is atomic (red.add in the wgrad epilogue, atomicAdd elsewhere).
         self.buf1 = _Buffers()
-        self.grad1 = None
 
-    def lane_grad(self, lane):
-        """Flat gradient bucket of `lane` (lane 1's is allocated on first use and starts zeroed)."""
-        if lane == 0:
-            return self.grad
-        if self.grad1 is None or self.grad1.shape != self.grad.shape or self.grad1.device != self.grad.device:
-            self.grad1 = torch.zeros_like(self.grad)
-        return self.grad1
-
-    def merge_lane_grads(self):
-        """grad += grad1 ; grad1 = 0 (after both lanes' passes have been joined)."""
-        if self.grad1 is not None:
-            self.grad.add_(self.grad1)
-            self.grad1.zero_()
+    def packed_layers(self):
+        fm = self.fmaps
+        ls = [PackedLayer("enc_blocks.%d.conv.weight" % l, 0, fm[l], fm[l - 1], 0, "Wf%d" % l, "Wdg%d" % l)
+              for l in range(1, self.nl)]
+        nout, kin = self._param("fc.0.weight").shape
+        ls.append(PackedLayer("fc.0.weight", 2, nout, fm[-1], kin // fm[-1], "W1p", "W1dg"))
+        return ls
 
     def pack(self):
-        dev, fm, st = self.flat.device, self.fmaps, _stream()
+        dev = self.flat.device
         wcol = wave_col_weights(self.pview("enc_blocks.0.conv.weight"), dev)
         self.packed["Wcol0"] = wcol.half().contiguous()
         self.packed["WcolT0"] = wcol.t().to(GT).contiguous()
         self._mark_packed("small")
-        for l in range(1, self.nl):
-            cin, cout = fm[l - 1], fm[l]
-            wf = self.buf.get("Wf%d" % l, (9, cout, 4 * cin), F16, dev)
-            wd = self.buf.get("Wdg%d" % l, (9, 4 * cin, cout), GT, dev)
-            _lib.call("sg_pack_weights", 0, _p(self.pview("enc_blocks.%d.conv.weight" % l)), cout, cin, 0,
-                      None, 0, _p(wf), _p(wd), SG_F16, GS, st)
-            self.packed["Wf%d" % l], self.packed["Wdg%d" % l] = wf, wd
-            self._mark_packed("Wf%d" % l)
-        w1 = self.pview("fc.0.weight")
-        nout, kin = w1.shape
-        C_ = fm[-1]
-        T = kin // C_
-        w1p = self.buf.get("W1p", (nout, kin), F16, dev)
-        w1d = self.buf.get("W1dg", (kin, nout), GT, dev)
-        _lib.call("sg_pack_weights", 2, _p(w1), nout, C_, T, None, 0, _p(w1p), _p(w1d), SG_F16, GS, st)
-        self.packed["W1p"], self.packed["W1dg"] = w1p, w1d
-        self._mark_packed("W1p")
+        for pl in self.layers:
+            self.emit(pl)
+            if pl.kind == 2:       # the Linear's operands are used as 2-D [nout][kin] / [kin][nout]
+                self.packed["W1p"] = self.packed["W1p"].view(pl.nc, pl.kc)
+                self.packed["W1dg"] = self.packed["W1dg"].view(pl.kc, pl.nc)
 
     def forward(self, x0, x1, shifts, training=True, fresh=False, twins=True, lane=0, shifts_dev=None):
         """x0: candidate (B,1,L), x1: reference/noisy (B,1,L) -- the reference's cat((x_, ref), 1)
@@ -1117,11 +1261,10 @@ class DiscriminatorEngine(_NetEngine):
         def rptr(i):
             return None if shifts_dev is None else C.c_void_p(shifts_dev.data_ptr() + 4 * i)
         fm, nl, st, buf = self.fmaps, self.nl, _stream(), (self.buf1 if lane == 1 else self.buf)
-        grad_flat = self.lane_grad(lane) if param_grads else None
-
-        def gview(name):
-            off, n, shape = self.index[name]
-            return grad_flat[off:off + n].view(shape)
+        grad_flat = self.grad if param_grads else None
+        if param_grads:
+            self._grad_dirty = True
+        gview = self.gview
         B, L, Lq = ctx["B"], ctx["L"], ctx["Lq"]
         a, hp, ss, mi, shifts = ctx["a"], ctx["hp"], ctx["ss"], ctx["mi"], ctx["shifts"]
         dev = ctx["x0"].device
@@ -1139,13 +1282,10 @@ class DiscriminatorEngine(_NetEngine):
         # data-gradient chain (dgrad GEMM -> BatchNorm/PReLU backward) on the caller's stream
         side = side_stream(dev, 3 if lane == 1 else 0) if param_grads else None
         if param_grads:
-            dw1 = buf.get("d.dwpfc", (256 * kin,), F32, dev)
+            dw1 = self.mgrad(self.by_name["fc.0.weight"])
             with on_side(side):
-                dw1.zero_()
                 run_w(g_z1, 1, GS, ctx["hpb"][-1], None, 1, 0, GS, kin, 256, tap_ranges("full", 0, kin, 256),
                       dw1, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
-                _lib.call("sg_unpack_wgrad", 2, _p(dw1), 256, fm[-1], Lq[-1], None, None, 0,
-                          _p(gview("fc.0.weight")), None, 1, _stream())
         g_h = buf.get("d.gh%d" % (nl - 1), (B, Lq[-1], fm[-1]), GT, dev)
         run_f(g_z1, None, 1, 0, GS, self.packed["W1dg"], GS, 256, kin, tap_ranges("full", 0, 256, kin),
               g_h, GS, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
@@ -1178,13 +1318,10 @@ class DiscriminatorEngine(_NetEngine):
                 if param_grads and ctx.get("colb") is not None:
                     dwq = buf.get("d.dwq0", (128 * 128,), F32, dev)
                     with on_side(side):
-                        dwq.zero_()
                         run_w(g_a, Lq[0] // 2, GS, ctx["colb"], None, Lq[0] // 2, 0, GS, 128, 128,
                               tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
                               backend=self.backend)
-                        t4 = dwq.view(2, 64, 2, 64)
-                        gview("enc_blocks.0.conv.weight").add_(
-                            (t4[0, :, 0, :] + t4[1, :, 1, :]).view(64, 2, 32)[:, :, :KW])
+                        _lib.call("sg_wave_wgrad_fold", _p(dwq), 2, _p(gview("enc_blocks.0.conv.weight")), _stream())
                 elif param_grads:
                     with on_side(side):
                         _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a),
@@ -1207,15 +1344,12 @@ class DiscriminatorEngine(_NetEngine):
                 break
             cin = fm[l - 1]
             if param_grads:
-                dwp_l = buf.get("d.dwp%d" % l, (9 * cout * 4 * cin,), F32, dev)
+                dwp_l = self.mgrad(self.by_name["enc_blocks.%d.conv.weight" % l])
                 with on_side(side):
-                    dwp_l.zero_()
                     n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
                     taps_w = tap_ranges("conv_fwd", cin, 4 * cin, cout)
                     run_w(g_a, Lq[l], GS, ctx["hpb"][l - 1], None, Lq[l], 4, GS, 4 * cin, cout, taps_w, dwp_l, B,
                           ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps_w, 4 * cin, cout), backend=self.backend)
-                    _lib.call("sg_unpack_wgrad", 0, _p(dwp_l), cout, cin, 0, None, None, 0,
-                              _p(gview("enc_blocks.%d.conv.weight" % l)), None, 1, _stream())
             g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), GT, dev)
             run_f(g_a, None, Lq[l], 0, GS, self.packed["Wdg%d" % l], GS, cout, 4 * cin,
                   tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_h, GS, Lq[l], 4, -4, Lq[l] + 4, B,

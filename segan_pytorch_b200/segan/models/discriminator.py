@@ -48,6 +48,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             g0 = torch.zeros(B, 1, L, dtype=torch.float32, device=g_logit.device)
             g1 = torch.zeros(B, 1, L, dtype=torch.float32, device=g_logit.device)
         eng.grad.zero_()
+        eng._alpha_fixed = False
         eng.backward(ectx, 0.0, 1.0, param_grads=True, input_grad=g0, input_grad1=g1,
                      g_logit=g_logit.contiguous().float().view(-1))
         inv = 1.0 / _engine.LOSS_SCALE            # the engine's gradients carry the fp16 loss scale
@@ -55,7 +56,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             gx = torch.cat((g0, g1), dim=1) * inv
         grads = []
         for n, p in eng.module.named_parameters():
-            grads.append(eng.gview(n) * inv if p.requires_grad else None)
+            grads.append(eng.grad_of(n) if p.requires_grad else None)      # reference layout, true units
         return (None, gx, None, None) + tuple(grads)
 
 
@@ -105,6 +106,18 @@ class Discriminator(Model):
         if self._engine is None:
             self._engine = _engine.DiscriminatorEngine(self)
         return self._engine
+
+    # The big weights' nn.Parameters are reference-layout mirrors of the engine's packed fp32 masters: anything that
+    # reads or moves the parameters wholesale first refreshes them (a no-op unless an optimiser step intervened).
+    def state_dict(self, *args, **kwargs):
+        if self._engine is not None:
+            self._engine.sync_to_reference()
+        return super().state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        if getattr(self, '_engine', None) is not None:
+            self._engine.sync_to_reference()
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, x, shifts=None):
         eng = self.engine

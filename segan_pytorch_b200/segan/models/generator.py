@@ -59,7 +59,7 @@ class _GeneratorFn(torch.autograd.Function):
         eng.backward(ctx.ectx, gy * scale if scale != 1.0 else gy)
         grads = []
         for n, p in eng.module.named_parameters():
-            grads.append(eng.gview(n) * (1.0 / scale) if p.requires_grad else None)
+            grads.append(eng.grad_of(n) if p.requires_grad else None)      # reference layout, true units
         return (None, None, None) + tuple(grads)
 
 
@@ -144,6 +144,18 @@ class Generator(Model):
         if self._engine is None:
             self._engine = _engine.GeneratorEngine(self)
         return self._engine
+
+    # The big weights' nn.Parameters are reference-layout mirrors of the engine's packed fp32 masters: anything that
+    # reads or moves the parameters wholesale first refreshes them (a no-op unless an optimiser step intervened).
+    def state_dict(self, *args, **kwargs):
+        if self._engine is not None:
+            self._engine.sync_to_reference()
+        return super().state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        if getattr(self, '_engine', None) is not None:
+            self._engine.sync_to_reference()
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, x, z=None, ret_hid=False):
         eng = self.engine

@@ -87,8 +87,9 @@ class FusedOptimizer(object):
         return flat
 
     def zero_grad(self):
+        """The bucket is cleared by step() as it is read: this only fills when gradients were left behind."""
         self.eng.bind()
-        self.eng.grad.zero_()
+        self.eng.zero_grad()
 
     def step(self, grad_scale=1.0):
         flat = self._state()
@@ -96,13 +97,16 @@ class FusedOptimizer(object):
         self.t += 1
         n = flat.numel()
         grad_scale = float(grad_scale) / _engine.LOSS_SCALE      # the bucket carries the fp16 loss scale
+        self.eng.finish_grads()                                  # dWeff -> dW, dalpha (decoder skip halves)
+        clear = 0 if _engine.KEEP_GRADS else 1
         if self.kind == 'rmsprop':
             _lib.call("sg_rmsprop_step", _p(flat), _p(self.eng.grad), _p(self.s1), n, lr, self.alpha, self.eps,
-                      float(grad_scale), _stream())
+                      float(grad_scale), clear, _stream())
         else:
             _lib.call("sg_adam_step", _p(flat), _p(self.eng.grad), _p(self.s1), _p(self.s2), n, lr, self.betas[0],
-                      self.betas[1], self.eps, self.t, float(grad_scale), _stream())
-        self.eng.mark_dirty()
+                      self.betas[1], self.eps, self.t, float(grad_scale), clear, _stream())
+        self.eng.grads_consumed(bool(clear))
+        self.eng.master_updated()
 
     def _trainable(self):
         """(name, parameter) in torch's optimiser order: the requires_grad parameters only (core.py:196-197)."""
@@ -116,8 +120,7 @@ class FusedOptimizer(object):
         state = {}
         names = self._trainable()
         for i, (name, p) in enumerate(names):
-            off, n, shape = self.eng.index[name]
-            view = lambda t: t[off:off + n].view(shape).detach().to('cpu', copy=True)
+            view = lambda t, name=name: self._state_view(t, name)
             step = torch.tensor(float(self.t))
             if self.kind == 'rmsprop':
                 state[i] = {'step': step, 'square_avg': view(self.s1)}
@@ -133,6 +136,26 @@ class FusedOptimizer(object):
         group['params'] = list(range(len(names)))
         return {'state': state if self.t > 0 else {}, 'param_groups': [group]}
 
+    def _state_view(self, t, name):
+        """Per-parameter state tensor in reference layout on the CPU (the state lives in the bucket's layout)."""
+        eng = self.eng
+        l = eng.by_name.get(name)
+        if l is None:
+            off, n, shape = eng.index[name]
+            return t[off:off + n].view(shape).detach().to('cpu', copy=True)
+        out = torch.empty_like(eng._param(name).data)
+        eng._export(l, t[l.off:l.off + l.numel], out)
+        return out.cpu()
+
+    def _state_load(self, t, name, value):
+        eng = self.eng
+        l = eng.by_name.get(name)
+        if l is None:
+            off, n, shape = eng.index[name]
+            t[off:off + n].copy_(value.reshape(-1))
+        else:
+            eng._import(l, src=value.to(t.device).float().contiguous(), dst=t[l.off:l.off + l.numel])
+
     def load_state_dict(self, sd):
         self._state()
         groups = sd.get('param_groups') or [{}]
@@ -142,13 +165,12 @@ class FusedOptimizer(object):
             st = sd.get('state', {}).get(i)
             if st is None:
                 continue
-            off, n, shape = self.eng.index[name]
             self.t = int(st.get('step', self.t))
             if 'square_avg' in st:
-                self.s1[off:off + n].copy_(st['square_avg'].reshape(-1))
+                self._state_load(self.s1, name, st['square_avg'])
             if 'exp_avg' in st:
-                self.s1[off:off + n].copy_(st['exp_avg'].reshape(-1))
-                self.s2[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+                self._state_load(self.s1, name, st['exp_avg'])
+                self._state_load(self.s2, name, st['exp_avg_sq'])
 
 
 def _dist():
@@ -398,8 +420,10 @@ class SEGAN(Model):
         if st.graphs is None:
             self._capture_step(st, z is None, shifts3, l1_weight, Gopt, Dopt)
         else:
-            if de._version() != de._packed_version:
-                de.ensure_packed()             # parameters were touched outside the step (checkpoint load ...)
+            # parameters touched outside the step (checkpoint load ...): import them; D's operands of graph 1 were
+            # emitted by the previous replay of graph 2, so they are refreshed here
+            ge.notice_external_writes()
+            de.ensure_packed()
             st.graphs[0].replay()
             allreduce_grads(de)
             st.graphs[1].replay()
@@ -407,7 +431,8 @@ class SEGAN(Model):
             st.graphs[2].replay()
             Dopt.t += 1
             Gopt.t += 1
-            ge.mark_dirty()                    # the replayed G optimiser step changed the master weights
+            ge.master_updated()                # the replayed optimiser steps changed the masters in place
+            de._mirror_stale = True
             _lib.launch_count += st.launches
         if losses is not None and losses.data_ptr() != st.losses.data_ptr():
             losses.copy_(st.losses, non_blocking=True)
@@ -445,8 +470,6 @@ class SEGAN(Model):
         _, c = de.forward(Genh, noisy, shifts3[1], training=True, shifts_dev=sdev(1))
         de.backward(c, 0.0, 1.0, param_grads=True, loss_out=lptr(1))
         _engine.join_side(rside)
-        if lane == 1:
-            de.merge_lane_grads()
         return Genh, gctx
 
     def _seg_g(self, clean, noisy, Genh, gctx, shifts3, shifts_dev, losses, l1_weight, Gopt, Dopt, dscale):
@@ -540,7 +563,8 @@ class SEGAN(Model):
         g3.replay()
         Dopt.t += 1
         Gopt.t += 1
-        ge.mark_dirty()
+        ge.master_updated()
+        de._mirror_stale = True
         _lib.launch_count += st.launches
         if sample_z and not hasattr(self.G, 'z'):
             self.G.z = st.z

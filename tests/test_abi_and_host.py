@@ -88,7 +88,9 @@ def test_phase_shift_draw_order_matches_oracle():
 def test_flat_buckets_and_checkpoint_roundtrip(tmp_path):
     s = build_segan()
     eng = s.G.engine.bind()
-    assert eng.flat.numel() == 64770561
+    # packed masters (36 of 31 tap slots) + small parameters in one bucket
+    assert sum(l.numel for l in eng.layers) == 75202560          # 64 757 760 packed weights x 36 / 31
+    assert 75202560 + (64770561 - 64757760) <= eng.flat.numel() <= 75202560 + (64770561 - 64757760) + 4 * 40
     w = dict(s.G.named_parameters())["enc_blocks.1.conv.weight"]
     assert w.data_ptr() == eng.pview("enc_blocks.1.conv.weight").data_ptr()
     sha = sd_sha(s.G.state_dict())
@@ -168,6 +170,8 @@ def test_fused_optimizer_state_dict_is_torch_compatible(kind):
     if kind == "adam":
         opt.s2.uniform_(0.1, 1.0)
     sd = opt.state_dict()
+    import copy
+    sd0 = copy.deepcopy(sd)                           # torch's load_state_dict adopts the tensors and step() mutates them
     params = list(s.G.parameters())
     assert len(sd["state"]) == len(params) == len(sd["param_groups"][0]["params"])
     assert all(not n.startswith("alpha_") for n, _ in opt._trainable())
@@ -178,13 +182,20 @@ def test_fused_optimizer_state_dict_is_torch_compatible(kind):
         p.grad = torch.zeros_like(p)
     ref.step()                                        # KeyError here if a hyper-parameter were missing
     key = "square_avg" if kind == "rmsprop" else "exp_avg"
-    off, n, shape = eng.index["enc_blocks.1.conv.weight"]
-    i = [k for k, _ in opt._trainable()].index("enc_blocks.1.conv.weight")
-    assert ref.state_dict()["state"][i][key].shape == torch.Size(shape)
+    names = [k for k, _ in opt._trainable()]
+    i = names.index("enc_blocks.1.conv.weight")          # a packed layer: its state is exported to reference layout
+    j = names.index("dec_blocks.2.act.weight")           # a small parameter: a view of the bucket
+    assert ref.state_dict()["state"][i][key].shape == torch.Size([128, 64, 31])
+    from segan_pytorch_b200.engine import unpack_reference
+    lay = eng.by_name["enc_blocks.1.conv.weight"]
+    assert torch.equal(sd0["state"][i][key], unpack_reference(0, opt.s1[lay.off:lay.off + lay.numel], 128, 64, 0))
     # and back, with a changed lr
     sd2 = ref.state_dict()
     sd2["param_groups"][0]["lr"] = 2e-5
     opt2 = FusedOptimizer(eng, kind, 5e-5, betas=(0, 0.9))
     opt2.load_state_dict(sd2)
     assert opt2.param_groups[0]["lr"] == 2e-5 and opt2.t == 4
-    assert torch.allclose(opt2.s1[off:off + n].view(shape), ref.state_dict()["state"][i][key])
+    assert torch.allclose(unpack_reference(0, opt2.s1[lay.off:lay.off + lay.numel], 128, 64, 0),
+                          ref.state_dict()["state"][i][key])
+    off, n, shape = eng.index["dec_blocks.2.act.weight"]
+    assert torch.allclose(opt2.s1[off:off + n].view(shape), ref.state_dict()["state"][j][key])

@@ -653,9 +653,12 @@ def test_optimizers_and_emphasis():
             opt.step()
             gd = gr.to(DEV)
             if kind == "rmsprop":
-                _lib.call("sg_rmsprop_step", _p(p), _p(gd), _p(s1), n, 5e-5, 0.99, 1e-8, 1.0, _stream())
+                _lib.call("sg_rmsprop_step", _p(p), _p(gd), _p(s1), n, 5e-5, 0.99, 1e-8, 1.0, t % 2, _stream())
             else:
-                _lib.call("sg_adam_step", _p(p), _p(gd), _p(s1), _p(s2), n, 5e-5, 0.0, 0.9, 1e-8, t, 1.0, _stream())
+                _lib.call("sg_adam_step", _p(p), _p(gd), _p(s1), _p(s2), n, 5e-5, 0.0, 0.9, 1e-8, t, 1.0, t % 2, _stream())
+            torch.cuda.synchronize()
+            # clear_grad: the gradient is zeroed as it is read (odd steps here), left alone otherwise
+            assert (int(gd.count_nonzero()) == 0) == (t % 2 == 1)
         torch.cuda.synchronize()
         assert max_abs(p.cpu(), pr.detach()) <= 2e-7, kind
     y = (0.1 * torch.randn(50001, generator=g))
@@ -797,3 +800,82 @@ def test_generator_forward_fused_vs_unfused_activation():
         finally:
             E.FUSE_ACT = prev
     assert max_abs(outs[0], outs[1]) <= 3e-4
+
+
+# ------------------------------------------------------------------------------------------------------
+# round 2: packed-master path (emit operands / alpha gradient / folds) against the tensor-algebra twins
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,co,ci,tl", [(0, 128, 64, 0), (1, 64, 256, 0), (2, 256, 128, 16)])
+def test_packed_master_roundtrip_and_operands(kind, co, ci, tl):
+    """sg_pack_weights(-> fp32 master) / sg_unpack_wgrad(alpha None) == engine.pack_reference / unpack_reference, and
+    sg_emit_operands produces exactly the operands the reference-layout packer (sg_pack_weights, 16-bit) makes."""
+    g = _gen(31)
+    shape = (co, ci, 31) if kind == 0 else ((ci, co, 31) if kind == 1 else (co, ci * tl))
+    w = torch.randn(*shape, generator=g).to(DEV)
+    layer = E.PackedLayer("w", kind, co, ci, tl, "f", "dg", alpha_name="alpha" if kind == 1 else None)
+    m = torch.zeros(layer.numel, device=DEV)
+    _lib.call("sg_pack_weights", kind, _p(w), co, ci, tl, None, 0, _p(m), None, SG_F32, SG_F32, _stream())
+    torch.cuda.synchronize()
+    ref = E.pack_reference(kind, w.cpu(), co, ci, tl)
+    assert torch.equal(m.cpu().view(ref.shape), ref)
+    back = torch.zeros_like(w)
+    _lib.call("sg_unpack_wgrad", kind, _p(m), co, ci, tl, None, None, 0, _p(back), None, 0, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(back, w)
+    # operands: from the master (new path) vs from the reference layout (round-1 path)
+    alpha = (0.5 + torch.rand(ci // 2, generator=g)).to(DEV) if kind == 1 else None
+    T, nc, kc = layer.T, layer.nc, layer.kc
+    f1 = torch.zeros(T, nc, kc, dtype=torch.float16, device=DEV)
+    d1 = torch.zeros(T, kc, nc, dtype=torch.float16, device=DEV)
+    f0, d0 = torch.zeros_like(f1), torch.zeros_like(d1)
+    _lib.call("sg_emit_operands", _p(m), T, nc, kc, _p(alpha), ci // 2 if kind == 1 else 0, _p(f1), _p(d1), SG_F16, SG_F16,
+              _stream())
+    _lib.call("sg_pack_weights", kind, _p(w), co, ci, tl, _p(alpha), ci // 2, _p(f0), _p(d0), SG_F16, SG_F16, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(f1, f0) and torch.equal(d1, d0)
+
+
+def test_alpha_grad_and_folds():
+    """sg_alpha_grad == what sg_unpack_wgrad(alpha) computes (dW = alpha*dWeff on the skip half, dalpha = sum dWeff*W);
+    the waveform-end folds against their index formulas (and they clear what they read)."""
+    g = _gen(32)
+    co, ci = 64, 256
+    w = torch.randn(ci, co, 31, generator=g).to(DEV)
+    dweff_ref_layout = torch.randn(ci, co, 31, generator=g)
+    alpha = (0.5 + torch.rand(ci // 2, generator=g)).to(DEV)
+    m = E.pack_reference(1, w.cpu(), co, ci, 0).to(DEV).contiguous()
+    dwp = E.pack_reference(1, dweff_ref_layout, co, ci, 0).to(DEV).contiguous()
+    dalpha = torch.zeros(ci // 2, device=DEV)
+    _lib.call("sg_alpha_grad", _p(dwp), _p(m), 9, 4 * co, ci, _p(alpha), ci // 2, _p(dalpha), _stream())
+    torch.cuda.synchronize()
+    dw = E.unpack_reference(1, dwp.cpu().view(9, 4 * co, ci), co, ci, 0)
+    exp = dweff_ref_layout.clone()
+    exp[ci // 2:] *= alpha.cpu().view(-1, 1, 1)
+    assert rel_err(dw, exp) <= 1e-6
+    assert rel_err(dalpha.cpu(), (dweff_ref_layout[ci // 2:] * w.cpu()[ci // 2:]).sum((1, 2))) <= 1e-5
+    # first conv fold, cin = 2
+    dwq = torch.randn(2, 64, 2, 64, generator=g).to(DEV)
+    src = dwq.cpu().clone()
+    dwg = torch.ones(64, 2, 31, device=DEV)
+    _lib.call("sg_wave_wgrad_fold", _p(dwq), 2, _p(dwg), _stream())
+    torch.cuda.synchronize()
+    exp = 1 + (src[0, :, 0, :] + src[1, :, 1, :]).view(64, 2, 32)[:, :, :31]
+    assert rel_err(dwg.cpu(), exp) <= 1e-6
+    after = dwq.cpu().view(2, 64, 2, 2, 32)
+    assert float(after[0, :, 0, :, :31].abs().max()) == 0.0 and float(after[1, :, 1, :, :31].abs().max()) == 0.0
+    assert torch.equal(after[0, :, 1], src.view(2, 64, 2, 2, 32)[0, :, 1])          # off-diagonal blocks untouched
+    # last deconv fold
+    half = 64
+    dwq = torch.randn(2, 64, 2, 2, half, generator=g).to(DEV)
+    src = dwq.cpu().clone()
+    wl = torch.randn(2 * half, 1, 31, generator=g).to(DEV)
+    al = (0.5 + torch.rand(half, generator=g)).to(DEV)
+    gw = torch.zeros(2 * half, 1, 31, device=DEV)
+    ga = torch.zeros(half, device=DEV)
+    _lib.call("sg_last_deconv_wgrad_fold", _p(dwq), half, _p(wl), _p(al), _p(gw), _p(ga), _stream())
+    torch.cuda.synchronize()
+    dweff = (src[0, :, :, 0, :] + src[1, :, :, 1, :]).permute(1, 2, 0).reshape(2 * half, 64)[:, :31]
+    exp = dweff.clone()
+    exp[half:] *= al.cpu().view(-1, 1)
+    assert rel_err(gw.cpu()[:, 0], exp) <= 1e-6
+    assert rel_err(ga.cpu(), (dweff[half:] * wl.cpu()[half:, 0]).sum(1)) <= 1e-5

@@ -293,6 +293,88 @@ def test_train_loop_with_prefetcher_matches_manual_steps(tmp_path):
     assert rel_err(s1.G.engine.flat, s2.G.engine.flat) <= 5e-2
 
 
+def test_clear_on_read_gradients_match_explicit_zeroing():
+    """Production path: the optimiser kernels zero the gradient buckets as they read them and no fill is launched;
+    KEEP_GRADS (the mode the parity tests run in) zeroes explicitly.  Three steps each way from the same state:
+    same losses and parameters up to the fp32-atomics noise floor (KEEP vs KEEP)."""
+    from segan_pytorch_b200 import engine as E
+    from tests.util import load_opts
+    t = golden("train_step_b4.npz")
+    B = t["clean"].shape[0]
+    clean = torch.from_numpy(t["clean"]).unsqueeze(1).to(DEV)
+    noisy = torch.from_numpy(t["noisy"]).unsqueeze(1).to(DEV)
+    gen = torch.Generator().manual_seed(4)
+    zs = [torch.randn(B, 1024, 16, generator=gen).to(DEV) for _ in range(3)]
+    random.seed(12)
+    shifts = [[O.draw_phase_shifts(5, 5) for _ in range(3)] for _ in range(3)]
+
+    def run(keep):
+        prev = E.KEEP_GRADS, E.GRAPHS
+        E.KEEP_GRADS, E.GRAPHS = keep, False
+        try:
+            s = build_segan(batch_size=B).to(DEV)
+            s.G.train()
+            s.D.train()
+            Gopt, Dopt = s.build_optimizers(load_opts(batch_size=B))
+            for i in range(3):
+                losses = s.train_step(clean, noisy, Gopt, Dopt, 100.0, z=zs[i], shifts3=shifts[i])
+            torch.cuda.synchronize()
+            nz = int(s.G.engine.grad.count_nonzero()) + int(s.D.engine.grad.count_nonzero())
+            return losses.tolist(), s.G.engine.flat.clone(), s.D.engine.flat.clone(), nz
+        finally:
+            E.KEEP_GRADS, E.GRAPHS = prev
+    k1, k2, c = run(True), run(True), run(False)
+    assert c[3] == 0 and k1[3] > 0                      # buckets left zeroed / left in place
+    floor = max(rel_err(k2[1], k1[1]), rel_err(k2[2], k1[2]))
+    err = max(rel_err(c[1], k1[1]), rel_err(c[2], k1[2]))
+    print("params after 3 steps: keep-vs-keep %.2e, clear-vs-keep %.2e; losses %s %s" % (floor, err, k1[0], c[0]))
+    assert err <= 10 * floor + 1e-4
+    for a, b in zip(c[0], k1[0]):
+        assert abs(a - b) <= 0.05 * max(1.0, abs(b))
+
+
+def test_state_dict_tracks_packed_masters(tmp_path):
+    """The big weights' nn.Parameters are mirrors of the packed masters: state_dict() / save() after a step return
+    the UPDATED weights, load_state_dict() reaches the masters, and a forward after loading uses the loaded weights."""
+    from tests.util import load_opts
+    B = 2
+    s = build_segan(batch_size=B).to(DEV)
+    s.G.train()
+    s.D.train()
+    Gopt, Dopt = s.build_optimizers(load_opts(batch_size=B))
+    gen = torch.Generator().manual_seed(5)
+    clean = (0.3 * torch.randn(B, 1, 16384, generator=gen)).to(DEV)
+    noisy = (clean.cpu() + 0.1 * torch.randn(B, 1, 16384, generator=gen)).to(DEV)
+    z = torch.randn(B, 1024, 16, generator=gen).to(DEV)
+    sd0 = {k: v.clone() for k, v in s.G.state_dict().items()}
+    s.train_step(clean, noisy, Gopt, Dopt, 100.0, z=z)
+    sd1 = {k: v.clone() for k, v in s.G.state_dict().items()}
+    k = "dec_blocks.1.deconv.weight"
+    delta = (sd1[k] - sd0[k]).abs()
+    assert 4e-4 <= float(delta.max()) <= 5.1e-4          # RMSprop first step: lr * g / (sqrt(0.01 g^2) + eps) = 10 lr sign(g)
+    # the mirror equals the master, exported through the tensor-algebra twin
+    from segan_pytorch_b200.engine import unpack_reference
+    eng = s.G.engine
+    lay = eng.by_name[k]
+    assert torch.equal(sd1[k], unpack_reference(1, eng.mview(lay), lay.c_out, lay.c_in, 0).reshape(sd1[k].shape))
+    s.G.eval()
+    with torch.no_grad():
+        y1 = s.G(noisy, z=z).clone()
+        s.G.load_state_dict(sd0)                          # back to the initial weights: masters must follow
+        y0 = s.G(noisy, z=z).clone()
+        s.G.load_state_dict(sd1)
+        y1b = s.G(noisy, z=z).clone()
+    assert max_abs(y1, y1b) == 0.0 and max_abs(y1, y0) > 1e-5
+    # checkpoint round trip through Saver
+    s.G.save(str(tmp_path), 1)
+    s2 = build_segan(seed=3, batch_size=B).to(DEV)
+    import os
+    s2.G.load_pretrained(os.path.join(str(tmp_path), "weights_Generator-Generator-1.ckpt"), True)
+    s2.G.eval()
+    with torch.no_grad():
+        assert max_abs(s2.G(noisy, z=z), y1) == 0.0
+
+
 def test_generate_chunked_vs_reference(segan):
     g = golden("generate_40000.npz")
     if hasattr(segan.G, "z"):
