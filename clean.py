@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """clean.py -- drop-in for the reference entry point (clean.py:28-110): load train.opts + a G
 checkpoint, enhance every wav under --test_files, write 16 kHz wavs to --synthesis_path.
-All 16384-sample windows of a file run as one batch on the GPU; de-emphasis is the GPU scan."""
+SEGAN: the windows of ALL files are batched across files and streamed (SEGAN.clean_files: wav decode, upload, int16 ->
+float + pre-emphasis on the device, G, segmented de-emphasis, download and wav writing overlap); --per_file keeps the
+reference's loop (one file per SEGAN.generate call).  WSEGAN: per file, un-chunked (model.py:755-766)."""
 import argparse
 import glob
 import json
@@ -35,6 +37,18 @@ def main(opts):
     twavs = glob.glob(os.path.join(opts.test_files[0], "*.wav")) if len(opts.test_files) == 1 else opts.test_files
     print("Cleaning {} wavs".format(len(twavs)))
     beg_t = timeit.default_timer()
+    if not getattr(args, "wsegan", False) and not opts.per_file:
+        # SEGAN: windows of all files batched on the GPU, wav decode / upload / G / download / wav write overlapped
+        # (SEGAN.clean_files); WSEGAN enhances each utterance un-chunked (model.py:755-766): the per-file loop below
+        done = []
+
+        def on_done(path, n):
+            done.append(path)
+            print("Cleaned {}/{}: {} ({} samples)".format(len(done), len(twavs), path, n))
+        nwin = segan.clean_files(twavs, opts.synthesis_path, batch=opts.batch_windows, on_done=on_done)
+        dt = timeit.default_timer() - beg_t
+        print("Cleaned {} wavs / {} windows in {:.3f} s ({:.0f} windows/s)".format(len(twavs), nwin, dt, nwin / dt))
+        return
     for t_i, twav in enumerate(twavs, start=1):
         rate, wav = wavfile.read(twav)
         wav = pre_emphasize(normalize_wave_minmax(wav), args.preemph)
@@ -56,6 +70,9 @@ if __name__ == "__main__":
     parser.add_argument("--cuda", action="store_true", default=False)
     parser.add_argument("--soundfile", action="store_true", default=False)
     parser.add_argument("--cfg_file", type=str, default=None)
+    # additive flags
+    parser.add_argument("--batch_windows", type=int, default=256, help="windows per Generator launch (streaming path)")
+    parser.add_argument("--per_file", action="store_true", default=False, help="the reference's one-file-at-a-time loop")
     opts = parser.parse_args()
     os.makedirs(opts.synthesis_path, exist_ok=True)
     random.seed(opts.seed)

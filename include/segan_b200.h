@@ -355,6 +355,9 @@ int sg_last_deconv_wgrad_fold(float* dwq /* the blocks read are cleared */, int 
  * x[n] = coef*x[n-1] + y[n] per utterance as a parallel scan; and the inverse used on input.
  * ------------------------------------------------------------------------------------------ */
 int sg_deemphasis(const float* y, int64_t n, float coef, float* x, void* stream);
+/* n_seg independent utterances inside one buffer: segment b = [seg[2b], seg[2b] + seg[2b+1]) (element offset, length;
+ * device int64 pairs), each filtered from a zero state by its own thread block (clean.py across files). */
+int sg_deemphasis_segments(const float* y, const int64_t* seg, int n_seg, float coef, float* x, void* stream);
 int sg_preemphasis(const float* x, int64_t n, float coef, float* y, void* stream);
 /* Input contract on the device (se_dataset.py:108-117,191-199,355-368): int16 PCM windows [n_windows][L] ->
  * normalize_wave_minmax -> pre_emphasize(coef) -> fp32 [n_windows][L] (coef <= 0: no pre-emphasis).  The reference
@@ -363,6 +366,8 @@ int sg_preemphasis(const float* x, int64_t n, float coef, float* y, void* stream
  * over PCIe and drops the host-side preprocessing. */
 #define SG_PCM_NO_PREV 0x7fffffff
 int sg_pcm16_to_wave(const int16_t* pcm, const int32_t* prev, int64_t n_windows, int L, float coef, float* out,
+                     const int32_t* valid_len /* or NULL: per window, samples >= valid_len[w] are written as 0 (the zero
+                                                 padding of an utterance's last window, model.py:122-131) */,
                      void* stream);
 
 #ifdef __cplusplus

@@ -312,8 +312,13 @@ __global__ void last_deconv_wgrad_fold_kernel(float* __restrict__ dwq, int half,
 // recurrence: single block, chunked scan over (a, b) pairs with the carry kept in a register.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) deemph_kernel(const float* __restrict__ y, int64_t n, float c,
-                                                      float* __restrict__ x) {
+                                                      float* __restrict__ x, const int64_t* __restrict__ seg) {
   constexpr int PER = 4;
+  if (seg) {                       // segmented: block b filters [seg[2b], seg[2b] + seg[2b+1]) from a zero state
+    y += seg[2 * blockIdx.x];
+    x += seg[2 * blockIdx.x];
+    n = seg[2 * blockIdx.x + 1];
+  }
   __shared__ float sa[32], sb[32];
   __shared__ float carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -496,7 +501,14 @@ extern "C" int sg_last_deconv_wgrad_fold(float* dwq, int half, const float* w, c
 }
 
 extern "C" int sg_deemphasis(const float* y, int64_t n, float coef, float* x, void* stream) {
-  deemph_kernel<<<1, 1024, 0, ST>>>(y, n, coef, x);
+  deemph_kernel<<<1, 1024, 0, ST>>>(y, n, coef, x, nullptr);
+  SG_CHECK_LAUNCH();
+  return SG_OK;
+}
+extern "C" int sg_deemphasis_segments(const float* y, const int64_t* seg, int n_seg, float coef, float* x,
+                                      void* stream) {
+  SG_CHECK_ARG(y && x && seg && n_seg > 0);
+  deemph_kernel<<<n_seg, 1024, 0, ST>>>(y, 0, coef, x, seg);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }
@@ -505,8 +517,12 @@ extern "C" int sg_deemphasis(const float* y, int64_t n, float coef, float* x, vo
 // slicing (read_wav_file, se_dataset.py:191-199), so the sample before a window matters: prev[w] holds it (int32;
 // SG_PCM_NO_PREV = the window starts the file, y[0] = x[0]); prev == NULL treats every window as a file start.
 __global__ void pcm16_to_wave_kernel(const int16_t* __restrict__ pcm, const int32_t* __restrict__ prev, int64_t total,
-                                     int L, float coef, float* __restrict__ out) {
+                                     int L, float coef, float* __restrict__ out, const int32_t* __restrict__ valid) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (valid && (int)(i % L) >= valid[i / L]) {     // zero padding of a file's last window (model.py:122-131)
+      out[i] = 0.f;
+      continue;
+    }
     const float x = (2.f / 65535.f) * ((float)pcm[i] - 32767.f) + 1.f;
     float y = x;
     if (coef > 0.f) {
@@ -521,9 +537,9 @@ __global__ void pcm16_to_wave_kernel(const int16_t* __restrict__ pcm, const int3
 }
 
 extern "C" int sg_pcm16_to_wave(const int16_t* pcm, const int32_t* prev, int64_t n_windows, int L, float coef,
-                                float* out, void* stream) {
+                                float* out, const int32_t* valid_len, void* stream) {
   SG_CHECK_ARG(pcm && out && n_windows > 0 && L > 0);
-  pcm16_to_wave_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(pcm, prev, n_windows * L, L, coef, out);
+  pcm16_to_wave_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(pcm, prev, n_windows * L, L, coef, out, valid_len);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

@@ -118,7 +118,7 @@ class DevicePrefetcher(object):
                 for i, dst in enumerate((slot["clean"], slot["noisy"])):
                     _lib.call("sg_pcm16_to_wave", C.c_void_p(slot["pcm"][i].data_ptr()),
                               C.c_void_p(pv[i].data_ptr()) if pv is not None else None, shape[0], shape[2],
-                              self.preemph, C.c_void_p(dst.data_ptr()), st)
+                              self.preemph, C.c_void_p(dst.data_ptr()), None, st)
             else:
                 slot["clean"].copy_(clean.reshape(shape), non_blocking=True)
                 slot["noisy"].copy_(noisy.reshape(shape), non_blocking=True)

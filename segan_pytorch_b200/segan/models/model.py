@@ -326,6 +326,155 @@ class SEGAN(Model):
             prev["out_done"].synchronize()
             yield prev["out"]
 
+    def clean_files(self, wav_paths, out_dir, batch=256, group_windows=None, on_done=None):
+        """Streaming enhancement of many wav files -- the clean.py:59-82 loop batched ACROSS files (SURVEY.md 8f-N1,
+        BASELINE config 5).  Per file the result equals `generate` on the normalised + pre-emphasised file
+        (model.py:116-157): 16384-sample windows, the last one zero-padded, z semantics of the reference (a fresh
+        z for the first window of every file, `G.z` -- the first z G ever saw -- for the others), de-emphasis.
+
+        Pipeline: a reader thread decodes wavs into pinned int16 window groups (whole files, about `group_windows`
+        windows); the copy stream uploads group n+1 while the main stream runs group n -- int16 -> float +
+        whole-file pre-emphasis on the device (sg_pcm16_to_wave), G in batches of `batch` windows, one
+        segmented de-emphasis launch for all files of the group -- and a third stream downloads group n-1 into
+        pinned memory, from which a writer thread saves float32 wavs (scipy, like clean.py:79).
+        Returns the number of windows processed.  on_done(path, n_samples) is called per written file."""
+        import queue
+        import threading
+        from scipy.io import wavfile
+        self.G.eval()
+        N = 16384
+        dev = next(super(Model, self.G).parameters()).device
+        code_len = N // (4 ** len(self.G.enc_blocks))
+        zdim = self.G.z_dim
+        group_windows = int(group_windows or 2 * batch)
+        coef = float(self.preemph)
+        os.makedirs(out_dir, exist_ok=True)
+        q_in, q_out = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
+        errors = []
+
+        def reader():
+            """Groups of whole files as pinned int16 windows + per-window side tables."""
+            try:
+                group, nwin = [], 0
+
+                def flush():
+                    nonlocal group, nwin
+                    if not group:
+                        return
+                    pcm = torch.zeros(nwin, N, dtype=torch.int16).pin_memory()
+                    prev = torch.full((nwin,), 0x7fffffff, dtype=torch.int32)
+                    valid = torch.full((nwin,), N, dtype=torch.int32)
+                    first, files, w0 = [], [], 0
+                    for path, wav in group:
+                        T = wav.shape[0]
+                        n = (T + N - 1) // N
+                        flat = pcm[w0:w0 + n].view(-1)
+                        flat[:T] = torch.from_numpy(wav)
+                        if n > 1:
+                            prev[w0 + 1:w0 + n] = torch.from_numpy(wav[N - 1:(n - 1) * N:N].astype(np.int32))
+                        valid[w0 + n - 1] = T - (n - 1) * N
+                        first.append(w0)
+                        files.append((path, w0, T))
+                        w0 += n
+                    # one fresh z per file, drawn in file order from torch's CPU generator (generator.py:197-199)
+                    zf = torch.randn(len(files), zdim, code_len)
+                    q_in.put(dict(pcm=pcm, prev=prev.pin_memory(), valid=valid.pin_memory(), files=files,
+                                  first=torch.tensor(first, dtype=torch.long), zf=zf.pin_memory(), nwin=nwin))
+                    group, nwin = [], 0
+                for path in wav_paths:
+                    rate, wav = wavfile.read(path)
+                    if wav.ndim != 1 or wav.dtype != np.int16:
+                        raise ValueError('mono 16-bit PCM wavs expected: %s' % path)
+                    n = (wav.shape[0] + N - 1) // N
+                    if group and nwin + n > group_windows:
+                        flush()
+                    group.append((path, wav))
+                    nwin += n
+                flush()
+            except Exception as e:            # surfaced in the main thread
+                errors.append(e)
+            finally:
+                q_in.put(None)
+
+        def writer():
+            try:
+                while True:
+                    item = q_out.get()
+                    if item is None:
+                        return
+                    ev, host, files = item
+                    ev.synchronize()
+                    arr = host.numpy()
+                    for path, w0, T in files:
+                        out = arr[w0 * N:w0 * N + T]
+                        wavfile.write(os.path.join(out_dir, os.path.basename(path)), 16000, out)
+                        if on_done is not None:
+                            on_done(path, T)
+            except Exception as e:
+                errors.append(e)
+
+        tr, tw = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
+        tr.start()
+        tw.start()
+        main = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        total = 0
+        pending = []                                   # (host buffer, done event) kept alive until written
+
+        def upload(g):
+            with torch.cuda.stream(h2d):
+                d = {k: g[k].to(dev, non_blocking=True) for k in ('pcm', 'prev', 'valid', 'zf')}
+                d['ready'] = torch.cuda.Event()
+                d['ready'].record(h2d)
+            return d
+        nxt = q_in.get()
+        nxt_dev = upload(nxt) if nxt is not None else None
+        while nxt is not None and not errors:
+            g, d = nxt, nxt_dev
+            nxt = q_in.get()                               # decode of the following group ran meanwhile
+            nxt_dev = upload(nxt) if nxt is not None else None
+            main.wait_event(d['ready'])
+            nw = g['nwin']
+            x = torch.empty(nw, 1, N, dtype=torch.float32, device=dev)
+            _lib.call("sg_pcm16_to_wave", _p(d['pcm']), _p(d['prev']), nw, N, coef, _p(x), _p(d['valid']), _stream())
+            if not hasattr(self.G, 'z'):
+                self.G.z = d['zf'][:1].clone()             # generator.py:203-204: the first z ever
+            first = g['first'].to(dev)
+            y = torch.empty(nw, N, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for b0 in range(0, nw, batch):
+                    b1 = min(nw, b0 + batch)
+                    zb = self.G.z[:1].expand(b1 - b0, -1, -1).clone()
+                    sel = (first >= b0) & (first < b1)
+                    if bool(sel.any()):
+                        zb[first[sel] - b0] = d['zf'][sel]
+                    y[b0:b1] = self.G(x[b0:b1], z=zb).view(b1 - b0, N)
+            out = torch.empty_like(y)
+            if coef > 0:
+                seg = torch.tensor([[w0 * N, T] for _, w0, T in g['files']], dtype=torch.int64).to(dev)
+                _lib.call("sg_deemphasis_segments", _p(y), _p(seg), len(g['files']), coef, _p(out), _stream())
+            else:
+                out = y
+            done = torch.cuda.Event()
+            done.record(main)
+            for t_ in (d['pcm'], d['prev'], d['valid'], d['zf']):
+                t_.record_stream(main)
+            host = torch.empty(nw * N, dtype=torch.float32).pin_memory()
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                host.copy_(out.view(-1), non_blocking=True)
+                out.record_stream(d2h)
+                copied = torch.cuda.Event()
+                copied.record(d2h)
+            q_out.put((copied, host, g['files']))
+            total += nw
+        q_out.put(None)
+        tw.join()
+        tr.join(timeout=1.0)
+        if errors:
+            raise errors[0]
+        return total
+
     def discriminate(self, cwav, nwav):
         self.D.eval()
         d_in = torch.cat((cwav, nwav), dim=1)

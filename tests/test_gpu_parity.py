@@ -386,6 +386,52 @@ def test_generate_chunked_vs_reference(segan):
     assert tuple(g_c.shape) == (1, 1024, 16)
 
 
+def test_clean_files_streaming_matches_per_file_generate(tmp_path):
+    """clean.py streaming (SEGAN.clean_files: windows batched ACROSS files, int16 -> float + whole-file pre-emphasis
+    on the device, segmented de-emphasis, threaded wav I/O) against the reference loop's semantics: one
+    SEGAN.generate call per normalised + pre-emphasised file (clean.py:59-82), same z stream, and against the
+    oracle's chunked inference for one file."""
+    from scipy.io import wavfile
+    from segan_pytorch_b200.segan.datasets import normalize_wave_minmax, pre_emphasize
+    rng = np.random.RandomState(9)
+    lengths = [40000, 16384, 9000, 70001, 32768, 50]
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    paths = []
+    for i, n in enumerate(lengths):
+        w = (rng.randn(n) * 3000).clip(-32768, 32767).astype(np.int16)
+        p = str(src / ("utt%02d.wav" % i))
+        wavfile.write(p, 16000, w)
+        paths.append(p)
+    s = build_segan().to(DEV)
+    sdG = cpu_state(s.G)
+    torch.manual_seed(77)
+    nwin = s.clean_files(paths, str(dst), batch=3, group_windows=5)        # tiny batches: groups and batches split
+    assert nwin == sum((n + 16383) // 16384 for n in lengths)
+    z_first = s.G.z.cpu().clone()
+    # the reference's loop on a fresh model with the same RNG stream
+    s2 = build_segan().to(DEV)
+    torch.manual_seed(77)
+    zs = torch.randn(len(lengths), 1024, 16)
+    torch.manual_seed(77)
+    assert torch.equal(z_first[0], zs[0])
+    for i, p in enumerate(paths):
+        rate, w = wavfile.read(p)
+        pw = torch.FloatTensor(pre_emphasize(normalize_wave_minmax(w), 0.95)).view(1, 1, -1)
+        ref, _ = s2.generate(pw)
+        rate2, got = wavfile.read(str(dst / ("utt%02d.wav" % i)))
+        assert rate2 == 16000 and got.dtype == np.float32 and got.shape == ref.shape == (lengths[i],)
+        # same kernels, different batch composition: M-tile boundaries move, fp16 results do not
+        assert max_abs(got, ref) <= 2e-4, (i, max_abs(got, ref))
+    # and one file against the oracle (fp32 reference arithmetic): z of file 0 for every window of file 0
+    rate, w = wavfile.read(paths[0])
+    pw = torch.FloatTensor(pre_emphasize(normalize_wave_minmax(w), 0.95)).view(1, 1, -1)
+    with O.oracle_mode(), torch.no_grad():
+        oref = O.segan_generate(sdG, pw, zs[:1])
+    rate2, got = wavfile.read(str(dst / "utt00.wav"))
+    assert max_abs(got, oref) <= 20 * WAVE_TOL
+
+
 def test_prefetcher_pcm16_path_matches_host_preprocessing():
     """int16 PCM batches staged by DevicePrefetcher are normalised + pre-emphasised per window on the device
     (sg_pcm16_to_wave) exactly like se_dataset.py:108-117 does on the host."""
