@@ -181,6 +181,8 @@ typedef struct sg_tapgemm_w {
   int32_t batch;
   int32_t ksplit; /* number of position-range splits (>=1) */
   int32_t backend;
+  const float* out_scale; /* or NULL: device scalar multiplying the accumulated products (1/sigma of a spectrally
+                             normalised layer: the gradient w.r.t. W / sigma lands as G / sigma, sg_snorm_sigma) */
 } sg_tapgemm_w;
 
 int sg_tapgemm_w_run(const sg_tapgemm_w* p, void* stream);
@@ -343,9 +345,33 @@ int sg_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, i
  * sg_wave_wgrad_fold / sg_last_deconv_wgrad_fold: the waveform-end layers' weight gradients out of their single-tap
  * GEMM results (dwq, see engine.py), accumulated atomically into reference-layout gradients. */
 int sg_emit_operands(const float* master, int n_taps, int nc, int kc, const float* alpha, int alpha_from,
-                     void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad, void* stream);
+                     void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad,
+                     const float* scale_dev /* or NULL: device scalar multiplying every element (1/sigma of a
+                                               spectrally normalised layer, sg_snorm_sigma) */, void* stream);
 int sg_alpha_grad(float* dwp, const float* master, int n_taps, int nc, int kc, const float* alpha, int alpha_from,
                   float* dalpha, void* stream);
+/* Spectral normalisation (norm_type='snorm': modules.py:12-14, discriminator.py:118-121 -> torch.nn.utils.spectral_norm)
+ * on a packed master M[n_taps][nc][kc] holding weight_orig:
+ *   sg_snorm_sigma: training != 0: one power iteration v = normalize(W^T u), u = normalize(W v) in place (u [nc], v
+ *     [n_taps*kc] in packed slots), scal[2] = sigma = u^T W v, scal[3] = 1/sigma; training == 0: sigma from the
+ *     stored vectors.  scal: 4 device floats; work: nc device floats.  The operands are then emitted with
+ *     sg_emit_operands(..., scale_dev = scal + 3).
+ *   sg_snorm_grad: gradient w.r.t. the normalised weight (packed, what sg_tapgemm_w_run produced) -> gradient
+ *     w.r.t. weight_orig in place: dW = G / sigma - <G, W> / sigma^3 * u v^T  (u, v constants, as torch
+ *     differentiates sigma).  dot_ws: one device float. */
+int sg_snorm_sigma(const float* master, int n_taps, int nc, int kc, float* u, float* v, float* scal, float* work,
+                   int training, void* stream);
+int sg_snorm_grad(float* dwp, const float* master, int n_taps, int nc, int kc, const float* u, const float* v,
+                  const float* scal, float* dot_ws, void* stream);
+/* The same correction for the big layers whose gradients of several passes (D real / fake / ... each with its own
+ * power-iteration state) accumulate in one bucket: the weight-gradient GEMM scales by 1/sigma_p itself
+ * (sg_tapgemm_w.out_scale); the sigma term's scalar of pass p is  coef_p = <dL/dW~, W~> / sigma_p  and, the layer
+ * output being linear in W~,  <dL/dW~, W~> = <g_pre, x - bias>  comes from the activation-backward statistics
+ * (sg_act_bwd_reduce's red: [1] = sum g_pre, [2] = sum g_pre * x) -- sg_snorm_coef; one sweep then subtracts
+ * sum_p coef_p * u_p v_p^T -- sg_snorm_rank1 (u [n_pass][nc], v [n_pass][n_taps*kc], coef [n_pass]). */
+int sg_snorm_coef(const double* red, const float* bias, int C, const float* scal, float* coef_out, void* stream);
+int sg_snorm_rank1(float* dwp, int n_taps, int nc, int kc, int n_pass, const float* u, const float* v,
+                   const float* coef, void* stream);
 int sg_wave_wgrad_fold(float* dwq /* the blocks read are cleared */, int cin, float* dw, void* stream);
 int sg_last_deconv_wgrad_fold(float* dwq /* the blocks read are cleared */, int half, const float* w, const float* alpha, float* dw,
                               float* dalpha, void* stream);

@@ -173,17 +173,46 @@ def phase_roll(h, s):
     return h
 
 
+def spectral_weight(sd, prefix, training, eps=1e-12):
+    """torch.nn.utils.spectral_norm's weight (SpectralNorm.compute_weight), which build_norm_layer applies for
+    norm_type='snorm' (modules.py:12-14; discriminator.py:118-121 for the head): parameters `weight_orig`, buffers
+    `weight_u`, `weight_v` over weight.reshape(dim0, -1).  Training: ONE power iteration in place, without grad,
+    v = normalize(W^T u), u = normalize(W v); then weight = weight_orig / sigma with sigma = u^T W v, differentiated
+    with u, v held constant."""
+    w, u, v = sd[prefix + "weight_orig"], sd[prefix + "weight_u"], sd[prefix + "weight_v"]
+    wm = w.reshape(w.shape[0], -1)
+    if training:
+        with torch.no_grad():
+            v.copy_(F.normalize(torch.mv(wm.detach().t(), u), dim=0, eps=eps))
+            u.copy_(F.normalize(torch.mv(wm.detach(), v), dim=0, eps=eps))
+        u, v = u.clone(), v.clone()
+    sigma = torch.dot(u, torch.mv(wm, v))
+    return w / sigma
+
+
+def _weight(sd, prefix, training):
+    """`<prefix>weight`, spectrally normalised when the layer carries weight_orig (norm_type='snorm')."""
+    if prefix + "weight_orig" in sd:
+        return spectral_weight(sd, prefix, training)
+    return sd[prefix + "weight"]
+
+
 def discriminator_forward(sd, x, shifts, training=True, ret_act=False):
-    """x: (B,2,16384) = cat(candidate, noisy).  `sd` buffers running_mean/var/num_batches_tracked
-    are updated in place when training.  Returns logits (B,1)."""
-    n_enc = len([k for k in sd if k.startswith("enc_blocks.") and k.endswith("conv.weight")])
+    """x: (B,2,16384) = cat(candidate, noisy).  `sd` buffers running_mean/var/num_batches_tracked (bnorm) or
+    weight_u / weight_v (snorm) are updated in place when training.  Returns logits (B,1).
+    norm_type is read off the state dict: 'bnorm' layers carry norm.* keys, 'snorm' layers weight_orig/u/v and no
+    norm layer (build_norm_layer returns None for it, modules.py:12-14)."""
+    n_enc = len([k for k in sd if k.startswith("enc_blocks.") and (k.endswith("conv.weight") or
+                                                                   k.endswith("conv.weight_orig"))])
     h = x
     acts = {}
     for l in range(n_enc):
         h = phase_roll(h, shifts[l])
         p = "enc_blocks.%d." % l
-        a = gconv_linear(h, sd[p + "conv.weight"], sd.get(p + "conv.bias"))
-        if training:
+        a = gconv_linear(h, _weight(sd, p + "conv.", training), sd.get(p + "conv.bias"))
+        if p + "norm.weight" not in sd:
+            pass                                        # snorm / no norm: conv -> PReLU
+        elif training:
             a = batchnorm_train(a, sd[p + "norm.weight"], sd[p + "norm.bias"],
                                 sd[p + "norm.running_mean"], sd[p + "norm.running_var"])
             if p + "norm.num_batches_tracked" in sd:
@@ -194,10 +223,10 @@ def discriminator_forward(sd, x, shifts, training=True, ret_act=False):
         h = prelu(a, sd[p + "act.weight"])
         acts["h_%d" % l] = h
     h = h.view(h.size(0), -1)                                     # discriminator.py:180-182
-    h = F.linear(_q(h), _q(sd["fc.0.weight"]), sd["fc.0.bias"])
+    h = F.linear(_q(h), _q(_weight(sd, "fc.0.", training)), sd["fc.0.bias"])
     h = F.prelu(h, sd["fc.1.weight"])
-    h = F.linear(h, sd["fc.2.weight"], sd["fc.2.bias"])
-    h = F.prelu(h, sd["fc.3.weight"])
+    h = F.linear(h, _weight(sd, "fc.2.", training), sd["fc.2.bias"])
+    h = F.prelu(h, _weight(sd, "fc.3.", training))      # discriminator.py:121 normalises the PReLU(128) slope vector
     y = F.linear(h, sd["fc.4.weight"], sd["fc.4.bias"])
     acts["logit"] = y
     return (y, acts) if ret_act else y
@@ -229,7 +258,7 @@ def adam_step(param, grad, state, lr, betas=(0.0, 0.9), eps=1e-8):
 # --------------------------------------------------------------------------------------
 # SEGAN+ train step (segan/models/model.py:283-321)
 # --------------------------------------------------------------------------------------
-TRAINABLE_SUFFIXES = ("weight", "bias", "skip_k")
+TRAINABLE_SUFFIXES = ("weight", "weight_orig", "bias", "skip_k")
 
 
 def _trainable(sd):

@@ -43,7 +43,7 @@ class TapGemmW(C.Structure):
         ("kc", C.c_int32), ("nc", C.c_int32), ("d_lo", C.c_int32), ("d_hi", C.c_int32),
         ("tap_k_lo", I9), ("tap_k_hi", I9), ("tap_n_lo", I9), ("tap_n_hi", I9),
         ("dw", _vp), ("dw_tap0", C.c_int32),
-        ("batch", C.c_int32), ("ksplit", C.c_int32), ("backend", C.c_int32),
+        ("batch", C.c_int32), ("ksplit", C.c_int32), ("backend", C.c_int32), ("out_scale", _vp),
     ]
 
 
@@ -77,7 +77,11 @@ _SIGS = {
     "sg_l1_loss_bwd": [_vp, _vp, _i64, _f, _vp, _vp, _i, _f, _vp],
     "sg_rmsprop_step": [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp],
     "sg_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _i, _vp],
-    "sg_emit_operands": [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp],
+    "sg_emit_operands": [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "sg_snorm_sigma": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
+    "sg_snorm_grad": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "sg_snorm_coef": [_vp, _vp, _i, _vp, _vp, _vp],
+    "sg_snorm_rank1": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "sg_alpha_grad": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp],
     "sg_wave_wgrad_fold": [_vp, _i, _vp, _vp],
     "sg_last_deconv_wgrad_fold": [_vp, _i, _vp, _vp, _vp, _vp, _vp],

@@ -215,12 +215,14 @@ __global__ void unpack_fc_kernel(const float* __restrict__ dwp, int nout, int C,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 emit_operands_kernel(const float* __restrict__ m, int T, int nc, int kc, const float* __restrict__ alpha,
-                     int alpha_from, void* __restrict__ f, void* __restrict__ dg, int dt_f, int dt_dg) {
+                     int alpha_from, void* __restrict__ f, void* __restrict__ dg, int dt_f, int dt_dg,
+                     const float* __restrict__ scale_dev) {
   __shared__ float tile[64][65];
   const int t = blockIdx.z;
   const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
-  const float sc = (alpha && k0 + tx >= alpha_from) ? alpha[k0 + tx - alpha_from] : 1.f;
+  const float sc = ((alpha && k0 + tx >= alpha_from) ? alpha[k0 + tx - alpha_from] : 1.f) *
+                   (scale_dev ? *scale_dev : 1.f);
   const int64_t mbase = ((int64_t)t * nc + n0) * kc + k0;
 #pragma unroll 4
   for (int r = ty; r < 64; r += 4) {
@@ -462,12 +464,13 @@ extern "C" int sg_unpack_wgrad(int kind, const float* dwp, int c_out, int c_in, 
 }
 
 extern "C" int sg_emit_operands(const float* master, int n_taps, int nc, int kc, const float* alpha, int alpha_from,
-                                void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad, void* stream) {
+                                void* w_fwd, void* w_dgrad, int dtype_fwd, int dtype_dgrad, const float* scale_dev,
+                                void* stream) {
   SG_CHECK_ARG(master && (w_fwd || w_dgrad) && n_taps >= 1 && nc % 64 == 0 && kc % 64 == 0);
   SG_CHECK_ARG(!alpha || (alpha_from >= 0 && alpha_from < kc));
   dim3 grid(kc / 64, nc / 64, n_taps);
   emit_operands_kernel<<<grid, 256, 0, ST>>>(master, n_taps, nc, kc, alpha, alpha_from, w_fwd, w_dgrad, dtype_fwd,
-                                             dtype_dgrad);
+                                             dtype_dgrad, scale_dev);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

@@ -107,6 +107,7 @@ struct WParams {
   TapRanges tr;
   float* dw; int dw_tap0;
   int batch, ksplit;
+  const float* out_scale;
 };
 
 // dWp[d+4][n][kc] += sum_{b,m} G[b,m,n] * A[b,m+d,kc]
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(256) tapgemm_w_ffma(WParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + ty * 4 + i, kc = kc0 + tx * 4 + j;
-      atomicAdd(p.dw + ((int64_t)(ti - p.dw_tap0) * p.nc + n) * p.kc + kc, acc[i][j]);
+      atomicAdd(p.dw + ((int64_t)(ti - p.dw_tap0) * p.nc + n) * p.kc + kc,
+                acc[i][j] * (p.out_scale ? *p.out_scale : 1.f));
     }
 }
 
@@ -210,6 +212,7 @@ int tapgemm_w_ffma_launch(const sg_tapgemm_w* q, cudaStream_t st) {
     p.tr.n_lo[i] = q->tap_n_lo[i]; p.tr.n_hi[i] = q->tap_n_hi[i];
   }
   p.dw = q->dw; p.dw_tap0 = q->dw_tap0; p.batch = q->batch; p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
+  p.out_scale = q->out_scale;
   dim3 grid(q->kc / TM, (q->nc / TNn) * (q->d_hi - q->d_lo + 1), p.ksplit);
   tapgemm_w_ffma<<<grid, 256, 0, st>>>(p);
   SG_CHECK_LAUNCH();

@@ -1124,6 +1124,7 @@ struct WTcParams {
   int n_tiles, k_tiles;      // nc/128, kc/TK
   int row_chunks, b_chunks;  // ceil(g_rows/PR), ceil(batch/PB)
   uint32_t idesc;
+  const float* out_scale;    // device scalar applied to the products before the atomic accumulation, or nullptr
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -1251,6 +1252,7 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
       float* o = p.dw + ((int64_t)(d + 4 - p.dw_tap0) * p.nc + n0 + row) * p.kc + kc0;
       const int ti = d + 4;
+      const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
       for (int c0 = 0; c0 < p.TK; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
@@ -1260,8 +1262,8 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         if (n0 + row < p.tr.n_lo[ti] || n0 + row >= p.tr.n_hi[ti]) continue;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          red_add_v4(o + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                     __uint_as_float(r[j + 3]));
+          red_add_v4(o + c0 + j, osc * __uint_as_float(r[j]), osc * __uint_as_float(r[j + 1]),
+                     osc * __uint_as_float(r[j + 2]), osc * __uint_as_float(r[j + 3]));
       }
       tc_fence_before();
       mbar_arrive(&ctl->tmem_empty[acc]);
@@ -1510,6 +1512,7 @@ int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st) {
   p.ksplit = q->ksplit < 1 ? 1 : q->ksplit;
   if (p.ksplit > pos_steps) p.ksplit = pos_steps;
   p.idesc = make_idesc(q->g_dtype == SG_BF16, q->a_dtype == SG_BF16, 1, 1, 128, p.TK);
+  p.out_scale = q->out_scale;
   CUtensorMap tmG, tmA0, tmA1;
   int rc = make_map3(&tmG, q->g, q->g_dtype, q->nc, q->g_rows, q->batch, p.PR, p.PB);
   if (rc) return rc;

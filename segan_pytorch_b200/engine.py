@@ -359,8 +359,9 @@ def run_f(a0, a1, a_rows, a_halo, a_dtype, w, w_dtype, kc, nc, taps, out, out_dt
 
 
 def run_w(g, g_rows, g_dtype, a0, a1, a_rows, a_halo, a_dtype, kc, nc, taps, dw, batch, d_lo=-4, d_hi=4,
-          dw_tap0=0, ksplit=1, backend=None, a0_c=None, a1_c=0):
+          dw_tap0=0, ksplit=1, backend=None, a0_c=None, a1_c=0, out_scale=None):
     q = TapGemmW()
+    q.out_scale = _p(out_scale)
     q.g, q.g_rows, q.g_dtype = _p(g), g_rows, g_dtype
     q.a0, q.a1 = _p(a0), _p(a1)
     q.a0_c = kc if a0_c is None else a0_c
@@ -469,6 +470,11 @@ def set_grad_dtype(kind, loss_scale=None):
         GT, GS = F16, SG_F16
         LOSS_SCALE = float(os.environ.get("SEGAN_B200_LOSS_SCALE", "1024")) if loss_scale is None else float(loss_scale)
     _lib.load().sg_set_grad_dtype(GS)
+
+
+def twins_or_alias(alias, twins):
+    """A forward pass that a weight-gradient computation will follow (its saved activations feed tapgemm_w)."""
+    return bool(alias or twins)
 
 
 def grad_twins():
@@ -600,6 +606,8 @@ class _NetEngine:
         self._mirror_stale, self._ops_stale = False, True
         self._grad_dirty, self._alpha_fixed = False, False
         self._seen = self._versions()
+        if hasattr(self, "sn"):
+            self.sn = {}                     # spectral-norm state is rebuilt from the module's buffers
 
     def _versions(self):
         return tuple(p._version for _, p in self.module.named_parameters())
@@ -727,13 +735,13 @@ class _NetEngine:
                 self.pack()
             self._ops_stale = False
 
-    def emit(self, l, alpha=None):
-        """Forward + data-gradient operand of packed layer `l` out of its master."""
+    def emit(self, l, alpha=None, scale=None):
+        """Forward + data-gradient operand of packed layer `l` out of its master (scale: device scalar, 1/sigma)."""
         dev = self.flat.device
         wf = self.buf.get(l.f_key, (l.T, l.nc, l.kc), F16, dev)
         wd = self.buf.get(l.dg_key, (l.T, l.kc, l.nc), GT, dev)
         _lib.call("sg_emit_operands", _p(self.mview(l)), l.T, l.nc, l.kc, _p(alpha), l.alpha_from, _p(wf), _p(wd),
-                  SG_F16, GS, _stream())
+                  SG_F16, GS, _p(scale), _stream())
         self.packed[l.f_key], self.packed[l.dg_key] = wf, wd
         self._mark_packed(l.f_key)
 
@@ -771,14 +779,24 @@ class GeneratorEngine(_NetEngine):
 
     # -- weights ----------------------------------------------------------------------------
     def packed_layers(self):
+        """Bucket order = the order in which a backward pass completes the gradients, so that the data-parallel
+        all-reduce can leave in contiguous chunks while the rest of the backward still runs (grad_chunks):
+        decoder (dec3 .. dec0 finish first), then enc4, then enc3 .. enc1 and the small parameters."""
         fm, nl = self.fmaps, self.nl
-        ls = [PackedLayer("enc_blocks.%d.conv.weight" % l, 0, fm[l], fm[l - 1], 0, "Wf%d" % l, "Wdg%d" % l)
-              for l in range(1, nl)]
+        ls = []
         for l in range(nl - 1):
             ls.append(PackedLayer("dec_blocks.%d.deconv.weight" % l, 1, self.dec_cout(l), self.dec_cin(l), 0,
                                   "Wt%d" % l, "Wtd%d" % l,
                                   alpha_name=("alpha_%d.skip_k" % (nl - 1 - l)) if l > 0 else None))
+        ls += [PackedLayer("enc_blocks.%d.conv.weight" % l, 0, fm[l], fm[l - 1], 0, "Wf%d" % l, "Wdg%d" % l)
+               for l in range(nl - 1, 0, -1)]
         return ls
+
+    def grad_chunks(self):
+        """[(offset, numel)]: decoder weights (complete after dec0's weight gradient) | enc_{nl-1} | the rest."""
+        a = sum(l.numel for l in self.layers[:self.nl - 1])
+        b = a + self.layers[self.nl - 1].numel
+        return [(0, a), (a, b - a), (b, self.grad.numel() - b)]
 
     def pack(self):
         dev = self.flat.device
@@ -985,8 +1003,10 @@ class GeneratorEngine(_NetEngine):
         return hall
 
     # -- backward ---------------------------------------------------------------------------
-    def backward(self, ctx, gy, accumulate=False):
-        """gy: (B,1,L) fp32 gradient w.r.t. the output.  Fills self.grad (flat, reference layout)."""
+    def backward(self, ctx, gy, accumulate=False, reducer=None):
+        """gy: (B,1,L) fp32 gradient w.r.t. the output.  Fills self.grad (the packed bucket).
+        reducer: optional model.GradReducer -- chunk i of grad_chunks() is all-reduced on the communication stream
+        as soon as its last weight-gradient GEMM has been enqueued, while the rest of the backward runs."""
         fm, nl, st, buf = self.fmaps, self.nl, _stream(), self.buf
         B, L, Lq = ctx["B"], ctx["L"], ctx["Lq"]
         a, hp, ad, dd = ctx["a"], ctx["hp"], ctx["ad"], ctx["dd"]
@@ -1061,6 +1081,8 @@ class GeneratorEngine(_NetEngine):
                 run_w(g_ad, lin, GS, s0, s1, lin, 0, GS, cin, 4 * cout, taps, dwp, B,
                       ksplit=wgrad_ksplit(B * lin, n_tiles, taps, cin, 4 * cout), a0_c=c0, a1_c=c1,
                       backend=self.backend)
+                if l == 0 and reducer is not None:
+                    reducer.ready(0, launch=True)              # every decoder weight gradient has been enqueued
             # data gradient w.r.t. cat(s0, s1); block 0 only needs the encoder half (z gets no gradient)
             g_in = buf.get("g.gin%d" % l, (B, lin, cin), GT, dev)
             run_f(g_ad, None, lin, 0, GS, self.packed["Wtd%d" % l], GS, 4 * cout, cin,
@@ -1105,11 +1127,15 @@ class GeneratorEngine(_NetEngine):
                 n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
                 run_w(g_a, Lq[l], GS, ctx["hpb"][l - 1], None, Lq[l], 4, GS, 4 * cin, cout, taps, dwp_l, B,
                       ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps, 4 * cin, cout), backend=self.backend)
+                if l == nl - 1 and reducer is not None:
+                    reducer.ready(1, launch=True)
             g_hp = buf.get("g.ghp%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), GT, dev)
             run_f(g_a, None, Lq[l], 0, GS, self.packed["Wdg%d" % l], GS, cout, 4 * cin,
                   tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_hp, GS, Lq[l], 4, -4, Lq[l] + 4, B,
                   backend=self.backend)
         join_side(side)
+        if reducer is not None:
+            reducer.ready(2, launch=True)
         return self.grad
 
 
@@ -1124,27 +1150,124 @@ class DiscriminatorEngine(_NetEngine):
         self.packed = {}
         self.eps = 1e-5
         self.momentum = 0.1
+        # norm_type='snorm' (modules.py:12-14, discriminator.py:118-121): no BatchNorm; every conv, fc.0, fc.2 and the
+        # fc.3 PReLU slope vector are divided by their spectral norm, re-estimated by one power iteration per
+        # training forward (sg_snorm_sigma).  The parameters are then called weight_orig.
+        self.snorm = getattr(module, "norm_type", "bnorm") == "snorm"
+        self.wsfx = "_orig" if self.snorm else ""
+        self.sn = {}                # name -> spectral-norm state (see _sn_state)
+        self._sn_pass = 0           # forward passes with parameter gradients since the last zero_grad
+        self._sn_slot = 0           # slot of the pass whose operands are current
         # lane 1: a second workspace so that one pass (the real pair of a train step) can run on its own stream
         # concurrently with another pass of the same network.  Both lanes accumulate into the SAME gradient
         # bucket: every parameter-gradient writer is atomic (red.add in the wgrad epilogue, atomicAdd elsewhere).
         self.buf1 = _Buffers()
 
     def packed_layers(self):
+        """Bucket order = gradient completion order of a backward pass: fc.0, enc4 | enc3 .. enc1, small."""
         fm = self.fmaps
-        ls = [PackedLayer("enc_blocks.%d.conv.weight" % l, 0, fm[l], fm[l - 1], 0, "Wf%d" % l, "Wdg%d" % l)
-              for l in range(1, self.nl)]
-        nout, kin = self._param("fc.0.weight").shape
-        ls.append(PackedLayer("fc.0.weight", 2, nout, fm[-1], kin // fm[-1], "W1p", "W1dg"))
+        nout, kin = self._param("fc.0.weight" + self.wsfx).shape
+        ls = [PackedLayer("fc.0.weight" + self.wsfx, 2, nout, fm[-1], kin // fm[-1], "W1p", "W1dg")]
+        ls += [PackedLayer("enc_blocks.%d.conv.weight%s" % (l, self.wsfx), 0, fm[l], fm[l - 1], 0, "Wf%d" % l, "Wdg%d" % l)
+               for l in range(self.nl - 1, 0, -1)]
         return ls
+
+    # -- spectral norm ----------------------------------------------------------------------------
+    SN_SLOTS = 5                    # up to 4 accumulating passes per optimiser step (WSEGAN) + 1 gradient-free pass
+
+    def _sn_names(self):
+        return (["enc_blocks.%d.conv.weight_orig" % l for l in range(self.nl)] +
+                ["fc.0.weight_orig", "fc.2.weight_orig", "fc.3.weight_orig"])
+
+    def _sn_state(self, name):
+        """Spectral-norm state of one weight: the power-iteration vectors (u: the module's buffer itself; v: packed
+        slots for the tap-GEMM layers, the module's buffer for the small ones), per-pass copies of both, the
+        per-pass [unused, unused, sigma, 1/sigma] scalars and the per-pass sigma-term coefficients."""
+        st = self.sn.get(name)
+        if st is not None:
+            return st
+        dev = self.flat.device
+        mod = dict(self.module.named_buffers())
+        base = name[:-len("weight_orig")]
+        u, vref = mod[base + "weight_u"], mod[base + "weight_v"]
+        pl = self.by_name.get(name)
+        if pl is not None:
+            T, nc, kc = pl.T, pl.nc, pl.kc
+            # v lives in packed slots: the same transform that packs a weight with one output channel
+            v = pack_reference(pl.kind, vref.reshape(1, -1) if pl.kind == 2 else vref.reshape(1, pl.c_in, KW), 1,
+                               pl.c_in, pl.t_len).reshape(-1).contiguous()
+        else:
+            shape = self.index[name][2]
+            T, nc, kc = 1, shape[0], int(torch.Size(shape[1:]).numel()) if len(shape) > 1 else 1
+            v = vref
+        P = self.SN_SLOTS
+        st = self.sn[name] = dict(T=T, nc=nc, kc=kc, u=u, v=v, vref=vref, pl=pl,
+                                  scal=torch.zeros(P, 4, device=dev), u_p=torch.zeros(P, nc, device=dev),
+                                  v_p=torch.zeros(P, T * kc, device=dev), coef=torch.zeros(P, device=dev),
+                                  work=torch.zeros(nc + 4, device=dev))
+        return st
+
+    def _sn_master(self, name):
+        pl = self.by_name.get(name)
+        return self.mview(pl) if pl is not None else self.pview(name)
+
+    def _sn_iterate(self, training, slot):
+        """sigma of every normalised weight for the coming pass (one power iteration when training), kept in pass
+        slot `slot` together with copies of the vectors: the backward of that pass and the sigma terms need them."""
+        st_ = _stream()
+        for name in self._sn_names():
+            st = self._sn_state(name)
+            _lib.call("sg_snorm_sigma", _p(self._sn_master(name)), st["T"], st["nc"], st["kc"], _p(st["u"]), _p(st["v"]),
+                      _p(st["scal"][slot]), _p(st["work"]), 1 if training else 0, st_)
+            st["u_p"][slot].copy_(st["u"])
+            st["v_p"][slot].copy_(st["v"].reshape(-1))
+        self._sn_slot = slot
+
+    def sn_inv_sigma(self, name, slot=None):
+        """Device scalar 1 / sigma of `name` for pass slot `slot` (default: the current one)."""
+        return self._sn_state(name)["scal"][self._sn_slot if slot is None else slot][3:4]
+
+    def sync_to_reference(self):
+        super().sync_to_reference()
+        for name, st in self.sn.items():          # packed v -> the module's reference-layout buffer
+            pl = st["pl"]
+            if pl is not None:
+                st["vref"].copy_(unpack_reference(pl.kind, st["v"], 1, pl.c_in, pl.t_len).reshape(-1))
+
+    def zero_grad(self):
+        super().zero_grad()
+        self._sn_pass = 0
+
+    def finish_grads(self):
+        """snorm: the sigma terms of every accumulating pass of this step, one sweep per tap-GEMM layer
+        (dW -= sum_p coef_p u_p v_p^T; the G / sigma_p part was applied by the weight-gradient GEMMs)."""
+        if self._alpha_fixed:
+            return
+        if self.snorm and self._sn_pass > 0:
+            for pl in self.layers:
+                stt = self._sn_state(pl.name)
+                _lib.call("sg_snorm_rank1", _p(self.mgrad(pl)), pl.T, pl.nc, pl.kc, self._sn_pass, _p(stt["u_p"]),
+                          _p(stt["v_p"]), _p(stt["coef"]), _stream())
+        self._alpha_fixed = True
+
+    def grad_chunks(self):
+        a = self.layers[0].numel + self.layers[1].numel
+        return [(0, a), (a, self.grad.numel() - a)]
 
     def pack(self):
         dev = self.flat.device
-        wcol = wave_col_weights(self.pview("enc_blocks.0.conv.weight"), dev)
+        w0 = self.pview("enc_blocks.0.conv.weight" + self.wsfx)
+        if self.snorm:
+            w0 = w0 * self.sn_inv_sigma("enc_blocks.0.conv.weight_orig")
+            # the head's small normalised tensors, consumed by sg_fc_tail_fwd / _bwd
+            self.packed["fc2n"] = (self.pview("fc.2.weight_orig") * self.sn_inv_sigma("fc.2.weight_orig")).contiguous()
+            self.packed["fc3n"] = (self.pview("fc.3.weight_orig") * self.sn_inv_sigma("fc.3.weight_orig")).contiguous()
+        wcol = wave_col_weights(w0, dev)
         self.packed["Wcol0"] = wcol.half().contiguous()
         self.packed["WcolT0"] = wcol.t().to(GT).contiguous()
         self._mark_packed("small")
         for pl in self.layers:
-            self.emit(pl)
+            self.emit(pl, scale=self.sn_inv_sigma(pl.name) if self.snorm else None)
             if pl.kind == 2:       # the Linear's operands are used as 2-D [nout][kin] / [kin][nout]
                 self.packed["W1p"] = self.packed["W1p"].view(pl.nc, pl.kc)
                 self.packed["W1dg"] = self.packed["W1dg"].view(pl.kc, pl.nc)
@@ -1157,6 +1280,19 @@ class DiscriminatorEngine(_NetEngine):
         _require_cuda(x0, x1)
         alias = twins and not grad_twins()
         twins = twins and grad_twins()
+        sn_slot = None
+        if self.snorm:
+            # a new sigma (training: after one more power iteration) for this pass -> the operands are re-emitted
+            self.bind()
+            self.notice_external_writes()
+            if training and twins_or_alias(alias, twins):
+                sn_slot = self._sn_pass
+                assert sn_slot < self.SN_SLOTS - 1, "more accumulating D passes per optimiser step than SN_SLOTS"
+                self._sn_pass += 1
+            else:
+                sn_slot = self.SN_SLOTS - 1               # gradient-free pass (G step, inference)
+            self._sn_iterate(training, sn_slot)
+            self._ops_stale = True
         self.ensure_packed()
         self.wait_packed("small")
         m = self.module
@@ -1166,17 +1302,18 @@ class DiscriminatorEngine(_NetEngine):
         x0 = x0.contiguous().float()
         x1 = x1.contiguous().float()
         Lq = [L // 4 ** (l + 1) for l in range(nl)]
-        assert Lq[-1] * fm[-1] == self.pview("fc.0.weight").shape[1], "D expects L = 16384"
+        assert Lq[-1] * fm[-1] == self._param("fc.0.weight" + self.wsfx).shape[1], "D expects L = 16384"
         if shifts_dev is not None and not wave_on_tensor_cores():
             raise _lib.SeganB200Error("device-resident phase shifts need the tensor-core waveform route")
 
         def rptr(i):
             return None if shifts_dev is None else C.c_void_p(shifts_dev.data_ptr() + 4 * i)
         a, hp, ss, mi, hpb = [None] * nl, [None] * nl, [None] * nl, [None] * nl, [None] * nl
-        stats = stat_arena(buf, "d.stats", [(SL, 2, fm[l]) for l in range(nl)], dev) if training else None
+        bnorm = not self.snorm
+        stats = stat_arena(buf, "d.stats", [(SL, 2, fm[l]) for l in range(nl)], dev) if (training and bnorm) else None
         # BatchNorm statistics in the conv epilogue (tcgen05 CTA-pair kernel; needs >= 2 M tiles: B * L/4 >= 256)
         eff_backend = default_backend() if self.backend is None else self.backend
-        fuse_stats = (training and FUSE_BN_STATS and eff_backend == BACKEND_TCGEN05 and B * Lq[-1] >= 256)
+        fuse_stats = (training and bnorm and FUSE_BN_STATS and eff_backend == BACKEND_TCGEN05 and B * Lq[-1] >= 256)
         for l in range(nl):
             cout = fm[l]
             a[l] = buf.get("d.a%d" % l, (B, Lq[l], cout), F16, dev)
@@ -1194,8 +1331,11 @@ class DiscriminatorEngine(_NetEngine):
                       d_lo=0, d_hi=0, w_tap0=4, backend=self.backend, stats=stats[0] if fuse_stats else None)
             elif l == 0:
                 colb0 = None
+                w0 = self.pview("enc_blocks.0.conv.weight" + self.wsfx)
+                if self.snorm:
+                    w0 = (w0 * self.sn_inv_sigma("enc_blocks.0.conv.weight_orig")).contiguous()
                 _lib.call("sg_wave_conv_fwd", _p(x0), _p(x1), 2, B, L, int(shifts[0]),
-                          _p(self.pview("enc_blocks.0.conv.weight")), _p(bias), cout, _p(a[0]), None, None, st)
+                          _p(w0), _p(bias), cout, _p(a[0]), None, None, st)
             else:
                 cin = fm[l - 1]
                 self.wait_packed("Wf%d" % l)
@@ -1203,9 +1343,12 @@ class DiscriminatorEngine(_NetEngine):
                       tap_ranges("conv_fwd", cin, 4 * cin, cout), a[l], SG_F16, Lq[l], 0, 0, Lq[l], B,
                       bias=bias, bias_mod=cout, backend=self.backend, stats=stats[l] if fuse_stats else None)
             bn = m.enc_blocks[l].norm
-            ss[l] = buf.get("d.ss%d" % l, (2, cout), F32, dev)
-            mi[l] = buf.get("d.mi%d" % l, (2, cout), F32, dev)
-            if training:
+            if bnorm:
+                ss[l] = buf.get("d.ss%d" % l, (2, cout), F32, dev)
+                mi[l] = buf.get("d.mi%d" % l, (2, cout), F32, dev)
+            if not bnorm:
+                pass                                   # snorm: conv -> PReLU, no statistics
+            elif training:
                 st2 = stats[l]
                 if not (fuse_stats and (l > 0 or wave_on_tensor_cores())):
                     _lib.call("sg_bn_stats", _p(a[l]), SG_F16, B * Lq[l], cout, _p(st2), st)
@@ -1240,17 +1383,19 @@ class DiscriminatorEngine(_NetEngine):
         z1 = buf.get("d.z1", (B, 256), F32, dev)
         z2 = buf.get("d.z2", (B, 128), F32, dev)
         logit = torch.empty(B, 1, dtype=F32, device=dev)
+        w2 = self.packed["fc2n"] if self.snorm else self.pview("fc.2.weight")
+        s3 = self.packed["fc3n"] if self.snorm else self.pview("fc.3.weight")
         _lib.call("sg_fc_tail_fwd", _p(acc), _p(self.pview("fc.0.bias")), _p(self.pview("fc.1.weight")),
-                  _p(self.pview("fc.2.weight")), _p(self.pview("fc.2.bias")), _p(self.pview("fc.3.weight")),
+                  _p(w2), _p(self.pview("fc.2.bias")), _p(s3),
                   _p(self.pview("fc.4.weight")), _p(self.pview("fc.4.bias")), B, _p(z1), _p(z2), _p(logit), st)
         self.packs_consumed()
         ctx = dict(x0=x0, x1=x1, B=B, L=L, Lq=Lq, a=a, hp=hp, hpb=hpb, colb=colb0, ss=ss, mi=mi, z1=z1, z2=z2,
-                   logit=logit, lane=lane, shifts_dev=shifts_dev,
+                   logit=logit, lane=lane, shifts_dev=shifts_dev, acc=acc, w2=w2, s3=s3, sn_slot=sn_slot,
                    shifts=[int(s) for s in shifts])
         return logit, ctx
 
     def backward(self, ctx, target, weight=1.0, param_grads=True, input_grad=None, loss_out=None, g_logit=None,
-                 input_grad1=None):
+                 input_grad1=None, reducer=None, reduce_now=True):
         """Backward of  weight * mean((logit - target)^2)  (nn.MSELoss, model.py:298,305,316).
         param_grads: accumulate parameter gradients into self.grad (D steps) or skip them (G step).
         input_grad: optional fp32 (B,1,L) buffer that receives (+=) the gradient w.r.t. x0."""
@@ -1272,20 +1417,45 @@ class DiscriminatorEngine(_NetEngine):
         g_z1 = buf.get("d.gz1", (B, 256), GT, dev)
         ws = buf.get("d.fcws", (B * (1 + 128 + 256 + 256),), F32, dev)
         gv = (lambda n: _p(gview(n))) if param_grads else (lambda n: None)
+        sn, slot, wsfx = self.snorm, ctx.get("sn_slot"), self.wsfx
+        sn_small = {}             # snorm: per-pass scratch gradients of the small normalised tensors
+        if sn and param_grads:
+            for nm in ("fc.2.weight_orig", "fc.3.weight_orig", "enc_blocks.0.conv.weight_orig"):
+                sn_small[nm] = buf.get("d.sng." + nm, self.index[nm][2], F32, dev, zero=True)
+        g_w2 = _p(sn_small["fc.2.weight_orig"]) if sn_small else gv("fc.2.weight")
+        g_s3 = _p(sn_small["fc.3.weight_orig"]) if sn_small else gv("fc.3.weight")
         _lib.call("sg_fc_tail_bwd", _p(ctx["z1"]), _p(ctx["z2"]), _p(ctx["logit"]), _p(g_logit), float(target),
                   float(weight),
-                  _p(self.pview("fc.1.weight")), _p(self.pview("fc.2.weight")), _p(self.pview("fc.3.weight")),
+                  _p(self.pview("fc.1.weight")), _p(ctx["w2"]), _p(ctx["s3"]),
                   _p(self.pview("fc.4.weight")), B, _p(loss_out), _p(g_z1), _p(ws),
-                  gv("fc.0.bias"), gv("fc.1.weight"), gv("fc.2.weight"), gv("fc.2.bias"), gv("fc.3.weight"),
+                  gv("fc.0.bias"), gv("fc.1.weight"), g_w2, gv("fc.2.bias"), g_s3,
                   gv("fc.4.weight"), gv("fc.4.bias"), float(LOSS_SCALE), st)
+
+        def sn_fix_small(nm):
+            """scratch gradient w.r.t. the normalised small tensor -> gradient w.r.t. weight_orig, into the bucket."""
+            stt = self._sn_state(nm)
+            _lib.call("sg_snorm_grad", _p(sn_small[nm]), _p(self.pview(nm)), 1, stt["nc"], stt["kc"], _p(stt["u_p"][slot]),
+                      _p(stt["v_p"][slot]), _p(stt["scal"][slot]), _p(stt["work"][stt["nc"]:]), _stream())
+            gview(nm).add_(sn_small[nm])
+        if sn_small:
+            sn_fix_small("fc.2.weight_orig")
+            sn_fix_small("fc.3.weight_orig")
         # weight-gradient chain (wgrad GEMM + unpack) of every layer: side stream 0, next to the
         # data-gradient chain (dgrad GEMM -> BatchNorm/PReLU backward) on the caller's stream
         side = side_stream(dev, 3 if lane == 1 else 0) if param_grads else None
         if param_grads:
-            dw1 = self.mgrad(self.by_name["fc.0.weight"])
+            fc0 = self.by_name["fc.0.weight" + wsfx]
+            dw1 = self.mgrad(fc0)
+            osc = None
+            if sn:
+                # <dL/dW~, W~> of fc.0 = <g_z1, fc0 output without bias>; coefficient of this pass's sigma term
+                stt = self._sn_state(fc0.name)
+                gz1f = ws[B * 129:B * 129 + B * 256]
+                stt["coef"][slot] = (gz1f * ctx["acc"].reshape(-1)).sum() * stt["scal"][slot][3]
+                osc = stt["scal"][slot][3:4]
             with on_side(side):
                 run_w(g_z1, 1, GS, ctx["hpb"][-1], None, 1, 0, GS, kin, 256, tap_ranges("full", 0, kin, 256),
-                      dw1, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend)
+                      dw1, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=1, backend=self.backend, out_scale=osc)
         g_h = buf.get("d.gh%d" % (nl - 1), (B, Lq[-1], fm[-1]), GT, dev)
         run_f(g_z1, None, 1, 0, GS, self.packed["W1dg"], GS, 256, kin, tap_ranges("full", 0, 256, kin),
               g_h, GS, 1, 0, 0, 1, B, d_lo=0, d_hi=0, w_tap0=4, backend=self.backend)
@@ -1299,33 +1469,54 @@ class DiscriminatorEngine(_NetEngine):
             g_a = buf.get("d.ga%d" % l, (B, Lq[l], cout), GT, dev)
             redl = reds[l]
             slope = self.pview("enc_blocks.%d.act.weight" % l)
-            _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
-                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
-            _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
-                      _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
-            if param_grads:
+            if sn:
+                # no norm layer: one pass gives the final gradient of the pre-activation (as in the Generator)
+                _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
+                          None, None, _p(slope), ACT_PRELU, _p(redl), _p(g_a), st)
+                if param_grads:
+                    bias_l = self.pview("enc_blocks.%d.conv.bias" % l) if m.bias else None
+                    _lib.call("sg_stat_grads", _p(redl), cout, 3, _p(gview("enc_blocks.%d.act.weight" % l)),
+                              _p(gview("enc_blocks.%d.conv.bias" % l)) if m.bias else None, None, st)
+                    if l > 0:        # sigma-term coefficient of this pass (layer 0 is a small tensor, fixed below)
+                        stt = self._sn_state("enc_blocks.%d.conv.weight_orig" % l)
+                        _lib.call("sg_snorm_coef", _p(redl), _p(bias_l), cout, _p(stt["scal"][slot]),
+                                  _p(stt["coef"][slot:slot + 1]), st)
+            else:
+                _lib.call("sg_act_bwd_reduce", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
+                          _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), None, st)
+                _lib.call("sg_act_bwd_apply", _p(g_h), cout, halo, roll, rp, None, 0, _p(a[l]), SG_F16, B, Lq[l], cout,
+                          _p(ss[l]), _p(mi[l]), _p(slope), ACT_PRELU, _p(redl), 1, _p(g_a), st)
+            if param_grads and not sn:
                 _lib.call("sg_stat_grads", _p(redl), cout, 3, _p(gview("enc_blocks.%d.act.weight" % l)),
                           _p(gview("enc_blocks.%d.norm.bias" % l)),
                           _p(gview("enc_blocks.%d.norm.weight" % l)), st)
                 # conv biases feed BatchNorm: their gradient is exactly zero (the BN backward output has
                 # zero mean per channel); the reference only sees rounding noise there.  Left at zero
                 # (SEGAN_B200_EXACT_BIAS_GRAD=1 computes the column sums anyway).
-                if m.bias and os.environ.get("SEGAN_B200_EXACT_BIAS_GRAD") == "1":
+                if m.bias and not sn and os.environ.get("SEGAN_B200_EXACT_BIAS_GRAD") == "1":
                     _lib.call("sg_colsum", _p(g_a), GS, B * Lq[l], cout, cout,
                               _p(gview("enc_blocks.%d.conv.bias" % l)), 1, _p(tmp), st)
             if l == 0:
-                w0 = self.pview("enc_blocks.0.conv.weight")
+                w0 = self.pview("enc_blocks.0.conv.weight" + wsfx)
+                if sn:
+                    w0 = (w0 * self.sn_inv_sigma("enc_blocks.0.conv.weight_orig", slot)).contiguous()
+                g_w0 = (sn_small["enc_blocks.0.conv.weight_orig"] if sn_small else gview("enc_blocks.0.conv.weight")) \
+                    if param_grads else None
                 if param_grads and ctx.get("colb") is not None:
                     dwq = buf.get("d.dwq0", (128 * 128,), F32, dev)
                     with on_side(side):
                         run_w(g_a, Lq[0] // 2, GS, ctx["colb"], None, Lq[0] // 2, 0, GS, 128, 128,
                               tap_ranges("full", 0, 128, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=148,
                               backend=self.backend)
-                        _lib.call("sg_wave_wgrad_fold", _p(dwq), 2, _p(gview("enc_blocks.0.conv.weight")), _stream())
+                        _lib.call("sg_wave_wgrad_fold", _p(dwq), 2, _p(g_w0), _stream())
+                        if sn_small:
+                            sn_fix_small("enc_blocks.0.conv.weight_orig")
                 elif param_grads:
                     with on_side(side):
                         _lib.call("sg_wave_conv_wgrad", _p(ctx["x0"]), _p(ctx["x1"]), 2, B, L, shifts[0], _p(g_a),
-                                  cout, _p(gview("enc_blocks.0.conv.weight")), None, _stream())
+                                  cout, _p(g_w0), None, _stream())
+                        if sn_small:
+                            sn_fix_small("enc_blocks.0.conv.weight_orig")
                 if (input_grad is not None or input_grad1 is not None) and wave_on_tensor_cores():
                     P2 = buf.get("d.P2", (B, Lq[0], 64), GT, dev)
                     run_f(g_a, None, Lq[0], 0, GS, self.packed["WcolT0"], GS, 64, 64,
@@ -1344,15 +1535,24 @@ class DiscriminatorEngine(_NetEngine):
                 break
             cin = fm[l - 1]
             if param_grads:
-                dwp_l = self.mgrad(self.by_name["enc_blocks.%d.conv.weight" % l])
+                pl_l = self.by_name["enc_blocks.%d.conv.weight%s" % (l, wsfx)]
+                dwp_l = self.mgrad(pl_l)
+                osc = self.sn_inv_sigma(pl_l.name, slot) if sn else None
                 with on_side(side):
                     n_tiles = 9 * (cout // 128) * max(1, 4 * cin // 256)
                     taps_w = tap_ranges("conv_fwd", cin, 4 * cin, cout)
                     run_w(g_a, Lq[l], GS, ctx["hpb"][l - 1], None, Lq[l], 4, GS, 4 * cin, cout, taps_w, dwp_l, B,
-                          ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps_w, 4 * cin, cout), backend=self.backend)
+                          ksplit=wgrad_ksplit(B * Lq[l], n_tiles, taps_w, 4 * cin, cout), backend=self.backend,
+                          out_scale=osc)
+                    if l == nl - 1 and reducer is not None:
+                        # fc.0 and enc4 of THIS pass are enqueued; the chunk leaves once every accumulating pass
+                        # (real / fake / misaligned ...) has said so: reduce_now marks the last one
+                        reducer.ready(0, launch=reduce_now)
             g_h = buf.get("d.gh%d" % (l - 1), (B, Lq[l] + 8, 4 * cin), GT, dev)
             run_f(g_a, None, Lq[l], 0, GS, self.packed["Wdg%d" % l], GS, cout, 4 * cin,
                   tap_ranges("conv_dgrad", cin, cout, 4 * cin), g_h, GS, Lq[l], 4, -4, Lq[l] + 4, B,
                   backend=self.backend)
         join_side(side)
+        if reducer is not None and param_grads:
+            reducer.ready(1, launch=reduce_now)
         return grad_flat

@@ -89,12 +89,17 @@ class Discriminator(Model):
                 nn.PReLU(128),
                 nn.Linear(128, 1)
             )
+            if norm_type == 'snorm':                   # discriminator.py:118-121 (incl. the PReLU(128) slope vector)
+                torch.nn.utils.spectral_norm(self.fc[0])
+                torch.nn.utils.spectral_norm(self.fc[2])
+                torch.nn.utils.spectral_norm(self.fc[3])
         else:
             raise NotImplementedError("pool_type %r is a SURVEY.md 8(f)-N4 'next' row; only 'none' is built"
                                       % (pool_type,))
         self.fmaps = list(fmaps)
         self.bias = bias
-        self._served = (ninputs == 2 and norm_type == 'bnorm' and kwidth == 31 and all(p == 4 for p in poolings)
+        self.norm_type = norm_type
+        self._served = (ninputs == 2 and norm_type in ('bnorm', 'snorm') and bias and kwidth == 31 and all(p == 4 for p in poolings)
                         and fmaps[0] == 64 and all(f % 64 == 0 for f in fmaps) and len(fmaps) >= 2)
         self._engine = None
 

@@ -190,6 +190,41 @@ def allreduce_grads(eng):
     return 1.0 / dist.get_world_size()
 
 
+# Data-parallel gradient exchange: one all-reduce per optimiser step over the network's gradient
+# bucket.  DP_OVERLAP (default on) sends the bucket in the 2-3 chunks of engine.grad_chunks() -- bucket order is
+# gradient-completion order -- on a communication stream as the backward pass produces them, so only the last,
+# small chunk is exposed; with CUDA graphs the collectives are captured into the step's single graph.
+DP_OVERLAP = os.environ.get("SEGAN_B200_DP_OVERLAP", "1").lower() not in ("0", "off", "no", "false")
+
+
+class GradReducer(object):
+    """Chunked, overlapped all-reduce (SUM) of one engine's gradient bucket."""
+
+    def __init__(self, eng):
+        self.eng = eng
+        self.comm = torch.cuda.Stream(device=eng.flat.device)
+        self.events = {}
+
+    def ready(self, i, launch):
+        """Called on the stream that just enqueued the last writer of chunk `i` for the current pass."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events.setdefault(i, []).append(ev)
+        if launch:
+            dist = _dist()
+            off, n = self.eng.grad_chunks()[i]
+            for e in self.events.pop(i):
+                self.comm.wait_event(e)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.eng.grad[off:off + n], op=dist.ReduceOp.SUM)
+
+    def finish(self):
+        """The optimiser's stream waits for every chunk; returns the gradient scale."""
+        assert not self.events, "gradient chunks marked ready but never reduced: %r" % list(self.events)
+        torch.cuda.current_stream().wait_stream(self.comm)
+        return 1.0 / _dist().get_world_size()
+
+
 class SEGAN(Model):
 
     def __init__(self, opts, name='SEGAN', generator=None, discriminator=None):
@@ -515,6 +550,16 @@ class SEGAN(Model):
             self.G.z = z
         return z
 
+    def _reducers(self):
+        """(D reducer, G reducer) of an overlapped data-parallel step, or (None, None)."""
+        if _dist() is None or not DP_OVERLAP:
+            return None, None
+        r = self.__dict__.get('_grad_reducers')
+        ge, de = self.G.engine, self.D.engine
+        if r is None or r[0].eng.grad is not de.grad or r[1].eng.grad is not ge.grad:
+            r = self.__dict__['_grad_reducers'] = (GradReducer(de), GradReducer(ge))
+        return r
+
     def train_step(self, clean, noisy, Gopt, Dopt, l1_weight, z=None, shifts3=None, losses=None):
         """clean / noisy: (B,1,L) fp32 cuda.  Returns the device tensor of the four losses
         [d_real, d_fake, g_adv, g_l1] (no host sync).
@@ -541,10 +586,11 @@ class SEGAN(Model):
                 losses = torch.zeros(4, dtype=torch.float32, device=dev)
             if z is None:
                 z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
-            Genh, gctx = self._seg_d(clean, noisy, z, shifts3, None, losses, Dopt, sample_z=False)
-            dscale = allreduce_grads(de)                                   # before model.py:308
-            self._seg_g(clean, noisy, Genh, gctx, shifts3, None, losses, l1_weight, Gopt, Dopt, dscale)
-            gscale = allreduce_grads(ge)                                   # before model.py:321
+            rd, rg = self._reducers()
+            Genh, gctx = self._seg_d(clean, noisy, z, shifts3, None, losses, Dopt, sample_z=False, reducer=rd)
+            dscale = rd.finish() if rd is not None else allreduce_grads(de)      # before model.py:308
+            self._seg_g(clean, noisy, Genh, gctx, shifts3, None, losses, l1_weight, Gopt, Dopt, dscale, reducer=rg)
+            gscale = rg.finish() if rg is not None else allreduce_grads(ge)      # before model.py:321
             Gopt.step(gscale)                                              # model.py:321
             return losses
         # ---- CUDA-graph schedule: refresh the static inputs, replay
@@ -573,11 +619,14 @@ class SEGAN(Model):
             # emitted by the previous replay of graph 2, so they are refreshed here
             ge.notice_external_writes()
             de.ensure_packed()
-            st.graphs[0].replay()
-            allreduce_grads(de)
-            st.graphs[1].replay()
-            allreduce_grads(ge)
-            st.graphs[2].replay()
+            if len(st.graphs) == 1:            # data-parallel with the collectives captured inside
+                st.graphs[0].replay()
+            else:
+                st.graphs[0].replay()
+                allreduce_grads(de)
+                st.graphs[1].replay()
+                allreduce_grads(ge)
+                st.graphs[2].replay()
             Dopt.t += 1
             Gopt.t += 1
             ge.master_updated()                # the replayed optimiser steps changed the masters in place
@@ -589,7 +638,7 @@ class SEGAN(Model):
         return st.losses
 
     # -- step segments (shared by the eager and the graph schedule) -------------------------------
-    def _seg_d(self, clean, noisy, z, shifts3, shifts_dev, losses, Dopt, sample_z):
+    def _seg_d(self, clean, noisy, z, shifts3, shifts_dev, losses, Dopt, sample_z, reducer=None):
         """G forward (model.py:295), D real (model.py:297-299) and D fake (model.py:303-306) passes.
         Schedule (engine.OVERLAP): the D(real) pass depends on neither G nor the fake pass, so it runs as
         lane 1 of the D engine (own workspace + gradient bucket) on side stream 2, concurrently with the
@@ -603,7 +652,8 @@ class SEGAN(Model):
         if sample_z:
             z.normal_()                                                    # generator.py:197-199 on the device
         Dopt.zero_grad()
-        rside = _engine.side_stream(dev, 2)
+        # (a spectrally normalised D re-emits its operands for every pass: its passes cannot overlap)
+        rside = None if de.snorm else _engine.side_stream(dev, 2)
         lane = 1 if rside is not None else 0
         fwd_real_done = None
         with _engine.on_side(rside):
@@ -611,17 +661,19 @@ class SEGAN(Model):
             if rside is not None:
                 fwd_real_done = torch.cuda.Event()
                 fwd_real_done.record()
-            de.backward(c, 1.0, 1.0, param_grads=True, loss_out=lptr(0))
+            de.backward(c, 1.0, 1.0, param_grads=True, loss_out=lptr(0), reducer=reducer, reduce_now=False)
         Genh, gctx = ge.forward(noisy, z)
         if fwd_real_done is not None:
             # BatchNorm running statistics are updated real pass first, fake pass second (model.py:297,303)
             torch.cuda.current_stream().wait_event(fwd_real_done)
         _, c = de.forward(Genh, noisy, shifts3[1], training=True, shifts_dev=sdev(1))
-        de.backward(c, 0.0, 1.0, param_grads=True, loss_out=lptr(1))
+        # the real lane's pass was enqueued above (python order), so its "ready" events exist: the fake pass launches
+        # each chunk once its own and the real lane's weight gradients of that chunk are enqueued
+        de.backward(c, 0.0, 1.0, param_grads=True, loss_out=lptr(1), reducer=reducer, reduce_now=True)
         _engine.join_side(rside)
         return Genh, gctx
 
-    def _seg_g(self, clean, noisy, Genh, gctx, shifts3, shifts_dev, losses, l1_weight, Gopt, Dopt, dscale):
+    def _seg_g(self, clean, noisy, Genh, gctx, shifts3, shifts_dev, losses, l1_weight, Gopt, Dopt, dscale, reducer=None):
         """D optimiser step (model.py:308), then the G update against the UPDATED D (model.py:313-320)."""
         ge, de = self.G.engine, self.D.engine
         B, _, L = clean.shape
@@ -636,7 +688,7 @@ class SEGAN(Model):
         de.backward(c, 1.0, 1.0, param_grads=False, input_grad=gy, loss_out=lptr(2))
         _lib.call("sg_l1_loss_bwd", _p(Genh), _p(clean.contiguous()), B * L, float(l1_weight), lptr(3), _p(gy), 1,
                   float(_engine.LOSS_SCALE), _stream())
-        ge.backward(gctx, gy)
+        ge.backward(gctx, gy, reducer=reducer)
 
     # -- CUDA graphs ------------------------------------------------------------------------------
     def _graph_state(self, clean, noisy, Gopt, Dopt, l1_weight, sample_z):
@@ -691,25 +743,57 @@ class SEGAN(Model):
         ge.mark_dirty()
         de.mark_dirty()
         n0 = _lib.launch_count
-        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         t_d, t_g = Dopt.t, Gopt.t
-        with torch.cuda.graph(g1):
-            Genh, gctx = self._seg_d(st.clean, st.noisy, st.z, shifts3, st.shifts, st.losses, Dopt, sample_z=sample_z)
-        with torch.cuda.graph(g2, pool=g1.pool()):
-            self._seg_g(st.clean, st.noisy, Genh, gctx, shifts3, st.shifts, st.losses, l1_weight, Gopt, Dopt, dscale)
-        with torch.cuda.graph(g3, pool=g1.pool()):
-            Gopt.step(dscale)
+        rd, rg = self._reducers()
+        graphs = None
+        if rd is not None and not getattr(self, '_dp_capture_failed', False):
+            # data parallel: ONE graph with the chunked all-reduces captured on the communication stream
+            # (thread-local capture mode: NCCL's watchdog thread keeps polling its events meanwhile)
+            g1 = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g1, capture_error_mode="thread_local"):
+                    Genh, gctx = self._seg_d(st.clean, st.noisy, st.z, shifts3, st.shifts, st.losses, Dopt,
+                                             sample_z=sample_z, reducer=rd)
+                    rd.finish()
+                    self._seg_g(st.clean, st.noisy, Genh, gctx, shifts3, st.shifts, st.losses, l1_weight, Gopt, Dopt,
+                                dscale, reducer=rg)
+                    rg.finish()
+                    Gopt.step(dscale)
+                graphs = (g1,)
+            except Exception as e:              # fall back to collectives between three graphs
+                print("segan_b200: capturing the NCCL all-reduces failed (%s): using eager collectives between graphs"
+                      % (str(e).splitlines()[0] if str(e) else type(e).__name__))
+                self._dp_capture_failed = True
+                rd.events.clear()
+                rg.events.clear()
+                torch.cuda.synchronize()
+                ge.mark_dirty()
+                de.mark_dirty()
+                Dopt.t, Gopt.t = t_d, t_g
+                _lib.launch_count = n0
+        if graphs is None:
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                Genh, gctx = self._seg_d(st.clean, st.noisy, st.z, shifts3, st.shifts, st.losses, Dopt, sample_z=sample_z)
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self._seg_g(st.clean, st.noisy, Genh, gctx, shifts3, st.shifts, st.losses, l1_weight, Gopt, Dopt, dscale)
+            with torch.cuda.graph(g3, pool=g1.pool()):
+                Gopt.step(dscale)
+            graphs = (g1, g2, g3)
         Dopt.t, Gopt.t = t_d, t_g               # capture only recorded the launches
         st.launches = _lib.launch_count - n0
         _lib.launch_count = n0
         st.keep = (Genh, gctx)                  # tensors of the graphs' private pool referenced by later nodes
-        st.graphs = (g1, g2, g3)
+        st.graphs = graphs
         # the step itself: replay
-        g1.replay()
-        allreduce_grads(de)
-        g2.replay()
-        allreduce_grads(ge)
-        g3.replay()
+        if len(graphs) == 1:
+            graphs[0].replay()
+        else:
+            graphs[0].replay()
+            allreduce_grads(de)
+            graphs[1].replay()
+            allreduce_grads(ge)
+            graphs[2].replay()
         Dopt.t += 1
         Gopt.t += 1
         ge.master_updated()
@@ -831,21 +915,23 @@ class WSEGAN(SEGAN):
         return 10 * torch.log10(mod ** 2 + 10e-20)
 
     def _d_pass(self, x0, x1, shifts, target, weight, losses, slot, input_grad=None, param_grads=True,
-                twins=True):
+                twins=True, reducer=None, reduce_now=True):
         """One D forward + backward of `weight * cost(D(x0 | x1), target)`: LSGAN (MSE, fused into the head
         backward kernel) or, with --vanilla_gan, BCE with logits (model.py:583-586; its gradient
         (sigmoid(logit) - target) * weight / B is handed to the same backward)."""
         de = self.D.engine
         lptr = C.c_void_p(losses.data_ptr() + 4 * slot)
         logit, c = de.forward(x0, x1, shifts, training=True, twins=twins)
+        red = dict(reducer=reducer, reduce_now=reduce_now) if param_grads else {}
         if not self.vanilla_gan:
-            de.backward(c, target, weight, param_grads=param_grads, input_grad=input_grad, loss_out=lptr)
+            de.backward(c, target, weight, param_grads=param_grads, input_grad=input_grad, loss_out=lptr, **red)
             return
         lg = logit.detach().view(-1)
         tg = torch.full_like(lg, float(target))
         losses[slot] += weight * F.binary_cross_entropy_with_logits(lg, tg)
         g_logit = ((torch.sigmoid(lg) - tg) * (float(weight) / lg.numel())).contiguous()
-        de.backward(c, target, weight, param_grads=param_grads, input_grad=input_grad, loss_out=None, g_logit=g_logit)
+        de.backward(c, target, weight, param_grads=param_grads, input_grad=input_grad, loss_out=None, g_logit=g_logit,
+                    **red)
 
     @staticmethod
     def interferer_squares(B, L, picks=None):
@@ -885,20 +971,23 @@ class WSEGAN(SEGAN):
         with _engine.on_side(gside):
             Genh, gctx = ge.forward(noisy, z)
         Dopt.zero_grad()
-        self._d_pass(clean, noisy, draw(), 1.0, d_weight, losses, 0)
+        rd, rg = self._reducers()
+        n_d = 2 + int(bool(self.misalign_pair)) + int(bool(self.interf_pair))      # the last D pass launches the chunks
+        self._d_pass(clean, noisy, draw(), 1.0, d_weight, losses, 0, reducer=rd, reduce_now=False)
         _engine.join_side(gside)
-        self._d_pass(Genh, noisy, draw(), 0.0, d_weight, losses, 0)
+        self._d_pass(Genh, noisy, draw(), 0.0, d_weight, losses, 0, reducer=rd, reduce_now=(n_d == 2))
         if self.misalign_pair:
             if perm is None:
                 perm = list(range(B))
                 random.shuffle(perm)                                       # model.py:598-600
             clean_shuf = clean[torch.as_tensor(perm, device=dev)]
-            self._d_pass(clean, clean_shuf, draw(), 0.0, d_weight, losses, 0)
+            self._d_pass(clean, clean_shuf, draw(), 0.0, d_weight, losses, 0, reducer=rd,
+                         reduce_now=not self.interf_pair)
         if self.interf_pair:
             if interf is None:
                 interf = self.interferer_squares(B, L)                     # model.py:606-622
-            self._d_pass(clean + interf.to(dev), noisy, draw(), 0.0, d_weight, losses, 0)
-        Dopt.step(allreduce_grads(de))
+            self._d_pass(clean + interf.to(dev), noisy, draw(), 0.0, d_weight, losses, 0, reducer=rd, reduce_now=True)
+        Dopt.step(rd.finish() if rd is not None else allreduce_grads(de))
         Gopt.zero_grad()
         gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
         self._d_pass(Genh, noisy, draw(), 1.0, 1.0, losses, 1, input_grad=gy, param_grads=False, twins=False)
@@ -918,8 +1007,8 @@ class WSEGAN(SEGAN):
             tot.backward()
         losses[2] += pow_loss.detach()
         gy.add_(gt.grad, alpha=_engine.LOSS_SCALE)
-        ge.backward(gctx, gy)
-        Gopt.step(allreduce_grads(ge))
+        ge.backward(gctx, gy, reducer=rg)
+        Gopt.step(rg.finish() if rg is not None else allreduce_grads(ge))
         return losses
 
     def train(self, opts, dloader, criterion, l1_init, l1_dec_step, l1_dec_epoch, log_freq, va_dloader=None,

@@ -14,8 +14,13 @@ def build_norm_layer(norm_type, param=None, num_feats=None):
     elif norm_type is None:
         return None
     elif norm_type == 'snorm':
-        raise NotImplementedError("norm_type='snorm' (spectral norm) is a SURVEY.md 8(f)-N4 'next' row; "
-                                  "not built yet")
+        # the reference re-parametrises the conv in place and uses no norm layer (modules.py:12-14): the same torch
+        # utility is applied to the container's nn.Conv1d so that the keys (weight_orig / weight_u / weight_v), the
+        # RNG consumption of the u / v initialisation and the init quirks (xavier on the derived `weight` is lost)
+        # are the reference's; the power iteration itself runs in the engine (sg_snorm_sigma)
+        from torch.nn.utils import spectral_norm
+        spectral_norm(param)
+        return None
     raise TypeError('Unrecognized norm type: ', norm_type)
 
 

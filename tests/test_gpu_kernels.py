@@ -829,7 +829,7 @@ def test_packed_master_roundtrip_and_operands(kind, co, ci, tl):
     d1 = torch.zeros(T, kc, nc, dtype=torch.float16, device=DEV)
     f0, d0 = torch.zeros_like(f1), torch.zeros_like(d1)
     _lib.call("sg_emit_operands", _p(m), T, nc, kc, _p(alpha), ci // 2 if kind == 1 else 0, _p(f1), _p(d1), SG_F16, SG_F16,
-              _stream())
+              None, _stream())
     _lib.call("sg_pack_weights", kind, _p(w), co, ci, tl, _p(alpha), ci // 2, _p(f0), _p(d0), SG_F16, SG_F16, _stream())
     torch.cuda.synchronize()
     assert torch.equal(f1, f0) and torch.equal(d1, d0)

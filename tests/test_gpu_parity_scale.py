@@ -322,3 +322,117 @@ def test_wsegan_generate_vs_reference():
     print("WSEGAN.generate max-abs (after de-emphasis): %.3e / %.3e" % (e1, e2))
     assert out2.shape == (4096,)
     assert e1 <= 20 * WAVE_TOL and e2 <= 20 * WAVE_TOL
+
+
+def test_snorm_discriminator_vs_oracle():
+    """norm_type='snorm' (run_wsegan_train.sh:8): D forward in train mode (two passes: the power iteration keeps
+    moving u / v), eval mode, and the D-step gradients through W / sigma against the oracle (which is pinned against
+    the reference's spectrally normalised Discriminator on the CPU, tests/test_oracle_pinned.py)."""
+    from segan_pytorch_b200.segan.models import Discriminator
+    B = 6
+    seed_all(111)
+    D = Discriminator(2, [64, 128, 256, 512, 1024], 31, [4, 4, 4, 4, 4], pool_type='none', pool_slen=16,
+                      norm_type='snorm', phase_shift=5)
+    sd = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    D = D.to(DEV)
+    clean, noisy, _ = _pairs(B, 120)
+    x = torch.cat((clean, noisy), 1)
+    random.seed(9)
+    shifts = [O.draw_phase_shifts(5, 5) for _ in range(3)]
+    D.train()
+    for i in range(2):
+        with torch.no_grad():
+            y, _ = D(x.to(DEV), shifts=shifts[i])
+        with O.oracle_mode(), torch.no_grad():
+            ref = O.discriminator_forward(sd, x, shifts[i], training=True)
+            with O.operand_precision(torch.float16):
+                ctl = O.discriminator_forward({k: v.clone() for k, v in sd.items()}, x, shifts[i], training=True)
+        e, c = max_abs(y.cpu(), ref), max_abs(ctl, ref)
+        print("snorm D fwd pass %d: logits max-abs %.3e (control %.3e), |logit| %.3f" % (i, e, c, float(ref.abs().mean())))
+        assert e <= max(LOGIT_TOL, 3 * c)
+    got = D.state_dict()
+    for k in ("enc_blocks.2.conv.weight_u", "enc_blocks.4.conv.weight_v", "fc.0.weight_v", "fc.3.weight_u", "enc_blocks.0.conv.weight_v"):
+        assert max_abs(got[k].cpu(), sd[k]) <= 2e-4, (k, max_abs(got[k].cpu(), sd[k]))
+    D.eval()
+    with torch.no_grad():
+        ye, _ = D(x.to(DEV), shifts=shifts[2])
+    with O.oracle_mode(), torch.no_grad():
+        re_ = O.discriminator_forward(sd, x, shifts[2], training=False)
+    assert max_abs(ye.cpu(), re_) <= max(LOGIT_TOL, 3 * c)
+    # gradients of a two-pass LSGAN D loss (real target 1, "fake" target 0 on swapped inputs): two power-iteration
+    # states accumulate into one bucket
+    D.train()
+    de = D.engine
+    de.zero_grad()
+    losses = torch.zeros(2, device=DEV)
+    import ctypes as C
+    x2 = torch.cat((noisy, clean), 1)
+    for i, (xx, tgt) in enumerate(((x, 1.0), (x2, 0.0))):
+        _, cx = de.forward(xx[:, :1].to(DEV).contiguous(), xx[:, 1:].to(DEV).contiguous(), shifts[i], training=True)
+        de.backward(cx, tgt, 1.0, param_grads=True, loss_out=C.c_void_p(losses.data_ptr() + 4 * i))
+    gD = {k: de.grad_of(k).cpu() for k, _ in D.named_parameters()}
+    pO = {k: sd[k].clone().requires_grad_(True) for k in O._trainable(sd)}
+
+    def oracle_loss(state):
+        l1 = O.discriminator_forward(state, x, shifts[0], training=True)
+        l2 = O.discriminator_forward(state, x2, shifts[1], training=True)
+        return torch.nn.functional.mse_loss(l1.view(-1), torch.ones(B)) + torch.nn.functional.mse_loss(l2.view(-1), torch.zeros(B))
+    with O.oracle_mode():
+        lo = oracle_loss({**{k: v.clone() for k, v in sd.items()}, **pO})
+        go = dict(zip(pO.keys(), torch.autograd.grad(lo, list(pO.values()))))
+        pC = {k: sd[k].clone().requires_grad_(True) for k in O._trainable(sd)}
+        with O.operand_precision(torch.float16):
+            lc = oracle_loss({**{k: v.clone() for k, v in sd.items()}, **pC})
+        gc = dict(zip(pC.keys(), torch.autograd.grad(lc, list(pC.values()))))
+    eD = {k: rel_err(gD[k], g) for k, g in go.items()}
+    cD = {k: rel_err(gc[k], g) for k, g in go.items()}
+    print("snorm D grads rel-L2: max %.3e (%s) median %.3e | control max %.3e; loss %.5f vs %.5f"
+          % (max(eD.values()), max(eD, key=eD.get), float(np.median(list(eD.values()))), max(cD.values()),
+             float(losses.sum()), float(lo)))
+    assert abs(float(losses.sum()) - float(lo)) <= max(LOSS_RTOL, 3 * abs(float(lc) - float(lo))) * max(1.0, float(lo))
+    assert max(eD.values()) <= GRAD_VS_CONTROL * max(cD.values()) + GRAD_ABS, sorted(eD.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_wsegan_canonical_recipe_step():
+    """run_wsegan_train.sh: --wsegan --gnorm_type snorm --dnorm_type snorm --opt adam --misalign_pair (gnorm_type is
+    parsed but never reaches the Generator): one step against the oracle."""
+    from segan_pytorch_b200.segan.models import WSEGAN
+    B = 4
+    seed_all(111)
+    opts = load_opts(batch_size=B, wsegan=True, misalign_pair=True, opt="adam", dnorm_type="snorm", gnorm_type="snorm")
+    s = WSEGAN(opts)
+    sdG, sdD = cpu_state(s.G), cpu_state(s.D)
+    assert "enc_blocks.1.conv.weight_orig" in sdD and "enc_blocks.1.norm.weight" not in sdD
+    s = s.to(DEV)
+    s.G.train()
+    s.D.train()
+    clean, noisy, z = _pairs(B, 121)
+    random.seed(5)
+    shifts = [O.draw_phase_shifts(5, 5) for _ in range(4)]
+    perm = [1, 3, 0, 2]
+    Gopt, Dopt = s.build_optimizers(opts)
+    losses = s.train_step(clean.to(DEV), noisy.to(DEV), Gopt, Dopt, 100.0, uttname=["a"] * B, z=z.to(DEV),
+                          shifts=shifts, perm=perm).tolist()
+    gD = {k: s.D.engine.grad_of(k).cpu() for k, _ in s.D.named_parameters()}
+    clone = lambda sd: {k: v.clone() for k, v in sd.items()}
+    with O.operand_precision(torch.float16):
+        ctl = O.wsegan_train_step(clone(sdG), clone(sdD), {}, {}, clean, noisy, z, shifts, perm, pow_weight=0.001,
+                                  l1_weight=100.0, opt="adam")
+    sdD0 = clone(sdD)
+    ref = O.wsegan_train_step(sdG, sdD, {}, {}, clean, noisy, z, shifts, perm, pow_weight=0.001, l1_weight=100.0,
+                              opt="adam")
+    for got, k in zip(losses, ("d_loss", "g_adv_loss", "pow_loss", "den_loss")):
+        tol = max(1e-2, 3 * abs(ctl[k] - ref[k]) / max(1.0, abs(ref[k])))
+        assert abs(got - ref[k]) <= tol * max(1.0, abs(ref[k])), (k, got, ref[k], ctl[k])
+    eD = {k: rel_err(gD[k], g) for k, g in ref["gradsD"].items()}
+    cD = {k: rel_err(ctl["gradsD"][k], g) for k, g in ref["gradsD"].items()}
+    print("canonical WSEGAN: losses", losses, "D grads max %.3e | control %.3e" % (max(eD.values()), max(cD.values())))
+    assert max(eD.values()) <= GRAD_VS_CONTROL * max(cD.values()) + GRAD_ABS
+    post = s.D.state_dict()
+    for k in ("enc_blocks.3.conv.weight_orig", "fc.0.weight_orig", "enc_blocks.0.conv.weight_orig"):
+        d_got = (post[k].cpu() - sdD0[k]).reshape(-1)
+        d_ref = (sdD[k] - sdD0[k]).reshape(-1)
+        agree = float((torch.sign(d_got) == torch.sign(d_ref)).float().mean())
+        assert float(d_got.abs().max()) <= 5.01e-5 and agree >= 0.95, (k, agree)
+    for k in ("enc_blocks.3.conv.weight_u", "fc.0.weight_v"):
+        assert max_abs(post[k].cpu(), sdD[k]) <= 5e-4, k
