@@ -150,9 +150,10 @@ typedef struct sg_tapgemm_f {
   const float* slope; /* with out2 == NULL and slope != NULL the PReLU is applied to `out` itself (inference decoder) */
   int32_t slope_mod;
   void* sk_ws;        /* or NULL.  Zero-initialised workspace of sg_tapgemm_f_workspace_bytes() bytes that lets the
-                         CTA-pair kernel split the tiles of its last, partial wave along K over all SMs (fp32 partial sums +
-                         counters; the kernel leaves it zeroed).  One workspace per stream: launches that may run
-                         concurrently must not share it. */
+                         CTA-pair kernel split the tiles of its last, partial wave along K over several CTA pairs (fp32
+                         partial sums in per-pair slots, summed in slot order by whoever finishes a tile: deterministic;
+                         counters, which the kernel leaves zeroed).  One workspace per stream: launches that may run
+                         concurrently must not share it.  (bias / slope must be 16-byte aligned for that kernel.) */
 } sg_tapgemm_f;
 
 int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream);

@@ -547,6 +547,17 @@ struct PieceIter {
   }
 };
 
+// v[j] += bias[(n_abs + j) % bias_mod], 16-byte loads (bias_mod is a multiple of 64, the chunk 32-aligned, the vector
+// a 16-byte aligned view)
+__device__ __forceinline__ void f_add_bias(const FTcParams& p, float (&v)[32], int n_abs) {
+  const float4* bp = reinterpret_cast<const float4*>(p.bias + (n_abs % p.bias_mod));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = __ldg(bp + j);
+    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+  }
+}
+
 // one 32-column chunk of an output row: bias / conversion / stores, and the fused second output
 //   out2[b][row2][n] = PReLU(v) (16-bit), the consumer-ready activation of the Generator's conv / deconv blocks
 //   (modules.py:99-101,139-141: no norm layer between the contraction and the PReLU), written next to the raw
@@ -566,11 +577,20 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
     return;
   }
   uint32_t pk[16];
+  float sl[32];
+  if (p.slope != nullptr) {
+    // 16-byte loads: slope / bias vectors are 16-byte aligned views and the chunk is 32-aligned
+    const float4* sp = reinterpret_cast<const float4*>(p.slope + (n_abs % p.slope_mod));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(sp + j);
+      sl[4 * j] = t.x; sl[4 * j + 1] = t.y; sl[4 * j + 2] = t.z; sl[4 * j + 3] = t.w;
+    }
+  }
   if (p.out2 == nullptr && p.slope != nullptr) {
     // PReLU applied to the (only) output: blocks whose pre-activation nobody reads (inference decoder)
-    const float* sp = p.slope + (n_abs % p.slope_mod);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : __ldg(sp + j) * v[j];
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : sl[j] * v[j];
   }
   if (p.out_dtype == SG_F16) {
 #pragma unroll
@@ -586,12 +606,11 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
 #pragma unroll
   for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   if (p.out2 != nullptr) {
-    const float* sp = p.slope + (n_abs % p.slope_mod);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float x0 = v[2 * j], x1 = v[2 * j + 1];
-      const float y0 = x0 > 0.f ? x0 : __ldg(sp + 2 * j) * x0;
-      const float y1 = x1 > 0.f ? x1 : __ldg(sp + 2 * j + 1) * x1;
+      const float y0 = x0 > 0.f ? x0 : sl[2 * j] * x0;
+      const float y1 = x1 > 0.f ? x1 : sl[2 * j + 1] * x1;
       pk[j] = pack_half2_sat(y0, y1);
     }
     uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out2) + o2base + c0);
@@ -605,7 +624,14 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// 10 warps: TMA producer, MMA issuer and EIGHT epilogue warps -- two per TMEM lane quadrant, taking alternate
+// 32-column chunks.  The layers with one or two k-steps per tile (the waveform-end GEMMs, K = 64) are bound by the
+// epilogue's instruction issue, not by the tensor pipe or HBM (profiles/r2_calls_*.txt: 157 MB in + 157 MB out took
+// 141 us with four warps).
+constexpr int NUM_THREADS2 = 320;
+__device__ __forceinline__ void epi2_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmW, const FTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -618,7 +644,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
     for (int s = 0; s < STAGES2; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 256); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 512); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(&ctl->tmem_base, 512);
@@ -709,8 +735,9 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
     }
   } else {
-    // ================= epilogue (warps 2..5, both CTAs; each CTA owns 128 of the 256 rows) =========
-    const int quad = warp & 3;
+    // ================= epilogue (warps 2..9, both CTAs; each CTA owns 128 of the 256 rows) =========
+    const int quad = warp & 3;                 // TMEM lane quadrant a warp may read = warp id % 4
+    const int half = (warp - 2) >> 2;          // the two warps of a quadrant take alternate 32-column chunks
     const int row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     const int out_buf_rows = p.out_rows + 2 * p.out_halo;
@@ -719,23 +746,23 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     // outputs, accumulated per CTA in shared memory across its tiles of one N tile, flushed with one double
     // atomic per column when the N tile changes and at the end
     float* colstat = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES + 256);
-    const int et = threadIdx.x - 64;           // 0..127 within the epilogue warps
+    const int et = threadIdx.x - 64;           // 0..255 within the epilogue warps
     int stat_nt = -1;
     auto flush_stats = [&](int nt_done) {
-      epi_bar_sync();
+      epi2_bar_sync();
       const int n0s = p.n_lo + nt_done * p.TN;
       double* o = p.stats + (int64_t)(blockIdx.x % SG_STAT_SLICES) * 2 * p.nc;
-      for (int c = et; c < p.TN; c += 128) {
+      for (int c = et; c < p.TN; c += 256) {
         atomicAdd(o + n0s + c, (double)colstat[c]);
         atomicAdd(o + p.nc + n0s + c, (double)colstat[256 + c]);
         colstat[c] = 0.f;
         colstat[256 + c] = 0.f;
       }
-      epi_bar_sync();
+      epi2_bar_sync();
     };
     if (p.stats != nullptr) {
-      for (int c = et; c < 512; c += 128) colstat[c] = 0.f;
-      epi_bar_sync();
+      for (int c = et; c < 512; c += 256) colstat[c] = 0.f;
+      epi2_bar_sync();
     }
     while (it.next(p, pc)) {
       const int mp = pc.tile % m_pairs;
@@ -749,7 +776,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int tb = row / p.TR, tr = row % p.TR;
       const int b = b0 + tb, m = m0 + tr;
       const bool valid = (mt < m_tiles) && (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
-      const bool partial = pc.kb != 0 || pc.ke != pc.total;         // a stream-K piece of a split tile
+      const bool partial = pc.kb != 0 || pc.ke != pc.total;         // one K range of a split tile
       if (p.stats != nullptr && nt != stat_nt) {
         if (stat_nt >= 0) flush_stats(stat_nt);
         stat_nt = nt;
@@ -771,35 +798,28 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (has) o2mirror = (rb + mm) * p.out_ld + (n0 - p.n_lo + p.out_col0);
         }
       }
-      // stream-K workspace of this (tile, CTA): [128 rows][TN] fp32, and this warp's k-step counter
-      const int slot = pc.tile - it.dp_end;
-      float* wsrow = nullptr;
-      unsigned int* cnt = nullptr;
-      if (partial) {
-        wsrow = p.sk_ws + (((int64_t)slot * 2 + rank) * 128 + row) * p.TN;
-        cnt = p.sk_cnt + ((slot * 2 + (int)rank) * 4 + quad);
-      }
-      for (int c0 = 0; c0 < p.TN; c0 += 32) {
+      // split tiles: this pair's fp32 partial sums go to ITS workspace slot [pair][rank][128 rows][TN] (plain
+      // stores); the warp that counts the tile's last contribution adds the sk_split slots up in slot order
+      // (deterministic) and finishes the tile
+      float* myrow = partial ? p.sk_ws + (((int64_t)pair_id * 2 + rank) * 128 + row) * p.TN : nullptr;
+      for (int c0 = half * 32; c0 < p.TN; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (partial) {
-          if (valid && (mt < m_tiles)) {
+          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) red_add_v4(wsrow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4)
+              __stcg(reinterpret_cast<float4*>(myrow + c0 + j),
+                     make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3])));
           }
           continue;
         }
-        if (p.bias != nullptr && ks == 0) {
-          // bias_mod is a multiple of 64 and the chunk is 32-aligned: one modulo per chunk
-          // (scalar loads: bias vectors are 4-byte-aligned views of the flat parameter buffer)
-          const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr && ks == 0) f_add_bias(p, v, n0 + c0);
         if (valid) f_store_chunk(p, v, obase, c0, n0 + c0, p.ksplit > 1, o2base, o2mirror);
         if (p.stats != nullptr) {                      // warp-uniform branch: the reduction is warp-collective
           float q[32];
@@ -820,36 +840,41 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive_leader(&ctl->tmem_empty[acc]);      // 2 x 128 arrivals release the accumulator
+      mbar_arrive_leader(&ctl->tmem_empty[acc]);      // 2 x 256 arrivals release the accumulator
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       if (partial && mt < m_tiles) {
-        // publish this warp's partial sums, count its k-steps; the warp that completes the tile finishes it
-        __threadfence();
+        const int slot = pc.tile - it.dp_end;
+        unsigned int* cnt = p.sk_cnt + ((((slot * 2 + (int)rank) * 4 + quad) * 2) + half);
+        __threadfence();                               // this warp's partial sums are visible ...
         __syncwarp();
         unsigned int old = 0;
-        if (lane == 0) old = atomicAdd(cnt, (unsigned int)(pc.ke - pc.kb));
+        if (lane == 0) old = atomicAdd(cnt, 1u);       // ... before its contribution is counted
         old = __shfl_sync(0xffffffffu, old, 0);
-        if (old + (unsigned int)(pc.ke - pc.kb) == (unsigned int)pc.total) {
+        if (old + 1u == (unsigned int)p.sk_split) {
           __threadfence();
           if (valid) {
-            for (int c0 = 0; c0 < p.TN; c0 += 32) {
+            const float* base0 = p.sk_ws + (((int64_t)(slot * p.sk_split) * 2 + rank) * 128 + row) * p.TN;
+            const int64_t pstride = (int64_t)2 * 128 * p.TN;          // next contributor's slot
+            for (int c0 = half * 32; c0 < p.TN; c0 += 64) {
               float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t = __ldcg(reinterpret_cast<const float4*>(wsrow + c0 + j));
-                v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
-                *reinterpret_cast<float4*>(wsrow + c0 + j) = make_float4(0.f, 0.f, 0.f, 0.f);   // clean for the next launch
-              }
-              if (p.bias != nullptr) {
-                const float* bp = p.bias + ((n0 + c0) % p.bias_mod);
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int sp = 0; sp < p.sk_split; ++sp) {
+                const float4* src = reinterpret_cast<const float4*>(base0 + sp * pstride + c0);
+                float4 t[8];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += __ldg(bp + j);
+                for (int j = 0; j < 8; ++j) t[j] = __ldcg(src + j);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w;
+                }
               }
+              if (p.bias != nullptr) f_add_bias(p, v, n0 + c0);
               f_store_chunk(p, v, obase, c0, n0 + c0, false, o2base, o2mirror);
             }
           }
           __syncwarp();
-          if (lane == 0) *cnt = 0u;
+          if (lane == 0) *cnt = 0u;                    // ready for the next launch
         }
       }
     }
@@ -1333,9 +1358,10 @@ static int make_map2(CUtensorMap* m, const void* base, int dtype, int C, int64_t
   return SG_OK;
 }
 
-// stream-K workspace: counters [SK_MAX_PAIRS][2][4] u32 (padded to 4 KB), then partial sums [SK_MAX_PAIRS][2][128][256] fp32
+// split-K workspace: counters [tiles][2 CTAs][4 quadrants][2 warps] u32 (8 KB), then one partial-sum slot per CTA
+// pair [SK_MAX_PAIRS][2][128][256] fp32
 constexpr int SK_MAX_PAIRS = 96;
-constexpr int64_t SK_CNT_BYTES = 4096;
+constexpr int64_t SK_CNT_BYTES = 8192;
 constexpr int64_t SK_WS_BYTES = SK_CNT_BYTES + (int64_t)SK_MAX_PAIRS * 2 * 128 * 256 * 4;
 int64_t tapgemm_f_workspace_bytes() { return SK_WS_BYTES; }
 // SEGAN_B200_STREAMK: 0 = off, n = largest split factor per leftover tile (default 16);
@@ -1448,6 +1474,8 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     }
     rc = make_map3(&tmW, q->w, q->w_dtype, q->kc, (q->d_hi + 4 - q->w_tap0 + 1) * q->nc, 1, p.TN / 2, 1);
     if (rc) return rc;
+    // the CTA-pair epilogue reads bias / slope with 16-byte loads
+    SG_CHECK_ARG(((reinterpret_cast<uintptr_t>(q->bias) | reinterpret_cast<uintptr_t>(q->slope)) & 15) == 0);
     p.idesc = make_idesc(q->a_dtype == SG_BF16, q->w_dtype == SG_BF16, 0, 0, 256, p.TN);
     const int pairs = ((m_tiles_all + 1) / 2) * p.n_tiles * p.ksplit;
     int npairs = num_sms() / 2;
@@ -1475,7 +1503,7 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
         p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->sk_ws) + SK_CNT_BYTES);
       }
     }
-    tapgemm_f_tc2<<<2 * npairs, NUM_THREADS, SMEM2_BYTES, st>>>(tmA0, tmA1, tmW, p);
+    tapgemm_f_tc2<<<2 * npairs, NUM_THREADS2, SMEM2_BYTES, st>>>(tmA0, tmA1, tmW, p);
     SG_CHECK_LAUNCH();
     return SG_OK;
   }
