@@ -114,8 +114,9 @@ def gdeconv_linear(x, weight, bias, stride=STRIDE):
 # Generator (segan/models/generator.py:180-230), SEGAN+ defaults:
 # skip_type='alpha', skip_merge='concat', no norm, PReLU, Tanh on the last decoder block
 # --------------------------------------------------------------------------------------
-def generator_forward(sd, x, z, ret_hid=False):
-    """sd: state_dict with the reference key names.  x: (B,1,T) z: (B,1024,T/1024)."""
+def generator_forward(sd, x, z, ret_hid=False, skip_merge="concat"):
+    """sd: state_dict with the reference key names.  x: (B,1,T) z: (B,1024,T/1024).
+    skip_merge: 'concat' (train.py default) or 'sum' (generator.py:72-74)."""
     n_enc = len([k for k in sd if k.startswith("enc_blocks.") and k.endswith("conv.weight")])
     n_dec = len([k for k in sd if k.startswith("dec_blocks.") and k.endswith("deconv.weight")])
     hall = {}
@@ -137,7 +138,10 @@ def generator_forward(sd, x, z, ret_hid=False):
             alpha = sd["alpha_%d.skip_k" % enc_idx]
             hj = skips[enc_idx]
             sk = alpha.repeat(hj.size(0), 1, hj.size(2)) * hj     # generator.py:68-69
-            hi = torch.cat((hi, sk), dim=1)                       # decoder first (generator.py:76)
+            if skip_merge == "sum":
+                hi = sk + hi                                      # generator.py:72-74
+            else:
+                hi = torch.cat((hi, sk), dim=1)                   # decoder first (generator.py:76)
         h = gdeconv_linear(hi, sd["dec_blocks.%d.deconv.weight" % l], sd["dec_blocks.%d.deconv.bias" % l])
         if l == n_dec - 1:
             hi = torch.tanh(h)                # act='Tanh' on the last block (generator.py:165-166)

@@ -489,9 +489,13 @@ class PackedLayer(object):
       kind 1: ConvTranspose1d W[cin][cout][31] -> M[9][4cout][cin]   (alpha: GSkip scale of the columns >= alpha_from)
       kind 2: Linear W[nout][C*T]              -> M[1][nout][T*C]"""
 
-    def __init__(self, name, kind, c_out, c_in, t_len, f_key, dg_key, alpha_name=None):
+    def __init__(self, name, kind, c_out, c_in, t_len, f_key, dg_key, alpha_name=None, tied=False):
+        """tied (skip_merge='sum', generator.py:72-74): W (hi + alpha*skip) = [W | alpha W] cat(hi, skip) -- the
+        layer runs as the two-source concat GEMM over 2*Cin' input channels whose two halves hold the SAME weights:
+        `c_in` is the doubled count, import duplicates the parameter, export returns the first half, and the
+        gradients of the two halves are summed into both (finish_grads) so the copies never drift apart."""
         self.name, self.kind, self.c_out, self.c_in, self.t_len = name, kind, c_out, c_in, t_len
-        self.f_key, self.dg_key, self.alpha_name = f_key, dg_key, alpha_name
+        self.f_key, self.dg_key, self.alpha_name, self.tied = f_key, dg_key, alpha_name, tied
         if kind == 0:
             self.T, self.nc, self.kc = 9, c_out, 4 * c_in
         elif kind == 1:
@@ -626,6 +630,8 @@ class _NetEngine:
         """reference layout -> packed (master by default)."""
         src = self._param(l.name).data if src is None else src
         dst = self.mview(l) if dst is None else dst
+        if l.tied:
+            src = torch.cat((src, src), 0).contiguous()          # both halves of the doubled input = the parameter
         if not dst.is_cuda:
             dst.copy_(pack_reference(l.kind, src.float(), l.c_out, l.c_in, l.t_len).reshape(-1))
             return
@@ -634,6 +640,14 @@ class _NetEngine:
 
     def _export(self, l, src, dst):
         """packed -> reference layout (pure layout transform)."""
+        if l.tied:
+            full = torch.empty((2 * dst.shape[0],) + tuple(dst.shape[1:]), dtype=dst.dtype, device=dst.device)
+            self._export_plain(l, src, full)
+            dst.copy_(full[:dst.shape[0]])
+            return
+        self._export_plain(l, src, dst)
+
+    def _export_plain(self, l, src, dst):
         if not src.is_cuda:
             dst.copy_(unpack_reference(l.kind, src, l.c_out, l.c_in, l.t_len).reshape(dst.shape))
             return
@@ -775,6 +789,7 @@ class GeneratorEngine(_NetEngine):
         self.fmaps = list(m.enc_fmaps)
         self.nl = len(self.fmaps)
         self.enc_bias = m.bias
+        self.sum_merge = getattr(m, "skip_merge", "concat") == "sum"
         self.packed = {}
 
     # -- weights ----------------------------------------------------------------------------
@@ -787,7 +802,8 @@ class GeneratorEngine(_NetEngine):
         for l in range(nl - 1):
             ls.append(PackedLayer("dec_blocks.%d.deconv.weight" % l, 1, self.dec_cout(l), self.dec_cin(l), 0,
                                   "Wt%d" % l, "Wtd%d" % l,
-                                  alpha_name=("alpha_%d.skip_k" % (nl - 1 - l)) if l > 0 else None))
+                                  alpha_name=("alpha_%d.skip_k" % (nl - 1 - l)) if l > 0 else None,
+                                  tied=(self.sum_merge and l > 0)))
         ls += [PackedLayer("enc_blocks.%d.conv.weight" % l, 0, fm[l], fm[l - 1], 0, "Wf%d" % l, "Wdg%d" % l)
                for l in range(nl - 1, 0, -1)]
         return ls
@@ -803,6 +819,9 @@ class GeneratorEngine(_NetEngine):
         # last decoder layer (Cout = 1): fp32 [cin][31] with alpha folded (tiny: torch ops)
         l = self.nl - 1
         w = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
+        if self.sum_merge:                       # tied halves: W (hi + alpha skip) = [W | alpha W] cat(hi, skip)
+            w = torch.cat((w, w), 0)
+        self.packed["w_last_dup"] = w.reshape(w.shape[0], 1, KW).contiguous()
         alpha = self.alpha_for_dec(l)
         half = w.shape[0] // 2
         weff = w.clone()
@@ -830,9 +849,16 @@ class GeneratorEngine(_NetEngine):
                 _lib.call("sg_alpha_grad", _p(self.mgrad(pl)), _p(self.mview(pl)), pl.T, pl.nc, pl.kc,
                           _p(self.pview(pl.alpha_name).reshape(-1)), pl.alpha_from,
                           _p(self.gview(pl.alpha_name).view(-1)) if trainable else None, _stream())
+            if pl.tied:                          # dW = dW_a + alpha dW_b, written to both copies
+                g2 = self.mgrad(pl).view(pl.T, pl.nc, 2, pl.kc // 2)
+                tot = g2[:, :, 0] + g2[:, :, 1]
+                g2[:, :, 0] = tot
+                g2[:, :, 1] = tot
         self._alpha_fixed = True
 
     def dec_cin(self, l):
+        """Input channels of decoder block l AS THE GEMM SEES THEM: cat(z, code) for block 0, cat(decoder, skip)
+        afterwards -- also with skip_merge='sum', which runs as the concat GEMM with tied weight halves."""
         return 2 * self.fmaps[-1] if l == 0 else 2 * self.fmaps[self.nl - 1 - l]
 
     def dec_cout(self, l):
@@ -1043,13 +1069,20 @@ class GeneratorEngine(_NetEngine):
                 run_w(colg, lin // 2, GS, ctx["ddb"][l - 1], ctx["ab"][0], lin // 2, 0, GS, 2 * cin, 128,
                       tap_ranges("full", 0, 2 * cin, 128), dwq, B, d_lo=0, d_hi=0, dw_tap0=4, ksplit=74,
                       a0_c=cin, a1_c=cin, backend=self.backend)
-                _lib.call("sg_last_deconv_wgrad_fold", _p(dwq), half, _p(self.pview("dec_blocks.%d.deconv.weight" % l)),
-                          _p(self.alpha_for_dec(l)), _p(self.gview("dec_blocks.%d.deconv.weight" % l)),
+                gw_dst = self.gview("dec_blocks.%d.deconv.weight" % l)
+                if self.sum_merge:
+                    gw_dst = buf.get("g.gw_last2", (cin, 1, KW), F32, dev, zero=True)
+                _lib.call("sg_last_deconv_wgrad_fold", _p(dwq), half, _p(self.packed["w_last_dup"]),
+                          _p(self.alpha_for_dec(l)), _p(gw_dst),
                           _p(self.gview("alpha_0.skip_k").view(-1)) if a_train else None, _stream())
+                if self.sum_merge:
+                    self.gview("dec_blocks.%d.deconv.weight" % l).add_(gw_dst[:half] + gw_dst[half:])
         else:
             dweff = buf.get("g.dweff", (cin, KW), F32, dev, zero=True)
             _lib.call("sg_wave_deconv_bwd", _p(src0), half, _p(src1), half, B, lin, _p(self.packed["w_last_eff"]),
                       _p(gy), _p(ctx["y"]), _p(gpre), _p(g_in), _p(dweff), _p(gb), st)
+            if self.sum_merge:
+                raise NotImplementedError("skip_merge='sum' needs the tensor-core waveform route (SEGAN_B200_WAVE=tc)")
             w_last = self.pview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]
             alpha = self.alpha_for_dec(l)
             gw = self.gview("dec_blocks.%d.deconv.weight" % l)[:, 0, :]

@@ -11,8 +11,8 @@ from ... import engine as _engine
 
 
 class GSkip(nn.Module):
-    """Learnable per-channel skip scale (generator.py:18-78).  Only skip_type 'alpha' | 'constant'
-    with merge 'concat' is served by the kernels (the SEGAN+ default, ckpt_segan+/train.opts)."""
+    """Learnable per-channel skip scale (generator.py:18-78).  skip_type 'alpha' | 'constant' with merge 'concat'
+    (ckpt_segan+/train.opts) or 'sum' (generator.py:72-74) is served by the kernels."""
 
     def __init__(self, skip_type, size, skip_init, skip_dropout=0, merge_mode='sum', kwidth=11, bias=True):
         super().__init__()
@@ -123,7 +123,8 @@ class Generator(Model):
             ninp = fmap
         # ---- what the kernels serve (everything else is a "next" row)
         self.enc_fmaps = list(fmaps)
-        self._served = (ninputs == 1 and skip and not no_z and skip_merge == 'concat'
+        self.skip_merge = skip_merge
+        self._served = (ninputs == 1 and skip and not no_z and skip_merge in ('concat', 'sum')
                         and skip_type in ('alpha', 'constant') and norm_type is None
                         and all(k == 31 for k in kwidth) and all(k == 31 for k in dec_kwidth)
                         and all(p == 4 for p in poolings) and all(p == 4 for p in dec_poolings)

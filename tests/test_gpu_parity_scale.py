@@ -436,3 +436,46 @@ def test_wsegan_canonical_recipe_step():
         assert float(d_got.abs().max()) <= 5.01e-5 and agree >= 0.95, (k, agree)
     for k in ("enc_blocks.3.conv.weight_u", "fc.0.weight_v"):
         assert max_abs(post[k].cpu(), sdD[k]) <= 5e-4, k
+
+
+def test_sum_merge_generator_vs_oracle():
+    """skip_merge='sum' (generator.py:72-74): forward and parameter gradients of 100 * L1 against the oracle.  The
+    engine runs it as the concat GEMM with tied weight halves; alphas are randomised so that they matter."""
+    B = 4
+    s = build_segan(batch_size=B, skip_merge="sum")
+    g = torch.Generator().manual_seed(8)
+    with torch.no_grad():
+        for k, p in s.G.named_parameters():
+            if k.endswith("skip_k"):
+                p.copy_(0.5 + torch.rand(p.shape, generator=g))
+            if k.endswith("act.weight"):
+                p.fill_(1.0)                                  # continuous activations: see GRAD_TOL_SMOOTH
+    sdG = cpu_state(s.G)
+    assert sdG["dec_blocks.1.deconv.weight"].shape[0] == 512
+    s = s.to(DEV)
+    clean, noisy, z = _pairs(B, 122)
+    s.G.train()
+    y = s.G(noisy.to(DEV), z=z.to(DEV))
+    loss = 100 * torch.nn.functional.l1_loss(y, clean.to(DEV))
+    loss.backward()
+    gG = {n: p.grad.detach().cpu() for n, p in s.G.named_parameters()}
+    pG = {k: sdG[k].clone().requires_grad_(True) for k in O._trainable(sdG)}
+    with O.oracle_mode():
+        yo = O.generator_forward({**sdG, **pG}, noisy, z, skip_merge="sum")
+        lo = 100 * torch.nn.functional.l1_loss(yo, clean)
+        go = dict(zip(pG.keys(), torch.autograd.grad(lo, list(pG.values()))))
+    assert max_abs(y.detach().cpu(), yo.detach()) <= WAVE_TOL
+    rep = {k: rel_err(gG[k], v) for k, v in go.items()}
+    print("sum-merge G: fwd max-abs %.2e, grads max %.3e (%s) median %.3e"
+          % (max_abs(y.detach().cpu(), yo.detach()), max(rep.values()), max(rep, key=rep.get),
+             float(np.median(list(rep.values())))))
+    assert max(rep.values()) <= 2 * GRAD_TOL_SMOOTH, sorted(rep.items(), key=lambda kv: -kv[1])[:5]
+    # the tied halves stay tied through an optimiser step and the exported weight is their common value
+    eng = s.G.engine
+    lay = eng.by_name["dec_blocks.2.deconv.weight"]
+    Gopt, _ = s.build_optimizers(load_opts(batch_size=B, skip_merge="sum"))
+    Gopt.step()
+    m = eng.mview(lay).view(lay.T, lay.nc, 2, lay.kc // 2)
+    assert torch.equal(m[:, :, 0], m[:, :, 1])
+    w_new = s.G.state_dict()["dec_blocks.2.deconv.weight"].cpu()
+    assert w_new.shape == sdG["dec_blocks.2.deconv.weight"].shape and float((w_new - sdG["dec_blocks.2.deconv.weight"]).abs().max()) > 0
