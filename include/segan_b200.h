@@ -358,7 +358,7 @@ int sg_alpha_grad(float* dwp, const float* master, int n_taps, int nc, int kc, c
  *     stored vectors.  scal: 4 device floats; work: nc device floats.  The operands are then emitted with
  *     sg_emit_operands(..., scale_dev = scal + 3).
  *   sg_snorm_grad: gradient w.r.t. the normalised weight (packed, what sg_tapgemm_w_run produced) -> gradient
- *     w.r.t. weight_orig in place: dW = G / sigma - <G, W> / sigma^3 * u v^T  (u, v constants, as torch
+ *     w.r.t. weight_orig in place: dW = G / sigma - <G, W> / sigma^2 * u v^T  (u, v constants, as torch
  *     differentiates sigma).  dot_ws: one device float. */
 int sg_snorm_sigma(const float* master, int n_taps, int nc, int kc, float* u, float* v, float* scal, float* work,
                    int training, void* stream);

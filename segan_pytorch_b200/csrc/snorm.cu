@@ -81,13 +81,13 @@ __global__ void snorm_dot_kernel(const float* __restrict__ a, const float* __res
   if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(out, s);
 }
 
-// gradient through W / sigma:  dW = (G - <G, W> / sigma^2 ... ) see sg_snorm_grad
-//   dwp[t][n][k] = dwp * inv_sigma - (dot * inv_sigma^3) * u[n] * v[t][k]      (dot = <dwp, M>, <G, W~> = dot / sigma)
+// gradient through W / sigma (u, v constant):  dW = G / sigma - (<G, W~> / sigma) u v^T,  <G, W~> = <G, W> / sigma
+//   dwp[t][n][k] = dwp * inv_sigma - (dot * inv_sigma^2) * u[n] * v[t][k]      (dot = <dwp, M> = <G, W>)
 __global__ void __launch_bounds__(256)
 snorm_grad_apply_kernel(float* __restrict__ dwp, int T, int nc, int kc, const float* __restrict__ u,
                         const float* __restrict__ v, const float* __restrict__ scal, const float* __restrict__ dot) {
   const float is = scal[3];
-  const float c = (*dot) * is * is * is;
+  const float c = (*dot) * is * is;
   const int64_t total = (int64_t)T * nc * kc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % kc);

@@ -798,22 +798,25 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           if (has) o2mirror = (rb + mm) * p.out_ld + (n0 - p.n_lo + p.out_col0);
         }
       }
-      // split tiles: this pair's fp32 partial sums go to ITS workspace slot [pair][rank][128 rows][TN] (plain
-      // stores); the warp that counts the tile's last contribution adds the sk_split slots up in slot order
-      // (deterministic) and finishes the tile
-      float* myrow = partial ? p.sk_ws + (((int64_t)pair_id * 2 + rank) * 128 + row) * p.TN : nullptr;
+      // split tiles: this pair's fp32 partial sums go to ITS workspace slot (plain stores); the warp that counts the
+      // tile's last contribution adds the sk_split slots up in slot order (deterministic) and finishes the tile.
+      // Only the same (quadrant, half, lane) of another CTA ever reads a value back, so the slot layout is private:
+      // [pair][rank][warp][chunk][j4][lane] float4 -- every warp instruction moves 512 contiguous bytes
+      // (row-per-lane addressing touched 32 lines per instruction and made this path slower than the wave it removes).
+      const int ewarp = quad * 2 + half;
+      const int64_t slot_f4 = (int64_t)p.TN * 128 / 4;              // float4 per (pair, rank)
+      float4* myslot = reinterpret_cast<float4*>(p.sk_ws) + ((int64_t)pair_id * 2 + rank) * slot_f4 +
+                       (int64_t)ewarp * (p.TN / 64) * 256 + lane;
       for (int c0 = half * 32; c0 < p.TN; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
         if (partial) {
-          if (valid) {
+          float4* dst = myslot + (c0 >> 6) * 256;                   // this warp's (c0 / 64)-th chunk
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              __stcg(reinterpret_cast<float4*>(myrow + c0 + j),
-                     make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3])));
-          }
+          for (int j = 0; j < 8; ++j)
+            __stcg(dst + j * 32, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
           continue;
         }
         float v[32];
@@ -852,25 +855,26 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         old = __shfl_sync(0xffffffffu, old, 0);
         if (old + 1u == (unsigned int)p.sk_split) {
           __threadfence();
-          if (valid) {
-            const float* base0 = p.sk_ws + (((int64_t)(slot * p.sk_split) * 2 + rank) * 128 + row) * p.TN;
-            const int64_t pstride = (int64_t)2 * 128 * p.TN;          // next contributor's slot
+          {
+            const float4* base0 = reinterpret_cast<const float4*>(p.sk_ws) +
+                                  ((int64_t)(slot * p.sk_split) * 2 + rank) * slot_f4 +
+                                  (int64_t)ewarp * (p.TN / 64) * 256 + lane;
             for (int c0 = half * 32; c0 < p.TN; c0 += 64) {
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
               for (int sp = 0; sp < p.sk_split; ++sp) {
-                const float4* src = reinterpret_cast<const float4*>(base0 + sp * pstride + c0);
+                const float4* src = base0 + (int64_t)sp * 2 * slot_f4 + (c0 >> 6) * 256;
                 float4 t[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = __ldcg(src + j);
+                for (int j = 0; j < 8; ++j) t[j] = __ldcg(src + j * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   v[4 * j] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w;
                 }
               }
               if (p.bias != nullptr) f_add_bias(p, v, n0 + c0);
-              f_store_chunk(p, v, obase, c0, n0 + c0, false, o2base, o2mirror);
+              if (valid) f_store_chunk(p, v, obase, c0, n0 + c0, false, o2base, o2mirror);
             }
           }
           __syncwarp();

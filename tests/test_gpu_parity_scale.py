@@ -24,15 +24,18 @@ WAVE_TOL = 1e-3          # north_star: max-abs on fp32 waveforms
 LOSS_RTOL = 1e-3
 LOGIT_TOL = 1e-3
 RUNSTAT_TOL = 1e-4
-# Gradients.  Measured on B200 (profiles/r2_parity_probe.txt): with the reference's PReLU slopes (init 0: the
-# derivative jumps from 0 to 1 at 0) every parameter gradient is 5-7 % away from the fp32 oracle in relative L2 --
-# with bf16 AND with fp16 gradient tensors alike, and the oracle's own operand-precision control (fp32 arithmetic,
-# fp16-rounded operands) is just as far.  The forward activations carry ~1e-3 of operand rounding; the ~1e-3 of
-# elements within that distance of 0 get the other side's derivative (100 % error on those elements), i.e.
-# sqrt(flipped fraction) ~ 3 % per layer, accumulating in quadrature.  The error scales with the jump: slopes 0.5
-# halve it and slopes 1 (no jump) leave the kernels' own error, which is what GRAD_TOL_SMOOTH gates.
-# The reference-slope gradients are therefore held to the control: <= GRAD_VS_CONTROL x its error (+ GRAD_ABS).
-GRAD_TOL_SMOOTH = 1e-2   # relative L2 per parameter tensor when the activation derivative is continuous
+# Gradients.  Measured on B200 (profiles/r2_parity_probe.txt, r2_dgrad_probe.txt): with the reference's PReLU slopes
+# (init 0: the derivative jumps from 0 to 1 at 0) every parameter gradient of a train step is 5-7 % away from the
+# fp32 oracle in relative L2 -- with bf16 AND with fp16 gradient tensors alike -- and the oracle's own operand-
+# precision control (fp32 arithmetic, fp16-rounded operands, no kernel of ours involved) is just as far, tensor by
+# tensor.  Two amplifiers of the ~1e-3 operand rounding of the forward activations: (i) the ~1e-3 of elements within
+# that distance of 0 get the other side's derivative (100 % error there): sqrt(flipped fraction) ~ 3 % per layer,
+# accumulating in quadrature and scaling with the jump (slopes 0.5 halve it); (ii) the D step adds the real and the
+# fake pass, whose logit gradients 2(l - 1)/B and 2 l/B largely cancel at initialisation, so the relative error of
+# the SUM is several times that of either pass (slopes 1, batch 8: each pass alone 0.2-0.5 %, the sum 6 % -- in the
+# control exactly as in the kernels).  Train-step gradients are therefore held to the control:
+# <= GRAD_VS_CONTROL x its error (+ GRAD_ABS); single-pass gradients with continuous activations to GRAD_TOL_SMOOTH.
+GRAD_TOL_SMOOTH = 1e-2   # relative L2 per parameter tensor: one pass, continuous activation derivative
 GRAD_VS_CONTROL = 1.5
 GRAD_ABS = 5e-3
 
@@ -175,25 +178,57 @@ def test_train_step_batch16_vs_oracle():
 
 
 @pytest.mark.parametrize("slope", [1.0, 0.5])
-def test_train_step_gradients_with_continuous_activation(slope):
-    """The same step with every PReLU slope set to 1 (derivative continuous): what is left is the backward
-    kernels' own error, held to GRAD_TOL_SMOOTH for every parameter tensor of D and -- through the updated D --
-    loosely for G.  Slope 0.5 halves the derivative jump of the reference's init and must land in between."""
+def test_train_step_gradients_vs_control_other_slopes(slope):
+    """The same step with every PReLU slope set to 0.5 / 1: the derivative jump halves / vanishes, the control's and
+    the kernels' D-step errors move together (at slope 1 what is left is the cancellation between the real and the
+    fake pass, see GRAD_TOL_SMOOTH's comment)."""
     B = 8
     s = build_segan(batch_size=B)
     _set_slopes(s, slope)
     sdG, sdD = cpu_state(s.G), cpu_state(s.D)
     s = s.to(DEV)
     losses, refl, lerr, eD, eG, cD, cG, cl = _step_vs_oracle(s, sdG, sdD, B, 117, load_opts(batch_size=B),
-                                                             "slope=%g" % slope, control=(slope != 1.0))
+                                                             "slope=%g" % slope)
     if slope == 1.0:
         # identity activations: a BatchNorm shift that feeds the next conv + BatchNorm has zero gradient in exact
         # arithmetic (layers 0-3), like the conv biases
-        eD = {k: v for k, v in eD.items() if not (k.endswith("norm.bias") and not k.startswith("enc_blocks.4"))}
-        bad = {k: v for k, v in eD.items() if v > GRAD_TOL_SMOOTH}
-        assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:6]
-    else:
-        assert max(eD.values()) <= GRAD_VS_CONTROL * max(cD.values()) + GRAD_ABS
+        drop = lambda d: {k: v for k, v in d.items() if not (k.endswith("norm.bias") and not k.startswith("enc_blocks.4"))}
+        eD, cD = drop(eD), drop(cD)
+    assert max(eD.values()) <= GRAD_VS_CONTROL * max(cD.values()) + GRAD_ABS, (max(eD.values()), max(cD.values()))
+    assert float(np.median(list(eD.values()))) <= GRAD_VS_CONTROL * float(np.median(list(cD.values()))) + GRAD_ABS
+
+
+def test_discriminator_single_pass_gradients_continuous_activation():
+    """One D pass (LSGAN loss against target 1) with every PReLU slope at 1 -- no derivative jump, no second pass to
+    cancel against: the backward kernels' own error, every parameter tensor within GRAD_TOL_SMOOTH of the oracle."""
+    import ctypes as C
+    B = 8
+    s = build_segan(batch_size=B)
+    _set_slopes(s, 1.0)
+    sdD = cpu_state(s.D)
+    s = s.to(DEV)
+    s.D.train()
+    clean, noisy, _ = _pairs(B, 118)
+    shifts = [3, -1, 4, -2, 5]
+    de = s.D.engine
+    de.bind()
+    de.zero_grad()
+    loss = torch.zeros(1, device=DEV)
+    _, cx = de.forward(clean.to(DEV), noisy.to(DEV), shifts, training=True)
+    de.backward(cx, 1.0, 1.0, param_grads=True, loss_out=C.c_void_p(loss.data_ptr()))
+    gD = {k: de.grad_of(k).cpu() for k, _ in s.D.named_parameters()}
+    pD = {k: sdD[k].clone().requires_grad_(True) for k in O._trainable(sdD)}
+    with O.oracle_mode():
+        lo = O.discriminator_forward({**{k: v.clone() for k, v in sdD.items()}, **pD}, torch.cat((clean, noisy), 1), shifts)
+        losso = torch.nn.functional.mse_loss(lo.view(-1), torch.ones(B))
+        go = dict(zip(pD.keys(), torch.autograd.grad(losso, list(pD.values()))))
+    zero_exact = lambda k: k.startswith("enc_blocks") and (k.endswith("conv.bias") or
+                                                            (k.endswith("norm.bias") and not k.startswith("enc_blocks.4")))
+    rep = {k: rel_err(gD[k], g) for k, g in go.items() if not zero_exact(k)}
+    print("D single pass, slopes 1: loss %.5f vs %.5f, grads max %.3e (%s) median %.3e"
+          % (float(loss), float(losso), max(rep.values()), max(rep, key=rep.get), float(np.median(list(rep.values())))))
+    assert abs(float(loss) - float(losso)) <= 3e-3 * max(1.0, float(losso))
+    assert max(rep.values()) <= GRAD_TOL_SMOOTH, sorted(rep.items(), key=lambda kv: -kv[1])[:5]
 
 
 def test_generator_gradients_with_identical_discriminator():
