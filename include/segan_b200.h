@@ -94,7 +94,8 @@ int sg_set_ew_variant(int kind, int vec, int unroll, int cap);
 int sg_set_grad_dtype(int dtype);
 /* Split-K over the last, partial wave of sg_tapgemm_f_run's CTA-pair kernel (needs sg_tapgemm_f.sk_ws):
  * max_split = largest number of CTA pairs one leftover tile is split over (0 | 1 = off, default 16; < 0 keeps it);
- * atomic_steps = cost-model constant, the L2-atomic cost of one partial tile in k-steps (<= 0 keeps it).
+ * atomic_steps = cost-model constant: the finisher's cost of adding one 256-wide partial tile, in k-steps (<= 0
+ * keeps it; a value below 1e-3 also drops the model's fixed cost, i.e. forces the split -- sweeps and tests).
  * Returns the previous max_split.  Environment: SEGAN_B200_STREAMK, SEGAN_B200_SK_ATOMIC. */
 int sg_set_stream_k(int max_split, float atomic_steps);
 

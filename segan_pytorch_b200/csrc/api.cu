@@ -18,6 +18,7 @@ int64_t tapgemm_f_workspace_bytes();
 extern int g_cta_pair;
 extern int g_stream_k;
 extern double g_sk_atomic_steps;
+extern double g_sk_fixed_steps;
 int g_grad_dtype = SG_F16;
 }  // namespace sg
 
@@ -35,7 +36,10 @@ extern "C" int sg_set_cta_pair(int on) {
 extern "C" int sg_set_stream_k(int max_split, float atomic_steps) {
   const int prev = g_stream_k;
   if (max_split >= 0) g_stream_k = max_split;
-  if (atomic_steps > 0.f) g_sk_atomic_steps = atomic_steps;
+  if (atomic_steps > 0.f) {
+    g_sk_atomic_steps = atomic_steps;
+    g_sk_fixed_steps = atomic_steps < 1e-3f ? 0.0 : 60.0;      // a vanishing constant forces the split (sweeps, tests)
+  }
   return prev;
 }
 

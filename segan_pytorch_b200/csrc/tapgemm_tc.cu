@@ -644,7 +644,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0); prefetch_tmap(&tmA1); prefetch_tmap(&tmW);
     for (int s = 0; s < STAGES2; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 512); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 16); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(&ctl->tmem_base, 512);
@@ -843,7 +843,8 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive_leader(&ctl->tmem_empty[acc]);      // 2 x 256 arrivals release the accumulator
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);      // one arrival per warp: 2 CTAs x 8 warps release it
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
       if (partial && mt < m_tiles) {
         const int slot = pc.tile - it.dp_end;
@@ -1369,9 +1370,10 @@ constexpr int64_t SK_CNT_BYTES = 8192;
 constexpr int64_t SK_WS_BYTES = SK_CNT_BYTES + (int64_t)SK_MAX_PAIRS * 2 * 128 * 256 * 4;
 int64_t tapgemm_f_workspace_bytes() { return SK_WS_BYTES; }
 // SEGAN_B200_STREAMK: 0 = off, n = largest split factor per leftover tile (default 16);
-// SEGAN_B200_SK_ATOMIC: cost of one partial tile's atomics in k-steps (cost model of tapgemm_f_tc_launch)
+// SEGAN_B200_SK_ATOMIC / SEGAN_B200_SK_FIXED: cost-model constants in k-steps (tapgemm_f_tc_launch)
 int g_stream_k = [] { const char* e = getenv("SEGAN_B200_STREAMK"); return e ? atoi(e) : 16; }();
-double g_sk_atomic_steps = [] { const char* e = getenv("SEGAN_B200_SK_ATOMIC"); return e ? atof(e) : 2.5; }();
+double g_sk_atomic_steps = [] { const char* e = getenv("SEGAN_B200_SK_ATOMIC"); return e ? atof(e) : 4.5; }();
+double g_sk_fixed_steps = [] { const char* e = getenv("SEGAN_B200_SK_FIXED"); return e ? atof(e) : 60.0; }();
 
 int g_cta_pair = 1;   // sg_set_cta_pair(): 0 single-CTA tiles, 1 cta_group::2 pairs, 2 pairs + A reuse across taps (tc3)
 
@@ -1484,10 +1486,11 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
     const int pairs = ((m_tiles_all + 1) / 2) * p.n_tiles * p.ksplit;
     int npairs = num_sms() / 2;
     if (pairs < npairs) npairs = pairs;
-    // split-K over the last, partial wave (see PieceIter).  Cost model (times in units of one k-step = 256 rows x
-    // TN x 64 MACs on a pair): leaving the r leftover tiles whole costs `steps`; splitting each S ways costs
-    // steps / S for the MMAs plus the L2 atomics of S * r partial tiles, measured at about SK_ATOMIC_STEPS k-steps
-    // per partial tile (profiles/r2_streamk_sweep.txt).  Short-K layers are left alone.
+    // split-K over the last, partial wave (see PieceIter).  Cost model in k-steps of this launch's tile (measured,
+    // profiles/r2_streamk_sweep.txt): leaving the leftover tiles whole costs `steps`; splitting each over S pairs
+    // costs steps / S for the MMAs, the finisher's ordered sum of S partial tiles (g_sk_atomic_steps each for a
+    // 256-wide tile) and a fixed ~g_sk_fixed_steps of fences, counters and pipeline refill.  Short-K layers are
+    // left alone.
     if (q->sk_ws != nullptr && g_stream_k > 1 && p.ksplit == 1 && q->bn_stats == nullptr && npairs <= SK_MAX_PAIRS &&
         pairs > npairs && pairs % npairs != 0) {
       const int r = pairs % npairs;
@@ -1496,11 +1499,12 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
       int best_s = 1;
       double best = (double)steps;
       const int s_max = npairs / r < g_stream_k ? npairs / r : g_stream_k;
+      const double per_partial = g_sk_atomic_steps * 256.0 / p.TN;      // narrower tiles have shorter k-steps
       for (int S = 2; S <= s_max; ++S) {
-        const double c = (double)steps / S + g_sk_atomic_steps * S * r;
-        if (c < best * 0.9) { best = c; best_s = S; }
+        const double c = (double)steps / S + per_partial * S + g_sk_fixed_steps;
+        if (c < best) { best = c; best_s = S; }
       }
-      if (best_s > 1 && steps >= 2 * best_s) {
+      if (best_s > 1 && best < 0.92 * steps && steps >= 2 * best_s) {
         p.sk_dp_tiles = (pairs / npairs) * npairs;
         p.sk_split = best_s;
         p.sk_cnt = reinterpret_cast<unsigned int*>(q->sk_ws);

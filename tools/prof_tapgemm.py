@@ -11,7 +11,7 @@ from segan_pytorch_b200._lib import SG_BF16, SG_F16
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 REP = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 COMPARE = sys.argv[3] if len(sys.argv) > 3 else ""
-MODEL_ATOMIC = float(sys.argv[4]) if len(sys.argv) > 4 else 2.5
+MODEL_ATOMIC = float(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[3] == "streamk" else 4.5
 dev = "cuda"
 h = lambda *s: (torch.randn(*s, device=dev) * 0.5).half()
 b = lambda *s: (torch.randn(*s, device=dev) * 0.5).bfloat16()
@@ -98,7 +98,30 @@ def conv_wgrad(cin, cout, R):
            lambda: E.run_w(g, R, SG_BF16, a, None, R, 4, SG_BF16, 4 * cin, cout, taps, dw, B, ksplit=ks, backend=1), fl)
 
 
+def wave0():
+    """The waveform-end layer as it runs in the step: single-tap GEMM over the 64-column im2col (K = 64, N = 64)."""
+    col = h(B, 4096, 64)
+    w = h(1, 64, 64)
+    bias = torch.randn(64, device=dev)
+    out = torch.empty(B, 4096, 64, device=dev, dtype=torch.float16)
+    taps = E.tap_ranges("full", 0, 64, 64)
+    fl = 2.0 * B * 4096 * 64 * 64
+    timeit("wave0 im2col-GEMM 64x64 R=4096", lambda: E.run_f(col, None, 4096, 0, SG_F16, w, SG_F16, 64, 64, taps, out,
+                                                              SG_F16, 4096, 0, 0, 4096, B, bias=bias, bias_mod=64,
+                                                              d_lo=0, d_hi=0, w_tap0=4, backend=1), fl)
+
+
+ONE = {"wave0": wave0, "enc1": lambda: conv_fwd(64, 128, 1024), "enc3": lambda: conv_fwd(256, 512, 64),
+       "enc4": lambda: conv_fwd(512, 1024, 16), "dec1": lambda: deconv_fwd(1024, 256, 64),
+       "dgrad3": lambda: conv_dgrad(256, 512, 64), "wgrad3": lambda: conv_wgrad(256, 512, 64),
+       "wgrad4": lambda: conv_wgrad(512, 1024, 16)}
+
 if __name__ == "__main__":
+    if COMPARE == "one":                # a single shape (ncu captures): python tools/prof_tapgemm.py 300 2 one enc3
+        COMPARE = ""
+        for name in sys.argv[4:]:
+            ONE[name]()
+        sys.exit(0)
     if COMPARE == "streamk":
         for fn, args in ((conv_fwd, (64, 128, 1024)), (conv_fwd, (128, 256, 256)), (conv_fwd, (256, 512, 64)),
                          (conv_fwd, (512, 1024, 16)), (deconv_fwd, (2048, 512, 16)), (deconv_fwd, (1024, 256, 64)),
