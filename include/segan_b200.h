@@ -323,6 +323,21 @@ int sg_l1_loss_bwd(const float* y, const float* clean, int64_t n, float weight, 
                    float* gy, int accumulate, float grad_scale /* multiplies gy only */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * WSEGAN's spectral term (model.py:638-653): pow_weight * mean| 10 log10(|STFT(G)|^2 + 1e-19) - 10 log10(|STFT(clean)|^2
+ * + 1e-19) |, torch.stft(n_fft 2048, hop 160, win_length 320 rectangular, centre-padded, center=True, normalized).
+ * Only 320 of a frame's 2048 samples are non-zero, so the STFT of a batch is ONE dense GEMM -- frames [B*(1 + L/160)][320]
+ * x DFT [320][re | im of the 1025 bins] -- run by sg_tapgemm_f_run with a single tap; these are the kernels around it:
+ *   sg_stft_frames      frames[b][t][n] = x[b][reflect(160 t + n - 160)]                       (16-bit A operand)
+ *   sg_logpow_l1        X_gen, X_clean fp32 [rows][ld] (re of bin f at column f, im at column half + f):
+ *                       loss_out += weight * mean|...| ; g_x (16-bit, may be NULL) = grad_scale * d loss / d X_gen
+ *   sg_stft_frames_fold g_wave[b][reflect(160 t + n - 160)] += scale * g_frames[b][t][n]        (overlap-add)
+ * ------------------------------------------------------------------------------------------ */
+int sg_stft_frames(const float* x, int batch, int L, void* frames, int dtype, void* stream);
+int sg_logpow_l1(const float* x_gen, const float* x_clean, int64_t rows, int bins, int half, int ld, float weight,
+                 float* loss_out, void* g_x, int g_dtype, float grad_scale, void* stream);
+int sg_stft_frames_fold(const float* g_frames, int batch, int L, float scale, float* g_wave, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimisers on flat fp32 buffers (torch.optim.RMSprop / Adam as used at model.py:221-225).
  * grad_scale multiplies the gradient first (1/world_size after an all-reduce SUM).
  * clear_grad != 0 zeroes `grad` as it is read (the next backward pass accumulates from zero: no separate fill).

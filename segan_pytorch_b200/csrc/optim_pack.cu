@@ -56,18 +56,39 @@ rmsprop_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__
   }
 }
 // torch.optim.Adam (amsgrad=False, weight_decay=0)
-__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                            float bc1, float bc2_sqrt, float gscale, int clear) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale, int clear) {
+  const int64_t n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float step = lr / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = p4[i], gv = g4[i], mv = m4[i], vv = v4[i];
+    float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = gp[j] * gscale;
+      const float mi = b1 * mp[j] + (1.f - b1) * gi;
+      const float vi = b2 * vp[j] + (1.f - b2) * gi * gi;
+      mp[j] = mi;
+      vp[j] = vi;
+      pp[j] = pp[j] - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+    p4[i] = pv; m4[i] = mv; v4[i] = vv;
+    if (clear) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t i = n4 * 4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gi = g[i] * gscale;
     if (clear) g[i] = 0.f;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = p[i] - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
   }
 }
 
@@ -414,7 +435,7 @@ extern "C" int sg_adam_step(float* param, float* grad, float* exp_avg, float* ex
                             void* stream) {
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<4 * NUM_SMS, 256, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1,
+  adam_kernel<<<8 * NUM_SMS, 256, 0, ST>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1,
                                            sqrtf(bc2), grad_scale, clear_grad);
   SG_CHECK_LAUNCH();
   return SG_OK;

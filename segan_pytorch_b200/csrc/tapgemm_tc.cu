@@ -213,7 +213,8 @@ struct FTcParams {
   int TR, TB, TN;            // M tile = TB batches x TR rows (<= 128), N tile
   int m_tiles_per_b, b_tiles, n_tiles;
   uint32_t idesc;
-  int dbg;                   // timing experiments only (SEGAN_B200_DEBUG): 1 skip B loads, 2 skip A loads, 4 skip stores
+  int dbg;                   // timing experiments only (SEGAN_B200_DEBUG): 1 skip B loads, 2 skip A loads, 4 skip stores,
+                             // 8 skip the split-K partial stores, 16 skip the finisher's partial loads
   double* stats;             // fused BatchNorm statistics [SG_STAT_SLICES][2][nc] (CTA-pair kernel), or nullptr
   // CTA-pair kernel only:
   int sk_dp_tiles;           // tiles [0, sk_dp_tiles) are tile-strided; each of the rest is split along K over
@@ -223,6 +224,7 @@ struct FTcParams {
   void* out2;                // fused PReLU output (16-bit, out's dtype and column geometry), or nullptr
   int out2_halo;             // reflect halo rows of out2 (its buffer has out_rows + 2 * out2_halo rows per batch element)
   const float* slope; int slope_mod;
+  int bias_mask, slope_mask; // mod - 1 when the modulus is a power of two (the channel counts are), else -1
 };
 
 struct SharedCtl {
@@ -508,30 +510,46 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 // zeroed for the next launch.  No pair ever waits for another one.  The split factor is chosen by the host: the
 // partial sums cost L2 atomics in proportion to sk_split, the tail shrinks as 1 / sk_split (tapgemm_f_tc_launch).
 struct Piece {
-  int tile;      // tile index (legacy decode: mp fastest, then ksplit, then nt)
-  int kb, ke;    // k-step range [kb, ke) of the tile's `total` steps (stream-K pieces; whole tile otherwise)
+  int tile;      // tile index (mp fastest, then ksplit, then nt)
+  int mp, rest;  // tile % m_pairs, tile / m_pairs (tracked incrementally: no division per tile)
+  int kb, ke;    // k-step range [kb, ke) of the tile's `total` steps (split-K pieces; whole tile otherwise)
   int total;
 };
 
+// The waveform-end GEMMs have ONE k-step per tile and 65 tiles per CTA: whatever a role executes per tile is their
+// critical path (ncu, profiles/r2_v1_ncu_tapgemm.md: ~2400 warp instructions per tile and epilogue warp, a dozen
+// integer divisions among them, made a 314 MB pass take 127 us).  The iterator therefore advances (mp, rest) by
+// addition and caches the k-step count per N tile; the roles hoist everything that does not depend on the tile.
 struct PieceIter {
   int m_pairs, npairs, dp_end, total_tiles, pair_id;
-  int next_dp;
+  int next_dp, cur_mp, cur_rest;
+  int cache_rest, cache_steps;
   bool sk_done;
 
-  __device__ __forceinline__ int steps_of(const FTcParams& p, int tile) const {
-    const int rest = tile / m_pairs;
-    return f_num_steps(p, p.n_lo + (rest / p.ksplit) * p.TN, rest % p.ksplit);
+  __device__ __forceinline__ int steps_of_rest(const FTcParams& p, int rest) {
+    if (rest != cache_rest) {
+      cache_rest = rest;
+      cache_steps = p.ksplit == 1 ? f_num_steps(p, p.n_lo + rest * p.TN, 0)
+                                  : f_num_steps(p, p.n_lo + (rest / p.ksplit) * p.TN, rest % p.ksplit);
+    }
+    return cache_steps;
   }
   __device__ __forceinline__ void init(const FTcParams& p, int m_pairs_, int total_tiles_, int pair_id_, int npairs_) {
     m_pairs = m_pairs_; npairs = npairs_; total_tiles = total_tiles_; pair_id = pair_id_;
     dp_end = p.sk_dp_tiles < total_tiles_ ? p.sk_dp_tiles : total_tiles_;
     next_dp = pair_id_;
+    cur_rest = pair_id_ / m_pairs_;
+    cur_mp = pair_id_ - cur_rest * m_pairs_;
+    cache_rest = -1; cache_steps = 0;
     sk_done = false;
   }
   __device__ __forceinline__ bool next(const FTcParams& p, Piece& pc) {
     if (next_dp < dp_end) {
-      pc.tile = next_dp; pc.kb = 0; pc.total = pc.ke = steps_of(p, next_dp);
+      pc.tile = next_dp; pc.mp = cur_mp; pc.rest = cur_rest;
+      pc.kb = 0; pc.total = pc.ke = steps_of_rest(p, cur_rest);
       next_dp += npairs;
+      cur_mp += npairs;
+      while (cur_mp >= m_pairs) { cur_mp -= m_pairs; ++cur_rest; }
       return true;
     }
     if (sk_done || dp_end >= total_tiles) return false;
@@ -539,8 +557,9 @@ struct PieceIter {
     const int t = dp_end + pair_id / p.sk_split;
     if (t >= total_tiles) return false;
     const int part = pair_id % p.sk_split;
-    const int s = steps_of(p, t);
-    pc.tile = t; pc.total = s;
+    pc.tile = t; pc.rest = t / m_pairs; pc.mp = t - pc.rest * m_pairs;
+    const int s = steps_of_rest(p, pc.rest);
+    pc.total = s;
     pc.kb = (int)((long long)s * part / p.sk_split);
     pc.ke = (int)((long long)s * (part + 1) / p.sk_split);
     return pc.kb < pc.ke;
@@ -549,8 +568,10 @@ struct PieceIter {
 
 // v[j] += bias[(n_abs + j) % bias_mod], 16-byte loads (bias_mod is a multiple of 64, the chunk 32-aligned, the vector
 // a 16-byte aligned view)
+__device__ __forceinline__ int f_mod(int x, int mod, int mask) { return mask >= 0 ? (x & mask) : (x % mod); }
+
 __device__ __forceinline__ void f_add_bias(const FTcParams& p, float (&v)[32], int n_abs) {
-  const float4* bp = reinterpret_cast<const float4*>(p.bias + (n_abs % p.bias_mod));
+  const float4* bp = reinterpret_cast<const float4*>(p.bias + f_mod(n_abs, p.bias_mod, p.bias_mask));
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 t = __ldg(bp + j);
@@ -580,7 +601,7 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
   float sl[32];
   if (p.slope != nullptr) {
     // 16-byte loads: slope / bias vectors are 16-byte aligned views and the chunk is 32-aligned
-    const float4* sp = reinterpret_cast<const float4*>(p.slope + (n_abs % p.slope_mod));
+    const float4* sp = reinterpret_cast<const float4*>(p.slope + f_mod(n_abs, p.slope_mod, p.slope_mask));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 t = __ldg(sp + j);
@@ -671,13 +692,12 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     if (lane < 2) {
       int stage = 0; uint32_t phase = 0;
       while (it.next(p, pc)) {
-        const int mp = pc.tile % m_pairs;
-        const int rest = pc.tile / m_pairs;
-        const int ks = rest % p.ksplit;
-        const int nt = rest / p.ksplit;
-        const int mt = 2 * mp + (int)rank;
-        const int b0 = (mt / p.m_tiles_per_b) * p.TB;
-        const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * p.TR;
+        const int ks = p.ksplit == 1 ? 0 : pc.rest % p.ksplit;
+        const int nt = p.ksplit == 1 ? pc.rest : pc.rest / p.ksplit;
+        const int mt = 2 * pc.mp + (int)rank;
+        const int mtb = p.m_tiles_per_b == 1 ? mt : mt / p.m_tiles_per_b;
+        const int b0 = mtb * p.TB;
+        const int m0 = p.m_lo + (mt - mtb * p.m_tiles_per_b) * p.TR;
         const int n0 = p.n_lo + nt * p.TN;
         int step = 0, sel = 0;              // step: every (tap, k-block) of the tile; sel: those of this k-split
         for (int d = p.d_lo; d <= p.d_hi; ++d) {
@@ -748,6 +768,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     float* colstat = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES + 256);
     const int et = threadIdx.x - 64;           // 0..255 within the epilogue warps
     int stat_nt = -1;
+    const int tb = row / p.TR, tr = row - tb * p.TR;      // this thread's (batch, row) inside an M tile: tile-invariant
     auto flush_stats = [&](int nt_done) {
       epi2_bar_sync();
       const int n0s = p.n_lo + nt_done * p.TN;
@@ -765,15 +786,13 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       epi2_bar_sync();
     }
     while (it.next(p, pc)) {
-      const int mp = pc.tile % m_pairs;
-      const int rest = pc.tile / m_pairs;
-      const int ks = rest % p.ksplit;
-      const int nt = rest / p.ksplit;
-      const int mt = 2 * mp + (int)rank;
-      const int b0 = (mt / p.m_tiles_per_b) * p.TB;
-      const int m0 = p.m_lo + (mt % p.m_tiles_per_b) * p.TR;
+      const int ks = p.ksplit == 1 ? 0 : pc.rest % p.ksplit;
+      const int nt = p.ksplit == 1 ? pc.rest : pc.rest / p.ksplit;
+      const int mt = 2 * pc.mp + (int)rank;
+      const int mtb = p.m_tiles_per_b == 1 ? mt : mt / p.m_tiles_per_b;
+      const int b0 = mtb * p.TB;
+      const int m0 = p.m_lo + (mt - mtb * p.m_tiles_per_b) * p.TR;
       const int n0 = p.n_lo + nt * p.TN;
-      const int tb = row / p.TR, tr = row % p.TR;
       const int b = b0 + tb, m = m0 + tr;
       const bool valid = (mt < m_tiles) && (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
       const bool partial = pc.kb != 0 || pc.ke != pc.total;         // one K range of a split tile
@@ -813,6 +832,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         tmem_ld_wait();
         if (partial) {
           float4* dst = myslot + (c0 >> 6) * 256;                   // this warp's (c0 / 64)-th chunk
+          if (!(p.dbg & 8))
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             __stcg(dst + j * 32, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -867,6 +887,10 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
               for (int sp = 0; sp < p.sk_split; ++sp) {
                 const float4* src = base0 + (int64_t)sp * 2 * slot_f4 + (c0 >> 6) * 256;
                 float4 t[8];
+                if (p.dbg & 16) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else
 #pragma unroll
                 for (int j = 0; j < 8; ++j) t[j] = __ldcg(src + j * 32);
 #pragma unroll
@@ -1428,6 +1452,8 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   p.stats = q->bn_stats;
   p.sk_dp_tiles = 0x7fffffff; p.sk_split = 1; p.sk_ws = nullptr; p.sk_cnt = nullptr;
   p.out2 = q->out2; p.out2_halo = q->out2_halo; p.slope = q->slope; p.slope_mod = q->slope_mod;
+  p.bias_mask = (p.bias_mod & (p.bias_mod - 1)) == 0 ? p.bias_mod - 1 : -1;
+  p.slope_mask = (p.slope_mod > 0 && (p.slope_mod & (p.slope_mod - 1)) == 0) ? p.slope_mod - 1 : -1;
   CUtensorMap tmA0, tmA1, tmW;
   const int a_buf_rows = q->a_rows + 2 * q->a_halo;
   int rc = make_map3(&tmA0, q->a0, q->a_dtype, q->a0_c, a_buf_rows, q->batch, p.TR, p.TB);
@@ -1504,6 +1530,10 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
         const double c = (double)steps / S + per_partial * S + g_sk_fixed_steps;
         if (c < best) { best = c; best_s = S; }
       }
+      static const bool verbose = getenv("SEGAN_B200_SK_VERBOSE") != nullptr;
+      if (verbose)
+        fprintf(stderr, "tapgemm_f split-K: %d pair tiles on %d pairs, %d left over, %d k-steps, TN %d -> split %d\n",
+                pairs, npairs, r, steps, p.TN, (best_s > 1 && best < 0.92 * steps && steps >= 2 * best_s) ? best_s : 1);
       if (best_s > 1 && best < 0.92 * steps && steps >= 2 * best_s) {
         p.sk_dp_tiles = (pairs / npairs) * npairs;
         p.sk_split = best_s;
