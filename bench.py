@@ -154,6 +154,69 @@ def cpu_reference_steps(steps, warmup, B):
     return B * len(times) / total, total / len(times), torch.get_num_threads()
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    import platform
+    return platform.processor() or "unknown"
+
+
+def cpu_baseline_section4(nthreads):
+    """BASELINE.md section 4 on this box's host cores: (i) config 1 -- Generator forward on 1 x 16384, eval / no_grad,
+    median of 20 after 3 warm-ups; (ii) the train-step analogue at B=16, 1 warm-up + 3 timed steps; both with oneDNN
+    off (the correctness oracle) and as configured by default (what a reference user gets)."""
+    import contextlib
+    import random
+    from oracle import segan_oracle as O
+    from tests.util import build_segan, cpu_state
+    torch.set_num_threads(nthreads)
+    out = {"cpu_model": cpu_model(), "nproc": os.cpu_count(), "torch_threads": torch.get_num_threads(),
+           "torch": torch.__version__, "impl": "oracle port of generator.py:180-230 / model.py:283-321"}
+    s = build_segan(batch_size=16)
+    sdG, sdD = cpu_state(s.G), cpu_state(s.D)
+    g = torch.Generator().manual_seed(111)
+    x1 = 0.3 * torch.randn(1, 1, 16384, generator=g)
+    z1 = torch.randn(1, 1024, 16, generator=g)
+    clean, noisy = synth_batch(16, 111)
+    clean, noisy = clean.unsqueeze(1), noisy.unsqueeze(1)
+    ref_y = None
+    for tag, ctx in (("onednn_off", contextlib.nullcontext), ("onednn_default", O.onednn_as_configured)):
+        with ctx():
+            with torch.no_grad():
+                ts = []
+                for i in range(23):
+                    t0 = time.perf_counter()
+                    y = O.generator_forward(sdG, x1, z1)
+                    if i >= 3:
+                        ts.append(time.perf_counter() - t0)
+            ts.sort()
+            med = ts[len(ts) // 2]
+            if ref_y is None:
+                ref_y = y
+            sG = {k: v.clone() for k, v in sdG.items()}
+            sD = {k: v.clone() for k, v in sdD.items()}
+            sqG = {k: torch.zeros_like(sG[k]) for k in O._trainable(sG)}
+            sqD = {k: torch.zeros_like(sD[k]) for k in O._trainable(sD)}
+            random.seed(111)
+            tt = []
+            for it in range(4):
+                z = torch.randn(16, 1024, 16)
+                sh = [O.draw_phase_shifts(5, 5) for _ in range(3)]
+                t0 = time.perf_counter()
+                O.segan_train_step(sG, sD, sqG, sqD, clean, noisy, z, sh, l1_weight=100.0)
+                if it >= 1:
+                    tt.append(time.perf_counter() - t0)
+        out[tag] = {"g_forward_1x16384_ms_median20": med * 1e3, "g_forward_windows_per_s": 1.0 / med,
+                    "g_forward_max_abs_vs_onednn_off": float((y - ref_y).abs().max()),
+                    "train_step_b16_s": sum(tt) / len(tt), "train_step_windows_per_s": 16 * len(tt) / sum(tt)}
+    return out
+
+
 def run_reference_arm(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -174,6 +237,118 @@ def run_reference_arm(args, emit=print):
         "gpu_launches": 0,
     }
     emit(json.dumps(line))
+
+
+def gpu_extras(dev, B, s_plus):
+    """BASELINE.json configs 4 and 5 as extra keys (rank 0, N=1; not the headline):
+    config 4 -- WSEGAN (--wsegan --misalign_pair) train step at batch B, device-resident inputs;
+    config 5 -- clean.py streaming inference over 10 000 windows incl. de-emphasis: (a) device-resident int16 PCM ->
+    enhanced float windows (pre-emphasis, G, segmented de-emphasis), (b) SEGAN.clean_files over wav files on disk
+    (decode, upload, G, de-emphasis, download, float32 wav writing: the host I/O included, wall clock)."""
+    import random
+    import shutil
+    import tempfile
+    import numpy as np
+    from scipy.io import wavfile
+    from segan_pytorch_b200 import _lib, engine as E
+    from segan_pytorch_b200.engine import _p, _stream
+    from segan_pytorch_b200.segan.models import WSEGAN
+    from tests.util import load_opts, seed_all
+    out = {}
+    # ---- config 4
+    opts = load_opts(batch_size=B, wsegan=True, misalign_pair=True, z_device="cuda")
+    seed_all(111)
+    w = WSEGAN(opts).to(dev)
+    w.G.train()
+    w.D.train()
+    Gopt, Dopt = w.build_optimizers(opts)
+    clean_h, noisy_h = synth_batch(B, 211)
+    clean, noisy = clean_h.to(dev).unsqueeze(1), noisy_h.to(dev).unsqueeze(1)
+    random.seed(211)
+    losses = torch.zeros(4, device=dev)
+    names = ["utt_%d.wav" % i for i in range(B)]
+    for _ in range(4):
+        w.train_step(clean, noisy, Gopt, Dopt, 0.0, uttname=names, losses=losses)
+    torch.cuda.synchronize()
+    n4 = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n4):
+        w.train_step(clean, noisy, Gopt, Dopt, 0.0, uttname=names, losses=losses)
+    e1.record()
+    torch.cuda.synchronize()
+    ms4 = e0.elapsed_time(e1) / n4
+    out["config4_wsegan_step"] = {
+        "value": B / (ms4 * 1e-3), "unit": "windows/s", "ms_per_step": ms4, "batch": B, "steps": n4,
+        "what": "WSEGAN --misalign_pair step (D on real / fake / misaligned pairs, RMSprop, G loss = adversarial + "
+                "STFT log-power L1 as a tensor-core GEMM), device-resident synthetic pairs, eager launches",
+        "last_losses": losses.tolist()}
+    del w, Gopt, Dopt
+    torch.cuda.empty_cache()
+    # ---- config 5
+    N, n_files, per_file = 16384, 40, 250                       # 40 files x 250 windows = 10 000 windows
+    rng = np.random.RandomState(5)
+    s_plus.G.eval()
+    total = n_files * per_file
+    pcm = torch.from_numpy(rng.randint(-9000, 9000, size=(per_file * N,)).astype(np.int16))
+    # (a) device-resident: one file's int16 PCM on the device, processed n_files times in batches of B windows
+    pcm_d = pcm.view(per_file, N).to(dev)
+    prev = torch.full((per_file,), 0x7fffffff, dtype=torch.int32)
+    prev[1:] = pcm.view(per_file, N)[:-1, -1].to(torch.int32)
+    prev_d = prev.to(dev)
+    valid_d = torch.full((per_file,), N, dtype=torch.int32, device=dev)
+    seg = torch.tensor([[0, per_file * N]], dtype=torch.int64, device=dev)
+    x = torch.empty(per_file, 1, N, device=dev)
+    y = torch.empty(per_file, N, device=dev)
+    o = torch.empty_like(y)
+    zb = torch.randn(per_file, 1024, 16, device=dev)
+    coef = float(s_plus.preemph)
+
+    def one_file():
+        _lib.call("sg_pcm16_to_wave", _p(pcm_d), _p(prev_d), per_file, N, coef, _p(x), _p(valid_d), _stream())
+        with torch.no_grad():
+            for b0 in range(0, per_file, B):
+                b1 = min(per_file, b0 + B)
+                y[b0:b1] = s_plus.G(x[b0:b1], z=zb[b0:b1]).view(b1 - b0, N)
+        _lib.call("sg_deemphasis_segments", _p(y), _p(seg), 1, coef, _p(o), _stream())
+    for _ in range(2):
+        one_file()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_files):
+        one_file()
+    e1.record()
+    torch.cuda.synchronize()
+    ms5a = e0.elapsed_time(e1)
+    # (b) through wav files on disk
+    tmp = tempfile.mkdtemp(prefix="segan_b200_bench_")
+    try:
+        src, dst = os.path.join(tmp, "in"), os.path.join(tmp, "out")
+        os.makedirs(src)
+        paths = []
+        for i in range(n_files):
+            pth = os.path.join(src, "f%03d.wav" % i)
+            wavfile.write(pth, 16000, np.roll(pcm.numpy(), 977 * i))
+            paths.append(pth)
+        s_plus.clean_files(paths[:4], dst, batch=B)                # warm-up (allocator, pinned pools)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nwin = s_plus.clean_files(paths, dst, batch=B)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    s_plus.G.train()
+    out["config5_clean_streaming"] = {
+        "windows": total, "unit": "windows/s",
+        "device_resident": {"value": total / (ms5a * 1e-3), "ms_total": ms5a,
+                            "what": "int16 PCM in HBM -> float + pre-emphasis -> G (fp16 operands, batches of %d) -> "
+                                    "segmented de-emphasis, CUDA events" % B},
+        "with_host_io": {"value": nwin / dt, "s_total": dt, "files": n_files,
+                         "what": "SEGAN.clean_files: %d wav files of %d windows on local disk -> float32 wavs on disk; "
+                                 "reader thread (decode), copy streams, writer thread; wall clock" % (n_files, per_file)}}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -203,6 +378,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample size of the reference arm")
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip BASELINE configs 4 / 5 (extra keys)")
     ap.add_argument("--backend", default=None, help="tcgen05 (default) | ffma")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -264,6 +440,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count - launches0
+    ngraphs = [len(v.graphs) for v in getattr(s, "_step_graphs", {}).values() if getattr(v, "graphs", None) is not None]
     clocks = sampler.stop() if rank == 0 else None
     # ---- timed region 1b: the same steps again with a CUDA-event pair around every C-ABI call
     #      (live per-kernel times for the roofline object; the ~600 extra event records per step
@@ -357,6 +534,9 @@ def main():
         barrier()
     ms_inf_dev = h0.elapsed_time(h1)
     s.G.train()
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = gpu_extras(dev, B, s)
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # max over ranks
@@ -411,7 +591,8 @@ def main():
         wps, spstep, cores = cpu_reference_steps(args.cpu_baseline_steps, 1, args.ref_batch)
         cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
                "sample": "%d timed steps of a %d-window batch of the same workload (oracle, oneDNN off)"
-                         % (args.cpu_baseline_steps, args.ref_batch)}
+                         % (args.cpu_baseline_steps, args.ref_batch),
+               "baseline_md_section4": cpu_baseline_section4(cores)}
     line = {
         "metric": "16384-sample windows/sec (G+D train step)", "value": value, "unit": "windows/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -422,7 +603,10 @@ def main():
                    "z": "device RNG (opts.z_device='cuda')", "backend": args.backend or "tcgen05",
                    "schedule": (("side streams (wgrad chains, D(real) pass next to G forward + D(fake) pass)"
                                  if overlap_on else "single stream") +
-                                (", step replayed from 3 CUDA graphs" if graphs_on else ", eager launches")),
+                                (", step replayed from %s CUDA graph(s)%s" % (
+                                    "/".join(str(n) for n in ngraphs) or "?",
+                                    " (NCCL all-reduce chunks captured inside)" if world > 1 and ngraphs == [1] else "")
+                                 if graphs_on else ", eager launches")),
                    "l2": "per-step working set (packed weights 0.4 GB + activations > 2 GB) exceeds the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": ms_e2e / args.steps,
@@ -437,6 +621,7 @@ def main():
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "extra_configs": extras,
     }
     emit(json.dumps(line))
     if world > 1:

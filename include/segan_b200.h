@@ -160,6 +160,11 @@ typedef struct sg_tapgemm_f {
 int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream);
 /* size of sg_tapgemm_f.sk_ws (device memory, zero-filled once by the caller) */
 int64_t sg_tapgemm_f_workspace_bytes(void);
+/* Diagnostics (SEGAN_B200_DEBUG bit 20): per-CTA phase timeline of the last CTA-pair tap-GEMM launch, 32 globaltimer
+ * words (ns) per CTA for up to 160 CTAs -- [0] start, then per tile piece: accumulator ready, epilogue done, (split
+ * tiles, bit 63 set) finisher done; last non-zero word = exit.  Copies min(max_words, 5120) words to the HOST buffer
+ * and returns the count (-1 on a CUDA error).  Not used by the product path. */
+int sg_debug_timeline(unsigned long long* host_out, int max_words);
 
 /* ------------------------------------------------------------------------------------------
  * Tap-GEMM, weight-gradient form ("W"):
@@ -328,11 +333,13 @@ int sg_l1_loss_bwd(const float* y, const float* clean, int64_t n, float weight, 
  * Only 320 of a frame's 2048 samples are non-zero, so the STFT of a batch is ONE dense GEMM -- frames [B*(1 + L/160)][320]
  * x DFT [320][re | im of the 1025 bins] -- run by sg_tapgemm_f_run with a single tap; these are the kernels around it:
  *   sg_stft_frames      frames[b][t][n] = x[b][reflect(160 t + n - 160)]                       (16-bit A operand)
+ *                       split != 0: rows of 960 = hi | lo | hi with x = hi + lo (two 16-bit halves, ~22 bits): against
+ *                       the DFT operand [Dhi ; Dhi ; Dlo] one K = 960 GEMM gives the fp32-grade spectrum
  *   sg_logpow_l1        X_gen, X_clean fp32 [rows][ld] (re of bin f at column f, im at column half + f):
  *                       loss_out += weight * mean|...| ; g_x (16-bit, may be NULL) = grad_scale * d loss / d X_gen
  *   sg_stft_frames_fold g_wave[b][reflect(160 t + n - 160)] += scale * g_frames[b][t][n]        (overlap-add)
  * ------------------------------------------------------------------------------------------ */
-int sg_stft_frames(const float* x, int batch, int L, void* frames, int dtype, void* stream);
+int sg_stft_frames(const float* x, int batch, int L, void* frames, int dtype, int split, void* stream);
 int sg_logpow_l1(const float* x_gen, const float* x_clean, int64_t rows, int bins, int half, int ld, float weight,
                  float* loss_out, void* g_x, int g_dtype, float grad_scale, void* stream);
 int sg_stft_frames_fold(const float* g_frames, int batch, int L, float scale, float* g_wave, void* stream);

@@ -29,14 +29,31 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+_KEEP_ONEDNN = False
+
+
 @contextlib.contextmanager
 def oracle_mode():
     prev = torch.backends.mkldnn.enabled
-    torch.backends.mkldnn.enabled = False
+    torch.backends.mkldnn.enabled = bool(_KEEP_ONEDNN and prev)
     try:
         yield
     finally:
         torch.backends.mkldnn.enabled = prev
+
+
+@contextlib.contextmanager
+def onednn_as_configured():
+    """TIMING ONLY (bench.py cpu_baseline): leave torch.backends.mkldnn as the user has it --
+    what a reference user gets by default -- instead of switching it off.  Never used as the parity oracle: the
+    oneDNN transposed convolution of this torch build is numerically wrong multi-threaded."""
+    global _KEEP_ONEDNN
+    prev = _KEEP_ONEDNN
+    _KEEP_ONEDNN = True
+    try:
+        yield
+    finally:
+        _KEEP_ONEDNN = prev
 
 
 # --------------------------------------------------------------------------------------

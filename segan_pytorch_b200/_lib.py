@@ -89,12 +89,12 @@ _SIGS = {
     "sg_preemphasis": [_vp, _i64, _f, _vp, _vp],
     "sg_pcm16_to_wave": [_vp, _vp, _i64, _i, _f, _vp, _vp, _vp],
     "sg_deemphasis_segments": [_vp, _vp, _i, _f, _vp, _vp],
-    "sg_stft_frames": [_vp, _i, _i, _vp, _i, _vp],
+    "sg_stft_frames": [_vp, _i, _i, _vp, _i, _i, _vp],
     "sg_logpow_l1": [_vp, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _i, _f, _vp],
     "sg_stft_frames_fold": [_vp, _i, _i, _f, _vp, _vp],
 }
 EXPORTS = ["sg_abi_version", "sg_last_error", "sg_device_ok", "sg_set_cta_pair", "sg_set_ew_variant",
-           "sg_set_grad_dtype", "sg_set_stream_k", "sg_tapgemm_f_workspace_bytes"] + list(_SIGS)
+           "sg_set_grad_dtype", "sg_set_stream_k", "sg_tapgemm_f_workspace_bytes", "sg_debug_timeline"] + list(_SIGS)
 
 _lib = None
 

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsegan_b200.so")
-SOURCES = ["api.cu", "tapgemm_ref.cu", "tapgemm_tc.cu", "wave_layers.cu", "elementwise.cu", "optim_pack.cu", "snorm.cu", "stft.cu"]
+SOURCES = ["api.cu", "tapgemm_ref.cu", "tapgemm_tc.cu", "wave_layers.cu", "elementwise.cu", "stream_ew.cu", "optim_pack.cu", "snorm.cu", "stft.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

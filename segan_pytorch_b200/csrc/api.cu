@@ -15,6 +15,7 @@ int tapgemm_w_ffma_launch(const sg_tapgemm_w* q, cudaStream_t st);
 int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st);
 int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st);
 int64_t tapgemm_f_workspace_bytes();
+int tapgemm_f_debug_timeline(unsigned long long* host_out, int max_words);
 extern int g_cta_pair;
 extern int g_stream_k;
 extern double g_sk_atomic_steps;
@@ -68,6 +69,9 @@ static int check_taps(const int32_t* k_lo, const int32_t* k_hi, const int32_t* n
 }
 
 extern "C" int64_t sg_tapgemm_f_workspace_bytes(void) { return tapgemm_f_workspace_bytes(); }
+extern "C" int sg_debug_timeline(unsigned long long* host_out, int max_words) {
+  return tapgemm_f_debug_timeline(host_out, max_words);
+}
 
 extern "C" int sg_tapgemm_f_run(const sg_tapgemm_f* p, void* stream) {
   SG_CHECK_ARG(p != nullptr);

@@ -819,6 +819,17 @@ __global__ void l1_loss_bwd_kernel(const float* __restrict__ y, const float* __r
 // backward kernels vec == 8 selects the tiled kernel (unroll 2 | 4), vec == 4 the generic one.
 // Kernels that end in a per-block reduction (smem + one double atomic per channel and block) keep
 // the grid small so the same-address atomics stay in the hundreds, not thousands.
+// TMA-staged versions (stream_ew.cu): variant vec == 16
+bool stream_ew_ok(int C);
+int launch_bn_stats_bulk(const void* a, int dtype, int64_t rows, int C, double* stats, cudaStream_t st);
+int launch_act_fwd_bulk(const void* a, int dtype, int batch, int L, int C, const float* scale_shift, const float* slope,
+                        int act, int roll, const int32_t* roll_dev, int H, void* h, cudaStream_t st);
+template <int MODE>
+int launch_act_bwd_bulk(const void* g_h, int H, int roll, const int32_t* roll_dev, const void* g_add, const void* a,
+                        int dtype, int g_dtype, int batch, int L, int C, const float* scale_shift,
+                        const float* mean_invstd, const float* slope, int act, const double* red_in, double* red_out,
+                        int use_bn, void* g_a_out, cudaStream_t st);
+
 // Defaults = the best of tools/ew_sweep.py on B200 (profiles/r1_v4_ew_sweep.txt).
 struct EwVariant { int vec, unroll, cap; };
 enum { EW_ACT_FWD = 1, EW_BN_STATS = 2, EW_BWD_REDUCE = 3, EW_BWD_APPLY = 4, EW_KINDS = 5 };
@@ -826,6 +837,7 @@ static EwVariant g_ew[EW_KINDS] = {{0, 0, 0}, {8, 4, 2}, {4, 4, 3}, {8, 2, 2}, {
 static bool g_ew_env_read = false;
 static bool ew_valid(int kind, int vec, int unroll, int cap) {
   if (kind < 1 || kind >= EW_KINDS) return false;
+  if (vec == 16) return cap >= 1 && cap <= 32;          // TMA-staged kernels: unroll / cap are fixed by the kernel
   if (!((vec == 4 || vec == 8) && (unroll == 2 || unroll == 4 || unroll == 8) && vec * unroll <= 32)) return false;
   if ((kind == EW_BWD_REDUCE || kind == EW_BWD_APPLY) && vec == 8 && unroll > 4) return false;
   return cap >= 1 && cap <= 32;
@@ -916,7 +928,13 @@ extern "C" int sg_set_ew_variant(int kind, int vec, int unroll, int cap) {
 extern "C" int sg_bn_stats(const void* a, int dtype, int64_t rows_total, int C, double* stats, void* stream) {
   SG_CHECK_ARG(ew_shape_ok(C) && a && stats && rows_total < (1ll << 31));
   const EwVariant v = ew(EW_BN_STATS);
-  EW_DISPATCH(v.vec, v.unroll, (bn_stats_kernel<VEC, UNR><<<stream_grid(rows_total, C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(
+  if (v.vec == 16 && (dtype == SG_F16 || dtype == SG_BF16) && stream_ew_ok(C)) {
+    int rc = launch_bn_stats_bulk(a, dtype, rows_total, C, stats, ST);
+    if (rc) return rc;
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
+  EW_DISPATCH(v.vec == 16 ? 4 : v.vec, v.vec == 16 ? 4 : v.unroll, (bn_stats_kernel<VEC, UNR><<<stream_grid(rows_total, C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(
       a, dtype, rows_total, C, stats)));
   SG_CHECK_LAUNCH();
   return SG_OK;
@@ -937,7 +955,14 @@ extern "C" int sg_act_fwd(const void* a, int dtype, int batch, int L, int C, con
   SG_CHECK_ARG(ew_shape_ok(C) && (out_halo_pos == 0 || L > out_halo_pos));      // reflect padding needs pad < L
   SG_CHECK_ARG(act == SG_ACT_NONE || (act == SG_ACT_PRELU && slope));
   const EwVariant v = ew(EW_ACT_FWD);
-  EW_DISPATCH(v.vec, v.unroll, (act_fwd_kernel<VEC, UNR><<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(
+  if (v.vec == 16 && (dtype == SG_F16 || dtype == SG_BF16) && stream_ew_ok(C) && !h_bf16 && !a_bf16 && h &&
+      (out_halo_pos == 0 || L >= 2 * out_halo_pos + 3)) {
+    int rc = launch_act_fwd_bulk(a, dtype, batch, L, C, scale_shift, slope, act, roll, roll_dev, out_halo_pos, h, ST);
+    if (rc) return rc;
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
+  EW_DISPATCH(v.vec == 16 ? 8 : v.vec, v.vec == 16 ? 4 : v.unroll, (act_fwd_kernel<VEC, UNR><<<stream_grid((int64_t)batch * (L + 2 * out_halo_pos), C, VEC, 2 * UNR, v.cap), 256, 0, ST>>>(
       a, dtype, batch, L, C, scale_shift, slope, act, roll, roll_dev, out_halo_pos, h, h_bf16, a_bf16)));
   SG_CHECK_LAUNCH();
   return SG_OK;
@@ -952,7 +977,14 @@ extern "C" int sg_act_bwd_reduce(const void* g_h, int g_h_ld, int in_halo_pos, i
   SG_CHECK_ARG(dtype == SG_F16 || dtype == SG_BF16);
   const EwVariant v = ew(EW_BWD_REDUCE);
   const int ldh = g_h_ld > 0 ? g_h_ld : C, lda = g_add_ld > 0 ? g_add_ld : C;
-  if (v.vec == 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
+  if (v.vec == 16 && g_h && ldh == C && (!g_add || lda == C) && stream_ew_ok(C)) {
+    int rc = launch_act_bwd_bulk<0>(g_h, in_halo_pos, roll, roll_dev, g_add, a, dtype, g_grad_dtype, batch, L, C,
+                                    scale_shift, mean_invstd, slope, act, nullptr, red, 0, g_a_out, ST);
+    if (rc) return rc;
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
+  if (v.vec >= 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
     int rc = launch_act_bwd_tiled<0>(g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C, scale_shift,
                                      mean_invstd, slope, act, nullptr, red, 0, g_a_out, v.unroll, v.cap, ST);
     if (rc) return rc;
@@ -976,7 +1008,14 @@ extern "C" int sg_act_bwd_apply(const void* g_h, int g_h_ld, int in_halo_pos, in
   SG_CHECK_ARG(!use_bn || (scale_shift && mean_invstd));
   const EwVariant v = ew(EW_BWD_APPLY);
   const int ldh = g_h_ld > 0 ? g_h_ld : C, lda = g_add_ld > 0 ? g_add_ld : C;
-  if (v.vec == 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
+  if (v.vec == 16 && g_h && ldh == C && (!g_add || lda == C) && stream_ew_ok(C)) {
+    int rc = launch_act_bwd_bulk<1>(g_h, in_halo_pos, roll, roll_dev, g_add, a, dtype, g_grad_dtype, batch, L, C,
+                                    scale_shift, mean_invstd, slope, act, red, nullptr, use_bn, g_a, ST);
+    if (rc) return rc;
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
+  if (v.vec >= 8 && g_h && ldh % 8 == 0 && lda % 8 == 0) {
     int rc = launch_act_bwd_tiled<1>(g_h, ldh, in_halo_pos, roll, roll_dev, g_add, lda, a, dtype, batch, L, C, scale_shift,
                                      mean_invstd, slope, act, red, nullptr, use_bn, g_a, v.unroll, v.cap, ST);
     if (rc) return rc;

@@ -24,12 +24,22 @@ __device__ __forceinline__ int stft_src(int t, int n, int L) {
 }
 
 __global__ void __launch_bounds__(256)
-stft_frames_kernel(const float* __restrict__ x, int L, int frames, void* __restrict__ out, int dtype) {
+stft_frames_kernel(const float* __restrict__ x, int L, int frames, void* __restrict__ out, int dtype, int split) {
   const int b = blockIdx.y;
   const int64_t total = (int64_t)frames * STFT_WIN;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int t = (int)(i / STFT_WIN), n = (int)(i % STFT_WIN);
-    st16(out, (int64_t)b * total + i, x[(int64_t)b * L + stft_src(t, n, L)], dtype);
+    const float v = x[(int64_t)b * L + stft_src(t, n, L)];
+    if (!split) {
+      st16(out, (int64_t)b * total + i, v, dtype);
+    } else {
+      // [hi | lo | hi]: v = hi + lo to ~22 bits; the K = 960 product against [Dhi ; Dhi ; Dlo] is hi Dhi + lo Dhi + hi Dlo
+      const int64_t row = ((int64_t)b * frames + t) * (3 * STFT_WIN);
+      const float hi = dtype == SG_F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
+      st16(out, row + n, hi, dtype);
+      st16(out, row + STFT_WIN + n, v - hi, dtype);
+      st16(out, row + 2 * STFT_WIN + n, hi, dtype);
+    }
   }
 }
 
@@ -75,12 +85,12 @@ stft_fold_kernel(const float* __restrict__ gf, int L, int frames, float scale, f
 using namespace sg;
 #define ST ((cudaStream_t)stream)
 
-// frames[b][t][n] = x[b][reflect(t*160 + n - 160)], t < 1 + L/160, n < 320 (16-bit)
-extern "C" int sg_stft_frames(const float* x, int batch, int L, void* frames, int dtype, void* stream) {
+// frames[b][t][n] = x[b][reflect(t*160 + n - 160)], t < 1 + L/160, n < 320 (16-bit); split: rows of 960 = hi | lo | hi
+extern "C" int sg_stft_frames(const float* x, int batch, int L, void* frames, int dtype, int split, void* stream) {
   SG_CHECK_ARG(x && frames && batch > 0 && L > STFT_NFFT / 2 && (dtype == SG_F16 || dtype == SG_BF16));
   const int fr = 1 + L / STFT_HOP;
   dim3 grid((unsigned)cdiv((int64_t)fr * STFT_WIN, 256 * 4), batch);
-  stft_frames_kernel<<<grid, 256, 0, ST>>>(x, L, fr, frames, dtype);
+  stft_frames_kernel<<<grid, 256, 0, ST>>>(x, L, fr, frames, dtype, split);
   SG_CHECK_LAUNCH();
   return SG_OK;
 }

@@ -520,6 +520,17 @@ struct Piece {
 // critical path (ncu, profiles/r2_v1_ncu_tapgemm.md: ~2400 warp instructions per tile and epilogue warp, a dozen
 // integer divisions among them, made a 314 MB pass take 127 us).  The iterator therefore advances (mp, rest) by
 // addition and caches the k-step count per N tile; the roles hoist everything that does not depend on the tile.
+// SEGAN_B200_DEBUG bit 20: phase timeline of tapgemm_f_tc2 (globaltimer ns; epilogue warp 2 / lane 0 of every CTA):
+// [cta][0] = kernel start, then per piece: accumulator ready, epilogue done, (split tiles) finisher done; last = exit.
+// Read back with sg_debug_timeline (diagnostics only).
+constexpr int TL_SLOTS = 32;
+__device__ unsigned long long g_tc2_timeline[160 * TL_SLOTS];
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct PieceIter {
   int m_pairs, npairs, dp_end, total_tiles, pair_id;
   int next_dp, cur_mp, cur_rest;
@@ -785,6 +796,10 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       for (int c = et; c < 512; c += 256) colstat[c] = 0.f;
       epi2_bar_sync();
     }
+    const bool tl_on = (p.dbg & (1 << 20)) && warp == 2 && lane == 0 && blockIdx.x < 160;
+    int tl_i = 0;
+    unsigned long long* tl = g_tc2_timeline + (blockIdx.x < 160 ? blockIdx.x : 0) * TL_SLOTS;
+    if (tl_on) { for (int i = 0; i < TL_SLOTS; ++i) tl[i] = 0; tl[tl_i++] = gtime_ns(); }
     while (it.next(p, pc)) {
       const int ks = p.ksplit == 1 ? 0 : pc.rest % p.ksplit;
       const int nt = p.ksplit == 1 ? pc.rest : pc.rest / p.ksplit;
@@ -802,6 +817,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
       mbar_wait(&ctl->tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (tl_on && tl_i < TL_SLOTS - 1) tl[tl_i++] = gtime_ns();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.TN);
       const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
       // second (activated) output: same column geometry, its own halo; reflect mirror row of position m, if any
@@ -866,6 +882,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);      // one arrival per warp: 2 CTAs x 8 warps release it
       if (++acc == nacc) { acc = 0; acc_phase ^= 1; }
+      if (tl_on && tl_i < TL_SLOTS - 1) tl[tl_i++] = gtime_ns();
       if (partial && mt < m_tiles) {
         const int slot = pc.tile - it.dp_end;
         unsigned int* cnt = p.sk_cnt + ((((slot * 2 + (int)rank) * 4 + quad) * 2) + half);
@@ -904,9 +921,11 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
           }
           __syncwarp();
           if (lane == 0) *cnt = 0u;                    // ready for the next launch
+          if (tl_on && tl_i < TL_SLOTS - 1) tl[tl_i++] = gtime_ns() | (1ull << 63);      // flagged: finisher
         }
       }
     }
+    if (tl_on && tl_i < TL_SLOTS) tl[tl_i++] = gtime_ns();
     if (p.stats != nullptr && stat_nt >= 0) flush_stats(stat_nt);
   }
   tc_fence_before();
@@ -1393,6 +1412,11 @@ constexpr int SK_MAX_PAIRS = 96;
 constexpr int64_t SK_CNT_BYTES = 8192;
 constexpr int64_t SK_WS_BYTES = SK_CNT_BYTES + (int64_t)SK_MAX_PAIRS * 2 * 128 * 256 * 4;
 int64_t tapgemm_f_workspace_bytes() { return SK_WS_BYTES; }
+int tapgemm_f_debug_timeline(unsigned long long* host_out, int max_words) {
+  const int n = max_words < 160 * TL_SLOTS ? max_words : 160 * TL_SLOTS;
+  if (cudaMemcpyFromSymbol(host_out, g_tc2_timeline, (size_t)n * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  return n;
+}
 // SEGAN_B200_STREAMK: 0 = off, n = largest split factor per leftover tile (default 16);
 // SEGAN_B200_SK_ATOMIC / SEGAN_B200_SK_FIXED: cost-model constants in k-steps (tapgemm_f_tc_launch)
 int g_stream_k = [] { const char* e = getenv("SEGAN_B200_STREAMK"); return e ? atoi(e) : 16; }();

@@ -12,6 +12,7 @@ Layer geometry follows the reference (file:line into /root/reference):
 HBM layouts are described in include/segan_b200.h and DESIGN.md.
 """
 import ctypes as C
+import math
 import os
 
 import torch
@@ -281,7 +282,8 @@ def sk_workspace(dev):
     one per stream because launches on different streams may run concurrently."""
     if not STREAM_K:
         return None
-    key = (torch.device(dev).index, torch.cuda.current_stream().cuda_stream)
+    idx = torch.device(dev).index
+    key = (torch.cuda.current_device() if idx is None else idx, torch.cuda.current_stream().cuda_stream)
     ws = _SK_WS.get(key)
     if ws is None:
         ws = _SK_WS[key] = torch.zeros(int(_lib.load().sg_tapgemm_f_workspace_bytes()), dtype=torch.uint8, device=dev)
@@ -1589,3 +1591,59 @@ class DiscriminatorEngine(_NetEngine):
         if reducer is not None and param_grads:
             reducer.ready(1, launch=reduce_now)
         return grad_flat
+
+
+class SpectralLoss(object):
+    """WSEGAN's spectral regression term (model.py:638-653): pow_weight * L1 between the log-power spectrograms of the
+    enhanced and the clean batch -- torch.stft(n_fft 2048, hop 160, win_length 320 rectangular, centred, normalised),
+    10 log10(|X|^2 + 1e-19).  Only the window's 320 samples of every 2048-sample frame are non-zero, so the transform
+    of all B x (1 + L/160) frames of BOTH signals is one dense GEMM on the tensor cores (the tap-GEMM with one tap):
+        [2 B frames][960 = hi | lo | hi] x [960 = Dhi ; Dhi ; Dlo][2176 = re(1025) pad | im(1025) pad]  (fp16, fp32 out)
+    the two-halves split of both operands (x = hi + lo) keeps the weak bins of a 60 dB spectrum out of the fp16
+    rounding floor.  |X| does not depend on where the window sits in the frame: the DFT runs over n = 0..319.
+    Backward: dL/dX (bf16: 1/|X|^2 has a wide range) x D^T (bf16) -> dL/dframes, overlap-added into dL/dwave."""
+
+    WIN, HOP, NFFT, BINS, HALF = 320, 160, 2048, 1025, 1088
+
+    def __init__(self, device):
+        self.dev = device
+        self.buf = _Buffers()
+        n = torch.arange(self.WIN, dtype=torch.float64)
+        f = torch.arange(self.BINS, dtype=torch.float64)
+        ang = 2.0 * math.pi * torch.outer(f, n) / self.NFFT                  # [bins][win]
+        d = torch.zeros(2 * self.HALF, self.WIN, dtype=torch.float64)
+        d[:self.BINS] = torch.cos(ang) / math.sqrt(self.NFFT)                # normalized=True: frame_length ** -0.5
+        d[self.HALF:self.HALF + self.BINS] = -torch.sin(ang) / math.sqrt(self.NFFT)
+        hi = d.to(torch.float16)
+        lo = (d - hi.double()).to(torch.float16)
+        self.w_fwd = torch.cat((hi, hi, lo), dim=1).contiguous().to(device)               # F[n = column][k = 960]
+        self.w_bwd = d.t().contiguous().to(torch.bfloat16).to(device)                     # F[n = sample][k = column]
+        self.taps_f = tap_ranges("full", 0, 3 * self.WIN, 2 * self.HALF)
+        self.taps_b = tap_ranges("full", 0, 2 * self.HALF, self.WIN)
+
+    def __call__(self, gen, clean, weight, loss_out, g_wave=None, g_scale=1.0):
+        """loss_out (device float*) += weight * mean|logpow(gen) - logpow(clean)|; g_wave (fp32 (B,1,L), optional)
+        += g_scale * d loss / d gen."""
+        B, _, L = gen.shape
+        assert L > self.NFFT // 2 and gen.dtype == torch.float32 and clean.dtype == torch.float32
+        fr = 1 + L // self.HOP
+        rows = B * fr
+        dev = gen.device
+        K, N = 3 * self.WIN, 2 * self.HALF
+        frames = self.buf.get("frames", (2 * rows, K), F16, dev)
+        _lib.call("sg_stft_frames", _p(gen.contiguous()), B, L, _p(frames), SG_F16, 1, _stream())
+        _lib.call("sg_stft_frames", _p(clean.contiguous()), B, L, C.c_void_p(frames.data_ptr() + rows * K * 2),
+                  SG_F16, 1, _stream())
+        X = self.buf.get("X", (2 * rows, N), F32, dev)
+        run_f(frames, None, 2 * rows, 0, SG_F16, self.w_fwd, SG_F16, K, N, self.taps_f, X, SG_F32, 2 * rows, 0,
+              0, 2 * rows, 1, d_lo=0, d_hi=0)
+        gX = None
+        if g_wave is not None:
+            gX = self.buf.get("gX", (rows, N), BF16, dev)          # pad columns stay zero (never written)
+        _lib.call("sg_logpow_l1", _p(X), C.c_void_p(X.data_ptr() + rows * N * 4), rows, self.BINS, self.HALF, N,
+                  float(weight), loss_out, _p(gX), SG_BF16, 1.0, _stream())
+        if g_wave is not None:
+            gf = self.buf.get("gf", (rows, self.WIN), F32, dev)
+            run_f(gX, None, rows, 0, SG_BF16, self.w_bwd, SG_BF16, N, self.WIN, self.taps_b, gf, SG_F32, rows, 0,
+                  0, rows, 1, d_lo=0, d_hi=0)
+            _lib.call("sg_stft_frames_fold", _p(gf), B, L, float(g_scale), _p(g_wave), _stream())

@@ -991,22 +991,37 @@ class WSEGAN(SEGAN):
         Gopt.zero_grad()
         gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
         self._d_pass(Genh, noisy, draw(), 1.0, 1.0, losses, 1, input_grad=gy, param_grads=False, twins=False)
-        # spectral power loss (model.py:638-653)
-        gt = Genh.detach().requires_grad_(True)
-        with torch.enable_grad():
-            pow_loss = self.pow_weight * F.l1_loss(self.stft_logpow(gt, self.n_fft), self.stft_logpow(clean, self.n_fft))
-            tot = pow_loss
-            if l1_weight > 0 and uttname is not None and any('additive' in u for u in uttname):
-                mask = torch.zeros(B, 1, L, device=dev)                    # model.py:655-665
-                for i, u in enumerate(uttname):
-                    if 'additive' in u:
-                        mask[i, 0, :] = 1.
-                den = l1_weight * F.l1_loss(gt * mask, clean * mask)
-                losses[3] += den.detach()
-                tot = tot + den
-            tot.backward()
-        losses[2] += pow_loss.detach()
-        gy.add_(gt.grad, alpha=_engine.LOSS_SCALE)
+        # spectral power loss (model.py:638-653): one tensor-core GEMM over the frames of both signals
+        # (engine.SpectralLoss); other n_fft / windows shorter than a frame keep the library transform
+        lscale = _engine.LOSS_SCALE
+        if self.n_fft == 2048 and L >= 2048:
+            if getattr(self, '_spectral', None) is None or self._spectral.dev != dev:
+                self._spectral = _engine.SpectralLoss(dev)
+            self._spectral(Genh, clean, self.pow_weight, C.c_void_p(losses.data_ptr() + 8), g_wave=gy, g_scale=lscale)
+        else:
+            gt = Genh.detach().requires_grad_(True)
+            with torch.enable_grad():
+                pow_loss = self.pow_weight * F.l1_loss(self.stft_logpow(gt, self.n_fft),
+                                                       self.stft_logpow(clean, self.n_fft))
+                pow_loss.backward()
+            losses[2] += pow_loss.detach()
+            gy.add_(gt.grad, alpha=lscale)
+        if l1_weight > 0 and uttname is not None and any('additive' in u for u in uttname):
+            # model.py:655-665: l1_weight * mean over ALL B*L samples of |mask (G - clean)|, mask = 1 on the samples of
+            # 'additive' utterances: one fused loss + gradient launch per run of consecutive masked windows
+            i = 0
+            while i < B:
+                if 'additive' not in uttname[i]:
+                    i += 1
+                    continue
+                j = i
+                while j < B and 'additive' in uttname[j]:
+                    j += 1
+                n_run = (j - i) * L
+                _lib.call("sg_l1_loss_bwd", C.c_void_p(Genh.data_ptr() + 4 * i * L), C.c_void_p(clean.data_ptr() + 4 * i * L),
+                          n_run, float(l1_weight) * n_run / (B * L), C.c_void_p(losses.data_ptr() + 12),
+                          C.c_void_p(gy.data_ptr() + 4 * i * L), 1, float(lscale), _engine._stream())
+                i = j
         ge.backward(gctx, gy, reducer=rg)
         Gopt.step(rg.finish() if rg is not None else allreduce_grads(ge))
         return losses

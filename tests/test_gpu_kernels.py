@@ -55,7 +55,8 @@ def _ref_f(a_pad, halo, w, m_lo, m_hi, d_lo=-4, d_hi=4, w_tap0=0):
     return out
 
 
-EW_DEFAULT = {1: (8, 4, 2), 2: (4, 4, 3), 3: (8, 2, 2), 4: (8, 2, 4)}      # elementwise.cu g_ew
+EW_DEFAULT_REG = {1: (8, 4, 2), 2: (4, 4, 3), 3: (8, 2, 2), 4: (8, 2, 4)}  # the best register-staged variants
+EW_DEFAULT = dict(EW_DEFAULT_REG)                                          # elementwise.cu g_ew
 
 
 @pytest.fixture(autouse=True)
@@ -502,11 +503,12 @@ def test_wave_deconv_fwd_and_bwd(grad_dtype):
     assert rel_err(gx.float().permute(0, 2, 1).cpu(), xin.grad) <= 1e-2      # bf16 output
 
 
-@pytest.mark.parametrize("variant", [(4, 2, 3), (4, 4, 16), (4, 8, 2), (8, 2, 8), (8, 4, 1)])
+@pytest.mark.parametrize("variant", [(4, 2, 3), (4, 4, 16), (4, 8, 2), (8, 2, 8), (8, 4, 1), (16, 2, 2)])
 @pytest.mark.parametrize("C_,L,roll,halo", [(64, 256, 2, 16), (256, 64, -5, 16), (1024, 16, 0, 0), (128, 96, 4, 16)])
 def test_bn_act_fwd_bwd(C_, L, roll, halo, variant, grad_dtype):
     """Every streaming-kernel variant (channels/thread, rows in flight, grid cap; for the backward
-    kernels vec 8 = the tiled kernel, vec 4 = the generic one) against fp32 torch."""
+    kernels vec 8 = the tiled kernel, vec 4 = the generic one; vec 16 = the TMA-staged kernels of stream_ew.cu)
+    against fp32 torch."""
     lib = _lib.load()
     for kind in (1, 2, 3, 4):
         v = variant if not (kind >= 3 and variant == (4, 8, 2)) else (4, 4, 2)
@@ -880,3 +882,84 @@ def test_alpha_grad_and_folds():
     exp[half:] *= al.cpu().view(-1, 1)
     assert rel_err(gw.cpu()[:, 0], exp) <= 1e-6
     assert rel_err(ga.cpu(), (dweff[half:] * wl.cpu()[half:, 0]).sum(1)) <= 1e-5
+
+
+@pytest.mark.parametrize("B,L,kind", [(3, 16384, "speech"), (2, 4096, "white"), (5, 16384, "weak_hf")])
+def test_spectral_loss_gemm_vs_torch_stft(B, L, kind):
+    """WSEGAN's log-power STFT L1 (model.py:638-653) as one tap-GEMM over the frames (engine.SpectralLoss) against
+    torch.stft + autograd in fp64: loss to 1e-4 relative (two-halves fp16 operands), gradient to 1 % rel-L2 (bf16
+    dL/dX).  'weak_hf' = a 70 dB spectral tilt: the bins an un-split fp16 transform would bury in rounding noise."""
+    g = _gen(51)
+    x = torch.randn(B, 1, L, generator=g)
+    if kind != "white":
+        # low-pass tilt: running mean filters make the high bins 40-70 dB weaker than the low ones
+        k = 9 if kind == "speech" else 33
+        for _ in range(2):
+            x = F.avg_pool1d(F.pad(x, (k // 2, k // 2), mode="reflect"), k, stride=1)
+        x = x / x.abs().max()
+    y = (x + 0.05 * torch.randn(B, 1, L, generator=g) * (1.0 if kind == "white" else 0.01)).clamp(-1, 1)
+
+    def logpow(t):
+        st = torch.stft(t.squeeze(1), n_fft=2048, hop_length=160, win_length=320, normalized=True, return_complex=True)
+        return 10 * torch.log10(st.real ** 2 + st.imag ** 2 + 10e-20)
+    yd = y.double().requires_grad_(True)
+    ref = 0.37 * (logpow(yd) - logpow(x.double())).abs().mean()
+    gref, = torch.autograd.grad(ref, yd)
+    sp = E.SpectralLoss(torch.device(DEV))
+    loss = torch.zeros(1, device=DEV)
+    gw = torch.zeros(B, 1, L, device=DEV)
+    sp(y.to(DEV), x.to(DEV), 0.37, C.c_void_p(loss.data_ptr()), g_wave=gw, g_scale=8.0)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref)), (float(loss), float(ref))
+    assert rel_err(gw.cpu() / 8.0, gref.float()) <= 1e-2
+    # loss only (no gradient buffers touched)
+    loss2 = torch.zeros(1, device=DEV)
+    sp(y.to(DEV), x.to(DEV), 0.37, C.c_void_p(loss2.data_ptr()))
+    assert float(loss2) == pytest.approx(float(loss), rel=1e-6)
+
+
+@pytest.mark.parametrize("C_,L,roll,halo,B", [(64, 1024, 3, 16, 160), (128, 256, -5, 16, 300), (512, 64, 1, 16, 300),
+                                               (1024, 16, 0, 0, 300), (64, 4096, -2, 16, 24)])
+def test_tma_staged_glue_kernels_match_register_staged(C_, L, roll, halo, B):
+    """stream_ew.cu (variant vec 16: cp.async.bulk row tiles through an mbarrier ring, two row ranges per batch element
+    at the phase-shift wrap) against the register-staged kernels at sizes where every CTA walks more tiles than its
+    ring has stages: forward and BN-backward outputs bit-identical (same fp32 arithmetic per element), reductions equal
+    up to the summation order."""
+    lib = _lib.load()
+    g = _gen(31)
+    a = torch.randn(B, L, C_, generator=g).to(torch.float16).to(DEV)
+    gh = torch.randn(B, L + 2 * halo, C_, generator=g).to(E.GT).to(DEV)
+    gadd = torch.randn(B, L, C_, generator=g).to(E.GT).to(DEV)
+    ss = torch.randn(2, C_, generator=g).to(DEV)
+    mi = (torch.randn(2, C_, generator=g).abs() + 0.5).to(DEV)
+    slope = (0.2 * torch.rand(C_, generator=g)).to(DEV)
+    roll_dev = torch.tensor([roll], dtype=torch.int32, device=DEV)
+    outs = {}
+    for tag, variants in (("reg", EW_DEFAULT_REG), ("tma", {k: (16, 2, 2) for k in (1, 2, 3, 4)})):
+        for kind, v in variants.items():
+            assert lib.sg_set_ew_variant(kind, *v) == 0
+        stats = torch.zeros(8, 2, C_, dtype=torch.float64, device=DEV)
+        _lib.call("sg_bn_stats", _p(a), SG_F16, B * L, C_, _p(stats), _stream())
+        h = torch.zeros(B, L + 2 * halo, C_, dtype=torch.float16, device=DEV)
+        _lib.call("sg_act_fwd", _p(a), SG_F16, B, L, C_, _p(ss), _p(slope), 1, 0, _p(roll_dev), halo, _p(h), None, None,
+                  _stream())
+        red = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
+        _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, roll, None, None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+                  _p(slope), 1, _p(red), None, _stream())
+        ga = torch.zeros(B, L, C_, dtype=E.GT, device=DEV)
+        _lib.call("sg_act_bwd_apply", _p(gh), C_, halo, 0, _p(roll_dev), None, 0, _p(a), SG_F16, B, L, C_, _p(ss), _p(mi),
+                  _p(slope), 1, _p(red), 1, _p(ga), _stream())
+        # Generator-encoder form: no BN, skip gradient joins after the activation derivative, g_pre written by pass 1
+        red2 = torch.zeros(8, 3, C_, dtype=torch.float64, device=DEV)
+        ga2 = torch.zeros(B, L, C_, dtype=E.GT, device=DEV)
+        _lib.call("sg_act_bwd_reduce", _p(gh), C_, halo, 0, None, _p(gadd), C_, _p(a), SG_F16, B, L, C_, None, None,
+                  _p(slope), 1, _p(red2), _p(ga2), _stream())
+        torch.cuda.synchronize()
+        outs[tag] = (stats.sum(0), h, red.sum(0), ga, red2.sum(0), ga2)
+    r, t = outs["reg"], outs["tma"]
+    assert rel_err(t[0], r[0]) <= 1e-6
+    assert torch.equal(t[1], r[1])
+    assert rel_err(t[2], r[2]) <= 1e-5
+    assert rel_err(t[3].float(), r[3].float()) <= 2e-3          # pass 2 consumes each run's own (re-ordered) sums
+    assert rel_err(t[4], r[4]) <= 1e-5
+    assert torch.equal(t[5], r[5])

@@ -18,6 +18,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=300)
 ap.add_argument("--rep", type=int, default=10)
 ap.add_argument("--with-gemm", action="store_true")
+ap.add_argument("--default-only", action="store_true", help="only the built-in variant of each kernel (ncu captures)")
+ap.add_argument("--shapes", type=int, default=5, help="first N layer shapes")
 args = ap.parse_args()
 B, REP = args.batch, args.rep
 dev = "cuda"
@@ -26,13 +28,15 @@ lib = _lib.load()
 
 SHAPES = [(64, 4096), (128, 1024), (256, 256), (512, 64), (1024, 16)]      # (C, L) of enc0..enc4
 # (vec, unroll, cap) per kernel family (kind 1 act_fwd, 2 bn_stats, 3 bwd_reduce, 4 bwd_apply; for the backward
-# kinds vec 8 = tiled kernel, vec 4 = generic kernel)
+# kinds vec 8 = tiled kernel, vec 4 = generic kernel; vec 16 = the TMA-staged kernels of stream_ew.cu)
 VARIANTS = {
-    1: [(4, 2, 16), (8, 2, 4), (8, 4, 4), (8, 4, 2), (8, 4, 1), (8, 4, 3)],
-    2: [(4, 2, 3), (4, 4, 3), (4, 4, 2), (4, 8, 2), (4, 8, 3), (8, 4, 2), (8, 4, 3)],
-    3: [(4, 2, 3), (4, 4, 3), (8, 2, 1), (8, 2, 2), (8, 2, 3), (8, 2, 4), (8, 2, 6), (8, 4, 1), (8, 4, 2), (8, 4, 3)],
-    4: [(4, 2, 16), (4, 4, 8), (8, 2, 1), (8, 2, 2), (8, 2, 3), (8, 2, 4), (8, 2, 6), (8, 2, 8), (8, 4, 2), (8, 4, 4)],
+    1: [(8, 4, 4), (8, 4, 2), (16, 2, 2)],
+    2: [(4, 4, 3), (4, 8, 3), (8, 4, 2), (16, 2, 2)],
+    3: [(8, 2, 2), (8, 4, 2), (16, 2, 2)],
+    4: [(8, 2, 2), (8, 2, 4), (8, 4, 2), (16, 2, 2)],
 }
+if args.default_only:
+    VARIANTS = {1: [(8, 4, 2)], 2: [(4, 4, 3)], 3: [(8, 2, 2)], 4: [(8, 2, 4)]}      # elementwise.cu g_ew
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -79,7 +83,7 @@ y = torch.empty_like(x)
 ms = timeit(lambda: y.copy_(x))
 print("copy 157MB->157MB: %.1f us  %.0f GB/s" % (ms * 1e3, 2 * x.numel() * 2 / ms / 1e6))
 
-for C_, L in SHAPES:
+for C_, L in SHAPES[:args.shapes]:
     halo = 16 if L >= 64 else 0
     roll = 3 if halo else 0
     a = torch.empty(B, L, C_, dtype=torch.float16, device=dev).normal_()

@@ -1,6 +1,7 @@
 """Launches representative SEGAN+ layer shapes of the two tcgen05 tap-GEMMs at batch 300 (for ncu /
 timing): conv fwd enc2 (Cin 128 -> 256), deconv fwd dec1 (1024 -> 256, two K sources), conv dgrad enc3,
 wgrad enc2, wgrad dec1.  Prints CUDA-event times and TFLOP/s."""
+import os
 import sys
 
 import torch
@@ -111,6 +112,36 @@ def wave0():
                                                               d_lo=0, d_hi=0, w_tap0=4, backend=1), fl)
 
 
+def dump_timeline(name):
+    """SEGAN_B200_DEBUG bit 20: per-CTA phase stamps of the LAST tapgemm_f_tc2 launch (sg_debug_timeline)."""
+    import ctypes as C
+    from segan_pytorch_b200 import _lib
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    buf = (C.c_uint64 * (160 * 32))()
+    lib.sg_debug_timeline.argtypes = [C.c_void_p, C.c_int]
+    n = lib.sg_debug_timeline(buf, 160 * 32)
+    rows = []
+    for cta in range(148):
+        w = [buf[cta * 32 + i] for i in range(32)]
+        w = [x for x in w if x]
+        if w:
+            rows.append((cta, w))
+    if not rows:
+        print("no timeline recorded")
+        return
+    t0 = min(w[0] & ~(1 << 63) for _, w in rows)
+    print("# %s timeline (us since the earliest CTA start): cta: start | per piece (acc ready, epilogue done, *finisher done) | exit" % name)
+    ends = []
+    for cta, w in rows:
+        vals = ["%s%.1f" % ("*" if x >> 63 else "", ((x & ~(1 << 63)) - t0) / 1e3) for x in w]
+        ends.append(((w[-1] & ~(1 << 63)) - t0) / 1e3)
+        if cta < 32 or cta % 16 == 0:
+            print("cta %3d: %s" % (cta, " ".join(vals)))
+    ends.sort()
+    print("exit times us: min %.1f median %.1f max %.1f" % (ends[0], ends[len(ends) // 2], ends[-1]))
+
+
 ONE = {"wave0": wave0, "enc1": lambda: conv_fwd(64, 128, 1024), "enc3": lambda: conv_fwd(256, 512, 64),
        "enc4": lambda: conv_fwd(512, 1024, 16), "dec1": lambda: deconv_fwd(1024, 256, 64),
        "dgrad3": lambda: conv_dgrad(256, 512, 64), "wgrad3": lambda: conv_wgrad(256, 512, 64),
@@ -121,6 +152,8 @@ if __name__ == "__main__":
         COMPARE = ""
         for name in sys.argv[4:]:
             ONE[name]()
+            if int(os.environ.get("SEGAN_B200_DEBUG", "0")) & (1 << 20):
+                dump_timeline(name)
         sys.exit(0)
     if COMPARE == "streamk":
         for fn, args in ((conv_fwd, (64, 128, 1024)), (conv_fwd, (128, 256, 256)), (conv_fwd, (256, 512, 64)),
