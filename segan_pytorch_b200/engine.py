@@ -1636,7 +1636,7 @@ class SpectralLoss(object):
                   SG_F16, 1, _stream())
         X = self.buf.get("X", (2 * rows, N), F32, dev)
         run_f(frames, None, 2 * rows, 0, SG_F16, self.w_fwd, SG_F16, K, N, self.taps_f, X, SG_F32, 2 * rows, 0,
-              0, 2 * rows, 1, d_lo=0, d_hi=0)
+              0, 2 * rows, 1, d_lo=0, d_hi=0, w_tap0=4)
         gX = None
         if g_wave is not None:
             gX = self.buf.get("gX", (rows, N), BF16, dev)          # pad columns stay zero (never written)
@@ -1645,5 +1645,5 @@ class SpectralLoss(object):
         if g_wave is not None:
             gf = self.buf.get("gf", (rows, self.WIN), F32, dev)
             run_f(gX, None, rows, 0, SG_BF16, self.w_bwd, SG_BF16, N, self.WIN, self.taps_b, gf, SG_F32, rows, 0,
-                  0, rows, 1, d_lo=0, d_hi=0)
+                  0, rows, 1, d_lo=0, d_hi=0, w_tap0=4)
             _lib.call("sg_stft_frames_fold", _p(gf), B, L, float(g_scale), _p(g_wave), _stream())

@@ -195,6 +195,8 @@ def allreduce_grads(eng):
 # gradient-completion order -- on a communication stream as the backward pass produces them, so only the last,
 # small chunk is exposed; with CUDA graphs the collectives are captured into the step's single graph.
 DP_OVERLAP = os.environ.get("SEGAN_B200_DP_OVERLAP", "1").lower() not in ("0", "off", "no", "false")
+# SEGAN_B200_DP_CAPTURE=0: keep the collectives out of the CUDA graph (three graphs, eager all-reduces between them)
+DP_CAPTURE = os.environ.get("SEGAN_B200_DP_CAPTURE", "1").lower() not in ("0", "off", "no", "false")
 
 
 class GradReducer(object):
@@ -746,7 +748,7 @@ class SEGAN(Model):
         t_d, t_g = Dopt.t, Gopt.t
         rd, rg = self._reducers()
         graphs = None
-        if rd is not None and not getattr(self, '_dp_capture_failed', False):
+        if rd is not None and DP_CAPTURE and not getattr(self, '_dp_capture_failed', False):
             # data parallel: ONE graph with the chunked all-reduces captured on the communication stream
             # (thread-local capture mode: NCCL's watchdog thread keeps polling its events meanwhile)
             g1 = torch.cuda.CUDAGraph()

@@ -31,6 +31,10 @@ def _worker(rank, world, port, q):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    def mark(msg):
+        import sys
+        sys.stderr.write("[dp rank %d] %s\n" % (rank, msg))
+        sys.stderr.flush()
     try:
         from segan_pytorch_b200 import _lib, engine as E
         from segan_pytorch_b200.engine import _p, _stream
@@ -61,6 +65,7 @@ def _worker(rank, world, port, q):
                 reducer.finish()
             torch.cuda.synchronize()
             return ge.grad.clone()
+        mark('init done')
         s = build_segan(batch_size=Bl).to(dev)
         s.G.train()
         red = M.GradReducer(s.G.engine.bind())
@@ -74,6 +79,7 @@ def _worker(rank, world, port, q):
             out["chunks_cover"] = (chunks[0][0] == 0 and all(chunks[i][0] + chunks[i][1] == chunks[i + 1][0]
                                                                for i in range(len(chunks) - 1))
                                    and chunks[-1][0] + chunks[-1][1] == s.G.engine.grad.numel())
+        mark('G gradient part done')
         del s
         # ---- (2) full train steps, data parallel: eager (2), then graph-replayed (3)
         random.seed(3 + rank)
@@ -87,6 +93,7 @@ def _worker(rank, world, port, q):
         losses = []
         for i in range(5):
             losses.append(s.train_step(c, n, Gopt, Dopt, 100.0).tolist())
+            mark('step %d done' % i)
         torch.cuda.synchronize()
         st = list(getattr(s, "_step_graphs", {}).values())
         out["graphs"] = [len(v.graphs) for v in st if v.graphs is not None]
@@ -116,12 +123,16 @@ def test_data_parallel_two_gpus():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        res = [q.get(timeout=300) for _ in procs]
+    finally:
+        for p in procs:                      # a hung collective must not outlive the test (and the GPU box's time limit)
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()
     for rank, out, err in res:
         assert err is None, "rank %d failed:\n%s" % (rank, err)
     outs = {rank: out for rank, out, _ in res}
