@@ -1352,6 +1352,164 @@ tapgemm_w_tc(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------
+// form W on CTA pairs (cta_group::2): one 256 (n) x 256 (kc) block of a tap per pair.  Each CTA stages ITS 128
+// gradient channels (the M half it owns) and HALF of the activation tile (128 of the 256 kc columns; the pair's
+// UMMA reads both halves), so a k-step costs 32 KB of L2 -> shared traffic per SM instead of 48 KB for the same
+// math.  The single-CTA kernel is L2-feed bound (ncu, profiles/r2_v1_ncu_tapgemm.md: tensor pipe 77 % of active
+// cycles at 96 B/clk/SM of TMA traffic).
+// ------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+tapgemm_w_tc2(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmA0,
+              const __grid_constant__ CUtensorMap tmA1, const WTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SharedCtl2* ctl = reinterpret_cast<SharedCtl2*>(smem + STAGES2 * STAGE2_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmG); prefetch_tmap(&tmA0); prefetch_tmap(&tmA1);
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ctl->tmem_full[i], 1); mbar_init(&ctl->tmem_empty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(&ctl->tmem_base, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  const int ntaps = p.d_hi - p.d_lo + 1;
+  const int n_tiles2 = p.nc / 256, k_tiles2 = p.kc / 256;
+  const int total_tiles = ntaps * n_tiles2 * k_tiles2 * p.ksplit;
+  const int pos_steps = p.row_chunks * p.b_chunks;
+  const int steps_per_split = (pos_steps + p.ksplit - 1) / p.ksplit;
+  const int npairs = gridDim.x / 2, pair_id = blockIdx.x / 2;
+
+  // taps fastest (see tapgemm_w_tc): concurrently running pairs share G and the row-shifted A rows through L2
+  auto decode = [&](int tile, int& d, int& n0, int& kc0, int& sp) -> bool {
+    d = p.d_lo + tile % ntaps; tile /= ntaps;
+    const int kt = tile % k_tiles2; tile /= k_tiles2;
+    const int nt = tile % n_tiles2; tile /= n_tiles2;
+    sp = tile;
+    n0 = nt * 256; kc0 = kt * 256;
+    const int ti = d + 4;
+    if (n0 + 256 <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) return false;
+    if (kc0 + 256 <= p.tr.k_lo[ti] || kc0 >= p.tr.k_hi[ti]) return false;
+    return true;
+  };
+
+  if (warp == 0) {
+    // TMA producer: lanes 0,1 = this CTA's two 64-channel G boxes, lanes 2,3 = its two 64-column A boxes; all four
+    // signal the LEADER's full barrier (2 x 32 KB per stage)
+    if (lane < 4) {
+      int stage = 0; uint32_t phase = 0;
+      const bool is_g = lane < 2;
+      const int j = lane & 1;
+      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+        int d, n0, kc0, sp;
+        if (!decode(tile, d, n0, kc0, sp)) continue;
+        const int s_lo = sp * steps_per_split;
+        const int s_hi = min(pos_steps, s_lo + steps_per_split);
+        const int kk = kc0 + 128 * (int)rank + 64 * j;
+        const CUtensorMap* map = is_g ? &tmG : (kk < p.a0_c ? &tmA0 : &tmA1);
+        const int c0 = is_g ? n0 + 128 * (int)rank + 64 * j : (kk < p.a0_c ? kk : kk - p.a0_c);
+        const int rshift = is_g ? 0 : d + p.a_halo;
+        const uint32_t off = is_g ? 8192u * j : (uint32_t)A_STAGE_BYTES + 8192u * j;
+        int rc = s_lo % p.row_chunks, bc = s_lo / p.row_chunks;
+        for (int s = s_lo; s < s_hi; ++s) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          if (leader && lane == 0) mbar_expect_tx(&ctl->full[stage], 2u * (uint32_t)STAGE2_BYTES);
+          tma_load_3d_pair(smem + stage * STAGE2_BYTES + off, map, &ctl->full[stage], c0, rc * p.PR + rshift,
+                           bc * p.PB);
+          if (++rc == p.row_chunks) { rc = 0; ++bc; }
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+        int d, n0, kc0, sp;
+        if (!decode(tile, d, n0, kc0, sp)) continue;
+        const int s_lo = sp * steps_per_split;
+        const int s_hi = min(pos_steps, s_lo + steps_per_split);
+        if (s_lo >= s_hi) continue;
+        mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        uint32_t accum = 0;
+        for (int s = s_lo; s < s_hi; ++s) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, 8192, 1024);
+          if (elect_one()) {
+            umma_f16_pair(tmem_d, adesc, bdesc, p.idesc, accum);
+            umma_f16_pair(tmem_d, adesc + 128, bdesc + 128, p.idesc, 1u);
+            umma_f16_pair(tmem_d, adesc + 256, bdesc + 256, p.idesc, 1u);
+            umma_f16_pair(tmem_d, adesc + 384, bdesc + 384, p.idesc, 1u);
+            umma_commit_pair(&ctl->empty[stage]);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit_pair(&ctl->tmem_full[acc]);
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    const float osc = p.out_scale ? __ldg(p.out_scale) : 1.f;
+    for (int tile = pair_id; tile < total_tiles; tile += npairs) {
+      int d, n0, kc0, sp;
+      if (!decode(tile, d, n0, kc0, sp)) continue;
+      const int s_lo = sp * steps_per_split;
+      const int s_hi = min(pos_steps, s_lo + steps_per_split);
+      if (s_lo >= s_hi) continue;
+      mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * 256u;
+      const int n = n0 + 128 * (int)rank + row;                 // this thread's gradient channel
+      float* o = p.dw + ((int64_t)(d + 4 - p.dw_tap0) * p.nc + n) * p.kc + kc0;
+      const int ti = d + 4;
+      const bool row_live = n >= p.tr.n_lo[ti] && n < p.tr.n_hi[ti];
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        // column blocks / rows that are structurally zero for this tap are not even read
+        if (kc0 + c0 + 32 <= p.tr.k_lo[ti] || kc0 + c0 >= p.tr.k_hi[ti]) continue;
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (!row_live) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(o + c0 + j, osc * __uint_as_float(r[j]), osc * __uint_as_float(r[j + 1]),
+                     osc * __uint_as_float(r[j + 2]), osc * __uint_as_float(r[j + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);    // 2 CTAs x 4 warps release the accumulator
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1612,6 +1770,22 @@ int tapgemm_w_tc_launch(const sg_tapgemm_w* q, cudaStream_t st) {
   if (q->a1) rc = make_map3(&tmA1, q->a1, q->a_dtype, q->a1_c, a_buf_rows, q->batch, p.PR, p.PB);
   else tmA1 = tmA0;
   if (rc) return rc;
+  // SEGAN_B200_W_PAIR=0: single-CTA tiles only (A/B runs)
+  static const bool w_pair = [] { const char* e = getenv("SEGAN_B200_W_PAIR"); return !e || atoi(e) != 0; }();
+  if (w_pair && g_cta_pair && q->nc % 256 == 0 && q->kc % 256 == 0) {
+    static bool attr2 = false;
+    if (!attr2) {
+      SG_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_w_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      attr2 = true;
+    }
+    p.idesc = make_idesc(q->g_dtype == SG_BF16, q->a_dtype == SG_BF16, 1, 1, 256, 256);
+    const int total2 = (q->d_hi - q->d_lo + 1) * (q->nc / 256) * (q->kc / 256) * p.ksplit;
+    int npairs = num_sms() / 2;
+    if (total2 < npairs) npairs = total2;
+    tapgemm_w_tc2<<<2 * npairs, NUM_THREADS, SMEM2_BYTES, st>>>(tmG, tmA0, tmA1, p);
+    SG_CHECK_LAUNCH();
+    return SG_OK;
+  }
   const int total = (q->d_hi - q->d_lo + 1) * p.n_tiles * p.k_tiles * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
   tapgemm_w_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmG, tmA0, tmA1, p);

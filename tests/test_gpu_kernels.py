@@ -331,7 +331,7 @@ def test_wgrad_split_plan_fills_whole_waves():
 
 
 @pytest.mark.parametrize("backend", [BACKEND_FFMA, BACKEND_TCGEN05])
-@pytest.mark.parametrize("case", ["conv", "deconv_cat", "small_rows", "fc"])
+@pytest.mark.parametrize("case", ["conv", "deconv_cat", "small_rows", "conv_wide", "fc"])
 def test_tapgemm_w(backend, case):
     g = _gen(2)
     a1, a1_c = None, 0
@@ -350,6 +350,11 @@ def test_tapgemm_w(backend, case):
         a1_c = 128
     elif case == "small_rows":
         B, cin, cout, R, halo = 9, 128, 128, 16, 4
+        kc, nc = 4 * cin, cout
+        taps = E.tap_ranges("conv_fwd", cin, kc, nc)
+        a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
+    elif case == "conv_wide":           # 2 x 2 blocks of 256 x 256 per tap: the CTA-pair kernel (cta_group::2)
+        B, cin, cout, R, halo = 5, 128, 512, 64, 4
         kc, nc = 4 * cin, cout
         taps = E.tap_ranges("conv_fwd", cin, kc, nc)
         a0 = torch.randn(B, R + 2 * halo, kc, generator=g).to(torch.float16).to(DEV)
