@@ -830,10 +830,12 @@ int launch_act_bwd_bulk(const void* g_h, int H, int roll, const int32_t* roll_de
                         const float* mean_invstd, const float* slope, int act, const double* red_in, double* red_out,
                         int use_bn, void* g_a_out, cudaStream_t st);
 
-// Defaults = the best of tools/ew_sweep.py on B200 (profiles/r1_v4_ew_sweep.txt).
+// Defaults = the best of tools/ew_sweep.py on B200 (profiles/r2_ew_sweep.txt): the TMA-staged kernels (vec 16) wherever
+// they apply -- contiguous 16-bit tensors without twins -- else the register-staged (8, 4, 2); BatchNorm statistics
+// (one read-only stream) gain nothing from staging and stay register-staged.
 struct EwVariant { int vec, unroll, cap; };
 enum { EW_ACT_FWD = 1, EW_BN_STATS = 2, EW_BWD_REDUCE = 3, EW_BWD_APPLY = 4, EW_KINDS = 5 };
-static EwVariant g_ew[EW_KINDS] = {{0, 0, 0}, {8, 4, 2}, {4, 4, 3}, {8, 2, 2}, {8, 2, 4}};
+static EwVariant g_ew[EW_KINDS] = {{0, 0, 0}, {16, 4, 2}, {4, 8, 3}, {16, 4, 2}, {16, 4, 2}};
 static bool g_ew_env_read = false;
 static bool ew_valid(int kind, int vec, int unroll, int cap) {
   if (kind < 1 || kind >= EW_KINDS) return false;

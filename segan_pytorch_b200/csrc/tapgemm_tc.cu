@@ -710,14 +710,27 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         const int b0 = mtb * p.TB;
         const int m0 = p.m_lo + (mt - mtb * p.m_tiles_per_b) * p.TR;
         const int n0 = p.n_lo + nt * p.TN;
+        // k-steps [kb, ke) of the tile's (tap, k-block) sequence.  A split-K piece JUMPS to its first step: walking
+        // there one (tap, k-block) at a time cost ~0.12 us per skipped step (two dependent constant-bank loads per
+        // iteration), i.e. the 7th piece of a 248-step tile started 25 us late (profiles/r2_tc2_timeline.txt).
         int step = 0, sel = 0;              // step: every (tap, k-block) of the tile; sel: those of this k-split
+        int skip = p.ksplit == 1 ? pc.kb : 0;
         for (int d = p.d_lo; d <= p.d_hi; ++d) {
           const int ti = d + 4;
           if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
-          for (int k0 = p.tr.k_lo[ti]; k0 < p.tr.k_hi[ti]; k0 += 64, ++step) {
+          const int klo = p.tr.k_lo[ti], khi = p.tr.k_hi[ti];
+          int k0 = klo;
+          if (p.ksplit == 1) {
+            const int nk = (khi - klo) >> 6;
+            if (skip >= nk) { skip -= nk; sel += nk; continue; }
+            k0 += skip << 6; sel += skip; skip = 0;
+            if (sel >= pc.ke) break;
+          }
+          for (; k0 < khi; k0 += 64, ++step) {
             if (p.ksplit > 1 && step % p.ksplit != ks) continue;
             const int mine = sel++;
-            if (mine < pc.kb || mine >= pc.ke) continue;
+            if (mine < pc.kb) continue;
+            if (mine >= pc.ke) break;
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE2_BYTES;
             if (leader && lane == 0) mbar_expect_tx(&ctl->full[stage], 2u * (a_bytes + b_bytes));
@@ -1706,7 +1719,8 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
       for (int d = q->d_lo; d <= q->d_hi; ++d) steps += (q->tap_k_hi[d + 4] - q->tap_k_lo[d + 4]) / 64;
       int best_s = 1;
       double best = (double)steps;
-      const int s_max = npairs / r < g_stream_k ? npairs / r : g_stream_k;
+      int s_max = npairs / r < g_stream_k ? npairs / r : g_stream_k;
+      if (s_max > steps / 2) s_max = steps / 2;       // every piece keeps at least two k-steps
       const double per_partial = g_sk_atomic_steps * 256.0 / p.TN;      // narrower tiles have shorter k-steps
       for (int S = 2; S <= s_max; ++S) {
         const double c = (double)steps / S + per_partial * S + g_sk_fixed_steps;

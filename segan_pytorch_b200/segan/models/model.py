@@ -434,19 +434,25 @@ class SEGAN(Model):
                 q_in.put(None)
 
         def writer():
+            # files of a group are independent: a few threads keep several write() system calls in flight (scipy's
+            # wavfile.write releases the GIL inside them)
+            from concurrent.futures import ThreadPoolExecutor
+
+            def save(arr, path, w0, T):
+                wavfile.write(os.path.join(out_dir, os.path.basename(path)), 16000, arr[w0 * N:w0 * N + T])
+                if on_done is not None:
+                    on_done(path, T)
             try:
-                while True:
-                    item = q_out.get()
-                    if item is None:
-                        return
-                    ev, host, files = item
-                    ev.synchronize()
-                    arr = host.numpy()
-                    for path, w0, T in files:
-                        out = arr[w0 * N:w0 * N + T]
-                        wavfile.write(os.path.join(out_dir, os.path.basename(path)), 16000, out)
-                        if on_done is not None:
-                            on_done(path, T)
+                with ThreadPoolExecutor(max_workers=4) as pool:
+                    while True:
+                        item = q_out.get()
+                        if item is None:
+                            return
+                        ev, host, files = item
+                        ev.synchronize()
+                        arr = host.numpy()
+                        for f in [pool.submit(save, arr, *fl) for fl in files]:
+                            f.result()
             except Exception as e:
                 errors.append(e)
 

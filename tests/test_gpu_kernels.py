@@ -56,7 +56,7 @@ def _ref_f(a_pad, halo, w, m_lo, m_hi, d_lo=-4, d_hi=4, w_tap0=0):
 
 
 EW_DEFAULT_REG = {1: (8, 4, 2), 2: (4, 4, 3), 3: (8, 2, 2), 4: (8, 2, 4)}  # the best register-staged variants
-EW_DEFAULT = dict(EW_DEFAULT_REG)                                          # elementwise.cu g_ew
+EW_DEFAULT = {1: (16, 4, 2), 2: (4, 8, 3), 3: (16, 4, 2), 4: (16, 4, 2)}    # elementwise.cu g_ew
 
 
 @pytest.fixture(autouse=True)
@@ -921,7 +921,7 @@ def test_spectral_loss_gemm_vs_torch_stft(B, L, kind):
     # loss only (no gradient buffers touched)
     loss2 = torch.zeros(1, device=DEV)
     sp(y.to(DEV), x.to(DEV), 0.37, C.c_void_p(loss2.data_ptr()))
-    assert float(loss2) == pytest.approx(float(loss), rel=1e-6)
+    assert float(loss2) == pytest.approx(float(loss), rel=2e-5)          # atomics: summation order differs run to run
 
 
 @pytest.mark.parametrize("C_,L,roll,halo,B", [(64, 1024, 3, 16, 160), (128, 256, -5, 16, 300), (512, 64, 1, 16, 300),

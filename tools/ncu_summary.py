@@ -56,6 +56,14 @@ def main():
                 print("| SM active / elapsed | %.3f |" % (act / el))
             except Exception:
                 pass
+            try:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                tscale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+                by = sum(float(d[k].replace(",", "")) * scale[units[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                t = float(d["gpu__time_duration.sum"].replace(",", "")) * tscale[units["gpu__time_duration.sum"]]
+                print("| achieved HBM GB/s ((read + write) / duration) | %.0f |" % (by / t / 1e9))
+            except Exception:
+                pass
             print()
 
 
