@@ -554,6 +554,7 @@ struct PieceIter {
     cache_rest = -1; cache_steps = 0;
     sk_done = false;
   }
+  template <bool SKF>
   __device__ __forceinline__ bool next(const FTcParams& p, Piece& pc) {
     if (next_dp < dp_end) {
       pc.tile = next_dp; pc.mp = cur_mp; pc.rest = cur_rest;
@@ -563,7 +564,7 @@ struct PieceIter {
       while (cur_mp >= m_pairs) { cur_mp -= m_pairs; ++cur_rest; }
       return true;
     }
-    if (sk_done || dp_end >= total_tiles) return false;
+    if (!SKF || sk_done || dp_end >= total_tiles) return false;
     sk_done = true;
     const int t = dp_end + pair_id / p.sk_split;
     if (t >= total_tiles) return false;
@@ -595,6 +596,7 @@ __device__ __forceinline__ void f_add_bias(const FTcParams& p, float (&v)[32], i
 //   (modules.py:99-101,139-141: no norm layer between the contraction and the PReLU), written next to the raw
 //   pre-activation (`out`, the skip connection's source, generator.py:185,191) with its reflect halo
 //   (modules.py:92-98): position m also lands on its mirror row when it lies within `out2_halo` of an end.
+template <bool ACF>
 __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32], int64_t obase, int c0, int n_abs,
                                               bool atomic, int64_t o2base, int64_t o2mirror) {
   if (p.out_dtype == SG_F32) {
@@ -610,7 +612,7 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
   }
   uint32_t pk[16];
   float sl[32];
-  if (p.slope != nullptr) {
+  if (ACF && p.slope != nullptr) {
     // 16-byte loads: slope / bias vectors are 16-byte aligned views and the chunk is 32-aligned
     const float4* sp = reinterpret_cast<const float4*>(p.slope + f_mod(n_abs, p.slope_mod, p.slope_mask));
 #pragma unroll
@@ -619,7 +621,7 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
       sl[4 * j] = t.x; sl[4 * j + 1] = t.y; sl[4 * j + 2] = t.z; sl[4 * j + 3] = t.w;
     }
   }
-  if (p.out2 == nullptr && p.slope != nullptr) {
+  if (ACF && p.out2 == nullptr && p.slope != nullptr) {
     // PReLU applied to the (only) output: blocks whose pre-activation nobody reads (inference decoder)
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : sl[j] * v[j];
@@ -637,7 +639,7 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
   uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + obase + c0);
 #pragma unroll
   for (int j = 0; j < 4; ++j) o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-  if (p.out2 != nullptr) {
+  if (ACF && p.out2 != nullptr) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float x0 = v[2 * j], x1 = v[2 * j + 1];
@@ -663,9 +665,16 @@ __device__ __forceinline__ void f_store_chunk(const FTcParams& p, float (&v)[32]
 constexpr int NUM_THREADS2 = 320;
 __device__ __forceinline__ void epi2_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// FEAT: compile-time feature set (bit 0 split-K pieces, 1 fused BatchNorm statistics, 2 fused PReLU / second output,
+// 3 interleaved k-split with fp32 atomics; 15 = everything + diagnostics).  The waveform-end launches run ONE k-step per
+// tile and 65 tiles per CTA: their epilogue warps were issuing at ~8 cycles per instruction through a 5500-instruction
+// kernel (timeline: 1.65 us per tile and warp for a 32 x 32 chunk), so the launch picks the leanest instantiation.
+template <int FEAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
               const __grid_constant__ CUtensorMap tmW, const FTcParams p) {
+  constexpr bool SKF = (FEAT & 1) != 0, STF = (FEAT & 2) != 0, ACF = (FEAT & 4) != 0, KSF = (FEAT & 8) != 0;
+  constexpr bool DBG = FEAT == 15;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   SharedCtl2* ctl = reinterpret_cast<SharedCtl2*>(smem + STAGES2 * STAGE2_BYTES);
@@ -702,9 +711,9 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
     // ================= TMA producer (both CTAs) =================
     if (lane < 2) {
       int stage = 0; uint32_t phase = 0;
-      while (it.next(p, pc)) {
-        const int ks = p.ksplit == 1 ? 0 : pc.rest % p.ksplit;
-        const int nt = p.ksplit == 1 ? pc.rest : pc.rest / p.ksplit;
+      while (it.template next<SKF>(p, pc)) {
+        const int ks = (!KSF || p.ksplit == 1) ? 0 : pc.rest % p.ksplit;
+        const int nt = (!KSF || p.ksplit == 1) ? pc.rest : pc.rest / p.ksplit;
         const int mt = 2 * pc.mp + (int)rank;
         const int mtb = p.m_tiles_per_b == 1 ? mt : mt / p.m_tiles_per_b;
         const int b0 = mtb * p.TB;
@@ -714,20 +723,20 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         // there one (tap, k-block) at a time cost ~0.12 us per skipped step (two dependent constant-bank loads per
         // iteration), i.e. the 7th piece of a 248-step tile started 25 us late (profiles/r2_tc2_timeline.txt).
         int step = 0, sel = 0;              // step: every (tap, k-block) of the tile; sel: those of this k-split
-        int skip = p.ksplit == 1 ? pc.kb : 0;
+        int skip = (!KSF || p.ksplit == 1) ? pc.kb : 0;
         for (int d = p.d_lo; d <= p.d_hi; ++d) {
           const int ti = d + 4;
           if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
           const int klo = p.tr.k_lo[ti], khi = p.tr.k_hi[ti];
           int k0 = klo;
-          if (p.ksplit == 1) {
+          if (!KSF || p.ksplit == 1) {
             const int nk = (khi - klo) >> 6;
             if (skip >= nk) { skip -= nk; sel += nk; continue; }
             k0 += skip << 6; sel += skip; skip = 0;
             if (sel >= pc.ke) break;
           }
           for (; k0 < khi; k0 += 64, ++step) {
-            if (p.ksplit > 1 && step % p.ksplit != ks) continue;
+            if (KSF && p.ksplit > 1 && step % p.ksplit != ks) continue;
             const int mine = sel++;
             if (mine < pc.kb) continue;
             if (mine >= pc.ke) break;
@@ -752,7 +761,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t smem0 = smem_u32(smem);
-      while (it.next(p, pc)) {
+      while (it.template next<SKF>(p, pc)) {
         mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.TN);
@@ -805,17 +814,17 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
       epi2_bar_sync();
     };
-    if (p.stats != nullptr) {
+    if (STF && p.stats != nullptr) {
       for (int c = et; c < 512; c += 256) colstat[c] = 0.f;
       epi2_bar_sync();
     }
-    const bool tl_on = (p.dbg & (1 << 20)) && warp == 2 && lane == 0 && blockIdx.x < 160;
+    const bool tl_on = DBG && (p.dbg & (1 << 20)) && warp == 2 && lane == 0 && blockIdx.x < 160;
     int tl_i = 0;
     unsigned long long* tl = g_tc2_timeline + (blockIdx.x < 160 ? blockIdx.x : 0) * TL_SLOTS;
     if (tl_on) { for (int i = 0; i < TL_SLOTS; ++i) tl[i] = 0; tl[tl_i++] = gtime_ns(); }
-    while (it.next(p, pc)) {
-      const int ks = p.ksplit == 1 ? 0 : pc.rest % p.ksplit;
-      const int nt = p.ksplit == 1 ? pc.rest : pc.rest / p.ksplit;
+    while (it.template next<SKF>(p, pc)) {
+      const int ks = (!KSF || p.ksplit == 1) ? 0 : pc.rest % p.ksplit;
+      const int nt = (!KSF || p.ksplit == 1) ? pc.rest : pc.rest / p.ksplit;
       const int mt = 2 * pc.mp + (int)rank;
       const int mtb = p.m_tiles_per_b == 1 ? mt : mt / p.m_tiles_per_b;
       const int b0 = mtb * p.TB;
@@ -823,8 +832,8 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int n0 = p.n_lo + nt * p.TN;
       const int b = b0 + tb, m = m0 + tr;
       const bool valid = (mt < m_tiles) && (tb < p.TB) && (b < p.batch) && (m < p.m_hi);
-      const bool partial = pc.kb != 0 || pc.ke != pc.total;         // one K range of a split tile
-      if (p.stats != nullptr && nt != stat_nt) {
+      const bool partial = SKF && (pc.kb != 0 || pc.ke != pc.total);         // one K range of a split tile
+      if (STF && p.stats != nullptr && nt != stat_nt) {
         if (stat_nt >= 0) flush_stats(stat_nt);
         stat_nt = nt;
       }
@@ -835,7 +844,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       const int64_t obase = ((int64_t)b * out_buf_rows + (m + p.out_halo)) * p.out_ld + (n0 - p.n_lo + p.out_col0);
       // second (activated) output: same column geometry, its own halo; reflect mirror row of position m, if any
       int64_t o2base = 0, o2mirror = -1;
-      if (p.out2 != nullptr) {
+      if (ACF && p.out2 != nullptr) {
         const int64_t rb = (int64_t)b * out2_buf_rows + p.out2_halo;
         o2base = (rb + m) * p.out_ld + (n0 - p.n_lo + p.out_col0);
         if (p.out2_halo > 0) {
@@ -861,7 +870,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         tmem_ld_wait();
         if (partial) {
           float4* dst = myslot + (c0 >> 6) * 256;                   // this warp's (c0 / 64)-th chunk
-          if (!(p.dbg & 8))
+          if (!(DBG && (p.dbg & 8)))
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             __stcg(dst + j * 32, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -872,8 +881,8 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (p.bias != nullptr && ks == 0) f_add_bias(p, v, n0 + c0);
-        if (valid) f_store_chunk(p, v, obase, c0, n0 + c0, p.ksplit > 1, o2base, o2mirror);
-        if (p.stats != nullptr) {                      // warp-uniform branch: the reduction is warp-collective
+        if (valid) f_store_chunk<ACF>(p, v, obase, c0, n0 + c0, KSF && p.ksplit > 1, o2base, o2mirror);
+        if (STF && p.stats != nullptr) {                      // warp-uniform branch: the reduction is warp-collective
           float q[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -917,7 +926,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
               for (int sp = 0; sp < p.sk_split; ++sp) {
                 const float4* src = base0 + (int64_t)sp * 2 * slot_f4 + (c0 >> 6) * 256;
                 float4 t[8];
-                if (p.dbg & 16) {
+                if (DBG && (p.dbg & 16)) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) t[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 } else
@@ -929,7 +938,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
                 }
               }
               if (p.bias != nullptr) f_add_bias(p, v, n0 + c0);
-              if (valid) f_store_chunk(p, v, obase, c0, n0 + c0, false, o2base, o2mirror);
+              if (valid) f_store_chunk<ACF>(p, v, obase, c0, n0 + c0, false, o2base, o2mirror);
             }
           }
           __syncwarp();
@@ -939,7 +948,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
       }
     }
     if (tl_on && tl_i < TL_SLOTS) tl[tl_i++] = gtime_ns();
-    if (p.stats != nullptr && stat_nt >= 0) flush_stats(stat_nt);
+    if (STF && p.stats != nullptr && stat_nt >= 0) flush_stats(stat_nt);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1694,11 +1703,6 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
   }
   if ((g_cta_pair || q->bn_stats != nullptr || fused_act) && m_tiles_all >= 2) {
     // CTA-pair kernel: A box per CTA as before, weight box = TN/2 rows per CTA, M = 256 UMMA
-    static bool attr2 = false;
-    if (!attr2) {
-      SG_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_f_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      attr2 = true;
-    }
     rc = make_map3(&tmW, q->w, q->w_dtype, q->kc, (q->d_hi + 4 - q->w_tap0 + 1) * q->nc, 1, p.TN / 2, 1);
     if (rc) return rc;
     // the CTA-pair epilogue reads bias / slope with 16-byte loads
@@ -1737,9 +1741,19 @@ int tapgemm_f_tc_launch(const sg_tapgemm_f* q, cudaStream_t st) {
         p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(q->sk_ws) + SK_CNT_BYTES);
       }
     }
-    tapgemm_f_tc2<<<2 * npairs, NUM_THREADS2, SMEM2_BYTES, st>>>(tmA0, tmA1, tmW, p);
-    SG_CHECK_LAUNCH();
-    return SG_OK;
+    const int need = (p.sk_split > 1 ? 1 : 0) | (p.stats != nullptr ? 2 : 0) | (fused_act ? 4 : 0) | (p.ksplit > 1 ? 8 : 0) |
+                     (p.dbg != 0 ? 15 : 0);
+    auto launch = [&](auto kern) -> int {
+      SG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      kern<<<2 * npairs, NUM_THREADS2, SMEM2_BYTES, st>>>(tmA0, tmA1, tmW, p);
+      SG_CHECK_LAUNCH();
+      return SG_OK;
+    };
+    if (need & (2 | 8)) return launch(tapgemm_f_tc2<15>);
+    if (need == 0) return launch(tapgemm_f_tc2<0>);
+    if (need == 1) return launch(tapgemm_f_tc2<1>);
+    if (need == 4) return launch(tapgemm_f_tc2<4>);
+    return launch(tapgemm_f_tc2<5>);
   }
   const int total = m_tiles_all * p.n_tiles * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();

@@ -969,3 +969,27 @@ def test_tma_staged_glue_kernels_match_register_staged(C_, L, roll, halo, B):
     assert rel_err(t[3].float(), r[3].float()) <= 2e-3          # pass 2 consumes each run's own (re-ordered) sums
     assert rel_err(t[4], r[4]) <= 1e-5
     assert torch.equal(t[5], r[5])
+
+
+@pytest.mark.parametrize("cin,L,roll", [(2, 2048, 3), (1, 16384, 0), (2, 1280, -5)])
+def test_wave_im2col_matches_unfold(cin, L, roll):
+    """sg_wave_im2col (shared-memory staged tiles): col[b][t][ci * 32 + k] = pad(shift(v_ci))[4 t + k - 14], reflect
+    padding (14, 15) of the stride-4 k = 31 conv (modules.py:91-98), columns 31 / 63 and absent channels zero."""
+    g = _gen(41)
+    B = 3
+    x = [torch.randn(B, L, generator=g) for _ in range(cin)]
+    col = torch.full((B, L // 4, 64), 7.0, dtype=torch.float16, device=DEV)
+    xd = [t.to(DEV) for t in x]
+    _lib.call("sg_wave_im2col", _p(xd[0]), _p(xd[1]) if cin == 2 else None, cin, B, L, roll, None, 1, 14, _p(col), None,
+              _stream())
+    rdev = torch.tensor([roll], dtype=torch.int32, device=DEV)
+    col_d = torch.zeros_like(col)
+    _lib.call("sg_wave_im2col", _p(xd[0]), _p(xd[1]) if cin == 2 else None, cin, B, L, 0, _p(rdev), 1, 14, _p(col_d), None,
+              _stream())
+    torch.cuda.synchronize()
+    ref = torch.zeros(B, L // 4, 64)
+    for ci in range(cin):
+        xp = F.pad(O.phase_roll(x[ci].unsqueeze(1), roll), (14, 15), mode="reflect").squeeze(1)
+        ref[:, :, ci * 32:ci * 32 + 31] = xp.unfold(1, 31, 4)
+    assert torch.equal(col.float().cpu(), ref.to(torch.float16).float())
+    assert torch.equal(col_d, col)
