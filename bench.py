@@ -399,7 +399,9 @@ def main():
         # lines (communicator / rank evidence the driver greps for) cannot pollute the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from segan_pytorch_b200 import _lib, engine as E
+    from segan_pytorch_b200.hostbind import bind_host_to_gpu
     from tests.util import build_segan, load_opts
+    numa_cpus = bind_host_to_gpu(dev)          # before any pinned staging buffer is allocated
     if not _lib.device_ok():
         raise SystemExit("bench.py needs an sm_100-class GPU and libsegan_b200.so (no fallback path)")
     B = args.batch
@@ -495,13 +497,17 @@ def main():
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    host_loss = None
-    for _, cbuf, nbuf, _ in pre:
+    # the four losses of EVERY step are read back into pinned host memory by an asynchronous copy ordered after the
+    # step (SEGAN.train reads them every log_freq steps, model.py:336-348); the host is synchronised once, at the end
+    host_losses = torch.zeros(args.steps, 4).pin_memory()
+    for i, (_, cbuf, nbuf, _) in enumerate(pre):
         ls = s.train_step(cbuf, nbuf, Gopt, Dopt, 100.0, losses=losses)
-        host_loss = ls.tolist()                                            # D2H read of the step's losses
+        host_losses[i].copy_(ls, non_blocking=True)                        # D2H read of the step's losses
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    host_loss = host_losses[-1].tolist()
+    assert all(abs(v) > 0 for v in host_losses[:, 3].tolist()), "a step's losses never reached the host"
     h2d_per_step = pre.h2d_bytes // args.steps
     cbuf = torch.empty(B, 1, 16384, device=dev)
     nbuf = torch.empty(B, 1, 16384, device=dev)
@@ -612,7 +618,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": 16, "last_losses": host_loss,
                 "path": "DevicePrefetcher (pinned int16 PCM host batch -> copy stream one step ahead -> sg_pcm16_to_wave "
-                        "on the device) + train_step + losses.tolist()"},
+                        "on the device) + train_step + async D2H copy of the step's four losses into pinned memory "
+                        "(host synchronised once, after the last step)",
+                "host_cpus_bound_to_gpu_numa": sorted(numa_cpus)[:4] + ["..."] if numa_cpus else None},
         "g_only_inference": {"value": B * n_inf / (ms_inf * 1e-3), "unit": "windows/s per GPU",
                              "what": "SEGAN.generate_stream: G forward (clean.py path), fp16 operands, %d batches of %d "
                                      "windows from pinned host memory back to pinned host memory; H2D of batch n+1, G "

@@ -17,6 +17,7 @@ from scipy.io import wavfile
 
 from segan_pytorch_b200.segan.models import SEGAN, WSEGAN
 from segan_pytorch_b200.segan.datasets import normalize_wave_minmax, pre_emphasize
+from segan_pytorch_b200.hostbind import bind_host_to_gpu
 
 
 class ArgParser(object):
@@ -32,6 +33,7 @@ def main(opts):
     args.cuda = True
     segan = WSEGAN(args) if getattr(args, "wsegan", False) else SEGAN(args)
     segan.G.load_pretrained(opts.g_pretrained_ckpt, True)
+    bind_host_to_gpu(torch.device('cuda', torch.cuda.current_device()))
     segan.cuda()
     segan.G.eval()
     twavs = glob.glob(os.path.join(opts.test_files[0], "*.wav")) if len(opts.test_files) == 1 else opts.test_files

@@ -199,3 +199,14 @@ def test_fused_optimizer_state_dict_is_torch_compatible(kind):
                           ref.state_dict()["state"][i][key])
     off, n, shape = eng.index["dec_blocks.2.act.weight"]
     assert torch.allclose(opt2.s1[off:off + n].view(shape), ref.state_dict()["state"][j][key])
+
+
+def test_hostbind_cpulist_and_noop_without_gpu():
+    from segan_pytorch_b200 import hostbind
+    assert hostbind.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostbind.parse_cpulist("") == set()
+    import os
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    if not torch.cuda.is_available():
+        assert hostbind.bind_host_to_gpu(0) is None              # no sysfs entry for a GPU: nothing is changed
+        assert before is None or os.sched_getaffinity(0) == before

@@ -18,6 +18,7 @@ from torch.utils.data import DataLoader
 
 from segan_pytorch_b200.segan.models import SEGAN, WSEGAN
 from segan_pytorch_b200.segan.datasets import SEDataset, SyntheticSEDataset, collate_fn
+from segan_pytorch_b200.hostbind import bind_host_to_gpu
 
 # (name, type, default) -- the reference's flag surface (train.py:102-245)
 FLAGS = [
@@ -64,6 +65,7 @@ def main(opts):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     opts.cuda = True
+    bind_host_to_gpu(device)               # pinned staging buffers (and the loader workers) on the GPU's NUMA node
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
