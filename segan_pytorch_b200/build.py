@@ -45,8 +45,10 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libsegan_b200.so")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    tmp = LIB + ".tmp.%d" % os.getpid()          # link aside, then rename: a reader never sees a half-written library
+    cmd = [_nvcc(), "-shared", "-o", tmp] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
     return LIB
 
 

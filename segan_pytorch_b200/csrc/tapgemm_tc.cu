@@ -722,24 +722,35 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
         // k-steps [kb, ke) of the tile's (tap, k-block) sequence.  A split-K piece JUMPS to its first step: walking
         // there one (tap, k-block) at a time cost ~0.12 us per skipped step (two dependent constant-bank loads per
         // iteration), i.e. the 7th piece of a 248-step tile started 25 us late (profiles/r2_tc2_timeline.txt).
-        int step = 0, sel = 0;              // step: every (tap, k-block) of the tile; sel: those of this k-split
-        int skip = (!KSF || p.ksplit == 1) ? pc.kb : 0;
+        // An interleaved k-split tile (ksplit > 1: the fc.0 GEMM, K = 16384) takes every ksplit-th (tap, k-block)
+        // starting at block ks: it strides there as well -- the per-block `step % ksplit` test was a division per
+        // skipped block (256 blocks walked for 16 loaded).
+        const bool interleaved = KSF && p.ksplit > 1;
+        int step = 0, sel = 0;              // step: first (tap, k-block) index of the current tap; sel: steps passed
+        int skip = interleaved ? 0 : pc.kb;
+        int next_sel = ks;                  // interleaved: global index of the next block this tile takes
+        const int kstride = interleaved ? 64 * p.ksplit : 64;
         for (int d = p.d_lo; d <= p.d_hi; ++d) {
           const int ti = d + 4;
           if (n0 + p.TN <= p.tr.n_lo[ti] || n0 >= p.tr.n_hi[ti]) continue;
           const int klo = p.tr.k_lo[ti], khi = p.tr.k_hi[ti];
+          const int nk = (khi - klo) >> 6;
           int k0 = klo;
-          if (!KSF || p.ksplit == 1) {
-            const int nk = (khi - klo) >> 6;
+          if (!interleaved) {
             if (skip >= nk) { skip -= nk; sel += nk; continue; }
             k0 += skip << 6; sel += skip; skip = 0;
             if (sel >= pc.ke) break;
+          } else {
+            if (next_sel >= step + nk) { step += nk; continue; }
+            k0 += (next_sel - step) << 6;
           }
-          for (; k0 < khi; k0 += 64, ++step) {
-            if (KSF && p.ksplit > 1 && step % p.ksplit != ks) continue;
-            const int mine = sel++;
-            if (mine < pc.kb) continue;
-            if (mine >= pc.ke) break;
+          for (; k0 < khi; k0 += kstride) {
+            if (!interleaved) {
+              const int mine = sel++;
+              if (mine >= pc.ke) break;
+            } else {
+              next_sel += p.ksplit;
+            }
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * STAGE2_BYTES;
             if (leader && lane == 0) mbar_expect_tx(&ctl->full[stage], 2u * (a_bytes + b_bytes));
@@ -752,6 +763,7 @@ tapgemm_f_tc2(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ 
             tma_load_3d_pair(lane == 0 ? sa : sa + A_STAGE_BYTES, map, &ctl->full[stage], c0, c1, c2);
             if (++stage == STAGES2) { stage = 0; phase ^= 1; }
           }
+          step += nk;
         }
       }
     }

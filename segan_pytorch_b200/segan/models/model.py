@@ -779,6 +779,14 @@ class SEGAN(Model):
                 de.mark_dirty()
                 Dopt.t, Gopt.t = t_d, t_g
                 _lib.launch_count = n0
+        if graphs is None and _dist() is None:
+            # single GPU: nothing separates the three segments -- one graph, one launch per step
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                Genh, gctx = self._seg_d(st.clean, st.noisy, st.z, shifts3, st.shifts, st.losses, Dopt, sample_z=sample_z)
+                self._seg_g(st.clean, st.noisy, Genh, gctx, shifts3, st.shifts, st.losses, l1_weight, Gopt, Dopt, dscale)
+                Gopt.step(dscale)
+            graphs = (g1,)
         if graphs is None:
             g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
