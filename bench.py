@@ -367,6 +367,20 @@ def _claim_stdout():
     return emit
 
 
+def _leave(world):
+    """End of a data-parallel run: the step's CUDA graph holds captured NCCL kernels, and tearing the process group
+    down under it was seen to block (2 x B200: the JSON line was out, destroy_process_group() never returned).  Every
+    rank has passed its last collective when it gets here, all device work is drained, so the process simply ends."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()                       # rank 0 is last (it prints): nobody leaves while a peer still computes
+        torch.cuda.synchronize()
+        time.sleep(0.2)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     emit = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -548,8 +562,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # max over ranks
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world)
         return
     total_windows = B * world * args.steps
     value = total_windows / (ms * 1e-3)
@@ -632,8 +645,7 @@ def main():
         "extra_configs": extras,
     }
     emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _leave(world)
 
 
 if __name__ == "__main__":
