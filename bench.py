@@ -43,13 +43,16 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1_v4_ncu_tapgemm_f.json: dram__bytes_read.sum + dram__bytes_write.sum, average of the captured
-    launches), or None when the summary is missing."""
-    p = os.path.join(ROOT, "profiles", "r1_v4_ncu_tapgemm_f.json")
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum, average over the
+    launches of one train step) from the committed step-level ncu capture of this round
+    (profiles/r2_step_traffic.json <- tools/step_traffic.py + tools/ncu_step_summary.py), or None when it is missing."""
+    p = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
     try:
         with open(p) as f:
-            return float(json.load(f)["dram_bytes_per_launch_avg"])
+            ks = json.load(f)["kernels"]
+        hits = [v for k, v in ks.items() if k.startswith("tapgemm_f_tc2")]
+        n = sum(v["launches"] for v in hits)
+        return sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in hits) / n if n else None
     except Exception:
         return None
 

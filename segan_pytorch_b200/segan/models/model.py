@@ -937,7 +937,8 @@ class WSEGAN(SEGAN):
         (sigmoid(logit) - target) * weight / B is handed to the same backward)."""
         de = self.D.engine
         lptr = C.c_void_p(losses.data_ptr() + 4 * slot)
-        logit, c = de.forward(x0, x1, shifts, training=True, twins=twins)
+        shifts, shifts_dev = shifts if isinstance(shifts, tuple) else (shifts, None)
+        logit, c = de.forward(x0, x1, shifts, training=True, twins=twins, shifts_dev=shifts_dev)
         red = dict(reducer=reducer, reduce_now=reduce_now) if param_grads else {}
         if not self.vanilla_gan:
             de.backward(c, target, weight, param_grads=param_grads, input_grad=input_grad, loss_out=lptr, **red)
@@ -968,45 +969,114 @@ class WSEGAN(SEGAN):
         Returns the device tensor [d_loss, g_adv, pow_loss, den_loss].  Draw order of python `random` as in the
         reference: D(real) shifts, [z], D(fake) shifts, [shuffle, D(misaligned) shifts], [per sample: interferer
         frequency, amplitude; D(interfered) shifts], D(fake) shifts.  `perm` / `interf` (the squares, (B,1,L))
-        override the draws (tests)."""
+        override the draws (tests).
+
+        Like SEGAN.train_step, after `engine.GRAPH_WARMUP` eager steps of a shape the step is captured into ONE CUDA
+        graph and replayed (RMSprop, LSGAN, no masked L1 term in the batch): the phase shifts, the misalignment
+        permutation and the interferers are device tensors the host refreshes before each replay."""
+        B, _, L = clean.shape
+        dev = clean.device
+        nl = len(self.D.enc_blocks)
+        # ---- host draws, in the reference's order
+        nsh = iter(shifts) if shifts is not None else None
+        draw = (lambda: next(nsh)) if nsh is not None else (lambda: draw_phase_shifts(nl, self.D.phase_shift))
+        sh = [draw()]                                                      # D(real)
+        sample_z = z is None and self.z_device != 'cpu'
+        if z is None and not sample_z:
+            z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+        sh.append(draw())                                                  # D(fake)
+        if self.misalign_pair:
+            if perm is None:
+                perm = list(range(B))
+                random.shuffle(perm)                                       # model.py:598-600
+            sh.append(draw())
+        if self.interf_pair:
+            if interf is None:
+                interf = self.interferer_squares(B, L)                     # model.py:606-622
+            sh.append(draw())
+        sh.append(draw())                                                  # D(fake) of the G step
+        masked = bool(l1_weight > 0 and uttname is not None and any('additive' in u for u in uttname))
+        st = None if masked else self._wgraph_state(clean, noisy, Gopt, Dopt, sample_z, len(sh))
+        if st is None:
+            losses = torch.zeros(4, dtype=torch.float32, device=dev) if losses is None else losses
+            if sample_z:
+                z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+            perm_d = torch.as_tensor(perm, device=dev) if self.misalign_pair else None
+            interf_d = interf.to(dev) if self.interf_pair else None
+            return self._wstep(clean, noisy, z, sh, None, perm_d, interf_d, losses, Gopt, Dopt, l1_weight, uttname,
+                               False)
+        # ---- CUDA-graph schedule: refresh the static inputs, replay
+        ge, de = self.G.engine, self.D.engine
+        if st.clean.data_ptr() != clean.data_ptr():
+            st.clean.copy_(clean, non_blocking=True)
+        if st.noisy.data_ptr() != noisy.data_ptr():
+            st.noisy.copy_(noisy, non_blocking=True)
+        if z is not None:
+            st.z.copy_(z, non_blocking=True)
+        i = st.ring_i % st.ring.shape[0]
+        st.ring_i += 1
+        if st.ring_ev[i] is not None:
+            st.ring_ev[i].synchronize()
+        row = [int(v) for one in sh for v in one] + ([int(v) for v in perm] if self.misalign_pair else [])
+        st.ring[i].copy_(torch.tensor(row, dtype=torch.int32))
+        st.table.copy_(st.ring[i], non_blocking=True)
+        st.ring_ev[i] = torch.cuda.Event()
+        st.ring_ev[i].record()
+        if self.interf_pair:
+            st.interf.copy_(interf.to(dev, non_blocking=True))
+        if st.graph is None:
+            self._wcapture(st, sh, sample_z, Gopt, Dopt, l1_weight)
+        else:
+            ge.notice_external_writes()
+            de.ensure_packed()
+            st.graph.replay()
+            Dopt.t += 1
+            Gopt.t += 1
+            ge.master_updated()
+            de._mirror_stale = True
+            _lib.launch_count += st.launches
+        if losses is not None and losses.data_ptr() != st.losses.data_ptr():
+            losses.copy_(st.losses, non_blocking=True)
+            return losses
+        return st.losses
+
+    def _wstep(self, clean, noisy, z, sh, table, perm_d, interf_d, losses, Gopt, Dopt, l1_weight, uttname, sample_z):
+        """The step's device work (shared by the eager and the captured schedule).  sh: the host's phase shifts per D
+        pass; table: device int32 copy of the same (then the kernels read the shifts from memory), or None."""
         ge, de = self.G.engine, self.D.engine
         B, _, L = clean.shape
         dev = clean.device
         nl = len(self.D.enc_blocks)
-        losses = torch.zeros(4, dtype=torch.float32, device=dev) if losses is None else losses.zero_()
-        nsh = iter(shifts) if shifts is not None else None
-        draw = (lambda: next(nsh)) if nsh is not None else (lambda: draw_phase_shifts(nl, self.D.phase_shift))
+        losses.zero_()
+        if sample_z:
+            z.normal_()
+        ip = iter(range(len(sh)))
+
+        def nxt():
+            i = next(ip)
+            return sh[i], (None if table is None else table[i * nl:(i + 1) * nl])
         # model.py:595,603,626: 1/2, 1/3 with the misaligned pair, 1/4 whenever the interferer pair is on
         d_weight = 0.25 if self.interf_pair else ((1.0 / 3) if self.misalign_pair else 0.5)
-        # the G forward (model.py:583) does not depend on the D(real) pass before it: side stream 1.
-        # (z comes from torch's generator, the phase shifts from python's `random`: drawing z first
-        # changes neither sequence.)
-        if z is None:
-            z = self._sample_z(B, L // (4 ** len(self.G.enc_blocks)), dev)
+        # the G forward (model.py:583) does not depend on the D(real) pass before it: side stream 1
         gside = _engine.side_stream(dev, 1)
         with _engine.on_side(gside):
             Genh, gctx = ge.forward(noisy, z)
         Dopt.zero_grad()
         rd, rg = self._reducers()
         n_d = 2 + int(bool(self.misalign_pair)) + int(bool(self.interf_pair))      # the last D pass launches the chunks
-        self._d_pass(clean, noisy, draw(), 1.0, d_weight, losses, 0, reducer=rd, reduce_now=False)
+        self._d_pass(clean, noisy, nxt(), 1.0, d_weight, losses, 0, reducer=rd, reduce_now=False)
         _engine.join_side(gside)
-        self._d_pass(Genh, noisy, draw(), 0.0, d_weight, losses, 0, reducer=rd, reduce_now=(n_d == 2))
+        self._d_pass(Genh, noisy, nxt(), 0.0, d_weight, losses, 0, reducer=rd, reduce_now=(n_d == 2))
         if self.misalign_pair:
-            if perm is None:
-                perm = list(range(B))
-                random.shuffle(perm)                                       # model.py:598-600
-            clean_shuf = clean[torch.as_tensor(perm, device=dev)]
-            self._d_pass(clean, clean_shuf, draw(), 0.0, d_weight, losses, 0, reducer=rd,
+            clean_shuf = torch.index_select(clean, 0, perm_d)              # model.py:598-600
+            self._d_pass(clean, clean_shuf, nxt(), 0.0, d_weight, losses, 0, reducer=rd,
                          reduce_now=not self.interf_pair)
         if self.interf_pair:
-            if interf is None:
-                interf = self.interferer_squares(B, L)                     # model.py:606-622
-            self._d_pass(clean + interf.to(dev), noisy, draw(), 0.0, d_weight, losses, 0, reducer=rd, reduce_now=True)
+            self._d_pass(clean + interf_d, noisy, nxt(), 0.0, d_weight, losses, 0, reducer=rd, reduce_now=True)
         Dopt.step(rd.finish() if rd is not None else allreduce_grads(de))
         Gopt.zero_grad()
         gy = ge.buf.get("g.gy", (B, 1, L), torch.float32, dev, zero=True)
-        self._d_pass(Genh, noisy, draw(), 1.0, 1.0, losses, 1, input_grad=gy, param_grads=False, twins=False)
+        self._d_pass(Genh, noisy, nxt(), 1.0, 1.0, losses, 1, input_grad=gy, param_grads=False, twins=False)
         # spectral power loss (model.py:638-653): one tensor-core GEMM over the frames of both signals
         # (engine.SpectralLoss); other n_fft / windows shorter than a frame keep the library transform
         lscale = _engine.LOSS_SCALE
@@ -1041,6 +1111,94 @@ class WSEGAN(SEGAN):
         ge.backward(gctx, gy, reducer=rg)
         Gopt.step(rg.finish() if rg is not None else allreduce_grads(ge))
         return losses
+
+    def _wgraph_state(self, clean, noisy, Gopt, Dopt, sample_z, n_pass):
+        """Static tensors + graph of the WSEGAN step for this key, or None while the eager schedule should run."""
+        if not _engine.GRAPHS or _engine.PROFILE is not None or _lib.call_profile is not None:
+            return None
+        if Gopt.kind != 'rmsprop' or Dopt.kind != 'rmsprop' or not _engine.wave_on_tensor_cores() or self.vanilla_gan:
+            return None                         # Adam passes its step count by value; BCE runs through torch ops
+        if self.n_fft != 2048 or clean.shape[-1] < 2048 or torch.cuda.is_current_stream_capturing():
+            return None
+        if getattr(self, '_wgraph_failed', False):
+            return None
+        ge, de = self.G.engine, self.D.engine
+        world = _dist().get_world_size() if _dist() is not None else 1
+        B, _, L = clean.shape
+        key = ('w', B, L, Gopt.param_groups[0]['lr'], Dopt.param_groups[0]['lr'], world,
+               ge.flat.data_ptr() if ge.flat is not None else 0, de.flat.data_ptr() if de.flat is not None else 0,
+               _engine.OVERLAP, self.z_device, bool(sample_z), ge.backend, de.backend, _engine.GS, _engine.LOSS_SCALE,
+               bool(self.misalign_pair), bool(self.interf_pair), float(self.pow_weight), n_pass)
+        cache = self.__dict__.setdefault('_step_graphs', {})
+        st = cache.get(key)
+        if st is None:
+            if len(cache) >= 4:
+                cache.clear()
+            st = cache[key] = types.SimpleNamespace(seen=0, graph=None, graphs=None)
+        st.seen += 1
+        if st.seen <= _engine.GRAPH_WARMUP:
+            return None
+        if st.graph is None and not hasattr(st, 'clean'):
+            dev = clean.device
+            nl = len(self.D.enc_blocks)
+            ntab = n_pass * nl + (B if self.misalign_pair else 0)
+            st.clean = torch.empty_like(clean)
+            st.noisy = torch.empty_like(noisy)
+            st.z = torch.empty(B, self.G.z_dim, L // (4 ** len(self.G.enc_blocks)), device=dev)
+            st.losses = torch.zeros(4, dtype=torch.float32, device=dev)
+            st.table = torch.zeros(ntab, dtype=torch.int32, device=dev)     # phase shifts of every pass [+ permutation]
+            st.interf = torch.zeros_like(clean) if self.interf_pair else None
+            st.ring = torch.zeros(32, ntab, dtype=torch.int32).pin_memory()
+            st.ring_ev = [None] * 32
+            st.ring_i = 0
+            st.launches = 0
+            st.n_shift = n_pass * nl
+        return st
+
+    def _wcapture(self, st, sh, sample_z, Gopt, Dopt, l1_weight):
+        """Captures one step (not executed) and replays it; on failure the key falls back to eager steps."""
+        ge, de = self.G.engine, self.D.engine
+        torch.cuda.synchronize()
+        ge.mark_dirty()
+        de.mark_dirty()
+        n0 = _lib.launch_count
+        t_d, t_g = Dopt.t, Gopt.t
+        perm_d = st.table[st.n_shift:].to(torch.int64) if self.misalign_pair else None
+        g = torch.cuda.CUDAGraph()
+        mode = dict(capture_error_mode="thread_local") if _dist() is not None and DP_OVERLAP else {}
+        try:
+            with torch.cuda.graph(g, **mode):
+                pd = st.table[st.n_shift:].to(torch.int64) if self.misalign_pair else None    # inside: follows the table
+                self._wstep(st.clean, st.noisy, st.z, sh, st.table, pd, st.interf, st.losses, Gopt, Dopt, l1_weight,
+                            None, sample_z)
+        except Exception as e:
+            print("segan_b200: capturing the WSEGAN step failed (%s): eager steps from here on"
+                  % (str(e).splitlines()[0] if str(e) else type(e).__name__))
+            self._wgraph_failed = True
+            for r in (self._reducers() if _dist() is not None else ()):
+                if r is not None:
+                    r.events.clear()
+            torch.cuda.synchronize()
+            ge.mark_dirty()
+            de.mark_dirty()
+            Dopt.t, Gopt.t = t_d, t_g
+            _lib.launch_count = n0
+            losses = st.losses
+            return self._wstep(st.clean, st.noisy, st.z, sh, None, perm_d, st.interf, losses, Gopt, Dopt, l1_weight,
+                               None, sample_z)
+        Dopt.t, Gopt.t = t_d, t_g
+        st.launches = _lib.launch_count - n0
+        _lib.launch_count = n0
+        st.graph = g
+        st.graphs = (g,)
+        g.replay()
+        Dopt.t += 1
+        Gopt.t += 1
+        ge.master_updated()
+        de._mirror_stale = True
+        _lib.launch_count += st.launches
+        if sample_z and not hasattr(self.G, 'z'):
+            self.G.z = st.z
 
     def train(self, opts, dloader, criterion, l1_init, l1_dec_step, l1_dec_epoch, log_freq, va_dloader=None,
               device='cuda'):

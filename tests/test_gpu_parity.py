@@ -561,3 +561,58 @@ def test_wsegan_step_vs_oracle(variant):
            if not (k.startswith("enc_blocks") and k.endswith("conv.bias"))}
     print("wsegan D grad rel errs (max):", max(rep.values()))
     assert max(rep.values()) <= 0.2, rep
+
+
+@pytest.mark.parametrize("flags", [dict(misalign_pair=True), dict(misalign_pair=True, interf_pair=True)],
+                         ids=["misalign", "misalign+interf"])
+def test_wsegan_graph_replayed_steps_match_eager_steps(flags):
+    """WSEGAN.train_step under CUDA-graph replay (phase shifts, the misalignment permutation and the interferers are
+    device tensors refreshed per step) against the eager schedule: same protocol as the SEGAN test above."""
+    from segan_pytorch_b200 import engine as E
+    from segan_pytorch_b200.segan.models import WSEGAN
+    from tests.util import load_opts, seed_all
+    B, L, n_steps = 4, 16384, 4
+    g = torch.Generator().manual_seed(77)
+    clean = (0.3 * torch.randn(B, 1, L, generator=g)).clamp(-1, 1).to(DEV)
+    noisy = (clean.cpu() + 0.1 * torch.randn(B, 1, L, generator=g)).clamp(-1, 1).to(DEV)
+    zs = [torch.randn(B, 1024, 16, generator=g).to(DEV) for _ in range(n_steps)]
+    n_pass = 3 + len(flags)
+    random.seed(13)
+    shifts = [[O.draw_phase_shifts(5, 5) for _ in range(n_pass)] for _ in range(n_steps)]
+    perms = [torch.randperm(B, generator=g).tolist() for _ in range(n_steps)]
+    interfs = [WSEGAN.interferer_squares(B, L, picks=[(250 * 4 ** (i % 3), [0.01, 0.05, 0.1, 1][(i + k) % 4])
+                                                       for i in range(B)]) for k in range(n_steps)]
+
+    def run(graphs):
+        prev = E.GRAPHS
+        E.GRAPHS = graphs
+        try:
+            opts = load_opts(batch_size=B, wsegan=True, **flags)
+            seed_all(111)
+            s = WSEGAN(opts).to(DEV)
+            s.G.train()
+            s.D.train()
+            Gopt, Dopt = s.build_optimizers(opts)
+            out = []
+            for i in range(n_steps):
+                losses = s.train_step(clean, noisy, Gopt, Dopt, 0.0, z=zs[i], shifts=shifts[i], perm=perms[i],
+                                      interf=interfs[i] if flags.get("interf_pair") else None)
+                torch.cuda.synchronize()
+                out.append((losses.tolist(), s.G.engine.grad.clone(), s.D.engine.grad.clone()))
+            n_graphs = sum(1 for v in getattr(s, "_step_graphs", {}).values() if v.graphs is not None)
+            return out, n_graphs, Gopt.t
+        finally:
+            E.GRAPHS = prev
+
+    (e1, n1, _), (e2, n2, _), (gr, n3, t3) = run(False), run(False), run(True)
+    assert n1 == 0 and n2 == 0 and n3 == 1 and t3 == n_steps
+    for step in range(n_steps):
+        (l0, gG0, gD0), (l1, gG1, gD1), (l2, gG2, gD2) = e1[step], e2[step], gr[step]
+        floor_l = max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(l0, l1))
+        floor_g = max(rel_err(gG1, gG0), rel_err(gD1, gD0))
+        err_l = max(abs(a - b) / max(1.0, abs(a)) for a, b in zip(l0, l2))
+        err_g = max(rel_err(gG2, gG0), rel_err(gD2, gD0))
+        print("step %d: eager-vs-eager loss %.2e grad %.2e | graph-vs-eager loss %.2e grad %.2e"
+              % (step, floor_l, floor_g, err_l, err_g))
+        assert err_l <= 10 * floor_l + 2e-3, (step, l0, l2)
+        assert err_g <= 10 * floor_g + 5e-3, (step, err_g, floor_g)
