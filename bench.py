@@ -377,6 +377,13 @@ def _claim_stdout():
     return emit
 
 
+def _guard(fn, *a):
+    try:
+        return fn(*a)
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")}
+
+
 def _leave(world):
     """End of a data-parallel run: the step's CUDA graph holds captured NCCL kernels, and tearing the process group
     down under it was seen to block (2 x B200: the JSON line was out, destroy_process_group() never returned).  Every
@@ -392,6 +399,7 @@ def _leave(world):
 
 
 def main():
+    t_start = time.time()
     emit = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -448,10 +456,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    trace = os.environ.get("SEGAN_B200_BENCH_TRACE", "0") not in ("0", "")
+
+    def mark(msg):
+        if trace:
+            sys.stderr.write("[bench rank %d +%.1fs] %s\n" % (rank, time.time() - t_start, msg))
+            sys.stderr.flush()
+
     # ---- warm-up
-    for _ in range(args.warmup):
+    mark("models built, process group up")
+    for i in range(args.warmup):
         s.train_step(clean, noisy, Gopt, Dopt, 100.0, losses=losses)
+        if trace:
+            torch.cuda.synchronize()
+            mark("warm-up step %d done" % i)
     barrier()
+    mark("warm-up barrier passed")
     # ---- timed region 1: device-resident inputs (the headline `value`)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -465,6 +485,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    mark("timed region done: %.3f ms/step" % (ms / args.steps))
     launches = _lib.launch_count - launches0
     ngraphs = [len(v.graphs) for v in getattr(s, "_step_graphs", {}).values() if getattr(v, "graphs", None) is not None]
     clocks = sampler.stop() if rank == 0 else None
@@ -487,6 +508,7 @@ def main():
     s1.record()
     barrier()
     ms_serial = s0.elapsed_time(s1)
+    mark("serial region done")
     E.PROFILE = []
     _lib.call_profile = []
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -497,6 +519,7 @@ def main():
     p1.record()
     barrier()
     ms_prof = p0.elapsed_time(p1)
+    mark("profiled region done")
     prof = E.PROFILE
     E.PROFILE = None
     calls = _lib.call_profile
@@ -530,6 +553,7 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    mark("e2e region done")
     host_loss = host_losses[-1].tolist()
     assert all(abs(v) > 0 for v in host_losses[:, 3].tolist()), "a step's losses never reached the host"
     h2d_per_step = pre.h2d_bytes // args.steps
@@ -563,10 +587,16 @@ def main():
         h1.record()
         barrier()
     ms_inf_dev = h0.elapsed_time(h1)
+    mark("inference regions done")
     s.G.train()
     extras = None
     if world == 1 and not args.no_extras:
-        extras = gpu_extras(dev, B, s)
+        try:
+            extras = gpu_extras(dev, B, s)
+        except Exception as e:                       # secondary figures must never cost the headline line
+            extras = {"error": "%s: %s" % (type(e).__name__, str(e).splitlines()[0] if str(e) else "")}
+            torch.cuda.synchronize()
+            s.G.train()
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                           # max over ranks
@@ -628,7 +658,7 @@ def main():
         cpu = {"value": wps, "unit": "windows/s", "cores": cores, "kind": "port",
                "sample": "%d timed steps of a %d-window batch of the same workload (oracle, oneDNN off)"
                          % (args.cpu_baseline_steps, args.ref_batch),
-               "baseline_md_section4": cpu_baseline_section4(cores)}
+               "baseline_md_section4": _guard(cpu_baseline_section4, cores)}
     line = {
         "metric": "16384-sample windows/sec (G+D train step)", "value": value, "unit": "windows/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
