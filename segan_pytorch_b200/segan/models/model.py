@@ -195,8 +195,12 @@ def allreduce_grads(eng):
 # gradient-completion order -- on a communication stream as the backward pass produces them, so only the last,
 # small chunk is exposed; with CUDA graphs the collectives are captured into the step's single graph.
 DP_OVERLAP = os.environ.get("SEGAN_B200_DP_OVERLAP", "1").lower() not in ("0", "off", "no", "false")
-# SEGAN_B200_DP_CAPTURE=0: keep the collectives out of the CUDA graph (three graphs, eager all-reduces between them)
-DP_CAPTURE = os.environ.get("SEGAN_B200_DP_CAPTURE", "1").lower() not in ("0", "off", "no", "false")
+# SEGAN_B200_DP_CAPTURE=1 captures the chunked collectives INSIDE the step's single CUDA graph.  Opt-in: on 2 x B200 it
+# works and is the fastest schedule (14.88 vs 15.17 ms/step, profiles/r2_bench_2gpu_*.json), but on 4 x B200 the
+# replays following the first one hang (NCCL 2.28.9, eager collectives -- barriers -- mixed with the captured ones:
+# profiles/r2_dp_4gpu_trace.txt).  Default: three graphs with one eager all-reduce per bucket between them (the
+# schedule every N was measured with: 4 x B200 14.63 ms/step).
+DP_CAPTURE = os.environ.get("SEGAN_B200_DP_CAPTURE", "0").lower() not in ("0", "off", "no", "false")
 
 
 class GradReducer(object):
@@ -1122,6 +1126,8 @@ class WSEGAN(SEGAN):
             return None
         if getattr(self, '_wgraph_failed', False):
             return None
+        if _dist() is not None and not DP_CAPTURE:
+            return None                         # data parallel: the collectives stay eager (see DP_CAPTURE)
         ge, de = self.G.engine, self.D.engine
         world = _dist().get_world_size() if _dist() is not None else 1
         B, _, L = clean.shape

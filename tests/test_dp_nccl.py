@@ -82,6 +82,7 @@ def _worker(rank, world, port, q):
         mark('G gradient part done')
         del s
         # ---- (2) full train steps, data parallel: eager (2), then graph-replayed (3)
+        M.DP_CAPTURE = True                               # opt-in schedule, verified on 2 GPUs (see model.DP_CAPTURE)
         random.seed(3 + rank)
         torch.manual_seed(3 + rank)
         s = build_segan(batch_size=Bl).to(dev)            # same seed on every rank -> identical init
@@ -109,6 +110,23 @@ def _worker(rank, world, port, q):
         allsame = gsum.clone()
         dist.broadcast(allsame, src=0)
         out["reduced_grads_identical"] = bool(torch.equal(gsum, allsame))
+        # ---- (4) the DEFAULT schedule: three graphs, one eager all-reduce per bucket between them
+        del s, Gopt, Dopt
+        M.DP_CAPTURE = False
+        s = build_segan(batch_size=Bl).to(dev)
+        s.G.train()
+        s.D.train()
+        Gopt, Dopt = s.build_optimizers(load_opts(batch_size=Bl))
+        for i in range(5):
+            s.train_step(c, n, Gopt, Dopt, 100.0)
+            mark('default-schedule step %d done' % i)
+        torch.cuda.synchronize()
+        out["graphs_default"] = [len(v.graphs) for v in getattr(s, "_step_graphs", {}).values() if v.graphs is not None]
+        for name, eng in (("G", s.G.engine), ("D", s.D.engine)):
+            mine = eng.flat.clone()
+            ref = mine.clone()
+            dist.broadcast(ref, src=0)
+            out["same_params_default_" + name] = bool(torch.equal(mine, ref))
         q.put((rank, out, None))
     except Exception as e:                                  # noqa
         import traceback
@@ -143,4 +161,6 @@ def test_data_parallel_two_gpus():
     for r in (0, 1):
         assert outs[r]["finite"] and outs[r]["same_params_G"] and outs[r]["same_params_D"], outs[r]
         assert outs[r]["reduced_grads_identical"], outs[r]
-        assert outs[r]["graphs"] == [1], outs[r]       # the step was captured as ONE graph incl. the collectives
+        assert outs[r]["graphs"] == [1], outs[r]       # opt-in: the step captured as ONE graph incl. the collectives
+        assert outs[r]["graphs_default"] == [3], outs[r]
+        assert outs[r]["same_params_default_G"] and outs[r]["same_params_default_D"], outs[r]
