@@ -616,3 +616,52 @@ def test_wsegan_graph_replayed_steps_match_eager_steps(flags):
               % (step, floor_l, floor_g, err_l, err_g))
         assert err_l <= 10 * floor_l + 2e-3, (step, l0, l2)
         assert err_g <= 10 * floor_g + 5e-3, (step, err_g, floor_g)
+
+
+def test_wsegan_train_loop_on_wav_directories(tmp_path):
+    """train.py --wsegan --misalign_pair on wav directories (this path used to crash on the first batch):
+    SEDataset(pcm16=True) -> persistent DevicePrefetcher iterator -> WSEGAN.train for two epochs -- eager warm-up steps,
+    then the captured step (no 'additive' utterance in the batch names) -- finite losses that match the same steps
+    driven by hand through train_step, and end-of-epoch checkpoints on disk."""
+    import glob
+    from torch.utils.data import DataLoader
+    from segan_pytorch_b200.segan.datasets import DevicePrefetcher, SEDataset, collate_fn
+    from segan_pytorch_b200.segan.models import WSEGAN
+    from tests.test_dataset import _make_wavs
+    from tests.util import load_opts, seed_all
+    cdir, ndir = _make_wavs(str(tmp_path), seed=9)
+
+    def loader():
+        return DataLoader(SEDataset(cdir, ndir, 0.95, pcm16=True), batch_size=3, shuffle=False, num_workers=0,
+                          collate_fn=collate_fn, drop_last=True, pin_memory=True)
+
+    def make(save):
+        opts = load_opts(batch_size=3, wsegan=True, misalign_pair=True, save_path=str(save), epoch=2, z_device="cuda")
+        seed_all(111)
+        s = WSEGAN(opts).to(DEV)
+        return s, opts
+    # (a) the entry-point loop
+    s, opts = make(tmp_path / "ckpt")
+    random.seed(21)
+    torch.manual_seed(21)
+    dl = loader()
+    timings = s.train(opts, dl, torch.nn.MSELoss(), 100.0, 1e-5, 100, 1, device=DEV)
+    torch.cuda.synchronize()
+    la = s.last_losses.tolist()
+    assert len(timings) == 2 * len(dl) and all(np.isfinite(la)), la
+    assert glob.glob(str(tmp_path / "ckpt" / "*EOE_G-*")) and glob.glob(str(tmp_path / "ckpt" / "*EOE_D-*"))
+    assert any(getattr(v, "graph", None) is not None for v in s._step_graphs.values()), "the step was never captured"
+    # (b) the same batches, the same draws, stepped by hand
+    s2, opts2 = make(tmp_path / "ckpt2")
+    s2.G.train()
+    s2.D.train()
+    Gopt, Dopt = s2.build_optimizers(opts2)
+    random.seed(21)
+    torch.manual_seed(21)
+    lb = None
+    for _ in range(2):
+        for names, c, n, _ in DevicePrefetcher(loader(), DEV, preemph=0.95):
+            lb = s2.train_step(c.clone(), n.clone(), Gopt, Dopt, 100.0, uttname=names).tolist()
+    print("WSEGAN.train last losses", la, "manual", lb)
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 0.15 * max(1.0, abs(b)), (la, lb)      # fp32-atomics order, amplified over six RMSprop steps
