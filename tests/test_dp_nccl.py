@@ -3,8 +3,10 @@ skipped on a single-GPU box).  SURVEY.md section 4: "DP(N ranks x B/N) == single
   * the Generator has no batch statistics, so its gradients of a batch-mean loss over a global batch are EXACTLY the
     sum of the per-shard gradients: 2 ranks x 2 windows, chunked + overlapped all-reduce (model.GradReducer), against
     one process computing all 4 windows;
-  * full G+D train steps on 2 ranks (eager warm-up, then the CUDA-graph schedule with the collectives captured inside):
-    every rank must hold bit-identical parameters afterwards, and the chunked reduction must equal one whole-bucket
+  * full G+D train steps on 2 ranks in BOTH schedules -- the default one (three CUDA graphs, one eager all-reduce per
+    gradient bucket between them) and the opt-in one (model.DP_CAPTURE: eager warm-up, then ONE graph with the chunked
+    collectives captured inside): every rank must hold bit-identical parameters afterwards, and the chunked reduction
+    must equal one whole-bucket
     all-reduce."""
 import os
 import random
@@ -81,7 +83,28 @@ def _worker(rank, world, port, q):
                                    and chunks[-1][0] + chunks[-1][1] == s.G.engine.grad.numel())
         mark('G gradient part done')
         del s
-        # ---- (2) full train steps, data parallel: eager (2), then graph-replayed (3)
+        # ---- (2) the DEFAULT schedule: three graphs, one eager all-reduce per bucket between them
+        M.DP_CAPTURE = False
+        random.seed(5 + rank)
+        torch.manual_seed(5 + rank)
+        s = build_segan(batch_size=Bl).to(dev)
+        s.G.train()
+        s.D.train()
+        Gopt, Dopt = s.build_optimizers(load_opts(batch_size=Bl))
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        c, n = clean[sl].to(dev), noisy[sl].to(dev)
+        for i in range(5):
+            s.train_step(c, n, Gopt, Dopt, 100.0)
+            mark('default-schedule step %d done' % i)
+        torch.cuda.synchronize()
+        out["graphs_default"] = [len(v.graphs) for v in getattr(s, "_step_graphs", {}).values() if v.graphs is not None]
+        for name, eng in (("G", s.G.engine), ("D", s.D.engine)):
+            mine = eng.flat.clone()
+            ref = mine.clone()
+            dist.broadcast(ref, src=0)
+            out["same_params_default_" + name] = bool(torch.equal(mine, ref))
+        del s, Gopt, Dopt
+        # ---- (3) the opt-in schedule: chunked collectives captured inside ONE graph (eager warm-up, then replays)
         M.DP_CAPTURE = True                               # opt-in schedule, verified on 2 GPUs (see model.DP_CAPTURE)
         random.seed(3 + rank)
         torch.manual_seed(3 + rank)
@@ -104,29 +127,12 @@ def _worker(rank, world, port, q):
             ref = mine.clone()
             dist.broadcast(ref, src=0)
             out["same_params_" + name] = bool(torch.equal(mine, ref))
-        # ---- (3) chunked reduction == one whole-bucket all-reduce (same gradients, D bucket)
+        # ---- (4) chunked reduction == one whole-bucket all-reduce (same gradients, D bucket)
         de = s.D.engine
         gsum = de.grad.clone()                              # KEEP_GRADS: the reduced gradients of the last step
         allsame = gsum.clone()
         dist.broadcast(allsame, src=0)
         out["reduced_grads_identical"] = bool(torch.equal(gsum, allsame))
-        # ---- (4) the DEFAULT schedule: three graphs, one eager all-reduce per bucket between them
-        del s, Gopt, Dopt
-        M.DP_CAPTURE = False
-        s = build_segan(batch_size=Bl).to(dev)
-        s.G.train()
-        s.D.train()
-        Gopt, Dopt = s.build_optimizers(load_opts(batch_size=Bl))
-        for i in range(5):
-            s.train_step(c, n, Gopt, Dopt, 100.0)
-            mark('default-schedule step %d done' % i)
-        torch.cuda.synchronize()
-        out["graphs_default"] = [len(v.graphs) for v in getattr(s, "_step_graphs", {}).values() if v.graphs is not None]
-        for name, eng in (("G", s.G.engine), ("D", s.D.engine)):
-            mine = eng.flat.clone()
-            ref = mine.clone()
-            dist.broadcast(ref, src=0)
-            out["same_params_default_" + name] = bool(torch.equal(mine, ref))
         q.put((rank, out, None))
     except Exception as e:                                  # noqa
         import traceback
