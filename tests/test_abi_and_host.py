@@ -2,6 +2,7 @@
 ctypes structs mirror the C structs, and the host-side logic of the drop-in (state-dict keys,
 checkpoint format, RNG order, tap tables, flat buckets) behaves like the reference."""
 import ctypes
+import json
 import os
 import random
 import re
@@ -210,3 +211,21 @@ def test_hostbind_cpulist_and_noop_without_gpu():
     if not torch.cuda.is_available():
         assert hostbind.bind_host_to_gpu(0) is None              # no sysfs entry for a GPU: nothing is changed
         assert before is None or os.sched_getaffinity(0) == before
+
+
+def test_step_traffic_summary_tool_and_bench_traffic(tmp_path):
+    """tools/ncu_step_summary.py on a committed ncu CSV (per-kernel aggregation), and bench.ncu_traffic() on the
+    committed step-level capture of this round (DRAM bytes per launch of the dominant kernel)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "s")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_step_summary.py"),
+                        os.path.join(root, "profiles", "r1_v5_launches.csv"), out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    js = json.load(open(out + ".json"))
+    assert js["total_launches"] > 100 and "tapgemm_f_tc2" in js["kernels"] and js["kernels"]["tapgemm_f_tc2"]["ms"] > 0
+    sys.path.insert(0, root)
+    import bench
+    t = bench.ncu_traffic()
+    assert t is not None and 1e7 < t < 1e9, t          # ~130 MB per tap-GEMM launch
