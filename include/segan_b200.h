@@ -74,8 +74,12 @@ int sg_set_cta_pair(int on);
  *   SG_EW_BWD_APPLY (sg_act_bwd_apply).
  * vec: channels per thread (4 | 8); unroll: rows in flight per thread and input stream (2 | 4 | 8 with
  * vec*unroll <= 32); cap: CTAs per SM (persistent grid beyond that).  For the two backward kinds vec == 8
- * selects the tiled kernel (unroll 2 | 4), vec == 4 the generic one.  Every variant computes the same values
- * (up to fp32 summation order).  Also read once from the environment: SEGAN_B200_EW="kind,vec,unroll,cap[;...]".
+ * selects the tiled kernel (unroll 2 | 4), vec == 4 the generic one.
+ * vec == 16 (the default for act_fwd and both backward kinds) selects the TMA-staged kernels (stream_ew.cu:
+ * cp.async.bulk row tiles through an mbarrier ring, 8 channels per consumer thread) wherever the call qualifies --
+ * contiguous 16-bit tensors (leading dimension == C), no bf16 twin outputs, L >= 2 * halo + 3 -- and otherwise falls
+ * back to the register-staged kernel with (8, unroll, cap).  Every variant computes the same values (up to fp32
+ * summation order).  Also read once from the environment: SEGAN_B200_EW="kind,vec,unroll,cap[;...]".
  * Returns SG_OK or SG_ERR_INVALID. */
 #define SG_EW_ACT_FWD 1
 #define SG_EW_BN_STATS 2
