@@ -82,14 +82,17 @@ def test_discriminator_forward(backend):
         idx = torch.from_numpy(d["act_idx.%d" % l]).to(DEV)
         rep["act%d" % l] = max_abs(acts["h_%d" % l].reshape(-1)[idx].cpu(), d["act_val.%d" % l])
     print("D fwd backend %d:" % backend, {k: "%.2e" % v for k, v in rep.items()})
-    assert rep["logit"] <= 2e-2
+    # measured (fp16 operands, fp32 accumulation; deterministic): logit 1.2-1.4e-3, running mean <= 1.0e-4, running
+    # var <= 3.4e-4, activations <= 3.9e-3 -- the survey's 1e-3 logit gate is the fp16 operand format's own distance
+    # here (tests/test_gpu_parity_scale.py holds the batch-300 case to the gate or the control); ~2x margins:
+    assert rep["logit"] <= 3e-3
     for l in range(5):
-        assert rep["rm%d" % l] <= 5e-4 and rep["rv%d" % l] <= 1e-3 and rep["act%d" % l] <= 3e-2, (l, rep)
+        assert rep["rm%d" % l] <= 3e-4 and rep["rv%d" % l] <= 6e-4 and rep["act%d" % l] <= 8e-3, (l, rep)
     s.D.eval()
     random.seed(8)
     with torch.no_grad():
         ye, _ = s.D(x)
-    assert max_abs(ye.cpu(), d["y_eval"]) <= 2e-2
+    assert max_abs(ye.cpu(), d["y_eval"]) <= 1e-2
 
 
 def _check_sampled(t, tag, name, got, tol_rel):
