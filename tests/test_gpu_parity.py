@@ -16,13 +16,16 @@ from segan_pytorch_b200._lib import BACKEND_FFMA, BACKEND_TCGEN05           # no
 from tests.util import build_segan, cpu_state, golden, max_abs, rel_err, sd_sha  # noqa: E402
 
 WAVE_TOL = 1e-3
-# Gradient tolerances (relative L2 over the 256 sampled entries per tensor; measured values in
-# DESIGN.md "parity").  D-step gradients: fp16 operands, bf16 gradient tensors and BatchNorm's
-# mean-subtracting backward leave ~0.11.  G-step gradients are taken through the discriminator
-# AFTER its RMSprop step; the first RMSprop step is lr*sign(g) for every one of D's 25.8 M weights
-# (it moves D(fake) from +0.26 to -16.2 in the reference itself), so a few % of sign flips among
-# near-zero gradient entries perturb the updated D visibly: 0.25-0.38 measured.  With an identical
-# D the same G gradients agree with the oracle to <= 0.06 (test_autograd_path_matches_fused_step).
+# Gradient tolerances of the small golden step below (relative L2 over the 256 sampled entries per tensor, B = 4).
+# They are upper bounds for THIS sample only; the gates that carry the parity claim are in
+# tests/test_gpu_parity_scale.py, where every gradient set is held to 1.5 x the distance of the fp16-operand control
+# (the oracle with fp16-rounded contractions) + 5e-3: with PReLU initialised at slope 0 the activation derivative is
+# discontinuous, fp16 operands flip ~0.1-0.4 % of the masks per layer, and the D step's real / fake terms cancel
+# (5-7 % at B = 16, control and kernels alike; 0.2-0.5 % with continuous activations).  G-step gradients are taken
+# through the discriminator AFTER its RMSprop step; the first RMSprop step is lr*sign(g) for every one of D's 25.8 M
+# weights (it moves D(fake) from +0.26 to -16.2 in the reference itself), so sign flips among near-zero gradient
+# entries perturb the updated D visibly.  With an identical D the same G gradients are control-gated
+# (test_generator_gradients_with_identical_discriminator).
 GRAD_TOL_D = 0.2
 GRAD_TOL_G_THROUGH_UPDATED_D = 0.5
 DEV = "cuda"
